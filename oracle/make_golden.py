@@ -1,0 +1,103 @@
+"""TEST INFRASTRUCTURE — mints tests/golden/*.pt by running the UNMODIFIED reference classes
+(/root/reference/scripts/train.py via oracle/ref_loader.py) in the authoring container.
+
+    python -m oracle.make_golden            # writes every fixture listed in FIXTURES
+
+Weights are not stored: both sides materialise them with tcavp_b200.deterministic_fill_(state_dict, seed)
+(a crc32(key)-seeded CPU generator), and each fixture records a few per-key checksums so drift of the filler
+is detected.  Inputs ARE stored (they are small).  The reference ships no golden vectors of its own
+(SURVEY.md §4), so these files are the pin.
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import tcavp_b200 as T  # noqa: E402
+from oracle import ref_loader  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+# name -> (model preset, overrides, B, l_text, weight seed, scene seed, explicit poly_len or None, script)
+FIXTURES = {
+    "tiny_b6": ("tiny", {}, 6, 24, 11, 101, [0, 64, 1, 33, 14, 22], "scripts/train.py"),
+    "cfg1_b8": ("cfg1", {}, 8, 128, 7, 3, None, "scripts/train.py"),
+    "cfg5_b4": ("cfg5", {}, 4, 128, 5, 9, None, "scripts/train.py"),
+}
+
+
+def weight_checksums(sd, n=12):
+    keys = sorted(k for k in sd if sd[k].is_floating_point())
+    pick = keys[:: max(1, len(keys) // n)][:n]
+    return {k: float(sd[k].double().sum()) for k in pick}
+
+
+def make(name):
+    preset, over, B, l_text, wseed, sseed, poly_len, script = FIXTURES[name]
+    mc = dict(T.MODEL_PRESETS[preset])
+    mc.update(over)
+    lc = T.resolve_llama(mc["base_model_name"])
+    mod = ref_loader.load_reference(script, lc)
+    model = ref_loader.build_reference_model(mod, mc, lc)
+    sd = model.state_dict()
+    T.deterministic_fill_(sd, wseed)
+    model.load_state_dict(sd, strict=True)
+    s = T.make_scenes(B, mc["seq_len"], mc["out_len"], vision_dim=mc.get("vision_dim", 512), l_text=l_text,
+                      vocab=lc["vocab_size"], seed=sseed)
+    if poly_len is not None:
+        g = torch.Generator().manual_seed(sseed + 1)
+        s["poly_len"] = list(poly_len)
+        pts = torch.rand(B, 64, 2, generator=g) * torch.tensor([3839.0, 750.0]) + torch.tensor([0.0, 700.0])
+        keep = torch.arange(64)[None, :] < torch.tensor(poly_len)[:, None]
+        s["polygon"] = torch.where(keep[..., None], pts, torch.zeros_like(pts))
+    with torch.no_grad():
+        loss, decoded = model(s["x"], s["vision"], s["context_str"], s["polygon"], s["poly_len"], y=s["y"],
+                              norm_stat=s["norm_stat"], input_ids=s["input_ids"], attention_mask=s["attention_mask"],
+                              labels=None)
+        decoded_only = model(s["x"], s["vision"], s["context_str"], s["polygon"], s["poly_len"],
+                             input_ids=s["input_ids"], attention_mask=s["attention_mask"])
+        assert torch.equal(decoded, decoded_only)
+        poly_emb = model.lane_polygon_encoder(s["polygon"], s["poly_len"])
+        image_tokens = model.mllm.qformer(s["vision"])
+        final_hidden, n_img = model.mllm(s["vision"], s["context_str"], input_ids=s["input_ids"],
+                                         attention_mask=s["attention_mask"])
+        lt = model.ltsf
+        enc = lt.attn_block(lt.nlinear_encoder(lt.token_proj(s["x"])) + lt.pos_encoding)
+        # ADE / FDE exactly as reference scripts/train.py:1302-1322
+        ns = torch.tensor(s["norm_stat"])
+        pred_den, y_den = decoded.clone(), s["y"].clone()
+        rx, ry = (ns[:, 1] - ns[:, 0])[:, None], (ns[:, 3] - ns[:, 2])[:, None]
+        pred_den[:, 0, :] = pred_den[:, 0, :] * rx + ns[:, 0][:, None]
+        pred_den[:, 1, :] = pred_den[:, 1, :] * ry + ns[:, 2][:, None]
+        y_den[:, 0, :] = y_den[:, 0, :] * rx + ns[:, 0][:, None]
+        y_den[:, 1, :] = y_den[:, 1, :] * ry + ns[:, 2][:, None]
+        err = torch.sqrt(((pred_den - y_den) ** 2).sum(dim=1))
+        ade, fde = err.mean(dim=1), err[:, -1]
+    keep_fh = min(B, 2)
+    fix = {
+        "name": name, "model_cfg": mc, "llama_cfg": lc, "weight_seed": wseed, "scene_seed": sseed,
+        "l_text": l_text, "script": script, "n_state_keys": len(sd), "state_shapes": {k: tuple(v.shape) for k, v in sd.items()},
+        "weight_checksums": weight_checksums(sd),
+        "inputs": {k: s[k] for k in ("x", "y", "vision", "polygon", "poly_len", "norm_stat", "input_ids", "attention_mask")},
+        "out": {
+            "decoded": decoded, "loss": loss, "poly_emb": poly_emb, "image_tokens": image_tokens, "enc": enc,
+            "final_hidden_head": final_hidden[:keep_fh].clone(),
+            "final_hidden_rowmean": final_hidden.mean(dim=-1), "final_hidden_absmean": final_hidden.abs().mean(dim=-1),
+            "ade": ade, "fde": fde, "n_img": int(n_img),
+        },
+        "versions": {"torch": torch.__version__, "transformers": __import__("transformers").__version__},
+    }
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    path = os.path.join(GOLDEN_DIR, name + ".pt")
+    torch.save(fix, path)
+    print(f"{name}: {os.path.getsize(path) / 1e6:.2f} MB  loss={float(loss):.4f} ade={float(ade.mean()):.4f} fde={float(fde.mean()):.4f}")
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count())
+    for n in (sys.argv[1:] or list(FIXTURES)):
+        make(n)

@@ -1,0 +1,5 @@
+"""tcavp_b200 — B200-native (sm_100a) forward hot path of the Traffic-Context-Augmented Vehicle Trajectory
+Prediction model.  Public surface mirrors the reference (reference scripts/train.py:847-964)."""
+from .config import LLAMA_PRESETS, MODEL_PRESETS, resolve_llama  # noqa: F401
+from .synthetic import make_scenes  # noqa: F401
+from .weights import deterministic_fill_  # noqa: F401

@@ -1,0 +1,51 @@
+"""Backbone shape presets and model-constructor presets for BASELINE.json's configs.
+
+The reference hard-codes a hub name (reference scripts/train.py:1347) and lets HF resolve the shape; there is
+no network here, so a `base_model_name` is resolved to one of these shapes (or to an explicit dict)."""
+
+LLAMA_PRESETS = {
+    # "GPT-2-small-class" Llama-arch backbone: cfg 1, 2, 5
+    "llama-768": dict(vocab_size=32000, hidden_size=768, intermediate_size=3072, num_hidden_layers=12,
+                      num_attention_heads=12, num_key_value_heads=12, head_dim=64, rms_norm_eps=1e-6,
+                      rope_theta=10000.0),
+    # Llama-2-7B shape (reference default name, scripts/train.py:461): cfg 3, 4
+    "llama-7b": dict(vocab_size=32000, hidden_size=4096, intermediate_size=11008, num_hidden_layers=32,
+                     num_attention_heads=32, num_key_value_heads=32, head_dim=128, rms_norm_eps=1e-5,
+                     rope_theta=10000.0),
+    # GQA fidelity shape (Llama-3.2-1B geometry with plain rope)
+    "llama-1b-gqa": dict(vocab_size=32000, hidden_size=2048, intermediate_size=8192, num_hidden_layers=16,
+                         num_attention_heads=32, num_key_value_heads=8, head_dim=64, rms_norm_eps=1e-5,
+                         rope_theta=500000.0),
+    # tiny shape for golden fixtures that carry their full state_dict
+    "llama-tiny": dict(vocab_size=97, hidden_size=128, intermediate_size=256, num_hidden_layers=2,
+                       num_attention_heads=4, num_key_value_heads=2, head_dim=32, rms_norm_eps=1e-6,
+                       rope_theta=10000.0),
+}
+_ALIASES = {
+    "meta-llama/Llama-2-7b-hf": "llama-7b", "meta-llama/Llama-7B": "llama-7b",
+    "gpt2-small-class": "llama-768",
+}
+
+
+def resolve_llama(name_or_cfg):
+    if isinstance(name_or_cfg, dict):
+        return dict(name_or_cfg)
+    key = _ALIASES.get(name_or_cfg, name_or_cfg)
+    if key not in LLAMA_PRESETS:
+        raise KeyError(f"unknown backbone {name_or_cfg!r}: pass a preset name {sorted(LLAMA_PRESETS)} or a shape dict "
+                       "(there is no hub access to resolve checkpoint names)")
+    return dict(LLAMA_PRESETS[key])
+
+
+# ctor kwargs of MultiModalTrajectoryModel (reference scripts/train.py:848-872, values from 1100-1125)
+MODEL_PRESETS = {
+    "cfg1": dict(seq_len=15, out_len=25, individual=True, d_model=64, base_model_name="llama-768", use_lora=True,
+                 lora_r=8, lora_alpha=32, ltsf_nhead=2),
+    "cfg3": dict(seq_len=15, out_len=25, individual=True, d_model=64, base_model_name="llama-7b", use_lora=True,
+                 lora_r=16, lora_alpha=32, ltsf_nhead=2),
+    "cfg5": dict(seq_len=15, out_len=50, individual=True, d_model=64, base_model_name="llama-768", use_lora=False,
+                 ltsf_nhead=2),
+    "tiny": dict(seq_len=6, out_len=12, individual=True, d_model=64, base_model_name="llama-tiny", use_lora=True,
+                 lora_r=4, lora_alpha=16, q_hidden_size=64, q_nhead=4, q_enc_layers=1, q_dec_layers=2,
+                 q_num_query_tokens=16, vision_dim=32, ltsf_nhead=2),
+}

@@ -1,0 +1,117 @@
+// Shared device/host helpers for libtcavp (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include "../../include/tcavp.h"
+
+namespace tcavp {
+
+// ---------------------------------------------------------------------------------------------
+// Host-side error plumbing: every entry point returns 0 or a negative code and records a
+// thread-local message readable through tcavp_last_error(). Nothing throws, nothing syncs.
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int  fail_arg(const char* fmt, ...);
+int  check_launch(const char* what);
+int  sm_count();
+
+#define TCAVP_REQUIRE(cond, ...)                         \
+  do {                                                   \
+    if (!(cond)) return ::tcavp::fail_arg(__VA_ARGS__);  \
+  } while (0)
+
+#define TCAVP_CUDA(expr)                                                          \
+  do {                                                                            \
+    cudaError_t _e = (expr);                                                      \
+    if (_e != cudaSuccess) {                                                      \
+      ::tcavp::set_error("%s failed: %s", #expr, cudaGetErrorString(_e));         \
+      return TCAVP_ERR_CUDA;                                                      \
+    }                                                                             \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Device helpers
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct Cvt;
+template <> struct Cvt<float> {
+  __device__ __forceinline__ static float to_f(float v) { return v; }
+  __device__ __forceinline__ static float from_f(float v) { return v; }
+};
+template <> struct Cvt<__nv_bfloat16> {
+  __device__ __forceinline__ static float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+  __device__ __forceinline__ static __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Load element i of a tensor whose dtype is only known at run time (TCAVP_F32 / TCAVP_BF16).
+__device__ __forceinline__ float load_as_f(const void* p, size_t i, int dtype) {
+  return dtype == TCAVP_F32 ? reinterpret_cast<const float*>(p)[i]
+                            : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+__device__ __forceinline__ void store_from_f(void* p, size_t i, int dtype, float v) {
+  if (dtype == TCAVP_F32) reinterpret_cast<float*>(p)[i] = v;
+  else reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// GEMM epilogue shared by the SIMT fp32 kernel and the tcgen05 bf16 kernel.
+//   v = acc (+bias[n]) (+ sum_k lora_t[m,k] * lora_b[n,k] inside a LoRA column segment)
+//   v = relu(v) if act == RELU          (SwiGLU is applied by the caller on column pairs)
+//   v += residual[m_out, n]
+//   out[m_out, n] = v        with m_out = (m / remap_gi) * remap_go + (m % remap_gi) + remap_off
+// ---------------------------------------------------------------------------------------------
+struct EpilogueParams {
+  int M, N;                 // logical output extent (N is post-SwiGLU width when act == SWIGLU)
+  void* out; int ldo; int out_dtype;
+  const float* bias;
+  const void* residual; int ldr; int res_dtype;
+  int act;
+  const float* lora_t; int lora_ldt; int lora_r; const float* lora_b;
+  int seg_begin[2], seg_end[2], seg_toff[2];
+  int remap_gi, remap_go, remap_off;
+  float out_scale;          // multiplies acc before bias (1.0f default)
+};
+
+__device__ __forceinline__ int remap_row(const EpilogueParams& p, int m) {
+  return p.remap_gi > 0 ? (m / p.remap_gi) * p.remap_go + (m % p.remap_gi) + p.remap_off : m;
+}
+
+__device__ __forceinline__ void epilogue_store(const EpilogueParams& p, int m, int n, float v) {
+  if (m >= p.M || n >= p.N) return;
+  v *= p.out_scale;
+  if (p.bias) v += __ldg(p.bias + n);
+  if (p.lora_r > 0) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      if (n >= p.seg_begin[s] && n < p.seg_end[s]) {
+        const float* t = p.lora_t + (size_t)m * p.lora_ldt + p.seg_toff[s];
+        const float* b = p.lora_b + (size_t)n * p.lora_r;
+        float a = 0.f;
+        for (int k = 0; k < p.lora_r; ++k) a = fmaf(__ldg(t + k), __ldg(b + k), a);
+        v += a;
+      }
+    }
+  }
+  if (p.act == TCAVP_ACT_RELU) v = fmaxf(v, 0.f);
+  const int mo = remap_row(p, m);
+  if (p.residual) v += load_as_f(p.residual, (size_t)mo * p.ldr + n, p.res_dtype);
+  store_from_f(p.out, (size_t)mo * p.ldo + n, p.out_dtype, v);
+}
+
+__device__ __forceinline__ float silu_f(float g) { return g / (1.f + __expf(-g)); }
+
+}  // namespace tcavp
