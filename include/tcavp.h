@@ -5,18 +5,19 @@
  * The reference (imjaegyun/Traffic-Context-Augmented-...-Multimodal-LLM) has no FFI/plugin layer: its
  * boundary is the Python class `MultiModalTrajectoryModel` (reference scripts/train.py:847-964).  This
  * header is the C boundary *beneath* our Python mirror of that class; each entry point names the
- * reference call site (file:line, relative to the reference root; "HF:" = transformers
- * models/llama/modeling_llama.py) whose arithmetic it replaces.
+ * reference call site (file:line, relative to the reference root; "HF:" = transformers 5.5.0
+ * models/llama/modeling_llama.py, "torch:" = torch.nn) whose arithmetic it replaces.
  *
  * Conventions
- *   - All pointers are DEVICE pointers unless the name ends in `_host`.  The caller owns every buffer;
- *     the library allocates no device memory and keeps no state besides a per-process cache of the
- *     driver entry point used to encode TMA descriptors.
+ *   - All pointers are DEVICE pointers.  The caller owns every buffer; the library allocates no device
+ *     memory and keeps no state besides the cached driver entry point used to encode TMA descriptors.
  *   - Every call is asynchronous on `stream` (a cudaStream_t passed as void*), never synchronises,
  *     returns 0 on success or a negative TCAVP_ERR_* code; tcavp_last_error() gives the thread-local text.
- *   - dtype codes: TCAVP_F32 (fp32 storage, fp32 SIMT math) / TCAVP_BF16 (bf16 storage, fp32 accumulate).
+ *   - dtype codes: TCAVP_F32 (fp32 storage, exact fp32 SIMT math, no TF32) / TCAVP_BF16 (bf16 storage,
+ *     fp32 accumulate; dense contractions on tcgen05 tensor cores).
  *   - Matrices are row-major; "ld*" are leading dimensions in ELEMENTS.  Weights keep nn.Linear's
  *     [out_features, in_features] layout so state_dict tensors are consumed without transposition.
+ *   - There is no CPU fallback anywhere: without an sm_100 device every compute entry point fails.
  */
 #ifndef TCAVP_H_
 #define TCAVP_H_
@@ -39,24 +40,26 @@ const char* tcavp_last_error(void);
 int tcavp_version(void);
 /* Fills SM count and compute capability of the current device. */
 int tcavp_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+long long tcavp_launch_count(void);
 
 /* ---- dense contraction with fused epilogue --------------------------------------------------
- * out[m', n] = act( scale * sum_k A[m,k] * W[n,k] + bias[n] + LoRA(m,n) ) + residual[m', n]
+ * out[m', n] = act( sum_k A[m,k] * W[n,k] + bias[n] ) + residual[m', n]
  *
  * Replaces every nn.Linear / F.linear on the path: HF LlamaAttention q/k/v/o_proj (HF:251-289) and
- * LlamaMLP gate/up/down (HF:182), peft lora.Linear (y = Wx + (alpha/r) B(A x), train.py:432-440),
+ * LlamaMLP gate/up/down (HF:182-196), peft lora.Linear (y = Wx + (alpha/r) B(A x), train.py:432-440),
  * nn.MultiheadAttention / nn.Transformer* in/out projections and FFNs (train.py:358-359, 402-406,
- * 663-670, 754), q_proj (train.py:521), lane_fc / post_mlp (train.py:784-790).
+ * 663-670, 754), q_proj (train.py:521), lane_fc / post_mlp / dec_proj / dec_unproj (train.py:784-799).
  *
- *   in_dtype   TCAVP_BF16: A and W are bf16, TMA-fed tcgen05.mma with TMEM accumulators (fp32);
- *              requires K % 8 == 0 and 16-byte aligned A/W rows.
- *              TCAVP_F32 : A and W are fp32, SIMT FFMA kernel (exact fp32 accumulate, no TF32).
+ *   in_dtype   TCAVP_BF16: A and W are bf16 -> TMA-fed tcgen05.mma, fp32 accumulators in TMEM.
+ *              Requires K % 8 == 0, lda % 8 == 0, ldw % 8 == 0 and 16-byte aligned A / W.
+ *              TCAVP_F32 : A and W are fp32 -> SIMT FFMA kernel (exact fp32 accumulate).
+ *   LoRA       is NOT an epilogue term: the caller appends T = x.A^T (rank r, from a skinny call of
+ *              this same function) as extra K columns of A and (alpha/r).B as extra K columns of W,
+ *              so the rank-r update accumulates in the same TMEM tile as the base product.
  *   act        RELU, or SWIGLU: W rows are interleaved (gate_0, up_0, gate_1, up_1, ...), N counts the
- *              interleaved rows, the output has N/2 columns: silu(gate_j) * up_j  (HF:190).
- *   LoRA       lora_r > 0: adds sum_k lora_t[m, toff + k] * lora_b[n, k] for columns n inside
- *              [seg_begin[i], seg_end[i]) (i = 0,1; toff = seg_toff[i]).  lora_t = x·A^T (fp32,
- *              leading dim lora_ldt) comes from a skinny GEMM over the same x; lora_b = (alpha/r)·B
- *              as fp32 [N, r].
+ *              interleaved rows, the output has N/2 columns silu(gate_j) * up_j (HF:190); bias,
+ *              residual and ldo refer to the N/2 output columns.
  *   row remap  remap_gi > 0: m' = (m / remap_gi) * remap_go + (m % remap_gi) + remap_off (writes the
  *              16 image-token rows of each scene straight into the fused (B, L, H) buffer,
  *              train.py:521-528).  Otherwise m' = m.
@@ -71,13 +74,109 @@ typedef struct tcavp_gemm_args {
   const float* bias;
   const void* residual; int ldr; int res_dtype;
   int act;
-  float scale;               /* 0 is treated as 1 */
-  const float* lora_t; int lora_ldt; int lora_r; const float* lora_b;
-  int seg_begin[2], seg_end[2], seg_toff[2];
   int remap_gi, remap_go, remap_off;
 } tcavp_gemm_args;
 
 int tcavp_gemm(const tcavp_gemm_args* args, tcavp_stream_t stream);
+
+/* ---- attention ----------------------------------------------------------------------------------
+ * out[b, i, h, :] = softmax_j( scale * q[b,i,h,:].k[b,j,hk,:] + mask ) . v[b,j,hk,:],  hk = h / (H/Hkv)
+ *
+ * Replaces torch: F.multi_head_attention_forward's core (train.py:371, 411-413, 678, 798) and HF
+ * sdpa_attention_forward with the causal+padding mask of create_causal_mask (HF:399, 251-289).
+ * q/k/v/out are strided views: element (b, t, h, d) lives at  ptr[b*s_b + t*s_t + h*dh + d].
+ *   causal      != 0: key j allowed only if j <= i (requires Tq == Tk).
+ *   key_mask    optional int32 [B, Tk], 1 = attend, 0 = masked (key padding).  Rows whose keys are all
+ *               masked produce zeros (the reference discards such rows, train.py:378-380).
+ * Softmax statistics and accumulation are fp32 for both dtypes.  `dtype` applies to q, k, v and out.
+ * bf16 with dh in {64,128} and Tk <= 256 runs on tensor cores; everything else on the SIMT kernel.
+ */
+typedef struct tcavp_attn_args {
+  int B, H, Hkv, Tq, Tk, dh;
+  const void* q; long long q_sb, q_st;
+  const void* k; long long k_sb, k_st;
+  const void* v; long long v_sb, v_st;
+  void* out; long long o_sb, o_st;
+  int dtype;
+  float scale;
+  int causal;
+  const int32_t* key_mask;
+} tcavp_attn_args;
+
+int tcavp_attention(const tcavp_attn_args* args, tcavp_stream_t stream);
+
+/* ---- normalisation ---------------------------------------------------------------------------- */
+/* out[r,:] = LayerNorm(x[r,:] + residual[r,:]) * w + b      (torch: nn.LayerNorm eps 1e-5; residual
+ * optional — post-norm nn.Transformer*Layer, train.py:358, 402-405; attn_block 677-681; fusion 759-764).
+ * remap/rowvec: optional scatter of row r to (r/gi)*go + r%gi + off with `rowvec[:]` added after the
+ * affine (writes Q-Former tokens + vision_modality_embedding into the fused buffer, train.py:522-528). */
+int tcavp_layernorm(const void* x, const void* residual, const float* w, const float* b, void* out, int rows, int cols,
+                    float eps, int in_dtype, int out_dtype, int remap_gi, int remap_go, int remap_off,
+                    const float* rowvec, tcavp_stream_t stream);
+/* out[r,:] = w * (x[r,:] * rsqrt(mean(x^2) + eps))          (HF:53-70 LlamaRMSNorm).  ldo lets the output land
+ * in a wider row (the K-extended activation that also carries the LoRA side columns). */
+int tcavp_rmsnorm(const void* x, const float* w, void* out, int rows, int cols, int ldo, float eps, int in_dtype,
+                  int out_dtype, tcavp_stream_t stream);
+
+/* ---- rotary embedding (HF:146-170 apply_rotary_pos_emb, default rope HF:73-136) ----------------
+ * In place on the q and k head blocks of a packed [rows, ld] qkv buffer (q heads first, then k heads);
+ * position of row r is r % L.  cos_sin is an fp32 [L, dh/2, 2] table. */
+int tcavp_rope(void* qkv, int rows, int L, int ld, int n_q_heads, int n_k_heads, int dh, const float* cos_sin,
+               int dtype, tcavp_stream_t stream);
+/* Fills the [L, dh/2, 2] table exactly as HF does (fp32 inv_freq, fp32 angle, cosf/sinf). */
+int tcavp_rope_table(float* cos_sin, int L, int dh, float theta, tcavp_stream_t stream);
+
+/* ---- fused-sequence assembly (train.py:526-528) -------------------------------------------------
+ * fused[b, n_img + j, :] = embed[ids[b, j], :] + text_mod[:]   for j < L_text; mask_out[b, :] = [1]*n_img ++ mask. */
+int tcavp_embed_text(const int64_t* ids, const int64_t* attn_mask, const void* embed, int embed_dtype,
+                     const float* text_mod, void* fused, int fused_dtype, int32_t* mask_out, int B, int L_text,
+                     int n_img, int H, int vocab, tcavp_stream_t stream);
+/* out[r', :] = x[r, :] + rowvec[:] with the row remap above (Identity q_proj case, train.py:492-495, 522). */
+int tcavp_add_rowvec(const void* x, const float* rowvec, void* out, int rows, int cols, int in_dtype, int out_dtype,
+                     int remap_gi, int remap_go, int remap_off, tcavp_stream_t stream);
+/* dtype conversion / strided copy / row broadcast: out[r, 0:cols] = in[r % in_row_mod, 0:cols]
+ * (in_row_mod <= 0: no modulo).  The broadcast form expands the Q-Former query tokens over the batch
+ * (train.py:412). */
+int tcavp_cast(const void* in, int ldi, int in_dtype, void* out, int ldo, int out_dtype, int rows, int cols,
+               int in_row_mod, tcavp_stream_t stream);
+
+/* ---- lane polygon encoder ends (train.py:364-365, 373-382) -------------------------------------- */
+/* out[b,p,:] = W[:, 0:2] . polygon[b,p,:] + bias + pos[p,:];  key_mask[b,p] = p < len[b] */
+int tcavp_poly_embed(const float* polygon, const int32_t* len, const float* w, const float* bias, const float* pos,
+                     void* out, int out_dtype, int32_t* key_mask, int B, int P, int D, tcavp_stream_t stream);
+/* out[b,:] = mean over p < len[b] of x[b,p,:]  (zeros when len[b] == 0) */
+int tcavp_masked_mean(const void* x, int in_dtype, const int32_t* len, void* out, int out_dtype, int B, int P, int D,
+                      tcavp_stream_t stream);
+
+/* ---- temporal encoder / NLinear decoder (train.py:701-716, 837-839, 769-785) --------------------
+ * enc[b, t, c] = sum_s We[c,t,s] * (xp[b,c,s] - xp[b,c,T-1]) + be[c,t] + xp[b,c,T-1] + pos[c,t],
+ *   xp[b,c,s] = sum_f Wt[c,f] * x[b,f,s] + bt[c]                (token_proj, 1x1 conv)
+ * Output layout is (B, T_in, C) — rows (b,t) with channels contiguous — so the attention block's
+ * projections are plain row-major GEMMs.  Weight layouts (permuted once at pack time so that the channel
+ * index is contiguous): we [T_in(t), T_in(s), C], be / pos [T_in, C], wt [C, F], bt [C]; T_in <= 64. */
+int tcavp_ltsf_encode(const float* x, const float* wt, const float* bt, const float* we, const float* be,
+                      const float* pos, void* enc, int out_dtype, int B, int F, int C, int T_in,
+                      tcavp_stream_t stream);
+/* dec[b, t, c] = sum_s Wd[c,t,s] * (enc[b,s,c] - enc[b,T-1,c]) + bd[c,t] + enc[b,T-1,c] + lane_adj[b,t,c]
+ * (lane_adj optional; (B, T_out, C) layout — post_mlp / lane_fc weights are permuted accordingly at pack time).
+ * wd [T_out, T_in(s), C], bd [T_out, C]. */
+int tcavp_nlinear_decode(const void* enc, int enc_dtype, const float* wd, const float* bd, const void* lane_adj,
+                         int adj_dtype, void* dec, int out_dtype, int B, int C, int T_in, int T_out,
+                         tcavp_stream_t stream);
+
+/* ---- fusion head + metrics (train.py:801-805, 941-943, 945-962, 1302-1322) ----------------------
+ * Per (b, t): f = LN(fused[b,t,:]); f = W2.relu(W1.f + b1) + b2; o = Wo.f + bo (2 values);
+ * decoded[b, :, t] = o + x[b, :, T_in-1].  With y and norm_stat (fp32 [B,4] = min_x,max_x,min_y,max_y):
+ * metrics[0..4] += (sum of squared de-normalised x error, same for y, sum_b ADE_b, sum_b FDE_b,
+ * MSE_x + MSE_y = the reference's training loss) and per_scene[b] = (ADE_b, FDE_b) — `metrics` is a
+ * float[8] zeroed by the caller. */
+int tcavp_fusion_head(const void* fused, int in_dtype, const float* ln_w, const float* ln_b, const float* w1,
+                      const float* b1, const float* w2, const float* b2, const float* wo, const float* bo,
+                      const float* x, float* decoded, const float* y, const float* norm_stat, float* metrics,
+                      float* per_scene, int B, int C, int T_in, int T_out, tcavp_stream_t stream);
+/* Same metrics for an existing prediction (train.py:1302-1322; RMSE: ablation_study_without_lora.py:1237). */
+int tcavp_traj_metrics(const float* decoded, const float* y, const float* norm_stat, float* metrics, float* per_scene,
+                       int B, int T_out, tcavp_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -88,7 +88,7 @@ def make(name):
             "final_hidden_rowmean": final_hidden.mean(dim=-1), "final_hidden_absmean": final_hidden.abs().mean(dim=-1),
             "ade": ade, "fde": fde, "n_img": int(n_img),
         },
-        "versions": {"torch": torch.__version__, "transformers": __import__("transformers").__version__},
+        "versions": {"torch": str(torch.__version__), "transformers": __import__("transformers").__version__},
     }
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     path = os.path.join(GOLDEN_DIR, name + ".pt")

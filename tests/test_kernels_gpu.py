@@ -1,0 +1,313 @@
+"""Per-kernel parity: every C-ABI entry point against the CPU oracle (oracle/restated.py) on seeded inputs.
+fp32 paths: rtol 1e-4 (the north-star fp32 tolerance); bf16 paths: compared with the oracle run on the
+bf16-rounded inputs, so only accumulation order / output rounding differ."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import restated as R  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ops(lib_built):
+    from tcavp_b200 import ops as o
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    sm, major, _ = o.device_info()
+    assert major == 10, f"libtcavp is built for sm_100a only (device is cc {major}.x)"
+    return o
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+DEV = "cuda"
+
+GEMM_SHAPES = [(1, 16, 64), (100, 24, 72), (128, 64, 64), (300, 100, 136), (257, 256, 768), (1000, 600, 200),
+               (130, 2304, 784), (64, 1600, 64), (515, 64, 1600), (384, 6144, 768), (200, 768, 3072)]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_gemm_plain(ops, M, N, K, dtype):
+    td = torch.float32 if dtype == "fp32" else torch.bfloat16
+    a, w = _rand(M, K, seed=1).to(td), _rand(N, K, seed=2, scale=K ** -0.5).to(td)
+    want = a.float() @ w.float().t()
+    out = torch.empty(M, N, dtype=torch.float32, device=DEV)
+    ops.gemm(a.to(DEV), w.to(DEV), out)
+    torch.testing.assert_close(out.cpu(), want, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("act", ["none", "relu", "swiglu"])
+def test_gemm_epilogue(ops, dtype, act):
+    td = torch.float32 if dtype == "fp32" else torch.bfloat16
+    M, N, K = 333, 200, 136
+    a, w = _rand(M, K, seed=3).to(td), _rand(N, K, seed=4, scale=K ** -0.5).to(td)
+    No = N // 2 if act == "swiglu" else N
+    bias = _rand(No, seed=5)
+    res = _rand(M, No, seed=6).to(td)
+    acc = a.float() @ w.float().t()
+    if act == "swiglu":
+        want = torch.nn.functional.silu(acc[:, 0::2]) * acc[:, 1::2] + bias
+    else:
+        want = acc + bias
+        if act == "relu":
+            want = torch.relu(want)
+    want = want + res.float()
+    for out_dtype in (torch.float32, td):
+        out = torch.empty(M, No, dtype=out_dtype, device=DEV)
+        ops.gemm(a.to(DEV), w.to(DEV), out, bias=bias.to(DEV), residual=res.to(DEV),
+                 act={"none": ops.ACT_NONE, "relu": ops.ACT_RELU, "swiglu": ops.ACT_SWIGLU}[act])
+        tol = dict(rtol=1e-4, atol=1e-4) if out_dtype == torch.float32 else dict(rtol=1e-2, atol=1e-2)
+        torch.testing.assert_close(out.float().cpu(), want, **tol)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_gemm_inplace_residual_strided_and_remap(ops, dtype):
+    td = torch.float32 if dtype == "fp32" else torch.bfloat16
+    # in-place residual (o_proj / down_proj pattern)
+    M, N, K = 260, 128, 64
+    a, w, x = _rand(M, K, seed=7).to(td), _rand(N, K, seed=8, scale=0.1).to(td), _rand(M, N, seed=9).to(td)
+    xd = x.to(DEV)
+    ops.gemm(a.to(DEV), w.to(DEV), xd, residual=xd)
+    torch.testing.assert_close(xd.float().cpu(), (a.float() @ w.float().t() + x.float()).to(td).float(), rtol=1e-2, atol=1e-2)
+    # K-extension pattern: A has a wider row than K, output lands in the trailing columns of the same buffer
+    H, kx = 128, 16
+    buf = torch.zeros(M, H + kx, dtype=td)
+    buf[:, :H] = _rand(M, H, seed=10).to(td)
+    acat = _rand(kx, H, seed=11, scale=H ** -0.5).to(td)
+    bd = buf.to(DEV)
+    ops.gemm(bd, acat.to(DEV), bd[:, H:], M=M, N=kx, K=H, lda=H + kx, ldo=H + kx)
+    want = buf[:, :H].float() @ acat.float().t()
+    torch.testing.assert_close(bd[:, H:].float().cpu(), want.to(td).float(), rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(bd[:, :H].cpu(), buf[:, :H])
+    # row remap: 16 rows per scene scattered into rows [0,16) of a (B, L, H) buffer
+    B, Q, L = 5, 16, 40
+    t, wq = _rand(B * Q, 64, seed=12).to(td), _rand(H, 64, seed=13, scale=0.125).to(td)
+    fused = torch.full((B, L, H), 7.0, dtype=td, device=DEV)
+    ops.gemm(t.to(DEV), wq.to(DEV), fused, remap=(Q, L, 0), ldo=H)
+    want = (t.float() @ wq.float().t()).view(B, Q, H)
+    torch.testing.assert_close(fused[:, :Q].float().cpu(), want.to(td).float(), rtol=1e-2, atol=1e-2)
+    assert (fused[:, Q:] == 7.0).all()
+
+
+def test_gemm_rejects_bad_arguments(ops):
+    from tcavp_b200.lib import TcavpError
+    a = torch.zeros(4, 12, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(TcavpError, match="multiples of 8"):
+        ops.gemm(a, torch.zeros(8, 12, dtype=torch.bfloat16, device=DEV), torch.zeros(4, 8, device=DEV))
+    with pytest.raises(TcavpError, match="CUDA tensors"):
+        ops.gemm(torch.zeros(4, 8), torch.zeros(8, 8), torch.zeros(4, 8))
+    out = torch.zeros(0, 8, device=DEV)
+    ops.gemm(torch.zeros(0, 8, device=DEV), torch.zeros(8, 8, device=DEV), out, M=0)   # empty batch is a no-op
+
+
+def _attn_ref(q, k, v, scale, causal, key_mask):
+    # q (B,Tq,H,dh) k/v (B,Tk,Hkv,dh)
+    B, Tq, H, dh = q.shape
+    Hkv = k.shape[2]
+    k = k.repeat_interleave(H // Hkv, dim=2)
+    v = v.repeat_interleave(H // Hkv, dim=2)
+    s = torch.einsum("bihd,bjhd->bhij", q, k) * scale
+    if causal:
+        s = s.masked_fill(~torch.tril(torch.ones(Tq, k.shape[1], dtype=torch.bool)), float("-inf"))
+    if key_mask is not None:
+        s = s.masked_fill(~key_mask.bool()[:, None, None, :], float("-inf"))
+    p = torch.nan_to_num(torch.softmax(s, dim=-1), nan=0.0)
+    return torch.einsum("bhij,bjhd->bihd", p, v)
+
+
+ATTN_CASES = [
+    # B, H, Hkv, Tq, Tk, dh, causal, masked
+    (3, 4, 4, 64, 64, 16, False, True),     # lane polygon encoder
+    (2, 8, 8, 15, 15, 96, False, False),    # Q-Former encoder
+    (2, 8, 8, 16, 15, 96, False, False),    # Q-Former decoder cross
+    (3, 2, 2, 15, 15, 32, False, False),    # LTSF attn block
+    (2, 2, 2, 25, 144, 384, False, False),  # LTSF cross-attn, H=768
+    (1, 2, 2, 25, 40, 2048, False, False),  # LTSF cross-attn, H=4096
+    (2, 12, 12, 144, 144, 64, True, True),  # LLM 768-class
+    (2, 4, 2, 40, 40, 32, True, True),      # tiny GQA
+    (1, 8, 2, 70, 70, 128, True, True),     # 7B-style head_dim with GQA
+]
+
+
+@pytest.mark.parametrize("B,H,Hkv,Tq,Tk,dh,causal,masked", ATTN_CASES)
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_attention(ops, B, H, Hkv, Tq, Tk, dh, causal, masked, dtype):
+    td = torch.float32 if dtype == "fp32" else torch.bfloat16
+    q, k, v = _rand(B, Tq, H, dh, seed=1).to(td), _rand(B, Tk, Hkv, dh, seed=2).to(td), _rand(B, Tk, Hkv, dh, seed=3).to(td)
+    km = None
+    if masked:
+        lens = torch.tensor([Tk, max(1, Tk // 2), 0][:B]) if not causal else torch.tensor([Tk, max(1, Tk // 2), 3][:B])
+        km = (torch.arange(Tk)[None, :] < lens[:, None]).int()
+    want = _attn_ref(q.float(), k.float(), v.float(), dh ** -0.5, causal, km)
+    out = torch.empty(B, Tq, H, dh, dtype=td, device=DEV)
+    ops.attention(q.to(DEV), k.to(DEV), v.to(DEV), out, B=B, H=H, Hkv=Hkv, Tq=Tq, Tk=Tk, dh=dh, q_strides=(Tq * H * dh, H * dh),
+                  k_strides=(Tk * Hkv * dh, Hkv * dh), v_strides=(Tk * Hkv * dh, Hkv * dh), o_strides=(Tq * H * dh, H * dh),
+                  scale=dh ** -0.5, causal=causal, key_mask=None if km is None else km.to(DEV))
+    tol = dict(rtol=1e-4, atol=1e-5) if dtype == "fp32" else dict(rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(out.float().cpu(), want, **tol)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("rows,cols", [(37, 64), (20, 768), (5, 4096), (9, 100)])
+def test_norms(ops, dtype, rows, cols):
+    td = torch.float32 if dtype == "fp32" else torch.bfloat16
+    x, r = _rand(rows, cols, seed=1).to(td), _rand(rows, cols, seed=2).to(td)
+    w, b = 1 + 0.1 * _rand(cols, seed=3), 0.1 * _rand(cols, seed=4)
+    tol = dict(rtol=1e-4, atol=1e-5) if dtype == "fp32" else dict(rtol=1e-2, atol=1e-2)
+    out = ops.layernorm(x.to(DEV), w.to(DEV), b.to(DEV), torch.empty(rows, cols, dtype=td, device=DEV), residual=r.to(DEV))
+    torch.testing.assert_close(out.float().cpu(), R.layer_norm(x.float() + r.float(), w, b), **tol)
+    out = ops.layernorm(x.to(DEV), w.to(DEV), b.to(DEV), torch.empty(rows, cols, dtype=torch.float32, device=DEV))
+    torch.testing.assert_close(out.cpu(), R.layer_norm(x.float(), w, b), rtol=1e-4, atol=1e-5)
+    wide = torch.zeros(rows, cols + 16, dtype=td, device=DEV)
+    ops.rmsnorm(x.to(DEV), w.to(DEV), wide, eps=1e-6, rows=rows, cols=cols, ldo=cols + 16)
+    torch.testing.assert_close(wide[:, :cols].float().cpu(), R.rms_norm(x.float(), w, 1e-6), **tol)
+    assert (wide[:, cols:] == 0).all()
+
+
+def test_layernorm_remap_rowvec(ops):
+    B, Q, L, H = 3, 16, 24, 64
+    x, w, b, vec = _rand(B * Q, H, seed=1), 1 + 0.1 * _rand(H, seed=2), 0.1 * _rand(H, seed=3), _rand(H, seed=4)
+    fused = torch.zeros(B, L, H, device=DEV)
+    ops.layernorm(x.to(DEV), w.to(DEV), b.to(DEV), fused, remap=(Q, L, 0), rowvec=vec.to(DEV))
+    torch.testing.assert_close(fused[:, :Q].cpu(), (R.layer_norm(x, w, b) + vec).view(B, Q, H), rtol=1e-4, atol=1e-5)
+    assert (fused[:, Q:] == 0).all()
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("nh,nkv,dh,theta", [(12, 12, 64, 10000.0), (4, 2, 32, 10000.0), (8, 2, 128, 500000.0)])
+def test_rope(ops, dtype, nh, nkv, dh, theta):
+    td = torch.float32 if dtype == "fp32" else torch.bfloat16
+    B, L = 2, 144
+    ld = (nh + 2 * nkv) * dh
+    qkv = _rand(B * L, ld, seed=1).to(td)
+    cos, sin = R.rope_cos_sin(L, dh, theta)
+    table = ops.rope_table(L, dh, theta, DEV)
+    torch.testing.assert_close(table[..., 0].cpu(), cos[:, : dh // 2], rtol=0, atol=2e-6)
+    torch.testing.assert_close(table[..., 1].cpu(), sin[:, : dh // 2], rtol=0, atol=2e-6)
+    q = qkv[:, : nh * dh].float().view(B, L, nh, dh)
+    k = qkv[:, nh * dh:(nh + nkv) * dh].float().view(B, L, nkv, dh)
+    c, s = cos[None, :, None, :], sin[None, :, None, :]
+    wq, wk = q * c + R.rotate_half(q) * s, k * c + R.rotate_half(k) * s
+    d = qkv.to(DEV)
+    ops.rope_(d, rows=B * L, L=L, ld=ld, n_q_heads=nh, n_k_heads=nkv, dh=dh, table=table)
+    tol = dict(rtol=1e-4, atol=1e-5) if dtype == "fp32" else dict(rtol=1e-2, atol=2e-2)
+    torch.testing.assert_close(d[:, : nh * dh].float().cpu().view(B, L, nh, dh), wq, **tol)
+    torch.testing.assert_close(d[:, nh * dh:(nh + nkv) * dh].float().cpu().view(B, L, nkv, dh), wk, **tol)
+    torch.testing.assert_close(d[:, (nh + nkv) * dh:].cpu(), qkv[:, (nh + nkv) * dh:])   # v untouched
+
+
+def test_embed_text_cast_rowvec(ops):
+    B, Lt, Q, H, V = 3, 10, 16, 64, 50
+    ids = torch.randint(0, V, (B, Lt), generator=torch.Generator().manual_seed(1))
+    am = (torch.arange(Lt)[None, :] < torch.tensor([10, 4, 1])[:, None]).long()
+    emb, tm = _rand(V, H, seed=2), _rand(H, seed=3)
+    fused = torch.zeros(B, Q + Lt, H, device=DEV)
+    mask = torch.zeros(B, Q + Lt, dtype=torch.int32, device=DEV)
+    ops.embed_text(ids.to(DEV), am.to(DEV), emb.to(DEV), tm.to(DEV), fused, mask, B=B, L_text=Lt, n_img=Q, H=H)
+    torch.testing.assert_close(fused[:, Q:].cpu(), emb[ids] + tm)
+    assert (fused[:, :Q] == 0).all()
+    assert torch.equal(mask.cpu(), torch.cat([torch.ones(B, Q, dtype=torch.int32), am.int()], 1))
+    q = _rand(Q, H, seed=4)
+    out = ops.cast(q.to(DEV), torch.empty(B * Q, H, dtype=torch.bfloat16, device=DEV), rows=B * Q, cols=H, in_row_mod=Q)
+    torch.testing.assert_close(out.float().cpu(), q.bfloat16().float().repeat(B, 1))
+    x = _rand(B * Q, H, seed=5)
+    o2 = torch.zeros(B, Q + Lt, H, device=DEV)
+    ops.add_rowvec(x.to(DEV), tm.to(DEV), o2, rows=B * Q, cols=H, remap=(Q, Q + Lt, 0))
+    torch.testing.assert_close(o2[:, :Q].cpu(), (x + tm).view(B, Q, H))
+
+
+def test_poly_embed_and_masked_mean(ops):
+    B, P, D = 4, 64, 64
+    poly = torch.rand(B, P, 2, generator=torch.Generator().manual_seed(1)) * 1000
+    lens = torch.tensor([0, 64, 1, 33], dtype=torch.int32)
+    w, b, pos = _rand(D, 2, seed=2, scale=0.01), _rand(D, seed=3), _rand(P, D, seed=4)
+    out = torch.empty(B * P, D, device=DEV)
+    km = torch.empty(B, P, dtype=torch.int32, device=DEV)
+    ops.poly_embed(poly.to(DEV), lens.to(DEV), w.to(DEV), b.to(DEV), pos.to(DEV), out, km, B=B, P=P, D=D)
+    want = poly @ w.t() + b + pos
+    torch.testing.assert_close(out.cpu().view(B, P, D), want, rtol=1e-5, atol=1e-4)
+    assert torch.equal(km.cpu(), (torch.arange(P)[None, :] < lens[:, None]).int())
+    mm = ops.masked_mean(out, lens.to(DEV), torch.empty(B, D, device=DEV), B=B, P=P, D=D).cpu()
+    for i, n in enumerate(lens.tolist()):
+        ref = want[i, :n].mean(0) if n > 0 else torch.zeros(D)
+        torch.testing.assert_close(mm[i], ref, rtol=1e-4, atol=1e-3)
+
+
+def _ltsf_sd(C, T, To, seed=0):
+    sd = {"ltsf.token_proj.weight": _rand(C, 2, 1, seed=seed + 1), "ltsf.token_proj.bias": _rand(C, seed=seed + 2),
+          "ltsf.pos_encoding": _rand(1, C, T, seed=seed + 3, scale=0.1)}
+    for i in range(C):
+        sd[f"ltsf.nlinear_encoder.encoder_linears.{i}.weight"] = _rand(T, T, seed=seed + 10 + i, scale=T ** -0.5)
+        sd[f"ltsf.nlinear_encoder.encoder_linears.{i}.bias"] = _rand(T, seed=seed + 100 + i, scale=0.1)
+        sd[f"ltsf.decoder.decoder_linears.{i}.weight"] = _rand(To, T, seed=seed + 200 + i, scale=T ** -0.5)
+        sd[f"ltsf.decoder.decoder_linears.{i}.bias"] = _rand(To, seed=seed + 300 + i, scale=0.1)
+    return sd
+
+
+@pytest.mark.parametrize("T,To", [(15, 25), (6, 12), (30, 30)])
+def test_ltsf_encode_and_nlinear_decode(ops, T, To):
+    B, C = 7, 64
+    sd = _ltsf_sd(C, T, To)
+    x = torch.rand(B, 2, T, generator=torch.Generator().manual_seed(5))
+    want = R.ltsf_encoder(sd, x)                                    # (B, C, T)
+    we, be = R.stack_individual(sd, "ltsf.nlinear_encoder.encoder_linears.", C)
+    enc = torch.empty(B, T, C, device=DEV)
+    ops.ltsf_encode(x.to(DEV), sd["ltsf.token_proj.weight"][:, :, 0].contiguous().to(DEV), sd["ltsf.token_proj.bias"].to(DEV),
+                    we.permute(1, 2, 0).contiguous().to(DEV), be.t().contiguous().to(DEV),
+                    sd["ltsf.pos_encoding"][0].t().contiguous().to(DEV), enc, B=B, F=2, C=C, T_in=T)
+    torch.testing.assert_close(enc.cpu().permute(0, 2, 1), want, rtol=1e-4, atol=1e-5)
+    wd, bd = R.stack_individual(sd, "ltsf.decoder.decoder_linears.", C)
+    adj = _rand(B, To, C, seed=9)
+    last = want[:, :, -1:]
+    wdec = torch.einsum("cot,bct->bco", wd, want - last) + bd[None] + last + adj.permute(0, 2, 1)
+    dec = torch.empty(B, To, C, device=DEV)
+    ops.nlinear_decode(enc, wd.permute(1, 2, 0).contiguous().to(DEV), bd.t().contiguous().to(DEV), adj.to(DEV), dec, B=B, C=C, T_in=T, T_out=To)
+    torch.testing.assert_close(dec.cpu().permute(0, 2, 1), wdec, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,To", [(5, 25), (300, 50), (1, 1)])
+def test_fusion_head_and_metrics(ops, B, To):
+    C, T = 64, 15
+    fused = _rand(B * To, C, seed=1)
+    p = "ltsf.decoder."
+    sd = {p + "fusion_layer.0.weight": 1 + 0.1 * _rand(C, seed=2), p + "fusion_layer.0.bias": 0.1 * _rand(C, seed=3),
+          p + "fusion_layer.1.weight": _rand(C, C, seed=4, scale=0.125), p + "fusion_layer.1.bias": 0.1 * _rand(C, seed=5),
+          p + "fusion_layer.3.weight": _rand(C, C, seed=6, scale=0.125), p + "fusion_layer.3.bias": 0.1 * _rand(C, seed=7),
+          p + "out_proj.weight": _rand(2, C, seed=8, scale=0.125), p + "out_proj.bias": 0.1 * _rand(2, seed=9)}
+    x = torch.rand(B, 2, T, generator=torch.Generator().manual_seed(10))
+    y = torch.rand(B, 2, To, generator=torch.Generator().manual_seed(11))
+    g = torch.Generator().manual_seed(12)
+    mn = torch.rand(B, 2, generator=g) * 2000
+    ns = torch.stack([mn[:, 0], mn[:, 0] + 100 + 1400 * torch.rand(B, generator=g), mn[:, 1], mn[:, 1] + 5 + 75 * torch.rand(B, generator=g)], 1)
+    f = R.layer_norm(fused, sd[p + "fusion_layer.0.weight"], sd[p + "fusion_layer.0.bias"])
+    f = R.linear(torch.relu(R.linear(f, sd[p + "fusion_layer.1.weight"], sd[p + "fusion_layer.1.bias"])), sd[p + "fusion_layer.3.weight"], sd[p + "fusion_layer.3.bias"])
+    want = R.linear(f, sd[p + "out_proj.weight"], sd[p + "out_proj.bias"]).view(B, To, 2).permute(0, 2, 1) + x[:, :, -1:]
+    dv = {k: v.to(DEV) for k, v in sd.items()}
+    decoded = torch.empty(B, 2, To, device=DEV)
+    metrics = torch.zeros(8, device=DEV)
+    per = torch.empty(B, 2, device=DEV)
+    ops.fusion_head(fused.to(DEV), dv[p + "fusion_layer.0.weight"], dv[p + "fusion_layer.0.bias"], dv[p + "fusion_layer.1.weight"],
+                    dv[p + "fusion_layer.1.bias"], dv[p + "fusion_layer.3.weight"], dv[p + "fusion_layer.3.bias"], dv[p + "out_proj.weight"],
+                    dv[p + "out_proj.bias"], x.to(DEV), decoded, y=y.to(DEV), norm_stat=ns.to(DEV), metrics=metrics, per_scene=per,
+                    B=B, C=C, T_in=T, T_out=To)
+    torch.testing.assert_close(decoded.cpu(), want, rtol=1e-4, atol=1e-5)
+    ade, fde = R.ade_fde(want, y, ns)
+    loss = R.mse_loss(want, y, ns)
+    torch.testing.assert_close(per[:, 0].cpu(), ade, rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(per[:, 1].cpu(), fde, rtol=1e-4, atol=1e-3)
+    m = metrics.cpu()
+    torch.testing.assert_close(m[2], ade.sum(), rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(m[3], fde.sum(), rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(m[4], loss, rtol=1e-4, atol=1e-3)
+    # standalone metrics kernel on the same prediction
+    m2, per2 = torch.zeros(8, device=DEV), torch.empty(B, 2, device=DEV)
+    ops.traj_metrics(decoded, y.to(DEV), ns.to(DEV), m2, per2, B=B, T_out=To)
+    torch.testing.assert_close(per2.cpu(), per.cpu(), rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(m2[:5].cpu(), m[:5], rtol=1e-4, atol=1e-3)

@@ -1,0 +1,73 @@
+"""End-to-end parity of the CUDA forward against the golden vectors minted from the unmodified reference.
+Tolerances are the north-star ones: predicted coordinates rtol 1e-4 (fp32) / 2e-2 (bf16), ADE/FDE within 0.5 %."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from conftest import build_filled_model, load_golden  # noqa: E402
+
+
+def _forward(fix, dtype, keep=True):
+    m = build_filled_model(fix, dtype, "cuda")
+    i = fix["inputs"]
+    out = m.engine().forward(i["x"], i["vision"], i["polygon"], i["poly_len"], i["input_ids"], i["attention_mask"], y=i["y"],
+                             norm_stat=i["norm_stat"], keep_intermediates=keep)
+    torch.cuda.synchronize()
+    return m, {k: (v.float().cpu() if torch.is_tensor(v) else v) for k, v in out.items()}
+
+
+@pytest.mark.parametrize("name", ["tiny_b6", "cfg1_b8", "cfg5_b4"])
+def test_fp32_forward_matches_reference(name, lib_built):
+    fix = load_golden(name)
+    _, o = _forward(fix, "fp32")
+    g = fix["out"]
+    tol = dict(rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(o["poly_emb"], g["poly_emb"], **tol)
+    torch.testing.assert_close(o["enc"], g["enc"], **tol)
+    n = g["final_hidden_head"].shape[0]
+    torch.testing.assert_close(o["final_hidden"][:n], g["final_hidden_head"], rtol=1e-4, atol=2e-4)
+    torch.testing.assert_close(o["final_hidden"].mean(-1), g["final_hidden_rowmean"], **tol)
+    torch.testing.assert_close(o["decoded"], g["decoded"], **tol)
+    torch.testing.assert_close(o["loss"], g["loss"], rtol=1e-4, atol=0)
+    torch.testing.assert_close(o["ade"], g["ade"], rtol=1e-4, atol=1e-2)
+    torch.testing.assert_close(o["fde"], g["fde"], rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("name", ["tiny_b6", "cfg1_b8", "cfg5_b4"])
+def test_bf16_forward_matches_reference(name, lib_built):
+    fix = load_golden(name)
+    _, o = _forward(fix, "bf16")
+    g = fix["out"]
+    torch.testing.assert_close(o["decoded"], g["decoded"], rtol=2e-2, atol=2e-2)
+    ade, fde = float(o["ade"].mean()), float(o["fde"].mean())
+    assert abs(ade - float(g["ade"].mean())) / float(g["ade"].mean()) < 5e-3, (ade, float(g["ade"].mean()))
+    assert abs(fde - float(g["fde"].mean())) / float(g["fde"].mean()) < 5e-3, (fde, float(g["fde"].mean()))
+
+
+def test_public_forward_signature_and_outputs(lib_built):
+    fix = load_golden("tiny_b6")
+    m = build_filled_model(fix, "fp32", "cuda")
+    i = fix["inputs"]
+    dev = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in i.items()}
+    with torch.no_grad():
+        dec = m(dev["x"], dev["vision"], ["ctx"] * 6, dev["polygon"], i["poly_len"], input_ids=dev["input_ids"],
+                attention_mask=dev["attention_mask"], labels=None)
+        loss, dec2 = m(dev["x"], dev["vision"], ["ctx"] * 6, dev["polygon"], i["poly_len"], y=dev["y"], norm_stat=i["norm_stat"],
+                       input_ids=dev["input_ids"], attention_mask=dev["attention_mask"], labels=dev["input_ids"])
+    assert dec.shape == (6, 2, fix["model_cfg"]["out_len"]) and dec.dtype == torch.float32
+    torch.testing.assert_close(dec, dec2)
+    torch.testing.assert_close(loss.cpu(), fix["out"]["loss"], rtol=1e-4, atol=0)
+
+
+def test_scene_independence_and_empty_batch(lib_built):
+    """Scenes are independent rows: a sub-batch must reproduce the same rows bit for bit."""
+    fix = load_golden("tiny_b6")
+    m = build_filled_model(fix, "bf16", "cuda")
+    i = fix["inputs"]
+    e = m.engine()
+    full = e.forward(i["x"], i["vision"], i["polygon"], i["poly_len"], i["input_ids"], i["attention_mask"])["decoded"]
+    sub = e.forward(i["x"][2:5], i["vision"][2:5], i["polygon"][2:5], i["poly_len"][2:5], i["input_ids"][2:5], i["attention_mask"][2:5])["decoded"]
+    assert torch.equal(full[2:5], sub)
+    empty = e.forward(i["x"][:0], i["vision"][:0], i["polygon"][:0], [], i["input_ids"][:0], i["attention_mask"][:0])["decoded"]
+    assert empty.shape == (0, 2, fix["model_cfg"]["out_len"])

@@ -69,49 +69,33 @@ __device__ __forceinline__ void store_from_f(void* p, size_t i, int dtype, float
 
 // ---------------------------------------------------------------------------------------------
 // GEMM epilogue shared by the SIMT fp32 kernel and the tcgen05 bf16 kernel.
-//   v = acc (+bias[n]) (+ sum_k lora_t[m,k] * lora_b[n,k] inside a LoRA column segment)
-//   v = relu(v) if act == RELU          (SwiGLU is applied by the caller on column pairs)
-//   v += residual[m_out, n]
-//   out[m_out, n] = v        with m_out = (m / remap_gi) * remap_go + (m % remap_gi) + remap_off
+//   v = acc (+bias[n]);  v = relu(v) if act == RELU   (SwiGLU is applied by the caller on column pairs)
+//   v += residual[m_out, n];  out[m_out, n] = v   with m_out = (m / remap_gi) * remap_go + m % remap_gi + remap_off
 // ---------------------------------------------------------------------------------------------
 struct EpilogueParams {
-  int M, N;                 // logical output extent (N is post-SwiGLU width when act == SWIGLU)
+  int M, N;                 // logical output extent (N is the post-SwiGLU width when act == SWIGLU)
   void* out; int ldo; int out_dtype;
   const float* bias;
   const void* residual; int ldr; int res_dtype;
   int act;
-  const float* lora_t; int lora_ldt; int lora_r; const float* lora_b;
-  int seg_begin[2], seg_end[2], seg_toff[2];
   int remap_gi, remap_go, remap_off;
-  float out_scale;          // multiplies acc before bias (1.0f default)
 };
 
-__device__ __forceinline__ int remap_row(const EpilogueParams& p, int m) {
-  return p.remap_gi > 0 ? (m / p.remap_gi) * p.remap_go + (m % p.remap_gi) + p.remap_off : m;
+__device__ __forceinline__ int remap_row(int gi, int go, int off, int m) {
+  return gi > 0 ? (m / gi) * go + (m % gi) + off : m;
 }
 
-__device__ __forceinline__ void epilogue_store(const EpilogueParams& p, int m, int n, float v) {
+__device__ __forceinline__ float silu_f(float g) { return g / (1.f + __expf(-g)); }
+
+// Scalar epilogue (SIMT kernel and the ragged edges of the tensor-core kernel).
+__device__ __forceinline__ void epilogue_store(const EpilogueParams& p, int m, int mo, int n, float v) {
   if (m >= p.M || n >= p.N) return;
-  v *= p.out_scale;
   if (p.bias) v += __ldg(p.bias + n);
-  if (p.lora_r > 0) {
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      if (n >= p.seg_begin[s] && n < p.seg_end[s]) {
-        const float* t = p.lora_t + (size_t)m * p.lora_ldt + p.seg_toff[s];
-        const float* b = p.lora_b + (size_t)n * p.lora_r;
-        float a = 0.f;
-        for (int k = 0; k < p.lora_r; ++k) a = fmaf(__ldg(t + k), __ldg(b + k), a);
-        v += a;
-      }
-    }
-  }
   if (p.act == TCAVP_ACT_RELU) v = fmaxf(v, 0.f);
-  const int mo = remap_row(p, m);
   if (p.residual) v += load_as_f(p.residual, (size_t)mo * p.ldr + n, p.res_dtype);
   store_from_f(p.out, (size_t)mo * p.ldo + n, p.out_dtype, v);
 }
 
-__device__ __forceinline__ float silu_f(float g) { return g / (1.f + __expf(-g)); }
+void count_launch();
 
 }  // namespace tcavp

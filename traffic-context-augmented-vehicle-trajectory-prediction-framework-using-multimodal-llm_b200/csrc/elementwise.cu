@@ -1,0 +1,187 @@
+// Small bandwidth-bound helpers: RoPE (in place), RoPE table, text-embedding gather into the fused
+// sequence buffer, row-vector add with row remap, dtype cast, polygon input projection, masked mean.
+#include "common.cuh"
+
+namespace tcavp {
+
+__global__ void rope_table_kernel(float* __restrict__ cs, int L, int half, float theta, int dh) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L * half) return;
+  const int pos = i / half, j = i % half;
+  // HF:86-88: inv_freq = 1 / theta^(2j/dh) in fp32; HF:131-134: angle = pos * inv_freq in fp32
+  const float inv = 1.0f / powf(theta, (float)(2 * j) / (float)dh);
+  const float ang = (float)pos * inv;
+  cs[2 * i] = cosf(ang);
+  cs[2 * i + 1] = sinf(ang);
+}
+
+// One thread per (row, head, 8 consecutive pair indices); q heads then k heads are adjacent in the row.
+template <typename T>
+__global__ void rope_kernel(T* __restrict__ qkv, int rows, int L, int ld, int heads, int dh, const float* __restrict__ cs) {
+  const int half = dh >> 1;
+  const long long total = (long long)rows * heads * half;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % half);
+    const int h = (int)((i / half) % heads);
+    const long long r = i / ((long long)half * heads);
+    const int pos = (int)(r % L);
+    const float c = __ldg(cs + 2 * ((size_t)pos * half + j)), s = __ldg(cs + 2 * ((size_t)pos * half + j) + 1);
+    T* p = qkv + (size_t)r * ld + (size_t)h * dh;
+    const float x1 = Cvt<T>::to_f(p[j]), x2 = Cvt<T>::to_f(p[j + half]);
+    p[j] = Cvt<T>::from_f(x1 * c - x2 * s);          // q*cos + rotate_half(q)*sin, first half: -q[j+half]
+    p[j + half] = Cvt<T>::from_f(x2 * c + x1 * s);   // second half: +q[j]
+  }
+}
+
+__global__ void embed_text_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ amask, const void* __restrict__ embed,
+                                  int embed_dtype, const float* __restrict__ text_mod, void* __restrict__ fused, int fused_dtype,
+                                  int32_t* __restrict__ mask_out, int B, int L_text, int n_img, int H, int vocab) {
+  const int L = n_img + L_text;
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);   // over B * L
+  if (row >= (long long)B * L) return;
+  const int b = (int)(row / L), t = (int)(row % L);
+  if (t < n_img) {
+    if (lane == 0 && mask_out) mask_out[row] = 1;
+    return;
+  }
+  const int j = t - n_img;
+  if (lane == 0 && mask_out) mask_out[row] = amask ? (amask[(size_t)b * L_text + j] != 0) : 1;
+  long long id = ids[(size_t)b * L_text + j];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  for (int c = lane; c < H; c += 32) {
+    const float v = load_as_f(embed, (size_t)id * H + c, embed_dtype) + __ldg(text_mod + c);
+    store_from_f(fused, (size_t)row * H + c, fused_dtype, v);
+  }
+}
+
+__global__ void add_rowvec_kernel(const void* __restrict__ x, const float* __restrict__ rowvec, void* __restrict__ out, int rows,
+                                  int cols, int in_dtype, int out_dtype, int gi, int go, int off) {
+  const long long total = (long long)rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    const float v = load_as_f(x, i, in_dtype) + (rowvec ? __ldg(rowvec + c) : 0.f);
+    store_from_f(out, (size_t)remap_row(gi, go, off, r) * cols + c, out_dtype, v);
+  }
+}
+
+__global__ void cast_kernel(const void* __restrict__ in, int ldi, int in_dtype, void* __restrict__ out, int ldo, int out_dtype,
+                            int rows, int cols, int in_row_mod) {
+  const long long total = (long long)rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i % cols);
+    const long long ri = in_row_mod > 0 ? r % in_row_mod : r;
+    store_from_f(out, (size_t)r * ldo + c, out_dtype, load_as_f(in, (size_t)ri * ldi + c, in_dtype));
+  }
+}
+
+__global__ void poly_embed_kernel(const float* __restrict__ poly, const int32_t* __restrict__ len, const float* __restrict__ w,
+                                  const float* __restrict__ bias, const float* __restrict__ pos, void* __restrict__ out,
+                                  int out_dtype, int32_t* __restrict__ key_mask, int B, int P, int D) {
+  const long long total = (long long)B * P * D;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(i % D);
+    const long long bp = i / D;
+    const int p = (int)(bp % P), b = (int)(bp / P);
+    const float px = __ldg(poly + bp * 2), py = __ldg(poly + bp * 2 + 1);
+    const float v = fmaf(__ldg(w + 2 * d), px, fmaf(__ldg(w + 2 * d + 1), py, __ldg(bias + d))) + __ldg(pos + (size_t)p * D + d);
+    store_from_f(out, i, out_dtype, v);
+    if (d == 0 && key_mask) key_mask[bp] = p < __ldg(len + b);
+  }
+}
+
+__global__ void masked_mean_kernel(const void* __restrict__ x, int in_dtype, const int32_t* __restrict__ len, void* __restrict__ out,
+                                   int out_dtype, int B, int P, int D) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)B * D) return;
+  const int d = (int)(i % D), b = (int)(i / D);
+  int n = __ldg(len + b);
+  n = n < 0 ? 0 : (n > P ? P : n);
+  float s = 0.f;
+  for (int p = 0; p < n; ++p) s += load_as_f(x, ((size_t)b * P + p) * D + d, in_dtype);
+  store_from_f(out, i, out_dtype, n > 0 ? s / (float)n : 0.f);
+}
+
+static int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = (long long)sm_count() * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace tcavp
+
+using namespace tcavp;
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+#define DT_OK(d) ((d) == TCAVP_F32 || (d) == TCAVP_BF16)
+
+extern "C" int tcavp_rope_table(float* cos_sin, int L, int dh, float theta, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(cos_sin && L > 0 && dh > 0 && dh % 2 == 0, "tcavp_rope_table: bad args L=%d dh=%d", L, dh);
+  const int n = L * (dh / 2);
+  rope_table_kernel<<<(n + 255) / 256, 256, 0, STREAM(stream)>>>(cos_sin, L, dh / 2, theta, dh);
+  return check_launch("rope_table_kernel");
+}
+
+extern "C" int tcavp_rope(void* qkv, int rows, int L, int ld, int n_q_heads, int n_k_heads, int dh, const float* cos_sin,
+                          int dtype, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(rows >= 0 && L > 0 && dh > 0 && dh % 2 == 0 && n_q_heads > 0 && n_k_heads >= 0, "tcavp_rope: bad shape");
+  TCAVP_REQUIRE(ld >= (n_q_heads + n_k_heads) * dh, "tcavp_rope: ld %d too small", ld);
+  if (rows == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(qkv && cos_sin && DT_OK(dtype), "tcavp_rope: bad pointer/dtype");
+  const int heads = n_q_heads + n_k_heads;
+  const long long total = (long long)rows * heads * (dh / 2);
+  if (dtype == TCAVP_BF16)
+    rope_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(reinterpret_cast<__nv_bfloat16*>(qkv), rows, L, ld, heads, dh, cos_sin);
+  else
+    rope_kernel<float><<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(reinterpret_cast<float*>(qkv), rows, L, ld, heads, dh, cos_sin);
+  return check_launch("rope_kernel");
+}
+
+extern "C" int tcavp_embed_text(const int64_t* ids, const int64_t* attn_mask, const void* embed, int embed_dtype,
+                                const float* text_mod, void* fused, int fused_dtype, int32_t* mask_out, int B, int L_text,
+                                int n_img, int H, int vocab, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(B >= 0 && L_text >= 0 && n_img >= 0 && H > 0 && vocab > 0, "tcavp_embed_text: bad shape");
+  if (B == 0 || n_img + L_text == 0) return TCAVP_OK;
+  TCAVP_REQUIRE((ids || L_text == 0) && embed && text_mod && fused && DT_OK(embed_dtype) && DT_OK(fused_dtype), "tcavp_embed_text: bad pointer/dtype");
+  const long long rows = (long long)B * (n_img + L_text);
+  embed_text_kernel<<<(int)((rows + 7) / 8), 256, 0, STREAM(stream)>>>(ids, attn_mask, embed, embed_dtype, text_mod, fused, fused_dtype,
+                                                                        mask_out, B, L_text, n_img, H, vocab);
+  return check_launch("embed_text_kernel");
+}
+
+extern "C" int tcavp_add_rowvec(const void* x, const float* rowvec, void* out, int rows, int cols, int in_dtype, int out_dtype,
+                                int remap_gi, int remap_go, int remap_off, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(rows >= 0 && cols > 0, "tcavp_add_rowvec: bad shape");
+  if (rows == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(x && out && DT_OK(in_dtype) && DT_OK(out_dtype), "tcavp_add_rowvec: bad pointer/dtype");
+  add_rowvec_kernel<<<grid_for((long long)rows * cols, 256), 256, 0, STREAM(stream)>>>(x, rowvec, out, rows, cols, in_dtype, out_dtype, remap_gi, remap_go, remap_off);
+  return check_launch("add_rowvec_kernel");
+}
+
+extern "C" int tcavp_cast(const void* in, int ldi, int in_dtype, void* out, int ldo, int out_dtype, int rows, int cols,
+                          int in_row_mod, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(rows >= 0 && cols > 0 && ldi >= cols && ldo >= cols, "tcavp_cast: bad shape");
+  if (rows == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(in && out && DT_OK(in_dtype) && DT_OK(out_dtype), "tcavp_cast: bad pointer/dtype");
+  cast_kernel<<<grid_for((long long)rows * cols, 256), 256, 0, STREAM(stream)>>>(in, ldi, in_dtype, out, ldo, out_dtype, rows, cols, in_row_mod);
+  return check_launch("cast_kernel");
+}
+
+extern "C" int tcavp_poly_embed(const float* polygon, const int32_t* len, const float* w, const float* bias, const float* pos,
+                                void* out, int out_dtype, int32_t* key_mask, int B, int P, int D, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(B >= 0 && P > 0 && D > 0, "tcavp_poly_embed: bad shape");
+  if (B == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(polygon && len && w && bias && pos && out && DT_OK(out_dtype), "tcavp_poly_embed: bad pointer/dtype");
+  poly_embed_kernel<<<grid_for((long long)B * P * D, 256), 256, 0, STREAM(stream)>>>(polygon, len, w, bias, pos, out, out_dtype, key_mask, B, P, D);
+  return check_launch("poly_embed_kernel");
+}
+
+extern "C" int tcavp_masked_mean(const void* x, int in_dtype, const int32_t* len, void* out, int out_dtype, int B, int P, int D,
+                                 tcavp_stream_t stream) {
+  TCAVP_REQUIRE(B >= 0 && P > 0 && D > 0, "tcavp_masked_mean: bad shape");
+  if (B == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(x && len && out && DT_OK(in_dtype) && DT_OK(out_dtype), "tcavp_masked_mean: bad pointer/dtype");
+  const long long n = (long long)B * D;
+  masked_mean_kernel<<<(int)((n + 255) / 256), 256, 0, STREAM(stream)>>>(x, in_dtype, len, out, out_dtype, B, P, D);
+  return check_launch("masked_mean_kernel");
+}

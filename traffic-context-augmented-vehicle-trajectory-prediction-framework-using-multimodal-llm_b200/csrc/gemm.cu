@@ -1,0 +1,482 @@
+// tcavp_gemm: out = act(A . W^T + bias) + residual, with row remap.
+//
+//   bf16 : persistent, warp-specialised tcgen05 kernel.  One elected thread issues TMA loads
+//          (cp.async.bulk.tensor, 128-byte swizzle) into a multi-stage shared-memory ring, one elected
+//          thread issues tcgen05.mma (UMMA 128 x BLOCK_N x 16, bf16 -> fp32) into one of two TMEM
+//          accumulator buffers, four epilogue warps drain the other buffer with tcgen05.ld and apply the
+//          fused epilogue, so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   fp32 : SIMT FFMA kernel with exact fp32 accumulation (the rtol 1e-4 parity mode; no TF32).
+//
+// LoRA (peft lora.Linear, reference scripts/train.py:432-440) is expressed by the caller as extra K columns
+// ([x | x.A^T] . [W | (alpha/r) B]^T), i.e. it accumulates in the same TMEM tile as the base product.
+#include <cuda.h>
+#include <mutex>
+#include "common.cuh"
+
+namespace tcavp {
+namespace tc {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one SWIZZLE_128B atom row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;  // two accumulator buffers
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// K-major operand tile in shared memory, SWIZZLE_128B: rows are 128 bytes, 8-row groups are 1024 bytes apart.
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);   // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M x N tile.
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// Epilogue of 32 accumulator columns [nacc0, nacc0+32) of row m for one thread.
+__device__ __forceinline__ void epilogue_chunk(const EpilogueParams& p, int m, int nacc0, const uint32_t (&r)[32],
+                                               bool vec_out, bool vec_res) {
+  if (m >= p.M) return;
+  const int mo = remap_row(p.remap_gi, p.remap_go, p.remap_off, m);
+  float o[32];
+  int cnt, n0;
+  if (p.act == TCAVP_ACT_SWIGLU) {
+    cnt = 16;
+    n0 = nacc0 >> 1;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] = silu_f(__uint_as_float(r[2 * j])) * __uint_as_float(r[2 * j + 1]);
+  } else {
+    cnt = 32;
+    n0 = nacc0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(r[j]);
+  }
+  if (n0 >= p.N) return;
+  const bool full = (n0 + cnt <= p.N);
+  if (p.bias) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < cnt && n0 + j < p.N) o[j] += __ldg(p.bias + n0 + j);
+  }
+  if (p.act == TCAVP_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.f);
+  }
+  if (p.residual) {
+    if (vec_res && full) {
+      if (p.res_dtype == TCAVP_BF16) {
+        const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + (size_t)mo * p.ldr + n0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (q * 8 < cnt) {
+            uint4 u = rp[q];
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float2 f = __bfloat1622float2(h[e]);
+              o[q * 8 + 2 * e] += f.x;
+              o[q * 8 + 2 * e + 1] += f.y;
+            }
+          }
+        }
+      } else {
+        const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + (size_t)mo * p.ldr + n0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (q * 4 < cnt) {
+            float4 f = rp[q];
+            o[q * 4] += f.x; o[q * 4 + 1] += f.y; o[q * 4 + 2] += f.z; o[q * 4 + 3] += f.w;
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < cnt && n0 + j < p.N) o[j] += load_as_f(p.residual, (size_t)mo * p.ldr + n0 + j, p.res_dtype);
+    }
+  }
+  if (vec_out && full) {
+    if (p.out_dtype == TCAVP_BF16) {
+      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)mo * p.ldo + n0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (q * 8 < cnt) {
+          uint4 u;
+          u.x = pack_bf16(o[q * 8], o[q * 8 + 1]);
+          u.y = pack_bf16(o[q * 8 + 2], o[q * 8 + 3]);
+          u.z = pack_bf16(o[q * 8 + 4], o[q * 8 + 5]);
+          u.w = pack_bf16(o[q * 8 + 6], o[q * 8 + 7]);
+          op[q] = u;
+        }
+      }
+    } else {
+      float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)mo * p.ldo + n0);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (q * 4 < cnt) op[q] = make_float4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < cnt && n0 + j < p.N) store_from_f(p.out, (size_t)mo * p.ldo + n0 + j, p.out_dtype, o[j]);
+  }
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, EpilogueParams ep,
+               int M, int Nacc, int K, int vec_out, int vec_res) {
+  using C = Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_base + C::STAGES * A_STAGE_BYTES;
+  const uint32_t bars = smem_base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t full_bar = bars;                         // STAGES x 8 bytes
+  const uint32_t empty_bar = bars + 8 * C::STAGES;        // STAGES x 8 bytes
+  const uint32_t tmem_full_bar = bars + 16 * C::STAGES;   // 2 x 8
+  const uint32_t tmem_empty_bar = tmem_full_bar + 16;     // 2 x 8
+  const uint32_t tmem_slot = tmem_empty_bar + 16;         // 4 bytes: TMEM base address
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_n = (Nacc + BLOCK_N - 1) / BLOCK_N;
+  const int tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tmem_full_bar + 8 * s, 1);
+      mbar_init(tmem_empty_bar + 8 * s, 4);   // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * BLOCK_M;
+        const int n0 = (tile % tiles_n) * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          mbar_expect_tx(full_bar + 8 * stage, C::STAGE_BYTES);
+          tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tma_a, full_bar + 8 * stage, kb * BLOCK_K, m0);
+          tma_load_2d(smem_b + stage * C::B_STAGE_BYTES, &tma_b, full_bar + 8 * stage, kb * BLOCK_K, n0);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(tmem_empty_bar + 8 * acc, ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar + 8 * stage, phase);
+          tc_fence_after();
+          const int k_left = K - kb * BLOCK_K;
+          const int ksteps = k_left >= BLOCK_K ? BLOCK_K / UMMA_K : (k_left + UMMA_K - 1) / UMMA_K;
+          const uint32_t a_addr = smem_a + stage * A_STAGE_BYTES;
+          const uint32_t b_addr = smem_b + stage * C::B_STAGE_BYTES;
+          for (int k = 0; k < ksteps; ++k) {
+            umma_bf16(tmem_d, umma_smem_desc(a_addr + k * UMMA_K * 2), umma_smem_desc(b_addr + k * UMMA_K * 2), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar + 8 * stage);   // frees the smem slot once the MMAs above retire
+          if (kb == num_kb - 1) umma_commit(tmem_full_bar + 8 * acc);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;   // TMEM lanes [32*quarter, +32) are the ones this warp may read
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int m0 = (tile / tiles_n) * BLOCK_M;
+      const int n0 = (tile % tiles_n) * BLOCK_N;
+      mbar_wait(tmem_full_bar + 8 * acc, (it >> 1) & 1);
+      tc_fence_after();
+      const int m = m0 + quarter * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        if (n0 + c * 32 >= Nacc) break;   // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + c * 32, r);
+        epilogue_chunk(ep, m, n0 + c * 32, r, vec_out != 0, vec_res != 0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar + 8 * acc);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: TMA descriptors through the driver entry point (no link-time dependency on libcuda)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// rows x cols bf16 matrix with leading dimension ld; box = box_rows x 64 columns, 128-byte swizzle.
+static int make_map(CUtensorMap* map, const void* base, int rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+    return TCAVP_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld);
+    return TCAVP_ERR_CUDA;
+  }
+  return TCAVP_OK;
+}
+
+template <int BLOCK_N>
+static int launch_tc(const tcavp_gemm_args& a, const EpilogueParams& ep, cudaStream_t stream) {
+  using C = Cfg<BLOCK_N>;
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, a.A, a.M, a.K, a.lda, BLOCK_M);
+  if (rc) return rc;
+  rc = make_map(&mb, a.W, a.N, a.K, a.ldw, BLOCK_N);
+  if (rc) return rc;
+  TCAVP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  const int tiles = ((a.M + BLOCK_M - 1) / BLOCK_M) * ((a.N + BLOCK_N - 1) / BLOCK_N);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  const size_t osz = ep.out_dtype == TCAVP_BF16 ? 2 : 4, rsz = ep.res_dtype == TCAVP_BF16 ? 2 : 4;
+  const int vec_out = ((size_t)ep.ldo * osz) % 16 == 0 && (reinterpret_cast<uintptr_t>(ep.out) % 16) == 0;
+  const int vec_res = ep.residual && ((size_t)ep.ldr * rsz) % 16 == 0 && (reinterpret_cast<uintptr_t>(ep.residual) % 16) == 0;
+  gemm_tc_kernel<BLOCK_N><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ma, mb, ep, a.M, a.N, a.K, vec_out, vec_res);
+  return check_launch("gemm_tc_kernel");
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------------------------------------
+// fp32 SIMT kernel: 64x64 output tile, 16-deep K slices, 4x4 outputs per thread
+// ------------------------------------------------------------------------------------------------
+namespace simt {
+constexpr int BM = 64, BN = 64, BK = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, int ldw,
+                                                        EpilogueParams ep, int M, int Nacc, int K) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Ws[BK][BN + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = threadIdx.x + i * 256;      // 0..1023
+      const int r = e >> 4, c = e & 15;         // row within tile, k within slice
+      const int gm = m0 + r, gn = n0 + r, gk = k0 + c;
+      As[c][r] = (gm < M && gk < K) ? Cvt<T>::to_f(A[(size_t)gm * lda + gk]) : 0.f;
+      Ws[c][r] = (gn < Nacc && gk < K) ? Cvt<T>::to_f(W[(size_t)gn * ldw + gk]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[4], w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[j] = Ws[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    const int mo = remap_row(ep.remap_gi, ep.remap_go, ep.remap_off, m);
+    const int n = n0 + tx * 4;
+    if (ep.act == TCAVP_ACT_SWIGLU) {
+      epilogue_store(ep, m, mo, n / 2, silu_f(acc[i][0]) * acc[i][1]);
+      epilogue_store(ep, m, mo, n / 2 + 1, silu_f(acc[i][2]) * acc[i][3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) epilogue_store(ep, m, mo, n + j, acc[i][j]);
+    }
+  }
+}
+}  // namespace simt
+}  // namespace tcavp
+
+extern "C" int tcavp_gemm(const tcavp_gemm_args* a, tcavp_stream_t stream_) {
+  using namespace tcavp;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  TCAVP_REQUIRE(a != nullptr, "tcavp_gemm: null args");
+  TCAVP_REQUIRE(a->M >= 0 && a->N > 0 && a->K > 0, "tcavp_gemm: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
+  if (a->M == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(a->A && a->W && a->out, "tcavp_gemm: null A/W/out");
+  TCAVP_REQUIRE(a->lda >= a->K && a->ldw >= a->K, "tcavp_gemm: lda/ldw smaller than K");
+  TCAVP_REQUIRE(a->act == TCAVP_ACT_NONE || a->act == TCAVP_ACT_RELU || a->act == TCAVP_ACT_SWIGLU, "tcavp_gemm: bad act %d", a->act);
+  TCAVP_REQUIRE(a->act != TCAVP_ACT_SWIGLU || (a->N % 2 == 0), "tcavp_gemm: SwiGLU needs an even number of interleaved rows");
+  TCAVP_REQUIRE(a->out_dtype == TCAVP_F32 || a->out_dtype == TCAVP_BF16, "tcavp_gemm: bad out_dtype");
+  TCAVP_REQUIRE(!a->residual || a->res_dtype == TCAVP_F32 || a->res_dtype == TCAVP_BF16, "tcavp_gemm: bad res_dtype");
+  EpilogueParams ep;
+  ep.M = a->M;
+  ep.N = a->act == TCAVP_ACT_SWIGLU ? a->N / 2 : a->N;
+  ep.out = a->out; ep.ldo = a->ldo; ep.out_dtype = a->out_dtype;
+  ep.bias = a->bias;
+  ep.residual = a->residual; ep.ldr = a->ldr; ep.res_dtype = a->res_dtype;
+  ep.act = a->act;
+  ep.remap_gi = a->remap_gi; ep.remap_go = a->remap_go; ep.remap_off = a->remap_off;
+  TCAVP_REQUIRE(ep.ldo >= ep.N, "tcavp_gemm: ldo %d < output width %d", ep.ldo, ep.N);
+  TCAVP_REQUIRE(!ep.residual || ep.ldr >= ep.N, "tcavp_gemm: ldr too small");
+
+  if (a->in_dtype == TCAVP_BF16) {
+    TCAVP_REQUIRE(a->K % 8 == 0 && a->lda % 8 == 0 && a->ldw % 8 == 0, "tcavp_gemm(bf16): K, lda, ldw must be multiples of 8 (K=%d lda=%d ldw=%d)", a->K, a->lda, a->ldw);
+    TCAVP_REQUIRE(reinterpret_cast<uintptr_t>(a->A) % 16 == 0 && reinterpret_cast<uintptr_t>(a->W) % 16 == 0, "tcavp_gemm(bf16): A and W must be 16-byte aligned");
+    if (a->N <= 32) return tc::launch_tc<32>(*a, ep, stream);
+    if (a->N <= 64) return tc::launch_tc<64>(*a, ep, stream);
+    if (a->N <= 128) return tc::launch_tc<128>(*a, ep, stream);
+    return tc::launch_tc<256>(*a, ep, stream);
+  }
+  if (a->in_dtype == TCAVP_F32) {
+    dim3 grid((a->N + simt::BN - 1) / simt::BN, (a->M + simt::BM - 1) / simt::BM);
+    simt::gemm_simt_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(a->A), a->lda,
+                                                            reinterpret_cast<const float*>(a->W), a->ldw, ep, a->M, a->N, a->K);
+    return check_launch("gemm_simt_kernel");
+  }
+  return fail_arg("tcavp_gemm: unsupported in_dtype %d", a->in_dtype);
+}

@@ -1,0 +1,280 @@
+// Temporal (LTSF) kernels: token_proj + NLinear encoder + positional add, NLinear decoder (+lane adjust),
+// and the fusion head (LayerNorm -> MLP -> out_proj -> last-position residual) fused with the
+// de-normalised loss / ADE / FDE reduction.  All fp32 math; weights are pre-permuted at pack time so the
+// channel index is the fastest-varying one and every global access is coalesced over channels.
+#include "common.cuh"
+
+namespace tcavp {
+
+constexpr int MAX_T_IN = 64;
+
+// reference scripts/train.py:837 (token_proj), 701-716 (NLinear encoder), 839 (+pos_encoding)
+//   we : [T_in(t), T_in(s), C]   be, pos : [T_in, C]   wt : [C, F]   enc : (B, T_in, C)
+__global__ void __launch_bounds__(256) ltsf_encode_kernel(const float* __restrict__ x, const float* __restrict__ wt,
+                                                          const float* __restrict__ bt, const float* __restrict__ we,
+                                                          const float* __restrict__ be, const float* __restrict__ pos,
+                                                          void* __restrict__ enc, int out_dtype, int B, int F, int C, int T) {
+  const long long total = (long long)B * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long b = i / C;
+    float xp[MAX_T_IN];
+#pragma unroll 1
+    for (int s = 0; s < T; ++s) {
+      float v = __ldg(bt + c);
+      for (int f = 0; f < F; ++f) v = fmaf(__ldg(wt + c * F + f), __ldg(x + ((size_t)b * F + f) * T + s), v);
+      xp[s] = v;
+    }
+    const float last = xp[T - 1];
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) {
+      float acc = __ldg(be + (size_t)t * C + c);
+      for (int s = 0; s < T; ++s) acc = fmaf(__ldg(we + ((size_t)t * T + s) * C + c), xp[s] - last, acc);
+      acc += last + __ldg(pos + (size_t)t * C + c);
+      store_from_f(enc, ((size_t)b * T + t) * C + c, out_dtype, acc);
+    }
+  }
+}
+
+// reference scripts/train.py:769-785.  wd : [T_out, T_in, C], bd : [T_out, C]; enc (B,T_in,C); dec (B,T_out,C)
+__global__ void __launch_bounds__(256) nlinear_decode_kernel(const void* __restrict__ enc, int enc_dtype, const float* __restrict__ wd,
+                                                             const float* __restrict__ bd, const void* __restrict__ adj, int adj_dtype,
+                                                             void* __restrict__ dec, int out_dtype, int B, int C, int T, int To) {
+  const long long total = (long long)B * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long b = i / C;
+    float e[MAX_T_IN];
+#pragma unroll 1
+    for (int s = 0; s < T; ++s) e[s] = load_as_f(enc, ((size_t)b * T + s) * C + c, enc_dtype);
+    const float last = e[T - 1];
+#pragma unroll 1
+    for (int t = 0; t < To; ++t) {
+      float acc = __ldg(bd + (size_t)t * C + c);
+      for (int s = 0; s < T; ++s) acc = fmaf(__ldg(wd + ((size_t)t * T + s) * C + c), e[s] - last, acc);
+      acc += last;
+      const size_t o = ((size_t)b * To + t) * C + c;
+      if (adj) acc += load_as_f(adj, o, adj_dtype);
+      store_from_f(dec, o, out_dtype, acc);
+    }
+  }
+}
+
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += scratch[w];
+  return t;
+}
+
+// Per-scene error statistics shared by fusion_head and traj_metrics.  Thread `t` owns time step t.
+//   sq_x, sq_y: squared de-normalised errors (MSE numerators, train.py:954-961)
+//   dist      : sqrt(dx^2 + dy^2)   (train.py:1318-1320)
+__device__ __forceinline__ void scene_error(float px, float py, float gx, float gy, const float* ns, float& sqx, float& sqy, float& dist) {
+  const float rx = ns[1] - ns[0], ry = ns[3] - ns[2];
+  const float dx = (px * rx + ns[0]) - (gx * rx + ns[0]);
+  const float dy = (py * ry + ns[2]) - (gy * ry + ns[2]);
+  sqx = dx * dx;
+  sqy = dy * dy;
+  dist = sqrtf(dx * dx + dy * dy);
+}
+
+// reference scripts/train.py:801-805 (fusion_layer, out_proj), 941-943 (+last input position), 945-962, 1302-1322.
+// One block per scene (grid-stride); warp w handles time steps w, w+8, ...; C <= 128, C % 32 == 0.
+// w1t / w2t are the transposed 64x64 weights ([in][out]) staged in shared memory: lanes read consecutive
+// outputs (conflict-free) while the input activation is a broadcast.
+template <int CPL>  // channels per lane = C / 32
+__global__ void __launch_bounds__(256) fusion_head_kernel(const void* __restrict__ fused, int in_dtype, const float* __restrict__ ln_w,
+                                                          const float* __restrict__ ln_b, const float* __restrict__ w1,
+                                                          const float* __restrict__ b1, const float* __restrict__ w2,
+                                                          const float* __restrict__ b2, const float* __restrict__ wo,
+                                                          const float* __restrict__ bo, const float* __restrict__ x,
+                                                          float* __restrict__ decoded, const float* __restrict__ y,
+                                                          const float* __restrict__ norm_stat, float* __restrict__ metrics,
+                                                          float* __restrict__ per_scene, int B, int T_in, int T_out) {
+  constexpr int C = CPL * 32;
+  extern __shared__ float sm[];
+  float* w1t = sm;                 // [C][C] : w1t[i*C + o] = w1[o*C + i]
+  float* w2t = w1t + C * C;
+  float* act = w2t + C * C;        // [8 warps][C]
+  float* red = act + 8 * C;        // [8][4]
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x) {
+    const int o = i / C, k = i % C;
+    w1t[k * C + o] = __ldg(w1 + i);
+    w2t[k * C + o] = __ldg(w2 + i);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* my = act + warp * C;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    float s_sqx = 0.f, s_sqy = 0.f, s_dist = 0.f, s_fde = 0.f;
+    for (int t = warp; t < T_out; t += 8) {
+      const size_t row = (size_t)b * T_out + t;
+      float v[CPL];
+      float s = 0.f;
+#pragma unroll
+      for (int e = 0; e < CPL; ++e) {
+        v[e] = load_as_f(fused, row * C + lane + 32 * e, in_dtype);
+        s += v[e];
+      }
+      const float mean = warp_sum(s) / C;
+      float q = 0.f;
+#pragma unroll
+      for (int e = 0; e < CPL; ++e) q += (v[e] - mean) * (v[e] - mean);
+      const float rstd = rsqrtf(warp_sum(q) / C + 1e-5f);
+#pragma unroll
+      for (int e = 0; e < CPL; ++e) {
+        const int c = lane + 32 * e;
+        my[c] = (v[e] - mean) * rstd * __ldg(ln_w + c) + __ldg(ln_b + c);
+      }
+      __syncwarp();
+      float h[CPL];
+#pragma unroll
+      for (int e = 0; e < CPL; ++e) h[e] = __ldg(b1 + lane + 32 * e);
+      for (int k = 0; k < C; ++k) {
+        const float a = my[k];
+#pragma unroll
+        for (int e = 0; e < CPL; ++e) h[e] = fmaf(w1t[k * C + lane + 32 * e], a, h[e]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int e = 0; e < CPL; ++e) my[lane + 32 * e] = fmaxf(h[e], 0.f);
+      __syncwarp();
+#pragma unroll
+      for (int e = 0; e < CPL; ++e) h[e] = __ldg(b2 + lane + 32 * e);
+      for (int k = 0; k < C; ++k) {
+        const float a = my[k];
+#pragma unroll
+        for (int e = 0; e < CPL; ++e) h[e] = fmaf(w2t[k * C + lane + 32 * e], a, h[e]);
+      }
+      __syncwarp();
+      float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+      for (int e = 0; e < CPL; ++e) {
+        const int c = lane + 32 * e;
+        o0 = fmaf(__ldg(wo + c), h[e], o0);
+        o1 = fmaf(__ldg(wo + C + c), h[e], o1);
+      }
+      o0 = warp_sum(o0) + __ldg(bo) + __ldg(x + ((size_t)b * 2 + 0) * T_in + T_in - 1);
+      o1 = warp_sum(o1) + __ldg(bo + 1) + __ldg(x + ((size_t)b * 2 + 1) * T_in + T_in - 1);
+      if (lane == 0) {
+        decoded[((size_t)b * 2 + 0) * T_out + t] = o0;
+        decoded[((size_t)b * 2 + 1) * T_out + t] = o1;
+        if (y) {
+          float sqx, sqy, dist;
+          scene_error(o0, o1, y[((size_t)b * 2 + 0) * T_out + t], y[((size_t)b * 2 + 1) * T_out + t], norm_stat + (size_t)b * 4, sqx, sqy, dist);
+          s_sqx += sqx; s_sqy += sqy; s_dist += dist;
+          if (t == T_out - 1) s_fde = dist;
+        }
+      }
+    }
+    if (y) {   // uniform across the block
+      if (lane == 0) {
+        red[warp * 4 + 0] = s_sqx; red[warp * 4 + 1] = s_sqy; red[warp * 4 + 2] = s_dist; red[warp * 4 + 3] = s_fde;
+      }
+      __syncthreads();
+      if (threadIdx.x < 4) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w * 4 + threadIdx.x];
+        if (threadIdx.x == 2) t /= (float)T_out;                    // ADE_b
+        if (threadIdx.x >= 2 && per_scene) per_scene[(size_t)b * 2 + threadIdx.x - 2] = t;
+        atomicAdd(metrics + threadIdx.x, t);
+      } else if (threadIdx.x == 4) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w * 4] + red[w * 4 + 1];
+        atomicAdd(metrics + 4, t / ((float)B * (float)T_out));      // MSE_x + MSE_y (train.py:959-961)
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) traj_metrics_kernel(const float* __restrict__ decoded, const float* __restrict__ y,
+                                                           const float* __restrict__ norm_stat, float* __restrict__ metrics,
+                                                           float* __restrict__ per_scene, int B, int T_out) {
+  __shared__ float scratch[8];
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    float sqx = 0.f, sqy = 0.f, dist = 0.f, fde = 0.f;
+    for (int t = threadIdx.x; t < T_out; t += blockDim.x) {
+      float a, c, d;
+      scene_error(decoded[((size_t)b * 2) * T_out + t], decoded[((size_t)b * 2 + 1) * T_out + t], y[((size_t)b * 2) * T_out + t],
+                  y[((size_t)b * 2 + 1) * T_out + t], norm_stat + (size_t)b * 4, a, c, d);
+      sqx += a; sqy += c; dist += d;
+      if (t == T_out - 1) fde = d;
+    }
+    sqx = block_sum(sqx, scratch);
+    sqy = block_sum(sqy, scratch);
+    dist = block_sum(dist, scratch);
+    fde = block_sum(fde, scratch);
+    if (threadIdx.x == 0) {
+      const float ade = dist / (float)T_out;
+      if (per_scene) { per_scene[(size_t)b * 2] = ade; per_scene[(size_t)b * 2 + 1] = fde; }
+      atomicAdd(metrics + 0, sqx); atomicAdd(metrics + 1, sqy); atomicAdd(metrics + 2, ade); atomicAdd(metrics + 3, fde);
+      atomicAdd(metrics + 4, (sqx + sqy) / ((float)B * (float)T_out));
+    }
+  }
+}
+
+}  // namespace tcavp
+
+using namespace tcavp;
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+#define DT_OK(d) ((d) == TCAVP_F32 || (d) == TCAVP_BF16)
+
+extern "C" int tcavp_ltsf_encode(const float* x, const float* wt, const float* bt, const float* we, const float* be,
+                                 const float* pos, void* enc, int out_dtype, int B, int F, int C, int T_in, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(B >= 0 && F > 0 && C > 0 && T_in > 0 && T_in <= MAX_T_IN, "tcavp_ltsf_encode: bad shape (T_in=%d, max %d)", T_in, MAX_T_IN);
+  if (B == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(x && wt && bt && we && be && pos && enc && DT_OK(out_dtype), "tcavp_ltsf_encode: bad pointer/dtype");
+  const long long total = (long long)B * C;
+  ltsf_encode_kernel<<<(int)((total + 127) / 128), 128, 0, STREAM(stream)>>>(x, wt, bt, we, be, pos, enc, out_dtype, B, F, C, T_in);
+  return check_launch("ltsf_encode_kernel");
+}
+
+extern "C" int tcavp_nlinear_decode(const void* enc, int enc_dtype, const float* wd, const float* bd, const void* lane_adj,
+                                    int adj_dtype, void* dec, int out_dtype, int B, int C, int T_in, int T_out, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(B >= 0 && C > 0 && T_in > 0 && T_in <= MAX_T_IN && T_out > 0, "tcavp_nlinear_decode: bad shape");
+  if (B == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(enc && wd && bd && dec && DT_OK(enc_dtype) && DT_OK(out_dtype) && (!lane_adj || DT_OK(adj_dtype)), "tcavp_nlinear_decode: bad pointer/dtype");
+  const long long total = (long long)B * C;
+  nlinear_decode_kernel<<<(int)((total + 127) / 128), 128, 0, STREAM(stream)>>>(enc, enc_dtype, wd, bd, lane_adj, adj_dtype, dec, out_dtype, B, C, T_in, T_out);
+  return check_launch("nlinear_decode_kernel");
+}
+
+extern "C" int tcavp_fusion_head(const void* fused, int in_dtype, const float* ln_w, const float* ln_b, const float* w1,
+                                 const float* b1, const float* w2, const float* b2, const float* wo, const float* bo,
+                                 const float* x, float* decoded, const float* y, const float* norm_stat, float* metrics,
+                                 float* per_scene, int B, int C, int T_in, int T_out, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(B >= 0 && T_in > 0 && T_out > 0, "tcavp_fusion_head: bad shape");
+  TCAVP_REQUIRE(C == 32 || C == 64 || C == 128, "tcavp_fusion_head: d_model must be 32, 64 or 128 (got %d)", C);
+  if (B == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(fused && ln_w && ln_b && w1 && b1 && w2 && b2 && wo && bo && x && decoded && DT_OK(in_dtype), "tcavp_fusion_head: bad pointer/dtype");
+  TCAVP_REQUIRE(!y || (norm_stat && metrics), "tcavp_fusion_head: y needs norm_stat and metrics");
+  const size_t smem = (size_t)(2 * C * C + 8 * C + 32) * sizeof(float);
+  const int grid = B < sm_count() * 2 ? B : sm_count() * 2;
+#define LAUNCH(CPL)                                                                                                            \
+  do {                                                                                                                         \
+    TCAVP_CUDA(cudaFuncSetAttribute(fusion_head_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+    fusion_head_kernel<CPL><<<grid, 256, smem, STREAM(stream)>>>(fused, in_dtype, ln_w, ln_b, w1, b1, w2, b2, wo, bo, x, decoded, y, \
+                                                                 norm_stat, metrics, per_scene, B, T_in, T_out);               \
+  } while (0)
+  if (C == 32) LAUNCH(1);
+  else if (C == 64) LAUNCH(2);
+  else LAUNCH(4);
+#undef LAUNCH
+  return check_launch("fusion_head_kernel");
+}
+
+extern "C" int tcavp_traj_metrics(const float* decoded, const float* y, const float* norm_stat, float* metrics, float* per_scene,
+                                  int B, int T_out, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(B >= 0 && T_out > 0, "tcavp_traj_metrics: bad shape");
+  if (B == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(decoded && y && norm_stat && metrics, "tcavp_traj_metrics: null pointer");
+  const int grid = B < sm_count() * 8 ? B : sm_count() * 8;
+  traj_metrics_kernel<<<grid, 128, 0, STREAM(stream)>>>(decoded, y, norm_stat, metrics, per_scene, B, T_out);
+  return check_launch("traj_metrics_kernel");
+}

@@ -1,0 +1,350 @@
+"""Forward engine: packs the reference-layout parameters into device buffers laid out for the kernels
+(fused QKV with the LoRA K-extension, interleaved gate/up, channel-contiguous NLinear weights, (t,c)-ordered
+lane_fc / post_mlp) and drives libtcavp.so over one CUDA stream.  No torch arithmetic on the data path."""
+import torch
+
+from . import ops
+
+_ACT = {"bf16": torch.bfloat16, "fp32": torch.float32}
+
+
+def _f32(t, dev):
+    return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+class _Lin:
+    """Packed linear: weight in the activation dtype ([N, K] row-major), bias in fp32."""
+    __slots__ = ("w", "b", "N", "K")
+
+    def __init__(self, w, b, act, dev):
+        self.w = w.detach().to(device=dev, dtype=act).contiguous()
+        self.b = None if b is None else _f32(b, dev)
+        self.N, self.K = self.w.shape
+
+
+class Engine:
+    def __init__(self, model, compute_dtype="bf16"):
+        p0 = next(model.ltsf.parameters())
+        self.dev = dev = p0.device   # packing works anywhere (host-side tests); forward() requires CUDA
+        self.act = act = _ACT[compute_dtype]
+        self.model_hp = dict(model.hparams)
+        self.T_in, self.T_out, self.C = model.seq_len, model.out_len, model.d_model
+        with torch.no_grad():
+            self._pack_poly(model.lane_polygon_encoder)
+            self._pack_qformer(model.mllm)
+            self._pack_llm(model.mllm)
+            self._pack_ltsf(model.ltsf)
+        self._rope = {}
+
+    # ---- packing ----------------------------------------------------------------------------------
+    def _mha(self, m):
+        E = m.embed_dim
+        return dict(qkv=_Lin(m.in_proj_weight, m.in_proj_bias, self.act, self.dev),
+                    q=_Lin(m.in_proj_weight[:E], m.in_proj_bias[:E], self.act, self.dev),
+                    kv=_Lin(m.in_proj_weight[E:], m.in_proj_bias[E:], self.act, self.dev),
+                    out=_Lin(m.out_proj.weight, m.out_proj.bias, self.act, self.dev), E=E, heads=m.num_heads)
+
+    def _ln(self, m):
+        return (_f32(m.weight, self.dev), _f32(m.bias, self.dev), m.eps)
+
+    def _enc_layer(self, l):
+        return dict(sa=self._mha(l.self_attn), l1=_Lin(l.linear1.weight, l.linear1.bias, self.act, self.dev),
+                    l2=_Lin(l.linear2.weight, l.linear2.bias, self.act, self.dev), n1=self._ln(l.norm1), n2=self._ln(l.norm2))
+
+    def _dec_layer(self, l):
+        d = self._enc_layer(l)
+        d["ca"] = self._mha(l.multihead_attn)
+        d["n3"] = self._ln(l.norm3)
+        return d
+
+    def _pack_poly(self, m):
+        self.poly = dict(D=m.d_model, P=m.max_points, heads=m.nhead, w=_f32(m.input_proj.weight, self.dev),
+                         b=_f32(m.input_proj.bias, self.dev), pos=_f32(m.pos_embedding[0], self.dev),
+                         layers=[self._enc_layer(l) for l in m.encoder.layers])
+
+    def _pack_qformer(self, mllm):
+        q = mllm.qformer
+        self.qf = dict(Hq=q.hidden_size, Q=q.num_query_tokens, heads=q.nhead, vproj=_Lin(q.vision_proj.weight, q.vision_proj.bias, self.act, self.dev),
+                       enc=[self._enc_layer(l) for l in q.encoder.layers], dec=[self._dec_layer(l) for l in q.decoder.layers],
+                       query=q.query_tokens.detach().to(self.dev, self.act).contiguous())
+        vis = _f32(mllm.vision_modality_embedding.reshape(-1), self.dev)
+        if isinstance(mllm.q_proj, torch.nn.Linear):
+            self.qf["qproj"] = _Lin(mllm.q_proj.weight, mllm.q_proj.bias.detach().float().to(self.dev) + vis, self.act, self.dev)
+        else:
+            self.qf["qproj"] = None
+        self.qf["vis_mod"] = vis
+        self.text_mod = _f32(mllm.text_modality_embedding.reshape(-1), self.dev)
+
+    def _pack_llm(self, mllm):
+        wrap = mllm.llama_wrapper
+        c = wrap.config
+        lm = wrap.causal_lm()
+        act, dev = self.act, self.dev
+        H, nh, nkv, dh, I = c["hidden_size"], c["num_attention_heads"], c["num_key_value_heads"], c["head_dim"], c["intermediate_size"]
+        targets = wrap.llama_model.targets if wrap.use_lora else ()
+        r = self.model_hp["lora_r"] if wrap.use_lora else 0
+        n_t = len(targets)
+        kx = ((n_t * r + 7) // 8) * 8            # LoRA side columns appended to K (multiple of 8 for TMA strides)
+        self.llm = dict(H=H, nh=nh, nkv=nkv, dh=dh, I=I, eps=c.get("rms_norm_eps", 1e-6), theta=float(c.get("rope_theta", 10000.0)),
+                        kx=kx, n_lora=n_t * r, vocab=c["vocab_size"], layers=[],
+                        embed=lm.model.embed_tokens.weight.detach().to(dev, act).contiguous(), norm=_f32(lm.model.norm.weight, dev))
+        nq, nk = nh * dh, nkv * dh
+        for layer in lm.model.layers:
+            sa = layer.self_attn
+            rows = {"q_proj": (0, nq), "k_proj": (nq, nq + nk), "v_proj": (nq + nk, nq + 2 * nk)}
+            wqkv = torch.zeros(nq + 2 * nk, H + kx, dtype=act, device=dev)
+            a_cat = torch.zeros(max(kx, 1), H, dtype=act, device=dev) if kx else None
+            for name, (r0, r1) in rows.items():
+                mod = getattr(sa, name)
+                if name in targets:
+                    ti = targets.index(name)
+                    wqkv[r0:r1, :H] = mod.base_layer.weight.detach().to(dev, act)
+                    wqkv[r0:r1, H + ti * r: H + (ti + 1) * r] = (mod.lora_B["default"].weight.detach().float() * mod.scaling).to(dev, act)
+                    a_cat[ti * r:(ti + 1) * r] = mod.lora_A["default"].weight.detach().to(dev, act)
+                else:
+                    wqkv[r0:r1, :H] = mod.weight.detach().to(dev, act)
+            gu = torch.empty(2 * I, H, dtype=act, device=dev)
+            gu[0::2] = layer.mlp.gate_proj.weight.detach().to(dev, act)
+            gu[1::2] = layer.mlp.up_proj.weight.detach().to(dev, act)
+            self.llm["layers"].append(dict(
+                ln1=_f32(layer.input_layernorm.weight, dev), ln2=_f32(layer.post_attention_layernorm.weight, dev),
+                wqkv=wqkv, a_cat=a_cat, wo=sa.o_proj.weight.detach().to(dev, act).contiguous(), wgu=gu,
+                wdown=layer.mlp.down_proj.weight.detach().to(dev, act).contiguous()))
+
+    def _pack_ltsf(self, lt):
+        act, dev = self.act, self.dev
+        C, T, To = self.C, self.T_in, self.T_out
+        d = lt.decoder
+        we = torch.stack([l.weight.detach() for l in lt.nlinear_encoder.encoder_linears]).float()   # (C, t, s)
+        be = torch.stack([l.bias.detach() for l in lt.nlinear_encoder.encoder_linears]).float()     # (C, t)
+        wd = torch.stack([l.weight.detach() for l in d.decoder_linears]).float()                    # (C, To, s)
+        bd = torch.stack([l.bias.detach() for l in d.decoder_linears]).float()
+        # (c,t)-flat -> (t,c)-flat permutation of the 64*T_out feature axis (lane_fc rows, post_mlp.0 cols, post_mlp.3 rows)
+        perm = (torch.arange(C)[None, :] * To + torch.arange(To)[:, None]).reshape(-1).to(d.lane_fc.weight.device)
+        self.lt = dict(
+            wt=_f32(lt.token_proj.weight[:, :, 0], dev), bt=_f32(lt.token_proj.bias, dev),
+            we=we.permute(1, 2, 0).contiguous().to(dev), be=be.t().contiguous().to(dev),
+            pos=_f32(lt.pos_encoding[0].t(), dev),
+            n1=self._ln(lt.attn_block.norm1), n2=self._ln(lt.attn_block.norm2), mha=self._mha(lt.attn_block.mha),
+            f0=_Lin(lt.attn_block.ffn[0].weight, lt.attn_block.ffn[0].bias, act, dev),
+            f3=_Lin(lt.attn_block.ffn[3].weight, lt.attn_block.ffn[3].bias, act, dev),
+            wd=wd.permute(1, 2, 0).contiguous().to(dev), bd=bd.t().contiguous().to(dev),
+            lane_fc=_Lin(d.lane_fc.weight[perm], d.lane_fc.bias[perm], act, dev),
+            dec_proj=_Lin(d.dec_proj.weight, d.dec_proj.bias, act, dev), dec_unproj=_Lin(d.dec_unproj.weight, d.dec_unproj.bias, act, dev),
+            cross=self._mha(d.cross_attn),
+            fl_ln=self._ln(d.fusion_layer[0]), fl_w1=_f32(d.fusion_layer[1].weight, dev), fl_b1=_f32(d.fusion_layer[1].bias, dev),
+            fl_w2=_f32(d.fusion_layer[3].weight, dev), fl_b2=_f32(d.fusion_layer[3].bias, dev),
+            wo=_f32(d.out_proj.weight, dev), bo=_f32(d.out_proj.bias, dev), post=None)
+        if d.use_post_mlp:
+            self.lt["post"] = (_Lin(d.post_mlp[0].weight[:, perm], d.post_mlp[0].bias, act, dev),
+                               _Lin(d.post_mlp[3].weight[perm], d.post_mlp[3].bias[perm], act, dev))
+
+    # ---- building blocks --------------------------------------------------------------------------
+    def _new(self, *shape, dtype=None):
+        return torch.empty(*shape, dtype=dtype or self.act, device=self.dev)
+
+    def _self_attention(self, x, rows_per_b, B, mha, key_mask=None):
+        """x: (B*T, E) -> attention output (B*T, E) (before out_proj)."""
+        E, heads = mha["E"], mha["heads"]
+        T = rows_per_b
+        qkv = ops.gemm(x, mha["qkv"].w, self._new(B * T, 3 * E), bias=mha["qkv"].b)
+        out = self._new(B * T, E)
+        dh = E // heads
+        ops.attention(qkv, qkv[:, E:], qkv[:, 2 * E:], out, B=B, H=heads, Hkv=heads, Tq=T, Tk=T, dh=dh,
+                      q_strides=(T * 3 * E, 3 * E), k_strides=(T * 3 * E, 3 * E), v_strides=(T * 3 * E, 3 * E),
+                      o_strides=(T * E, E), scale=dh ** -0.5, key_mask=key_mask)
+        return out
+
+    def _cross_attention(self, xq, Tq, mem, Tk, B, mha):
+        E, heads = mha["E"], mha["heads"]
+        dh = E // heads
+        q = ops.gemm(xq, mha["q"].w, self._new(B * Tq, E), bias=mha["q"].b)
+        kv = ops.gemm(mem, mha["kv"].w, self._new(B * Tk, 2 * E), bias=mha["kv"].b)
+        out = self._new(B * Tq, E)
+        ops.attention(q, kv, kv[:, E:], out, B=B, H=heads, Hkv=heads, Tq=Tq, Tk=Tk, dh=dh, q_strides=(Tq * E, E),
+                      k_strides=(Tk * 2 * E, 2 * E), v_strides=(Tk * 2 * E, 2 * E), o_strides=(Tq * E, E), scale=dh ** -0.5)
+        return out
+
+    def _ln_res(self, y, ln, out=None, **kw):
+        return ops.layernorm(y, ln[0], ln[1], self._new(*y.shape) if out is None else out, eps=ln[2], **kw)
+
+    def _encoder_layer(self, x, T, B, L, key_mask=None):
+        """torch: nn.TransformerEncoderLayer (post-norm, ReLU)."""
+        a = self._self_attention(x, T, B, L["sa"], key_mask)
+        y = ops.gemm(a, L["sa"]["out"].w, self._new(*x.shape), bias=L["sa"]["out"].b, residual=x)
+        x = self._ln_res(y, L["n1"])
+        h = ops.gemm(x, L["l1"].w, self._new(x.shape[0], L["l1"].N), bias=L["l1"].b, act=ops.ACT_RELU)
+        y = ops.gemm(h, L["l2"].w, self._new(*x.shape), bias=L["l2"].b, residual=x)
+        return self._ln_res(y, L["n2"])
+
+    # ---- sub-models ---------------------------------------------------------------------------------
+    def poly_forward(self, polygon, lens):
+        """reference scripts/train.py:362-383 -> (B, D) in the activation dtype."""
+        p = self.poly
+        B, P, D = polygon.shape[0], polygon.shape[1], p["D"]
+        x = self._new(B * P, D)
+        kmask = torch.empty(B, P, dtype=torch.int32, device=self.dev)
+        ops.poly_embed(polygon, lens, p["w"], p["b"], p["pos"], x, kmask, B=B, P=P, D=D)
+        for L in p["layers"]:
+            x = self._encoder_layer(x, P, B, L, kmask)
+        return ops.masked_mean(x, lens, self._new(B, D), B=B, P=P, D=D)
+
+    def qformer_into(self, vision, fused, L_total):
+        """reference scripts/train.py:408-414, 520-522: writes image tokens (+vision modality) into fused[:, :Q]."""
+        q = self.qf
+        B, Tv, Dv = vision.shape
+        Hq, Q = q["Hq"], q["Q"]
+        v = vision.reshape(B * Tv, Dv)
+        if v.dtype != self.act:
+            v = ops.cast(v, self._new(B * Tv, Dv), rows=B * Tv, cols=Dv)
+        x = ops.gemm(v, q["vproj"].w, self._new(B * Tv, Hq), bias=q["vproj"].b)
+        for L in q["enc"]:
+            x = self._encoder_layer(x, Tv, B, L)
+        t = ops.cast(q["query"], self._new(B * Q, Hq), rows=B * Q, cols=Hq, in_row_mod=Q)
+        n = len(q["dec"])
+        for i, L in enumerate(q["dec"]):
+            a = self._self_attention(t, Q, B, L["sa"])
+            y = ops.gemm(a, L["sa"]["out"].w, self._new(B * Q, Hq), bias=L["sa"]["out"].b, residual=t)
+            t = self._ln_res(y, L["n1"])
+            a = self._cross_attention(t, Q, x, Tv, B, L["ca"])
+            y = ops.gemm(a, L["ca"]["out"].w, self._new(B * Q, Hq), bias=L["ca"]["out"].b, residual=t)
+            t = self._ln_res(y, L["n2"])
+            h = ops.gemm(t, L["l1"].w, self._new(B * Q, L["l1"].N), bias=L["l1"].b, act=ops.ACT_RELU)
+            y = ops.gemm(h, L["l2"].w, self._new(B * Q, Hq), bias=L["l2"].b, residual=t)
+            if i == n - 1 and q["qproj"] is None:
+                # Identity q_proj (H == 768): the last LayerNorm scatters straight into the fused buffer
+                self._ln_res(y, L["n3"], out=fused, remap=(Q, L_total, 0), rowvec=q["vis_mod"])
+                return
+            t = self._ln_res(y, L["n3"])
+        if q["qproj"] is not None:
+            ops.gemm(t, q["qproj"].w, fused, bias=q["qproj"].b, remap=(Q, L_total, 0), ldo=fused.shape[-1])
+        else:   # zero decoder layers
+            ops.add_rowvec(t, q["vis_mod"], fused, rows=B * Q, cols=Hq, remap=(Q, L_total, 0))
+
+    def llm_forward(self, fused, mask, B, L):
+        """HF:375-427 LlamaModel over inputs_embeds with LoRA on q/k/v (in place on `fused`); returns the
+        post-final-norm hidden states (= hidden_states[-1], reference scripts/train.py:553)."""
+        m = self.llm
+        H, nh, nkv, dh, I, kx = m["H"], m["nh"], m["nkv"], m["dh"], m["I"], m["kx"]
+        M = B * L
+        key = (L, dh)
+        if key not in self._rope:
+            self._rope[key] = ops.rope_table(L, dh, m["theta"], self.dev)
+        table = self._rope[key]
+        x = fused.view(M, H)
+        Kx = H + kx
+        hn = torch.zeros(M, Kx, dtype=self.act, device=self.dev) if kx != m["n_lora"] else self._new(M, Kx)
+        nqkv = (nh + 2 * nkv) * dh
+        qkv = self._new(M, nqkv)
+        attn = self._new(M, nh * dh)
+        hn2 = self._new(M, H)
+        mid = self._new(M, I)
+        for ly in m["layers"]:
+            ops.rmsnorm(x, ly["ln1"], hn, eps=m["eps"], rows=M, cols=H, ldo=Kx)
+            if kx:
+                # T = xn . [A_q; A_v]^T lands in the K-extension columns of the same activation buffer
+                ops.gemm(hn, ly["a_cat"], hn[:, H:], M=M, N=m["n_lora"], K=H, lda=Kx, ldo=Kx)
+            ops.gemm(hn, ly["wqkv"], qkv, M=M, N=nqkv, K=Kx, lda=Kx)
+            ops.rope_(qkv, rows=M, L=L, ld=nqkv, n_q_heads=nh, n_k_heads=nkv, dh=dh, table=table)
+            ops.attention(qkv, qkv[:, nh * dh:], qkv[:, (nh + nkv) * dh:], attn, B=B, H=nh, Hkv=nkv, Tq=L, Tk=L, dh=dh,
+                          q_strides=(L * nqkv, nqkv), k_strides=(L * nqkv, nqkv), v_strides=(L * nqkv, nqkv),
+                          o_strides=(L * nh * dh, nh * dh), scale=dh ** -0.5, causal=True, key_mask=mask)
+            ops.gemm(attn, ly["wo"], x, residual=x)
+            ops.rmsnorm(x, ly["ln2"], hn2, eps=m["eps"], rows=M, cols=H)
+            ops.gemm(hn2, ly["wgu"], mid, act=ops.ACT_SWIGLU)
+            ops.gemm(mid, ly["wdown"], x, residual=x)
+        return ops.rmsnorm(x, m["norm"], self._new(M, H), eps=m["eps"], rows=M, cols=H)
+
+    def ltsf_encode(self, x, B):
+        """reference scripts/train.py:837-840 -> enc (B*T_in, C)."""
+        lt, C, T = self.lt, self.C, self.T_in
+        e0 = ops.ltsf_encode(x, lt["wt"], lt["bt"], lt["we"], lt["be"], lt["pos"], self._new(B * T, C), B=B, F=2, C=C, T_in=T)
+        xn = self._ln_res(e0, lt["n1"])
+        a = self._self_attention(xn, T, B, lt["mha"])
+        y = ops.gemm(a, lt["mha"]["out"].w, self._new(B * T, C), bias=lt["mha"]["out"].b, residual=xn)
+        r = self._ln_res(y, lt["n2"])
+        h = ops.gemm(r, lt["f0"].w, self._new(B * T, lt["f0"].N), bias=lt["f0"].b, act=ops.ACT_RELU)
+        return ops.gemm(h, lt["f3"].w, self._new(B * T, C), bias=lt["f3"].b, residual=r)
+
+    def ltsf_decode(self, enc, poly_emb, fh, x, B, L, y=None, norm_stat=None):
+        """reference scripts/train.py:767-806 + 941-943 (+ 945-962 / 1302-1322 when y is given)."""
+        lt, C, T, To = self.lt, self.C, self.T_in, self.T_out
+        H = self.llm["H"]
+        adj = ops.gemm(poly_emb, lt["lane_fc"].w, self._new(B, To * C), bias=lt["lane_fc"].b)
+        dec = ops.nlinear_decode(enc, lt["wd"], lt["bd"], adj, self._new(B, To * C), B=B, C=C, T_in=T, T_out=To)
+        if lt["post"] is not None:
+            p0, p3 = lt["post"]
+            h = ops.gemm(dec, p0.w, self._new(B, p0.N), bias=p0.b, act=ops.ACT_RELU)
+            dec = ops.gemm(h, p3.w, self._new(B, To * C), bias=p3.b)
+        dec_t = dec.view(B * To, C)
+        q = ops.gemm(dec_t, lt["dec_proj"].w, self._new(B * To, H), bias=lt["dec_proj"].b)
+        a = self._cross_attention(q, To, fh, L, B, lt["cross"])
+        co = ops.gemm(a, lt["cross"]["out"].w, self._new(B * To, H), bias=lt["cross"]["out"].b)
+        fused = ops.gemm(co, lt["dec_unproj"].w, self._new(B * To, C), bias=lt["dec_unproj"].b, residual=dec_t)
+        decoded = torch.empty(B, 2, To, dtype=torch.float32, device=self.dev)
+        out = {"decoded": decoded}
+        metrics = per_scene = None
+        if y is not None:
+            metrics = torch.zeros(8, dtype=torch.float32, device=self.dev)
+            per_scene = torch.empty(B, 2, dtype=torch.float32, device=self.dev)
+        ops.fusion_head(fused, lt["fl_ln"][0], lt["fl_ln"][1], lt["fl_w1"], lt["fl_b1"], lt["fl_w2"], lt["fl_b2"], lt["wo"], lt["bo"], x,
+                        decoded, y=y, norm_stat=norm_stat, metrics=metrics, per_scene=per_scene, B=B, C=C, T_in=T, T_out=To)
+        if y is not None:
+            out.update(metrics=metrics, per_scene=per_scene)
+        return out
+
+    # ---- full forward -------------------------------------------------------------------------------
+    def _dev_f32(self, t):
+        if not torch.is_tensor(t):
+            t = torch.tensor(t, dtype=torch.float32)
+        return t.to(device=self.dev, dtype=torch.float32, non_blocking=True).contiguous()
+
+    @torch.no_grad()
+    def forward(self, x, vision, polygon, poly_len, input_ids, attention_mask, y=None, norm_stat=None, final_hidden=None,
+                keep_intermediates=False):
+        dev = self.dev
+        if dev.type != "cuda":
+            raise ops._lib.TcavpError("the model must be on a CUDA device (there is no CPU fallback): model.to('cuda')")
+        x = self._dev_f32(x)
+        B = x.shape[0]
+        polygon = self._dev_f32(polygon)
+        lens = poly_len if torch.is_tensor(poly_len) else torch.tensor(list(poly_len), dtype=torch.int32)
+        lens = lens.to(device=dev, dtype=torch.int32, non_blocking=True)
+        if y is not None and norm_stat is not None:
+            y = self._dev_f32(y)
+            norm_stat = self._dev_f32(norm_stat).view(B, 4)
+        else:
+            y = norm_stat = None
+        out = {}
+        poly_emb = self.poly_forward(polygon, lens)
+        if final_hidden is None:
+            vision = vision.to(dev, non_blocking=True)
+            if vision.dtype not in (torch.float32, torch.bfloat16):
+                vision = vision.float()
+            ids = input_ids.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
+            am = attention_mask.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
+            Q, H = self.qf["Q"], self.llm["H"]
+            L = Q + ids.shape[1]
+            fused = self._new(B, L, H)
+            mask = torch.empty(B, L, dtype=torch.int32, device=dev)
+            self.qformer_into(vision.contiguous(), fused, L)
+            ops.embed_text(ids, am, self.llm["embed"], self.text_mod, fused, mask, B=B, L_text=ids.shape[1], n_img=Q, H=H)
+            if keep_intermediates:
+                out["image_tokens_plus_mod"] = fused[:, :Q].float()
+            fh = self.llm_forward(fused, mask, B, L)
+        else:
+            fh = final_hidden.to(device=dev, dtype=self.act).contiguous()
+            L = fh.shape[1]
+            fh = fh.view(B * L, -1)
+        enc = self.ltsf_encode(x, B)
+        out.update(self.ltsf_decode(enc, poly_emb, fh, x, B, L, y, norm_stat))
+        if y is not None:
+            m = out["metrics"]
+            out["loss"] = m[4]                                  # MSE_x + MSE_y, reference scripts/train.py:959-961
+            out["sum_ade"], out["sum_fde"] = m[2], m[3]
+            out["ade"], out["fde"] = out["per_scene"][:, 0], out["per_scene"][:, 1]
+        if keep_intermediates:
+            out["poly_emb"] = poly_emb.float()
+            out["final_hidden"] = fh.view(B, L, -1).float()
+            out["enc"] = enc.view(B, self.T_in, self.C).permute(0, 2, 1).float()
+        return out

@@ -1,0 +1,99 @@
+"""Build + load of libtcavp.so (the C-ABI shared library declared in include/tcavp.h).
+
+The library is compiled in-tree with nvcc for sm_100a only and loaded through ctypes; there is no CPU
+fallback — every op raises if the library is missing or a call fails."""
+import ctypes
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "libtcavp.so")
+INCLUDE = os.path.join(_ROOT, "include")
+SOURCES = ["api.cu", "gemm.cu", "attention.cu", "attention_tc.cu", "norm.cu", "elementwise.cu", "ltsf.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-I", INCLUDE]
+
+EXPORTS = [
+    "tcavp_last_error", "tcavp_version", "tcavp_device_info", "tcavp_launch_count", "tcavp_gemm", "tcavp_attention",
+    "tcavp_layernorm", "tcavp_rmsnorm", "tcavp_rope", "tcavp_rope_table", "tcavp_embed_text", "tcavp_add_rowvec",
+    "tcavp_cast", "tcavp_poly_embed", "tcavp_masked_mean", "tcavp_ltsf_encode", "tcavp_nlinear_decode",
+    "tcavp_fusion_head", "tcavp_traj_metrics",
+]
+
+
+def _nvcc():
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
+            return c
+    raise RuntimeError("nvcc not found")
+
+
+def _stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(INCLUDE, "tcavp.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compiles csrc/*.cu -> libtcavp.so (sm_100a).  Cross-compiles fine on a box without a GPU."""
+    if not force and not _stale():
+        return LIB_PATH
+    objdir = os.path.join(_HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    nvcc = _nvcc()
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    objs = []
+    for src, obj, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{out}")
+        if verbose and out:
+            print(out)
+        objs.append(obj)
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}")
+    return LIB_PATH
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """Returns the ctypes handle, raising loudly if the library has not been built."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                   "(there is no CPU fallback)")
+            lib = ctypes.CDLL(LIB_PATH)
+            lib.tcavp_last_error.restype = ctypes.c_char_p
+            lib.tcavp_launch_count.restype = ctypes.c_longlong
+            for name in EXPORTS:
+                getattr(lib, name)   # AttributeError if a declared symbol is not exported
+            _lib = lib
+    return _lib
+
+
+class TcavpError(RuntimeError):
+    pass
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().tcavp_last_error().decode(errors="replace")
+        raise TcavpError(f"{what} failed ({rc}): {msg}")

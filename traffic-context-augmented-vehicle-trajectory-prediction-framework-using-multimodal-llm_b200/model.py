@@ -1,0 +1,353 @@
+"""Host-side mirror of the reference model contract (reference scripts/train.py:847-964).
+
+`MultiModalTrajectoryModel` keeps the reference's constructor kwargs, forward() signature, sub-module
+attribute names and state_dict key layout, so it drops into the reference's
+train/test drivers.  The nn.Module tree below is ONLY a parameter container with the reference's names —
+its torch forward() methods are never called; all arithmetic runs in libtcavp.so through engine.py."""
+import math
+
+import torch
+import torch.nn as nn
+
+from .config import resolve_llama
+from .engine import Engine
+
+# --------------------------------------------------------------------------------------------------
+# parameter containers (names = reference names)
+# --------------------------------------------------------------------------------------------------
+
+
+class LanePolygonEncoder(nn.Module):
+    """reference scripts/train.py:352-383"""
+
+    def __init__(self, d_model=64, nhead=4, num_layers=2, max_points=64):
+        super().__init__()
+        self.d_model, self.max_points, self.nhead = d_model, max_points, nhead
+        self.input_proj = nn.Linear(2, d_model)
+        enc_layer = nn.TransformerEncoderLayer(d_model=d_model, nhead=nhead, batch_first=True)
+        self.encoder = nn.TransformerEncoder(enc_layer, num_layers=num_layers, enable_nested_tensor=False)
+        self.pos_embedding = nn.Parameter(torch.zeros(1, max_points, d_model))
+
+
+class BlipQFormer(nn.Module):
+    """reference scripts/train.py:388-414"""
+
+    def __init__(self, vision_dim=512, hidden_size=768, nhead=8, num_encoder_layers=4, num_decoder_layers=4,
+                 num_query_tokens=16):
+        super().__init__()
+        self.num_query_tokens, self.hidden_size, self.nhead = num_query_tokens, hidden_size, nhead
+        self.vision_proj = nn.Linear(vision_dim, hidden_size)
+        enc_layer = nn.TransformerEncoderLayer(d_model=hidden_size, nhead=nhead, batch_first=True)
+        self.encoder = nn.TransformerEncoder(enc_layer, num_layers=num_encoder_layers, enable_nested_tensor=False)
+        self.query_tokens = nn.Parameter(torch.randn(num_query_tokens, hidden_size))
+        dec_layer = nn.TransformerDecoderLayer(d_model=hidden_size, nhead=nhead, batch_first=True)
+        self.decoder = nn.TransformerDecoder(dec_layer, num_layers=num_decoder_layers)
+
+
+class _RMSNormW(nn.Module):
+    def __init__(self, n, **kw):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(n, **kw))
+
+
+class _LlamaAttentionW(nn.Module):
+    def __init__(self, c, **kw):
+        super().__init__()
+        H, nh, nkv, dh = c["hidden_size"], c["num_attention_heads"], c["num_key_value_heads"], c["head_dim"]
+        self.q_proj = nn.Linear(H, nh * dh, bias=False, **kw)
+        self.k_proj = nn.Linear(H, nkv * dh, bias=False, **kw)
+        self.v_proj = nn.Linear(H, nkv * dh, bias=False, **kw)
+        self.o_proj = nn.Linear(nh * dh, H, bias=False, **kw)
+
+
+class _LlamaMLPW(nn.Module):
+    def __init__(self, c, **kw):
+        super().__init__()
+        H, I = c["hidden_size"], c["intermediate_size"]
+        self.gate_proj = nn.Linear(H, I, bias=False, **kw)
+        self.up_proj = nn.Linear(H, I, bias=False, **kw)
+        self.down_proj = nn.Linear(I, H, bias=False, **kw)
+
+
+class _LlamaLayerW(nn.Module):
+    def __init__(self, c, **kw):
+        super().__init__()
+        self.self_attn = _LlamaAttentionW(c, **kw)
+        self.mlp = _LlamaMLPW(c, **kw)
+        self.input_layernorm = _RMSNormW(c["hidden_size"], **kw)
+        self.post_attention_layernorm = _RMSNormW(c["hidden_size"], **kw)
+
+
+class _LlamaModelW(nn.Module):
+    def __init__(self, c, **kw):
+        super().__init__()
+        self.embed_tokens = nn.Embedding(c["vocab_size"], c["hidden_size"], **kw)
+        self.layers = nn.ModuleList([_LlamaLayerW(c, **kw) for _ in range(c["num_hidden_layers"])])
+        self.norm = _RMSNormW(c["hidden_size"], **kw)
+
+
+class LlamaForCausalLMW(nn.Module):
+    """Key layout of HF LlamaForCausalLM (HF:430-500): model.* + lm_head.weight.  lm_head is kept for
+    checkpoint interop (strict loads) but never computed: its logits are discarded by the reference
+    (reference scripts/train.py:547-554)."""
+
+    def __init__(self, c, **kw):
+        super().__init__()
+        self.config = dict(c)
+        self.model = _LlamaModelW(c, **kw)
+        self.lm_head = nn.Linear(c["hidden_size"], c["vocab_size"], bias=False, **kw)
+        std = 0.02
+        with torch.no_grad():
+            for m in self.modules():
+                if isinstance(m, (nn.Linear, nn.Embedding)):
+                    m.weight.normal_(0.0, std)
+
+    def get_input_embeddings(self):
+        return self.model.embed_tokens
+
+
+class LoraLinearW(nn.Module):
+    """peft >= 0.7 lora.Linear key layout: base_layer.weight, lora_A.default.weight, lora_B.default.weight."""
+
+    def __init__(self, base, r, alpha, dropout):
+        super().__init__()
+        kw = dict(device=base.weight.device, dtype=base.weight.dtype)
+        self.base_layer = base
+        self.lora_A = nn.ModuleDict({"default": nn.Linear(base.in_features, r, bias=False, **kw)})
+        self.lora_B = nn.ModuleDict({"default": nn.Linear(r, base.out_features, bias=False, **kw)})
+        nn.init.kaiming_uniform_(self.lora_A["default"].weight, a=math.sqrt(5))
+        nn.init.zeros_(self.lora_B["default"].weight)
+        self.r, self.lora_alpha, self.scaling, self.lora_dropout_p = r, alpha, alpha / r, dropout
+
+
+class _LoraModelW(nn.Module):
+    def __init__(self, model):
+        super().__init__()
+        self.model = model
+
+
+class PeftModelW(nn.Module):
+    """peft.get_peft_model(LoraConfig(r, alpha, dropout, bias='none', CAUSAL_LM)) for a llama-type model:
+    default targets q_proj, v_proj; base weights frozen (reference scripts/train.py:432-440)."""
+
+    TARGETS = ("q_proj", "v_proj")
+
+    def __init__(self, model, r, alpha, dropout, target_modules=None):
+        super().__init__()
+        self.targets = tuple(target_modules or self.TARGETS)
+        bad = [t for t in self.targets if t not in ("q_proj", "k_proj", "v_proj")]
+        if bad:
+            raise NotImplementedError(f"LoRA targets {bad} are not supported (q_proj/k_proj/v_proj only)")
+        for p in model.parameters():
+            p.requires_grad_(False)
+        for layer in model.model.layers:
+            for t in self.targets:
+                setattr(layer.self_attn, t, LoraLinearW(getattr(layer.self_attn, t), r, alpha, dropout))
+        self.base_model = _LoraModelW(model)
+        self.config = model.config
+
+    def get_input_embeddings(self):
+        return self.base_model.model.get_input_embeddings()
+
+
+class LlamaWithCrossAttnPEFT(nn.Module):
+    """reference scripts/train.py:419-453 (name is historical: there is no cross-attention inside the LLM)."""
+
+    def __init__(self, base_model_name, use_lora=True, lora_r=8, lora_alpha=32, lora_dropout=0.1, **kw):
+        super().__init__()
+        cfg = resolve_llama(base_model_name)
+        cfg.setdefault("num_key_value_heads", cfg["num_attention_heads"])
+        cfg.setdefault("head_dim", cfg["hidden_size"] // cfg["num_attention_heads"])
+        self.llama_model = LlamaForCausalLMW(cfg, **kw)
+        self.use_lora = use_lora
+        if use_lora:
+            self.llama_model = PeftModelW(self.llama_model, lora_r, lora_alpha, lora_dropout)
+        self.config = cfg
+        self.hidden_size = cfg["hidden_size"]
+
+    def causal_lm(self):
+        return self.llama_model.base_model.model if self.use_lora else self.llama_model
+
+
+class LlamaMultiModal(nn.Module):
+    """reference scripts/train.py:459-575 ("TSUE")."""
+
+    def __init__(self, base_model_name="meta-llama/Llama-2-7b-hf", use_lora=True, lora_r=8, lora_alpha=32, lora_dropout=0.1,
+                 vision_dim=512, q_hidden_size=768, q_nhead=8, q_enc_layers=4, q_dec_layers=4, q_num_query_tokens=16, **kw):
+        super().__init__()
+        self.qformer = BlipQFormer(vision_dim, q_hidden_size, q_nhead, q_enc_layers, q_dec_layers, q_num_query_tokens)
+        self.q_hidden_size = q_hidden_size
+        self.llama_wrapper = LlamaWithCrossAttnPEFT(base_model_name, use_lora, lora_r, lora_alpha, lora_dropout, **kw)
+        self.llama_hidden_size = self.llama_wrapper.hidden_size
+        self.q_proj = nn.Linear(q_hidden_size, self.llama_hidden_size) if self.llama_hidden_size != q_hidden_size else nn.Identity()
+        self.vision_modality_embedding = nn.Parameter(torch.randn(1, 1, self.llama_hidden_size))
+        self.text_modality_embedding = nn.Parameter(torch.randn(1, 1, self.llama_hidden_size))
+        self.tokenizer = None   # no hub access: callers pass input_ids / attention_mask (train.py:524 branch)
+
+    def generate_batch(self, *a, **k):
+        raise NotImplementedError("text generation (reference scripts/train.py:577-654) is outside the hot path (SURVEY.md §8f)")
+
+
+class SelfAttentionBlock(nn.Module):
+    """reference scripts/train.py:659-686"""
+
+    def __init__(self, embed_dim, nhead=1, dropout_rate=0.1):
+        super().__init__()
+        self.nhead = nhead
+        self.norm1 = nn.LayerNorm(embed_dim)
+        self.mha = nn.MultiheadAttention(embed_dim, num_heads=nhead, dropout=dropout_rate)
+        self.ffn = nn.Sequential(nn.Linear(embed_dim, embed_dim * 4), nn.ReLU(), nn.Dropout(dropout_rate),
+                                 nn.Linear(embed_dim * 4, embed_dim))
+        self.norm2 = nn.LayerNorm(embed_dim)
+
+
+class LTSF_NLinearEncoder(nn.Module):
+    """reference scripts/train.py:688-716"""
+
+    def __init__(self, window_size, individual, d_model):
+        super().__init__()
+        if not individual:
+            raise NotImplementedError("individual=False is never used by the reference drivers (train.py:1103)")
+        self.encoder_linears = nn.ModuleList([nn.Linear(window_size, window_size) for _ in range(d_model)])
+
+
+class LTSF_NLinearDecoder(nn.Module):
+    """reference scripts/train.py:718-806 ("MFP")"""
+
+    def __init__(self, window_size, forecast_size, individual, d_model, polygon_embed_dim=64, use_post_mlp=True,
+                 post_mlp_hidden_dim=64, dropout_rate=0.1, cross_dim=768, cross_nhead=2, output_feature_dim=2):
+        super().__init__()
+        if not individual:
+            raise NotImplementedError("individual=False is never used by the reference drivers (train.py:1103)")
+        self.decoder_linears = nn.ModuleList([nn.Linear(window_size, forecast_size) for _ in range(d_model)])
+        self.lane_fc = nn.Linear(polygon_embed_dim, d_model * forecast_size)
+        self.use_post_mlp = use_post_mlp
+        if use_post_mlp:
+            self.post_mlp = nn.Sequential(nn.Linear(d_model * forecast_size, post_mlp_hidden_dim), nn.ReLU(),
+                                          nn.Dropout(dropout_rate), nn.Linear(post_mlp_hidden_dim, d_model * forecast_size))
+        self.cross_nhead = cross_nhead
+        self.cross_attn = nn.MultiheadAttention(embed_dim=cross_dim, num_heads=cross_nhead, dropout=dropout_rate, batch_first=False)
+        self.dec_proj = nn.Linear(d_model, cross_dim)
+        self.dec_unproj = nn.Linear(cross_dim, d_model)
+        self.fusion_layer = nn.Sequential(nn.LayerNorm(d_model), nn.Linear(d_model, d_model), nn.ReLU(), nn.Linear(d_model, d_model))
+        self.out_proj = nn.Linear(d_model, output_feature_dim)
+
+
+class TransformerLTSF(nn.Module):
+    """reference scripts/train.py:808-842"""
+
+    def __init__(self, seq_len, out_len, individual, feature_size, d_model, polygon_embed_dim=64, use_post_mlp=True,
+                 post_mlp_hidden_dim=64, nhead=1, dropout_rate=0.1, cross_dim=768, cross_nhead=2, output_feature_dim=2):
+        super().__init__()
+        self.token_proj = nn.Conv1d(feature_size, d_model, kernel_size=1)
+        self.nlinear_encoder = LTSF_NLinearEncoder(seq_len, individual, d_model)
+        self.pos_encoding = nn.Parameter(torch.zeros(1, d_model, seq_len))
+        self.attn_block = SelfAttentionBlock(embed_dim=d_model, nhead=nhead, dropout_rate=dropout_rate)
+        self.decoder = LTSF_NLinearDecoder(seq_len, out_len, individual, d_model, polygon_embed_dim, use_post_mlp,
+                                           post_mlp_hidden_dim, dropout_rate, cross_dim, cross_nhead, output_feature_dim)
+
+
+# --------------------------------------------------------------------------------------------------
+# the model
+# --------------------------------------------------------------------------------------------------
+
+
+class MultiModalTrajectoryModel(nn.Module):
+    """Drop-in for reference scripts/train.py:847-964.
+
+    Extra (keyword-only, defaulted) arguments beyond the reference's:
+      compute_dtype : "bf16" (tcgen05 tensor-core path) or "fp32" (exact-fp32 SIMT parity path)
+      llm_param_dtype / llm_device : create the frozen backbone parameters directly in this dtype / on this
+                      device (a 7B fp32 host copy is 27 GB; the reference always builds fp32 on CPU)
+      llm_variant   : "wrapper" -> keys `mllm.llama_wrapper.llama_model.*` (train.py), "direct" ->
+                      `mllm.llama_model.*` (im_kim_train_GRN.py:444-455) on save; both are accepted on load.
+    """
+
+    def __init__(self, seq_len, out_len, individual, feature_size=2, d_model=64, lane_polygon_d_model=64, lane_polygon_nhead=4,
+                 lane_polygon_layers=2, max_polygon_points=64, use_post_mlp=True, post_mlp_hidden_dim=64,
+                 base_model_name="meta-llama/Llama-7B", use_lora=True, lora_r=8, lora_alpha=32, lora_dropout=0.1, vision_dim=512,
+                 q_hidden_size=768, q_nhead=8, q_enc_layers=4, q_dec_layers=4, q_num_query_tokens=16, ltsf_nhead=1,
+                 ltsf_dropout=0.1, *, compute_dtype="bf16", llm_param_dtype=None, llm_device=None):
+        super().__init__()
+        if feature_size != 2:
+            raise NotImplementedError("feature_size must be 2 ((x, y) trajectories)")
+        kw = {}
+        if llm_param_dtype is not None:
+            kw["dtype"] = llm_param_dtype
+        if llm_device is not None:
+            kw["device"] = llm_device
+        self.lane_polygon_encoder = LanePolygonEncoder(lane_polygon_d_model, lane_polygon_nhead, lane_polygon_layers, max_polygon_points)
+        self.mllm = LlamaMultiModal(base_model_name, use_lora, lora_r, lora_alpha, lora_dropout, vision_dim, q_hidden_size, q_nhead,
+                                    q_enc_layers, q_dec_layers, q_num_query_tokens, **kw)
+        self.llama_hidden_size = self.mllm.llama_hidden_size
+        self.ltsf = TransformerLTSF(seq_len, out_len, individual, feature_size, d_model, lane_polygon_d_model, use_post_mlp,
+                                    post_mlp_hidden_dim, ltsf_nhead, ltsf_dropout, self.llama_hidden_size, 2, feature_size)
+        self.feature_size, self.out_len, self.seq_len, self.d_model = feature_size, out_len, seq_len, d_model
+        self.hparams = dict(lora_r=lora_r, lora_alpha=lora_alpha, use_lora=use_lora, q_nhead=q_nhead, ltsf_nhead=ltsf_nhead,
+                            lane_polygon_nhead=lane_polygon_nhead, use_post_mlp=use_post_mlp, q_num_query_tokens=q_num_query_tokens)
+        self.compute_dtype = compute_dtype
+        self._engine = None
+        self._engine_sig = None
+        self._register_load_state_dict_pre_hook(self._translate_keys)
+
+    # ---- checkpoint interop -----------------------------------------------------
+    def _translate_keys(self, state_dict, prefix, *args):
+        """Accepts (a) the V2 layout `mllm.llama_model.` (im_kim_train_GRN.py:444-455) and (b) the peft<0.7 layout
+        without `.base_layer` (implied by ablation_study_without_lora.py:1071-1079); (c) a LoRA checkpoint loaded into
+        a use_lora=False model is stripped exactly like the reference's adjust_state_dict."""
+        want_lora = self.mllm.llama_wrapper.use_lora
+        for k in list(state_dict.keys()):
+            nk = k
+            if nk.startswith(prefix + "mllm.llama_model."):
+                nk = prefix + "mllm.llama_wrapper.llama_model." + nk[len(prefix + "mllm.llama_model."):]
+            if not want_lora:
+                if "lora_A" in nk or "lora_B" in nk:
+                    del state_dict[k]
+                    continue
+                nk = nk.replace("llama_model.base_model.model.", "llama_model.").replace(".base_layer.", ".")
+            else:
+                for t in self.mllm.llama_wrapper.llama_model.targets:
+                    if nk.endswith(f".self_attn.{t}.weight"):
+                        nk = nk[: -len("weight")] + "base_layer.weight"
+            if nk != k:
+                state_dict[nk] = state_dict.pop(k)
+
+    # ---- engine management -------------------------------------------------------------------------
+    def set_compute_dtype(self, name):
+        assert name in ("bf16", "fp32")
+        self.compute_dtype = name
+        self._engine = None
+        return self
+
+    def _signature(self):
+        return (self.compute_dtype,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def engine(self):
+        sig = self._signature()
+        if self._engine is None or sig != self._engine_sig:
+            self._engine = Engine(self, self.compute_dtype)
+            self._engine_sig = sig
+        return self._engine
+
+    # ---- forward -----------------------------------------------------------------------------------
+    def forward(self, x, vision_embs, context_str, lane_polygon_batch, lane_polygon_len, y=None, norm_stat=None, input_ids=None,
+                attention_mask=None, labels=None):
+        """Same contract as reference scripts/train.py:914-964.  `labels` is accepted and ignored: it only feeds HF's
+        internal CE loss, which the reference discards (train.py:547-554).  `lane_polygon_len` / `norm_stat` may be
+        Python lists (as the reference's collate produces) or device tensors."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+            raise NotImplementedError("training backward is not implemented yet: call under torch.no_grad() / eval()")
+        if input_ids is None or attention_mask is None:
+            raise NotImplementedError("tokenizer branch (train.py:556-575) needs a hub tokenizer; pass input_ids and attention_mask")
+        eng = self.engine()
+        out = eng.forward(x, vision_embs, lane_polygon_batch, lane_polygon_len, input_ids, attention_mask, y=y, norm_stat=norm_stat)
+        if y is not None and norm_stat is not None:
+            return out["loss"], out["decoded"]
+        return out["decoded"]
+
+    @torch.no_grad()
+    def predict_with_metrics(self, x, vision_embs, lane_polygon_batch, lane_polygon_len, y, norm_stat, input_ids, attention_mask):
+        """forward + the reference's test-loop reduction (train.py:1302-1322) in one pass.
+        Returns dict(decoded, loss, sum_ade, sum_fde, ade[B], fde[B]) — all device tensors, no host sync."""
+        return self.engine().forward(x, vision_embs, lane_polygon_batch, lane_polygon_len, input_ids, attention_mask, y=y,
+                                     norm_stat=norm_stat)
