@@ -123,8 +123,9 @@ int tcavp_rmsnorm(const void* x, const float* w, void* out, int rows, int cols, 
  * position of row r is r % L.  cos_sin is an fp32 [L, dh/2, 2] table. */
 int tcavp_rope(void* qkv, int rows, int L, int ld, int n_q_heads, int n_k_heads, int dh, const float* cos_sin,
                int dtype, tcavp_stream_t stream);
-/* Fills the [L, dh/2, 2] table exactly as HF does (fp32 inv_freq, fp32 angle, cosf/sinf). */
-int tcavp_rope_table(float* cos_sin, int L, int dh, float theta, tcavp_stream_t stream);
+/* Fills the [L, dh/2, 2] table as HF does: angle = pos * inv_freq[j] in fp32, cosf / sinf.  inv_freq is a device
+ * fp32 [dh/2] vector the host computes with HF's formula 1 / theta^(2j/dh) (HF:86-88). */
+int tcavp_rope_table(float* cos_sin, const float* inv_freq, int L, int dh, tcavp_stream_t stream);
 
 /* ---- fused-sequence assembly (train.py:526-528) -------------------------------------------------
  * fused[b, n_img + j, :] = embed[ids[b, j], :] + text_mod[:]   for j < L_text; mask_out[b, :] = [1]*n_img ++ mask. */

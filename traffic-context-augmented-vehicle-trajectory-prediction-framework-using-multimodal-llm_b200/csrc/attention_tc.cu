@@ -1,6 +1,209 @@
-// Tensor-core flash attention for the LLM self-attention (bf16, head_dim 64/128).  Placeholder until the
-// mma kernel lands: reports "not applicable" so tcavp_attention uses the generic warp kernel.
+// Tensor-core flash attention for the LLM self-attention (HF:251-289 with the causal + key-padding mask of
+// HF:399): bf16 operands, head_dim 64 or 128, Tk <= 256, optional causal mask, optional key mask, GQA.
+//
+// One CTA per (batch, head): K and V of that head are staged ONCE in shared memory (padded rows, conflict-free
+// ldmatrix), every warp owns a 16-row query slab and runs the FlashAttention-2 register pipeline
+// (mma.sync m16n8k16: S = Q.K^T -> online softmax in fp32 -> O += P.V) over 64-key blocks, skipping blocks
+// beyond its causal bound.  Scores and probabilities never touch shared or global memory.
 #include "common.cuh"
+
 namespace tcavp {
-int attention_tc_launch(const tcavp_attn_args& a, cudaStream_t stream) { (void)a; (void)stream; return 1; }
+namespace fa {
+
+constexpr int KB = 64;      // keys per iteration
+constexpr int PAD = 8;      // bf16 elements of row padding (16 bytes): ldmatrix rows land in distinct banks
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int DH>
+__global__ void __launch_bounds__(DH == 64 ? 384 : 320) attn_flash_kernel(tcavp_attn_args a, int tk_pad_all) {
+  constexpr int LDS = DH + PAD;            // smem row stride in elements
+  constexpr int KS = DH / 16;              // k-steps of the Q.K^T contraction
+  constexpr int NT = DH / 8;               // n8 tiles of the output
+  extern __shared__ __align__(16) uint8_t smem[];
+  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem);
+  __nv_bfloat16* sV = sK + (size_t)tk_pad_all * LDS;
+  int* sMask = reinterpret_cast<int*>(sV + (size_t)tk_pad_all * LDS);   // [tk_pad_all] 1 = attend
+
+  const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+  const int hk = h / (a.H / a.Hkv);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q_base = blockIdx.y * (blockDim.x >> 5) * 16;                      // first query row of this CTA
+  // keys this CTA can ever need (causal: up to its last query row), rounded up to whole 64-key blocks
+  const int tk_need = a.causal ? min(a.Tk, q_base + (int)(blockDim.x >> 5) * 16) : a.Tk;
+  const int tk_pad = min(tk_pad_all, (tk_need + KB - 1) / KB * KB);
+  const __nv_bfloat16* gq = reinterpret_cast<const __nv_bfloat16*>(a.q) + (size_t)b * a.q_sb + (size_t)h * DH;
+  const __nv_bfloat16* gk = reinterpret_cast<const __nv_bfloat16*>(a.k) + (size_t)b * a.k_sb + (size_t)hk * DH;
+  const __nv_bfloat16* gv = reinterpret_cast<const __nv_bfloat16*>(a.v) + (size_t)b * a.v_sb + (size_t)hk * DH;
+
+  // ---- stage K, V (zero-filled beyond Tk) and the key mask ----
+  constexpr int VPR = DH / 8;              // 16-byte vectors per row
+  for (int i = threadIdx.x; i < tk_pad * VPR; i += blockDim.x) {
+    const int r = i / VPR, c = (i % VPR) * 8;
+    uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+    if (r < a.Tk) {
+      kv = *reinterpret_cast<const uint4*>(gk + (size_t)r * a.k_st + c);
+      vv = *reinterpret_cast<const uint4*>(gv + (size_t)r * a.v_st + c);
+    }
+    *reinterpret_cast<uint4*>(sK + (size_t)r * LDS + c) = kv;
+    *reinterpret_cast<uint4*>(sV + (size_t)r * LDS + c) = vv;
+  }
+  for (int j = threadIdx.x; j < tk_pad; j += blockDim.x)
+    sMask[j] = (j < a.Tk) && (!a.key_mask || a.key_mask[(size_t)b * a.Tk + j] != 0);
+  __syncthreads();
+
+  const int row0 = q_base + warp * 16;
+  if (row0 >= a.Tq) return;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int r_lo = row0 + g, r_hi = row0 + g + 8;
+
+  // ---- Q fragments straight from global memory (A operand, row-major m16k16 per k-step) ----
+  uint32_t qf[KS][4];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    const int c = ks * 16 + t4 * 2;
+    const __nv_bfloat16* p_lo = gq + (size_t)r_lo * a.q_st + c;
+    const __nv_bfloat16* p_hi = gq + (size_t)r_hi * a.q_st + c;
+    qf[ks][0] = r_lo < a.Tq ? *reinterpret_cast<const uint32_t*>(p_lo) : 0u;
+    qf[ks][1] = r_hi < a.Tq ? *reinterpret_cast<const uint32_t*>(p_hi) : 0u;
+    qf[ks][2] = r_lo < a.Tq ? *reinterpret_cast<const uint32_t*>(p_lo + 8) : 0u;
+    qf[ks][3] = r_hi < a.Tq ? *reinterpret_cast<const uint32_t*>(p_hi + 8) : 0u;
+  }
+
+  float o[NT][4];
+#pragma unroll
+  for (int n = 0; n < NT; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+  float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+  const float sl2 = a.scale * 1.4426950408889634f;   // softmax in base 2
+
+  const int k_end = a.causal ? min(a.Tk, row0 + 16) : a.Tk;   // keys this warp can ever see
+  const uint32_t sK_u = (uint32_t)__cvta_generic_to_shared(sK), sV_u = (uint32_t)__cvta_generic_to_shared(sV);
+  // ldmatrix lane -> row/col offsets.  K (non-transposed, x4 = keys [0,8)/[8,16) x dims [0,8)/[8,16)):
+  const int k_row = (lane & 7) + ((lane >> 4) << 3), k_col = ((lane >> 3) & 1) * 8;
+  // V (transposed, x4 = keys [0,8)/[8,16) x dims [0,8)/[8,16)):
+  const int v_row = (lane & 7) + (((lane >> 3) & 1) << 3), v_col = (lane >> 4) * 8;
+
+  for (int kb = 0; kb < k_end; kb += KB) {
+    float s[KB / 8][4];
+#pragma unroll
+    for (int n = 0; n < KB / 8; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+    // ---- S = Q . K^T for 64 keys ----
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+      for (int np = 0; np < KB / 16; ++np) {      // pairs of n8 tiles (16 keys)
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(sK_u + (uint32_t)(((kb + np * 16 + k_row) * LDS + ks * 16 + k_col) * 2), b0, b1, b2, b3);
+        mma16816(s[2 * np], qf[ks], b0, b1);       // keys [0,8) of the pair: dims [0,8), [8,16)
+        mma16816(s[2 * np + 1], qf[ks], b2, b3);   // keys [8,16)
+      }
+    }
+    // ---- mask + online softmax ----
+    float mx_lo = m_lo, mx_hi = m_hi;
+#pragma unroll
+    for (int n = 0; n < KB / 8; ++n) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = kb + n * 8 + t4 * 2 + e;
+        const bool okj = sMask[j] != 0;
+        const bool ok_lo = okj && (!a.causal || j <= r_lo), ok_hi = okj && (!a.causal || j <= r_hi);
+        s[n][e] = ok_lo ? s[n][e] * sl2 : -INFINITY;
+        s[n][2 + e] = ok_hi ? s[n][2 + e] * sl2 : -INFINITY;
+        mx_lo = fmaxf(mx_lo, s[n][e]);
+        mx_hi = fmaxf(mx_hi, s[n][2 + e]);
+      }
+    }
+    mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
+    mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
+    mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
+    mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+    // rows with nothing attendable yet keep m = -inf: use 0 as the reference point so exp2(-inf - 0) = 0
+    const float ref_lo = mx_lo == -INFINITY ? 0.f : mx_lo, ref_hi = mx_hi == -INFINITY ? 0.f : mx_hi;
+    const float c_lo = exp2f(m_lo - ref_lo), c_hi = exp2f(m_hi - ref_hi);
+    m_lo = mx_lo;
+    m_hi = mx_hi;
+    float ps_lo = 0.f, ps_hi = 0.f;
+    uint32_t pf[KB / 16][4];
+#pragma unroll
+    for (int n = 0; n < KB / 8; ++n) {
+      const float p0 = exp2f(s[n][0] - ref_lo), p1 = exp2f(s[n][1] - ref_lo);
+      const float p2 = exp2f(s[n][2] - ref_hi), p3 = exp2f(s[n][3] - ref_hi);
+      ps_lo += p0 + p1;
+      ps_hi += p2 + p3;
+      // accumulator layout of two adjacent n8 tiles == A-operand layout of one k16 step
+      pf[n >> 1][(n & 1) * 2] = pack2(p0, p1);
+      pf[n >> 1][(n & 1) * 2 + 1] = pack2(p2, p3);
+    }
+    l_lo = l_lo * c_lo + ps_lo;
+    l_hi = l_hi * c_hi + ps_hi;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      o[n][0] *= c_lo; o[n][1] *= c_lo; o[n][2] *= c_hi; o[n][3] *= c_hi;
+    }
+    // ---- O += P . V ----
+#pragma unroll
+    for (int kk = 0; kk < KB / 16; ++kk) {        // 16 keys per k-step
+#pragma unroll
+      for (int np = 0; np < NT / 2; ++np) {       // pairs of output n8 tiles (16 dims)
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_t(sV_u + (uint32_t)(((kb + kk * 16 + v_row) * LDS + np * 16 + v_col) * 2), b0, b1, b2, b3);
+        mma16816(o[2 * np], pf[kk], b0, b1);       // dims [0,8): keys [0,8), [8,16)
+        mma16816(o[2 * np + 1], pf[kk], b2, b3);   // dims [8,16)
+      }
+    }
+  }
+  // ---- finalize: row sums across the quad, normalise, store ----
+  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1);
+  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1);
+  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+  const float i_lo = l_lo > 0.f ? 1.f / l_lo : 0.f, i_hi = l_hi > 0.f ? 1.f / l_hi : 0.f;
+  __nv_bfloat16* go = reinterpret_cast<__nv_bfloat16*>(a.out) + (size_t)b * a.o_sb + (size_t)h * DH;
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    const int c = n * 8 + t4 * 2;
+    if (r_lo < a.Tq) *reinterpret_cast<uint32_t*>(go + (size_t)r_lo * a.o_st + c) = pack2(o[n][0] * i_lo, o[n][1] * i_lo);
+    if (r_hi < a.Tq) *reinterpret_cast<uint32_t*>(go + (size_t)r_hi * a.o_st + c) = pack2(o[n][2] * i_hi, o[n][3] * i_hi);
+  }
+}
+
+}  // namespace fa
+
+// Returns 1 when the shape is not covered (caller falls back to the generic kernel), <= 0 otherwise.
+int attention_tc_launch(const tcavp_attn_args& a, cudaStream_t stream) {
+  if (!(a.dh == 64 || a.dh == 128) || a.Tk > 256 || a.Tq > 256 || a.Tk < 1) return 1;
+  auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+  if (!al16(a.q) || !al16(a.k) || !al16(a.v) || !al16(a.out)) return 1;
+  if (a.q_sb % 8 || a.q_st % 8 || a.k_sb % 8 || a.k_st % 8 || a.v_sb % 8 || a.v_st % 8 || a.o_sb % 2 || a.o_st % 2) return 1;
+  const int tk_pad = (a.Tk + fa::KB - 1) / fa::KB * fa::KB;
+  const int max_warps = a.dh == 64 ? 12 : 10;
+  const int need = (a.Tq + 15) / 16;
+  const int chunks = (need + max_warps - 1) / max_warps;
+  const int warps = (need + chunks - 1) / chunks;                              // balanced query chunks
+  const size_t smem = (size_t)2 * tk_pad * (a.dh + fa::PAD) * 2 + (size_t)tk_pad * 4;
+  const dim3 grid(a.B * a.H, chunks);
+  if (a.dh == 64) {
+    TCAVP_CUDA(cudaFuncSetAttribute(fa::attn_flash_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fa::attn_flash_kernel<64><<<grid, warps * 32, smem, stream>>>(a, tk_pad);
+  } else {
+    TCAVP_CUDA(cudaFuncSetAttribute(fa::attn_flash_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fa::attn_flash_kernel<128><<<grid, warps * 32, smem, stream>>>(a, tk_pad);
+  }
+  return check_launch("attn_flash_kernel");
+}
+
 }  // namespace tcavp

@@ -4,13 +4,12 @@
 
 namespace tcavp {
 
-__global__ void rope_table_kernel(float* __restrict__ cs, int L, int half, float theta, int dh) {
+__global__ void rope_table_kernel(float* __restrict__ cs, const float* __restrict__ inv_freq, int L, int half) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= L * half) return;
   const int pos = i / half, j = i % half;
-  // HF:86-88: inv_freq = 1 / theta^(2j/dh) in fp32; HF:131-134: angle = pos * inv_freq in fp32
-  const float inv = 1.0f / powf(theta, (float)(2 * j) / (float)dh);
-  const float ang = (float)pos * inv;
+  // HF:131-134: angle = pos * inv_freq in fp32 (inv_freq comes from the host, computed exactly as HF:86-88 does)
+  const float ang = (float)pos * __ldg(inv_freq + j);
   cs[2 * i] = cosf(ang);
   cs[2 * i + 1] = sinf(ang);
 }
@@ -115,10 +114,10 @@ using namespace tcavp;
 #define STREAM(s) reinterpret_cast<cudaStream_t>(s)
 #define DT_OK(d) ((d) == TCAVP_F32 || (d) == TCAVP_BF16)
 
-extern "C" int tcavp_rope_table(float* cos_sin, int L, int dh, float theta, tcavp_stream_t stream) {
-  TCAVP_REQUIRE(cos_sin && L > 0 && dh > 0 && dh % 2 == 0, "tcavp_rope_table: bad args L=%d dh=%d", L, dh);
+extern "C" int tcavp_rope_table(float* cos_sin, const float* inv_freq, int L, int dh, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(cos_sin && inv_freq && L > 0 && dh > 0 && dh % 2 == 0, "tcavp_rope_table: bad args L=%d dh=%d", L, dh);
   const int n = L * (dh / 2);
-  rope_table_kernel<<<(n + 255) / 256, 256, 0, STREAM(stream)>>>(cos_sin, L, dh / 2, theta, dh);
+  rope_table_kernel<<<(n + 255) / 256, 256, 0, STREAM(stream)>>>(cos_sin, inv_freq, L, dh / 2);
   return check_launch("rope_table_kernel");
 }
 

@@ -27,6 +27,9 @@ class Engine:
         p0 = next(model.ltsf.parameters())
         self.dev = dev = p0.device   # packing works anywhere (host-side tests); forward() requires CUDA
         self.act = act = _ACT[compute_dtype]
+        # The temporal encoder block and the NLinear decoder / lane_fc / post_mlp are a few MFLOP per scene: they always
+        # run in exact fp32 (SIMT), which keeps the regression path's residuals at full precision in bf16 mode.
+        self.small = torch.float32
         self.model_hp = dict(model.hparams)
         self.T_in, self.T_out, self.C = model.seq_len, model.out_len, model.d_model
         with torch.no_grad():
@@ -37,12 +40,12 @@ class Engine:
         self._rope = {}
 
     # ---- packing ----------------------------------------------------------------------------------
-    def _mha(self, m):
-        E = m.embed_dim
-        return dict(qkv=_Lin(m.in_proj_weight, m.in_proj_bias, self.act, self.dev),
-                    q=_Lin(m.in_proj_weight[:E], m.in_proj_bias[:E], self.act, self.dev),
-                    kv=_Lin(m.in_proj_weight[E:], m.in_proj_bias[E:], self.act, self.dev),
-                    out=_Lin(m.out_proj.weight, m.out_proj.bias, self.act, self.dev), E=E, heads=m.num_heads)
+    def _mha(self, m, dtype=None):
+        E, dt = m.embed_dim, dtype or self.act
+        return dict(qkv=_Lin(m.in_proj_weight, m.in_proj_bias, dt, self.dev),
+                    q=_Lin(m.in_proj_weight[:E], m.in_proj_bias[:E], dt, self.dev),
+                    kv=_Lin(m.in_proj_weight[E:], m.in_proj_bias[E:], dt, self.dev),
+                    out=_Lin(m.out_proj.weight, m.out_proj.bias, dt, self.dev), E=E, heads=m.num_heads)
 
     def _ln(self, m):
         return (_f32(m.weight, self.dev), _f32(m.bias, self.dev), m.eps)
@@ -112,7 +115,7 @@ class Engine:
                 wdown=layer.mlp.down_proj.weight.detach().to(dev, act).contiguous()))
 
     def _pack_ltsf(self, lt):
-        act, dev = self.act, self.dev
+        act, dev, small = self.act, self.dev, self.small
         C, T, To = self.C, self.T_in, self.T_out
         d = lt.decoder
         we = torch.stack([l.weight.detach() for l in lt.nlinear_encoder.encoder_linears]).float()   # (C, t, s)
@@ -125,19 +128,19 @@ class Engine:
             wt=_f32(lt.token_proj.weight[:, :, 0], dev), bt=_f32(lt.token_proj.bias, dev),
             we=we.permute(1, 2, 0).contiguous().to(dev), be=be.t().contiguous().to(dev),
             pos=_f32(lt.pos_encoding[0].t(), dev),
-            n1=self._ln(lt.attn_block.norm1), n2=self._ln(lt.attn_block.norm2), mha=self._mha(lt.attn_block.mha),
-            f0=_Lin(lt.attn_block.ffn[0].weight, lt.attn_block.ffn[0].bias, act, dev),
-            f3=_Lin(lt.attn_block.ffn[3].weight, lt.attn_block.ffn[3].bias, act, dev),
+            n1=self._ln(lt.attn_block.norm1), n2=self._ln(lt.attn_block.norm2), mha=self._mha(lt.attn_block.mha, small),
+            f0=_Lin(lt.attn_block.ffn[0].weight, lt.attn_block.ffn[0].bias, small, dev),
+            f3=_Lin(lt.attn_block.ffn[3].weight, lt.attn_block.ffn[3].bias, small, dev),
             wd=wd.permute(1, 2, 0).contiguous().to(dev), bd=bd.t().contiguous().to(dev),
-            lane_fc=_Lin(d.lane_fc.weight[perm], d.lane_fc.bias[perm], act, dev),
+            lane_fc=_Lin(d.lane_fc.weight[perm], d.lane_fc.bias[perm], small, dev),
             dec_proj=_Lin(d.dec_proj.weight, d.dec_proj.bias, act, dev), dec_unproj=_Lin(d.dec_unproj.weight, d.dec_unproj.bias, act, dev),
             cross=self._mha(d.cross_attn),
             fl_ln=self._ln(d.fusion_layer[0]), fl_w1=_f32(d.fusion_layer[1].weight, dev), fl_b1=_f32(d.fusion_layer[1].bias, dev),
             fl_w2=_f32(d.fusion_layer[3].weight, dev), fl_b2=_f32(d.fusion_layer[3].bias, dev),
             wo=_f32(d.out_proj.weight, dev), bo=_f32(d.out_proj.bias, dev), post=None)
         if d.use_post_mlp:
-            self.lt["post"] = (_Lin(d.post_mlp[0].weight[:, perm], d.post_mlp[0].bias, act, dev),
-                               _Lin(d.post_mlp[3].weight[perm], d.post_mlp[3].bias[perm], act, dev))
+            self.lt["post"] = (_Lin(d.post_mlp[0].weight[:, perm], d.post_mlp[0].bias, small, dev),
+                               _Lin(d.post_mlp[3].weight[perm], d.post_mlp[3].bias[perm], small, dev))
 
     # ---- building blocks --------------------------------------------------------------------------
     def _new(self, *shape, dtype=None):
@@ -147,8 +150,8 @@ class Engine:
         """x: (B*T, E) -> attention output (B*T, E) (before out_proj)."""
         E, heads = mha["E"], mha["heads"]
         T = rows_per_b
-        qkv = ops.gemm(x, mha["qkv"].w, self._new(B * T, 3 * E), bias=mha["qkv"].b)
-        out = self._new(B * T, E)
+        qkv = ops.gemm(x, mha["qkv"].w, self._new(B * T, 3 * E, dtype=x.dtype), bias=mha["qkv"].b)
+        out = self._new(B * T, E, dtype=x.dtype)
         dh = E // heads
         ops.attention(qkv, qkv[:, E:], qkv[:, 2 * E:], out, B=B, H=heads, Hkv=heads, Tq=T, Tk=T, dh=dh,
                       q_strides=(T * 3 * E, 3 * E), k_strides=(T * 3 * E, 3 * E), v_strides=(T * 3 * E, 3 * E),
@@ -166,7 +169,7 @@ class Engine:
         return out
 
     def _ln_res(self, y, ln, out=None, **kw):
-        return ops.layernorm(y, ln[0], ln[1], self._new(*y.shape) if out is None else out, eps=ln[2], **kw)
+        return ops.layernorm(y, ln[0], ln[1], self._new(*y.shape, dtype=y.dtype) if out is None else out, eps=ln[2], **kw)
 
     def _encoder_layer(self, x, T, B, L, key_mask=None):
         """torch: nn.TransformerEncoderLayer (post-norm, ReLU)."""
@@ -179,7 +182,7 @@ class Engine:
 
     # ---- sub-models ---------------------------------------------------------------------------------
     def poly_forward(self, polygon, lens):
-        """reference scripts/train.py:362-383 -> (B, D) in the activation dtype."""
+        """reference scripts/train.py:362-383 -> (B, D) fp32."""
         p = self.poly
         B, P, D = polygon.shape[0], polygon.shape[1], p["D"]
         x = self._new(B * P, D)
@@ -187,7 +190,7 @@ class Engine:
         ops.poly_embed(polygon, lens, p["w"], p["b"], p["pos"], x, kmask, B=B, P=P, D=D)
         for L in p["layers"]:
             x = self._encoder_layer(x, P, B, L, kmask)
-        return ops.masked_mean(x, lens, self._new(B, D), B=B, P=P, D=D)
+        return ops.masked_mean(x, lens, self._new(B, D, dtype=self.small), B=B, P=P, D=D)
 
     def qformer_into(self, vision, fused, L_total):
         """reference scripts/train.py:408-414, 520-522: writes image tokens (+vision modality) into fused[:, :Q]."""
@@ -257,30 +260,31 @@ class Engine:
 
     def ltsf_encode(self, x, B):
         """reference scripts/train.py:837-840 -> enc (B*T_in, C)."""
-        lt, C, T = self.lt, self.C, self.T_in
-        e0 = ops.ltsf_encode(x, lt["wt"], lt["bt"], lt["we"], lt["be"], lt["pos"], self._new(B * T, C), B=B, F=2, C=C, T_in=T)
+        lt, C, T, sm = self.lt, self.C, self.T_in, self.small
+        e0 = ops.ltsf_encode(x, lt["wt"], lt["bt"], lt["we"], lt["be"], lt["pos"], self._new(B * T, C, dtype=sm), B=B, F=2, C=C, T_in=T)
         xn = self._ln_res(e0, lt["n1"])
         a = self._self_attention(xn, T, B, lt["mha"])
-        y = ops.gemm(a, lt["mha"]["out"].w, self._new(B * T, C), bias=lt["mha"]["out"].b, residual=xn)
+        y = ops.gemm(a, lt["mha"]["out"].w, self._new(B * T, C, dtype=sm), bias=lt["mha"]["out"].b, residual=xn)
         r = self._ln_res(y, lt["n2"])
-        h = ops.gemm(r, lt["f0"].w, self._new(B * T, lt["f0"].N), bias=lt["f0"].b, act=ops.ACT_RELU)
-        return ops.gemm(h, lt["f3"].w, self._new(B * T, C), bias=lt["f3"].b, residual=r)
+        h = ops.gemm(r, lt["f0"].w, self._new(B * T, lt["f0"].N, dtype=sm), bias=lt["f0"].b, act=ops.ACT_RELU)
+        return ops.gemm(h, lt["f3"].w, self._new(B * T, C, dtype=sm), bias=lt["f3"].b, residual=r)
 
     def ltsf_decode(self, enc, poly_emb, fh, x, B, L, y=None, norm_stat=None):
         """reference scripts/train.py:767-806 + 941-943 (+ 945-962 / 1302-1322 when y is given)."""
-        lt, C, T, To = self.lt, self.C, self.T_in, self.T_out
+        lt, C, T, To, sm = self.lt, self.C, self.T_in, self.T_out, self.small
         H = self.llm["H"]
-        adj = ops.gemm(poly_emb, lt["lane_fc"].w, self._new(B, To * C), bias=lt["lane_fc"].b)
-        dec = ops.nlinear_decode(enc, lt["wd"], lt["bd"], adj, self._new(B, To * C), B=B, C=C, T_in=T, T_out=To)
+        adj = ops.gemm(poly_emb, lt["lane_fc"].w, self._new(B, To * C, dtype=sm), bias=lt["lane_fc"].b)
+        dec = ops.nlinear_decode(enc, lt["wd"], lt["bd"], adj, self._new(B, To * C, dtype=sm), B=B, C=C, T_in=T, T_out=To)
         if lt["post"] is not None:
             p0, p3 = lt["post"]
-            h = ops.gemm(dec, p0.w, self._new(B, p0.N), bias=p0.b, act=ops.ACT_RELU)
-            dec = ops.gemm(h, p3.w, self._new(B, To * C), bias=p3.b)
-        dec_t = dec.view(B * To, C)
-        q = ops.gemm(dec_t, lt["dec_proj"].w, self._new(B * To, H), bias=lt["dec_proj"].b)
+            h = ops.gemm(dec, p0.w, self._new(B, p0.N, dtype=sm), bias=p0.b, act=ops.ACT_RELU)
+            dec = ops.gemm(h, p3.w, self._new(B, To * C, dtype=sm), bias=p3.b)
+        dec_t = dec.view(B * To, C)                  # fp32 residual path of the regression head
+        dq = dec_t if self.act == sm else ops.cast(dec_t, self._new(B * To, C), rows=B * To, cols=C)
+        q = ops.gemm(dq, lt["dec_proj"].w, self._new(B * To, H), bias=lt["dec_proj"].b)
         a = self._cross_attention(q, To, fh, L, B, lt["cross"])
         co = ops.gemm(a, lt["cross"]["out"].w, self._new(B * To, H), bias=lt["cross"]["out"].b)
-        fused = ops.gemm(co, lt["dec_unproj"].w, self._new(B * To, C), bias=lt["dec_unproj"].b, residual=dec_t)
+        fused = ops.gemm(co, lt["dec_unproj"].w, self._new(B * To, C, dtype=sm), bias=lt["dec_unproj"].b, residual=dec_t)
         decoded = torch.empty(B, 2, To, dtype=torch.float32, device=self.dev)
         out = {"decoded": decoded}
         metrics = per_scene = None

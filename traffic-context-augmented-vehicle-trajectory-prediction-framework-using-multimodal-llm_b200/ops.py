@@ -35,6 +35,71 @@ class AttnArgs(Structure):
                 ("dtype", c_int), ("scale", c_float), ("causal", c_int), ("key_mask", c_void_p)]
 
 
+_PROF = None
+
+
+class LaunchProfiler:
+    """Times every libtcavp launch with CUDA events on the launching stream (bench.py's roofline numbers).
+    Events are recorded around each launch inside the timed region; nothing synchronises until summary()."""
+
+    def __init__(self):
+        self.rec = []
+
+    def __enter__(self):
+        global _PROF
+        _PROF = self
+        return self
+
+    def __exit__(self, *a):
+        global _PROF
+        _PROF = None
+
+    def add(self, kernel, flops, nbytes, e0, e1):
+        self.rec.append((kernel, flops, nbytes, e0, e1))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        groups = {}
+        for kernel, flops, nbytes, e0, e1 in self.rec:
+            g = groups.setdefault(kernel, dict(kernel=kernel, launches=0, time_ms=0.0, flops=0.0, bytes=0.0))
+            g["launches"] += 1
+            g["time_ms"] += e0.elapsed_time(e1)
+            g["flops"] += flops
+            g["bytes"] += nbytes
+        for g in groups.values():
+            g["avg_ms"] = g["time_ms"] / max(g["launches"], 1)
+            g["tflops"] = g["flops"] / (g["time_ms"] * 1e-3) / 1e12 if g["time_ms"] > 0 else 0.0
+            g["gbs"] = g["bytes"] / (g["time_ms"] * 1e-3) / 1e9 if g["time_ms"] > 0 else 0.0
+        order = sorted(groups.values(), key=lambda g: -g["time_ms"])
+        total = sum(g["time_ms"] for g in order) or 1.0
+        brief = [dict(kernel=g["kernel"], launches=g["launches"], time_ms=round(g["time_ms"], 3), share=round(g["time_ms"] / total, 4),
+                      tflops=round(g["tflops"], 1), gbs=round(g["gbs"], 1)) for g in order]
+        return {"dominant": order[0] if order else None, "groups": brief}
+
+
+class _Timed:
+    __slots__ = ("kernel", "flops", "nbytes", "e0")
+
+    def __init__(self, kernel, flops=0.0, nbytes=0.0):
+        self.kernel, self.flops, self.nbytes = kernel, flops, nbytes
+
+    def __enter__(self):
+        if _PROF is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *a):
+        if _PROF is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _PROF.add(self.kernel, self.flops, self.nbytes, self.e0, e1)
+
+
+def _nb(*ts):
+    return float(sum(t.numel() * t.element_size() for t in ts if t is not None))
+
+
 def dt(t):
     try:
         return _DT[t.dtype]
@@ -77,7 +142,13 @@ def gemm(a, w, out, *, M=None, N=None, K=None, lda=None, ldw=None, ldo=None, bia
         g.residual, g.ldr, g.res_dtype = residual.data_ptr(), (residual.stride(0) if ldr is None else ldr), dt(residual)
     g.act = act
     g.remap_gi, g.remap_go, g.remap_off = remap
-    _lib.check(_lib.load().tcavp_gemm(byref(g), _stream()), "tcavp_gemm")
+    if g.in_dtype == BF16:
+        kern = "gemm_tc_kernel<%d>" % (32 if g.N <= 32 else 64 if g.N <= 64 else 128 if g.N <= 128 else 256)
+    else:
+        kern = "gemm_simt_kernel"
+    esz = a.element_size()
+    with _Timed(kern, 2.0 * g.M * g.N * g.K, float(g.M * g.K * esz + g.N * g.K * esz + g.M * g.N * out.element_size())):
+        _lib.check(_lib.load().tcavp_gemm(byref(g), _stream()), "tcavp_gemm")
     return out
 
 
@@ -96,7 +167,10 @@ def attention(q, k, v, out, *, B, H, Hkv, Tq, Tk, dh, q_strides, k_strides, v_st
         if key_mask.dtype != torch.int32:
             raise TypeError("attention: key_mask must be int32")
         a.key_mask = key_mask.data_ptr()
-    _lib.check(_lib.load().tcavp_attention(byref(a), _stream()), "tcavp_attention")
+    tc = a.dtype == BF16 and dh in (64, 128) and Tq == Tk and Tk <= 256
+    fl = 4.0 * B * H * Tq * Tk * dh * (0.5 if causal else 1.0)
+    with _Timed("attn_flash_kernel" if tc else "attn_warp_kernel", fl, 2.0 * q.element_size() * B * dh * (H * Tq + Hkv * Tk)):
+        _lib.check(_lib.load().tcavp_attention(byref(a), _stream()), "tcavp_attention")
     return out
 
 
@@ -104,7 +178,8 @@ def layernorm(x, w, b, out, *, residual=None, eps=1e-5, remap=(0, 0, 0), rowvec=
     _need_cuda(x, w, b, out, residual, rowvec)
     rows = x.numel() // x.shape[-1] if rows is None else rows
     cols = x.shape[-1] if cols is None else cols
-    _lib.check(_lib.load().tcavp_layernorm(_p(x), _p(residual), _p(w), _p(b), _p(out), rows, cols, c_float(eps), dt(x), dt(out),
+    with _Timed("layernorm_kernel"):
+        _lib.check(_lib.load().tcavp_layernorm(_p(x), _p(residual), _p(w), _p(b), _p(out), rows, cols, c_float(eps), dt(x), dt(out),
                                            remap[0], remap[1], remap[2], _p(rowvec), _stream()), "tcavp_layernorm")
     return out
 
@@ -114,20 +189,25 @@ def rmsnorm(x, w, out, *, eps, rows=None, cols=None, ldo=None):
     rows = x.numel() // x.shape[-1] if rows is None else rows
     cols = x.shape[-1] if cols is None else cols
     ldo = cols if ldo is None else ldo
-    _lib.check(_lib.load().tcavp_rmsnorm(_p(x), _p(w), _p(out), rows, cols, ldo, c_float(eps), dt(x), dt(out), _stream()),
+    with _Timed("rmsnorm_kernel"):
+        _lib.check(_lib.load().tcavp_rmsnorm(_p(x), _p(w), _p(out), rows, cols, ldo, c_float(eps), dt(x), dt(out), _stream()),
                "tcavp_rmsnorm")
     return out
 
 
 def rope_table(L, dh, theta, device):
+    # HF:86-88 inv_freq, evaluated on the host exactly as transformers does
+    inv = (1.0 / (theta ** (torch.arange(0, dh, 2, dtype=torch.int64).float() / dh))).to(device)
     t = torch.empty(L, dh // 2, 2, dtype=torch.float32, device=device)
-    _lib.check(_lib.load().tcavp_rope_table(_p(t), L, dh, c_float(theta), _stream()), "tcavp_rope_table")
+    with _Timed("rope_table_kernel"):
+        _lib.check(_lib.load().tcavp_rope_table(_p(t), _p(inv), L, dh, _stream()), "tcavp_rope_table")
     return t
 
 
 def rope_(qkv, *, rows, L, ld, n_q_heads, n_k_heads, dh, table):
     _need_cuda(qkv, table)
-    _lib.check(_lib.load().tcavp_rope(_p(qkv), rows, L, ld, n_q_heads, n_k_heads, dh, _p(table), dt(qkv), _stream()), "tcavp_rope")
+    with _Timed("rope_kernel"):
+        _lib.check(_lib.load().tcavp_rope(_p(qkv), rows, L, ld, n_q_heads, n_k_heads, dh, _p(table), dt(qkv), _stream()), "tcavp_rope")
     return qkv
 
 
@@ -135,46 +215,53 @@ def embed_text(ids, attn_mask, embed, text_mod, fused, mask_out, *, B, L_text, n
     _need_cuda(ids, attn_mask, embed, text_mod, fused, mask_out)
     if ids.dtype != torch.int64 or (attn_mask is not None and attn_mask.dtype != torch.int64):
         raise TypeError("embed_text: ids / attention_mask must be int64")
-    _lib.check(_lib.load().tcavp_embed_text(_p(ids), _p(attn_mask), _p(embed), dt(embed), _p(text_mod), _p(fused), dt(fused),
+    with _Timed("embed_text_kernel"):
+        _lib.check(_lib.load().tcavp_embed_text(_p(ids), _p(attn_mask), _p(embed), dt(embed), _p(text_mod), _p(fused), dt(fused),
                                             _p(mask_out), B, L_text, n_img, H, embed.shape[0], _stream()), "tcavp_embed_text")
 
 
 def add_rowvec(x, rowvec, out, *, rows, cols, remap=(0, 0, 0)):
     _need_cuda(x, rowvec, out)
-    _lib.check(_lib.load().tcavp_add_rowvec(_p(x), _p(rowvec), _p(out), rows, cols, dt(x), dt(out), remap[0], remap[1], remap[2],
+    with _Timed("add_rowvec_kernel"):
+        _lib.check(_lib.load().tcavp_add_rowvec(_p(x), _p(rowvec), _p(out), rows, cols, dt(x), dt(out), remap[0], remap[1], remap[2],
                                             _stream()), "tcavp_add_rowvec")
     return out
 
 
 def cast(x, out, *, rows, cols, ldi=None, ldo=None, in_row_mod=0):
     _need_cuda(x, out)
-    _lib.check(_lib.load().tcavp_cast(_p(x), cols if ldi is None else ldi, dt(x), _p(out), cols if ldo is None else ldo, dt(out),
+    with _Timed("cast_kernel"):
+        _lib.check(_lib.load().tcavp_cast(_p(x), cols if ldi is None else ldi, dt(x), _p(out), cols if ldo is None else ldo, dt(out),
                                       rows, cols, in_row_mod, _stream()), "tcavp_cast")
     return out
 
 
 def poly_embed(polygon, lens, w, bias, pos, out, key_mask, *, B, P, D):
     _need_cuda(polygon, lens, w, bias, pos, out, key_mask)
-    _lib.check(_lib.load().tcavp_poly_embed(_p(polygon), _p(lens), _p(w), _p(bias), _p(pos), _p(out), dt(out), _p(key_mask), B, P, D,
+    with _Timed("poly_embed_kernel"):
+        _lib.check(_lib.load().tcavp_poly_embed(_p(polygon), _p(lens), _p(w), _p(bias), _p(pos), _p(out), dt(out), _p(key_mask), B, P, D,
                                             _stream()), "tcavp_poly_embed")
 
 
 def masked_mean(x, lens, out, *, B, P, D):
     _need_cuda(x, lens, out)
-    _lib.check(_lib.load().tcavp_masked_mean(_p(x), dt(x), _p(lens), _p(out), dt(out), B, P, D, _stream()), "tcavp_masked_mean")
+    with _Timed("masked_mean_kernel"):
+        _lib.check(_lib.load().tcavp_masked_mean(_p(x), dt(x), _p(lens), _p(out), dt(out), B, P, D, _stream()), "tcavp_masked_mean")
     return out
 
 
 def ltsf_encode(x, wt, bt, we, be, pos, enc, *, B, F, C, T_in):
     _need_cuda(x, wt, bt, we, be, pos, enc)
-    _lib.check(_lib.load().tcavp_ltsf_encode(_p(x), _p(wt), _p(bt), _p(we), _p(be), _p(pos), _p(enc), dt(enc), B, F, C, T_in,
+    with _Timed("ltsf_encode_kernel"):
+        _lib.check(_lib.load().tcavp_ltsf_encode(_p(x), _p(wt), _p(bt), _p(we), _p(be), _p(pos), _p(enc), dt(enc), B, F, C, T_in,
                                              _stream()), "tcavp_ltsf_encode")
     return enc
 
 
 def nlinear_decode(enc, wd, bd, lane_adj, dec, *, B, C, T_in, T_out):
     _need_cuda(enc, wd, bd, lane_adj, dec)
-    _lib.check(_lib.load().tcavp_nlinear_decode(_p(enc), dt(enc), _p(wd), _p(bd), _p(lane_adj), 0 if lane_adj is None else dt(lane_adj),
+    with _Timed("nlinear_decode_kernel"):
+        _lib.check(_lib.load().tcavp_nlinear_decode(_p(enc), dt(enc), _p(wd), _p(bd), _p(lane_adj), 0 if lane_adj is None else dt(lane_adj),
                                                 _p(dec), dt(dec), B, C, T_in, T_out, _stream()), "tcavp_nlinear_decode")
     return dec
 
@@ -182,7 +269,8 @@ def nlinear_decode(enc, wd, bd, lane_adj, dec, *, B, C, T_in, T_out):
 def fusion_head(fused, ln_w, ln_b, w1, b1, w2, b2, wo, bo, x, decoded, *, y=None, norm_stat=None, metrics=None, per_scene=None,
                 B, C, T_in, T_out):
     _need_cuda(fused, x, decoded, y, norm_stat, metrics, per_scene)
-    _lib.check(_lib.load().tcavp_fusion_head(_p(fused), dt(fused), _p(ln_w), _p(ln_b), _p(w1), _p(b1), _p(w2), _p(b2), _p(wo), _p(bo),
+    with _Timed("fusion_head_kernel"):
+        _lib.check(_lib.load().tcavp_fusion_head(_p(fused), dt(fused), _p(ln_w), _p(ln_b), _p(w1), _p(b1), _p(w2), _p(b2), _p(wo), _p(bo),
                                              _p(x), _p(decoded), _p(y), _p(norm_stat), _p(metrics), _p(per_scene), B, C, T_in, T_out,
                                              _stream()), "tcavp_fusion_head")
     return decoded
@@ -190,7 +278,8 @@ def fusion_head(fused, ln_w, ln_b, w1, b1, w2, b2, wo, bo, x, decoded, *, y=None
 
 def traj_metrics(decoded, y, norm_stat, metrics, per_scene, *, B, T_out):
     _need_cuda(decoded, y, norm_stat, metrics, per_scene)
-    _lib.check(_lib.load().tcavp_traj_metrics(_p(decoded), _p(y), _p(norm_stat), _p(metrics), _p(per_scene), B, T_out, _stream()),
+    with _Timed("traj_metrics_kernel"):
+        _lib.check(_lib.load().tcavp_traj_metrics(_p(decoded), _p(y), _p(norm_stat), _p(metrics), _p(per_scene), B, T_out, _stream()),
                "tcavp_traj_metrics")
 
 
