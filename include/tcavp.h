@@ -64,6 +64,11 @@ long long tcavp_launch_count(void);
  *              16 image-token rows of each scene straight into the fused (B, L, H) buffer,
  *              train.py:521-528).  Otherwise m' = m.
  *   residual   optional [M', N] tensor added after the activation; may alias `out`.
+ *   RoPE       rope_cols > 0 fuses HF's apply_rotary_pos_emb (HF:146-170) into the epilogue of the packed QKV
+ *              projection: output columns [0, rope_cols) are heads of width rope_dh whose W rows were
+ *              permuted at pack time so that the rotation partners (i, i + dh/2) sit in adjacent columns
+ *              (2i, 2i+1); row m has position m % rope_L; rope_cos_sin is the [L, dh/2, 2] table of
+ *              tcavp_rope_table.  q.k is invariant under the shared permutation, v is not permuted.
  */
 typedef struct tcavp_gemm_args {
   int M, N, K;
@@ -75,6 +80,7 @@ typedef struct tcavp_gemm_args {
   const void* residual; int ldr; int res_dtype;
   int act;
   int remap_gi, remap_go, remap_off;
+  const float* rope_cos_sin; int rope_L, rope_dh, rope_cols;
 } tcavp_gemm_args;
 
 int tcavp_gemm(const tcavp_gemm_args* args, tcavp_stream_t stream);

@@ -311,3 +311,25 @@ def test_fusion_head_and_metrics(ops, B, To):
     ops.traj_metrics(decoded, y.to(DEV), ns.to(DEV), m2, per2, B=B, T_out=To)
     torch.testing.assert_close(per2.cpu(), per.cpu(), rtol=1e-5, atol=1e-4)
     torch.testing.assert_close(m2[:5].cpu(), m[:5], rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("nh,nkv,dh", [(12, 12, 64), (4, 2, 32), (4, 2, 128)])
+def test_gemm_fused_rope(ops, dtype, nh, nkv, dh):
+    """QKV projection with HF's rotary embedding fused into the epilogue (rotation partners made adjacent by a row
+    permutation of W) == plain projection followed by the oracle's apply_rotary_pos_emb, up to that permutation."""
+    td = torch.float32 if dtype == "fp32" else torch.bfloat16
+    B, L, K = 3, 40, 136
+    N = (nh + 2 * nkv) * dh
+    x, w = _rand(B * L, K, seed=1).to(td), _rand(N, K, seed=2, scale=K ** -0.5).to(td)
+    hp = torch.stack([torch.arange(dh // 2), torch.arange(dh // 2) + dh // 2], dim=1).reshape(-1)
+    perm = torch.cat([h * dh + hp for h in range(nh + nkv)] + [torch.arange((nh + nkv) * dh, N)])
+    table = ops.rope_table(L, dh, 10000.0, DEV)
+    out = torch.empty(B * L, N, dtype=torch.float32, device=DEV)
+    ops.gemm(x.to(DEV), w[perm].contiguous().to(DEV), out, rope=(table, L, dh, (nh + nkv) * dh))
+    y = (x.float() @ w.float().t()).view(B, L, N)
+    cos, sin = R.rope_cos_sin(L, dh, 10000.0)
+    qk = y[..., : (nh + nkv) * dh].reshape(B, L, nh + nkv, dh)
+    qk = qk * cos[None, :, None, :] + R.rotate_half(qk) * sin[None, :, None, :]
+    want = torch.cat([qk.reshape(B, L, -1), y[..., (nh + nkv) * dh:]], dim=-1).view(B * L, N)[:, perm]
+    torch.testing.assert_close(out.cpu(), want, rtol=1e-4, atol=1e-4)

@@ -1,6 +1,6 @@
 """Stage-by-stage diagnostics of the CUDA forward against the golden fixtures (run on the GPU box)."""
 import sys, time, torch
-sys.path.insert(0, "tests")
+import os; ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import build_filled_model, load_golden
 import tcavp_b200.lib as L
 L.build()

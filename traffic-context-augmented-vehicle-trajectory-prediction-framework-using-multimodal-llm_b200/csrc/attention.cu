@@ -4,11 +4,13 @@
 //                  processed four at a time (four interleaved warp-shuffle reductions), online softmax in
 //                  fp32.  Handles every head_dim on the path (16 ... 2048), causal and key-padding masks.
 //   flash path   : bf16, head_dim 64/128 (the LLM self-attention, HF:251-289) — see attention_tc.cu.
+//   wide path    : bf16, few queries against a wide head (LTSF cross-attention) — see attention_x.cu.
 #include "common.cuh"
 
 namespace tcavp {
 
 int attention_tc_launch(const tcavp_attn_args& a, cudaStream_t stream);   // attention_tc.cu; returns 1 if not applicable
+int attention_x_launch(const tcavp_attn_args& a, cudaStream_t stream);    // attention_x.cu;  returns 1 if not applicable
 
 template <typename T, int NE>   // NE = ceil(dh / 32) head-dim elements per lane
 __global__ void __launch_bounds__(128) attn_warp_kernel(tcavp_attn_args a) {
@@ -123,7 +125,7 @@ extern "C" int tcavp_attention(const tcavp_attn_args* a, tcavp_stream_t stream_)
   TCAVP_REQUIRE(!a->causal || a->Tq == a->Tk, "tcavp_attention: causal needs Tq == Tk");
   TCAVP_REQUIRE(a->dtype == TCAVP_F32 || a->dtype == TCAVP_BF16, "tcavp_attention: bad dtype");
   if (a->dtype == TCAVP_BF16) {
-    const int rc = attention_tc_launch(*a, stream);
+    int rc = a->dh > 128 ? attention_x_launch(*a, stream) : attention_tc_launch(*a, stream);
     if (rc <= 0) return rc;
     return launch_warp<__nv_bfloat16>(*a, stream);
   }

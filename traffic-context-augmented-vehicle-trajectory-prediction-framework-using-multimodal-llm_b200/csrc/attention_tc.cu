@@ -29,8 +29,16 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int DH>
-__global__ void __launch_bounds__(DH == 64 ? 384 : 320) attn_flash_kernel(tcavp_attn_args a, int tk_pad_all) {
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// MAXT / MINB: launch bounds.  (288, 2) keeps two 9-warp CTAs (L = 144) resident per SM so the K/V staging of one
+// overlaps the MMAs of the other.
+template <int DH, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) attn_flash_kernel(tcavp_attn_args a, int tk_pad_all) {
   constexpr int LDS = DH + PAD;            // smem row stride in elements
   constexpr int KS = DH / 16;              // k-steps of the Q.K^T contraction
   constexpr int NT = DH / 8;               // n8 tiles of the output
@@ -38,6 +46,7 @@ __global__ void __launch_bounds__(DH == 64 ? 384 : 320) attn_flash_kernel(tcavp_
   __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem);
   __nv_bfloat16* sV = sK + (size_t)tk_pad_all * LDS;
   int* sMask = reinterpret_cast<int*>(sV + (size_t)tk_pad_all * LDS);   // [tk_pad_all] 1 = attend
+  int* sBlkValid = sMask + tk_pad_all;                                  // [tk_pad_all / 64] all keys of the block attendable
 
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
   const int hk = h / (a.H / a.Hkv);
@@ -64,6 +73,12 @@ __global__ void __launch_bounds__(DH == 64 ? 384 : 320) attn_flash_kernel(tcavp_
   }
   for (int j = threadIdx.x; j < tk_pad; j += blockDim.x)
     sMask[j] = (j < a.Tk) && (!a.key_mask || a.key_mask[(size_t)b * a.Tk + j] != 0);
+  __syncthreads();
+  if (threadIdx.x < tk_pad / KB) {
+    int all = 1;
+    for (int j = 0; j < KB; ++j) all &= sMask[threadIdx.x * KB + j];
+    sBlkValid[threadIdx.x] = all;
+  }
   __syncthreads();
 
   const int row0 = q_base + warp * 16;
@@ -114,18 +129,29 @@ __global__ void __launch_bounds__(DH == 64 ? 384 : 320) attn_flash_kernel(tcavp_
     }
     // ---- mask + online softmax ----
     float mx_lo = m_lo, mx_hi = m_hi;
+    const bool need_mask = !sBlkValid[kb / KB] || (a.causal && kb + KB - 1 > row0);   // warp-uniform
+    if (need_mask) {
+#pragma unroll
+      for (int n = 0; n < KB / 8; ++n) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = kb + n * 8 + t4 * 2 + e;
+          const bool okj = sMask[j] != 0;
+          const bool ok_lo = okj && (!a.causal || j <= r_lo), ok_hi = okj && (!a.causal || j <= r_hi);
+          s[n][e] = ok_lo ? s[n][e] * sl2 : -INFINITY;
+          s[n][2 + e] = ok_hi ? s[n][2 + e] * sl2 : -INFINITY;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int n = 0; n < KB / 8; ++n) {
+        s[n][0] *= sl2; s[n][1] *= sl2; s[n][2] *= sl2; s[n][3] *= sl2;
+      }
+    }
 #pragma unroll
     for (int n = 0; n < KB / 8; ++n) {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int j = kb + n * 8 + t4 * 2 + e;
-        const bool okj = sMask[j] != 0;
-        const bool ok_lo = okj && (!a.causal || j <= r_lo), ok_hi = okj && (!a.causal || j <= r_hi);
-        s[n][e] = ok_lo ? s[n][e] * sl2 : -INFINITY;
-        s[n][2 + e] = ok_hi ? s[n][2 + e] * sl2 : -INFINITY;
-        mx_lo = fmaxf(mx_lo, s[n][e]);
-        mx_hi = fmaxf(mx_hi, s[n][2 + e]);
-      }
+      mx_lo = fmaxf(mx_lo, fmaxf(s[n][0], s[n][1]));
+      mx_hi = fmaxf(mx_hi, fmaxf(s[n][2], s[n][3]));
     }
     mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
     mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
@@ -133,15 +159,15 @@ __global__ void __launch_bounds__(DH == 64 ? 384 : 320) attn_flash_kernel(tcavp_
     mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
     // rows with nothing attendable yet keep m = -inf: use 0 as the reference point so exp2(-inf - 0) = 0
     const float ref_lo = mx_lo == -INFINITY ? 0.f : mx_lo, ref_hi = mx_hi == -INFINITY ? 0.f : mx_hi;
-    const float c_lo = exp2f(m_lo - ref_lo), c_hi = exp2f(m_hi - ref_hi);
+    const float c_lo = ex2(m_lo - ref_lo), c_hi = ex2(m_hi - ref_hi);
     m_lo = mx_lo;
     m_hi = mx_hi;
     float ps_lo = 0.f, ps_hi = 0.f;
     uint32_t pf[KB / 16][4];
 #pragma unroll
     for (int n = 0; n < KB / 8; ++n) {
-      const float p0 = exp2f(s[n][0] - ref_lo), p1 = exp2f(s[n][1] - ref_lo);
-      const float p2 = exp2f(s[n][2] - ref_hi), p3 = exp2f(s[n][3] - ref_hi);
+      const float p0 = ex2(s[n][0] - ref_lo), p1 = ex2(s[n][1] - ref_lo);
+      const float p2 = ex2(s[n][2] - ref_hi), p3 = ex2(s[n][3] - ref_hi);
       ps_lo += p0 + p1;
       ps_hi += p2 + p3;
       // accumulator layout of two adjacent n8 tiles == A-operand layout of one k16 step
@@ -194,15 +220,20 @@ int attention_tc_launch(const tcavp_attn_args& a, cudaStream_t stream) {
   const int need = (a.Tq + 15) / 16;
   const int chunks = (need + max_warps - 1) / max_warps;
   const int warps = (need + chunks - 1) / chunks;                              // balanced query chunks
-  const size_t smem = (size_t)2 * tk_pad * (a.dh + fa::PAD) * 2 + (size_t)tk_pad * 4;
+  const size_t smem = (size_t)2 * tk_pad * (a.dh + fa::PAD) * 2 + (size_t)tk_pad * 4 + (size_t)(tk_pad / fa::KB) * 4;
   const dim3 grid(a.B * a.H, chunks);
+#define TCAVP_FLASH(DH, MAXT, MINB)                                                                                         \
+  do {                                                                                                                      \
+    TCAVP_CUDA(cudaFuncSetAttribute(fa::attn_flash_kernel<DH, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    fa::attn_flash_kernel<DH, MAXT, MINB><<<grid, warps * 32, smem, stream>>>(a, tk_pad);                                    \
+  } while (0)
   if (a.dh == 64) {
-    TCAVP_CUDA(cudaFuncSetAttribute(fa::attn_flash_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fa::attn_flash_kernel<64><<<grid, warps * 32, smem, stream>>>(a, tk_pad);
+    if (warps <= 9) TCAVP_FLASH(64, 288, 2);
+    else TCAVP_FLASH(64, 384, 1);
   } else {
-    TCAVP_CUDA(cudaFuncSetAttribute(fa::attn_flash_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fa::attn_flash_kernel<128><<<grid, warps * 32, smem, stream>>>(a, tk_pad);
+    TCAVP_FLASH(128, 320, 1);
   }
+#undef TCAVP_FLASH
   return check_launch("attn_flash_kernel");
 }
 

@@ -79,6 +79,7 @@ struct EpilogueParams {
   const void* residual; int ldr; int res_dtype;
   int act;
   int remap_gi, remap_go, remap_off;
+  const float* rope; int rope_L, rope_dh, rope_cols;   // fused rotary embedding on adjacent column pairs
 };
 
 __device__ __forceinline__ int remap_row(int gi, int go, int off, int m) {

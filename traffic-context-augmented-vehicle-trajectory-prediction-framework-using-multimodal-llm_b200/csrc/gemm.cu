@@ -131,6 +131,18 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueParams& p, int m, i
   }
   if (n0 >= p.N) return;
   const bool full = (n0 + cnt <= p.N);
+  if (p.rope_cols > 0 && n0 < p.rope_cols) {
+    // chunk = 32 columns = 16 rotation pairs of one head (rope_dh is a multiple of 32)
+    const int half = p.rope_dh >> 1;
+    const float2* cs = reinterpret_cast<const float2*>(p.rope) + (size_t)(m % p.rope_L) * half + ((n0 % p.rope_dh) >> 1);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float2 t = __ldg(cs + j);
+      const float x1 = o[2 * j], x2 = o[2 * j + 1];
+      o[2 * j] = x1 * t.x - x2 * t.y;
+      o[2 * j + 1] = x2 * t.x + x1 * t.y;
+    }
+  }
   if (p.bias) {
 #pragma unroll
     for (int j = 0; j < 32; ++j)
@@ -432,6 +444,16 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A,
     if (ep.act == TCAVP_ACT_SWIGLU) {
       epilogue_store(ep, m, mo, n / 2, silu_f(acc[i][0]) * acc[i][1]);
       epilogue_store(ep, m, mo, n / 2 + 1, silu_f(acc[i][2]) * acc[i][3]);
+    } else if (ep.rope_cols > 0 && n < ep.rope_cols) {
+      const int half = ep.rope_dh >> 1;
+      const float2* cs = reinterpret_cast<const float2*>(ep.rope) + (size_t)(m % ep.rope_L) * half + ((n % ep.rope_dh) >> 1);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float2 t = __ldg(cs + j);
+        const float x1 = acc[i][2 * j], x2 = acc[i][2 * j + 1];
+        epilogue_store(ep, m, mo, n + 2 * j, x1 * t.x - x2 * t.y);
+        epilogue_store(ep, m, mo, n + 2 * j + 1, x2 * t.x + x1 * t.y);
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) epilogue_store(ep, m, mo, n + j, acc[i][j]);
@@ -461,6 +483,12 @@ extern "C" int tcavp_gemm(const tcavp_gemm_args* a, tcavp_stream_t stream_) {
   ep.residual = a->residual; ep.ldr = a->ldr; ep.res_dtype = a->res_dtype;
   ep.act = a->act;
   ep.remap_gi = a->remap_gi; ep.remap_go = a->remap_go; ep.remap_off = a->remap_off;
+  ep.rope = a->rope_cos_sin; ep.rope_L = a->rope_L; ep.rope_dh = a->rope_dh; ep.rope_cols = a->rope_cos_sin ? a->rope_cols : 0;
+  if (ep.rope_cols > 0) {
+    TCAVP_REQUIRE(a->act == TCAVP_ACT_NONE && !a->bias, "tcavp_gemm: fused RoPE needs act NONE and no bias");
+    TCAVP_REQUIRE(a->rope_L > 0 && a->rope_dh >= 32 && a->rope_dh % 32 == 0 && a->rope_cols % a->rope_dh == 0 && a->rope_cols <= a->N,
+                  "tcavp_gemm: bad RoPE geometry (L=%d dh=%d cols=%d)", a->rope_L, a->rope_dh, a->rope_cols);
+  }
   TCAVP_REQUIRE(ep.ldo >= ep.N, "tcavp_gemm: ldo %d < output width %d", ep.ldo, ep.N);
   TCAVP_REQUIRE(!ep.residual || ep.ldr >= ep.N, "tcavp_gemm: ldr too small");
 

@@ -92,6 +92,11 @@ class Engine:
                         kx=kx, n_lora=n_t * r, vocab=c["vocab_size"], layers=[],
                         embed=lm.model.embed_tokens.weight.detach().to(dev, act).contiguous(), norm=_f32(lm.model.norm.weight, dev))
         nq, nk = nh * dh, nkv * dh
+        # RoPE fusion: within every q / k head, move rotation partners (i, i + dh/2) to adjacent rows (2i, 2i+1) so the
+        # GEMM epilogue can rotate in registers; q.k is invariant under the shared permutation, v keeps its order.
+        self.llm["fuse_rope"] = dh % 32 == 0
+        hp = torch.stack([torch.arange(dh // 2), torch.arange(dh // 2) + dh // 2], dim=1).reshape(-1)
+        qk_perm = torch.cat([h * dh + hp for h in range(nh + nkv)] + [torch.arange(nq + nk, nq + 2 * nk)]).to(dev)
         for layer in lm.model.layers:
             sa = layer.self_attn
             rows = {"q_proj": (0, nq), "k_proj": (nq, nq + nk), "v_proj": (nq + nk, nq + 2 * nk)}
@@ -106,6 +111,8 @@ class Engine:
                     a_cat[ti * r:(ti + 1) * r] = mod.lora_A["default"].weight.detach().to(dev, act)
                 else:
                     wqkv[r0:r1, :H] = mod.weight.detach().to(dev, act)
+            if self.llm["fuse_rope"]:
+                wqkv = wqkv[qk_perm].contiguous()
             gu = torch.empty(2 * I, H, dtype=act, device=dev)
             gu[0::2] = layer.mlp.gate_proj.weight.detach().to(dev, act)
             gu[1::2] = layer.mlp.up_proj.weight.detach().to(dev, act)
@@ -247,8 +254,11 @@ class Engine:
             if kx:
                 # T = xn . [A_q; A_v]^T lands in the K-extension columns of the same activation buffer
                 ops.gemm(hn, ly["a_cat"], hn[:, H:], M=M, N=m["n_lora"], K=H, lda=Kx, ldo=Kx)
-            ops.gemm(hn, ly["wqkv"], qkv, M=M, N=nqkv, K=Kx, lda=Kx)
-            ops.rope_(qkv, rows=M, L=L, ld=nqkv, n_q_heads=nh, n_k_heads=nkv, dh=dh, table=table)
+            if m["fuse_rope"]:
+                ops.gemm(hn, ly["wqkv"], qkv, M=M, N=nqkv, K=Kx, lda=Kx, rope=(table, L, dh, (nh + nkv) * dh))
+            else:
+                ops.gemm(hn, ly["wqkv"], qkv, M=M, N=nqkv, K=Kx, lda=Kx)
+                ops.rope_(qkv, rows=M, L=L, ld=nqkv, n_q_heads=nh, n_k_heads=nkv, dh=dh, table=table)
             ops.attention(qkv, qkv[:, nh * dh:], qkv[:, (nh + nkv) * dh:], attn, B=B, H=nh, Hkv=nkv, Tq=L, Tk=L, dh=dh,
                           q_strides=(L * nqkv, nqkv), k_strides=(L * nqkv, nqkv), v_strides=(L * nqkv, nqkv),
                           o_strides=(L * nh * dh, nh * dh), scale=dh ** -0.5, causal=True, key_mask=mask)

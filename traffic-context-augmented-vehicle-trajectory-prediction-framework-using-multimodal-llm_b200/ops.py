@@ -23,7 +23,8 @@ class GemmArgs(Structure):
                 ("bias", c_void_p),
                 ("residual", c_void_p), ("ldr", c_int), ("res_dtype", c_int),
                 ("act", c_int),
-                ("remap_gi", c_int), ("remap_go", c_int), ("remap_off", c_int)]
+                ("remap_gi", c_int), ("remap_go", c_int), ("remap_off", c_int),
+                ("rope_cos_sin", c_void_p), ("rope_L", c_int), ("rope_dh", c_int), ("rope_cols", c_int)]
 
 
 class AttnArgs(Structure):
@@ -122,7 +123,7 @@ def _need_cuda(*ts):
 
 
 def gemm(a, w, out, *, M=None, N=None, K=None, lda=None, ldw=None, ldo=None, bias=None, residual=None, ldr=None,
-         act=ACT_NONE, remap=(0, 0, 0)):
+         act=ACT_NONE, remap=(0, 0, 0), rope=None):
     """out = act(a @ w.T + bias) + residual.  a: [M, >=K] row-major (lda = a.stride(0)), w: [N, >=K]."""
     _need_cuda(a, w, out, bias, residual)
     g = GemmArgs()
@@ -142,6 +143,8 @@ def gemm(a, w, out, *, M=None, N=None, K=None, lda=None, ldw=None, ldo=None, bia
         g.residual, g.ldr, g.res_dtype = residual.data_ptr(), (residual.stride(0) if ldr is None else ldr), dt(residual)
     g.act = act
     g.remap_gi, g.remap_go, g.remap_off = remap
+    if rope is not None:     # (table, L, dh, cols)
+        g.rope_cos_sin, g.rope_L, g.rope_dh, g.rope_cols = rope[0].data_ptr(), rope[1], rope[2], rope[3]
     if g.in_dtype == BF16:
         kern = "gemm_tc_kernel<%d>" % (32 if g.N <= 32 else 64 if g.N <= 64 else 128 if g.N <= 128 else 256)
     else:
@@ -167,9 +170,14 @@ def attention(q, k, v, out, *, B, H, Hkv, Tq, Tk, dh, q_strides, k_strides, v_st
         if key_mask.dtype != torch.int32:
             raise TypeError("attention: key_mask must be int32")
         a.key_mask = key_mask.data_ptr()
-    tc = a.dtype == BF16 and dh in (64, 128) and Tq == Tk and Tk <= 256
+    if a.dtype == BF16 and dh in (64, 128) and max(Tq, Tk) <= 256:
+        kern = "attn_flash_kernel"
+    elif a.dtype == BF16 and dh > 128 and dh % 64 == 0 and Tq <= 32 and Tk <= 256 and not causal:
+        kern = "attn_x_kernel"
+    else:
+        kern = f"attn_warp_kernel[dh{dh},q{Tq},k{Tk}]"
     fl = 4.0 * B * H * Tq * Tk * dh * (0.5 if causal else 1.0)
-    with _Timed("attn_flash_kernel" if tc else "attn_warp_kernel", fl, 2.0 * q.element_size() * B * dh * (H * Tq + Hkv * Tk)):
+    with _Timed(kern, fl, 2.0 * q.element_size() * B * dh * (H * Tq + Hkv * Tk)):
         _lib.check(_lib.load().tcavp_attention(byref(a), _stream()), "tcavp_attention")
     return out
 
