@@ -95,7 +95,8 @@ int tcavp_gemm(const tcavp_gemm_args* args, tcavp_stream_t stream);
  *   key_mask    optional int32 [B, Tk], 1 = attend, 0 = masked (key padding).  Rows whose keys are all
  *               masked produce zeros (the reference discards such rows, train.py:378-380).
  * Softmax statistics and accumulation are fp32 for both dtypes.  `dtype` applies to q, k, v and out.
- * bf16 with dh in {64,128} and Tk <= 256 runs on tensor cores; everything else on the SIMT kernel.
+ * bf16 with dh in {16,32,64,96,128} and Tq,Tk <= 256 (flash kernel) or with few queries against a wide head
+ * (Tq <= 32, dh % 64 == 0: LTSF cross-attention) runs on tensor cores; everything else on the SIMT kernel.
  */
 typedef struct tcavp_attn_args {
   int B, H, Hkv, Tq, Tk, dh;

@@ -10,6 +10,6 @@ $CMD > gpurun_out/plain_${TAG}.json 2> gpurun_out/plain_${TAG}.err || { echo "pl
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_list_${TAG}.log 2>&1
 for K in "$@"; do
   NAME=$(echo "$K" | tr -c 'A-Za-z0-9\n' '_')
-  ncu --set full --clock-control none --import-source on -k regex:$K -s 8 -c 2 -o gpurun_out/prof_${TAG}_${NAME} -f $CMD > gpurun_out/ncu_${TAG}_${NAME}.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:$K -s 60 -c 6 -o gpurun_out/prof_${TAG}_${NAME} -f $CMD > gpurun_out/ncu_${TAG}_${NAME}.log 2>&1
 done
 ls -la gpurun_out | tail -20

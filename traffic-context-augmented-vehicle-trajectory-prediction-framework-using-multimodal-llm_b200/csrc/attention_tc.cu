@@ -1,5 +1,6 @@
-// Tensor-core flash attention for the LLM self-attention (HF:251-289 with the causal + key-padding mask of
-// HF:399): bf16 operands, head_dim 64 or 128, Tk <= 256, optional causal mask, optional key mask, GQA.
+// Tensor-core flash attention: the LLM self-attention (HF:251-289 with the causal + key-padding mask of HF:399)
+// and the small nn.MultiheadAttention cores of the Q-Former / lane-polygon encoder (train.py:371, 411-413).
+// bf16 operands, head_dim 16/32/64/96/128, Tq, Tk <= 256, optional causal mask, optional key mask, GQA.
 //
 // One CTA per (batch, head): K and V of that head are staged ONCE in shared memory (padded rows, conflict-free
 // ldmatrix), every warp owns a 16-row query slab and runs the FlashAttention-2 register pipeline
@@ -211,12 +212,12 @@ __global__ void __launch_bounds__(MAXT, MINB) attn_flash_kernel(tcavp_attn_args 
 
 // Returns 1 when the shape is not covered (caller falls back to the generic kernel), <= 0 otherwise.
 int attention_tc_launch(const tcavp_attn_args& a, cudaStream_t stream) {
-  if (!(a.dh == 64 || a.dh == 128) || a.Tk > 256 || a.Tq > 256 || a.Tk < 1) return 1;
+  if (!(a.dh == 16 || a.dh == 32 || a.dh == 64 || a.dh == 96 || a.dh == 128) || a.Tk > 256 || a.Tq > 256 || a.Tk < 1) return 1;
   auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
   if (!al16(a.q) || !al16(a.k) || !al16(a.v) || !al16(a.out)) return 1;
   if (a.q_sb % 8 || a.q_st % 8 || a.k_sb % 8 || a.k_st % 8 || a.v_sb % 8 || a.v_st % 8 || a.o_sb % 2 || a.o_st % 2) return 1;
   const int tk_pad = (a.Tk + fa::KB - 1) / fa::KB * fa::KB;
-  const int max_warps = a.dh == 64 ? 12 : 10;
+  const int max_warps = (a.dh == 128 || a.dh == 96) ? 10 : 12;
   const int need = (a.Tq + 15) / 16;
   const int chunks = (need + max_warps - 1) / max_warps;
   const int warps = (need + chunks - 1) / chunks;                              // balanced query chunks
@@ -230,8 +231,14 @@ int attention_tc_launch(const tcavp_attn_args& a, cudaStream_t stream) {
   if (a.dh == 64) {
     if (warps <= 9) TCAVP_FLASH(64, 288, 2);
     else TCAVP_FLASH(64, 384, 1);
-  } else {
+  } else if (a.dh == 128) {
     TCAVP_FLASH(128, 320, 1);
+  } else if (a.dh == 96) {       // Q-Former heads (768 / 8)
+    TCAVP_FLASH(96, 320, 1);
+  } else if (a.dh == 32) {
+    TCAVP_FLASH(32, 384, 1);
+  } else {                       // lane-polygon encoder heads (64 / 4)
+    TCAVP_FLASH(16, 384, 1);
   }
 #undef TCAVP_FLASH
   return check_launch("attn_flash_kernel");

@@ -10,6 +10,7 @@
 // LoRA (peft lora.Linear, reference scripts/train.py:432-440) is expressed by the caller as extra K columns
 // ([x | x.A^T] . [W | (alpha/r) B]^T), i.e. it accumulates in the same TMEM tile as the base product.
 #include <cuda.h>
+#include <stdlib.h>
 #include <mutex>
 #include "common.cuh"
 
@@ -19,7 +20,8 @@ namespace tc {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one SWIZZLE_128B atom row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int NUM_EPI_WARPS = 8;   // two warps per TMEM lane quarter, each draining alternate 32-column chunks
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..: epilogue
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 
 template <int BLOCK_N>
@@ -62,6 +64,23 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
+// Same load, delivered to the same shared-memory offset (and signalling the same barrier offset) in every CTA of `mask`.
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // K-major operand tile in shared memory, SWIZZLE_128B: rows are 128 bytes, 8-row groups are 1024 bytes apart.
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -89,6 +108,10 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -111,9 +134,21 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// Epilogue of 32 accumulator columns [nacc0, nacc0+32) of row m for one thread.
-__device__ __forceinline__ void epilogue_chunk(const EpilogueParams& p, int m, int nacc0, const uint32_t (&r)[32],
-                                               bool vec_out, bool vec_res) {
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// silu(g) * u with one EX2 and one RCP: g * u / (1 + 2^(-g log2 e)); saturates correctly at +-inf.
+__device__ __forceinline__ float swiglu_f(float g, float u) {
+  return __fdividef(g * u, 1.f + ex2_approx(-1.4426950408889634f * g));
+}
+
+enum { EPI_VEC_OUT = 1, EPI_VEC_RES = 2, EPI_VEC_BIAS = 4 };
+
+// Epilogue of 32 accumulator columns [nacc0, nacc0+32) of row m for one thread.  The interior-tile path (full chunk,
+// 16-byte aligned rows) is branch-light and fully vectorised; ragged edges take the scalar path.
+__device__ __forceinline__ void epilogue_chunk(const EpilogueParams& p, int m, int nacc0, const uint32_t (&r)[32], int flags) {
   if (m >= p.M) return;
   const int mo = remap_row(p.remap_gi, p.remap_go, p.remap_off, m);
   float o[32];
@@ -122,7 +157,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueParams& p, int m, i
     cnt = 16;
     n0 = nacc0 >> 1;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) o[j] = silu_f(__uint_as_float(r[2 * j])) * __uint_as_float(r[2 * j + 1]);
+    for (int j = 0; j < 16; ++j) o[j] = swiglu_f(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
   } else {
     cnt = 32;
     n0 = nacc0;
@@ -134,38 +169,53 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueParams& p, int m, i
   if (p.rope_cols > 0 && n0 < p.rope_cols) {
     // chunk = 32 columns = 16 rotation pairs of one head (rope_dh is a multiple of 32)
     const int half = p.rope_dh >> 1;
-    const float2* cs = reinterpret_cast<const float2*>(p.rope) + (size_t)(m % p.rope_L) * half + ((n0 % p.rope_dh) >> 1);
+    const float4* cs = reinterpret_cast<const float4*>(p.rope + 2 * ((size_t)(m % p.rope_L) * half + ((n0 % p.rope_dh) >> 1)));
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float2 t = __ldg(cs + j);
-      const float x1 = o[2 * j], x2 = o[2 * j + 1];
-      o[2 * j] = x1 * t.x - x2 * t.y;
-      o[2 * j + 1] = x2 * t.x + x1 * t.y;
+    for (int j = 0; j < 8; ++j) {
+      const float4 t = __ldg(cs + j);   // (cos, sin) of two adjacent pairs
+      const float a0 = o[4 * j], a1 = o[4 * j + 1], a2 = o[4 * j + 2], a3 = o[4 * j + 3];
+      o[4 * j] = a0 * t.x - a1 * t.y;
+      o[4 * j + 1] = a1 * t.x + a0 * t.y;
+      o[4 * j + 2] = a2 * t.z - a3 * t.w;
+      o[4 * j + 3] = a3 * t.z + a2 * t.w;
     }
   }
   if (p.bias) {
+    if (full && (flags & EPI_VEC_BIAS)) {
+      const float4* bp = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < cnt && n0 + j < p.N) o[j] += __ldg(p.bias + n0 + j);
+      for (int q = 0; q < 8; ++q) {
+        if (q * 4 < cnt) {
+          const float4 b = __ldg(bp + q);
+          o[q * 4] += b.x; o[q * 4 + 1] += b.y; o[q * 4 + 2] += b.z; o[q * 4 + 3] += b.w;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < cnt && n0 + j < p.N) o[j] += __ldg(p.bias + n0 + j);
+    }
   }
   if (p.act == TCAVP_ACT_RELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.f);
   }
   if (p.residual) {
-    if (vec_res && full) {
+    if ((flags & EPI_VEC_RES) && full) {
       if (p.res_dtype == TCAVP_BF16) {
         const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + (size_t)mo * p.ldr + n0);
+        uint4 u[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q * 8 < cnt) u[q] = rp[q];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           if (q * 8 < cnt) {
-            uint4 u = rp[q];
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+            const uint32_t w[4] = {u[q].x, u[q].y, u[q].z, u[q].w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float2 f = __bfloat1622float2(h[e]);
-              o[q * 8 + 2 * e] += f.x;
-              o[q * 8 + 2 * e + 1] += f.y;
+            for (int e = 0; e < 4; ++e) {     // bf16 -> fp32 is a 16-bit shift
+              o[q * 8 + 2 * e] += __uint_as_float(w[e] << 16);
+              o[q * 8 + 2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
             }
           }
         }
@@ -185,7 +235,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueParams& p, int m, i
         if (j < cnt && n0 + j < p.N) o[j] += load_as_f(p.residual, (size_t)mo * p.ldr + n0 + j, p.res_dtype);
     }
   }
-  if (vec_out && full) {
+  if ((flags & EPI_VEC_OUT) && full) {
     if (p.out_dtype == TCAVP_BF16) {
       uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)mo * p.ldo + n0);
 #pragma unroll
@@ -212,11 +262,16 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueParams& p, int m, i
   }
 }
 
-template <int BLOCK_N>
+// CM = CTAs per cluster along M.  With CM = 2 the two CTAs of a cluster work on vertically adjacent output tiles that
+// share the W tile: each CTA fetches half of it and TMA-multicasts that half into both shared memories, which cuts
+// the L2 -> SM operand traffic per CTA from A + W to A + W/2 (the binding resource for K <= 1024 GEMMs).
+template <int BLOCK_N, int CM>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, EpilogueParams ep,
-               int M, int Nacc, int K, int vec_out, int vec_res) {
+               int M, int Nacc, int K, int flags) {
   using C = Cfg<BLOCK_N>;
+  const uint32_t cta_rank = CM > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t MC_MASK = (uint16_t)((1u << CM) - 1);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a = smem_base;
@@ -233,7 +288,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int lane = threadIdx.x & 31;
   const int tiles_n = (Nacc + BLOCK_N - 1) / BLOCK_N;
   const int tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
-  const int num_tiles = tiles_m * tiles_n;
+  // work unit = CM vertically adjacent tiles; unit u -> (m group u / tiles_n, n tile u % tiles_n); a cluster strides over units
+  const int num_units = ((tiles_m + CM - 1) / CM) * tiles_n;
+  const int unit0 = blockIdx.x / CM, unit_stride = gridDim.x / CM;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
 
   if (warp == 0 && lane == 0) {
@@ -241,11 +298,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(full_bar + 8 * s, 1);
-      mbar_init(empty_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, CM);      // one tcgen05.commit arrival from every CTA that reads the stage
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tmem_full_bar + 8 * s, 1);
-      mbar_init(tmem_empty_bar + 8 * s, 4);   // one arrive per epilogue warp
+      mbar_init(tmem_empty_bar + 8 * s, NUM_EPI_WARPS);   // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -255,6 +312,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (CM > 1) cluster_sync_all();   // peers' barriers must be initialised before any multicast lands
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -263,14 +321,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * BLOCK_M;
-        const int n0 = (tile % tiles_n) * BLOCK_N;
+      for (int unit = unit0; unit < num_units; unit += unit_stride) {
+        const int m0 = ((unit / tiles_n) * CM + (int)cta_rank) * BLOCK_M;
+        const int n0 = (unit % tiles_n) * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           mbar_expect_tx(full_bar + 8 * stage, C::STAGE_BYTES);
           tma_load_2d(smem_a + stage * A_STAGE_BYTES, &tma_a, full_bar + 8 * stage, kb * BLOCK_K, m0);
-          tma_load_2d(smem_b + stage * C::B_STAGE_BYTES, &tma_b, full_bar + 8 * stage, kb * BLOCK_K, n0);
+          if (CM == 1) {
+            tma_load_2d(smem_b + stage * C::B_STAGE_BYTES, &tma_b, full_bar + 8 * stage, kb * BLOCK_K, n0);
+          } else {   // my 1/CM slice of the W tile goes to every CTA of the cluster
+            constexpr int SLICE = BLOCK_N / CM;
+            tma_load_2d_mc(smem_b + stage * C::B_STAGE_BYTES + cta_rank * (SLICE * BLOCK_K * 2), &tma_b, full_bar + 8 * stage,
+                           kb * BLOCK_K, n0 + (int)cta_rank * SLICE, MC_MASK);
+          }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -282,7 +346,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int unit = unit0; unit < num_units; unit += unit_stride, ++it) {
         const int acc = it & 1;
         mbar_wait(tmem_empty_bar + 8 * acc, ((it >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -298,29 +362,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             umma_bf16(tmem_d, umma_smem_desc(a_addr + k * UMMA_K * 2), umma_smem_desc(b_addr + k * UMMA_K * 2), idesc,
                       (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar + 8 * stage);   // frees the smem slot once the MMAs above retire
+          // frees the smem slot (in every CTA whose multicast writes into it) once the MMAs above retire
+          if (CM == 1) umma_commit(empty_bar + 8 * stage);
+          else umma_commit_mc(empty_bar + 8 * stage, MC_MASK);
           if (kb == num_kb - 1) umma_commit(tmem_full_bar + 8 * acc);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quarter = warp & 3;   // TMEM lanes [32*quarter, +32) are the ones this warp may read
+    // ===================== epilogue (warps 2..) =====================
+    const int quarter = warp & 3;           // TMEM lanes [32*quarter, +32) are the ones this warp may read
+    const int chunk0 = (warp - 2) >> 2;     // the two warps of a quarter take alternate 32-column chunks
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int unit = unit0; unit < num_units; unit += unit_stride, ++it) {
       const int acc = it & 1;
-      const int m0 = (tile / tiles_n) * BLOCK_M;
-      const int n0 = (tile % tiles_n) * BLOCK_N;
+      const int m0 = ((unit / tiles_n) * CM + (int)cta_rank) * BLOCK_M;
+      const int n0 = (unit % tiles_n) * BLOCK_N;
       mbar_wait(tmem_full_bar + 8 * acc, (it >> 1) & 1);
       tc_fence_after();
       const int m = m0 + quarter * 32 + lane;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
+      for (int c = chunk0; c < BLOCK_N / 32; c += NUM_EPI_WARPS / 4) {
         if (n0 + c * 32 >= Nacc) break;   // warp-uniform
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + c * 32, r);
-        epilogue_chunk(ep, m, n0 + c * 32, r, vec_out != 0, vec_res != 0);
+        epilogue_chunk(ep, m, n0 + c * 32, r, flags);
       }
       tc_fence_before();
       __syncwarp();
@@ -330,6 +397,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (CM > 1) cluster_sync_all();   // no CTA may exit while a peer can still multicast into it / arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
@@ -377,21 +445,47 @@ static int make_map(CUtensorMap* map, const void* base, int rows, int cols, int 
   return TCAVP_OK;
 }
 
-template <int BLOCK_N>
+static int cluster_pref() {   // TCAVP_GEMM_CLUSTER=1 disables the 2-CTA multicast clusters (A/B testing)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TCAVP_GEMM_CLUSTER");
+    v = e ? atoi(e) : 2;
+    if (v != 1 && v != 2) v = 2;
+  }
+  return v;
+}
+
+template <int BLOCK_N, int CM>
 static int launch_tc(const tcavp_gemm_args& a, const EpilogueParams& ep, cudaStream_t stream) {
   using C = Cfg<BLOCK_N>;
   CUtensorMap ma, mb;
   int rc = make_map(&ma, a.A, a.M, a.K, a.lda, BLOCK_M);
   if (rc) return rc;
-  rc = make_map(&mb, a.W, a.N, a.K, a.ldw, BLOCK_N);
+  rc = make_map(&mb, a.W, a.N, a.K, a.ldw, BLOCK_N / CM);
   if (rc) return rc;
-  TCAVP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-  const int tiles = ((a.M + BLOCK_M - 1) / BLOCK_M) * ((a.N + BLOCK_N - 1) / BLOCK_N);
-  const int grid = tiles < sm_count() ? tiles : sm_count();
+  TCAVP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  const int tiles_m = (a.M + BLOCK_M - 1) / BLOCK_M, tiles_n = (a.N + BLOCK_N - 1) / BLOCK_N;
+  const int units = ((tiles_m + CM - 1) / CM) * tiles_n;
+  const int max_clusters = sm_count() / CM;
+  const int grid = (units < max_clusters ? units : max_clusters) * CM;
   const size_t osz = ep.out_dtype == TCAVP_BF16 ? 2 : 4, rsz = ep.res_dtype == TCAVP_BF16 ? 2 : 4;
-  const int vec_out = ((size_t)ep.ldo * osz) % 16 == 0 && (reinterpret_cast<uintptr_t>(ep.out) % 16) == 0;
-  const int vec_res = ep.residual && ((size_t)ep.ldr * rsz) % 16 == 0 && (reinterpret_cast<uintptr_t>(ep.residual) % 16) == 0;
-  gemm_tc_kernel<BLOCK_N><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ma, mb, ep, a.M, a.N, a.K, vec_out, vec_res);
+  int flags = 0;
+  if (((size_t)ep.ldo * osz) % 16 == 0 && (reinterpret_cast<uintptr_t>(ep.out) % 16) == 0) flags |= EPI_VEC_OUT;
+  if (ep.residual && ((size_t)ep.ldr * rsz) % 16 == 0 && (reinterpret_cast<uintptr_t>(ep.residual) % 16) == 0) flags |= EPI_VEC_RES;
+  if (ep.bias && (reinterpret_cast<uintptr_t>(ep.bias) % 16) == 0) flags |= EPI_VEC_BIAS;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CM;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TCAVP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, CM>, ma, mb, ep, a.M, a.N, a.K, flags));
   return check_launch("gemm_tc_kernel");
 }
 
@@ -495,10 +589,12 @@ extern "C" int tcavp_gemm(const tcavp_gemm_args* a, tcavp_stream_t stream_) {
   if (a->in_dtype == TCAVP_BF16) {
     TCAVP_REQUIRE(a->K % 8 == 0 && a->lda % 8 == 0 && a->ldw % 8 == 0, "tcavp_gemm(bf16): K, lda, ldw must be multiples of 8 (K=%d lda=%d ldw=%d)", a->K, a->lda, a->ldw);
     TCAVP_REQUIRE(reinterpret_cast<uintptr_t>(a->A) % 16 == 0 && reinterpret_cast<uintptr_t>(a->W) % 16 == 0, "tcavp_gemm(bf16): A and W must be 16-byte aligned");
-    if (a->N <= 32) return tc::launch_tc<32>(*a, ep, stream);
-    if (a->N <= 64) return tc::launch_tc<64>(*a, ep, stream);
-    if (a->N <= 128) return tc::launch_tc<128>(*a, ep, stream);
-    return tc::launch_tc<256>(*a, ep, stream);
+    if (a->N <= 32) return tc::launch_tc<32, 1>(*a, ep, stream);
+    if (a->N <= 64) return tc::launch_tc<64, 1>(*a, ep, stream);
+    if (a->N <= 128) return tc::launch_tc<128, 1>(*a, ep, stream);
+    // large problems: 2-CTA clusters sharing the W tile through TMA multicast
+    if (tc::cluster_pref() == 2 && a->M >= 16 * tc::BLOCK_M) return tc::launch_tc<256, 2>(*a, ep, stream);
+    return tc::launch_tc<256, 1>(*a, ep, stream);
   }
   if (a->in_dtype == TCAVP_F32) {
     dim3 grid((a->N + simt::BN - 1) / simt::BN, (a->M + simt::BM - 1) / simt::BM);

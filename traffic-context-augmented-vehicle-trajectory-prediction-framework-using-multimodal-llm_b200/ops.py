@@ -60,14 +60,16 @@ class LaunchProfiler:
 
     def summary(self):
         torch.cuda.synchronize()
-        groups = {}
+        groups, base = {}, {}
         for kernel, flops, nbytes, e0, e1 in self.rec:
-            g = groups.setdefault(kernel, dict(kernel=kernel, launches=0, time_ms=0.0, flops=0.0, bytes=0.0))
-            g["launches"] += 1
-            g["time_ms"] += e0.elapsed_time(e1)
-            g["flops"] += flops
-            g["bytes"] += nbytes
-        for g in groups.values():
+            ms = e0.elapsed_time(e1)
+            for key, table in ((kernel, groups), (kernel.split("[")[0], base)):
+                g = table.setdefault(key, dict(kernel=key, launches=0, time_ms=0.0, flops=0.0, bytes=0.0))
+                g["launches"] += 1
+                g["time_ms"] += ms
+                g["flops"] += flops
+                g["bytes"] += nbytes
+        for g in list(groups.values()) + list(base.values()):
             g["avg_ms"] = g["time_ms"] / max(g["launches"], 1)
             g["tflops"] = g["flops"] / (g["time_ms"] * 1e-3) / 1e12 if g["time_ms"] > 0 else 0.0
             g["gbs"] = g["bytes"] / (g["time_ms"] * 1e-3) / 1e9 if g["time_ms"] > 0 else 0.0
@@ -75,7 +77,8 @@ class LaunchProfiler:
         total = sum(g["time_ms"] for g in order) or 1.0
         brief = [dict(kernel=g["kernel"], launches=g["launches"], time_ms=round(g["time_ms"], 3), share=round(g["time_ms"] / total, 4),
                       tflops=round(g["tflops"], 1), gbs=round(g["gbs"], 1)) for g in order]
-        return {"dominant": order[0] if order else None, "groups": brief}
+        dominant = max(base.values(), key=lambda g: g["time_ms"]) if base else None
+        return {"dominant": dominant, "groups": brief}
 
 
 class _Timed:
@@ -146,7 +149,7 @@ def gemm(a, w, out, *, M=None, N=None, K=None, lda=None, ldw=None, ldo=None, bia
     if rope is not None:     # (table, L, dh, cols)
         g.rope_cos_sin, g.rope_L, g.rope_dh, g.rope_cols = rope[0].data_ptr(), rope[1], rope[2], rope[3]
     if g.in_dtype == BF16:
-        kern = "gemm_tc_kernel<%d>" % (32 if g.N <= 32 else 64 if g.N <= 64 else 128 if g.N <= 128 else 256)
+        kern = "gemm_tc_kernel<%d>[N%d,K%d]" % (32 if g.N <= 32 else 64 if g.N <= 64 else 128 if g.N <= 128 else 256, g.N, g.K)
     else:
         kern = "gemm_simt_kernel"
     esz = a.element_size()
@@ -170,8 +173,8 @@ def attention(q, k, v, out, *, B, H, Hkv, Tq, Tk, dh, q_strides, k_strides, v_st
         if key_mask.dtype != torch.int32:
             raise TypeError("attention: key_mask must be int32")
         a.key_mask = key_mask.data_ptr()
-    if a.dtype == BF16 and dh in (64, 128) and max(Tq, Tk) <= 256:
-        kern = "attn_flash_kernel"
+    if a.dtype == BF16 and dh in (16, 32, 64, 96, 128) and max(Tq, Tk) <= 256:
+        kern = f"attn_flash_kernel[dh{dh},q{Tq},k{Tk}]"
     elif a.dtype == BF16 and dh > 128 and dh % 64 == 0 and Tq <= 32 and Tk <= 256 and not causal:
         kern = "attn_x_kernel"
     else:
