@@ -64,10 +64,14 @@ long long tcavp_launch_count(void);
  *              16 image-token rows of each scene straight into the fused (B, L, H) buffer,
  *              train.py:521-528).  Otherwise m' = m.
  *   residual   optional [M', N] tensor added after the activation; may alias `out`.
+ *   row scale  row_scale != NULL: every accumulator of row m is multiplied by row_scale[m] before anything else.
+ *              With the RMSNorm weight folded into W at pack time this fuses HF's LlamaRMSNorm (HF:53-70) into the
+ *              projection that consumes it: w * (x * rstd) . W^T == rstd * (x . (W diag(w))^T); rstd comes from
+ *              tcavp_row_rstd.
  *   RoPE       rope_cols > 0 fuses HF's apply_rotary_pos_emb (HF:146-170) into the epilogue of the packed QKV
  *              projection: output columns [0, rope_cols) are heads of width rope_dh whose W rows were
  *              permuted at pack time so that the rotation partners (i, i + dh/2) sit in adjacent columns
- *              (2i, 2i+1); row m has position m % rope_L; rope_cos_sin is the [L, dh/2, 2] table of
+ *              (2i, 2i+1); row m has position m % rope_L; rope_cos_sin is the layout-1 table of
  *              tcavp_rope_table.  q.k is invariant under the shared permutation, v is not permuted.
  */
 typedef struct tcavp_gemm_args {
@@ -81,6 +85,7 @@ typedef struct tcavp_gemm_args {
   int act;
   int remap_gi, remap_go, remap_off;
   const float* rope_cos_sin; int rope_L, rope_dh, rope_cols;
+  const float* row_scale;
 } tcavp_gemm_args;
 
 int tcavp_gemm(const tcavp_gemm_args* args, tcavp_stream_t stream);
@@ -120,19 +125,24 @@ int tcavp_attention(const tcavp_attn_args* args, tcavp_stream_t stream);
 int tcavp_layernorm(const void* x, const void* residual, const float* w, const float* b, void* out, int rows, int cols,
                     float eps, int in_dtype, int out_dtype, int remap_gi, int remap_go, int remap_off,
                     const float* rowvec, tcavp_stream_t stream);
-/* out[r,:] = w * (x[r,:] * rsqrt(mean(x^2) + eps))          (HF:53-70 LlamaRMSNorm).  ldo lets the output land
- * in a wider row (the K-extended activation that also carries the LoRA side columns). */
-int tcavp_rmsnorm(const void* x, const float* w, void* out, int rows, int cols, int ldo, float eps, int in_dtype,
+/* out[r,:] = w * (x[r,:] * rsqrt(mean(x^2) + eps))          (HF:53-70 LlamaRMSNorm).  ldi / ldo are the row strides of
+ * x / out in elements (the residual stream lives in K-extended rows that also carry the LoRA side columns). */
+int tcavp_rmsnorm(const void* x, int ldi, const float* w, void* out, int rows, int cols, int ldo, float eps, int in_dtype,
                   int out_dtype, tcavp_stream_t stream);
+/* out[r] = rsqrt(mean(x[r, 0:cols]^2) + eps)  — the per-row factor of LlamaRMSNorm, consumed by tcavp_gemm's row_scale. */
+int tcavp_row_rstd(const void* x, int ldx, int rows, int cols, float eps, int dtype, float* out, tcavp_stream_t stream);
 
 /* ---- rotary embedding (HF:146-170 apply_rotary_pos_emb, default rope HF:73-136) ----------------
  * In place on the q and k head blocks of a packed [rows, ld] qkv buffer (q heads first, then k heads);
  * position of row r is r % L.  cos_sin is an fp32 [L, dh/2, 2] table. */
 int tcavp_rope(void* qkv, int rows, int L, int ld, int n_q_heads, int n_k_heads, int dh, const float* cos_sin,
                int dtype, tcavp_stream_t stream);
-/* Fills the [L, dh/2, 2] table as HF does: angle = pos * inv_freq[j] in fp32, cosf / sinf.  inv_freq is a device
- * fp32 [dh/2] vector the host computes with HF's formula 1 / theta^(2j/dh) (HF:86-88). */
-int tcavp_rope_table(float* cos_sin, const float* inv_freq, int L, int dh, tcavp_stream_t stream);
+/* Fills the cos/sin table as HF does: angle = pos * inv_freq[j] in fp32, cosf / sinf.  inv_freq is a device fp32
+ * [dh/2] vector the host computes with HF's formula 1 / theta^(2j/dh) (HF:86-88).
+ *   layout 0: [L, dh/2, 2]  (tcavp_rope)
+ *   layout 1: [dh/4, L, 4]  (tcavp_gemm's fused RoPE: consecutive positions are contiguous, so the row-per-thread
+ *                            epilogue reads it coalesced) */
+int tcavp_rope_table(float* cos_sin, const float* inv_freq, int L, int dh, int layout, tcavp_stream_t stream);
 
 /* ---- fused-sequence assembly (train.py:526-528) -------------------------------------------------
  * fused[b, n_img + j, :] = embed[ids[b, j], :] + text_mod[:]   for j < L_text; mask_out[b, :] = [1]*n_img ++ mask. */

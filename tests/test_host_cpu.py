@@ -11,7 +11,7 @@ from conftest import ROOT, load_golden
 
 
 def test_state_dict_layout_matches_reference():
-    for name in ("tiny_b6", "cfg1_b8", "cfg5_b4"):
+    for name in ("tiny_b6", "cfg1_b8", "cfg5_b32"):
         fix = load_golden(name)
         sd = T.MultiModalTrajectoryModel(**fix["model_cfg"]).state_dict()
         assert set(sd) == set(fix["state_shapes"]), name

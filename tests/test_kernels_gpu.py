@@ -324,7 +324,7 @@ def test_gemm_fused_rope(ops, dtype, nh, nkv, dh):
     x, w = _rand(B * L, K, seed=1).to(td), _rand(N, K, seed=2, scale=K ** -0.5).to(td)
     hp = torch.stack([torch.arange(dh // 2), torch.arange(dh // 2) + dh // 2], dim=1).reshape(-1)
     perm = torch.cat([h * dh + hp for h in range(nh + nkv)] + [torch.arange((nh + nkv) * dh, N)])
-    table = ops.rope_table(L, dh, 10000.0, DEV)
+    table = ops.rope_table(L, dh, 10000.0, DEV, layout=1)
     out = torch.empty(B * L, N, dtype=torch.float32, device=DEV)
     ops.gemm(x.to(DEV), w[perm].contiguous().to(DEV), out, rope=(table, L, dh, (nh + nkv) * dh))
     y = (x.float() @ w.float().t()).view(B, L, N)
@@ -333,3 +333,27 @@ def test_gemm_fused_rope(ops, dtype, nh, nkv, dh):
     qk = qk * cos[None, :, None, :] + R.rotate_half(qk) * sin[None, :, None, :]
     want = torch.cat([qk.reshape(B, L, -1), y[..., (nh + nkv) * dh:]], dim=-1).view(B * L, N)[:, perm]
     torch.testing.assert_close(out.cpu(), want, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_fused_rmsnorm_gemm(ops, dtype):
+    """RMSNorm folded into the consuming projection: rstd from tcavp_row_rstd applied as the GEMM's row scale on
+    weights pre-multiplied by the norm weight == oracle rms_norm followed by the projection (incl. SwiGLU)."""
+    td = torch.float32 if dtype == "fp32" else torch.bfloat16
+    M, H, N, kx = 300, 128, 192, 16
+    xs = torch.zeros(M, H + kx, dtype=td)
+    xs[:, :H] = _rand(M, H, seed=1, scale=3.0).to(td)
+    g, w = 1 + 0.1 * _rand(H, seed=2), _rand(N, H, seed=3, scale=H ** -0.5)
+    wf = (w * g[None, :]).to(td)
+    want = R.rms_norm(xs[:, :H].float(), g, 1e-6) @ w.t()
+    d = xs.to(DEV)
+    rstd = ops.row_rstd(d, torch.empty(M, device=DEV), rows=M, cols=H, ldx=H + kx, eps=1e-6)
+    ref = torch.rsqrt((xs[:, :H].float() ** 2).mean(-1) + 1e-6)
+    torch.testing.assert_close(rstd.cpu(), ref, rtol=1e-5, atol=1e-6)
+    out = ops.gemm(d, wf.to(DEV), torch.empty(M, N, device=DEV), M=M, K=H, lda=H + kx, row_scale=rstd)
+    tol = dict(rtol=1e-4, atol=1e-4) if dtype == "fp32" else dict(rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(out.cpu(), want, **tol)
+    out = ops.gemm(d, wf.to(DEV), torch.empty(M, N // 2, device=DEV), M=M, K=H, lda=H + kx, row_scale=rstd, act=ops.ACT_SWIGLU)
+    torch.testing.assert_close(out.cpu(), torch.nn.functional.silu(want[:, 0::2]) * want[:, 1::2], **tol)
+    o2 = ops.rmsnorm(d, g.to(DEV), torch.empty(M, H, device=DEV), eps=1e-6, rows=M, cols=H, ldi=H + kx)
+    torch.testing.assert_close(o2.cpu(), R.rms_norm(xs[:, :H].float(), g, 1e-6), **tol)

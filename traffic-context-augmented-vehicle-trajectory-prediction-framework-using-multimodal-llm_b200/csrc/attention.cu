@@ -97,8 +97,82 @@ __global__ void __launch_bounds__(128) attn_warp_kernel(tcavp_attn_args a) {
   }
 }
 
+// Narrow heads (dh <= 32: lane-polygon encoder dh = 16, LTSF attention block dh = 32): one CTA per (batch, head), K and V
+// staged once in shared memory as fp32, ONE THREAD per query row (q and the output accumulator live in registers, K/V
+// reads are warp-wide broadcasts), online softmax.  No cross-lane reductions at all.
+template <typename T, int DH>
+__global__ void __launch_bounds__(128) attn_row_kernel(tcavp_attn_args a) {
+  extern __shared__ float sm_kv[];
+  float* sK = sm_kv;
+  float* sV = sK + (size_t)a.Tk * DH;
+  int* sM = reinterpret_cast<int*>(sV + (size_t)a.Tk * DH);
+  const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+  const int hk = h / (a.H / a.Hkv);
+  const T* k = reinterpret_cast<const T*>(a.k) + (size_t)b * a.k_sb + (size_t)hk * DH;
+  const T* v = reinterpret_cast<const T*>(a.v) + (size_t)b * a.v_sb + (size_t)hk * DH;
+  for (int i = threadIdx.x; i < a.Tk * DH; i += blockDim.x) {
+    const int j = i / DH, d = i % DH;
+    sK[i] = Cvt<T>::to_f(k[(size_t)j * a.k_st + d]);
+    sV[i] = Cvt<T>::to_f(v[(size_t)j * a.v_st + d]);
+  }
+  for (int j = threadIdx.x; j < a.Tk; j += blockDim.x) sM[j] = !a.key_mask || a.key_mask[(size_t)b * a.Tk + j] != 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < a.Tq; i += blockDim.x) {
+    const T* q = reinterpret_cast<const T*>(a.q) + (size_t)b * a.q_sb + (size_t)i * a.q_st + (size_t)h * DH;
+    float qr[DH], acc[DH];
+#pragma unroll
+    for (int d = 0; d < DH; ++d) {
+      qr[d] = Cvt<T>::to_f(q[d]) * a.scale;
+      acc[d] = 0.f;
+    }
+    float m = -INFINITY, l = 0.f;
+    const int kend = a.causal ? i + 1 : a.Tk;
+    for (int j = 0; j < kend; ++j) {
+      if (!sM[j]) continue;
+      const float4* kj = reinterpret_cast<const float4*>(sK + (size_t)j * DH);
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int d4 = 0; d4 < DH / 4; ++d4) {
+        const float4 kk = kj[d4];
+        s0 = fmaf(qr[4 * d4], kk.x, s0);
+        s1 = fmaf(qr[4 * d4 + 1], kk.y, s1);
+        s0 = fmaf(qr[4 * d4 + 2], kk.z, s0);
+        s1 = fmaf(qr[4 * d4 + 3], kk.w, s1);
+      }
+      const float s = s0 + s1;
+      const float mn = fmaxf(m, s);
+      const float corr = __expf(m - mn), p = __expf(s - mn);
+      l = l * corr + p;
+      const float4* vj = reinterpret_cast<const float4*>(sV + (size_t)j * DH);
+#pragma unroll
+      for (int d4 = 0; d4 < DH / 4; ++d4) {
+        const float4 vv = vj[d4];
+        acc[4 * d4] = fmaf(acc[4 * d4], corr, p * vv.x);
+        acc[4 * d4 + 1] = fmaf(acc[4 * d4 + 1], corr, p * vv.y);
+        acc[4 * d4 + 2] = fmaf(acc[4 * d4 + 2], corr, p * vv.z);
+        acc[4 * d4 + 3] = fmaf(acc[4 * d4 + 3], corr, p * vv.w);
+      }
+      m = mn;
+    }
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    T* o = reinterpret_cast<T*>(a.out) + (size_t)b * a.o_sb + (size_t)i * a.o_st + (size_t)h * DH;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) o[d] = Cvt<T>::from_f(acc[d] * inv);
+  }
+}
+
+template <typename T>
+static int launch_row(const tcavp_attn_args& a, cudaStream_t stream) {
+  const size_t smem = (size_t)a.Tk * a.dh * 8 + (size_t)a.Tk * 4;
+  const int threads = a.Tq <= 32 ? 32 : (a.Tq <= 64 ? 64 : 128);
+  if (a.dh == 16) attn_row_kernel<T, 16><<<a.B * a.H, threads, smem, stream>>>(a);
+  else attn_row_kernel<T, 32><<<a.B * a.H, threads, smem, stream>>>(a);
+  return check_launch("attn_row_kernel");
+}
+
 template <typename T>
 static int launch_warp(const tcavp_attn_args& a, cudaStream_t stream) {
+  if ((a.dh == 16 || a.dh == 32) && a.Tk <= 128) return launch_row<T>(a, stream);
   const long long total = (long long)a.B * a.H * a.Tq;
   const int grid = (int)((total + 3) / 4);
   const int ne = (a.dh + 31) / 32;

@@ -3,7 +3,7 @@
 // bf16 operands, head_dim 16/32/64/96/128, Tq, Tk <= 256, optional causal mask, optional key mask, GQA.
 //
 // One CTA per (batch, head): K and V of that head are staged ONCE in shared memory (padded rows, conflict-free
-// ldmatrix), every warp owns a 16-row query slab and runs the FlashAttention-2 register pipeline
+// ldmatrix), every warp owns two 16-row query slabs (one from each end of the range: balanced causal work) and runs the FlashAttention-2 register pipeline
 // (mma.sync m16n8k16: S = Q.K^T -> online softmax in fp32 -> O += P.V) over 64-key blocks, skipping blocks
 // beyond its causal bound.  Scores and probabilities never touch shared or global memory.
 #include "common.cuh"
@@ -52,28 +52,30 @@ __global__ void __launch_bounds__(MAXT, MINB) attn_flash_kernel(tcavp_attn_args 
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
   const int hk = h / (a.H / a.Hkv);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q_base = blockIdx.y * (blockDim.x >> 5) * 16;                      // first query row of this CTA
-  // keys this CTA can ever need (causal: up to its last query row), rounded up to whole 64-key blocks
-  const int tk_need = a.causal ? min(a.Tk, q_base + (int)(blockDim.x >> 5) * 16) : a.Tk;
-  const int tk_pad = min(tk_pad_all, (tk_need + KB - 1) / KB * KB);
+  const int tk_pad = tk_pad_all;
   const __nv_bfloat16* gq = reinterpret_cast<const __nv_bfloat16*>(a.q) + (size_t)b * a.q_sb + (size_t)h * DH;
   const __nv_bfloat16* gk = reinterpret_cast<const __nv_bfloat16*>(a.k) + (size_t)b * a.k_sb + (size_t)hk * DH;
   const __nv_bfloat16* gv = reinterpret_cast<const __nv_bfloat16*>(a.v) + (size_t)b * a.v_sb + (size_t)hk * DH;
 
   // ---- stage K, V (zero-filled beyond Tk) and the key mask ----
   constexpr int VPR = DH / 8;              // 16-byte vectors per row
-  for (int i = threadIdx.x; i < tk_pad * VPR; i += blockDim.x) {
-    const int r = i / VPR, c = (i % VPR) * 8;
-    uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-    if (r < a.Tk) {
-      kv = *reinterpret_cast<const uint4*>(gk + (size_t)r * a.k_st + c);
-      vv = *reinterpret_cast<const uint4*>(gv + (size_t)r * a.v_st + c);
+  // cp.async: every 16-byte copy is in flight at once (no register staging, no per-iteration round trip); rows
+  // beyond Tk are zero-filled (src-size 0) so masked probabilities never meet NaN payloads.
+  {
+    const uint32_t sK_a = (uint32_t)__cvta_generic_to_shared(sK), sV_a = (uint32_t)__cvta_generic_to_shared(sV);
+    for (int i = threadIdx.x; i < tk_pad * VPR; i += blockDim.x) {
+      const int r = i / VPR, c = (i % VPR) * 8;
+      const int sz = r < a.Tk ? 16 : 0;
+      const size_t rr = r < a.Tk ? r : 0;
+      const uint32_t off = (uint32_t)((r * LDS + c) * 2);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sK_a + off), "l"(gk + rr * a.k_st + c), "r"(sz) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sV_a + off), "l"(gv + rr * a.v_st + c), "r"(sz) : "memory");
     }
-    *reinterpret_cast<uint4*>(sK + (size_t)r * LDS + c) = kv;
-    *reinterpret_cast<uint4*>(sV + (size_t)r * LDS + c) = vv;
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
   for (int j = threadIdx.x; j < tk_pad; j += blockDim.x)
     sMask[j] = (j < a.Tk) && (!a.key_mask || a.key_mask[(size_t)b * a.Tk + j] != 0);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   if (threadIdx.x < tk_pad / KB) {
     int all = 1;
@@ -82,9 +84,22 @@ __global__ void __launch_bounds__(MAXT, MINB) attn_flash_kernel(tcavp_attn_args 
   }
   __syncthreads();
 
-  const int row0 = q_base + warp * 16;
-  if (row0 >= a.Tq) return;
+  // Causal work grows with the row index, so every warp takes one slab from each end of the query range:
+  // slabs (w, nslabs-1-w) cost about the same for every w and no warp idles while the last rows finish.
+  const int nslabs = (a.Tq + 15) / 16;
   const int g = lane >> 2, t4 = lane & 3;
+  const uint32_t sK_u = (uint32_t)__cvta_generic_to_shared(sK), sV_u = (uint32_t)__cvta_generic_to_shared(sV);
+  // ldmatrix lane -> row/col offsets.  K (non-transposed, x4 = keys [0,8)/[8,16) x dims [0,8)/[8,16)):
+  const int k_row = (lane & 7) + ((lane >> 4) << 3), k_col = ((lane >> 3) & 1) * 8;
+  // V (transposed, x4 = keys [0,8)/[8,16) x dims [0,8)/[8,16)):
+  const int v_row = (lane & 7) + (((lane >> 3) & 1) << 3), v_col = (lane >> 4) * 8;
+  const float sl2 = a.scale * 1.4426950408889634f;   // softmax in base 2
+  __nv_bfloat16* go = reinterpret_cast<__nv_bfloat16*>(a.out) + (size_t)b * a.o_sb + (size_t)h * DH;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+  const int slab = pass == 0 ? nslabs - 1 - warp : warp;
+  if (slab < 0 || slab >= nslabs || (pass == 1 && slab >= nslabs - 1 - warp)) continue;
+  const int row0 = slab * 16;
   const int r_lo = row0 + g, r_hi = row0 + g + 8;
 
   // ---- Q fragments straight from global memory (A operand, row-major m16k16 per k-step) ----
@@ -104,15 +119,8 @@ __global__ void __launch_bounds__(MAXT, MINB) attn_flash_kernel(tcavp_attn_args 
 #pragma unroll
   for (int n = 0; n < NT; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
   float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
-  const float sl2 = a.scale * 1.4426950408889634f;   // softmax in base 2
 
   const int k_end = a.causal ? min(a.Tk, row0 + 16) : a.Tk;   // keys this warp can ever see
-  const uint32_t sK_u = (uint32_t)__cvta_generic_to_shared(sK), sV_u = (uint32_t)__cvta_generic_to_shared(sV);
-  // ldmatrix lane -> row/col offsets.  K (non-transposed, x4 = keys [0,8)/[8,16) x dims [0,8)/[8,16)):
-  const int k_row = (lane & 7) + ((lane >> 4) << 3), k_col = ((lane >> 3) & 1) * 8;
-  // V (transposed, x4 = keys [0,8)/[8,16) x dims [0,8)/[8,16)):
-  const int v_row = (lane & 7) + (((lane >> 3) & 1) << 3), v_col = (lane >> 4) * 8;
-
   for (int kb = 0; kb < k_end; kb += KB) {
     float s[KB / 8][4];
 #pragma unroll
@@ -199,13 +207,13 @@ __global__ void __launch_bounds__(MAXT, MINB) attn_flash_kernel(tcavp_attn_args 
   l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1);
   l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
   const float i_lo = l_lo > 0.f ? 1.f / l_lo : 0.f, i_hi = l_hi > 0.f ? 1.f / l_hi : 0.f;
-  __nv_bfloat16* go = reinterpret_cast<__nv_bfloat16*>(a.out) + (size_t)b * a.o_sb + (size_t)h * DH;
 #pragma unroll
   for (int n = 0; n < NT; ++n) {
     const int c = n * 8 + t4 * 2;
     if (r_lo < a.Tq) *reinterpret_cast<uint32_t*>(go + (size_t)r_lo * a.o_st + c) = pack2(o[n][0] * i_lo, o[n][1] * i_lo);
     if (r_hi < a.Tq) *reinterpret_cast<uint32_t*>(go + (size_t)r_hi * a.o_st + c) = pack2(o[n][2] * i_hi, o[n][3] * i_hi);
   }
+  }   // slab passes
 }
 
 }  // namespace fa
@@ -217,28 +225,26 @@ int attention_tc_launch(const tcavp_attn_args& a, cudaStream_t stream) {
   if (!al16(a.q) || !al16(a.k) || !al16(a.v) || !al16(a.out)) return 1;
   if (a.q_sb % 8 || a.q_st % 8 || a.k_sb % 8 || a.k_st % 8 || a.v_sb % 8 || a.v_st % 8 || a.o_sb % 2 || a.o_st % 2) return 1;
   const int tk_pad = (a.Tk + fa::KB - 1) / fa::KB * fa::KB;
-  const int max_warps = (a.dh == 128 || a.dh == 96) ? 10 : 12;
-  const int need = (a.Tq + 15) / 16;
-  const int chunks = (need + max_warps - 1) / max_warps;
-  const int warps = (need + chunks - 1) / chunks;                              // balanced query chunks
+  const int warps = ((a.Tq + 15) / 16 + 1) / 2;                                // every warp owns a pair of 16-row slabs (<= 8 warps)
   const size_t smem = (size_t)2 * tk_pad * (a.dh + fa::PAD) * 2 + (size_t)tk_pad * 4 + (size_t)(tk_pad / fa::KB) * 4;
-  const dim3 grid(a.B * a.H, chunks);
+  const dim3 grid(a.B * a.H);
 #define TCAVP_FLASH(DH, MAXT, MINB)                                                                                         \
   do {                                                                                                                      \
     TCAVP_CUDA(cudaFuncSetAttribute(fa::attn_flash_kernel<DH, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     fa::attn_flash_kernel<DH, MAXT, MINB><<<grid, warps * 32, smem, stream>>>(a, tk_pad);                                    \
   } while (0)
   if (a.dh == 64) {
-    if (warps <= 9) TCAVP_FLASH(64, 288, 2);
-    else TCAVP_FLASH(64, 384, 1);
+    if (warps <= 5) TCAVP_FLASH(64, 160, 3);   // L <= 160: three CTAs per SM
+    else TCAVP_FLASH(64, 256, 2);
   } else if (a.dh == 128) {
-    TCAVP_FLASH(128, 320, 1);
+    if (warps <= 5) TCAVP_FLASH(128, 160, 2);
+    else TCAVP_FLASH(128, 256, 1);
   } else if (a.dh == 96) {       // Q-Former heads (768 / 8)
-    TCAVP_FLASH(96, 320, 1);
+    TCAVP_FLASH(96, 256, 1);
   } else if (a.dh == 32) {
-    TCAVP_FLASH(32, 384, 1);
+    TCAVP_FLASH(32, 256, 2);
   } else {                       // lane-polygon encoder heads (64 / 4)
-    TCAVP_FLASH(16, 384, 1);
+    TCAVP_FLASH(16, 256, 2);
   }
 #undef TCAVP_FLASH
   return check_launch("attn_flash_kernel");

@@ -4,14 +4,16 @@
 
 namespace tcavp {
 
-__global__ void rope_table_kernel(float* __restrict__ cs, const float* __restrict__ inv_freq, int L, int half) {
+__global__ void rope_table_kernel(float* __restrict__ cs, const float* __restrict__ inv_freq, int L, int half, int layout) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= L * half) return;
   const int pos = i / half, j = i % half;
   // HF:131-134: angle = pos * inv_freq in fp32 (inv_freq comes from the host, computed exactly as HF:86-88 does)
   const float ang = (float)pos * __ldg(inv_freq + j);
-  cs[2 * i] = cosf(ang);
-  cs[2 * i + 1] = sinf(ang);
+  // layout 0: [L][dh/2][2]   layout 1: [dh/4][L][4] (pairs 2q, 2q+1 of position pos share one float4)
+  const size_t o = layout == 0 ? 2 * (size_t)i : ((size_t)(j >> 1) * L + pos) * 4 + (j & 1) * 2;
+  cs[o] = cosf(ang);
+  cs[o + 1] = sinf(ang);
 }
 
 // One thread per (row, head, 8 consecutive pair indices); q heads then k heads are adjacent in the row.
@@ -114,10 +116,11 @@ using namespace tcavp;
 #define STREAM(s) reinterpret_cast<cudaStream_t>(s)
 #define DT_OK(d) ((d) == TCAVP_F32 || (d) == TCAVP_BF16)
 
-extern "C" int tcavp_rope_table(float* cos_sin, const float* inv_freq, int L, int dh, tcavp_stream_t stream) {
+extern "C" int tcavp_rope_table(float* cos_sin, const float* inv_freq, int L, int dh, int layout, tcavp_stream_t stream) {
   TCAVP_REQUIRE(cos_sin && inv_freq && L > 0 && dh > 0 && dh % 2 == 0, "tcavp_rope_table: bad args L=%d dh=%d", L, dh);
+  TCAVP_REQUIRE(layout == 0 || (layout == 1 && dh % 4 == 0), "tcavp_rope_table: bad layout %d for dh=%d", layout, dh);
   const int n = L * (dh / 2);
-  rope_table_kernel<<<(n + 255) / 256, 256, 0, STREAM(stream)>>>(cos_sin, inv_freq, L, dh / 2);
+  rope_table_kernel<<<(n + 255) / 256, 256, 0, STREAM(stream)>>>(cos_sin, inv_freq, L, dh / 2, layout);
   return check_launch("rope_table_kernel");
 }
 

@@ -20,7 +20,7 @@ namespace tc {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one SWIZZLE_128B atom row
 constexpr int UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 8;   // two warps per TMEM lane quarter, each draining alternate 32-column chunks
+constexpr int NUM_EPI_WARPS = 16;  // four warps per TMEM lane quarter, each draining every fourth 32-column chunk
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..: epilogue
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 
@@ -148,7 +148,7 @@ enum { EPI_VEC_OUT = 1, EPI_VEC_RES = 2, EPI_VEC_BIAS = 4 };
 
 // Epilogue of 32 accumulator columns [nacc0, nacc0+32) of row m for one thread.  The interior-tile path (full chunk,
 // 16-byte aligned rows) is branch-light and fully vectorised; ragged edges take the scalar path.
-__device__ __forceinline__ void epilogue_chunk(const EpilogueParams& p, int m, int nacc0, const uint32_t (&r)[32], int flags) {
+__device__ __forceinline__ void epilogue_chunk(const EpilogueParams& p, int m, int pos, int nacc0, const uint32_t (&r)[32], float rs, int flags) {
   if (m >= p.M) return;
   const int mo = remap_row(p.remap_gi, p.remap_go, p.remap_off, m);
   float o[32];
@@ -157,22 +157,23 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueParams& p, int m, i
     cnt = 16;
     n0 = nacc0 >> 1;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) o[j] = swiglu_f(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+    for (int j = 0; j < 16; ++j) o[j] = swiglu_f(__uint_as_float(r[2 * j]) * rs, __uint_as_float(r[2 * j + 1]) * rs);
   } else {
     cnt = 32;
     n0 = nacc0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(r[j]);
+    for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(r[j]) * rs;
   }
   if (n0 >= p.N) return;
   const bool full = (n0 + cnt <= p.N);
   if (p.rope_cols > 0 && n0 < p.rope_cols) {
-    // chunk = 32 columns = 16 rotation pairs of one head (rope_dh is a multiple of 32)
-    const int half = p.rope_dh >> 1;
-    const float4* cs = reinterpret_cast<const float4*>(p.rope + 2 * ((size_t)(m % p.rope_L) * half + ((n0 % p.rope_dh) >> 1)));
+    // chunk = 32 columns = 16 rotation pairs of one head (rope_dh is a multiple of 32).  The table is laid out
+    // [dh/4][L] x float4 (cos, sin of two adjacent pairs): consecutive rows (= consecutive positions = consecutive lanes)
+    // read consecutive 16-byte entries, so each load is 4 wavefronts instead of 32.
+    const float4* cs = reinterpret_cast<const float4*>(p.rope) + (size_t)((n0 % p.rope_dh) >> 2) * p.rope_L + pos;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float4 t = __ldg(cs + j);   // (cos, sin) of two adjacent pairs
+      const float4 t = __ldg(cs + (size_t)j * p.rope_L);   // (cos, sin) of two adjacent pairs
       const float a0 = o[4 * j], a1 = o[4 * j + 1], a2 = o[4 * j + 2], a3 = o[4 * j + 3];
       o[4 * j] = a0 * t.x - a1 * t.y;
       o[4 * j + 1] = a1 * t.x + a0 * t.y;
@@ -382,12 +383,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       mbar_wait(tmem_full_bar + 8 * acc, (it >> 1) & 1);
       tc_fence_after();
       const int m = m0 + quarter * 32 + lane;
+      const float rs = (ep.row_scale && m < M) ? __ldg(ep.row_scale + m) : 1.f;
+      const int pos = ep.rope_cols > 0 ? m % ep.rope_L : 0;
 #pragma unroll 1
       for (int c = chunk0; c < BLOCK_N / 32; c += NUM_EPI_WARPS / 4) {
         if (n0 + c * 32 >= Nacc) break;   // warp-uniform
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + c * 32, r);
-        epilogue_chunk(ep, m, n0 + c * 32, r, flags);
+        epilogue_chunk(ep, m, pos, n0 + c * 32, r, rs, flags);
       }
       tc_fence_before();
       __syncwarp();
@@ -535,19 +538,20 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A,
     if (m >= M) continue;
     const int mo = remap_row(ep.remap_gi, ep.remap_go, ep.remap_off, m);
     const int n = n0 + tx * 4;
+    if (ep.row_scale) {
+      const float rs = __ldg(ep.row_scale + m);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] *= rs;
+    }
     if (ep.act == TCAVP_ACT_SWIGLU) {
       epilogue_store(ep, m, mo, n / 2, silu_f(acc[i][0]) * acc[i][1]);
       epilogue_store(ep, m, mo, n / 2 + 1, silu_f(acc[i][2]) * acc[i][3]);
     } else if (ep.rope_cols > 0 && n < ep.rope_cols) {
-      const int half = ep.rope_dh >> 1;
-      const float2* cs = reinterpret_cast<const float2*>(ep.rope) + (size_t)(m % ep.rope_L) * half + ((n % ep.rope_dh) >> 1);
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const float2 t = __ldg(cs + j);
-        const float x1 = acc[i][2 * j], x2 = acc[i][2 * j + 1];
-        epilogue_store(ep, m, mo, n + 2 * j, x1 * t.x - x2 * t.y);
-        epilogue_store(ep, m, mo, n + 2 * j + 1, x2 * t.x + x1 * t.y);
-      }
+      const float4 t = __ldg(reinterpret_cast<const float4*>(ep.rope) + (size_t)((n % ep.rope_dh) >> 2) * ep.rope_L + (m % ep.rope_L));
+      epilogue_store(ep, m, mo, n, acc[i][0] * t.x - acc[i][1] * t.y);
+      epilogue_store(ep, m, mo, n + 1, acc[i][1] * t.x + acc[i][0] * t.y);
+      epilogue_store(ep, m, mo, n + 2, acc[i][2] * t.z - acc[i][3] * t.w);
+      epilogue_store(ep, m, mo, n + 3, acc[i][3] * t.z + acc[i][2] * t.w);
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) epilogue_store(ep, m, mo, n + j, acc[i][j]);
@@ -577,6 +581,7 @@ extern "C" int tcavp_gemm(const tcavp_gemm_args* a, tcavp_stream_t stream_) {
   ep.residual = a->residual; ep.ldr = a->ldr; ep.res_dtype = a->res_dtype;
   ep.act = a->act;
   ep.remap_gi = a->remap_gi; ep.remap_go = a->remap_go; ep.remap_off = a->remap_off;
+  ep.row_scale = a->row_scale;
   ep.rope = a->rope_cos_sin; ep.rope_L = a->rope_L; ep.rope_dh = a->rope_dh; ep.rope_cols = a->rope_cos_sin ? a->rope_cols : 0;
   if (ep.rope_cols > 0) {
     TCAVP_REQUIRE(a->act == TCAVP_ACT_NONE && !a->bias, "tcavp_gemm: fused RoPE needs act NONE and no bias");

@@ -114,12 +114,12 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* x, const voi
 
 template <bool VEC>
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const void* __restrict__ x, const float* __restrict__ w,
-                                                      void* __restrict__ out, int rows, int cols, int ldo, float eps,
+                                                      void* __restrict__ out, int rows, int cols, int ldi, int ldo, float eps,
                                                       int in_dtype, int out_dtype) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
-  const size_t base = (size_t)row * cols, obase = (size_t)row * ldo;
+  const size_t base = (size_t)row * ldi, obase = (size_t)row * ldo;
   float q = 0.f;
   if (VEC) {
     for (int c = lane * 8; c < cols; c += 256) {
@@ -152,6 +152,32 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const void* __restrict__ x
   }
 }
 
+// rstd[r] = rsqrt(mean(x[r,:]^2) + eps): one warp per row, 16-byte loads
+template <bool VEC>
+__global__ void __launch_bounds__(256) row_rstd_kernel(const void* __restrict__ x, int ldx, int rows, int cols, float eps, int dtype,
+                                                       float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const size_t base = (size_t)row * ldx;
+  float q = 0.f;
+  if (VEC) {
+    for (int c = lane * 8; c < cols; c += 256) {
+      float v[8];
+      load8(x, base + c, dtype, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) q += v[e] * v[e];
+    }
+  } else {
+    for (int c = lane; c < cols; c += 32) {
+      const float v = load_as_f(x, base + c, dtype);
+      q += v * v;
+    }
+  }
+  q = warp_sum(q);
+  if (lane == 0) out[row] = rsqrtf(q / cols + eps);
+}
+
 static bool aligned_rows(const void* p, int ld, int dtype) {
   const size_t es = dtype == TCAVP_BF16 ? 2 : 4;
   return p == nullptr || (reinterpret_cast<uintptr_t>(p) % (8 * es) == 0 && ((size_t)ld * es) % (8 * es) == 0);
@@ -179,20 +205,34 @@ extern "C" int tcavp_layernorm(const void* x, const void* residual, const float*
   return check_launch("layernorm_kernel");
 }
 
-extern "C" int tcavp_rmsnorm(const void* x, const float* w, void* out, int rows, int cols, int ldo, float eps, int in_dtype,
+extern "C" int tcavp_row_rstd(const void* x, int ldx, int rows, int cols, float eps, int dtype, float* out, tcavp_stream_t stream_) {
+  using namespace tcavp;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  TCAVP_REQUIRE(rows >= 0 && cols > 0 && ldx >= cols, "tcavp_row_rstd: bad shape rows=%d cols=%d ldx=%d", rows, cols, ldx);
+  if (rows == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(x && out && (dtype | 1) == 1, "tcavp_row_rstd: bad pointer/dtype");
+  const int grid = (rows + 7) / 8;
+  if (cols % 8 == 0 && aligned_rows(x, ldx, dtype))
+    row_rstd_kernel<true><<<grid, 256, 0, stream>>>(x, ldx, rows, cols, eps, dtype, out);
+  else
+    row_rstd_kernel<false><<<grid, 256, 0, stream>>>(x, ldx, rows, cols, eps, dtype, out);
+  return check_launch("row_rstd_kernel");
+}
+
+extern "C" int tcavp_rmsnorm(const void* x, int ldi, const float* w, void* out, int rows, int cols, int ldo, float eps, int in_dtype,
                              int out_dtype, tcavp_stream_t stream_) {
   using namespace tcavp;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  TCAVP_REQUIRE(rows >= 0 && cols > 0 && ldo >= cols, "tcavp_rmsnorm: bad shape rows=%d cols=%d ldo=%d", rows, cols, ldo);
+  TCAVP_REQUIRE(rows >= 0 && cols > 0 && ldo >= cols && ldi >= cols, "tcavp_rmsnorm: bad shape rows=%d cols=%d ldi=%d ldo=%d", rows, cols, ldi, ldo);
   if (rows == 0) return TCAVP_OK;
   TCAVP_REQUIRE(x && w && out, "tcavp_rmsnorm: null pointer");
   TCAVP_REQUIRE((in_dtype | 1) == 1 && (out_dtype | 1) == 1, "tcavp_rmsnorm: bad dtype");
-  const bool vec = cols % 8 == 0 && aligned_rows(x, cols, in_dtype) && aligned_rows(out, ldo, out_dtype);
+  const bool vec = cols % 8 == 0 && aligned_rows(x, ldi, in_dtype) && aligned_rows(out, ldo, out_dtype);
   const int wpb = 8;
   const int grid = (rows + wpb - 1) / wpb;
   if (vec)
-    rmsnorm_kernel<true><<<grid, wpb * 32, 0, stream>>>(x, w, out, rows, cols, ldo, eps, in_dtype, out_dtype);
+    rmsnorm_kernel<true><<<grid, wpb * 32, 0, stream>>>(x, w, out, rows, cols, ldi, ldo, eps, in_dtype, out_dtype);
   else
-    rmsnorm_kernel<false><<<grid, wpb * 32, 0, stream>>>(x, w, out, rows, cols, ldo, eps, in_dtype, out_dtype);
+    rmsnorm_kernel<false><<<grid, wpb * 32, 0, stream>>>(x, w, out, rows, cols, ldi, ldo, eps, in_dtype, out_dtype);
   return check_launch("rmsnorm_kernel");
 }

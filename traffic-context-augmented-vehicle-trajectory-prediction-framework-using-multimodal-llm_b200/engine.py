@@ -1,6 +1,8 @@
 """Forward engine: packs the reference-layout parameters into device buffers laid out for the kernels
 (fused QKV with the LoRA K-extension, interleaved gate/up, channel-contiguous NLinear weights, (t,c)-ordered
 lane_fc / post_mlp) and drives libtcavp.so over one CUDA stream.  No torch arithmetic on the data path."""
+import os
+
 import torch
 
 from . import ops
@@ -64,6 +66,11 @@ class Engine:
         self.poly = dict(D=m.d_model, P=m.max_points, heads=m.nhead, w=_f32(m.input_proj.weight, self.dev),
                          b=_f32(m.input_proj.bias, self.dev), pos=_f32(m.pos_embedding[0], self.dev),
                          layers=[self._enc_layer(l) for l in m.encoder.layers])
+        # The first layer sees raw pixel coordinates (|x| ~ 1e3, train.py:364): its attention logits are ~1e6 and the
+        # softmax is argmax-like, so bf16 operands would change which key wins.  That one attention sub-block therefore
+        # always runs in exact fp32; everything after the first LayerNorm is O(1) and uses the activation dtype.
+        if len(m.encoder.layers) > 0:
+            self.poly["sa0_f32"] = self._mha(m.encoder.layers[0].self_attn, torch.float32)
 
     def _pack_qformer(self, mllm):
         q = mllm.qformer
@@ -94,7 +101,7 @@ class Engine:
         nq, nk = nh * dh, nkv * dh
         # RoPE fusion: within every q / k head, move rotation partners (i, i + dh/2) to adjacent rows (2i, 2i+1) so the
         # GEMM epilogue can rotate in registers; q.k is invariant under the shared permutation, v keeps its order.
-        self.llm["fuse_rope"] = dh % 32 == 0
+        self.llm["fuse_rope"] = dh % 32 == 0 and not os.environ.get("TCAVP_NO_FUSE_ROPE")
         hp = torch.stack([torch.arange(dh // 2), torch.arange(dh // 2) + dh // 2], dim=1).reshape(-1)
         qk_perm = torch.cat([h * dh + hp for h in range(nh + nkv)] + [torch.arange(nq + nk, nq + 2 * nk)]).to(dev)
         for layer in lm.model.layers:
@@ -113,11 +120,18 @@ class Engine:
                     wqkv[r0:r1, :H] = mod.weight.detach().to(dev, act)
             if self.llm["fuse_rope"]:
                 wqkv = wqkv[qk_perm].contiguous()
+            # RMSNorm fusion: w * (x * rstd) . W^T == rstd * (x . (W diag(w))^T): the norm weight is folded into the weight
+            # columns (fp32 product, rounded once), rstd is applied to the accumulators in the GEMM epilogue.  The LoRA side
+            # product then has to be T' = x . (A diag(w))^T WITHOUT rstd, so that rstd * ([x | T'] . [W' | sB]^T) is exact.
+            ln1 = layer.input_layernorm.weight.detach().float().to(dev)
+            ln2 = layer.post_attention_layernorm.weight.detach().float().to(dev)
+            wqkv[:, :H] = (wqkv[:, :H].float() * ln1[None, :]).to(act)
+            if a_cat is not None:
+                a_cat = (a_cat.float() * ln1[None, :]).to(act)
             gu = torch.empty(2 * I, H, dtype=act, device=dev)
-            gu[0::2] = layer.mlp.gate_proj.weight.detach().to(dev, act)
-            gu[1::2] = layer.mlp.up_proj.weight.detach().to(dev, act)
+            gu[0::2] = (layer.mlp.gate_proj.weight.detach().to(dev).float() * ln2[None, :]).to(act)
+            gu[1::2] = (layer.mlp.up_proj.weight.detach().to(dev).float() * ln2[None, :]).to(act)
             self.llm["layers"].append(dict(
-                ln1=_f32(layer.input_layernorm.weight, dev), ln2=_f32(layer.post_attention_layernorm.weight, dev),
                 wqkv=wqkv, a_cat=a_cat, wo=sa.o_proj.weight.detach().to(dev, act).contiguous(), wgu=gu,
                 wdown=layer.mlp.down_proj.weight.detach().to(dev, act).contiguous()))
 
@@ -178,11 +192,13 @@ class Engine:
     def _ln_res(self, y, ln, out=None, **kw):
         return ops.layernorm(y, ln[0], ln[1], self._new(*y.shape, dtype=y.dtype) if out is None else out, eps=ln[2], **kw)
 
-    def _encoder_layer(self, x, T, B, L, key_mask=None):
-        """torch: nn.TransformerEncoderLayer (post-norm, ReLU)."""
-        a = self._self_attention(x, T, B, L["sa"], key_mask)
-        y = ops.gemm(a, L["sa"]["out"].w, self._new(*x.shape), bias=L["sa"]["out"].b, residual=x)
-        x = self._ln_res(y, L["n1"])
+    def _encoder_layer(self, x, T, B, L, key_mask=None, sa_f32=None):
+        """torch: nn.TransformerEncoderLayer (post-norm, ReLU).  `sa_f32`: run the attention sub-block on an fp32 input in
+        exact fp32 and hand the LayerNorm output over in the activation dtype."""
+        sa = sa_f32 if sa_f32 is not None else L["sa"]
+        a = self._self_attention(x, T, B, sa, key_mask)
+        y = ops.gemm(a, sa["out"].w, self._new(*x.shape, dtype=x.dtype), bias=sa["out"].b, residual=x)
+        x = self._ln_res(y, L["n1"], out=self._new(*x.shape))
         h = ops.gemm(x, L["l1"].w, self._new(x.shape[0], L["l1"].N), bias=L["l1"].b, act=ops.ACT_RELU)
         y = ops.gemm(h, L["l2"].w, self._new(*x.shape), bias=L["l2"].b, residual=x)
         return self._ln_res(y, L["n2"])
@@ -192,11 +208,13 @@ class Engine:
         """reference scripts/train.py:362-383 -> (B, D) fp32."""
         p = self.poly
         B, P, D = polygon.shape[0], polygon.shape[1], p["D"]
-        x = self._new(B * P, D)
+        x = self._new(B * P, D, dtype=torch.float32)
         kmask = torch.empty(B, P, dtype=torch.int32, device=self.dev)
         ops.poly_embed(polygon, lens, p["w"], p["b"], p["pos"], x, kmask, B=B, P=P, D=D)
-        for L in p["layers"]:
-            x = self._encoder_layer(x, P, B, L, kmask)
+        for i, L in enumerate(p["layers"]):
+            x = self._encoder_layer(x, P, B, L, kmask, sa_f32=p["sa0_f32"] if i == 0 else None)
+        if not p["layers"] and x.dtype != self.act:
+            x = ops.cast(x, self._new(B * P, D), rows=B * P, cols=D)
         return ops.masked_mean(x, lens, self._new(B, D, dtype=self.small), B=B, P=P, D=D)
 
     def qformer_into(self, vision, fused, L_total):
@@ -237,36 +255,36 @@ class Engine:
         m = self.llm
         H, nh, nkv, dh, I, kx = m["H"], m["nh"], m["nkv"], m["dh"], m["I"], m["kx"]
         M = B * L
-        key = (L, dh)
+        key = (L, dh, 1 if m["fuse_rope"] else 0)
         if key not in self._rope:
-            self._rope[key] = ops.rope_table(L, dh, m["theta"], self.dev)
+            self._rope[key] = ops.rope_table(L, dh, m["theta"], self.dev, layout=key[2])
         table = self._rope[key]
-        x = fused.view(M, H)
         Kx = H + kx
-        hn = torch.zeros(M, Kx, dtype=self.act, device=self.dev) if kx != m["n_lora"] else self._new(M, Kx)
+        # residual stream in K-extended rows: columns [0,H) hold x, columns [H,H+kx) receive the LoRA side product
+        xs = torch.zeros(M, Kx, dtype=self.act, device=self.dev) if kx != m["n_lora"] else self._new(M, Kx)
+        ops.cast(fused.view(M, H), xs, rows=M, cols=H, ldi=H, ldo=Kx)
+        x = xs[:, :H]
+        rstd = torch.empty(M, dtype=torch.float32, device=self.dev)
         nqkv = (nh + 2 * nkv) * dh
         qkv = self._new(M, nqkv)
         attn = self._new(M, nh * dh)
-        hn2 = self._new(M, H)
         mid = self._new(M, I)
+        rope = (table, L, dh, (nh + nkv) * dh) if m["fuse_rope"] else None
         for ly in m["layers"]:
-            ops.rmsnorm(x, ly["ln1"], hn, eps=m["eps"], rows=M, cols=H, ldo=Kx)
+            ops.row_rstd(xs, rstd, rows=M, cols=H, ldx=Kx, eps=m["eps"])
             if kx:
-                # T = xn . [A_q; A_v]^T lands in the K-extension columns of the same activation buffer
-                ops.gemm(hn, ly["a_cat"], hn[:, H:], M=M, N=m["n_lora"], K=H, lda=Kx, ldo=Kx)
-            if m["fuse_rope"]:
-                ops.gemm(hn, ly["wqkv"], qkv, M=M, N=nqkv, K=Kx, lda=Kx, rope=(table, L, dh, (nh + nkv) * dh))
-            else:
-                ops.gemm(hn, ly["wqkv"], qkv, M=M, N=nqkv, K=Kx, lda=Kx)
+                ops.gemm(xs, ly["a_cat"], xs[:, H:], M=M, N=m["n_lora"], K=H, lda=Kx, ldo=Kx)
+            ops.gemm(xs, ly["wqkv"], qkv, M=M, N=nqkv, K=Kx, lda=Kx, rope=rope, row_scale=rstd)
+            if rope is None:
                 ops.rope_(qkv, rows=M, L=L, ld=nqkv, n_q_heads=nh, n_k_heads=nkv, dh=dh, table=table)
             ops.attention(qkv, qkv[:, nh * dh:], qkv[:, (nh + nkv) * dh:], attn, B=B, H=nh, Hkv=nkv, Tq=L, Tk=L, dh=dh,
                           q_strides=(L * nqkv, nqkv), k_strides=(L * nqkv, nqkv), v_strides=(L * nqkv, nqkv),
                           o_strides=(L * nh * dh, nh * dh), scale=dh ** -0.5, causal=True, key_mask=mask)
-            ops.gemm(attn, ly["wo"], x, residual=x)
-            ops.rmsnorm(x, ly["ln2"], hn2, eps=m["eps"], rows=M, cols=H)
-            ops.gemm(hn2, ly["wgu"], mid, act=ops.ACT_SWIGLU)
-            ops.gemm(mid, ly["wdown"], x, residual=x)
-        return ops.rmsnorm(x, m["norm"], self._new(M, H), eps=m["eps"], rows=M, cols=H)
+            ops.gemm(attn, ly["wo"], x, ldo=Kx, residual=x, ldr=Kx)
+            ops.row_rstd(xs, rstd, rows=M, cols=H, ldx=Kx, eps=m["eps"])
+            ops.gemm(xs, ly["wgu"], mid, M=M, K=H, lda=Kx, act=ops.ACT_SWIGLU, row_scale=rstd)
+            ops.gemm(mid, ly["wdown"], x, ldo=Kx, residual=x, ldr=Kx)
+        return ops.rmsnorm(xs, m["norm"], self._new(M, H), eps=m["eps"], rows=M, cols=H, ldi=Kx)
 
     def ltsf_encode(self, x, B):
         """reference scripts/train.py:837-840 -> enc (B*T_in, C)."""

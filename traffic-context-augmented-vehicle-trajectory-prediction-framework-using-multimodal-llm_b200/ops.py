@@ -24,7 +24,8 @@ class GemmArgs(Structure):
                 ("residual", c_void_p), ("ldr", c_int), ("res_dtype", c_int),
                 ("act", c_int),
                 ("remap_gi", c_int), ("remap_go", c_int), ("remap_off", c_int),
-                ("rope_cos_sin", c_void_p), ("rope_L", c_int), ("rope_dh", c_int), ("rope_cols", c_int)]
+                ("rope_cos_sin", c_void_p), ("rope_L", c_int), ("rope_dh", c_int), ("rope_cols", c_int),
+                ("row_scale", c_void_p)]
 
 
 class AttnArgs(Structure):
@@ -126,7 +127,7 @@ def _need_cuda(*ts):
 
 
 def gemm(a, w, out, *, M=None, N=None, K=None, lda=None, ldw=None, ldo=None, bias=None, residual=None, ldr=None,
-         act=ACT_NONE, remap=(0, 0, 0), rope=None):
+         act=ACT_NONE, remap=(0, 0, 0), rope=None, row_scale=None):
     """out = act(a @ w.T + bias) + residual.  a: [M, >=K] row-major (lda = a.stride(0)), w: [N, >=K]."""
     _need_cuda(a, w, out, bias, residual)
     g = GemmArgs()
@@ -146,6 +147,10 @@ def gemm(a, w, out, *, M=None, N=None, K=None, lda=None, ldw=None, ldo=None, bia
         g.residual, g.ldr, g.res_dtype = residual.data_ptr(), (residual.stride(0) if ldr is None else ldr), dt(residual)
     g.act = act
     g.remap_gi, g.remap_go, g.remap_off = remap
+    if row_scale is not None:
+        if row_scale.dtype != torch.float32:
+            raise TypeError("gemm: row_scale must be fp32")
+        g.row_scale = row_scale.data_ptr()
     if rope is not None:     # (table, L, dh, cols)
         g.rope_cos_sin, g.rope_L, g.rope_dh, g.rope_cols = rope[0].data_ptr(), rope[1], rope[2], rope[3]
     if g.in_dtype == BF16:
@@ -177,6 +182,8 @@ def attention(q, k, v, out, *, B, H, Hkv, Tq, Tk, dh, q_strides, k_strides, v_st
         kern = f"attn_flash_kernel[dh{dh},q{Tq},k{Tk}]"
     elif a.dtype == BF16 and dh > 128 and dh % 64 == 0 and Tq <= 32 and Tk <= 256 and not causal:
         kern = "attn_x_kernel"
+    elif dh in (16, 32) and Tk <= 128:
+        kern = f"attn_row_kernel[dh{dh},q{Tq},k{Tk}]"
     else:
         kern = f"attn_warp_kernel[dh{dh},q{Tq},k{Tk}]"
     fl = 4.0 * B * H * Tq * Tk * dh * (0.5 if causal else 1.0)
@@ -195,23 +202,31 @@ def layernorm(x, w, b, out, *, residual=None, eps=1e-5, remap=(0, 0, 0), rowvec=
     return out
 
 
-def rmsnorm(x, w, out, *, eps, rows=None, cols=None, ldo=None):
+def rmsnorm(x, w, out, *, eps, rows=None, cols=None, ldi=None, ldo=None):
     _need_cuda(x, w, out)
     rows = x.numel() // x.shape[-1] if rows is None else rows
     cols = x.shape[-1] if cols is None else cols
     ldo = cols if ldo is None else ldo
-    with _Timed("rmsnorm_kernel"):
-        _lib.check(_lib.load().tcavp_rmsnorm(_p(x), _p(w), _p(out), rows, cols, ldo, c_float(eps), dt(x), dt(out), _stream()),
-               "tcavp_rmsnorm")
+    ldi = cols if ldi is None else ldi
+    with _Timed("rmsnorm_kernel", 0.0, float(rows * cols * (x.element_size() + out.element_size()))):
+        _lib.check(_lib.load().tcavp_rmsnorm(_p(x), ldi, _p(w), _p(out), rows, cols, ldo, c_float(eps), dt(x), dt(out), _stream()),
+                   "tcavp_rmsnorm")
     return out
 
 
-def rope_table(L, dh, theta, device):
+def row_rstd(x, out, *, rows, cols, ldx, eps):
+    _need_cuda(x, out)
+    with _Timed("row_rstd_kernel", 0.0, float(rows * cols * x.element_size())):
+        _lib.check(_lib.load().tcavp_row_rstd(_p(x), ldx, rows, cols, c_float(eps), dt(x), _p(out), _stream()), "tcavp_row_rstd")
+    return out
+
+
+def rope_table(L, dh, theta, device, layout=0):
     # HF:86-88 inv_freq, evaluated on the host exactly as transformers does
     inv = (1.0 / (theta ** (torch.arange(0, dh, 2, dtype=torch.int64).float() / dh))).to(device)
-    t = torch.empty(L, dh // 2, 2, dtype=torch.float32, device=device)
+    t = torch.empty((L, dh // 2, 2) if layout == 0 else (dh // 4, L, 4), dtype=torch.float32, device=device)
     with _Timed("rope_table_kernel"):
-        _lib.check(_lib.load().tcavp_rope_table(_p(t), _p(inv), L, dh, _stream()), "tcavp_rope_table")
+        _lib.check(_lib.load().tcavp_rope_table(_p(t), _p(inv), L, dh, layout, _stream()), "tcavp_rope_table")
     return t
 
 
