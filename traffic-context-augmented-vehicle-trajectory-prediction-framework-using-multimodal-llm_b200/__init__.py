@@ -5,3 +5,4 @@ from .synthetic import make_scenes  # noqa: F401
 from .weights import deterministic_fill_  # noqa: F401
 from .model import MultiModalTrajectoryModel  # noqa: F401,E402
 from . import ops  # noqa: F401,E402
+from . import distributed  # noqa: F401,E402
