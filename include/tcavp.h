@@ -196,6 +196,68 @@ int tcavp_fusion_head(const void* fused, int in_dtype, const float* ln_w, const 
 int tcavp_traj_metrics(const float* decoded, const float* y, const float* norm_stat, float* metrics, float* per_scene,
                        int B, int T_out, tcavp_stream_t stream);
 
+/* ==== fine-tune step: backward kernels (reference scripts/im_kim_train_GRN.py:1039-1040 loss.backward() + AdamW; the
+ * reference leaves these to torch autograd).  Dense gradient contractions are tcavp_gemm calls on transposed operands:
+ *   dX = dY . W      -> tcavp_gemm(A = dY, W = W^T)          dW = dY^T . X  -> tcavp_gemm(A = dY^T, W = X^T) ======== */
+
+/* out[b][c][r] = in[b][r][c] for r < rows, c < cols (batch strides / leading dimensions in elements). */
+int tcavp_transpose(const void* in, long long in_bstride, int ldi, int in_dtype, void* out, long long out_bstride, int ldo,
+                    int out_dtype, int batch, int rows, int cols, tcavp_stream_t stream);
+/* out[r % period][c] += x[r][c]  (fp32 [period, cols], accumulated): bias gradients (period 1) and the gradients of
+ * broadcast tables — pos_embedding / pos_encoding / query_tokens / modality embeddings (train.py:365, 412, 522, 527, 839). */
+int tcavp_period_sum(const void* x, int ldx, int dtype, long long rows, int cols, int period, float* out, tcavp_stream_t stream);
+/* dx = y > 0 ? dy : 0  (nn.ReLU backward on the stored activation output). */
+int tcavp_relu_bwd(const void* dy, int lddy, const void* y, int ldy, void* dx, int lddx, int dtype, long long rows, int cols,
+                   tcavp_stream_t stream);
+/* out = alpha * a + beta * b  (b optional): gradient accumulation where two consumers share a tensor, LoRA scaling. */
+int tcavp_axpby(const void* a, int lda, int a_dtype, float alpha, const void* b, int ldb, int b_dtype, float beta, void* out, int ldo,
+                int out_dtype, long long rows, int cols, tcavp_stream_t stream);
+/* SwiGLU on interleaved (gate, up) columns (HF:190) and its backward; gu / dgu are [rows, 2I], out / dout [rows, I]. */
+int tcavp_swiglu(const void* gu, void* out, int dtype, long long rows, int I, tcavp_stream_t stream);
+int tcavp_swiglu_bwd(const void* dout, const void* gu, void* dgu, int dtype, long long rows, int I, tcavp_stream_t stream);
+/* Backward of tcavp_layernorm (input x + residual): dx (optional), dw += sum_r dy*xhat, db += sum_r dy (optional pair). */
+int tcavp_layernorm_bwd(const void* dy, int dy_dtype, const void* x, const void* residual, int x_dtype, const float* w, int rows,
+                        int cols, float eps, void* dx, int dx_dtype, float* dw, float* db, tcavp_stream_t stream);
+/* Backward of LlamaRMSNorm (HF:53-70): dx = rstd * (g - xhat * mean(g * xhat)) + add, g = dy * w (w NULL = unit weight,
+ * the folded-weight form of the LLM stack); `add` (optional) is the residual-branch gradient. */
+int tcavp_rmsnorm_bwd(const void* dy, int lddy, const void* x, int ldx, const float* w, const void* add, int ldadd, void* dx, int lddx,
+                      int dtype, int rows, int cols, float eps, tcavp_stream_t stream);
+/* Rotary embedding on adjacent column pairs (the layout of tcavp_gemm's fused RoPE), in place on columns [0, cols) of a
+ * [rows, ld] buffer; inverse != 0 applies the transpose rotation (= the backward of HF:146-170). Table layout 1. */
+int tcavp_rope_adjacent(void* buf, int dtype, long long rows, int L, int ld, int cols, int dh, const float* table, int inverse,
+                        tcavp_stream_t stream);
+/* out[remap_out(r), :] = in[remap_in(r), :], remap(r) = (r / gi) * go + r % gi + off (gi = 0: identity): scatter into /
+ * gather from the fused (B, L, H) sequence (train.py:528 torch.cat and its backward). */
+int tcavp_copy_rows(const void* in, int ldi, int in_dtype, int in_gi, int in_go, int in_off, void* out, int ldo, int out_dtype,
+                    int out_gi, int out_go, int out_off, long long rows, int cols, tcavp_stream_t stream);
+/* Backward of tcavp_masked_mean (train.py:373-382). */
+int tcavp_masked_mean_bwd(const void* dout, int dout_dtype, const int32_t* len, void* dx, int dx_dtype, int B, int P, int D,
+                          tcavp_stream_t stream);
+/* Backward of the per-channel NLinear map out[b,t,c] = sum_s W[t][s][c] (in[b,s,c] - in[b,T-1,c]) + bias[t][c] + in[b,T-1,c]
+ * (train.py:701-716, 769-785): din (optional, needs w) and dw[t][s][c] += ... (optional, needs in).  The bias gradient is
+ * tcavp_period_sum(g, period = T_out). */
+int tcavp_nlinear_bwd(const void* g, int g_dtype, const void* in, int in_dtype, const float* w, void* din, int din_dtype, float* dw,
+                      int B, int C, int T_in, int T_out, tcavp_stream_t stream);
+/* decoded[b,f,t] = o[b,t,f] + x[b,f,T_in-1]  (train.py:941-943; o = out_proj rows). */
+int tcavp_head_assemble(const float* o, const float* x, float* decoded, int B, int T_in, int T_out, tcavp_stream_t stream);
+/* d_o[b,t,f] = gscale * d loss / d decoded[b,f,t] for loss = MSE_x + MSE_y on de-normalised coordinates (train.py:945-962);
+ * gscale: optional device scalar (the incoming loss gradient). */
+int tcavp_traj_loss_bwd(const float* decoded, const float* y, const float* norm_stat, const float* gscale, float* d_o, int B, int T_out,
+                        tcavp_stream_t stream);
+/* Rank-r weight gradients of peft lora.Linear (train.py:432-440): out[n][j] += sum_m row_scale[m] * Y[m][n] * Z[m][j], J <= 32
+ * (row_scale optional: the RMSNorm rstd of the folded-norm form). */
+int tcavp_skinny_dw(const void* Y, int ldy, int y_dtype, const void* Z, int ldz, int z_dtype, const float* row_scale, float* out, int ldo,
+                    long long M, int N, int J, tcavp_stream_t stream);
+/* Backward of tcavp_attention (probabilities recomputed; any head_dim; Tk <= 768).  dq has the dtype/layout convention of q;
+ * dk / dv are fp32 accumulators (caller zeroes them) because query blocks and GQA groups add into the same keys. */
+int tcavp_attention_bwd(const tcavp_attn_args* args, const void* dout, long long do_sb, long long do_st, void* dq, long long dq_sb,
+                        long long dq_st, float* dk, long long dk_sb, long long dk_st, float* dv, long long dv_sb, long long dv_st,
+                        tcavp_stream_t stream);
+/* Fused AdamW over flat fp32 buffers, torch.optim.AdamW semantics (im_kim_train_GRN.py:1008); grad_scale multiplies the
+ * gradient first (1/world_size after a sum all-reduce). */
+int tcavp_adamw(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1, float beta2,
+                float eps, float weight_decay, int step, float grad_scale, tcavp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,275 @@
+"""Per-kernel gradient parity of the fine-tune step: every backward C-ABI entry point against torch autograd of the same
+op evaluated in fp32 on the CPU (the plain-tensor restatement the oracle uses).  fp32 storage: rtol 1e-4; bf16 storage:
+compared on bf16-rounded inputs with tolerances that cover output rounding only."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import restated as R  # noqa: E402
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def ops(lib_built):
+    from tcavp_b200 import ops as o
+    assert torch.cuda.is_available()
+    return o
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def _td(name):
+    return torch.float32 if name == "fp32" else torch.bfloat16
+
+
+def _tol(name):
+    return dict(rtol=1e-4, atol=1e-5) if name == "fp32" else dict(rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("batch,rows,cols", [(1, 70, 33), (1, 1000, 64), (5, 2, 15), (3, 64, 40)])
+def test_transpose(ops, dtype, batch, rows, cols):
+    x = _rand(batch, rows, cols, seed=1).to(_td(dtype))
+    ldo = (rows + 7) // 8 * 8
+    out = torch.zeros(batch, cols, ldo, dtype=torch.float32, device=DEV)
+    ops.transpose(x.to(DEV), out, rows=rows, cols=cols, ldo=ldo, batch=batch, in_bstride=rows * cols, out_bstride=cols * ldo)
+    torch.testing.assert_close(out.cpu()[:, :, :rows], x.float().transpose(1, 2))
+    assert torch.count_nonzero(out[:, :, rows:]) == 0
+
+
+@pytest.mark.parametrize("period", [1, 7, 16])
+def test_period_sum(ops, period):
+    rows, cols = period * 37, 200
+    x = _rand(rows, cols, seed=2)
+    out = torch.ones(period, cols, device=DEV)
+    ops.period_sum(x.to(DEV), out, rows=rows, cols=cols, period=period)
+    torch.testing.assert_close(out.cpu(), 1.0 + x.view(37, period, cols).sum(0), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_relu_bwd_axpby_swiglu(ops, dtype):
+    td = _td(dtype)
+    rows, cols = 129, 72
+    y, dy = _rand(rows, cols, seed=3).to(td), _rand(rows, cols, seed=4).to(td)
+    dx = torch.empty(rows, cols, dtype=td, device=DEV)
+    ops.relu_bwd(dy.to(DEV), y.to(DEV), dx, rows=rows, cols=cols)
+    torch.testing.assert_close(dx.cpu().float(), torch.where(y.float() > 0, dy.float(), torch.zeros(())))
+    out = torch.empty(rows, cols, dtype=torch.float32, device=DEV)
+    ops.axpby(y.to(DEV), out, rows=rows, cols=cols, alpha=0.5, b=dy.to(DEV), beta=-2.0)
+    torch.testing.assert_close(out.cpu(), 0.5 * y.float() - 2.0 * dy.float())
+    I = 40
+    gu = _rand(rows, 2 * I, seed=5).to(td).float().requires_grad_(True)
+    want = torch.nn.functional.silu(gu[:, 0::2]) * gu[:, 1::2]
+    d = _rand(rows, I, seed=6).to(td)
+    want.backward(d.float())
+    got = torch.empty(rows, I, dtype=td, device=DEV)
+    ops.swiglu(gu.detach().to(td).to(DEV), got, rows=rows, I=I)
+    torch.testing.assert_close(got.cpu().float(), want.detach(), **_tol(dtype))
+    dgu = torch.empty(rows, 2 * I, dtype=td, device=DEV)
+    ops.swiglu_bwd(d.to(DEV), gu.detach().to(td).to(DEV), dgu, rows=rows, I=I)
+    torch.testing.assert_close(dgu.cpu().float(), gu.grad, **_tol(dtype))
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("rows,cols,with_res", [(37, 64, True), (300, 768, False), (5, 40, True)])
+def test_layernorm_bwd(ops, dtype, rows, cols, with_res):
+    td = _td(dtype)
+    x = _rand(rows, cols, seed=7).to(td).float().requires_grad_(True)
+    r = _rand(rows, cols, seed=8).to(td).float() if with_res else None
+    w = (1.0 + 0.1 * _rand(cols, seed=9)).requires_grad_(True)
+    b = (0.1 * _rand(cols, seed=10)).requires_grad_(True)
+    y = R.layer_norm(x + r if with_res else x, w, b)
+    dy = _rand(rows, cols, seed=11).to(td)
+    y.backward(dy.float())
+    dx = torch.empty(rows, cols, dtype=td, device=DEV)
+    dw, db = torch.zeros(cols, device=DEV), torch.zeros(cols, device=DEV)
+    ops.layernorm_bwd(dy.to(DEV), x.detach().to(td).to(DEV), w.detach().to(DEV), residual=None if r is None else r.to(td).to(DEV),
+                      dx=dx, dw=dw, db=db)
+    torch.testing.assert_close(dx.cpu().float(), x.grad, **_tol(dtype))
+    torch.testing.assert_close(dw.cpu(), w.grad, rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(db.cpu(), b.grad, rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("unit_w", [True, False])
+def test_rmsnorm_bwd(ops, dtype, unit_w):
+    td = _td(dtype)
+    rows, cols, ld = 77, 128, 136
+    xb = _rand(rows, ld, seed=12).to(td)
+    x = xb[:, :cols].float().requires_grad_(True)
+    w = torch.ones(cols) if unit_w else 1.0 + 0.1 * _rand(cols, seed=13)
+    y = R.rms_norm(x, w, 1e-6)
+    dy = _rand(rows, cols, seed=14).to(td)
+    add = _rand(rows, cols, seed=15).to(td)
+    y.backward(dy.float())
+    dx = torch.empty(rows, cols, dtype=td, device=DEV)
+    ops.rmsnorm_bwd(dy.to(DEV), xb.to(DEV), dx, rows=rows, cols=cols, eps=1e-6, w=None if unit_w else w.to(DEV), add=add.to(DEV), ldx=ld)
+    torch.testing.assert_close(dx.cpu().float(), x.grad + add.float(), **_tol(dtype))
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_rope_adjacent_matches_fused_gemm_layout_and_inverts(ops, dtype):
+    td = _td(dtype)
+    L, dh, heads, B = 12, 32, 3, 4
+    rows, cols = B * L, heads * dh
+    table = ops.rope_table(L, dh, 10000.0, DEV, layout=1)
+    x = _rand(rows, cols + 8, seed=16).to(td)
+    buf = x.clone().to(DEV)
+    ops.rope_adjacent_(buf, rows=rows, L=L, ld=cols + 8, cols=cols, dh=dh, table=table)
+    # reference: HF rotate_half on the un-permuted layout; adjacent pair (2i, 2i+1) of a head = HF pair (i, i + dh/2)
+    cos, sin = R.rope_cos_sin(L, dh, 10000.0)
+    xh = x[:, :cols].float().view(B, L, heads, dh)
+    unperm = torch.cat([xh[..., 0::2], xh[..., 1::2]], dim=-1)                      # adjacent -> HF order
+    rot = unperm * cos[None, :, None, :] + R.rotate_half(unperm) * sin[None, :, None, :]
+    want = torch.stack([rot[..., : dh // 2], rot[..., dh // 2:]], dim=-1).reshape(B, L, heads, dh).reshape(rows, cols)
+    torch.testing.assert_close(buf.cpu().float()[:, :cols], want, **_tol(dtype))
+    torch.testing.assert_close(buf.cpu()[:, cols:], x[:, cols:])
+    if dtype == "fp32":
+        ops.rope_adjacent_(buf, rows=rows, L=L, ld=cols + 8, cols=cols, dh=dh, table=table, inverse=True)
+        torch.testing.assert_close(buf.cpu(), x, rtol=1e-5, atol=1e-5)
+
+
+def test_copy_rows_scatter_gather(ops):
+    B, Q, L, H = 3, 4, 10, 16
+    img = _rand(B * Q, H, seed=17)
+    fused = torch.zeros(B * L, H, device=DEV)
+    ops.copy_rows(img.to(DEV), fused, rows=B * Q, cols=H, out_remap=(Q, L, 0))
+    assert torch.equal(fused.cpu().view(B, L, H)[:, :Q].reshape(B * Q, H), img)
+    back = torch.empty(B * (L - Q), H, dtype=torch.bfloat16, device=DEV)
+    ops.copy_rows(fused, back, rows=B * (L - Q), cols=H, in_remap=(L - Q, L, Q))
+    assert torch.count_nonzero(back) == 0
+    back2 = torch.empty(B * Q, H, device=DEV)
+    ops.copy_rows(fused, back2, rows=B * Q, cols=H, in_remap=(Q, L, 0))
+    assert torch.equal(back2.cpu(), img)
+
+
+def test_masked_mean_bwd(ops):
+    B, P, D = 5, 16, 8
+    lens = [0, 16, 1, 7, 3]
+    x = _rand(B, P, D, seed=18).requires_grad_(True)
+    valid = (torch.arange(P)[None, :] < torch.tensor(lens)[:, None]).float()[:, :, None]
+    out = (x * valid).sum(1) / torch.tensor(lens).clamp(min=1)[:, None]
+    d = _rand(B, D, seed=19)
+    out.backward(d)
+    dx = torch.empty(B, P, D, device=DEV)
+    ops.masked_mean_bwd(d.to(DEV), torch.tensor(lens, dtype=torch.int32, device=DEV), dx, B=B, P=P, D=D)
+    torch.testing.assert_close(dx.cpu(), x.grad)
+
+
+@pytest.mark.parametrize("T_in,T_out", [(6, 12), (15, 25), (15, 15)])
+def test_nlinear_bwd(ops, T_in, T_out):
+    B, C = 9, 64
+    x = _rand(B, T_in, C, seed=20).requires_grad_(True)
+    w = _rand(T_out, T_in, C, seed=21, scale=0.3).requires_grad_(True)          # [t][s][c]
+    last = x[:, -1:, :]
+    out = torch.einsum("tsc,bsc->btc", w, x - last) + last
+    g = _rand(B, T_out, C, seed=22)
+    out.backward(g)
+    din = torch.empty(B, T_in, C, device=DEV)
+    dw = torch.zeros(T_out, T_in, C, device=DEV)
+    ops.nlinear_bwd(g.to(DEV), B=B, C=C, T_in=T_in, T_out=T_out, x_in=x.detach().to(DEV), w=w.detach().to(DEV), din=din, dw=dw)
+    torch.testing.assert_close(din.cpu(), x.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(dw.cpu(), w.grad, rtol=1e-4, atol=1e-5)
+    # forward kernel agrees with the same formula (no lane adjust, zero bias)
+    dec = torch.empty(B, T_out, C, device=DEV)
+    ops.nlinear_decode(x.detach().to(DEV), w.detach().to(DEV), torch.zeros(T_out, C, device=DEV), None, dec, B=B, C=C, T_in=T_in, T_out=T_out)
+    torch.testing.assert_close(dec.cpu(), out.detach(), rtol=1e-4, atol=1e-5)
+
+
+def test_head_assemble_and_loss_bwd(ops):
+    B, T_in, T_out = 7, 6, 12
+    o = _rand(B, T_out, 2, seed=23).requires_grad_(True)
+    x, y = torch.rand(B, 2, T_in), torch.rand(B, 2, T_out)
+    ns = [(10.0 * b, 10.0 * b + 100.0 + b, 700.0, 705.0 + 9 * b) for b in range(B)]
+    dec = o.permute(0, 2, 1) + x[:, :, -1:]
+    loss = R.mse_loss(dec, y, ns)
+    loss.backward(torch.tensor(0.5))
+    decoded = torch.empty(B, 2, T_out, device=DEV)
+    ops.head_assemble(o.detach().reshape(B * T_out, 2).to(DEV), x.to(DEV), decoded, B=B, T_in=T_in, T_out=T_out)
+    torch.testing.assert_close(decoded.cpu(), dec.detach())
+    d_o = torch.empty(B * T_out, 2, device=DEV)
+    ops.traj_loss_bwd(decoded, y.to(DEV), torch.tensor(ns, device=DEV), d_o, B=B, T_out=T_out, gscale=torch.tensor([0.5], device=DEV))
+    # the oracle de-normalises both operands before subtracting (fp32 cancellation near min_y ~ 700); the kernel uses (dec - y) * range^2
+    torch.testing.assert_close(d_o.cpu().view(B, T_out, 2), o.grad, rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("J", [4, 16, 32])
+def test_skinny_dw(ops, dtype, J):
+    td = _td(dtype)
+    M, N, ld = 1000, 300, 312
+    Y = _rand(M, ld, seed=24).to(td)
+    Z = _rand(M, J + 8, seed=25).to(td)
+    rs = torch.rand(M) + 0.5
+    out = torch.zeros(N, J, device=DEV)
+    ops.skinny_dw(Y.to(DEV), Z.to(DEV), out, M=M, N=N, J=J, ldy=ld, ldz=J + 8, row_scale=rs.to(DEV))
+    want = (Y[:, :N].float() * rs[:, None]).t() @ Z[:, :J].float()
+    torch.testing.assert_close(out.cpu(), want, rtol=1e-3, atol=1e-3)
+
+
+ATTN_CASES = [  # B, H, Hkv, Tq, Tk, dh, causal, masked
+    (3, 4, 2, 24, 24, 32, True, True),     # LLM-like: causal + padding + GQA
+    (2, 12, 12, 144, 144, 64, True, True),
+    (2, 2, 2, 25, 40, 384, False, False),  # LTSF cross-attention: wide heads, no mask
+    (4, 4, 4, 64, 64, 16, False, True),    # lane polygon encoder
+    (3, 8, 8, 16, 15, 96, False, False),   # Q-Former cross-attention
+    (2, 2, 2, 15, 15, 32, False, False),   # temporal self-attention
+]
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("B,H,Hkv,Tq,Tk,dh,causal,masked", ATTN_CASES)
+def test_attention_bwd(ops, dtype, B, H, Hkv, Tq, Tk, dh, causal, masked):
+    td = _td(dtype)
+    q = _rand(B, Tq, H, dh, seed=26).to(td).float().requires_grad_(True)
+    k = _rand(B, Tk, Hkv, dh, seed=27).to(td).float().requires_grad_(True)
+    v = _rand(B, Tk, Hkv, dh, seed=28).to(td).float().requires_grad_(True)
+    valid = torch.ones(B, Tk, dtype=torch.bool)
+    if masked:
+        for b in range(B):
+            valid[b, Tk - 1 - 2 * b:] = False
+    scale = dh ** -0.5
+    kk = k.repeat_interleave(H // Hkv, dim=2)
+    vv = v.repeat_interleave(H // Hkv, dim=2)
+    s = torch.einsum("bihd,bjhd->bhij", q, kk) * scale
+    allow = valid[:, None, None, :].expand(B, H, Tq, Tk)
+    if causal:
+        allow = allow & torch.tril(torch.ones(Tq, Tk, dtype=torch.bool))[None, None]
+    s = s.masked_fill(~allow, float("-inf"))
+    o = torch.einsum("bhij,bjhd->bihd", torch.softmax(s, dim=-1), vv)
+    do = _rand(B, Tq, H, dh, seed=29).to(td)
+    o.backward(do.float())
+    qd, kd, vd, dod = (t.detach().to(td).to(DEV).contiguous() for t in (q, k, v, do))
+    dq = torch.empty_like(qd)
+    dk = torch.zeros(B, Tk, Hkv, dh, device=DEV)
+    dv = torch.zeros(B, Tk, Hkv, dh, device=DEV)
+    km = valid.to(torch.int32).to(DEV) if masked else None
+    ops.attention_bwd(qd, kd, vd, dod, dq, dk, dv, B=B, H=H, Hkv=Hkv, Tq=Tq, Tk=Tk, dh=dh, q_strides=(Tq * H * dh, H * dh),
+                      k_strides=(Tk * Hkv * dh, Hkv * dh), v_strides=(Tk * Hkv * dh, Hkv * dh), do_strides=(Tq * H * dh, H * dh),
+                      dq_strides=(Tq * H * dh, H * dh), dk_strides=(Tk * Hkv * dh, Hkv * dh), dv_strides=(Tk * Hkv * dh, Hkv * dh),
+                      scale=scale, causal=causal, key_mask=km)
+    tol = dict(rtol=1e-3, atol=1e-4) if dtype == "fp32" else dict(rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(dq.cpu().float(), q.grad, **tol)
+    torch.testing.assert_close(dk.cpu(), k.grad, rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(dv.cpu(), v.grad, rtol=1e-3, atol=1e-4)
+
+
+def test_adamw_matches_torch(ops):
+    n = 10_001
+    p0, g = _rand(n, seed=30), _rand(n, seed=31)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref], lr=5e-4, weight_decay=1e-4)
+    p, m, v = p0.clone().to(DEV), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    for step in range(1, 4):
+        gs = g * step
+        ref.grad = gs.clone()
+        opt.step()
+        ops.adamw_(p, (gs * 2.0).to(DEV), m, v, lr=5e-4, weight_decay=1e-4, step=step, grad_scale=0.5)
+    torch.testing.assert_close(p.cpu(), ref.detach(), rtol=1e-5, atol=1e-6)

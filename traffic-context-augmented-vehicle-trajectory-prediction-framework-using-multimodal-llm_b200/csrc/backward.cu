@@ -1,0 +1,740 @@
+// Backward-pass kernels of the fine-tune step (reference scripts/im_kim_train_GRN.py:1039-1040: loss.backward() +
+// AdamW).  The reference leaves all of this to torch autograd; here every gradient is a hand-written kernel behind
+// the C ABI.  Dense gradient contractions reuse tcavp_gemm on explicitly transposed operands (tcavp_transpose);
+// this file holds the rest: transposes, reductions over rows, the norm / activation / attention / NLinear / head
+// backward kernels, the skinny (rank-r) weight-gradient kernel used for LoRA, and the fused AdamW update.
+// All arithmetic is fp32; bf16 is a storage type only.
+#include "common.cuh"
+
+namespace tcavp {
+
+static int grid_cap(long long blocks, int per_sm) {
+  const long long cap = (long long)sm_count() * per_sm;
+  return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+// ------------------------------------------------------------------------------------------------
+// transpose: out[b][c][r] = in[b][r][c]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) transpose_kernel(const void* __restrict__ in, long long in_bs, int ldi, int in_dtype,
+                                                        void* __restrict__ out, long long out_bs, int ldo, int out_dtype, int rows,
+                                                        int cols) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < rows && c < cols) ? load_as_f(in, (size_t)b * in_bs + (size_t)r * ldi + c, in_dtype) : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (c < cols && r < rows) store_from_f(out, (size_t)b * out_bs + (size_t)c * ldo + r, out_dtype, tile[tx][i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// period_sum: out[r % period][c] += x[r][c]   (period 1 = bias gradient; period P = positional-table gradient)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) period_sum_kernel(const void* __restrict__ x, int ldx, int dtype, long long rows, int cols,
+                                                         int period, float* __restrict__ out, long long k_per_split) {
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  const int p = blockIdx.y;
+  if (c >= cols) return;
+  const long long K = (rows - p + period - 1) / period;   // rows r = p + period * k, k < K
+  const long long k0 = (long long)blockIdx.z * k_per_split;
+  long long k1 = k0 + k_per_split;
+  if (k1 > K) k1 = K;
+  float acc = 0.f;
+  for (long long k = k0; k < k1; ++k) acc += load_as_f(x, (size_t)(p + period * k) * ldx + c, dtype);
+  if (k1 > k0) atomicAdd(out + (size_t)p * cols + c, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// elementwise: relu backward, axpby, SwiGLU forward / backward
+// ------------------------------------------------------------------------------------------------
+__global__ void relu_bwd_kernel(const void* __restrict__ dy, int lddy, const void* __restrict__ y, int ldy, void* __restrict__ dx, int lddx,
+                                int dtype, long long rows, int cols) {
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i % cols);
+    const float g = load_as_f(dy, (size_t)r * lddy + c, dtype);
+    store_from_f(dx, (size_t)r * lddx + c, dtype, load_as_f(y, (size_t)r * ldy + c, dtype) > 0.f ? g : 0.f);
+  }
+}
+
+__global__ void axpby_kernel(const void* __restrict__ a, int lda, int a_dtype, float alpha, const void* __restrict__ b, int ldb, int b_dtype,
+                             float beta, void* __restrict__ out, int ldo, int out_dtype, long long rows, int cols) {
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i % cols);
+    float v = alpha * load_as_f(a, (size_t)r * lda + c, a_dtype);
+    if (b) v += beta * load_as_f(b, (size_t)r * ldb + c, b_dtype);
+    store_from_f(out, (size_t)r * ldo + c, out_dtype, v);
+  }
+}
+
+// gu rows are interleaved (g0,u0,g1,u1,...): out[r][j] = silu(g_j) * u_j   (HF:190)
+__global__ void swiglu_kernel(const void* __restrict__ gu, void* __restrict__ out, int dtype, long long rows, int I) {
+  const long long total = rows * I;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const float g = load_as_f(gu, 2 * (size_t)i, dtype), u = load_as_f(gu, 2 * (size_t)i + 1, dtype);
+    store_from_f(out, (size_t)i, dtype, g / (1.f + __expf(-g)) * u);
+  }
+}
+__global__ void swiglu_bwd_kernel(const void* __restrict__ dout, const void* __restrict__ gu, void* __restrict__ dgu, int dtype, long long rows,
+                                  int I) {
+  const long long total = rows * I;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const float g = load_as_f(gu, 2 * (size_t)i, dtype), u = load_as_f(gu, 2 * (size_t)i + 1, dtype);
+    const float d = load_as_f(dout, (size_t)i, dtype);
+    const float sg = 1.f / (1.f + __expf(-g));
+    store_from_f(dgu, 2 * (size_t)i, dtype, d * u * sg * (1.f + g * (1.f - sg)));
+    store_from_f(dgu, 2 * (size_t)i + 1, dtype, d * g * sg);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward (input was x + res): dx, dw += sum_r dy * xhat, db += sum_r dy.  Warp per row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const void* __restrict__ x,
+                                                            const void* __restrict__ res, int x_dtype, const float* __restrict__ w, int rows,
+                                                            int cols, float eps, void* __restrict__ dx, int dx_dtype, float* __restrict__ dw,
+                                                            float* __restrict__ db) {
+  extern __shared__ float sacc[];   // [2][cols]
+  float* s_dw = sacc;
+  float* s_db = sacc + cols;
+  for (int c = threadIdx.x; c < 2 * cols; c += blockDim.x) sacc[c] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    const size_t base = (size_t)row * cols;
+    float s = 0.f;
+    for (int c = lane; c < cols; c += 32) s += load_as_f(x, base + c, x_dtype) + (res ? load_as_f(res, base + c, x_dtype) : 0.f);
+    const float mean = warp_sum(s) / cols;
+    float q = 0.f;
+    for (int c = lane; c < cols; c += 32) {
+      const float v = load_as_f(x, base + c, x_dtype) + (res ? load_as_f(res, base + c, x_dtype) : 0.f) - mean;
+      q += v * v;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / cols + eps);
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < cols; c += 32) {
+      const float xh = (load_as_f(x, base + c, x_dtype) + (res ? load_as_f(res, base + c, x_dtype) : 0.f) - mean) * rstd;
+      const float d = load_as_f(dy, base + c, dy_dtype);
+      const float g = d * __ldg(w + c);
+      s1 += g;
+      s2 += g * xh;
+      if (dw) {
+        atomicAdd(s_dw + c, d * xh);
+        atomicAdd(s_db + c, d);
+      }
+    }
+    s1 = warp_sum(s1) / cols;
+    s2 = warp_sum(s2) / cols;
+    if (dx) {
+      for (int c = lane; c < cols; c += 32) {
+        const float xh = (load_as_f(x, base + c, x_dtype) + (res ? load_as_f(res, base + c, x_dtype) : 0.f) - mean) * rstd;
+        const float g = load_as_f(dy, base + c, dy_dtype) * __ldg(w + c);
+        store_from_f(dx, base + c, dx_dtype, rstd * (g - s1 - xh * s2));
+      }
+    }
+  }
+  __syncthreads();
+  if (dw) {
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+      atomicAdd(dw + c, s_dw[c]);
+      atomicAdd(db + c, s_db[c]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// RMSNorm backward.  y = w * (x * rstd)  (w == nullptr: unit weight, the folded-weight form used by the LLM stack):
+//   g = dy * w;  dx = rstd * (g - xhat * mean(g * xhat)) + add,   xhat = x * rstd
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const void* __restrict__ dy, int lddy, const void* __restrict__ x, int ldx,
+                                                          const float* __restrict__ w, const void* __restrict__ add, int ldadd,
+                                                          void* __restrict__ dx, int lddx, int dtype, int rows, int cols, float eps) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    float ss = 0.f;
+    for (int c = lane; c < cols; c += 32) {
+      const float v = load_as_f(x, (size_t)row * ldx + c, dtype);
+      ss += v * v;
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / cols + eps);
+    float dot = 0.f;
+    for (int c = lane; c < cols; c += 32) {
+      const float g = load_as_f(dy, (size_t)row * lddy + c, dtype) * (w ? __ldg(w + c) : 1.f);
+      dot += g * load_as_f(x, (size_t)row * ldx + c, dtype) * rstd;
+    }
+    dot = warp_sum(dot) / cols;
+    for (int c = lane; c < cols; c += 32) {
+      const float g = load_as_f(dy, (size_t)row * lddy + c, dtype) * (w ? __ldg(w + c) : 1.f);
+      const float xh = load_as_f(x, (size_t)row * ldx + c, dtype) * rstd;
+      float v = rstd * (g - xh * dot);
+      if (add) v += load_as_f(add, (size_t)row * ldadd + c, dtype);
+      store_from_f(dx, (size_t)row * lddx + c, dtype, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rotary embedding on ADJACENT column pairs (the layout tcavp_gemm's fused RoPE produces), forward or inverse.
+// Table layout 1: [dh/4][L] x float4 = (cos, sin) of pairs (2k, 2k+1).
+// ------------------------------------------------------------------------------------------------
+__global__ void rope_adjacent_kernel(void* __restrict__ buf, int dtype, long long rows, int L, int ld, int cols, int dh,
+                                     const float* __restrict__ table, int inverse) {
+  const int quads = cols >> 2;
+  const long long total = rows * quads;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / quads;
+    const int c = (int)(i % quads) * 4;
+    const int pos = (int)(r % L);
+    const float4 t = __ldg(reinterpret_cast<const float4*>(table) + (size_t)((c % dh) >> 2) * L + pos);
+    const float sg = inverse ? -1.f : 1.f;
+    const size_t o = (size_t)r * ld + c;
+    const float a0 = load_as_f(buf, o, dtype), a1 = load_as_f(buf, o + 1, dtype), a2 = load_as_f(buf, o + 2, dtype),
+                a3 = load_as_f(buf, o + 3, dtype);
+    store_from_f(buf, o, dtype, a0 * t.x - sg * a1 * t.y);
+    store_from_f(buf, o + 1, dtype, a1 * t.x + sg * a0 * t.y);
+    store_from_f(buf, o + 2, dtype, a2 * t.z - sg * a3 * t.w);
+    store_from_f(buf, o + 3, dtype, a3 * t.z + sg * a2 * t.w);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// copy_rows: out[remap_out(r), :] = in[remap_in(r), :]  with dtype conversion (scatter into / gather from the fused
+// (B, L, H) sequence buffer; reference scripts/train.py:528 torch.cat and its backward split)
+// ------------------------------------------------------------------------------------------------
+__global__ void copy_rows_kernel(const void* __restrict__ in, int ldi, int in_dtype, int igi, int igo, int ioff, void* __restrict__ out, int ldo,
+                                 int out_dtype, int ogi, int ogo, int ooff, long long rows, int cols) {
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    const size_t ri = (size_t)remap_row(igi, igo, ioff, r), ro = (size_t)remap_row(ogi, ogo, ooff, r);
+    store_from_f(out, ro * ldo + c, out_dtype, load_as_f(in, ri * ldi + c, in_dtype));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// masked mean backward (reference scripts/train.py:373-382): dx[b,p,:] = p < len[b] ? dout[b,:] / len[b] : 0
+// ------------------------------------------------------------------------------------------------
+__global__ void masked_mean_bwd_kernel(const void* __restrict__ dout, int dout_dtype, const int32_t* __restrict__ len, void* __restrict__ dx,
+                                       int dx_dtype, int B, int P, int D) {
+  const long long total = (long long)B * P * D;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(i % D);
+    const long long bp = i / D;
+    const int p = (int)(bp % P), b = (int)(bp / P);
+    int n = __ldg(len + b);
+    n = n < 0 ? 0 : (n > P ? P : n);
+    store_from_f(dx, (size_t)i, dx_dtype, p < n ? load_as_f(dout, (size_t)b * D + d, dout_dtype) / (float)n : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// NLinear backward (reference scripts/train.py:701-716 / 769-785):
+//   out[b,t,c] = sum_s W[t][s][c] * (in[b,s,c] - in[b,T_in-1,c]) + bias[t][c] + in[b,T_in-1,c]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) nlinear_bwd_in_kernel(const void* __restrict__ g, int g_dtype, const float* __restrict__ w,
+                                                             void* __restrict__ din, int din_dtype, int B, int C, int T_in, int T_out) {
+  const long long total = (long long)B * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long b = i / C;
+    float sum_g = 0.f, sum_du = 0.f, du_last = 0.f;
+    for (int t = 0; t < T_out; ++t) sum_g += load_as_f(g, ((size_t)b * T_out + t) * C + c, g_dtype);
+    for (int s = 0; s < T_in; ++s) {
+      float du = 0.f;
+      for (int t = 0; t < T_out; ++t)
+        du = fmaf(load_as_f(g, ((size_t)b * T_out + t) * C + c, g_dtype), __ldg(w + ((size_t)t * T_in + s) * C + c), du);
+      sum_du += du;
+      if (s < T_in - 1) store_from_f(din, ((size_t)b * T_in + s) * C + c, din_dtype, du);
+      else du_last = du;
+    }
+    store_from_f(din, ((size_t)b * T_in + T_in - 1) * C + c, din_dtype, du_last + sum_g - sum_du);
+  }
+}
+
+// dW[t][s][c] += sum_b g[b,t,c] * (in[b,s,c] - in[b,T_in-1,c]);  grid (T_out*T_in, splits), block = (256/C) b-lanes x C
+__global__ void __launch_bounds__(256) nlinear_bwd_w_kernel(const void* __restrict__ g, int g_dtype, const void* __restrict__ in, int in_dtype,
+                                                            float* __restrict__ dw, int B, int C, int T_in, int T_out, int b_per_split) {
+  const int t = blockIdx.x / T_in, s = blockIdx.x % T_in;
+  const int c = threadIdx.x % C, bl = threadIdx.x / C, nb = blockDim.x / C;
+  if (bl >= nb) return;
+  const int b0 = blockIdx.y * b_per_split;
+  int b1 = b0 + b_per_split;
+  if (b1 > B) b1 = B;
+  float acc = 0.f;
+  for (int b = b0 + bl; b < b1; b += nb) {
+    const float u = load_as_f(in, ((size_t)b * T_in + s) * C + c, in_dtype) - load_as_f(in, ((size_t)b * T_in + T_in - 1) * C + c, in_dtype);
+    acc = fmaf(load_as_f(g, ((size_t)b * T_out + t) * C + c, g_dtype), u, acc);
+  }
+  atomicAdd(dw + ((size_t)t * T_in + s) * C + c, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// head: decoded[b,f,t] = o[b,t,f] + x[b,f,T_in-1]  (reference scripts/train.py:941-943) and the loss gradient
+//   d_o[b,t,f] = gscale * 2 * (decoded - y) * range_f^2 / (B * T_out)       (reference scripts/train.py:945-962)
+// ------------------------------------------------------------------------------------------------
+__global__ void head_assemble_kernel(const float* __restrict__ o, const float* __restrict__ x, float* __restrict__ decoded, int B, int T_in,
+                                     int T_out) {
+  const long long total = (long long)B * 2 * T_out;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % T_out);
+    const long long bf = i / T_out;
+    const int f = (int)(bf % 2);
+    const long long b = bf / 2;
+    decoded[i] = o[((size_t)b * T_out + t) * 2 + f] + x[(size_t)bf * T_in + T_in - 1];
+  }
+}
+__global__ void traj_loss_bwd_kernel(const float* __restrict__ decoded, const float* __restrict__ y, const float* __restrict__ norm_stat,
+                                     const float* __restrict__ gscale, float* __restrict__ d_o, int B, int T_out) {
+  const long long total = (long long)B * 2 * T_out;
+  const float gs = gscale ? __ldg(gscale) : 1.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % T_out);
+    const long long bf = i / T_out;
+    const int f = (int)(bf % 2);
+    const long long b = bf / 2;
+    const float range = norm_stat[b * 4 + 2 * f + 1] - norm_stat[b * 4 + 2 * f];
+    d_o[((size_t)b * T_out + t) * 2 + f] = gs * 2.f * (decoded[i] - y[i]) * range * range / ((float)B * (float)T_out);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Skinny weight gradient (LoRA A / B): out[n][j] += sum_m scale[m] * Y[m][n] * Z[m][j],  J <= 32.
+// One thread per output column n (coalesced reads of Y), Z rows staged in shared memory, atomics at the end.
+// ------------------------------------------------------------------------------------------------
+template <int J>
+__global__ void __launch_bounds__(128) skinny_dw_kernel(const void* __restrict__ Y, int ldy, int y_dtype, const void* __restrict__ Z, int ldz,
+                                                        int z_dtype, const float* __restrict__ scale, float* __restrict__ out, int ldo,
+                                                        long long M, int N, int jn, int m_per_block) {
+  constexpr int MB = 32;
+  __shared__ float sz[MB][J];
+  const int n = blockIdx.x * 128 + threadIdx.x;
+  const long long m0 = (long long)blockIdx.y * m_per_block;
+  long long m1 = m0 + m_per_block;
+  if (m1 > M) m1 = M;
+  float acc[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) acc[j] = 0.f;
+  for (long long mb = m0; mb < m1; mb += MB) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < MB * J; e += 128) {
+      const int r = e / J, j = e % J;
+      const long long m = mb + r;
+      float v = 0.f;
+      if (m < m1 && j < jn) v = load_as_f(Z, (size_t)m * ldz + j, z_dtype) * (scale ? __ldg(scale + m) : 1.f);
+      sz[r][j] = v;
+    }
+    __syncthreads();
+    if (n < N) {
+      const int lim = (int)((m1 - mb) < MB ? (m1 - mb) : MB);
+      for (int r = 0; r < lim; ++r) {
+        const float y = load_as_f(Y, (size_t)(mb + r) * ldy + n, y_dtype);
+#pragma unroll
+        for (int j = 0; j < J; ++j) acc[j] = fmaf(y, sz[r][j], acc[j]);
+      }
+    }
+  }
+  if (n < N) {
+#pragma unroll
+    for (int j = 0; j < J; ++j)
+      if (j < jn) atomicAdd(out + (size_t)n * ldo + j, acc[j]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Attention backward.  One CTA per (batch, head, 16-query block); probabilities are recomputed (no saved
+// statistics), head_dim is streamed in chunks so any width works (LTSF cross-attention: dh = H/2).
+//   P = softmax(scale * Q K^T + mask);  dP = dO V^T;  D_i = sum_j P_ij dP_ij;  dS = scale * P o (dP - D)
+//   dQ = dS K (owned rows, plain stores);  dK += dS^T Q;  dV += P^T dO  (fp32 atomics: q-blocks and GQA groups share keys)
+// ------------------------------------------------------------------------------------------------
+namespace ab {
+constexpr int QB = 16;
+constexpr int THREADS = 256;
+constexpr int JJ = 3;          // keys per thread in the score phase: Tk <= JJ * THREADS
+
+template <typename T>
+__global__ void __launch_bounds__(THREADS) attn_bwd_kernel(tcavp_attn_args a, const T* __restrict__ dout, long long do_sb, long long do_st,
+                                                           T* __restrict__ dq, long long dq_sb, long long dq_st, float* __restrict__ dk,
+                                                           long long dk_sb, long long dk_st, float* __restrict__ dv, long long dv_sb,
+                                                           long long dv_st, int DC) {
+  extern __shared__ float sm[];
+  const int Tk = a.Tk, LD = DC + 1;
+  float* sP = sm;                       // [QB][Tk]   probabilities, later unchanged
+  float* sdS = sP + QB * Tk;            // [QB][Tk]   dP, then dS
+  float* sQ = sdS + QB * Tk;            // [QB][LD]
+  float* sdO = sQ + QB * LD;            // [QB][LD]
+  float* sK = sdO + QB * LD;            // [Tk][LD]
+  float* sV = sK + (size_t)Tk * LD;     // [Tk][LD]
+  const int nqb = (a.Tq + QB - 1) / QB;
+  const int qb = blockIdx.x % nqb;
+  const int bh = blockIdx.x / nqb;
+  const int b = bh / a.H, h = bh % a.H, hk = h / (a.H / a.Hkv);
+  const int q0 = qb * QB;
+  const int tid = threadIdx.x;
+  const T* gq = reinterpret_cast<const T*>(a.q) + (size_t)b * a.q_sb + (size_t)h * a.dh;
+  const T* gk = reinterpret_cast<const T*>(a.k) + (size_t)b * a.k_sb + (size_t)hk * a.dh;
+  const T* gv = reinterpret_cast<const T*>(a.v) + (size_t)b * a.v_sb + (size_t)hk * a.dh;
+  const T* gdo = dout + (size_t)b * do_sb + (size_t)h * a.dh;
+
+  // ---- phase A: S = Q K^T and dP = dO V^T, accumulated over head-dim chunks ----
+  float accS[JJ][QB], accP[JJ][QB];
+#pragma unroll
+  for (int jj = 0; jj < JJ; ++jj)
+#pragma unroll
+    for (int i = 0; i < QB; ++i) accS[jj][i] = accP[jj][i] = 0.f;
+  for (int d0 = 0; d0 < a.dh; d0 += DC) {
+    const int dc = min(DC, a.dh - d0);
+    __syncthreads();
+    for (int e = tid; e < QB * DC; e += THREADS) {
+      const int i = e / DC, d = e % DC;
+      const bool ok = (q0 + i < a.Tq) && d < dc;
+      sQ[i * LD + d] = ok ? Cvt<T>::to_f(gq[(size_t)(q0 + i) * a.q_st + d0 + d]) : 0.f;
+      sdO[i * LD + d] = ok ? Cvt<T>::to_f(gdo[(size_t)(q0 + i) * do_st + d0 + d]) : 0.f;
+    }
+    for (int e = tid; e < Tk * DC; e += THREADS) {
+      const int j = e / DC, d = e % DC;
+      const bool ok = d < dc;
+      sK[j * LD + d] = ok ? Cvt<T>::to_f(gk[(size_t)j * a.k_st + d0 + d]) : 0.f;
+      sV[j * LD + d] = ok ? Cvt<T>::to_f(gv[(size_t)j * a.v_st + d0 + d]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int jj = 0; jj < JJ; ++jj) {
+      const int j = tid + jj * THREADS;
+      if (j < Tk) {
+        for (int d = 0; d < dc; ++d) {
+          const float kv = sK[j * LD + d], vv = sV[j * LD + d];
+#pragma unroll
+          for (int i = 0; i < QB; ++i) {
+            accS[jj][i] = fmaf(sQ[i * LD + d], kv, accS[jj][i]);
+            accP[jj][i] = fmaf(sdO[i * LD + d], vv, accP[jj][i]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int jj = 0; jj < JJ; ++jj) {
+    const int j = tid + jj * THREADS;
+    if (j < Tk) {
+      const bool okj = !a.key_mask || a.key_mask[(size_t)b * Tk + j] != 0;
+#pragma unroll
+      for (int i = 0; i < QB; ++i) {
+        const bool ok = okj && (q0 + i < a.Tq) && (!a.causal || j <= q0 + i);
+        sP[i * Tk + j] = ok ? accS[jj][i] * a.scale : -INFINITY;
+        sdS[i * Tk + j] = accP[jj][i];
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase B: softmax rows and dS (warp per row) ----
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int i = warp; i < QB; i += THREADS / 32) {
+      float mx = -INFINITY;
+      for (int j = lane; j < Tk; j += 32) mx = fmaxf(mx, sP[i * Tk + j]);
+      mx = warp_max(mx);
+      float l = 0.f;
+      for (int j = lane; j < Tk; j += 32) {
+        const float p = mx == -INFINITY ? 0.f : __expf(sP[i * Tk + j] - mx);
+        sP[i * Tk + j] = p;
+        l += p;
+      }
+      l = warp_sum(l);
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      float dsum = 0.f;
+      for (int j = lane; j < Tk; j += 32) {
+        const float p = sP[i * Tk + j] * inv;
+        sP[i * Tk + j] = p;
+        dsum += p * sdS[i * Tk + j];
+      }
+      dsum = warp_sum(dsum);
+      for (int j = lane; j < Tk; j += 32) sdS[i * Tk + j] = a.scale * sP[i * Tk + j] * (sdS[i * Tk + j] - dsum);
+    }
+  }
+  // ---- phase C: dQ, dK, dV per head-dim chunk ----
+  T* gdq = dq + (size_t)b * dq_sb + (size_t)h * a.dh;
+  float* gdk = dk + (size_t)b * dk_sb + (size_t)hk * a.dh;
+  float* gdv = dv + (size_t)b * dv_sb + (size_t)hk * a.dh;
+  for (int d0 = 0; d0 < a.dh; d0 += DC) {
+    const int dc = min(DC, a.dh - d0);
+    __syncthreads();
+    for (int e = tid; e < QB * DC; e += THREADS) {
+      const int i = e / DC, d = e % DC;
+      const bool ok = (q0 + i < a.Tq) && d < dc;
+      sQ[i * LD + d] = ok ? Cvt<T>::to_f(gq[(size_t)(q0 + i) * a.q_st + d0 + d]) : 0.f;
+      sdO[i * LD + d] = ok ? Cvt<T>::to_f(gdo[(size_t)(q0 + i) * do_st + d0 + d]) : 0.f;
+    }
+    for (int e = tid; e < Tk * DC; e += THREADS) {
+      const int j = e / DC, d = e % DC;
+      sK[j * LD + d] = d < dc ? Cvt<T>::to_f(gk[(size_t)j * a.k_st + d0 + d]) : 0.f;
+    }
+    __syncthreads();
+    for (int e = tid; e < QB * DC; e += THREADS) {     // dQ[i][d] = sum_j dS[i][j] K[j][d]
+      const int i = e / DC, d = e % DC;
+      if (q0 + i < a.Tq && d < dc) {
+        float acc = 0.f;
+        for (int j = 0; j < Tk; ++j) acc = fmaf(sdS[i * Tk + j], sK[j * LD + d], acc);
+        gdq[(size_t)(q0 + i) * dq_st + d0 + d] = Cvt<T>::from_f(acc);
+      }
+    }
+    for (int e = tid; e < Tk * DC; e += THREADS) {     // dK[j][d] += sum_i dS[i][j] Q[i][d];  dV[j][d] += sum_i P[i][j] dO[i][d]
+      const int j = e / DC, d = e % DC;
+      if (d < dc) {
+        float ak = 0.f, av = 0.f;
+#pragma unroll
+        for (int i = 0; i < QB; ++i) {
+          ak = fmaf(sdS[i * Tk + j], sQ[i * LD + d], ak);
+          av = fmaf(sP[i * Tk + j], sdO[i * LD + d], av);
+        }
+        atomicAdd(gdk + (size_t)j * dk_st + d0 + d, ak);
+        atomicAdd(gdv + (size_t)j * dv_st + d0 + d, av);
+      }
+    }
+  }
+}
+}  // namespace ab
+
+// ------------------------------------------------------------------------------------------------
+// AdamW (torch.optim.AdamW semantics, reference scripts/im_kim_train_GRN.py:1008): decoupled weight decay,
+// bias-corrected moments.  One flat fp32 buffer per state.
+// ------------------------------------------------------------------------------------------------
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+                             float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    float pi = p[i] * (1.f - lr * wd);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi -= (lr / bc1) * (mi / denom);
+    p[i] = pi;
+  }
+}
+
+}  // namespace tcavp
+
+using namespace tcavp;
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+#define DT_OK(d) ((d) == TCAVP_F32 || (d) == TCAVP_BF16)
+
+extern "C" int tcavp_transpose(const void* in, long long in_bstride, int ldi, int in_dtype, void* out, long long out_bstride, int ldo,
+                               int out_dtype, int batch, int rows, int cols, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(batch >= 0 && rows >= 0 && cols >= 0 && batch <= 65535, "tcavp_transpose: bad shape");
+  if (batch == 0 || rows == 0 || cols == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(in && out && DT_OK(in_dtype) && DT_OK(out_dtype) && ldi >= cols && ldo >= rows, "tcavp_transpose: bad pointer/dtype/ld");
+  TCAVP_REQUIRE((cols + 31) / 32 <= 65535, "tcavp_transpose: too many columns");
+  dim3 grid((rows + 31) / 32, (cols + 31) / 32, batch);
+  transpose_kernel<<<grid, 256, 0, STREAM(stream)>>>(in, in_bstride, ldi, in_dtype, out, out_bstride, ldo, out_dtype, rows, cols);
+  return check_launch("transpose_kernel");
+}
+
+extern "C" int tcavp_period_sum(const void* x, int ldx, int dtype, long long rows, int cols, int period, float* out, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(rows >= 0 && cols > 0 && period > 0 && period <= 65535, "tcavp_period_sum: bad shape");
+  if (rows == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(x && out && DT_OK(dtype) && ldx >= cols, "tcavp_period_sum: bad pointer/dtype");
+  const long long K = (rows + period - 1) / period;
+  const int cblocks = (cols + 127) / 128;
+  long long want = ((long long)sm_count() * 8) / ((long long)cblocks * period);
+  if (want < 1) want = 1;
+  if (want > K) want = K;
+  if (want > 4096) want = 4096;
+  const long long kper = (K + want - 1) / want;
+  dim3 grid(cblocks, period, (unsigned)((K + kper - 1) / kper));
+  period_sum_kernel<<<grid, 128, 0, STREAM(stream)>>>(x, ldx, dtype, rows, cols, period, out, kper);
+  return check_launch("period_sum_kernel");
+}
+
+extern "C" int tcavp_relu_bwd(const void* dy, int lddy, const void* y, int ldy, void* dx, int lddx, int dtype, long long rows, int cols,
+                              tcavp_stream_t stream) {
+  TCAVP_REQUIRE(rows >= 0 && cols > 0, "tcavp_relu_bwd: bad shape");
+  if (rows == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(dy && y && dx && DT_OK(dtype), "tcavp_relu_bwd: bad pointer/dtype");
+  relu_bwd_kernel<<<grid_cap((rows * cols + 255) / 256, 16), 256, 0, STREAM(stream)>>>(dy, lddy, y, ldy, dx, lddx, dtype, rows, cols);
+  return check_launch("relu_bwd_kernel");
+}
+
+extern "C" int tcavp_axpby(const void* a, int lda, int a_dtype, float alpha, const void* b, int ldb, int b_dtype, float beta, void* out,
+                           int ldo, int out_dtype, long long rows, int cols, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(rows >= 0 && cols > 0, "tcavp_axpby: bad shape");
+  if (rows == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(a && out && DT_OK(a_dtype) && DT_OK(out_dtype) && (!b || DT_OK(b_dtype)), "tcavp_axpby: bad pointer/dtype");
+  axpby_kernel<<<grid_cap((rows * cols + 255) / 256, 16), 256, 0, STREAM(stream)>>>(a, lda, a_dtype, alpha, b, ldb, b_dtype, beta, out, ldo,
+                                                                                  out_dtype, rows, cols);
+  return check_launch("axpby_kernel");
+}
+
+extern "C" int tcavp_swiglu(const void* gu, void* out, int dtype, long long rows, int I, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(rows >= 0 && I > 0, "tcavp_swiglu: bad shape");
+  if (rows == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(gu && out && DT_OK(dtype), "tcavp_swiglu: bad pointer/dtype");
+  swiglu_kernel<<<grid_cap((rows * I + 255) / 256, 16), 256, 0, STREAM(stream)>>>(gu, out, dtype, rows, I);
+  return check_launch("swiglu_kernel");
+}
+
+extern "C" int tcavp_swiglu_bwd(const void* dout, const void* gu, void* dgu, int dtype, long long rows, int I, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(rows >= 0 && I > 0, "tcavp_swiglu_bwd: bad shape");
+  if (rows == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(dout && gu && dgu && DT_OK(dtype), "tcavp_swiglu_bwd: bad pointer/dtype");
+  swiglu_bwd_kernel<<<grid_cap((rows * I + 255) / 256, 16), 256, 0, STREAM(stream)>>>(dout, gu, dgu, dtype, rows, I);
+  return check_launch("swiglu_bwd_kernel");
+}
+
+extern "C" int tcavp_layernorm_bwd(const void* dy, int dy_dtype, const void* x, const void* residual, int x_dtype, const float* w, int rows,
+                                   int cols, float eps, void* dx, int dx_dtype, float* dw, float* db, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(rows >= 0 && cols > 0 && cols <= 8192, "tcavp_layernorm_bwd: bad shape");
+  if (rows == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(dy && x && w && DT_OK(dy_dtype) && DT_OK(x_dtype) && (!dx || DT_OK(dx_dtype)) && ((dw == nullptr) == (db == nullptr)),
+                "tcavp_layernorm_bwd: bad pointer/dtype");
+  const size_t smem = (size_t)2 * cols * sizeof(float);
+  TCAVP_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  layernorm_bwd_kernel<<<grid_cap((rows + 7) / 8, 4), 256, smem, STREAM(stream)>>>(dy, dy_dtype, x, residual, x_dtype, w, rows, cols, eps, dx,
+                                                                                 dx_dtype, dw, db);
+  return check_launch("layernorm_bwd_kernel");
+}
+
+extern "C" int tcavp_rmsnorm_bwd(const void* dy, int lddy, const void* x, int ldx, const float* w, const void* add, int ldadd, void* dx,
+                                 int lddx, int dtype, int rows, int cols, float eps, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(rows >= 0 && cols > 0, "tcavp_rmsnorm_bwd: bad shape");
+  if (rows == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(dy && x && dx && DT_OK(dtype), "tcavp_rmsnorm_bwd: bad pointer/dtype");
+  rmsnorm_bwd_kernel<<<grid_cap((rows + 7) / 8, 8), 256, 0, STREAM(stream)>>>(dy, lddy, x, ldx, w, add, ldadd, dx, lddx, dtype, rows, cols, eps);
+  return check_launch("rmsnorm_bwd_kernel");
+}
+
+extern "C" int tcavp_rope_adjacent(void* buf, int dtype, long long rows, int L, int ld, int cols, int dh, const float* table, int inverse,
+                                   tcavp_stream_t stream) {
+  TCAVP_REQUIRE(rows >= 0 && L > 0 && cols >= 0 && dh >= 4 && dh % 4 == 0 && cols % dh == 0 && ld >= cols, "tcavp_rope_adjacent: bad shape");
+  if (rows == 0 || cols == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(buf && table && DT_OK(dtype), "tcavp_rope_adjacent: bad pointer/dtype");
+  rope_adjacent_kernel<<<grid_cap((rows * (cols / 4) + 255) / 256, 16), 256, 0, STREAM(stream)>>>(buf, dtype, rows, L, ld, cols, dh, table, inverse);
+  return check_launch("rope_adjacent_kernel");
+}
+
+extern "C" int tcavp_copy_rows(const void* in, int ldi, int in_dtype, int in_gi, int in_go, int in_off, void* out, int ldo, int out_dtype,
+                               int out_gi, int out_go, int out_off, long long rows, int cols, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(rows >= 0 && cols > 0, "tcavp_copy_rows: bad shape");
+  if (rows == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(in && out && DT_OK(in_dtype) && DT_OK(out_dtype), "tcavp_copy_rows: bad pointer/dtype");
+  copy_rows_kernel<<<grid_cap((rows * cols + 255) / 256, 16), 256, 0, STREAM(stream)>>>(in, ldi, in_dtype, in_gi, in_go, in_off, out, ldo,
+                                                                                      out_dtype, out_gi, out_go, out_off, rows, cols);
+  return check_launch("copy_rows_kernel");
+}
+
+extern "C" int tcavp_masked_mean_bwd(const void* dout, int dout_dtype, const int32_t* len, void* dx, int dx_dtype, int B, int P, int D,
+                                     tcavp_stream_t stream) {
+  TCAVP_REQUIRE(B >= 0 && P > 0 && D > 0, "tcavp_masked_mean_bwd: bad shape");
+  if (B == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(dout && len && dx && DT_OK(dout_dtype) && DT_OK(dx_dtype), "tcavp_masked_mean_bwd: bad pointer/dtype");
+  masked_mean_bwd_kernel<<<grid_cap(((long long)B * P * D + 255) / 256, 16), 256, 0, STREAM(stream)>>>(dout, dout_dtype, len, dx, dx_dtype, B, P, D);
+  return check_launch("masked_mean_bwd_kernel");
+}
+
+extern "C" int tcavp_nlinear_bwd(const void* g, int g_dtype, const void* in, int in_dtype, const float* w, void* din, int din_dtype,
+                                 float* dw, int B, int C, int T_in, int T_out, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(B >= 0 && C > 0 && C <= 256 && T_in > 0 && T_out > 0, "tcavp_nlinear_bwd: bad shape");
+  if (B == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(g && DT_OK(g_dtype) && (!din || (w && DT_OK(din_dtype))) && (!dw || (in && DT_OK(in_dtype))), "tcavp_nlinear_bwd: bad pointer/dtype");
+  if (din) {
+    nlinear_bwd_in_kernel<<<grid_cap(((long long)B * C + 127) / 128, 16), 128, 0, STREAM(stream)>>>(g, g_dtype, w, din, din_dtype, B, C, T_in, T_out);
+    int rc = check_launch("nlinear_bwd_in_kernel");
+    if (rc) return rc;
+  }
+  if (dw) {
+    int splits = (sm_count() * 4) / (T_in * T_out);
+    if (splits < 1) splits = 1;
+    if (splits > B) splits = B;
+    const int bper = (B + splits - 1) / splits;
+    dim3 grid(T_out * T_in, (B + bper - 1) / bper);
+    nlinear_bwd_w_kernel<<<grid, (256 / C) * C, 0, STREAM(stream)>>>(g, g_dtype, in, in_dtype, dw, B, C, T_in, T_out, bper);
+    return check_launch("nlinear_bwd_w_kernel");
+  }
+  return TCAVP_OK;
+}
+
+extern "C" int tcavp_head_assemble(const float* o, const float* x, float* decoded, int B, int T_in, int T_out, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(B >= 0 && T_in > 0 && T_out > 0, "tcavp_head_assemble: bad shape");
+  if (B == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(o && x && decoded, "tcavp_head_assemble: null pointer");
+  head_assemble_kernel<<<grid_cap(((long long)B * 2 * T_out + 255) / 256, 16), 256, 0, STREAM(stream)>>>(o, x, decoded, B, T_in, T_out);
+  return check_launch("head_assemble_kernel");
+}
+
+extern "C" int tcavp_traj_loss_bwd(const float* decoded, const float* y, const float* norm_stat, const float* gscale, float* d_o, int B,
+                                   int T_out, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(B >= 0 && T_out > 0, "tcavp_traj_loss_bwd: bad shape");
+  if (B == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(decoded && y && norm_stat && d_o, "tcavp_traj_loss_bwd: null pointer");
+  traj_loss_bwd_kernel<<<grid_cap(((long long)B * 2 * T_out + 255) / 256, 16), 256, 0, STREAM(stream)>>>(decoded, y, norm_stat, gscale, d_o, B, T_out);
+  return check_launch("traj_loss_bwd_kernel");
+}
+
+extern "C" int tcavp_skinny_dw(const void* Y, int ldy, int y_dtype, const void* Z, int ldz, int z_dtype, const float* row_scale, float* out,
+                               int ldo, long long M, int N, int J, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(M >= 0 && N > 0 && J > 0 && J <= 32 && ldo >= J, "tcavp_skinny_dw: bad shape (J=%d, max 32)", J);
+  if (M == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(Y && Z && out && DT_OK(y_dtype) && DT_OK(z_dtype), "tcavp_skinny_dw: bad pointer/dtype");
+  const int nblocks = (N + 127) / 128;
+  long long splits = ((long long)sm_count() * 8) / nblocks;
+  if (splits < 1) splits = 1;
+  long long mper = (M + splits - 1) / splits;
+  mper = (mper + 31) / 32 * 32;
+  dim3 grid(nblocks, (unsigned)((M + mper - 1) / mper));
+  if (J <= 8) skinny_dw_kernel<8><<<grid, 128, 0, STREAM(stream)>>>(Y, ldy, y_dtype, Z, ldz, z_dtype, row_scale, out, ldo, M, N, J, (int)mper);
+  else if (J <= 16) skinny_dw_kernel<16><<<grid, 128, 0, STREAM(stream)>>>(Y, ldy, y_dtype, Z, ldz, z_dtype, row_scale, out, ldo, M, N, J, (int)mper);
+  else skinny_dw_kernel<32><<<grid, 128, 0, STREAM(stream)>>>(Y, ldy, y_dtype, Z, ldz, z_dtype, row_scale, out, ldo, M, N, J, (int)mper);
+  return check_launch("skinny_dw_kernel");
+}
+
+extern "C" int tcavp_attention_bwd(const tcavp_attn_args* a, const void* dout, long long do_sb, long long do_st, void* dq, long long dq_sb,
+                                   long long dq_st, float* dk, long long dk_sb, long long dk_st, float* dv, long long dv_sb, long long dv_st,
+                                   tcavp_stream_t stream) {
+  TCAVP_REQUIRE(a != nullptr, "tcavp_attention_bwd: null args");
+  TCAVP_REQUIRE(a->B >= 0 && a->H > 0 && a->Hkv > 0 && a->H % a->Hkv == 0 && a->Tq > 0 && a->Tk > 0 && a->dh > 0, "tcavp_attention_bwd: bad shape");
+  TCAVP_REQUIRE(a->Tk <= ab::JJ * ab::THREADS, "tcavp_attention_bwd: Tk %d > %d", a->Tk, ab::JJ * ab::THREADS);
+  TCAVP_REQUIRE(!a->causal || a->Tq == a->Tk, "tcavp_attention_bwd: causal needs Tq == Tk");
+  if (a->B == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(a->q && a->k && a->v && dout && dq && dk && dv && DT_OK(a->dtype), "tcavp_attention_bwd: bad pointer/dtype");
+  int DC = a->dh < 32 ? a->dh : 32;
+  auto smem_for = [&](int dc) { return (size_t)(2 * ab::QB * a->Tk + 2 * ab::QB * (dc + 1) + 2 * (size_t)a->Tk * (dc + 1)) * sizeof(float); };
+  if (smem_for(DC) > 200 * 1024) DC = 16 < a->dh ? 16 : a->dh;
+  const size_t smem = smem_for(DC);
+  TCAVP_REQUIRE(smem <= 220 * 1024, "tcavp_attention_bwd: Tk %d needs %zu bytes of shared memory", a->Tk, smem);
+  const int nqb = (a->Tq + ab::QB - 1) / ab::QB;
+  const long long blocks = (long long)a->B * a->H * nqb;
+  TCAVP_REQUIRE(blocks <= 0x7fffffffLL, "tcavp_attention_bwd: grid too large");
+  if (a->dtype == TCAVP_BF16) {
+    TCAVP_CUDA(cudaFuncSetAttribute(ab::attn_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ab::attn_bwd_kernel<__nv_bfloat16><<<(unsigned)blocks, ab::THREADS, smem, STREAM(stream)>>>(
+        *a, reinterpret_cast<const __nv_bfloat16*>(dout), do_sb, do_st, reinterpret_cast<__nv_bfloat16*>(dq), dq_sb, dq_st, dk, dk_sb, dk_st, dv,
+        dv_sb, dv_st, DC);
+  } else {
+    TCAVP_CUDA(cudaFuncSetAttribute(ab::attn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ab::attn_bwd_kernel<float><<<(unsigned)blocks, ab::THREADS, smem, STREAM(stream)>>>(
+        *a, reinterpret_cast<const float*>(dout), do_sb, do_st, reinterpret_cast<float*>(dq), dq_sb, dq_st, dk, dk_sb, dk_st, dv, dv_sb, dv_st, DC);
+  }
+  return check_launch("attn_bwd_kernel");
+}
+
+extern "C" int tcavp_adamw(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1, float beta2,
+                           float eps, float weight_decay, int step, float grad_scale, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(n >= 0 && step >= 1, "tcavp_adamw: bad n/step");
+  if (n == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(param && grad && exp_avg && exp_avg_sq, "tcavp_adamw: null pointer");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2 = sqrtf(1.f - powf(beta2, (float)step));
+  adamw_kernel<<<grid_cap((n + 255) / 256, 16), 256, 0, STREAM(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
+                                                                        bc1, bc2, grad_scale);
+  return check_launch("adamw_kernel");
+}

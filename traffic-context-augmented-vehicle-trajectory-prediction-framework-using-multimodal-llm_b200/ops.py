@@ -317,3 +317,151 @@ def device_info():
     sm, maj, mnr = c_int(), c_int(), c_int()
     _lib.check(_lib.load().tcavp_device_info(byref(sm), byref(maj), byref(mnr)), "tcavp_device_info")
     return sm.value, maj.value, mnr.value
+
+
+# --------------------------------------------------------------------------------------------------
+# fine-tune step: backward kernels (include/tcavp.h, "fine-tune step")
+# --------------------------------------------------------------------------------------------------
+from ctypes import c_longlong as _ll  # noqa: E402
+
+
+def _call(name, kernel, *args, flops=0.0, nbytes=0.0):
+    with _Timed(kernel, flops, nbytes):
+        _lib.check(getattr(_lib.load(), name)(*args, _stream()), name)
+
+
+def transpose(x, out, *, rows, cols, ldi=None, ldo=None, batch=1, in_bstride=0, out_bstride=0):
+    """out[b][c][r] = x[b][r][c]."""
+    _need_cuda(x, out)
+    _call("tcavp_transpose", "transpose_kernel", _p(x), _ll(in_bstride), cols if ldi is None else ldi, dt(x), _p(out), _ll(out_bstride),
+          rows if ldo is None else ldo, dt(out), batch, rows, cols, nbytes=float(batch * rows * cols * (x.element_size() + out.element_size())))
+    return out
+
+
+def period_sum(x, out, *, rows, cols, period=1, ldx=None):
+    """out[r % period][c] += x[r][c] (out fp32, accumulated)."""
+    _need_cuda(x, out)
+    if out.dtype != torch.float32:
+        raise TypeError("period_sum: out must be fp32")
+    _call("tcavp_period_sum", "period_sum_kernel", _p(x), cols if ldx is None else ldx, dt(x), _ll(rows), cols, period, _p(out))
+    return out
+
+
+def relu_bwd(dy, y, dx, *, rows, cols, lddy=None, ldy=None, lddx=None):
+    _need_cuda(dy, y, dx)
+    if not (dy.dtype == y.dtype == dx.dtype):
+        raise TypeError("relu_bwd: dtype mismatch")
+    _call("tcavp_relu_bwd", "relu_bwd_kernel", _p(dy), cols if lddy is None else lddy, _p(y), cols if ldy is None else ldy, _p(dx),
+          cols if lddx is None else lddx, dt(dy), _ll(rows), cols)
+    return dx
+
+
+def axpby(a, out, *, rows, cols, alpha=1.0, b=None, beta=1.0, lda=None, ldb=None, ldo=None):
+    _need_cuda(a, b, out)
+    _call("tcavp_axpby", "axpby_kernel", _p(a), cols if lda is None else lda, dt(a), c_float(alpha), _p(b), cols if ldb is None else ldb,
+          0 if b is None else dt(b), c_float(beta), _p(out), cols if ldo is None else ldo, dt(out), _ll(rows), cols)
+    return out
+
+
+def swiglu(gu, out, *, rows, I):
+    _need_cuda(gu, out)
+    _call("tcavp_swiglu", "swiglu_kernel", _p(gu), _p(out), dt(gu), _ll(rows), I)
+    return out
+
+
+def swiglu_bwd(dout, gu, dgu, *, rows, I):
+    _need_cuda(dout, gu, dgu)
+    _call("tcavp_swiglu_bwd", "swiglu_bwd_kernel", _p(dout), _p(gu), _p(dgu), dt(gu), _ll(rows), I)
+    return dgu
+
+
+def layernorm_bwd(dy, x, w, *, residual=None, eps=1e-5, dx=None, dw=None, db=None, rows=None, cols=None):
+    _need_cuda(dy, x, w, residual, dx, dw, db)
+    rows = x.numel() // x.shape[-1] if rows is None else rows
+    cols = x.shape[-1] if cols is None else cols
+    _call("tcavp_layernorm_bwd", "layernorm_bwd_kernel", _p(dy), dt(dy), _p(x), _p(residual), dt(x), _p(w), rows, cols, c_float(eps), _p(dx),
+          0 if dx is None else dt(dx), _p(dw), _p(db))
+    return dx
+
+
+def rmsnorm_bwd(dy, x, dx, *, rows, cols, eps, w=None, add=None, lddy=None, ldx=None, ldadd=None, lddx=None):
+    _need_cuda(dy, x, dx, w, add)
+    _call("tcavp_rmsnorm_bwd", "rmsnorm_bwd_kernel", _p(dy), cols if lddy is None else lddy, _p(x), cols if ldx is None else ldx, _p(w),
+          _p(add), cols if ldadd is None else ldadd, _p(dx), cols if lddx is None else lddx, dt(x), rows, cols, c_float(eps))
+    return dx
+
+
+def rope_adjacent_(buf, *, rows, L, ld, cols, dh, table, inverse=False):
+    _need_cuda(buf, table)
+    _call("tcavp_rope_adjacent", "rope_adjacent_kernel", _p(buf), dt(buf), _ll(rows), L, ld, cols, dh, _p(table), int(inverse))
+    return buf
+
+
+def copy_rows(x, out, *, rows, cols, ldi=None, ldo=None, in_remap=(0, 0, 0), out_remap=(0, 0, 0)):
+    _need_cuda(x, out)
+    _call("tcavp_copy_rows", "copy_rows_kernel", _p(x), cols if ldi is None else ldi, dt(x), *in_remap, _p(out), cols if ldo is None else ldo,
+          dt(out), *out_remap, _ll(rows), cols)
+    return out
+
+
+def masked_mean_bwd(dout, lens, dx, *, B, P, D):
+    _need_cuda(dout, lens, dx)
+    _call("tcavp_masked_mean_bwd", "masked_mean_bwd_kernel", _p(dout), dt(dout), _p(lens), _p(dx), dt(dx), B, P, D)
+    return dx
+
+
+def nlinear_bwd(g, *, B, C, T_in, T_out, x_in=None, w=None, din=None, dw=None):
+    _need_cuda(g, x_in, w, din, dw)
+    _call("tcavp_nlinear_bwd", "nlinear_bwd_kernel", _p(g), dt(g), _p(x_in), 0 if x_in is None else dt(x_in), _p(w), _p(din),
+          0 if din is None else dt(din), _p(dw), B, C, T_in, T_out)
+
+
+def head_assemble(o, x, decoded, *, B, T_in, T_out):
+    _need_cuda(o, x, decoded)
+    _call("tcavp_head_assemble", "head_assemble_kernel", _p(o), _p(x), _p(decoded), B, T_in, T_out)
+    return decoded
+
+
+def traj_loss_bwd(decoded, y, norm_stat, d_o, *, B, T_out, gscale=None):
+    _need_cuda(decoded, y, norm_stat, d_o, gscale)
+    _call("tcavp_traj_loss_bwd", "traj_loss_bwd_kernel", _p(decoded), _p(y), _p(norm_stat), _p(gscale), _p(d_o), B, T_out)
+    return d_o
+
+
+def skinny_dw(Y, Z, out, *, M, N, J, ldy=None, ldz=None, ldo=None, row_scale=None):
+    """out[n][j] += sum_m row_scale[m] * Y[m][n] * Z[m][j]   (out fp32)."""
+    _need_cuda(Y, Z, out, row_scale)
+    _call("tcavp_skinny_dw", "skinny_dw_kernel", _p(Y), N if ldy is None else ldy, dt(Y), _p(Z), J if ldz is None else ldz, dt(Z),
+          _p(row_scale), _p(out), J if ldo is None else ldo, _ll(M), N, J, flops=2.0 * M * N * J, nbytes=float(M * N * Y.element_size()))
+    return out
+
+
+def attention_bwd(q, k, v, dout, dq, dk, dv, *, B, H, Hkv, Tq, Tk, dh, q_strides, k_strides, v_strides, do_strides, dq_strides,
+                  dk_strides, dv_strides, scale, causal=False, key_mask=None):
+    """dk / dv: fp32 accumulators (zeroed by the caller)."""
+    _need_cuda(q, k, v, dout, dq, dk, dv, key_mask)
+    if dk.dtype != torch.float32 or dv.dtype != torch.float32:
+        raise TypeError("attention_bwd: dk / dv must be fp32")
+    a = AttnArgs()
+    a.B, a.H, a.Hkv, a.Tq, a.Tk, a.dh = B, H, Hkv, Tq, Tk, dh
+    a.q, (a.q_sb, a.q_st) = q.data_ptr(), q_strides
+    a.k, (a.k_sb, a.k_st) = k.data_ptr(), k_strides
+    a.v, (a.v_sb, a.v_st) = v.data_ptr(), v_strides
+    a.dtype, a.scale, a.causal = dt(q), scale, int(causal)
+    if key_mask is not None:
+        a.key_mask = key_mask.data_ptr()
+    fl = 10.0 * B * H * Tq * Tk * dh
+    with _Timed(f"attn_bwd_kernel[dh{dh},q{Tq},k{Tk}]", fl, 0.0):
+        _lib.check(_lib.load().tcavp_attention_bwd(byref(a), _p(dout), _ll(do_strides[0]), _ll(do_strides[1]), _p(dq), _ll(dq_strides[0]),
+                                                   _ll(dq_strides[1]), _p(dk), _ll(dk_strides[0]), _ll(dk_strides[1]), _p(dv),
+                                                   _ll(dv_strides[0]), _ll(dv_strides[1]), _stream()), "tcavp_attention_bwd")
+
+
+def adamw_(param, grad, exp_avg, exp_avg_sq, *, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, step, grad_scale=1.0):
+    _need_cuda(param, grad, exp_avg, exp_avg_sq)
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise TypeError("adamw_: flat contiguous fp32 buffers required")
+    _call("tcavp_adamw", "adamw_kernel", _p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), _ll(param.numel()), c_float(lr), c_float(betas[0]),
+          c_float(betas[1]), c_float(eps), c_float(weight_decay), int(step), c_float(grad_scale))
+    return param
