@@ -314,3 +314,35 @@ def forward(sd, cfg, llama_cfg, x, vision, polygon, poly_len, input_ids, attenti
         out["loss"] = mse_loss(out["decoded"], y, norm_stat)
         out["ade"], out["fde"] = ade_fde(out["decoded"], y, norm_stat)
     return out
+
+
+# --------------------------------------------------------------------------------------------------
+# fine-tune step: reference gradients = torch autograd through the restatement above
+# (reference scripts/im_kim_train_GRN.py:1029-1039 with every dropout p = 0)
+# --------------------------------------------------------------------------------------------------
+
+
+def trainable_keys(sd):
+    """peft semantics (oracle/peft_shim.py): every LLM tensor is frozen except lora_A / lora_B; everything else trains."""
+    return [k for k, v in sd.items() if v.is_floating_point() and ("llama_model" not in k or "lora_" in k)]
+
+
+def loss_and_grads(sd, cfg, llama_cfg, x, vision, polygon, poly_len, input_ids, attention_mask, y, norm_stat, keys=None):
+    """Returns (loss, decoded, {key: d loss / d sd[key]}) for the trainable keys (fp32, CPU)."""
+    sd = {k: (v.detach().float().clone() if v.is_floating_point() else v) for k, v in sd.items()}
+    keys = list(keys) if keys is not None else trainable_keys(sd)
+    for k in keys:
+        sd[k].requires_grad_(True)
+    with torch.enable_grad():
+        out = forward.__wrapped__(sd, cfg, llama_cfg, x, vision, polygon, poly_len, input_ids, attention_mask, y, norm_stat)
+        grads = torch.autograd.grad(out["loss"], [sd[k] for k in keys], allow_unused=True)
+    return out["loss"].detach(), out["decoded"].detach(), {k: (g if g is not None else torch.zeros_like(sd[k])) for k, g in zip(keys, grads)}
+
+
+def compress_grad(g, big=50_000):
+    """Golden-fixture form of a gradient: full tensor when small, else first rows + row / column sums."""
+    g = g.detach().float()
+    if g.numel() <= big or g.dim() < 2:
+        return {"full": g.clone()}
+    g2 = g.reshape(g.shape[0], -1)
+    return {"head": g2[:4].clone(), "rowsum": g2.double().sum(1).float(), "colsum": g2.double().sum(0).float(), "shape": tuple(g.shape)}

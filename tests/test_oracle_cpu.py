@@ -52,3 +52,32 @@ def test_peft_shim_layout_and_math():
     want = x @ base.weight.t() + (x @ l.lora_A["default"].weight.t()) @ l.lora_B["default"].weight.t() * 4.0
     torch.testing.assert_close(l(x), want)
     assert set(l.state_dict()) == {"base_layer.weight", "lora_A.default.weight", "lora_B.default.weight"}
+
+
+def _check_against_compressed(got, want, rtol, atol, key):
+    if "full" in want:
+        torch.testing.assert_close(got.float().cpu(), want["full"], rtol=rtol, atol=atol, msg=lambda m: f"{key}: {m}")
+        return
+    g2 = got.float().cpu().reshape(got.shape[0], -1)
+    assert tuple(got.shape) == tuple(want["shape"]), key
+    torch.testing.assert_close(g2[:4], want["head"], rtol=rtol, atol=atol, msg=lambda m: f"{key} head: {m}")
+    scale = float(want["rowsum"].abs().max()) + float(want["colsum"].abs().max()) + 1e-12
+    torch.testing.assert_close(g2.double().sum(1).float(), want["rowsum"], rtol=rtol, atol=atol + 1e-4 * scale, msg=lambda m: f"{key} rowsum: {m}")
+    torch.testing.assert_close(g2.double().sum(0).float(), want["colsum"], rtol=rtol, atol=atol + 1e-4 * scale, msg=lambda m: f"{key} colsum: {m}")
+
+
+def test_restated_gradients_match_reference_autograd():
+    """Pins the fine-tune oracle: autograd through oracle/restated.py == gradients of the unmodified reference model."""
+    fix = load_golden("tiny_b5_grads")
+    m = T.MultiModalTrajectoryModel(**fix["model_cfg"])
+    sd = m.state_dict()
+    T.deterministic_fill_(sd, fix["weight_seed"])
+    i = fix["inputs"]
+    loss, decoded, grads = restated.loss_and_grads(sd, fix["model_cfg"], fix["llama_cfg"], i["x"], i["vision"], i["polygon"], i["poly_len"],
+                                                   i["input_ids"], i["attention_mask"], i["y"], i["norm_stat"])
+    torch.testing.assert_close(loss, fix["loss"], rtol=1e-5, atol=0)
+    assert set(grads) == set(fix["grads"]) and len(grads) == fix["n_trainable"]
+    assert {n for n, p in m.named_parameters() if p.requires_grad} == set(grads)
+    for k, want in fix["grads"].items():
+        ref_scale = float((want["full"] if "full" in want else want["head"]).abs().max()) + 1e-8
+        _check_against_compressed(grads[k], want, rtol=2e-3, atol=2e-4 * ref_scale + 1e-6, key=k)

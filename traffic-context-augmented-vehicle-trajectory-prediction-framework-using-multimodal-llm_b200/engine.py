@@ -16,12 +16,13 @@ def _f32(t, dev):
 
 class _Lin:
     """Packed linear: weight in the activation dtype ([N, K] row-major), bias in fp32."""
-    __slots__ = ("w", "b", "N", "K")
+    __slots__ = ("w", "b", "N", "K", "wT")
 
     def __init__(self, w, b, act, dev):
         self.w = w.detach().to(device=dev, dtype=act).contiguous()
         self.b = None if b is None else _f32(b, dev)
         self.N, self.K = self.w.shape
+        self.wT = None   # [K, N] copy used by the backward pass (train_engine.py)
 
 
 class Engine:
@@ -104,6 +105,8 @@ class Engine:
         self.llm["fuse_rope"] = dh % 32 == 0 and not os.environ.get("TCAVP_NO_FUSE_ROPE")
         hp = torch.stack([torch.arange(dh // 2), torch.arange(dh // 2) + dh // 2], dim=1).reshape(-1)
         qk_perm = torch.cat([h * dh + hp for h in range(nh + nkv)] + [torch.arange(nq + nk, nq + 2 * nk)]).to(dev)
+        self.llm["qk_perm"] = qk_perm
+        self.llm["targets"], self.llm["r"] = tuple(targets), r
         for layer in lm.model.layers:
             sa = layer.self_attn
             rows = {"q_proj": (0, nq), "k_proj": (nq, nq + nk), "v_proj": (nq + nk, nq + 2 * nk)}
@@ -132,7 +135,7 @@ class Engine:
             gu[0::2] = (layer.mlp.gate_proj.weight.detach().to(dev).float() * ln2[None, :]).to(act)
             gu[1::2] = (layer.mlp.up_proj.weight.detach().to(dev).float() * ln2[None, :]).to(act)
             self.llm["layers"].append(dict(
-                wqkv=wqkv, a_cat=a_cat, wo=sa.o_proj.weight.detach().to(dev, act).contiguous(), wgu=gu,
+                wqkv=wqkv, a_cat=a_cat, ln1=ln1, wo=sa.o_proj.weight.detach().to(dev, act).contiguous(), wgu=gu,
                 wdown=layer.mlp.down_proj.weight.detach().to(dev, act).contiguous()))
 
     def _pack_ltsf(self, lt):

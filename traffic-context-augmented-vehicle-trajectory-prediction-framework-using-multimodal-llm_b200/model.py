@@ -9,8 +9,40 @@ import math
 import torch
 import torch.nn as nn
 
+import warnings
+
 from .config import resolve_llama
 from .engine import Engine
+from .train_engine import TrainEngine
+
+
+class _FineTuneStep(torch.autograd.Function):
+    """One autograd node for the whole model: forward = TrainEngine.train_forward (libtcavp kernels, activations stashed),
+    backward = TrainEngine.train_backward (hand-written backward kernels).  The trainable nn.Parameters are the node's
+    inputs, so `loss.backward()` deposits their gradients exactly where torch.optim / DistributedDataParallel expect them
+    (reference scripts/im_kim_train_GRN.py:1029-1040)."""
+
+    @staticmethod
+    def forward(ctx, eng, inputs, *params):
+        out = eng.train_forward(**inputs)
+        ctx.eng = eng
+        ctx.names = [n for n, _ in eng.params]
+        ctx.mark_non_differentiable(out["decoded"])
+        ctx.set_materialize_grads(False)
+        return out["loss"].clone(), out["decoded"]
+
+    @staticmethod
+    def backward(ctx, gloss, _gdec):
+        if gloss is None:
+            return (None, None) + (None,) * len(ctx.names)
+        grads = ctx.eng.train_backward(gloss)
+        res = []
+        for (name, p) in ctx.eng.params:
+            g = grads.get(name)
+            if g is not None:
+                g = g.reshape(p.shape).to(p.dtype)
+            res.append(g)
+        return (None, None) + tuple(res)
 
 # --------------------------------------------------------------------------------------------------
 # parameter containers (names = reference names)
@@ -288,6 +320,9 @@ class MultiModalTrajectoryModel(nn.Module):
         self.compute_dtype = compute_dtype
         self._engine = None
         self._engine_sig = None
+        self._train_engine = None
+        self._train_sig = None
+        self._warned_dropout = False
         self._register_load_state_dict_pre_hook(self._translate_keys)
 
     # ---- checkpoint interop -----------------------------------------------------
@@ -335,15 +370,35 @@ class MultiModalTrajectoryModel(nn.Module):
         """Same contract as reference scripts/train.py:914-964.  `labels` is accepted and ignored: it only feeds HF's
         internal CE loss, which the reference discards (train.py:547-554).  `lane_polygon_len` / `norm_stat` may be
         Python lists (as the reference's collate produces) or device tensors."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError("training backward is not implemented yet: call under torch.no_grad() / eval()")
         if input_ids is None or attention_mask is None:
             raise NotImplementedError("tokenizer branch (train.py:556-575) needs a hub tokenizer; pass input_ids and attention_mask")
+        if torch.is_grad_enabled() and y is not None and norm_stat is not None and any(p.requires_grad for p in self.parameters()):
+            return self._train_step(x, vision_embs, lane_polygon_batch, lane_polygon_len, y, norm_stat, input_ids, attention_mask)
         eng = self.engine()
         out = eng.forward(x, vision_embs, lane_polygon_batch, lane_polygon_len, input_ids, attention_mask, y=y, norm_stat=norm_stat)
         if y is not None and norm_stat is not None:
             return out["loss"], out["decoded"]
         return out["decoded"]
+
+    # ---- fine-tune step (reference scripts/im_kim_train_GRN.py:1028-1041) ----------------------------
+    def train_engine(self):
+        """The engine of the differentiable path; rebuilt when the frozen backbone or the set of trainable tensors changes."""
+        sig = (self.compute_dtype,) + tuple((p.data_ptr(), p.requires_grad) for p in self.parameters()) + \
+            tuple(p._version for n, p in self.named_parameters() if "llama_model" in n and "lora_" not in n)
+        if self._train_engine is None or sig != self._train_sig:
+            self._train_engine = TrainEngine(self, self.compute_dtype)
+            self._train_sig = sig
+        return self._train_engine
+
+    def _train_step(self, x, vision_embs, lane_polygon_batch, lane_polygon_len, y, norm_stat, input_ids, attention_mask):
+        if self.training and not self._warned_dropout:
+            self._warned_dropout = True
+            warnings.warn("tcavp_b200: dropout (lora_dropout / ltsf_dropout / nn.Transformer dropout) is not applied in the fine-tune "
+                          "step; gradients match the reference with every dropout p = 0")
+        eng = self.train_engine()
+        inputs = dict(x=x, vision=vision_embs, polygon=lane_polygon_batch, poly_len=lane_polygon_len, input_ids=input_ids,
+                      attention_mask=attention_mask, y=y, norm_stat=norm_stat)
+        return _FineTuneStep.apply(eng, inputs, *[p for _, p in eng.params])
 
     @torch.no_grad()
     def predict_with_metrics(self, x, vision_embs, lane_polygon_batch, lane_polygon_len, y, norm_stat, input_ids, attention_mask):
