@@ -249,7 +249,9 @@ int tcavp_traj_loss_bwd(const float* decoded, const float* y, const float* norm_
 int tcavp_skinny_dw(const void* Y, int ldy, int y_dtype, const void* Z, int ldz, int z_dtype, const float* row_scale, float* out, int ldo,
                     long long M, int N, int J, tcavp_stream_t stream);
 /* Backward of tcavp_attention (probabilities recomputed; any head_dim; Tk <= 768).  dq has the dtype/layout convention of q;
- * dk / dv are fp32 accumulators (caller zeroes them) because query blocks and GQA groups add into the same keys. */
+ * dk / dv are fp32 (caller zeroes them: the generic kernel accumulates with atomics because query blocks and GQA groups add
+ * into the same keys).  When args->out / o_sb / o_st hold the FORWARD OUTPUT and the shape is bf16, H == Hkv, head_dim in
+ * {16,32,64,96,128}, Tq, Tk <= 256, a tensor-core kernel (mma.sync, one CTA per (batch, head), no atomics) is used. */
 int tcavp_attention_bwd(const tcavp_attn_args* args, const void* dout, long long do_sb, long long do_st, void* dq, long long dq_sb,
                         long long dq_st, float* dk, long long dk_sb, long long dk_st, float* dv, long long dv_sb, long long dv_st,
                         tcavp_stream_t stream);

@@ -273,3 +273,52 @@ def test_adamw_matches_torch(ops):
         opt.step()
         ops.adamw_(p, (gs * 2.0).to(DEV), m, v, lr=5e-4, weight_decay=1e-4, step=step, grad_scale=0.5)
     torch.testing.assert_close(p.cpu(), ref.detach(), rtol=1e-5, atol=1e-6)
+
+
+TC_ATTN_CASES = [  # B, H, Tq, Tk, dh, causal, masked   (bf16, H == Hkv, forward output supplied -> tensor-core kernel)
+    (2, 12, 144, 144, 64, True, True),     # LLM cfg-1/2
+    (2, 4, 144, 144, 128, True, True),     # LLM 7B-class head
+    (3, 4, 24, 24, 32, True, True),
+    (4, 4, 64, 64, 16, False, True),       # lane polygon encoder
+    (3, 8, 16, 15, 96, False, False),      # Q-Former cross-attention
+    (3, 8, 15, 15, 96, False, False),
+    (2, 2, 15, 15, 32, False, False),      # temporal self-attention
+    (1, 2, 200, 256, 64, False, True),
+    (2, 3, 256, 256, 64, True, False),
+]
+
+
+@pytest.mark.parametrize("B,H,Tq,Tk,dh,causal,masked", TC_ATTN_CASES)
+def test_attention_bwd_tensor_core(ops, B, H, Tq, Tk, dh, causal, masked):
+    td = torch.bfloat16
+    q = _rand(B, Tq, H, dh, seed=40).to(td).float().requires_grad_(True)
+    k = _rand(B, Tk, H, dh, seed=41).to(td).float().requires_grad_(True)
+    v = _rand(B, Tk, H, dh, seed=42).to(td).float().requires_grad_(True)
+    valid = torch.ones(B, Tk, dtype=torch.bool)
+    if masked:
+        for b in range(B):
+            valid[b, Tk - 1 - 3 * b:] = False
+    scale = dh ** -0.5
+    s = torch.einsum("bihd,bjhd->bhij", q, k) * scale
+    allow = valid[:, None, None, :].expand(B, H, Tq, Tk)
+    if causal:
+        allow = allow & torch.tril(torch.ones(Tq, Tk, dtype=torch.bool))[None, None]
+    s = s.masked_fill(~allow, float("-inf"))
+    o = torch.einsum("bhij,bjhd->bihd", torch.softmax(s, dim=-1), v)
+    do = _rand(B, Tq, H, dh, seed=43).to(td)
+    o.backward(do.float())
+    qd, kd, vd, dod, od = (t.detach().to(td).to(DEV).contiguous() for t in (q, k, v, do, o))
+    dq = torch.full_like(qd, float("nan"))
+    dk = torch.zeros(B, Tk, H, dh, device=DEV)
+    dv = torch.zeros(B, Tk, H, dh, device=DEV)
+    km = valid.to(torch.int32).to(DEV) if masked else None
+    sq, sk = (Tq * H * dh, H * dh), (Tk * H * dh, H * dh)
+    n0 = ops.launch_count()
+    ops.attention_bwd(qd, kd, vd, dod, dq, dk, dv, B=B, H=H, Hkv=H, Tq=Tq, Tk=Tk, dh=dh, q_strides=sq, k_strides=sk, v_strides=sk,
+                      do_strides=sq, dq_strides=sq, dk_strides=sk, dv_strides=sk, scale=scale, causal=causal, key_mask=km, o=od, o_strides=sq)
+    assert ops.launch_count() - n0 == 1
+    # bf16 P / dS operands inside the kernel: tolerance scaled to each tensor's magnitude
+    for name, got, want in (("dq", dq.float().cpu(), q.grad), ("dk", dk.cpu(), k.grad), ("dv", dv.cpu(), v.grad)):
+        err = float((got - want).abs().max()) / (float(want.abs().max()) + 1e-12)
+        assert err < 2e-2, (name, err)
+        assert torch.isfinite(got).all(), name

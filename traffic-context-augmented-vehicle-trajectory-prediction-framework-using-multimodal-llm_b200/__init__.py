@@ -6,3 +6,4 @@ from .weights import deterministic_fill_  # noqa: F401
 from .model import MultiModalTrajectoryModel  # noqa: F401,E402
 from . import ops  # noqa: F401,E402
 from . import distributed  # noqa: F401,E402
+from .finetune import FineTuner  # noqa: F401,E402

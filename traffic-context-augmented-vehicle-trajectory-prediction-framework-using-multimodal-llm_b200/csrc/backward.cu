@@ -504,6 +504,10 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_kernel(tcavp_attn_args a, co
 }
 }  // namespace ab
 
+int attention_bwd_tc_launch(const tcavp_attn_args& a, const void* dout, long long do_sb, long long do_st, void* dq, long long dq_sb,
+                            long long dq_st, float* dk, long long dk_sb, long long dk_st, float* dv, long long dv_sb, long long dv_st,
+                            cudaStream_t stream);   // attention_bwd_tc.cu
+
 // ------------------------------------------------------------------------------------------------
 // AdamW (torch.optim.AdamW semantics, reference scripts/im_kim_train_GRN.py:1008): decoupled weight decay,
 // bias-corrected moments.  One flat fp32 buffer per state.
@@ -706,6 +710,10 @@ extern "C" int tcavp_attention_bwd(const tcavp_attn_args* a, const void* dout, l
   TCAVP_REQUIRE(!a->causal || a->Tq == a->Tk, "tcavp_attention_bwd: causal needs Tq == Tk");
   if (a->B == 0) return TCAVP_OK;
   TCAVP_REQUIRE(a->q && a->k && a->v && dout && dq && dk && dv && DT_OK(a->dtype), "tcavp_attention_bwd: bad pointer/dtype");
+  {   // tensor-core path: bf16, MHA, small head, forward output available (args->out)
+    const int rc = attention_bwd_tc_launch(*a, dout, do_sb, do_st, dq, dq_sb, dq_st, dk, dk_sb, dk_st, dv, dv_sb, dv_st, STREAM(stream));
+    if (rc <= 0) return rc;
+  }
   int DC = a->dh < 32 ? a->dh : 32;
   auto smem_for = [&](int dc) { return (size_t)(2 * ab::QB * a->Tk + 2 * ab::QB * (dc + 1) + 2 * (size_t)a->Tk * (dc + 1)) * sizeof(float); };
   if (smem_for(DC) > 200 * 1024) DC = 16 < a->dh ? 16 : a->dh;

@@ -143,7 +143,7 @@ class LoraLinearW(nn.Module):
 
     def __init__(self, base, r, alpha, dropout):
         super().__init__()
-        kw = dict(device=base.weight.device, dtype=base.weight.dtype)
+        kw = dict(device=base.weight.device, dtype=torch.float32)   # adapters are fp32 masters (peft: autocast_adapter_dtype)
         self.base_layer = base
         self.lora_A = nn.ModuleDict({"default": nn.Linear(base.in_features, r, bias=False, **kw)})
         self.lora_B = nn.ModuleDict({"default": nn.Linear(r, base.out_features, bias=False, **kw)})
@@ -381,6 +381,11 @@ class MultiModalTrajectoryModel(nn.Module):
         return out["decoded"]
 
     # ---- fine-tune step (reference scripts/im_kim_train_GRN.py:1028-1041) ----------------------------
+    def trainable_named_parameters(self):
+        """(name, parameter) of every tensor the fine-tune step produces a gradient for: everything with requires_grad except
+        non-LoRA backbone weights (peft freezes those, train.py:432-440; full backbone fine-tuning is out of scope)."""
+        return [(n, p) for n, p in self.named_parameters() if p.requires_grad and ("llama_model" not in n or "lora_" in n)]
+
     def train_engine(self):
         """The engine of the differentiable path; rebuilt when the frozen backbone or the set of trainable tensors changes."""
         sig = (self.compute_dtype,) + tuple((p.data_ptr(), p.requires_grad) for p in self.parameters()) + \

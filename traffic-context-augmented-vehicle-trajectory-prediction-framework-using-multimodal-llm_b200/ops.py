@@ -437,9 +437,9 @@ def skinny_dw(Y, Z, out, *, M, N, J, ldy=None, ldz=None, ldo=None, row_scale=Non
 
 
 def attention_bwd(q, k, v, dout, dq, dk, dv, *, B, H, Hkv, Tq, Tk, dh, q_strides, k_strides, v_strides, do_strides, dq_strides,
-                  dk_strides, dv_strides, scale, causal=False, key_mask=None):
-    """dk / dv: fp32 accumulators (zeroed by the caller)."""
-    _need_cuda(q, k, v, dout, dq, dk, dv, key_mask)
+                  dk_strides, dv_strides, scale, causal=False, key_mask=None, o=None, o_strides=None):
+    """dk / dv: fp32 accumulators (zeroed by the caller).  o = the forward output (enables the tensor-core kernel)."""
+    _need_cuda(q, k, v, dout, dq, dk, dv, key_mask, o)
     if dk.dtype != torch.float32 or dv.dtype != torch.float32:
         raise TypeError("attention_bwd: dk / dv must be fp32")
     a = AttnArgs()
@@ -450,8 +450,12 @@ def attention_bwd(q, k, v, dout, dq, dk, dv, *, B, H, Hkv, Tq, Tk, dh, q_strides
     a.dtype, a.scale, a.causal = dt(q), scale, int(causal)
     if key_mask is not None:
         a.key_mask = key_mask.data_ptr()
-    fl = 10.0 * B * H * Tq * Tk * dh
-    with _Timed(f"attn_bwd_kernel[dh{dh},q{Tq},k{Tk}]", fl, 0.0):
+    tc = False
+    if o is not None:
+        a.out, (a.o_sb, a.o_st) = o.data_ptr(), o_strides
+        tc = a.dtype == BF16 and H == Hkv and dh in (16, 32, 64, 96, 128) and max(Tq, Tk) <= 256
+    fl = 10.0 * B * H * Tq * Tk * dh * (0.5 if causal else 1.0)
+    with _Timed(f"attn_bwd_{'tc_' if tc else ''}kernel[dh{dh},q{Tq},k{Tk}]", fl, 0.0):
         _lib.check(_lib.load().tcavp_attention_bwd(byref(a), _p(dout), _ll(do_strides[0]), _ll(do_strides[1]), _p(dq), _ll(dq_strides[0]),
                                                    _ll(dq_strides[1]), _p(dk), _ll(dk_strides[0]), _ll(dk_strides[1]), _p(dv),
                                                    _ll(dv_strides[0]), _ll(dv_strides[1]), _stream()), "tcavp_attention_bwd")

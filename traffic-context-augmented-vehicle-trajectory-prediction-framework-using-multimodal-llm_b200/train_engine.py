@@ -43,8 +43,7 @@ class TrainEngine(Engine):
     def _names(self):
         """(name, parameter) of every trainable tensor this engine produces a gradient for.  Non-LoRA LLM weights are treated
         as frozen even if requires_grad is set (full fine-tuning of the backbone is out of scope)."""
-        self.params = [(n, p) for n, p in self.model.named_parameters()
-                       if p.requires_grad and ("llama_model" not in n or "lora_" in n)]
+        self.params = self.model.trainable_named_parameters()
         wrap = self.model.mllm.llama_wrapper
         self.llm_prefix = "mllm.llama_wrapper.llama_model." + ("base_model.model." if wrap.use_lora else "") + "model.layers."
 
@@ -140,14 +139,14 @@ class TrainEngine(Engine):
 
     # ---- attention backward into packed gradient buffers ------------------------------------------------
     def _attn_bwd(self, q, k, v, do, *, B, H, Hkv, Tq, Tk, dh, qs, ks, vs, dos, dq, dqs, dk_out, dv_out, ld_kv, scale, causal=False,
-                  key_mask=None):
+                  key_mask=None, o=None):
         """dq is written in place (strides dqs); dk / dv are accumulated in fp32 and cast into dk_out / dv_out (row stride ld_kv)."""
         wk = Hkv * dh
         dk = torch.zeros(B * Tk, wk, dtype=torch.float32, device=self.dev)
         dv = torch.zeros(B * Tk, wk, dtype=torch.float32, device=self.dev)
         ops.attention_bwd(q, k, v, do, dq, dk, dv, B=B, H=H, Hkv=Hkv, Tq=Tq, Tk=Tk, dh=dh, q_strides=qs, k_strides=ks, v_strides=vs,
                           do_strides=dos, dq_strides=dqs, dk_strides=(Tk * wk, wk), dv_strides=(Tk * wk, wk), scale=scale, causal=causal,
-                          key_mask=key_mask)
+                          key_mask=key_mask, o=o, o_strides=dos)
         ops.cast(dk, dk_out, rows=B * Tk, cols=wk, ldo=ld_kv)
         ops.cast(dv, dv_out, rows=B * Tk, cols=wk, ldo=ld_kv)
 
@@ -160,14 +159,14 @@ class TrainEngine(Engine):
                       k_strides=(T * 3 * E, 3 * E), v_strides=(T * 3 * E, 3 * E), o_strides=(T * E, E), scale=dh ** -0.5, key_mask=key_mask)
         return qkv, a
 
-    def _self_attn_bwd(self, da, qkv, x, T, B, mha, pre, key_mask=None, dx_residual=None, train=True):
+    def _self_attn_bwd(self, da, qkv, x, T, B, mha, pre, key_mask=None, dx_residual=None, train=True, o=None):
         """-> dx (gradient w.r.t. the block input through the qkv projection, + dx_residual)."""
         E, heads = mha["E"], mha["heads"]
         dh = E // heads
         dqkv = self._new(B * T, 3 * E, dtype=qkv.dtype)
         s3 = (T * 3 * E, 3 * E)
         self._attn_bwd(qkv, qkv[:, E:], qkv[:, 2 * E:], da, B=B, H=heads, Hkv=heads, Tq=T, Tk=T, dh=dh, qs=s3, ks=s3, vs=s3, dos=(T * E, E),
-                       dq=dqkv, dqs=s3, dk_out=dqkv[:, E:], dv_out=dqkv[:, 2 * E:], ld_kv=3 * E, scale=dh ** -0.5, key_mask=key_mask)
+                       dq=dqkv, dqs=s3, dk_out=dqkv[:, E:], dv_out=dqkv[:, 2 * E:], ld_kv=3 * E, scale=dh ** -0.5, key_mask=key_mask, o=o)
         return self._lin_bwd(dqkv, x, mha["qkv"], pre + "in_proj_weight", pre + "in_proj_bias", dx_residual=dx_residual, train=train)
 
     def _cross_attn_fwd(self, xq, Tq, mem, Tk, B, mha):
@@ -180,14 +179,15 @@ class TrainEngine(Engine):
                       v_strides=(Tk * 2 * E, 2 * E), o_strides=(Tq * E, E), scale=dh ** -0.5)
         return q, kv, a
 
-    def _cross_attn_bwd(self, da, q, kv, xq, Tq, mem, Tk, B, mha, pre, *, need_dmem=True, dmem_residual=None, dxq_residual=None, train=True):
+    def _cross_attn_bwd(self, da, q, kv, xq, Tq, mem, Tk, B, mha, pre, *, need_dmem=True, dmem_residual=None, dxq_residual=None, train=True,
+                        o=None):
         E, heads = mha["E"], mha["heads"]
         dh = E // heads
         dq = self._new(B * Tq, E, dtype=q.dtype)
         dkv = self._new(B * Tk, 2 * E, dtype=kv.dtype)
         s2 = (Tk * 2 * E, 2 * E)
         self._attn_bwd(q, kv, kv[:, E:], da, B=B, H=heads, Hkv=heads, Tq=Tq, Tk=Tk, dh=dh, qs=(Tq * E, E), ks=s2, vs=s2, dos=(Tq * E, E),
-                       dq=dq, dqs=(Tq * E, E), dk_out=dkv, dv_out=dkv[:, E:], ld_kv=2 * E, scale=dh ** -0.5)
+                       dq=dq, dqs=(Tq * E, E), dk_out=dkv, dv_out=dkv[:, E:], ld_kv=2 * E, scale=dh ** -0.5, o=o)
         dw = db = None
         if train:
             dw, db = self._g(pre + "in_proj_weight", (3 * E, E)), self._g(pre + "in_proj_bias", (3 * E,))
@@ -218,7 +218,7 @@ class TrainEngine(Engine):
         da = self._lin_bwd(dy1, a, sa["out"], pre + "self_attn.out_proj.weight", pre + "self_attn.out_proj.bias", train=train)
         if not need_dx and not train:
             return None
-        return self._self_attn_bwd(da, qkv, x, T, B, sa, pre + "self_attn.", key_mask, dx_residual=dy1, train=train)
+        return self._self_attn_bwd(da, qkv, x, T, B, sa, pre + "self_attn.", key_mask, dx_residual=dy1, train=train, o=a)
 
     def _dec_fwd(self, t, Q, mem, Tv, B, L):
         qkv, a = self._self_attn_fwd(t, Q, B, L["sa"])
@@ -239,10 +239,10 @@ class TrainEngine(Engine):
         dt2 = self._lin_bwd(dpre, t2, L["l1"], pre + "linear1.weight", pre + "linear1.bias", dx_residual=dy3)
         dy2 = self._ln_bwd(dt2, y2, L["n2"], pre + "norm2.weight", pre + "norm2.bias")
         dc = self._lin_bwd(dy2, c, L["ca"]["out"], pre + "multihead_attn.out_proj.weight", pre + "multihead_attn.out_proj.bias")
-        dt1, dmem = self._cross_attn_bwd(dc, q, kv, t1, Q, mem, Tv, B, L["ca"], pre + "multihead_attn.", dmem_residual=dmem, dxq_residual=dy2)
+        dt1, dmem = self._cross_attn_bwd(dc, q, kv, t1, Q, mem, Tv, B, L["ca"], pre + "multihead_attn.", dmem_residual=dmem, dxq_residual=dy2, o=c)
         dy1 = self._ln_bwd(dt1, y1, L["n1"], pre + "norm1.weight", pre + "norm1.bias")
         da = self._lin_bwd(dy1, a, L["sa"]["out"], pre + "self_attn.out_proj.weight", pre + "self_attn.out_proj.bias")
-        dt = self._self_attn_bwd(da, qkv, t, Q, B, L["sa"], pre + "self_attn.", dx_residual=dy1)
+        dt = self._self_attn_bwd(da, qkv, t, Q, B, L["sa"], pre + "self_attn.", dx_residual=dy1, o=a)
         return dt, dmem
 
     # ---- lane polygon encoder (reference scripts/train.py:362-383) ----------------------------------------
@@ -389,7 +389,8 @@ class TrainEngine(Engine):
             dattn = ops.gemm(dx2, ly["woT"], self._new(M, nq))
             dqkv = self._new(M, nqkv)
             self._attn_bwd(qkv, qkv[:, nq:], qkv[:, nq + nk:], dattn, B=B, H=nh, Hkv=nkv, Tq=L, Tk=L, dh=dh, qs=sq, ks=sq, vs=sq, dos=(L * nq, nq),
-                           dq=dqkv, dqs=sq, dk_out=dqkv[:, nq:], dv_out=dqkv[:, nq + nk:], ld_kv=nqkv, scale=dh ** -0.5, causal=True, key_mask=mask)
+                           dq=dqkv, dqs=sq, dk_out=dqkv[:, nq:], dv_out=dqkv[:, nq + nk:], ld_kv=nqkv, scale=dh ** -0.5, causal=True, key_mask=mask,
+                           o=attn)
             ops.rope_adjacent_(dqkv, rows=M, L=L, ld=nqkv, cols=nq + nk, dh=dh, table=table, inverse=True)
             dxs = ops.gemm(dqkv, ly["wqkvT"], self._new(M, Kx))            # [dn1 | dTn]
             if kx and self.tr_lora:
@@ -434,7 +435,7 @@ class TrainEngine(Engine):
         dr = self._lin_bwd(dpre, r, lt["f0"], pre + "ffn.0.weight", pre + "ffn.0.bias", dx_residual=denc)
         dy = self._ln_bwd(dr, y, lt["n2"], pre + "norm2.weight", pre + "norm2.bias")
         da = self._lin_bwd(dy, a, lt["mha"]["out"], pre + "mha.out_proj.weight", pre + "mha.out_proj.bias")
-        dxn = self._self_attn_bwd(da, qkv, xn, T, B, lt["mha"], pre + "mha.", dx_residual=dy)
+        dxn = self._self_attn_bwd(da, qkv, xn, T, B, lt["mha"], pre + "mha.", dx_residual=dy, o=a)
         de0 = self._ln_bwd(dxn, e0, lt["n1"], pre + "norm1.weight", pre + "norm1.bias")
         # e0 = NLinear(xp; we, be) + pos   (bias and positional table share the [T, C] gradient)
         gb = torch.zeros(T, C, dtype=torch.float32, device=self.dev)
