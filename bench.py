@@ -24,6 +24,16 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# stdout carries exactly ONE JSON line: everything else a library writes to fd 1 (e.g. NCCL's version banner) goes to stderr.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(obj):
+    _JSON_OUT.write(json.dumps(obj) + "\n")
+    _JSON_OUT.flush()
+
+
 METRIC = "predicted scenes/sec (forward + ADE/FDE)"
 UNIT = "scenes/s"
 WORKLOADS = {
@@ -239,7 +249,7 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(model, cfg, lc, l_text, sample=args.cpu_sample, repeats=2)
-    print(json.dumps(out), flush=True)
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -319,7 +329,7 @@ def run_train(args):
     pk = peaks()
     top = prof.summary()
     dom = top["dominant"]
-    print(json.dumps({
+    emit(({
         "metric": "LoRA fine-tune tokens/sec (forward + backward + grad all-reduce + AdamW)", "value": round(value, 1), "unit": "tokens/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -331,7 +341,7 @@ def run_train(args):
         "gpu_launches": launches, "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": dom["kernel"], "achieved": round(dom["tflops"], 1), "peak": pk["tf_sustained"],
                      "unit": "TFLOP/s", "frac": round(dom["tflops"] / pk["tf_sustained"], 4), "traffic": None,
-                     "share_of_step": round(dom["time_ms"] / ms, 4), "by_group": top["groups"][:24]}}), flush=True)
+                     "share_of_step": round(dom["time_ms"] / ms, 4), "by_group": top["groups"][:24]}}))
     if world > 1:
         dist.destroy_process_group()
 
@@ -382,12 +392,12 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     v = round(sample * args.steps / dt, 2)
     desc = f"{sample} scenes per step (bounded sample of the {B}-scene workload), fp32, all host threads"
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": {"workload": f"{args.workload}: same model/config as the CUDA arm; {desc}"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": desc},
-        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
 
 
 if __name__ == "__main__":

@@ -144,7 +144,8 @@ __device__ __forceinline__ float swiglu_f(float g, float u) {
   return __fdividef(g * u, 1.f + ex2_approx(-1.4426950408889634f * g));
 }
 
-enum { EPI_VEC_OUT = 1, EPI_VEC_RES = 2, EPI_VEC_BIAS = 4 };
+enum { EPI_VEC_OUT = 1, EPI_VEC_RES = 2, EPI_VEC_BIAS = 4,
+       DBG_NO_TMA = 16, DBG_NO_MMA = 32, DBG_NO_EPI = 64 };   // TCAVP_GEMM_DEBUG: ablation switches for profiling (results are garbage)
 
 // Epilogue of 32 accumulator columns [nacc0, nacc0+32) of row m for one thread.  The interior-tile path (full chunk,
 // 16-byte aligned rows) is branch-light and fully vectorised; ragged edges take the scalar path.
@@ -408,6 +409,203 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): the two CTAs of a cluster (one TPC) compute ONE 256 x BLOCK_N tile.  Each CTA
+// stages its own 128 rows of A and its own BLOCK_N/2 rows of W; the leader CTA's single thread issues
+// tcgen05.mma.cta_group::2 (UMMA 256 x BLOCK_N x 16), which reads both shared memories and writes rows [0,128) of the
+// tile into the leader's TMEM and rows [128,256) into the peer's.  Per k-block an SM ingests 16 KB (A) + BLOCK_N*64 B
+// (half of W) instead of A + the whole W tile, which is what bounds the K <= 1024 GEMMs, and the ring gets 6 stages.
+// Synchronisation: every TMA load (both CTAs) completes on the LEADER's full barrier; the MMA thread's commits are
+// multicast to both CTAs' empty / tmem_full barriers; epilogue warps of both CTAs arrive on the leader's tmem_empty.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {   // arrives on the same barrier offset in both CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+template <int BLOCK_N>
+struct PairCfg {
+  static constexpr int HALF_N = BLOCK_N / 2;
+  static constexpr int B_STAGE_BYTES = HALF_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = BLOCK_N >= 256 ? 6 : 8;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, EpilogueParams ep,
+                    int M, int Nacc, int K, int flags) {
+  using C = PairCfg<BLOCK_N>;
+  constexpr int PAIR_M = 2 * BLOCK_M;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_base + C::STAGES * A_STAGE_BYTES;
+  const uint32_t bars = smem_base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t full_bar = bars;                         // leader's copy is the live one
+  const uint32_t empty_bar = bars + 8 * C::STAGES;        // per CTA, signalled by the multicast commit
+  const uint32_t tmem_full_bar = bars + 16 * C::STAGES;   // per CTA, signalled by the multicast commit
+  const uint32_t tmem_empty_bar = tmem_full_bar + 16;     // leader's copy is the live one
+  const uint32_t tmem_slot = tmem_empty_bar + 16;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_n = (Nacc + BLOCK_N - 1) / BLOCK_N;
+  const int tiles_m = (M + PAIR_M - 1) / PAIR_M;
+  const int num_units = tiles_m * tiles_n;
+  const int unit0 = blockIdx.x >> 1, unit_stride = gridDim.x >> 1;
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tmem_full_bar + 8 * s, 1);
+      mbar_init(tmem_empty_bar + 8 * s, 2 * NUM_EPI_WARPS);   // epilogue warps of both CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // the same warp of both CTAs allocates the pair's TMEM columns
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      const uint32_t leader_full = mapa_shared(full_bar, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = unit0; unit < num_units; unit += unit_stride) {
+        const int m0 = (unit / tiles_n) * PAIR_M + (int)cta_rank * BLOCK_M;
+        const int n0 = (unit % tiles_n) * BLOCK_N + (int)cta_rank * C::HALF_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          if (flags & DBG_NO_TMA) {
+            if (leader) mbar_arrive(full_bar + 8 * stage);
+          } else {
+            if (leader) mbar_expect_tx(full_bar + 8 * stage, 2 * C::STAGE_BYTES);
+            tma_load_2d_pair(smem_a + stage * A_STAGE_BYTES, &tma_a, leader_full + 8 * stage, kb * BLOCK_K, m0);
+            tma_load_2d_pair(smem_b + stage * C::B_STAGE_BYTES, &tma_b, leader_full + 8 * stage, kb * BLOCK_K, n0);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(PAIR_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int unit = unit0; unit < num_units; unit += unit_stride, ++it) {
+        const int acc = it & 1;
+        mbar_wait(tmem_empty_bar + 8 * acc, ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar + 8 * stage, phase);
+          tc_fence_after();
+          const int k_left = K - kb * BLOCK_K;
+          const int ksteps = k_left >= BLOCK_K ? BLOCK_K / UMMA_K : (k_left + UMMA_K - 1) / UMMA_K;
+          const uint32_t a_addr = smem_a + stage * A_STAGE_BYTES;
+          const uint32_t b_addr = smem_b + stage * C::B_STAGE_BYTES;
+          if (flags & DBG_NO_MMA) {
+            mbar_arrive_remote(mapa_shared(empty_bar + 8 * stage, 0));
+            mbar_arrive_remote(mapa_shared(empty_bar + 8 * stage, 1));
+            if (kb == num_kb - 1) {
+              mbar_arrive_remote(mapa_shared(tmem_full_bar + 8 * acc, 0));
+              mbar_arrive_remote(mapa_shared(tmem_full_bar + 8 * acc, 1));
+            }
+          } else {
+            for (int k = 0; k < ksteps; ++k) {
+              umma_bf16_pair(tmem_d, umma_smem_desc(a_addr + k * UMMA_K * 2), umma_smem_desc(b_addr + k * UMMA_K * 2), idesc,
+                             (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit_pair(empty_bar + 8 * stage);
+            if (kb == num_kb - 1) umma_commit_pair(tmem_full_bar + 8 * acc);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2.., both CTAs: each drains its own 128 rows) =====================
+    const int quarter = warp & 3;
+    const int chunk0 = (warp - 2) >> 2;
+    const uint32_t leader_tmem_empty = mapa_shared(tmem_empty_bar, 0);
+    int it = 0;
+    for (int unit = unit0; unit < num_units; unit += unit_stride, ++it) {
+      const int acc = it & 1;
+      const int m0 = (unit / tiles_n) * PAIR_M + (int)cta_rank * BLOCK_M;
+      const int n0 = (unit % tiles_n) * BLOCK_N;
+      mbar_wait(tmem_full_bar + 8 * acc, (it >> 1) & 1);
+      tc_fence_after();
+      const int m = m0 + quarter * 32 + lane;
+      const float rs = (ep.row_scale && m < M) ? __ldg(ep.row_scale + m) : 1.f;
+      const int pos = ep.rope_cols > 0 ? m % ep.rope_L : 0;
+      if (!(flags & DBG_NO_EPI)) {
+#pragma unroll 1
+        for (int c = chunk0; c < BLOCK_N / 32; c += NUM_EPI_WARPS / 4) {
+          if (n0 + c * 32 >= Nacc) break;   // warp-uniform
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + c * 32, r);
+          epilogue_chunk(ep, m, pos, n0 + c * 32, r, rs, flags);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(leader_tmem_empty + 8 * acc);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side: TMA descriptors through the driver entry point (no link-time dependency on libcuda)
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -448,12 +646,13 @@ static int make_map(CUtensorMap* map, const void* base, int rows, int cols, int 
   return TCAVP_OK;
 }
 
-static int cluster_pref() {   // TCAVP_GEMM_CLUSTER=1 disables the 2-CTA multicast clusters (A/B testing)
+// TCAVP_GEMM_CLUSTER (A/B testing): 1 = no clusters, 2 = 2-CTA clusters with TMA multicast of W, 3 = CTA pairs (cta_group::2, default)
+static int cluster_pref() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("TCAVP_GEMM_CLUSTER");
-    v = e ? atoi(e) : 2;
-    if (v != 1 && v != 2) v = 2;
+    v = e ? atoi(e) : 3;
+    if (v < 1 || v > 3) v = 3;
   }
   return v;
 }
@@ -490,6 +689,41 @@ static int launch_tc(const tcavp_gemm_args& a, const EpilogueParams& ep, cudaStr
   cfg.numAttrs = 1;
   TCAVP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, CM>, ma, mb, ep, a.M, a.N, a.K, flags));
   return check_launch("gemm_tc_kernel");
+}
+
+template <int BLOCK_N>
+static int launch_tc_pair(const tcavp_gemm_args& a, const EpilogueParams& ep, cudaStream_t stream) {
+  using C = PairCfg<BLOCK_N>;
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, a.A, a.M, a.K, a.lda, BLOCK_M);
+  if (rc) return rc;
+  rc = make_map(&mb, a.W, a.N, a.K, a.ldw, C::HALF_N);
+  if (rc) return rc;
+  TCAVP_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  const int tiles_m = (a.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), tiles_n = (a.N + BLOCK_N - 1) / BLOCK_N;
+  const int units = tiles_m * tiles_n;
+  const int max_pairs = sm_count() / 2;
+  const int grid = (units < max_pairs ? units : max_pairs) * 2;
+  const size_t osz = ep.out_dtype == TCAVP_BF16 ? 2 : 4, rsz = ep.res_dtype == TCAVP_BF16 ? 2 : 4;
+  int flags = 0;
+  if (((size_t)ep.ldo * osz) % 16 == 0 && (reinterpret_cast<uintptr_t>(ep.out) % 16) == 0) flags |= EPI_VEC_OUT;
+  if (ep.residual && ((size_t)ep.ldr * rsz) % 16 == 0 && (reinterpret_cast<uintptr_t>(ep.residual) % 16) == 0) flags |= EPI_VEC_RES;
+  if (ep.bias && (reinterpret_cast<uintptr_t>(ep.bias) % 16) == 0) flags |= EPI_VEC_BIAS;
+  if (const char* e = getenv("TCAVP_GEMM_DEBUG")) flags |= atoi(e) & (DBG_NO_TMA | DBG_NO_MMA | DBG_NO_EPI);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TCAVP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<BLOCK_N>, ma, mb, ep, a.M, a.N, a.K, flags));
+  return check_launch("gemm_tc_pair_kernel");
 }
 
 }  // namespace tc
@@ -597,7 +831,8 @@ extern "C" int tcavp_gemm(const tcavp_gemm_args* a, tcavp_stream_t stream_) {
     if (a->N <= 32) return tc::launch_tc<32, 1>(*a, ep, stream);
     if (a->N <= 64) return tc::launch_tc<64, 1>(*a, ep, stream);
     if (a->N <= 128) return tc::launch_tc<128, 1>(*a, ep, stream);
-    // large problems: 2-CTA clusters sharing the W tile through TMA multicast
+    // large problems: CTA pairs (one 256 x 256 tile per TPC), or 2-CTA clusters sharing the W tile through TMA multicast
+    if (tc::cluster_pref() == 3 && a->M >= 16 * tc::BLOCK_M) return tc::launch_tc_pair<256>(*a, ep, stream);
     if (tc::cluster_pref() == 2 && a->M >= 16 * tc::BLOCK_M) return tc::launch_tc<256, 2>(*a, ep, stream);
     return tc::launch_tc<256, 1>(*a, ep, stream);
   }
