@@ -42,6 +42,9 @@ int tcavp_version(void);
 int tcavp_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 long long tcavp_launch_count(void);
+/* Profiling aid: one warp spins for `ns` nanoseconds on `stream` and writes (elapsed SM cycles, elapsed ns) to out2[0..1]
+ * (device memory) — the true average SM clock while other kernels run next to it. */
+int tcavp_clock_probe(unsigned long long* out2, unsigned long long ns, tcavp_stream_t stream);
 
 /* ---- dense contraction with fused epilogue --------------------------------------------------
  * out[m', n] = act( sum_k A[m,k] * W[n,k] + bias[n] ) + residual[m', n]

@@ -48,9 +48,31 @@ int sm_count() {
   return cached[dev];
 }
 
+// One warp spins for `ns` nanoseconds next to whatever else is resident on its SM and records (SM cycles, nanoseconds):
+// the true average SM clock while another kernel runs (NVML's sampled clock hides fast power-cap modulation).
+__global__ void clock_probe_kernel(unsigned long long* out, unsigned long long ns) {
+  if (threadIdx.x != 0) return;
+  unsigned long long t0, t1, c0, c1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  c0 = clock64();
+  do {
+    __nanosleep(2000);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+  } while (t1 - t0 < ns);
+  c1 = clock64();
+  out[0] = c1 - c0;
+  out[1] = t1 - t0;
+}
+
 }  // namespace tcavp
 
 extern "C" {
+
+int tcavp_clock_probe(unsigned long long* out2, unsigned long long ns, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(out2 != nullptr, "tcavp_clock_probe: null out");
+  tcavp::clock_probe_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out2, ns);
+  return tcavp::check_launch("clock_probe_kernel");
+}
 
 const char* tcavp_last_error(void) { return tcavp::g_err; }
 int tcavp_version(void) { return 100; }

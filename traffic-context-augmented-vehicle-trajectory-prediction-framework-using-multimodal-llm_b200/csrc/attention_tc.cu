@@ -11,7 +11,6 @@
 namespace tcavp {
 namespace fa {
 
-constexpr int KB = 64;      // keys per iteration
 constexpr int PAD = 8;      // bf16 elements of row padding (16 bytes): ldmatrix rows land in distinct banks
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
@@ -38,16 +37,18 @@ __device__ __forceinline__ float ex2(float x) {
 
 // MAXT / MINB: launch bounds.  (288, 2) keeps two 9-warp CTAs (L = 144) resident per SM so the K/V staging of one
 // overlaps the MMAs of the other.
-template <int DH, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) attn_flash_kernel(tcavp_attn_args a, int tk_pad_all) {
+// KB = keys per iteration (16 / 48 / 64): chosen by the host so that Tk pads to the fewest dead keys (L = 144 = 3 x 48).
+template <int DH, int MAXT, int MINB, int KB>
+__global__ void __launch_bounds__(MAXT, MINB) attn_flash_kernel(tcavp_attn_args a, int tk_pad_all, int tq_pad) {
   constexpr int LDS = DH + PAD;            // smem row stride in elements
   constexpr int KS = DH / 16;              // k-steps of the Q.K^T contraction
   constexpr int NT = DH / 8;               // n8 tiles of the output
   extern __shared__ __align__(16) uint8_t smem[];
   __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem);
   __nv_bfloat16* sV = sK + (size_t)tk_pad_all * LDS;
-  int* sMask = reinterpret_cast<int*>(sV + (size_t)tk_pad_all * LDS);   // [tk_pad_all] 1 = attend
-  int* sBlkValid = sMask + tk_pad_all;                                  // [tk_pad_all / 64] all keys of the block attendable
+  __nv_bfloat16* sQ = sV + (size_t)tk_pad_all * LDS;                    // [tq_pad] rows, zero-filled beyond Tq
+  int* sMask = reinterpret_cast<int*>(sQ + (size_t)tq_pad * LDS);       // [tk_pad_all] 1 = attend
+  int* sBlkValid = sMask + tk_pad_all;                                  // [tk_pad_all / KB] all keys of the block attendable
 
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
   const int hk = h / (a.H / a.Hkv);
@@ -71,6 +72,13 @@ __global__ void __launch_bounds__(MAXT, MINB) attn_flash_kernel(tcavp_attn_args 
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sK_a + off), "l"(gk + rr * a.k_st + c), "r"(sz) : "memory");
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sV_a + off), "l"(gv + rr * a.v_st + c), "r"(sz) : "memory");
     }
+    const uint32_t sQ_a = (uint32_t)__cvta_generic_to_shared(sQ);
+    for (int i = threadIdx.x; i < tq_pad * VPR; i += blockDim.x) {
+      const int r = i / VPR, c = (i % VPR) * 8;
+      const int sz = r < a.Tq ? 16 : 0;
+      const size_t rr = r < a.Tq ? r : 0;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sQ_a + (uint32_t)((r * LDS + c) * 2)), "l"(gq + rr * a.q_st + c), "r"(sz) : "memory");
+    }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
   for (int j = threadIdx.x; j < tk_pad; j += blockDim.x)
@@ -89,6 +97,7 @@ __global__ void __launch_bounds__(MAXT, MINB) attn_flash_kernel(tcavp_attn_args 
   const int nslabs = (a.Tq + 15) / 16;
   const int g = lane >> 2, t4 = lane & 3;
   const uint32_t sK_u = (uint32_t)__cvta_generic_to_shared(sK), sV_u = (uint32_t)__cvta_generic_to_shared(sV);
+  const uint32_t sQ_u = (uint32_t)__cvta_generic_to_shared(sQ);
   // ldmatrix lane -> row/col offsets.  K (non-transposed, x4 = keys [0,8)/[8,16) x dims [0,8)/[8,16)):
   const int k_row = (lane & 7) + ((lane >> 4) << 3), k_col = ((lane >> 3) & 1) * 8;
   // V (transposed, x4 = keys [0,8)/[8,16) x dims [0,8)/[8,16)):
@@ -102,17 +111,23 @@ __global__ void __launch_bounds__(MAXT, MINB) attn_flash_kernel(tcavp_attn_args 
   const int row0 = slab * 16;
   const int r_lo = row0 + g, r_hi = row0 + g + 8;
 
-  // ---- Q fragments straight from global memory (A operand, row-major m16k16 per k-step) ----
+  // ---- Q fragments from the staged tile (A operand, row-major m16k16 per k-step; x4 = rows [0,8)/[8,16) x dims [0,8)/[8,16)) ----
   uint32_t qf[KS][4];
+  if (tq_pad > 0) {
 #pragma unroll
-  for (int ks = 0; ks < KS; ++ks) {
-    const int c = ks * 16 + t4 * 2;
-    const __nv_bfloat16* p_lo = gq + (size_t)r_lo * a.q_st + c;
-    const __nv_bfloat16* p_hi = gq + (size_t)r_hi * a.q_st + c;
-    qf[ks][0] = r_lo < a.Tq ? *reinterpret_cast<const uint32_t*>(p_lo) : 0u;
-    qf[ks][1] = r_hi < a.Tq ? *reinterpret_cast<const uint32_t*>(p_hi) : 0u;
-    qf[ks][2] = r_lo < a.Tq ? *reinterpret_cast<const uint32_t*>(p_lo + 8) : 0u;
-    qf[ks][3] = r_hi < a.Tq ? *reinterpret_cast<const uint32_t*>(p_hi + 8) : 0u;
+    for (int ks = 0; ks < KS; ++ks)
+      ldsm_x4(sQ_u + (uint32_t)(((row0 + v_row) * LDS + ks * 16 + v_col) * 2), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+  } else {   // tq_pad == 0: Q was not staged (shared memory is better spent on a second resident CTA): fragments from global
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const int c = ks * 16 + t4 * 2;
+      const __nv_bfloat16* p_lo = gq + (size_t)r_lo * a.q_st + c;
+      const __nv_bfloat16* p_hi = gq + (size_t)r_hi * a.q_st + c;
+      qf[ks][0] = r_lo < a.Tq ? *reinterpret_cast<const uint32_t*>(p_lo) : 0u;
+      qf[ks][1] = r_hi < a.Tq ? *reinterpret_cast<const uint32_t*>(p_hi) : 0u;
+      qf[ks][2] = r_lo < a.Tq ? *reinterpret_cast<const uint32_t*>(p_lo + 8) : 0u;
+      qf[ks][3] = r_hi < a.Tq ? *reinterpret_cast<const uint32_t*>(p_hi + 8) : 0u;
+    }
   }
 
   float o[NT][4];
@@ -224,14 +239,23 @@ int attention_tc_launch(const tcavp_attn_args& a, cudaStream_t stream) {
   auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
   if (!al16(a.q) || !al16(a.k) || !al16(a.v) || !al16(a.out)) return 1;
   if (a.q_sb % 8 || a.q_st % 8 || a.k_sb % 8 || a.k_st % 8 || a.v_sb % 8 || a.v_st % 8 || a.o_sb % 2 || a.o_st % 2) return 1;
-  const int tk_pad = (a.Tk + fa::KB - 1) / fa::KB * fa::KB;
+  auto pad_to = [](int n, int m) { return (n + m - 1) / m * m; };
+  const int kb = a.Tk <= 16 ? 16 : (pad_to(a.Tk, 48) < pad_to(a.Tk, 64) ? 48 : 64);   // keys per iteration: fewest dead keys
+  const int tk_pad = pad_to(a.Tk, kb);
+  const int tq_pad = a.dh >= 128 ? 0 : pad_to(a.Tq, 16);   // dh 128: K + V + Q would leave room for one CTA per SM only
   const int warps = ((a.Tq + 15) / 16 + 1) / 2;                                // every warp owns a pair of 16-row slabs (<= 8 warps)
-  const size_t smem = (size_t)2 * tk_pad * (a.dh + fa::PAD) * 2 + (size_t)tk_pad * 4 + (size_t)(tk_pad / fa::KB) * 4;
+  const size_t smem = (size_t)(2 * tk_pad + tq_pad) * (a.dh + fa::PAD) * 2 + (size_t)tk_pad * 4 + (size_t)(tk_pad / kb) * 4;
   const dim3 grid(a.B * a.H);
-#define TCAVP_FLASH(DH, MAXT, MINB)                                                                                         \
-  do {                                                                                                                      \
-    TCAVP_CUDA(cudaFuncSetAttribute(fa::attn_flash_kernel<DH, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    fa::attn_flash_kernel<DH, MAXT, MINB><<<grid, warps * 32, smem, stream>>>(a, tk_pad);                                    \
+#define TCAVP_FLASH_KB(DH, MAXT, MINB, KB_)                                                                                       \
+  do {                                                                                                                            \
+    TCAVP_CUDA(cudaFuncSetAttribute(fa::attn_flash_kernel<DH, MAXT, MINB, KB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    fa::attn_flash_kernel<DH, MAXT, MINB, KB_><<<grid, warps * 32, smem, stream>>>(a, tk_pad, tq_pad);                              \
+  } while (0)
+#define TCAVP_FLASH(DH, MAXT, MINB)                          \
+  do {                                                       \
+    if (kb == 16) TCAVP_FLASH_KB(DH, MAXT, MINB, 16);        \
+    else if (kb == 48) TCAVP_FLASH_KB(DH, MAXT, MINB, 48);   \
+    else TCAVP_FLASH_KB(DH, MAXT, MINB, 64);                 \
   } while (0)
   if (a.dh == 64) {
     if (warps <= 5) TCAVP_FLASH(64, 160, 3);   // L <= 160: three CTAs per SM
@@ -247,6 +271,7 @@ int attention_tc_launch(const tcavp_attn_args& a, cudaStream_t stream) {
     TCAVP_FLASH(16, 256, 2);
   }
 #undef TCAVP_FLASH
+#undef TCAVP_FLASH_KB
   return check_launch("attn_flash_kernel");
 }
 

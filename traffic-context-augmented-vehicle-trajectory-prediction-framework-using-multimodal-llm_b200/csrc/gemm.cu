@@ -144,6 +144,18 @@ __device__ __forceinline__ float swiglu_f(float g, float u) {
   return __fdividef(g * u, 1.f + ex2_approx(-1.4426950408889634f * g));
 }
 
+// 256-bit global accesses (sm_100): one full 32-byte sector per lane per instruction.
+__device__ __forceinline__ void stg256(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
+               "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void ldg256(const void* p, uint32_t (&v)[8]) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p));
+}
+
 enum { EPI_VEC_OUT = 1, EPI_VEC_RES = 2, EPI_VEC_BIAS = 4,
        DBG_NO_TMA = 16, DBG_NO_MMA = 32, DBG_NO_EPI = 64 };   // TCAVP_GEMM_DEBUG: ablation switches for profiling (results are garbage)
 
@@ -205,19 +217,18 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueParams& p, int m, i
   if (p.residual) {
     if ((flags & EPI_VEC_RES) && full) {
       if (p.res_dtype == TCAVP_BF16) {
-        const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + (size_t)mo * p.ldr + n0);
-        uint4 u[4];
+        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + (size_t)mo * p.ldr + n0;
+        uint32_t u[2][8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (q * 8 < cnt) u[q] = rp[q];
+        for (int q = 0; q < 2; ++q)
+          if (q * 16 < cnt) ldg256(rp + q * 16, u[q]);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (q * 8 < cnt) {
-            const uint32_t w[4] = {u[q].x, u[q].y, u[q].z, u[q].w};
+        for (int q = 0; q < 2; ++q) {
+          if (q * 16 < cnt) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {     // bf16 -> fp32 is a 16-bit shift
-              o[q * 8 + 2 * e] += __uint_as_float(w[e] << 16);
-              o[q * 8 + 2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+            for (int e = 0; e < 8; ++e) {     // bf16 -> fp32 is a 16-bit shift
+              o[q * 16 + 2 * e] += __uint_as_float(u[q][e] << 16);
+              o[q * 16 + 2 * e + 1] += __uint_as_float(u[q][e] & 0xffff0000u);
             }
           }
         }
@@ -239,23 +250,27 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueParams& p, int m, i
   }
   if ((flags & EPI_VEC_OUT) && full) {
     if (p.out_dtype == TCAVP_BF16) {
-      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)mo * p.ldo + n0);
+      __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)mo * p.ldo + n0;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (q * 8 < cnt) {
-          uint4 u;
-          u.x = pack_bf16(o[q * 8], o[q * 8 + 1]);
-          u.y = pack_bf16(o[q * 8 + 2], o[q * 8 + 3]);
-          u.z = pack_bf16(o[q * 8 + 4], o[q * 8 + 5]);
-          u.w = pack_bf16(o[q * 8 + 6], o[q * 8 + 7]);
-          op[q] = u;
+      for (int q = 0; q < 2; ++q) {
+        if (q * 16 < cnt) {
+          uint32_t u[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) u[e] = pack_bf16(o[q * 16 + 2 * e], o[q * 16 + 2 * e + 1]);
+          stg256(op + q * 16, u);
         }
       }
     } else {
-      float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)mo * p.ldo + n0);
+      float* op = reinterpret_cast<float*>(p.out) + (size_t)mo * p.ldo + n0;
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        if (q * 4 < cnt) op[q] = make_float4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
+      for (int q = 0; q < 4; ++q) {
+        if (q * 8 < cnt) {
+          uint32_t u[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) u[e] = __float_as_uint(o[q * 8 + e]);
+          stg256(op + q * 8, u);
+        }
+      }
     }
   } else {
 #pragma unroll
@@ -672,8 +687,8 @@ static int launch_tc(const tcavp_gemm_args& a, const EpilogueParams& ep, cudaStr
   const int grid = (units < max_clusters ? units : max_clusters) * CM;
   const size_t osz = ep.out_dtype == TCAVP_BF16 ? 2 : 4, rsz = ep.res_dtype == TCAVP_BF16 ? 2 : 4;
   int flags = 0;
-  if (((size_t)ep.ldo * osz) % 16 == 0 && (reinterpret_cast<uintptr_t>(ep.out) % 16) == 0) flags |= EPI_VEC_OUT;
-  if (ep.residual && ((size_t)ep.ldr * rsz) % 16 == 0 && (reinterpret_cast<uintptr_t>(ep.residual) % 16) == 0) flags |= EPI_VEC_RES;
+  if (((size_t)ep.ldo * osz) % 32 == 0 && (reinterpret_cast<uintptr_t>(ep.out) % 32) == 0) flags |= EPI_VEC_OUT;
+  if (ep.residual && ((size_t)ep.ldr * rsz) % 32 == 0 && (reinterpret_cast<uintptr_t>(ep.residual) % 32) == 0) flags |= EPI_VEC_RES;
   if (ep.bias && (reinterpret_cast<uintptr_t>(ep.bias) % 16) == 0) flags |= EPI_VEC_BIAS;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
@@ -706,8 +721,8 @@ static int launch_tc_pair(const tcavp_gemm_args& a, const EpilogueParams& ep, cu
   const int grid = (units < max_pairs ? units : max_pairs) * 2;
   const size_t osz = ep.out_dtype == TCAVP_BF16 ? 2 : 4, rsz = ep.res_dtype == TCAVP_BF16 ? 2 : 4;
   int flags = 0;
-  if (((size_t)ep.ldo * osz) % 16 == 0 && (reinterpret_cast<uintptr_t>(ep.out) % 16) == 0) flags |= EPI_VEC_OUT;
-  if (ep.residual && ((size_t)ep.ldr * rsz) % 16 == 0 && (reinterpret_cast<uintptr_t>(ep.residual) % 16) == 0) flags |= EPI_VEC_RES;
+  if (((size_t)ep.ldo * osz) % 32 == 0 && (reinterpret_cast<uintptr_t>(ep.out) % 32) == 0) flags |= EPI_VEC_OUT;
+  if (ep.residual && ((size_t)ep.ldr * rsz) % 32 == 0 && (reinterpret_cast<uintptr_t>(ep.residual) % 32) == 0) flags |= EPI_VEC_RES;
   if (ep.bias && (reinterpret_cast<uintptr_t>(ep.bias) % 16) == 0) flags |= EPI_VEC_BIAS;
   if (const char* e = getenv("TCAVP_GEMM_DEBUG")) flags |= atoi(e) & (DBG_NO_TMA | DBG_NO_MMA | DBG_NO_EPI);
   cudaLaunchConfig_t cfg = {};
