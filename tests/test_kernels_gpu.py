@@ -130,6 +130,9 @@ ATTN_CASES = [
     (3, 2, 2, 15, 15, 32, False, False),    # LTSF attn block
     (2, 2, 2, 25, 144, 384, False, False),  # LTSF cross-attn, H=768
     (1, 2, 2, 25, 40, 2048, False, False),  # LTSF cross-attn, H=4096
+    (3, 2, 2, 50, 144, 384, False, True),   # LTSF cross-attn, 50-step horizon (cfg5), with a key mask incl. an empty row
+    (2, 2, 2, 64, 250, 384, False, False),  # widest supported few-query shape
+    (2, 2, 2, 12, 30, 384, False, False),   # fewer queries than one padded m-tile pair
     (2, 12, 12, 144, 144, 64, True, True),  # LLM 768-class
     (2, 4, 2, 40, 40, 32, True, True),      # tiny GQA
     (1, 8, 2, 70, 70, 128, True, True),     # 7B-style head_dim with GQA

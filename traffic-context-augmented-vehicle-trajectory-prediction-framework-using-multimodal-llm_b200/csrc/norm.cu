@@ -112,6 +112,73 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* x, const voi
   }
 }
 
+// Register-resident LayerNorm for rows of <= G * NV * 8 elements: G lanes share a row (32 / G rows per warp), every lane
+// keeps NV 8-element vectors, so the row is read ONCE and narrow rows (d_model = 64: G = 8) still use all 32 lanes.
+template <int G, int NV>
+__global__ void __launch_bounds__(256) layernorm_reg_kernel(const void* __restrict__ x, const void* __restrict__ res,
+                                                            const float* __restrict__ w, const float* __restrict__ b,
+                                                            void* __restrict__ out, int rows, int cols, float eps, int in_dtype,
+                                                            int out_dtype, int gi, int go, int off, const float* __restrict__ rowvec) {
+  constexpr int RPW = 32 / G;
+  const int lane = threadIdx.x & 31, sub = lane % G;
+  const int row = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / G;
+  const bool live = row < rows;
+  const size_t base = (size_t)(live ? row : 0) * cols;
+  float v[NV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * G + sub) * 8;
+    if (live && c < cols) {
+      load8(x, base + c, in_dtype, v[i]);
+      if (res) {
+        float r[8];
+        load8(res, base + c, in_dtype, r);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[i][e] += r[e];
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += v[i][e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[i][e] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / cols;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if ((i * G + sub) * 8 < cols) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) q += (v[i][e] - mean) * (v[i][e] - mean);
+    }
+  }
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / cols + eps);
+  if (!live) return;
+  const size_t obase = (size_t)remap_row(gi, go, off, row) * cols;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * G + sub) * 8;
+    if (c < cols) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + c)), w1 = __ldg(reinterpret_cast<const float4*>(w + c + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + c)), b1 = __ldg(reinterpret_cast<const float4*>(b + c + 4));
+      const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float o8[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        o8[e] = (v[i][e] - mean) * rstd * ww[e] + bb[e];
+        if (rowvec) o8[e] += __ldg(rowvec + c + e);
+      }
+      store8(out, obase + c, out_dtype, o8);
+    }
+  }
+}
+
 template <bool VEC>
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const void* __restrict__ x, const float* __restrict__ w,
                                                       void* __restrict__ out, int rows, int cols, int ldi, int ldo, float eps,
@@ -198,7 +265,22 @@ extern "C" int tcavp_layernorm(const void* x, const void* residual, const float*
                    aligned_rows(out, cols, out_dtype);
   const int wpb = 8;
   const int grid = (rows + wpb - 1) / wpb;
-  if (vec)
+  const bool wb_al = reinterpret_cast<uintptr_t>(w) % 16 == 0 && reinterpret_cast<uintptr_t>(b) % 16 == 0;
+  if (vec && wb_al && cols <= 1024) {
+#define TCAVP_LN_REG(G, NV)                                                                                                         \
+  do {                                                                                                                              \
+    const int rpb = wpb * (32 / G);                                                                                                 \
+    layernorm_reg_kernel<G, NV><<<(rows + rpb - 1) / rpb, wpb * 32, 0, stream>>>(x, residual, w, b, out, rows, cols, eps, in_dtype, \
+                                                                               out_dtype, remap_gi, remap_go, remap_off, rowvec); \
+  } while (0)
+    if (cols <= 64) TCAVP_LN_REG(8, 1);
+    else if (cols <= 128) TCAVP_LN_REG(16, 1);
+    else if (cols <= 256) TCAVP_LN_REG(32, 1);
+    else if (cols <= 512) TCAVP_LN_REG(32, 2);
+    else if (cols <= 768) TCAVP_LN_REG(32, 3);
+    else TCAVP_LN_REG(32, 4);
+#undef TCAVP_LN_REG
+  } else if (vec)
     layernorm_kernel<true><<<grid, wpb * 32, 0, stream>>>(x, residual, w, b, out, rows, cols, eps, in_dtype, out_dtype, remap_gi, remap_go, remap_off, rowvec);
   else
     layernorm_kernel<false><<<grid, wpb * 32, 0, stream>>>(x, residual, w, b, out, rows, cols, eps, in_dtype, out_dtype, remap_gi, remap_go, remap_off, rowvec);

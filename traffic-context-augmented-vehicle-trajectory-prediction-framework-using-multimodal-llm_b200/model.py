@@ -406,8 +406,11 @@ class MultiModalTrajectoryModel(nn.Module):
         return _FineTuneStep.apply(eng, inputs, *[p for _, p in eng.params])
 
     @torch.no_grad()
-    def predict_with_metrics(self, x, vision_embs, lane_polygon_batch, lane_polygon_len, y, norm_stat, input_ids, attention_mask):
+    def predict_with_metrics(self, x, vision_embs, lane_polygon_batch, lane_polygon_len, y, norm_stat, input_ids, attention_mask,
+                             final_hidden=None):
         """forward + the reference's test-loop reduction (train.py:1302-1322) in one pass.
-        Returns dict(decoded, loss, sum_ade, sum_fde, ade[B], fde[B]) — all device tensors, no host sync."""
+        Returns dict(decoded, loss, sum_ade, sum_fde, ade[B], fde[B]) — all device tensors, no host sync.
+        `final_hidden` (B, L, H): precomputed backbone output — the frozen-backbone path of
+        scripts/ablation_study_without_lora.py (encoder + fusion only; vision / token inputs are then ignored)."""
         return self.engine().forward(x, vision_embs, lane_polygon_batch, lane_polygon_len, input_ids, attention_mask, y=y,
-                                     norm_stat=norm_stat)
+                                     norm_stat=norm_stat, final_hidden=final_hidden)

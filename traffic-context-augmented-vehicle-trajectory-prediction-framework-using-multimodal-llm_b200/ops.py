@@ -180,7 +180,7 @@ def attention(q, k, v, out, *, B, H, Hkv, Tq, Tk, dh, q_strides, k_strides, v_st
         a.key_mask = key_mask.data_ptr()
     if a.dtype == BF16 and dh in (16, 32, 64, 96, 128) and max(Tq, Tk) <= 256:
         kern = f"attn_flash_kernel[dh{dh},q{Tq},k{Tk}]"
-    elif a.dtype == BF16 and dh > 128 and dh % 64 == 0 and Tq <= 32 and Tk <= 256 and not causal:
+    elif a.dtype == BF16 and dh > 128 and dh % 64 == 0 and Tq <= 64 and Tk <= 256 and not causal:
         kern = "attn_x_kernel"
     elif dh in (16, 32) and Tk <= 128:
         kern = f"attn_row_kernel[dh{dh},q{Tq},k{Tk}]"
@@ -196,7 +196,7 @@ def layernorm(x, w, b, out, *, residual=None, eps=1e-5, remap=(0, 0, 0), rowvec=
     _need_cuda(x, w, b, out, residual, rowvec)
     rows = x.numel() // x.shape[-1] if rows is None else rows
     cols = x.shape[-1] if cols is None else cols
-    with _Timed("layernorm_kernel"):
+    with _Timed("layernorm_kernel", 0.0, float(rows * cols * (x.element_size() + out.element_size() + (residual.element_size() if residual is not None else 0)))):
         _lib.check(_lib.load().tcavp_layernorm(_p(x), _p(residual), _p(w), _p(b), _p(out), rows, cols, c_float(eps), dt(x), dt(out),
                                            remap[0], remap[1], remap[2], _p(rowvec), _stream()), "tcavp_layernorm")
     return out
@@ -241,14 +241,14 @@ def embed_text(ids, attn_mask, embed, text_mod, fused, mask_out, *, B, L_text, n
     _need_cuda(ids, attn_mask, embed, text_mod, fused, mask_out)
     if ids.dtype != torch.int64 or (attn_mask is not None and attn_mask.dtype != torch.int64):
         raise TypeError("embed_text: ids / attention_mask must be int64")
-    with _Timed("embed_text_kernel"):
+    with _Timed("embed_text_kernel", 0.0, float(B * L_text * (H * (embed.element_size() + fused.element_size()) + 16))):
         _lib.check(_lib.load().tcavp_embed_text(_p(ids), _p(attn_mask), _p(embed), dt(embed), _p(text_mod), _p(fused), dt(fused),
                                             _p(mask_out), B, L_text, n_img, H, embed.shape[0], _stream()), "tcavp_embed_text")
 
 
 def add_rowvec(x, rowvec, out, *, rows, cols, remap=(0, 0, 0)):
     _need_cuda(x, rowvec, out)
-    with _Timed("add_rowvec_kernel"):
+    with _Timed("add_rowvec_kernel", 0.0, float(rows * cols * (x.element_size() + out.element_size()))):
         _lib.check(_lib.load().tcavp_add_rowvec(_p(x), _p(rowvec), _p(out), rows, cols, dt(x), dt(out), remap[0], remap[1], remap[2],
                                             _stream()), "tcavp_add_rowvec")
     return out
@@ -256,7 +256,7 @@ def add_rowvec(x, rowvec, out, *, rows, cols, remap=(0, 0, 0)):
 
 def cast(x, out, *, rows, cols, ldi=None, ldo=None, in_row_mod=0):
     _need_cuda(x, out)
-    with _Timed("cast_kernel"):
+    with _Timed("cast_kernel", 0.0, float(rows * cols * (x.element_size() + out.element_size()))):
         _lib.check(_lib.load().tcavp_cast(_p(x), cols if ldi is None else ldi, dt(x), _p(out), cols if ldo is None else ldo, dt(out),
                                       rows, cols, in_row_mod, _stream()), "tcavp_cast")
     return out
@@ -264,21 +264,21 @@ def cast(x, out, *, rows, cols, ldi=None, ldo=None, in_row_mod=0):
 
 def poly_embed(polygon, lens, w, bias, pos, out, key_mask, *, B, P, D):
     _need_cuda(polygon, lens, w, bias, pos, out, key_mask)
-    with _Timed("poly_embed_kernel"):
+    with _Timed("poly_embed_kernel", 0.0, float(B * P * (8 + 4 + D * out.element_size()))):
         _lib.check(_lib.load().tcavp_poly_embed(_p(polygon), _p(lens), _p(w), _p(bias), _p(pos), _p(out), dt(out), _p(key_mask), B, P, D,
                                             _stream()), "tcavp_poly_embed")
 
 
 def masked_mean(x, lens, out, *, B, P, D):
     _need_cuda(x, lens, out)
-    with _Timed("masked_mean_kernel"):
+    with _Timed("masked_mean_kernel", 0.0, float(B * P * D * x.element_size() + B * D * out.element_size())):
         _lib.check(_lib.load().tcavp_masked_mean(_p(x), dt(x), _p(lens), _p(out), dt(out), B, P, D, _stream()), "tcavp_masked_mean")
     return out
 
 
 def ltsf_encode(x, wt, bt, we, be, pos, enc, *, B, F, C, T_in):
     _need_cuda(x, wt, bt, we, be, pos, enc)
-    with _Timed("ltsf_encode_kernel"):
+    with _Timed("ltsf_encode_kernel", 0.0, float(B * F * T_in * 4 + B * T_in * C * enc.element_size())):
         _lib.check(_lib.load().tcavp_ltsf_encode(_p(x), _p(wt), _p(bt), _p(we), _p(be), _p(pos), _p(enc), dt(enc), B, F, C, T_in,
                                              _stream()), "tcavp_ltsf_encode")
     return enc
@@ -286,7 +286,7 @@ def ltsf_encode(x, wt, bt, we, be, pos, enc, *, B, F, C, T_in):
 
 def nlinear_decode(enc, wd, bd, lane_adj, dec, *, B, C, T_in, T_out):
     _need_cuda(enc, wd, bd, lane_adj, dec)
-    with _Timed("nlinear_decode_kernel"):
+    with _Timed("nlinear_decode_kernel", 0.0, float(B * T_in * C * enc.element_size() + B * T_out * C * (dec.element_size() + (lane_adj.element_size() if lane_adj is not None else 0)))):
         _lib.check(_lib.load().tcavp_nlinear_decode(_p(enc), dt(enc), _p(wd), _p(bd), _p(lane_adj), 0 if lane_adj is None else dt(lane_adj),
                                                 _p(dec), dt(dec), B, C, T_in, T_out, _stream()), "tcavp_nlinear_decode")
     return dec
@@ -295,7 +295,7 @@ def nlinear_decode(enc, wd, bd, lane_adj, dec, *, B, C, T_in, T_out):
 def fusion_head(fused, ln_w, ln_b, w1, b1, w2, b2, wo, bo, x, decoded, *, y=None, norm_stat=None, metrics=None, per_scene=None,
                 B, C, T_in, T_out):
     _need_cuda(fused, x, decoded, y, norm_stat, metrics, per_scene)
-    with _Timed("fusion_head_kernel"):
+    with _Timed("fusion_head_kernel", 0.0, float(B * T_out * C * fused.element_size() + B * 2 * T_out * 4 * (2 if y is not None else 1) + B * (2 * T_in * 4 + 16))):
         _lib.check(_lib.load().tcavp_fusion_head(_p(fused), dt(fused), _p(ln_w), _p(ln_b), _p(w1), _p(b1), _p(w2), _p(b2), _p(wo), _p(bo),
                                              _p(x), _p(decoded), _p(y), _p(norm_stat), _p(metrics), _p(per_scene), B, C, T_in, T_out,
                                              _stream()), "tcavp_fusion_head")
@@ -304,7 +304,7 @@ def fusion_head(fused, ln_w, ln_b, w1, b1, w2, b2, wo, bo, x, decoded, *, y=None
 
 def traj_metrics(decoded, y, norm_stat, metrics, per_scene, *, B, T_out):
     _need_cuda(decoded, y, norm_stat, metrics, per_scene)
-    with _Timed("traj_metrics_kernel"):
+    with _Timed("traj_metrics_kernel", 0.0, float(B * 2 * T_out * 4 * 2 + B * 24)):
         _lib.check(_lib.load().tcavp_traj_metrics(_p(decoded), _p(y), _p(norm_stat), _p(metrics), _p(per_scene), B, T_out, _stream()),
                "tcavp_traj_metrics")
 
