@@ -251,6 +251,12 @@ int tcavp_traj_loss_bwd(const float* decoded, const float* y, const float* norm_
  * (row_scale optional: the RMSNorm rstd of the folded-norm form). */
 int tcavp_skinny_dw(const void* Y, int ldy, int y_dtype, const void* Z, int ldz, int z_dtype, const float* row_scale, float* out, int ldo,
                     long long M, int N, int J, tcavp_stream_t stream);
+/* Weight gradient of a linear map (autograd of F.linear, reference loop im_kim_train_GRN.py:1039):
+ * out[n][k] += sum_m dY[m][n] * X[m][k], out fp32 [N, ldo] (caller zero-initialises; M-slices are combined with atomics), dY / X in
+ * their row-major [M, *] layouts (fp32 or bf16, may differ) — no transposed copies.  fp32 FFMA: meant for the narrow fp32 layers
+ * (temporal encoder / decoder, fusion head, polygon input projection); wide bf16 layers go through tcavp_transpose + tcavp_gemm. */
+int tcavp_dw(const void* dY, int lddy, int dy_dtype, const void* X, int ldx, int x_dtype, float* out, int ldo, long long M, int N, int K,
+             tcavp_stream_t stream);
 /* Backward of tcavp_attention (probabilities recomputed; any head_dim; Tk <= 768).  dq has the dtype/layout convention of q;
  * dk / dv are fp32 (caller zeroes them: the generic kernel accumulates with atomics because query blocks and GQA groups add
  * into the same keys).  When args->out / o_sb / o_st hold the FORWARD OUTPUT and the shape is bf16, H == Hkv, head_dim in

@@ -158,3 +158,33 @@ def test_adamw_steps_reduce_the_loss_and_match_torch_optimizer(lib_built):
             # so the check is on the fraction of elements that moved differently, not on every element
             bad = ((a - b).abs() > 1e-5 + 1e-3 * b.abs()).float().mean()
             assert float(bad) < 2e-3, (n, float(bad))
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_finetuner_matches_the_reference_loop(lib_built, graph):
+    """tcavp_b200.FineTuner (gradients written straight into the flat bucket, optional CUDA-graph replay of forward+backward,
+    fused AdamW) against the reference's loop — forward, loss.backward(), torch.optim.AdamW.step() (im_kim_train_GRN.py:1028-1040)."""
+    fix = load_golden("tiny_b5_grads")
+    i = fix["inputs"]
+    m, m_ref = _model(fix, "fp32"), _model(fix, "fp32")
+    opt = torch.optim.AdamW([p for p in m_ref.parameters() if p.requires_grad], lr=5e-4, weight_decay=1e-4)
+    import warnings
+    warnings.simplefilter("ignore")
+    ft = T.FineTuner(m, lr=5e-4, weight_decay=1e-4, use_cuda_graph=graph)
+    ctx = ["ctx"] * i["x"].shape[0]
+    for step in range(3):
+        loss, dec = ft.step(i["x"].cuda(), i["vision"].cuda(), ctx, i["polygon"].cuda(), i["poly_len"], i["y"].cuda(), i["norm_stat"],
+                            i["input_ids"].cuda(), i["attention_mask"].cuda())
+        opt.zero_grad()
+        l2, d2 = _step(m_ref, i)
+        l2.backward()
+        if step == 0:      # same weights on both sides: the flat-bucket gradients are the autograd gradients
+            torch.cuda.synchronize()
+            for (n, p), v in zip(m.trainable_named_parameters(), ft.bucket.views):
+                g = dict(m_ref.named_parameters())[n].grad
+                if not n.startswith(ILL):
+                    torch.testing.assert_close(v, g, rtol=2e-3, atol=1e-6 + 1e-4 * float(g.abs().max()), msg=lambda s, n=n: f"{n}: {s}")
+        opt.step()
+        assert abs(float(l2) - float(loss)) <= 2e-4 * abs(float(loss)), (step, float(l2), float(loss))
+        torch.testing.assert_close(dec, d2, rtol=1e-3, atol=1e-3)
+    assert ft.launches_per_step > 100

@@ -351,6 +351,63 @@ __global__ void __launch_bounds__(128) skinny_dw_kernel(const void* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
+// Weight gradient of a linear map without operand transposes: out[n][k] += sum_m dY[m][n] * X[m][k]   (fp32 FFMA).
+// Both operands are read in their natural row-major [M, *] layout (rows of dY / X are coalesced over n / k), a CTA owns a
+// 64 x 64 output tile and one slice of the M rows (grid.z splits M so small outputs still fill the GPU), partial tiles are
+// combined with fp32 atomics into the zero-initialised output.  Used for the fp32 temporal / fusion / polygon layers, whose
+// outputs are at most a few hundred rows wide while M = scenes x positions is large.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dw_simt_kernel(const void* __restrict__ dY, int lddy, int dy_dtype, const void* __restrict__ X, int ldx,
+                                                      int x_dtype, float* __restrict__ out, int ldo, long long M, int N, int K, int m_per_block) {
+  constexpr int T = 64, MB = 16;
+  __shared__ float sy[MB][T + 4];
+  __shared__ float sx[MB][T + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int n0 = blockIdx.y * T, k0 = blockIdx.x * T;
+  const long long m0 = (long long)blockIdx.z * m_per_block;
+  long long m1 = m0 + m_per_block;
+  if (m1 > M) m1 = M;
+  float acc[4][4] = {};
+  for (long long mb = m0; mb < m1; mb += MB) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = threadIdx.x + i * 256;     // 0..1023
+      const int r = e >> 6, c = e & 63;        // row of the M slice, column of the tile (consecutive lanes -> consecutive columns)
+      const long long m = mb + r;
+      sy[r][c] = (m < m1 && n0 + c < N) ? load_as_f(dY, (size_t)m * lddy + n0 + c, dy_dtype) : 0.f;
+      sx[r][c] = (m < m1 && k0 + c < K) ? load_as_f(X, (size_t)m * ldx + k0 + c, x_dtype) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < MB; ++r) {
+      float a[4], w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sy[r][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[j] = sx[r][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + ty * 4 + i;
+    if (n >= N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx * 4 + j;
+      if (k < K) {
+        if (gridDim.z == 1) out[(size_t)n * ldo + k] += acc[i][j];
+        else atomicAdd(out + (size_t)n * ldo + k, acc[i][j]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Attention backward.  One CTA per (batch, head, 16-query block); probabilities are recomputed (no saved
 // statistics), head_dim is streamed in chunks so any width works (LTSF cross-attention: dh = H/2).
 //   P = softmax(scale * Q K^T + mask);  dP = dO V^T;  D_i = sum_j P_ij dP_ij;  dS = scale * P o (dP - D)
@@ -699,6 +756,24 @@ extern "C" int tcavp_skinny_dw(const void* Y, int ldy, int y_dtype, const void* 
   else if (J <= 16) skinny_dw_kernel<16><<<grid, 128, 0, STREAM(stream)>>>(Y, ldy, y_dtype, Z, ldz, z_dtype, row_scale, out, ldo, M, N, J, (int)mper);
   else skinny_dw_kernel<32><<<grid, 128, 0, STREAM(stream)>>>(Y, ldy, y_dtype, Z, ldz, z_dtype, row_scale, out, ldo, M, N, J, (int)mper);
   return check_launch("skinny_dw_kernel");
+}
+
+extern "C" int tcavp_dw(const void* dY, int lddy, int dy_dtype, const void* X, int ldx, int x_dtype, float* out, int ldo, long long M, int N,
+                        int K, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(M >= 0 && N > 0 && K > 0 && lddy >= N && ldx >= K && ldo >= K, "tcavp_dw: bad shape M=%lld N=%d K=%d", M, N, K);
+  if (M == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(dY && X && out && DT_OK(dy_dtype) && DT_OK(x_dtype), "tcavp_dw: bad pointer/dtype");
+  const int tn = (N + 63) / 64, tk = (K + 63) / 64;
+  long long splits = ((long long)sm_count() * 4) / ((long long)tn * tk);
+  if (splits < 1) splits = 1;
+  long long mper = (M + splits - 1) / splits;
+  mper = (mper + 15) / 16 * 16;
+  if (mper < 64) mper = 64;
+  const long long nz = (M + mper - 1) / mper;
+  TCAVP_REQUIRE(nz <= 65535 && tn <= 65535, "tcavp_dw: grid too large");
+  dim3 grid(tk, tn, (unsigned)nz);
+  dw_simt_kernel<<<grid, 256, 0, STREAM(stream)>>>(dY, lddy, dy_dtype, X, ldx, x_dtype, out, ldo, M, N, K, (int)mper);
+  return check_launch("dw_simt_kernel");
 }
 
 extern "C" int tcavp_attention_bwd(const tcavp_attn_args* a, const void* dout, long long do_sb, long long do_st, void* dq, long long dq_sb,

@@ -147,7 +147,10 @@ class Engine:
         wd = torch.stack([l.weight.detach() for l in d.decoder_linears]).float()                    # (C, To, s)
         bd = torch.stack([l.bias.detach() for l in d.decoder_linears]).float()
         # (c,t)-flat -> (t,c)-flat permutation of the 64*T_out feature axis (lane_fc rows, post_mlp.0 cols, post_mlp.3 rows)
-        perm = (torch.arange(C)[None, :] * To + torch.arange(To)[:, None]).reshape(-1).to(d.lane_fc.weight.device)
+        pdev = d.lane_fc.weight.device
+        if getattr(self, "_tc_perm", None) is None or self._tc_perm.device != pdev:     # built once: re-packing must stay capturable
+            self._tc_perm = (torch.arange(C)[None, :] * To + torch.arange(To)[:, None]).reshape(-1).to(pdev)
+        perm = self._tc_perm
         self.lt = dict(
             wt=_f32(lt.token_proj.weight[:, :, 0], dev), bt=_f32(lt.token_proj.bias, dev),
             we=we.permute(1, 2, 0).contiguous().to(dev), be=be.t().contiguous().to(dev),

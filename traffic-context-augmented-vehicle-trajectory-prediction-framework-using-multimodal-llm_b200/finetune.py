@@ -3,9 +3,11 @@ AdamW.step(), wrapped in DistributedDataParallel, train.py:1127-1132).
 
 `FineTuner` keeps every trainable tensor in ONE flat fp32 parameter buffer (the nn.Parameters are re-pointed to views of
 it), their gradients in one flat buffer (`distributed.FlatGradBucket`) and the AdamW moments in two more, so a step is:
-forward + hand-written backward (train_engine.py) -> ONE all-reduce of the trainable gradients over NCCL (LoRA / Q-Former /
-encoder / fusion only; frozen base weights never move) -> ONE fused AdamW launch (tcavp_adamw).  The reference's own loop
-(torch.optim.AdamW + DDP) also works unchanged on the same model — this class is the faster equivalent."""
+forward + hand-written backward (train_engine.py, gradients written straight into their slices of the flat buffer) -> ONE
+all-reduce of the trainable gradients over NCCL (LoRA / Q-Former / encoder / fusion only; frozen base weights never move)
+-> ONE fused AdamW launch (tcavp_adamw).  Forward + backward of a fixed batch shape are captured once in a CUDA graph and
+replayed (one host call instead of ~900 kernel launches per step).  The reference's own loop (torch.optim.AdamW + DDP
++ loss.backward()) also works unchanged on the same model — this class is the faster equivalent."""
 import torch
 import torch.distributed as dist
 
@@ -14,10 +16,12 @@ from .distributed import FlatGradBucket
 
 
 class FineTuner:
-    def __init__(self, model, lr=5e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, group=None):
+    def __init__(self, model, lr=5e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, group=None, use_cuda_graph=True):
         self.model, self.group = model, group
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
-        self.params = [p for _, p in model.trainable_named_parameters()]
+        named = model.trainable_named_parameters()
+        self.names = [n for n, _ in named]
+        self.params = [p for _, p in named]
         if not self.params:
             raise ValueError("no trainable parameters")
         if any(p.dtype != torch.float32 for p in self.params):
@@ -33,23 +37,83 @@ class FineTuner:
                 p.data = v
                 off += p.numel()
         self.bucket = FlatGradBucket(self.params)
+        self.targets = dict(zip(self.names, self.bucket.views))
         self.exp_avg = torch.zeros_like(self.flat_p)
         self.exp_avg_sq = torch.zeros_like(self.flat_p)
         self.steps = 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.use_cuda_graph = use_cuda_graph
+        self._graph = None
+        self._static = None
+        self._sig = None
+        self.launches_per_step = 0    # libtcavp launches of one forward + backward (captured launches are replayed, not re-counted)
 
     @property
     def payload_bytes(self):
         """Bytes exchanged by the one all-reduce of a step."""
         return self.bucket.flat.numel() * self.bucket.flat.element_size()
 
+    # ---- forward + backward into the flat gradient buffer (no autograd graph, no per-tensor accumulation) --------------
+    @torch.no_grad()
+    def _fwd_bwd(self, inp):
+        eng = self.model.train_engine()
+        eng.grad_targets = self.targets
+        self.bucket.flat.zero_()
+        try:
+            out = eng.train_forward(**inp)
+            grads = eng.train_backward(None)
+        finally:
+            eng.grad_targets = None
+        for name, view in self.targets.items():
+            g = grads.get(name)
+            if g is not None and g.data_ptr() != view.data_ptr():
+                view.copy_(g.reshape(view.shape))
+        return out["loss"], out["decoded"]
+
+    def _device_inputs(self, x, vision_embs, lane_polygon_batch, lane_polygon_len, y, norm_stat, input_ids, attention_mask):
+        dev = self.flat_p.device
+        lens = lane_polygon_len if torch.is_tensor(lane_polygon_len) else torch.tensor(list(lane_polygon_len), dtype=torch.int32)
+        ns = norm_stat if torch.is_tensor(norm_stat) else torch.tensor(norm_stat, dtype=torch.float32)
+        f32 = lambda t: t.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()      # noqa: E731
+        vis = vision_embs.to(dev, non_blocking=True)
+        if vis.dtype not in (torch.float32, torch.bfloat16):
+            vis = vis.float()
+        return dict(x=f32(x), vision=vis.contiguous(), polygon=f32(lane_polygon_batch), poly_len=lens.to(device=dev, dtype=torch.int32),
+                    input_ids=input_ids.to(device=dev, dtype=torch.int64).contiguous(),
+                    attention_mask=attention_mask.to(device=dev, dtype=torch.int64).contiguous(), y=f32(y), norm_stat=f32(ns).view(-1, 4))
+
+    def _run(self, inp):
+        if not self.use_cuda_graph:
+            n0 = ops.launch_count()
+            r = self._fwd_bwd(inp)
+            self.launches_per_step = ops.launch_count() - n0
+            return r
+        sig = tuple((k, tuple(v.shape), v.dtype) for k, v in inp.items())
+        if self._graph is None or sig != self._sig:
+            # static input buffers + two eager steps on a side stream (lazy packing, cudaFuncSetAttribute, allocator warm-up), then capture
+            self._static = {k: v.clone() for k, v in inp.items()}
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    self._fwd_bwd(self._static)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = ops.launch_count()
+            with torch.cuda.graph(g):
+                self._out = self._fwd_bwd(self._static)
+            self.launches_per_step = ops.launch_count() - n0
+            self._graph, self._sig = g, sig
+        for k, v in inp.items():
+            self._static[k].copy_(v, non_blocking=True)
+        self._graph.replay()
+        return self._out
+
     def step(self, x, vision_embs, context_str, lane_polygon_batch, lane_polygon_len, y, norm_stat, input_ids, attention_mask):
         """One optimisation step on this rank's shard of the batch; returns (loss, decoded) like the reference forward."""
-        self.bucket.zero_()
-        with torch.enable_grad():
-            loss, decoded = self.model(x, vision_embs, context_str, lane_polygon_batch, lane_polygon_len, y=y, norm_stat=norm_stat,
-                                       input_ids=input_ids, attention_mask=attention_mask)
-            loss.backward()
+        inp = self._device_inputs(x, vision_embs, lane_polygon_batch, lane_polygon_len, y, norm_stat, input_ids, attention_mask)
+        loss, decoded = self._run(inp)
         if self.world > 1:
             dist.all_reduce(self.bucket.flat, op=dist.ReduceOp.SUM, group=self.group)
         self.steps += 1

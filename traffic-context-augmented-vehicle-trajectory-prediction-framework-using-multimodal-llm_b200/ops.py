@@ -436,6 +436,17 @@ def skinny_dw(Y, Z, out, *, M, N, J, ldy=None, ldz=None, ldo=None, row_scale=Non
     return out
 
 
+def dw(dy, x, out, *, M, N, K, lddy=None, ldx=None, ldo=None):
+    """out[n][k] += sum_m dy[m][n] * x[m][k]   (out fp32, zero-initialised by the caller; no transposes)."""
+    _need_cuda(dy, x, out)
+    if out.dtype != torch.float32:
+        raise TypeError("dw: out must be fp32")
+    _call("tcavp_dw", "dw_simt_kernel", _p(dy), dy.stride(0) if lddy is None else lddy, dt(dy), _p(x), x.stride(0) if ldx is None else ldx, dt(x),
+          _p(out), out.stride(0) if ldo is None else ldo, _ll(M), N, K, flops=2.0 * M * N * K,
+          nbytes=float(M * (N * dy.element_size() + K * x.element_size())))
+    return out
+
+
 def attention_bwd(q, k, v, dout, dq, dk, dv, *, B, H, Hkv, Tq, Tk, dh, q_strides, k_strides, v_strides, do_strides, dq_strides,
                   dk_strides, dv_strides, scale, causal=False, key_mask=None, o=None, o_strides=None):
     """dk / dv: fp32 accumulators (zeroed by the caller).  o = the forward output (enables the tensor-core kernel)."""

@@ -11,6 +11,8 @@ inference engine (new buffers per block instead of in-place reuse, so every acti
 Gradients are produced in the reference's state_dict layout (fp32) and handed to torch through ONE autograd.Function
 (model.py), so `loss.backward(); optimizer.step()` and DistributedDataParallel hooks work unchanged.
 Dropout is treated as p = 0 (gradient parity with the reference is only defined there)."""
+import math
+
 import torch
 
 from . import ops
@@ -26,6 +28,7 @@ class TrainEngine(Engine):
         super().__init__(model, compute_dtype)
         self.model = model
         self.G = {}
+        self.grad_targets = None      # {reference parameter name: fp32 view to write its gradient into} (optional)
         self._flags()
         self._bwd_packed = False
         self._names()
@@ -89,7 +92,14 @@ class TrainEngine(Engine):
             ly["a_catT"] = ly["a_cat"].t().contiguous()
 
     def _g(self, name, shape):
-        t = torch.zeros(*shape, dtype=torch.float32, device=self.dev)
+        """Zero-initialised fp32 gradient buffer for reference parameter `name`.  When the caller registered a target view for
+        it (FineTuner: a slice of the flat all-reduce buffer, zeroed at the start of the step) the gradient is produced in
+        place and never copied."""
+        tgt = self.grad_targets.get(name) if self.grad_targets else None
+        if tgt is not None and tgt.numel() == math.prod(shape):
+            t = tgt.view(*shape)
+        else:
+            t = torch.zeros(*shape, dtype=torch.float32, device=self.dev)
         self.G[name] = t
         return t
 
@@ -108,6 +118,9 @@ class TrainEngine(Engine):
     def _dw_gemm(self, dy, x, out, *, N, K, lddy=None, ldx=None):
         """out[N, K] (fp32) = dy^T . x over the M rows; operands are transposed (and dtype-unified) explicitly."""
         M = dy.shape[0]
+        if dy.dtype == torch.float32 or x.dtype == torch.float32 or 2.0 * M * N * K < 1.5e9:
+            # narrow / fp32 layers: FFMA kernel on the row-major operands, M split over the grid (no transposed copies)
+            return ops.dw(dy, x, out, M=M, N=N, K=K, lddy=dy.stride(0) if lddy is None else lddy, ldx=x.stride(0) if ldx is None else ldx)
         Mp = _pad8(M)
         td = x.dtype
         alloc = torch.zeros if Mp != M else torch.empty
@@ -378,7 +391,9 @@ class TrainEngine(Engine):
         sq = (L * nqkv, nqkv)
         dx = ops.rmsnorm_bwd(dfh, xs_last, self._new(M, H), rows=M, cols=H, eps=m["eps"], w=m["norm"], ldx=Kx)
         wrap = self.model.mllm.llama_wrapper
-        inv_perm = torch.argsort(m["qk_perm"]) if m["fuse_rope"] else None
+        if m["fuse_rope"] and "qk_inv_perm" not in m:
+            m["qk_inv_perm"] = torch.argsort(m["qk_perm"])
+        inv_perm = m["qk_inv_perm"] if m["fuse_rope"] else None
         for i in reversed(range(len(ctxs))):
             xs, rstd1, qkv, attn, xs2, rstd2, gu, mid = ctxs[i]
             ly = m["layers"][i]
