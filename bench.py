@@ -282,8 +282,8 @@ def run_ours(args):
 
 TRAIN_WORKLOADS = {
     # name: (model preset, scenes per GPU per step, L_text)  — BASELINE.json configs[3]: LoRA fine-tune step, data parallel
-    "cfg2": ("cfg1", 256, 128),
-    "cfg3": ("cfg3", 32, 128),
+    "cfg2": ("cfg1", 512, 128),
+    "cfg3": ("cfg3", 64, 128),
 }
 
 

@@ -89,6 +89,8 @@ typedef struct tcavp_gemm_args {
   int remap_gi, remap_go, remap_off;
   const float* rope_cos_sin; int rope_L, rope_dh, rope_cols;
   const float* row_scale;
+  void* aux_out; int ld_aux;   /* SWIGLU + bf16 operands only: also store the raw (row-scaled) gate/up accumulators, interleaved
+                                  [M', N] bf16, for the backward pass (the fine-tune step stashes them; NULL otherwise) */
 } tcavp_gemm_args;
 
 int tcavp_gemm(const tcavp_gemm_args* args, tcavp_stream_t stream);
@@ -264,6 +266,13 @@ int tcavp_dw(const void* dY, int lddy, int dy_dtype, const void* X, int ldx, int
 int tcavp_attention_bwd(const tcavp_attn_args* args, const void* dout, long long do_sb, long long do_st, void* dq, long long dq_sb,
                         long long dq_st, float* dk, long long dk_sb, long long dk_st, float* dv, long long dv_sb, long long dv_st,
                         tcavp_stream_t stream);
+/* Tensor-core-only form of tcavp_attention_bwd for H == Hkv: one CTA owns every key row of its (batch, head), so dk / dv are
+ * plain stores in `dkv_dtype` (TCAVP_BF16: straight into the packed d(qkv) activation buffer — no fp32 staging, no zero-fill,
+ * no cast) with the same stride convention as k / v.  args->out must hold the forward output.  Fails (TCAVP_ERR_ARG) on shapes the
+ * tensor-core kernel does not cover; callers then use tcavp_attention_bwd. */
+int tcavp_attention_bwd_owned(const tcavp_attn_args* args, const void* dout, long long do_sb, long long do_st, void* dq, long long dq_sb,
+                              long long dq_st, void* dk, long long dk_sb, long long dk_st, void* dv, long long dv_sb, long long dv_st,
+                              int dkv_dtype, tcavp_stream_t stream);
 /* Fused AdamW over flat fp32 buffers, torch.optim.AdamW semantics (im_kim_train_GRN.py:1008); grad_scale multiplies the
  * gradient first (1/world_size after a sum all-reduce). */
 int tcavp_adamw(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1, float beta2,

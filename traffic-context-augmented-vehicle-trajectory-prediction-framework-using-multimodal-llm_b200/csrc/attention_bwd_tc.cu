@@ -43,9 +43,9 @@ __device__ __forceinline__ float ex2(float x) {
 template <int DH, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) attn_bwd_tc_kernel(tcavp_attn_args a, const __nv_bfloat16* __restrict__ dout, long long do_sb,
                                                                  long long do_st, __nv_bfloat16* __restrict__ dq, long long dq_sb,
-                                                                 long long dq_st, float* __restrict__ dk, long long dk_sb, long long dk_st,
-                                                                 float* __restrict__ dv, long long dv_sb, long long dv_st, int tq_pad,
-                                                                 int tk_pad) {
+                                                                 long long dq_st, void* __restrict__ dk, long long dk_sb, long long dk_st,
+                                                                 void* __restrict__ dv, long long dv_sb, long long dv_st, int dkv_bf16,
+                                                                 int tq_pad, int tk_pad) {
   constexpr int LDS = DH + PAD;
   constexpr int KS = DH / 16;
   constexpr int NT = DH / 8;
@@ -320,18 +320,35 @@ __global__ void __launch_bounds__(MAXT, MINB) attn_bwd_tc_kernel(tcavp_attn_args
           mma16816(ak[2 * np + 1], dsT, b2, b3);
         }
       }
-      float* gdk = dk + (size_t)b * dk_sb + (size_t)h * DH;
-      float* gdv = dv + (size_t)b * dv_sb + (size_t)h * DH;
+      if (dkv_bf16) {     // this CTA owns every key row of its head: the activation dtype is written directly (no fp32 round trip)
+        __nv_bfloat16* gdk = reinterpret_cast<__nv_bfloat16*>(dk) + (size_t)b * dk_sb + (size_t)h * DH;
+        __nv_bfloat16* gdv = reinterpret_cast<__nv_bfloat16*>(dv) + (size_t)b * dv_sb + (size_t)h * DH;
 #pragma unroll
-      for (int n = 0; n < NT; ++n) {
-        const int c = n * 8 + t4 * 2;
-        if (j_lo < a.Tk) {
-          *reinterpret_cast<float2*>(gdk + (size_t)j_lo * dk_st + c) = make_float2(ak[n][0], ak[n][1]);
-          *reinterpret_cast<float2*>(gdv + (size_t)j_lo * dv_st + c) = make_float2(av[n][0], av[n][1]);
+        for (int n = 0; n < NT; ++n) {
+          const int c = n * 8 + t4 * 2;
+          if (j_lo < a.Tk) {
+            *reinterpret_cast<uint32_t*>(gdk + (size_t)j_lo * dk_st + c) = pack2(ak[n][0], ak[n][1]);
+            *reinterpret_cast<uint32_t*>(gdv + (size_t)j_lo * dv_st + c) = pack2(av[n][0], av[n][1]);
+          }
+          if (j_hi < a.Tk) {
+            *reinterpret_cast<uint32_t*>(gdk + (size_t)j_hi * dk_st + c) = pack2(ak[n][2], ak[n][3]);
+            *reinterpret_cast<uint32_t*>(gdv + (size_t)j_hi * dv_st + c) = pack2(av[n][2], av[n][3]);
+          }
         }
-        if (j_hi < a.Tk) {
-          *reinterpret_cast<float2*>(gdk + (size_t)j_hi * dk_st + c) = make_float2(ak[n][2], ak[n][3]);
-          *reinterpret_cast<float2*>(gdv + (size_t)j_hi * dv_st + c) = make_float2(av[n][2], av[n][3]);
+      } else {
+        float* gdk = reinterpret_cast<float*>(dk) + (size_t)b * dk_sb + (size_t)h * DH;
+        float* gdv = reinterpret_cast<float*>(dv) + (size_t)b * dv_sb + (size_t)h * DH;
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+          const int c = n * 8 + t4 * 2;
+          if (j_lo < a.Tk) {
+            *reinterpret_cast<float2*>(gdk + (size_t)j_lo * dk_st + c) = make_float2(ak[n][0], ak[n][1]);
+            *reinterpret_cast<float2*>(gdv + (size_t)j_lo * dv_st + c) = make_float2(av[n][0], av[n][1]);
+          }
+          if (j_hi < a.Tk) {
+            *reinterpret_cast<float2*>(gdk + (size_t)j_hi * dk_st + c) = make_float2(ak[n][2], ak[n][3]);
+            *reinterpret_cast<float2*>(gdv + (size_t)j_hi * dv_st + c) = make_float2(av[n][2], av[n][3]);
+          }
         }
       }
     }
@@ -342,8 +359,8 @@ __global__ void __launch_bounds__(MAXT, MINB) attn_bwd_tc_kernel(tcavp_attn_args
 
 // Returns 1 when the shape is not covered (caller uses the generic SIMT kernel), <= 0 otherwise.
 int attention_bwd_tc_launch(const tcavp_attn_args& a, const void* dout, long long do_sb, long long do_st, void* dq, long long dq_sb,
-                            long long dq_st, float* dk, long long dk_sb, long long dk_st, float* dv, long long dv_sb, long long dv_st,
-                            cudaStream_t stream) {
+                            long long dq_st, void* dk, long long dk_sb, long long dk_st, void* dv, long long dv_sb, long long dv_st,
+                            int dkv_dtype, cudaStream_t stream) {
   if (a.dtype != TCAVP_BF16 || a.out == nullptr || a.H != a.Hkv) return 1;
   if (!(a.dh == 16 || a.dh == 32 || a.dh == 64 || a.dh == 96 || a.dh == 128) || a.Tk > 256 || a.Tq > 256) return 1;
   auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
@@ -367,7 +384,7 @@ int attention_bwd_tc_launch(const tcavp_attn_args& a, const void* dout, long lon
     TCAVP_CUDA(cudaFuncSetAttribute(fb::attn_bwd_tc_kernel<DH, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
     fb::attn_bwd_tc_kernel<DH, MAXT, MINB><<<grid, warps * 32, smem, stream>>>(                                                             \
         a, reinterpret_cast<const __nv_bfloat16*>(dout), do_sb, do_st, reinterpret_cast<__nv_bfloat16*>(dq), dq_sb, dq_st, dk, dk_sb, dk_st, \
-        dv, dv_sb, dv_st, tq_pad, tk_pad);                                                                                                  \
+        dv, dv_sb, dv_st, dkv_dtype == TCAVP_BF16 ? 1 : 0, tq_pad, tk_pad);                                                                                                  \
   } while (0)
   if (a.dh == 64) {
     if (warps <= 5) TCAVP_BWD(64, 160, 2);

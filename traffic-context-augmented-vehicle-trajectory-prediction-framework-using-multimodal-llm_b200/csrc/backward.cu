@@ -183,6 +183,90 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const void* __restrict
   }
 }
 
+// Vectorised bf16 variant: 16-byte accesses, one warp per row; NV > 0 keeps the row (x and dy, NV 8-element vectors per lane)
+// in registers so both are read exactly once, NV == 0 streams wider rows three times (the re-reads hit L1).
+__device__ __forceinline__ void ld8_bf16(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    v[2 * e] = __uint_as_float(w[e] << 16);
+    v[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ void st8_bf16(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256) rmsnorm_bwd_vec_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, const __nv_bfloat16* __restrict__ x,
+                                                              int ldx, const float* __restrict__ w, const __nv_bfloat16* __restrict__ add,
+                                                              int ldadd, __nv_bfloat16* __restrict__ dx, int lddx, int rows, int cols, float eps) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    const __nv_bfloat16* xr = x + (size_t)row * ldx;
+    const __nv_bfloat16* gr = dy + (size_t)row * lddy;
+    float xv[NV > 0 ? NV : 1][8], gv[NV > 0 ? NV : 1][8];
+    float ss = 0.f, dot = 0.f;
+    if (NV > 0) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 8;
+        if (c < cols) {
+          ld8_bf16(xr + c, xv[i]);
+          ld8_bf16(gr + c, gv[i]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            if (w) gv[i][e] *= __ldg(w + c + e);
+            ss += xv[i][e] * xv[i][e];
+            dot += gv[i][e] * xv[i][e];
+          }
+        }
+      }
+    } else {
+      for (int c = lane * 8; c < cols; c += 256) {
+        float a[8], g[8];
+        ld8_bf16(xr + c, a);
+        ld8_bf16(gr + c, g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          ss += a[e] * a[e];
+          dot += g[e] * (w ? __ldg(w + c + e) : 1.f) * a[e];
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / cols + eps);
+    dot = warp_sum(dot) * rstd / cols;          // mean(g * xhat)
+    if (NV > 0) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 8;
+        if (c < cols) {
+          float o[8], ad[8];
+          if (add) ld8_bf16(add + (size_t)row * ldadd + c, ad);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = rstd * (gv[i][e] - xv[i][e] * rstd * dot) + (add ? ad[e] : 0.f);
+          st8_bf16(dx + (size_t)row * lddx + c, o);
+        }
+      }
+    } else {
+      for (int c = lane * 8; c < cols; c += 256) {
+        float a[8], g[8], o[8], ad[8];
+        ld8_bf16(xr + c, a);
+        ld8_bf16(gr + c, g);
+        if (add) ld8_bf16(add + (size_t)row * ldadd + c, ad);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = rstd * (g[e] * (w ? __ldg(w + c + e) : 1.f) - a[e] * rstd * dot) + (add ? ad[e] : 0.f);
+        st8_bf16(dx + (size_t)row * lddx + c, o);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Rotary embedding on ADJACENT column pairs (the layout tcavp_gemm's fused RoPE produces), forward or inverse.
 // Table layout 1: [dh/4][L] x float4 = (cos, sin) of pairs (2k, 2k+1).
@@ -562,8 +646,8 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_kernel(tcavp_attn_args a, co
 }  // namespace ab
 
 int attention_bwd_tc_launch(const tcavp_attn_args& a, const void* dout, long long do_sb, long long do_st, void* dq, long long dq_sb,
-                            long long dq_st, float* dk, long long dk_sb, long long dk_st, float* dv, long long dv_sb, long long dv_st,
-                            cudaStream_t stream);   // attention_bwd_tc.cu
+                            long long dq_st, void* dk, long long dk_sb, long long dk_st, void* dv, long long dv_sb, long long dv_st,
+                            int dkv_dtype, cudaStream_t stream);   // attention_bwd_tc.cu
 
 // ------------------------------------------------------------------------------------------------
 // AdamW (torch.optim.AdamW semantics, reference scripts/im_kim_train_GRN.py:1008): decoupled weight decay,
@@ -670,6 +754,22 @@ extern "C" int tcavp_rmsnorm_bwd(const void* dy, int lddy, const void* x, int ld
   TCAVP_REQUIRE(rows >= 0 && cols > 0, "tcavp_rmsnorm_bwd: bad shape");
   if (rows == 0) return TCAVP_OK;
   TCAVP_REQUIRE(dy && x && dx && DT_OK(dtype), "tcavp_rmsnorm_bwd: bad pointer/dtype");
+  auto al = [](const void* p, int ld) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % 16 == 0 && ld % 8 == 0); };
+  if (dtype == TCAVP_BF16 && cols % 8 == 0 && al(dy, lddy) && al(x, ldx) && al(add, ldadd) && al(dx, lddx)) {
+    const __nv_bfloat16* dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
+    const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
+    const __nv_bfloat16* ab = reinterpret_cast<const __nv_bfloat16*>(add);
+    __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(dx);
+    const int grid = grid_cap((rows + 7) / 8, 16);
+#define TCAVP_RB(NV) rmsnorm_bwd_vec_kernel<NV><<<grid, 256, 0, STREAM(stream)>>>(dyb, lddy, xb, ldx, w, ab, ldadd, ob, lddx, rows, cols, eps)
+    if (cols <= 256) TCAVP_RB(1);
+    else if (cols <= 512) TCAVP_RB(2);
+    else if (cols <= 768) TCAVP_RB(3);
+    else if (cols <= 1024) TCAVP_RB(4);
+    else TCAVP_RB(0);
+#undef TCAVP_RB
+    return check_launch("rmsnorm_bwd_kernel");
+  }
   rmsnorm_bwd_kernel<<<grid_cap((rows + 7) / 8, 8), 256, 0, STREAM(stream)>>>(dy, lddy, x, ldx, w, add, ldadd, dx, lddx, dtype, rows, cols, eps);
   return check_launch("rmsnorm_bwd_kernel");
 }
@@ -786,7 +886,7 @@ extern "C" int tcavp_attention_bwd(const tcavp_attn_args* a, const void* dout, l
   if (a->B == 0) return TCAVP_OK;
   TCAVP_REQUIRE(a->q && a->k && a->v && dout && dq && dk && dv && DT_OK(a->dtype), "tcavp_attention_bwd: bad pointer/dtype");
   {   // tensor-core path: bf16, MHA, small head, forward output available (args->out)
-    const int rc = attention_bwd_tc_launch(*a, dout, do_sb, do_st, dq, dq_sb, dq_st, dk, dk_sb, dk_st, dv, dv_sb, dv_st, STREAM(stream));
+    const int rc = attention_bwd_tc_launch(*a, dout, do_sb, do_st, dq, dq_sb, dq_st, dk, dk_sb, dk_st, dv, dv_sb, dv_st, TCAVP_F32, STREAM(stream));
     if (rc <= 0) return rc;
   }
   int DC = a->dh < 32 ? a->dh : 32;
@@ -808,6 +908,19 @@ extern "C" int tcavp_attention_bwd(const tcavp_attn_args* a, const void* dout, l
         *a, reinterpret_cast<const float*>(dout), do_sb, do_st, reinterpret_cast<float*>(dq), dq_sb, dq_st, dk, dk_sb, dk_st, dv, dv_sb, dv_st, DC);
   }
   return check_launch("attn_bwd_kernel");
+}
+
+extern "C" int tcavp_attention_bwd_owned(const tcavp_attn_args* a, const void* dout, long long do_sb, long long do_st, void* dq, long long dq_sb,
+                                         long long dq_st, void* dk, long long dk_sb, long long dk_st, void* dv, long long dv_sb, long long dv_st,
+                                         int dkv_dtype, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(a != nullptr, "tcavp_attention_bwd_owned: null args");
+  TCAVP_REQUIRE(a->B >= 0 && a->H > 0 && a->H == a->Hkv && a->Tq > 0 && a->Tk > 0, "tcavp_attention_bwd_owned: bad shape (needs H == Hkv)");
+  TCAVP_REQUIRE(!a->causal || a->Tq == a->Tk, "tcavp_attention_bwd_owned: causal needs Tq == Tk");
+  if (a->B == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(a->q && a->k && a->v && a->out && dout && dq && dk && dv && DT_OK(dkv_dtype), "tcavp_attention_bwd_owned: bad pointer/dtype");
+  const int rc = attention_bwd_tc_launch(*a, dout, do_sb, do_st, dq, dq_sb, dq_st, dk, dk_sb, dk_st, dv, dv_sb, dv_st, dkv_dtype, STREAM(stream));
+  if (rc > 0) return fail_arg("tcavp_attention_bwd_owned: shape not covered by the tensor-core kernel (bf16, head_dim 16/32/64/96/128, Tq, Tk <= 256)");
+  return rc;
 }
 
 extern "C" int tcavp_adamw(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1, float beta2,

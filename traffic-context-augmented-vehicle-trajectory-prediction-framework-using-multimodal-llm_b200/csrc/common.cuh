@@ -81,6 +81,7 @@ struct EpilogueParams {
   int remap_gi, remap_go, remap_off;
   const float* rope; int rope_L, rope_dh, rope_cols;   // fused rotary embedding on adjacent column pairs
   const float* row_scale;                              // per-row factor applied to the raw accumulators (fused RMSNorm)
+  __nv_bfloat16* aux; int ld_aux;                      // SwiGLU only: raw (row-scaled) gate/up accumulators for the backward pass
 };
 
 __device__ __forceinline__ int remap_row(int gi, int go, int off, int m) {

@@ -169,6 +169,16 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueParams& p, int m, i
   if (p.act == TCAVP_ACT_SWIGLU) {
     cnt = 16;
     n0 = nacc0 >> 1;
+    if (p.aux && nacc0 + 32 <= 2 * p.N) {     // stash (gate, up) pairs for the backward pass: 32 bf16 = two 32-byte stores
+      __nv_bfloat16* ap = p.aux + (size_t)remap_row(p.remap_gi, p.remap_go, p.remap_off, m) * p.ld_aux + nacc0;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        uint32_t u[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) u[e] = pack_bf16(__uint_as_float(r[q * 16 + 2 * e]) * rs, __uint_as_float(r[q * 16 + 2 * e + 1]) * rs);
+        stg256(ap + q * 16, u);
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 16; ++j) o[j] = swiglu_f(__uint_as_float(r[2 * j]) * rs, __uint_as_float(r[2 * j + 1]) * rs);
   } else {
@@ -832,6 +842,12 @@ extern "C" int tcavp_gemm(const tcavp_gemm_args* a, tcavp_stream_t stream_) {
   ep.remap_gi = a->remap_gi; ep.remap_go = a->remap_go; ep.remap_off = a->remap_off;
   ep.row_scale = a->row_scale;
   ep.rope = a->rope_cos_sin; ep.rope_L = a->rope_L; ep.rope_dh = a->rope_dh; ep.rope_cols = a->rope_cos_sin ? a->rope_cols : 0;
+  ep.aux = reinterpret_cast<__nv_bfloat16*>(a->aux_out); ep.ld_aux = a->ld_aux;
+  if (ep.aux) {
+    TCAVP_REQUIRE(a->act == TCAVP_ACT_SWIGLU && a->in_dtype == TCAVP_BF16, "tcavp_gemm: aux_out needs act SWIGLU and bf16 operands");
+    TCAVP_REQUIRE(a->N % 32 == 0 && a->ld_aux >= a->N && a->ld_aux % 16 == 0 && reinterpret_cast<uintptr_t>(a->aux_out) % 32 == 0,
+                  "tcavp_gemm: aux_out needs N %% 32 == 0, ld_aux >= N, ld_aux %% 16 == 0 and a 32-byte aligned pointer");
+  }
   if (ep.rope_cols > 0) {
     TCAVP_REQUIRE(a->act == TCAVP_ACT_NONE && !a->bias, "tcavp_gemm: fused RoPE needs act NONE and no bias");
     TCAVP_REQUIRE(a->rope_L > 0 && a->rope_dh >= 32 && a->rope_dh % 32 == 0 && a->rope_cols % a->rope_dh == 0 && a->rope_cols <= a->N,

@@ -25,7 +25,8 @@ class GemmArgs(Structure):
                 ("act", c_int),
                 ("remap_gi", c_int), ("remap_go", c_int), ("remap_off", c_int),
                 ("rope_cos_sin", c_void_p), ("rope_L", c_int), ("rope_dh", c_int), ("rope_cols", c_int),
-                ("row_scale", c_void_p)]
+                ("row_scale", c_void_p),
+                ("aux_out", c_void_p), ("ld_aux", c_int)]
 
 
 class AttnArgs(Structure):
@@ -127,7 +128,7 @@ def _need_cuda(*ts):
 
 
 def gemm(a, w, out, *, M=None, N=None, K=None, lda=None, ldw=None, ldo=None, bias=None, residual=None, ldr=None,
-         act=ACT_NONE, remap=(0, 0, 0), rope=None, row_scale=None):
+         act=ACT_NONE, remap=(0, 0, 0), rope=None, row_scale=None, aux_out=None):
     """out = act(a @ w.T + bias) + residual.  a: [M, >=K] row-major (lda = a.stride(0)), w: [N, >=K]."""
     _need_cuda(a, w, out, bias, residual)
     g = GemmArgs()
@@ -151,6 +152,10 @@ def gemm(a, w, out, *, M=None, N=None, K=None, lda=None, ldw=None, ldo=None, bia
         if row_scale.dtype != torch.float32:
             raise TypeError("gemm: row_scale must be fp32")
         g.row_scale = row_scale.data_ptr()
+    if aux_out is not None:  # SwiGLU: raw gate/up accumulators (bf16, interleaved) for the backward pass
+        if aux_out.dtype != torch.bfloat16:
+            raise TypeError("gemm: aux_out must be bf16")
+        g.aux_out, g.ld_aux = aux_out.data_ptr(), aux_out.stride(0)
     if rope is not None:     # (table, L, dh, cols)
         g.rope_cos_sin, g.rope_L, g.rope_dh, g.rope_cols = rope[0].data_ptr(), rope[1], rope[2], rope[3]
     if g.in_dtype == BF16:
@@ -470,6 +475,33 @@ def attention_bwd(q, k, v, dout, dq, dk, dv, *, B, H, Hkv, Tq, Tk, dh, q_strides
         _lib.check(_lib.load().tcavp_attention_bwd(byref(a), _p(dout), _ll(do_strides[0]), _ll(do_strides[1]), _p(dq), _ll(dq_strides[0]),
                                                    _ll(dq_strides[1]), _p(dk), _ll(dk_strides[0]), _ll(dk_strides[1]), _p(dv),
                                                    _ll(dv_strides[0]), _ll(dv_strides[1]), _stream()), "tcavp_attention_bwd")
+
+
+def attention_bwd_owned_ok(q, *, H, Hkv, Tq, Tk, dh, o):
+    """True when tcavp_attention_bwd_owned (tensor-core kernel, dk / dv stored directly in the activation dtype) covers the shape."""
+    return o is not None and q.dtype == torch.bfloat16 and H == Hkv and dh in (16, 32, 64, 96, 128) and max(Tq, Tk) <= 256
+
+
+def attention_bwd_owned(q, k, v, dout, dq, dk, dv, *, B, H, Tq, Tk, dh, q_strides, k_strides, v_strides, do_strides, dq_strides,
+                        dk_strides, dv_strides, scale, causal=False, key_mask=None, o=None, o_strides=None):
+    """dk / dv are written (not accumulated) in their own dtype, e.g. straight into the packed d(qkv) buffer."""
+    _need_cuda(q, k, v, dout, dq, dk, dv, key_mask, o)
+    if dk.dtype != dv.dtype:
+        raise TypeError("attention_bwd_owned: dk / dv dtypes differ")
+    a = AttnArgs()
+    a.B, a.H, a.Hkv, a.Tq, a.Tk, a.dh = B, H, H, Tq, Tk, dh
+    a.q, (a.q_sb, a.q_st) = q.data_ptr(), q_strides
+    a.k, (a.k_sb, a.k_st) = k.data_ptr(), k_strides
+    a.v, (a.v_sb, a.v_st) = v.data_ptr(), v_strides
+    a.out, (a.o_sb, a.o_st) = o.data_ptr(), o_strides
+    a.dtype, a.scale, a.causal = dt(q), scale, int(causal)
+    if key_mask is not None:
+        a.key_mask = key_mask.data_ptr()
+    fl = 10.0 * B * H * Tq * Tk * dh * (0.5 if causal else 1.0)
+    with _Timed(f"attn_bwd_tc_kernel[dh{dh},q{Tq},k{Tk}]", fl, 0.0):
+        _lib.check(_lib.load().tcavp_attention_bwd_owned(byref(a), _p(dout), _ll(do_strides[0]), _ll(do_strides[1]), _p(dq), _ll(dq_strides[0]),
+                                                         _ll(dq_strides[1]), _p(dk), _ll(dk_strides[0]), _ll(dk_strides[1]), _p(dv),
+                                                         _ll(dv_strides[0]), _ll(dv_strides[1]), dt(dk), _stream()), "tcavp_attention_bwd_owned")
 
 
 def adamw_(param, grad, exp_avg, exp_avg_sq, *, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, step, grad_scale=1.0):

@@ -154,6 +154,13 @@ class TrainEngine(Engine):
     def _attn_bwd(self, q, k, v, do, *, B, H, Hkv, Tq, Tk, dh, qs, ks, vs, dos, dq, dqs, dk_out, dv_out, ld_kv, scale, causal=False,
                   key_mask=None, o=None):
         """dq is written in place (strides dqs); dk / dv are accumulated in fp32 and cast into dk_out / dv_out (row stride ld_kv)."""
+        if ops.attention_bwd_owned_ok(q, H=H, Hkv=Hkv, Tq=Tq, Tk=Tk, dh=dh, o=o):
+            # one CTA owns all key rows of a head: dk / dv land directly in the packed gradient buffer (no fp32 staging, no casts)
+            kvs = (Tk * ld_kv, ld_kv)
+            ops.attention_bwd_owned(q, k, v, do, dq, dk_out, dv_out, B=B, H=H, Tq=Tq, Tk=Tk, dh=dh, q_strides=qs, k_strides=ks, v_strides=vs,
+                                    do_strides=dos, dq_strides=dqs, dk_strides=kvs, dv_strides=kvs, scale=scale, causal=causal,
+                                    key_mask=key_mask, o=o, o_strides=dos)
+            return
         wk = Hkv * dh
         dk = torch.zeros(B * Tk, wk, dtype=torch.float32, device=self.dev)
         dv = torch.zeros(B * Tk, wk, dtype=torch.float32, device=self.dev)
@@ -372,8 +379,13 @@ class TrainEngine(Engine):
             xs2 = self._new_xs(M)
             ops.gemm(attn, ly["wo"], xs2, ldo=Kx, residual=xs, ldr=Kx)
             rstd2 = ops.row_rstd(xs2, torch.empty(M, dtype=torch.float32, device=self.dev), rows=M, cols=H, ldx=Kx, eps=m["eps"])
-            gu = ops.gemm(xs2, ly["wgu"], self._new(M, 2 * I), M=M, K=H, lda=Kx, row_scale=rstd2)
-            mid = ops.swiglu(gu, self._new(M, I), rows=M, I=I)
+            if self.act == torch.bfloat16 and (2 * I) % 32 == 0:
+                # one pass: the SwiGLU epilogue emits mid and stashes the raw gate/up accumulators for swiglu_bwd
+                gu = self._new(M, 2 * I)
+                mid = ops.gemm(xs2, ly["wgu"], self._new(M, I), M=M, K=H, lda=Kx, act=ops.ACT_SWIGLU, row_scale=rstd2, aux_out=gu)
+            else:
+                gu = ops.gemm(xs2, ly["wgu"], self._new(M, 2 * I), M=M, K=H, lda=Kx, row_scale=rstd2)
+                mid = ops.swiglu(gu, self._new(M, I), rows=M, I=I)
             xs3 = self._new_xs(M)
             ops.gemm(mid, ly["wdown"], xs3, ldo=Kx, residual=xs2, ldr=Kx)
             ctxs.append((xs, rstd1, qkv, attn, xs2, rstd2, gu, mid))
