@@ -214,6 +214,39 @@ def test_skinny_dw(ops, dtype, J):
     torch.testing.assert_close(out.cpu(), want, rtol=1e-3, atol=1e-3)
 
 
+@pytest.mark.parametrize("J", [16, 32])
+def test_skinny_dw_tensor_core_path(ops, J):
+    """bf16 operands with 16-byte aligned rows take the mma.sync kernel (ldmatrix.trans on the row-major operands); the row factor is
+    applied to Z in bf16 on its way into shared memory, so the reference rounds the same product."""
+    M, N, ld = 5000, 304, 312
+    Y = _rand(M, ld, seed=24).bfloat16()
+    Z = _rand(M, J + 8, seed=25).bfloat16()
+    rs = torch.rand(M) + 0.5
+    out = torch.zeros(N, J, device=DEV)
+    ops.skinny_dw(Y.to(DEV), Z.to(DEV), out, M=M, N=N, J=J, ldy=ld, ldz=J + 8, row_scale=rs.to(DEV))
+    want = Y[:, :N].float().t() @ (Z[:, :J].float() * rs[:, None]).bfloat16().float()
+    torch.testing.assert_close(out.cpu(), want, rtol=1e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("dtype,M,N,K", [("fp32", 1000, 200, 70), ("fp32", 3000, 64, 2), ("bf16", 1000, 200, 72), ("bf16", 4100, 384, 256),
+                                         ("bf16", 700, 130, 36), ("mixed", 900, 64, 64)])
+def test_dw(ops, dtype, M, N, K):
+    """out[n][k] += sum_m dy[m][n] x[m][k] on the row-major operands (no transposes): FFMA kernel (fp32 / mixed / ragged) and
+    tensor-core kernel (bf16, N % 8 == K % 8 == 0)."""
+    tdy = torch.float32 if dtype in ("fp32", "mixed") else torch.bfloat16
+    tdx = torch.float32 if dtype == "fp32" else torch.bfloat16
+    dy = _rand(M, N + 8, seed=31).to(tdy)
+    x = _rand(M, K + 16, seed=32).to(tdx)
+    out = torch.zeros(N, K + 3, device=DEV)
+    out[:, K:] = 7.0
+    ops.dw(dy.to(DEV)[:, :N], x.to(DEV)[:, :K], out, M=M, N=N, K=K)
+    want = dy[:, :N].float().t() @ x[:, :K].float()
+    torch.testing.assert_close(out[:, :K].cpu(), want, rtol=1e-3, atol=2e-3)
+    assert (out[:, K:] == 7.0).all()
+    ops.dw(dy.to(DEV)[:, :N], x.to(DEV)[:, :K], out, M=M, N=N, K=K)          # accumulates
+    torch.testing.assert_close(out[:, :K].cpu(), 2 * want, rtol=1e-3, atol=4e-3)
+
+
 ATTN_CASES = [  # B, H, Hkv, Tq, Tk, dh, causal, masked
     (3, 4, 2, 24, 24, 32, True, True),     # LLM-like: causal + padding + GQA
     (2, 12, 12, 144, 144, 64, True, True),

@@ -645,6 +645,8 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_kernel(tcavp_attn_args a, co
 }
 }  // namespace ab
 
+int dw_tc_launch(const void* Y, int ldy, const void* X, int ldx, const float* scale, float* out, int ldo, long long M, int N, int K,
+                 cudaStream_t stream);
 int attention_bwd_tc_launch(const tcavp_attn_args& a, const void* dout, long long do_sb, long long do_st, void* dq, long long dq_sb,
                             long long dq_st, void* dk, long long dk_sb, long long dk_st, void* dv, long long dv_sb, long long dv_st,
                             int dkv_dtype, cudaStream_t stream);   // attention_bwd_tc.cu
@@ -774,11 +776,41 @@ extern "C" int tcavp_rmsnorm_bwd(const void* dy, int lddy, const void* x, int ld
   return check_launch("rmsnorm_bwd_kernel");
 }
 
+// bf16 rows with 16-byte aligned starts: 8 elements (two rotation quads) per thread, one 16-byte load + store.
+__global__ void __launch_bounds__(256) rope_adjacent_vec_kernel(__nv_bfloat16* __restrict__ buf, long long rows, int L, int ld, int cols, int dh,
+                                                                const float* __restrict__ table, int inverse) {
+  const int octs = cols >> 3;
+  const long long total = rows * octs;
+  const float sg = inverse ? -1.f : 1.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / octs;
+    const int c = (int)(i % octs) * 8;
+    const int pos = (int)(r % L);
+    float v[8];
+    ld8_bf16(buf + (size_t)r * ld + c, v);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(table) + (size_t)(((c + 4 * h) % dh) >> 2) * L + pos);
+      const float a0 = v[4 * h], a1 = v[4 * h + 1], a2 = v[4 * h + 2], a3 = v[4 * h + 3];
+      v[4 * h] = a0 * t.x - sg * a1 * t.y;
+      v[4 * h + 1] = a1 * t.x + sg * a0 * t.y;
+      v[4 * h + 2] = a2 * t.z - sg * a3 * t.w;
+      v[4 * h + 3] = a3 * t.z + sg * a2 * t.w;
+    }
+    st8_bf16(buf + (size_t)r * ld + c, v);
+  }
+}
+
 extern "C" int tcavp_rope_adjacent(void* buf, int dtype, long long rows, int L, int ld, int cols, int dh, const float* table, int inverse,
                                    tcavp_stream_t stream) {
   TCAVP_REQUIRE(rows >= 0 && L > 0 && cols >= 0 && dh >= 4 && dh % 4 == 0 && cols % dh == 0 && ld >= cols, "tcavp_rope_adjacent: bad shape");
   if (rows == 0 || cols == 0) return TCAVP_OK;
   TCAVP_REQUIRE(buf && table && DT_OK(dtype), "tcavp_rope_adjacent: bad pointer/dtype");
+  if (dtype == TCAVP_BF16 && cols % 8 == 0 && dh % 8 == 0 && ld % 8 == 0 && reinterpret_cast<uintptr_t>(buf) % 16 == 0) {
+    rope_adjacent_vec_kernel<<<grid_cap((rows * (cols / 8) + 255) / 256, 16), 256, 0, STREAM(stream)>>>(reinterpret_cast<__nv_bfloat16*>(buf), rows, L,
+                                                                                                        ld, cols, dh, table, inverse);
+    return check_launch("rope_adjacent_kernel");
+  }
   rope_adjacent_kernel<<<grid_cap((rows * (cols / 4) + 255) / 256, 16), 256, 0, STREAM(stream)>>>(buf, dtype, rows, L, ld, cols, dh, table, inverse);
   return check_launch("rope_adjacent_kernel");
 }
@@ -846,6 +878,10 @@ extern "C" int tcavp_skinny_dw(const void* Y, int ldy, int y_dtype, const void* 
   TCAVP_REQUIRE(M >= 0 && N > 0 && J > 0 && J <= 32 && ldo >= J, "tcavp_skinny_dw: bad shape (J=%d, max 32)", J);
   if (M == 0) return TCAVP_OK;
   TCAVP_REQUIRE(Y && Z && out && DT_OK(y_dtype) && DT_OK(z_dtype), "tcavp_skinny_dw: bad pointer/dtype");
+  if (y_dtype == TCAVP_BF16 && z_dtype == TCAVP_BF16 && M < (1ll << 31)) {   // bound by the one pass over Y instead of FFMA issue
+    const int rc = dw_tc_launch(Y, ldy, Z, ldz, row_scale, out, ldo, M, N, J, STREAM(stream));
+    if (rc <= 0) return rc;
+  }
   const int nblocks = (N + 127) / 128;
   long long splits = ((long long)sm_count() * 8) / nblocks;
   if (splits < 1) splits = 1;
@@ -863,6 +899,10 @@ extern "C" int tcavp_dw(const void* dY, int lddy, int dy_dtype, const void* X, i
   TCAVP_REQUIRE(M >= 0 && N > 0 && K > 0 && lddy >= N && ldx >= K && ldo >= K, "tcavp_dw: bad shape M=%lld N=%d K=%d", M, N, K);
   if (M == 0) return TCAVP_OK;
   TCAVP_REQUIRE(dY && X && out && DT_OK(dy_dtype) && DT_OK(x_dtype), "tcavp_dw: bad pointer/dtype");
+  if (dy_dtype == TCAVP_BF16 && x_dtype == TCAVP_BF16) {     // tensor cores on the row-major operands (ldmatrix.trans)
+    const int rc = dw_tc_launch(dY, lddy, X, ldx, nullptr, out, ldo, M, N, K, STREAM(stream));
+    if (rc <= 0) return rc;
+  }
   const int tn = (N + 63) / 64, tk = (K + 63) / 64;
   long long splits = ((long long)sm_count() * 4) / ((long long)tn * tk);
   if (splits < 1) splits = 1;

@@ -118,8 +118,9 @@ class TrainEngine(Engine):
     def _dw_gemm(self, dy, x, out, *, N, K, lddy=None, ldx=None):
         """out[N, K] (fp32) = dy^T . x over the M rows; operands are transposed (and dtype-unified) explicitly."""
         M = dy.shape[0]
-        if dy.dtype == torch.float32 or x.dtype == torch.float32 or 2.0 * M * N * K < 1.5e9:
-            # narrow / fp32 layers: FFMA kernel on the row-major operands, M split over the grid (no transposed copies)
+        if dy.dtype == torch.float32 or x.dtype == torch.float32 or 2.0 * M * N * K < 6e10:
+            # no transposed copies: tensor-core kernel on the row-major bf16 operands (ldmatrix.trans), FFMA kernel for the fp32 layers;
+            # only the very long contractions (K/V projection of the fusion cross-attention) go through transpose + tcgen05 GEMM
             return ops.dw(dy, x, out, M=M, N=N, K=K, lddy=dy.stride(0) if lddy is None else lddy, ldx=x.stride(0) if ldx is None else ldx)
         Mp = _pad8(M)
         td = x.dtype
