@@ -54,46 +54,84 @@ def peaks():
 
 
 class ClockSampler:
+    """SM clock / power / throttle reasons DURING the timed region.  NVML is read in-process every 20 ms (nvidia-smi takes
+    ~0.3 s to start, longer than a short timed region); the nvidia-smi loop of the profiling recipe is the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        import threading
+        self.sm, self.mx, self.pw, self.reasons = [], [], [], set()
+        self.p = self.f = self.t = None
+        self._stop = False
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+
+            def loop():
+                while not self._stop:
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        self.mx.append(mx)
+                        self.pw.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1e3)
+                        r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        for n, b in bits.items():
+                            if r & b:
+                                self.reasons.add(n)
+                    except Exception:
+                        pass
+                    time.sleep(0.02)
+            self.t = threading.Thread(target=loop, daemon=True)
+            self.t.start()
+        except Exception:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            try:
+                self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                          stdout=self.f, stderr=subprocess.DEVNULL)
+            except OSError:
+                self.p = None
 
     def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.f.read().splitlines():
-            c = [t.strip() for t in line.split(",")]
-            if len(c) < 7:
-                continue
+        if self.t is not None:
+            self._stop = True
+            self.t.join(timeout=2)
+            sm, mx, reasons, src = self.sm, self.mx, self.reasons, "nvml, 20 ms period"
+        else:
+            if self.p is None:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            self.p.terminate()
             try:
-                sm.append(float(c[0]))
-                mx.append(float(c[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, c[3:7]):
-                if v == "Active":
-                    reasons.add(n)
-        os.unlink(self.f.name)
-        # "under load" = the upper half of the samples (idle samples before/after the region drag the median down)
-        sm_load = sorted(sm)[len(sm) // 2:] if sm else []
-        return {"sm_mhz": statistics.median(sm_load) if sm_load else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                self.p.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.p.kill()
+            self.f.flush()
+            self.f.seek(0)
+            sm, mx, reasons, src = [], [], set(), "nvidia-smi -lms 100"
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for line in self.f.read().splitlines():
+                c = [t.strip() for t in line.split(",")]
+                if len(c) < 7:
+                    continue
+                try:
+                    sm.append(float(c[0]))
+                    mx.append(float(c[1]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, c[3:7]):
+                    if v == "Active":
+                        reasons.add(n)
+            os.unlink(self.f.name)
+        load = sm       # the sampler only lives inside the timed region: every sample is a sample under load
+        out = {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm), "source": src}
+        if self.pw:
+            out["power_w_max"] = round(max(self.pw), 1)
+        return out
 
 
 def build_model(preset, device, compute_dtype="bf16"):
@@ -273,6 +311,14 @@ def run_ours(args):
         gb = sum(g["gbs"] * g["time_ms"] for g in bw) / t_bw
         out["roofline"]["hbm_kernels"] = {"bound": "hbm", "achieved": round(gb, 1), "peak": pk["hbm"], "unit": "GB/s", "frac": round(gb / pk["hbm"], 4),
                                           "share_of_step": round(t_bw / ms, 4), "kernels": [g["kernel"] for g in bw]}
+    # DRAM bytes per launch of the dominant kernel, from the committed ncu capture of this same command (tools/profile.sh)
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        t = json.load(open(tpath)).get(args.workload)
+        if t and dom["kernel"].split("<")[0] in t.get("kernel", ""):
+            out["roofline"]["traffic"] = t["dram_bytes_per_launch"]
+            out["roofline"]["traffic_source"] = f"profiles/ncu_traffic.json ({t['source']}: mean of {t['launches']} launches of one step, dram__bytes_read+write)"
+            out["roofline"]["algorithmic_bytes_per_launch"] = round(dom["bytes"] / max(dom["launches"], 1))
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(model, cfg, lc, l_text, sample=args.cpu_sample, repeats=2, frozen=frozen)
     emit(out)

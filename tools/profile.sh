@@ -11,10 +11,19 @@ if [ "${LIST:-1}" = "1" ]; then
   ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_list_${TAG}.log 2>&1
   python tools/launch_summary.py gpurun_out/launches_${TAG}.csv > gpurun_out/launches_${TAG}.md 2>/dev/null
 fi
+# DRAM traffic of every launch of the dominant kernel in ONE timed step (bench.py's roofline.traffic = their mean)
+if [ -n "${TRAFFIC_KERNEL:-}" ]; then
+  ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --kernel-name-base demangled \
+      -k "regex:${TRAFFIC_KERNEL}" -s ${TRAFFIC_SKIP:-300} -c ${TRAFFIC_COUNT:-100} --csv --log-file gpurun_out/traffic_${TAG}.csv $CMD \
+      > gpurun_out/ncu_traffic_${TAG}.log 2>&1
+  python tools/traffic_summary.py gpurun_out/traffic_${TAG}.csv 2>&1 | tail -3
+fi
 i=0
-for K in "$@"; do
+for SPEC in "$@"; do      # "<kernel regex>[@<matching launches to skip>]"
   i=$((i+1))
-  ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$K" -s ${SKIP:-30} -c ${COUNT:-4} \
+  K="${SPEC%@*}"; S="${SKIP:-30}"
+  case "$SPEC" in *@*) S="${SPEC##*@}";; esac
+  ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$K" -s $S -c ${COUNT:-4} \
       -o gpurun_out/prof_${TAG}_$i -f $CMD > gpurun_out/ncu_${TAG}_$i.log 2>&1
   tail -2 gpurun_out/ncu_${TAG}_$i.log | cut -c1-200
 done
