@@ -185,6 +185,8 @@ def run_ours(args):
     if args.scenes:
         B = args.scenes
     model, cfg = build_model(preset, dev)
+    if args.merge_lora:
+        model.merge_lora_for_inference(True)
     lc = T.resolve_llama(cfg["base_model_name"])
     s = scenes_for(cfg, B, l_text, 1234 + rank, lc["vocab_size"])
     eng = model.engine()
@@ -293,6 +295,7 @@ def run_ours(args):
                                f"{B} scenes/GPU/step, T_in {cfg['seq_len']} -> T_out {cfg['out_len']}, L = 16 image + {l_text} text tokens",
                    "scenes_per_gpu": B, "seq_len": Lseq, "parallelism": f"scene-parallel x{world}",
                    "l2": "per-step working set (>= 3 GB of activations) is far larger than the 126 MB L2; no explicit flush",
+                   "lora": "merged into the base weights at pack time" if args.merge_lora else "unmerged (rank-r side path fused into the QKV GEMM)",
                    "weights": "seeded random init (no checkpoints offline)", "ade_px": round(ade, 3), "fde_px": round(fde, 3)},
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "MultiModalTrajectoryModel.predict_with_metrics (pinned host tensors in, decoded + metrics out)"},
@@ -494,6 +497,8 @@ if __name__ == "__main__":
     ap.add_argument("--scenes", type=int, default=0, help="override scenes per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--merge-lora", action="store_true", help="serve-time option: fold LoRA into the base weights at pack time (not the default "
+                    "benchmark configuration: the reference runs the unmerged peft form)")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

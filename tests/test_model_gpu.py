@@ -77,3 +77,25 @@ def test_scene_independence_and_empty_batch(lib_built):
     assert torch.equal(full[2:5], sub)
     empty = e.forward(i["x"][:0], i["vision"][:0], i["polygon"][:0], [], i["input_ids"][:0], i["attention_mask"][:0])["decoded"]
     assert empty.shape == (0, 2, fix["model_cfg"]["out_len"])
+
+
+@pytest.mark.parametrize("dtype,tol", [("fp32", 2e-4), ("bf16", 3e-2)])
+def test_merged_lora_matches_the_side_path(lib_built, dtype, tol):
+    """Serve-time LoRA merge (W + (alpha/r) B A folded at pack time) against the fused side-path form on the same weights."""
+    fix = load_golden("tiny_b6")
+    m = build_filled_model(fix, dtype, "cuda")
+    i = fix["inputs"]
+    keys = set(m.state_dict())
+
+    def run():
+        o = m.engine().forward(i["x"], i["vision"], i["polygon"], i["poly_len"], i["input_ids"], i["attention_mask"])
+        torch.cuda.synchronize()
+        return o["decoded"].float().cpu()
+    side = run()
+    assert m.engine().llm["kx"] > 0
+    m.merge_lora_for_inference(True)
+    merged = run()
+    assert m.engine().llm["kx"] == 0
+    torch.testing.assert_close(merged, side, rtol=tol, atol=tol)
+    torch.testing.assert_close(merged, fix["out"]["decoded"], rtol=tol, atol=tol)
+    assert set(m.state_dict()) == keys

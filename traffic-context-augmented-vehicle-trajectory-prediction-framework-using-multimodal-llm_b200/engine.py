@@ -26,8 +26,9 @@ class _Lin:
 
 
 class Engine:
-    def __init__(self, model, compute_dtype="bf16"):
+    def __init__(self, model, compute_dtype="bf16", merge_lora=False):
         p0 = next(model.ltsf.parameters())
+        self.merge_lora = merge_lora
         self.dev = dev = p0.device   # packing works anywhere (host-side tests); forward() requires CUDA
         self.act = act = _ACT[compute_dtype]
         # The temporal encoder block and the NLinear decoder / lane_fc / post_mlp are a few MFLOP per scene: they always
@@ -92,8 +93,11 @@ class Engine:
         lm = wrap.causal_lm()
         act, dev = self.act, self.dev
         H, nh, nkv, dh, I = c["hidden_size"], c["num_attention_heads"], c["num_key_value_heads"], c["head_dim"], c["intermediate_size"]
-        targets = wrap.llama_model.targets if wrap.use_lora else ()
-        r = self.model_hp["lora_r"] if wrap.use_lora else 0
+        # serve-time option: W' = W + (alpha/r) B A merged at pack time — no side path, K stays H
+        merge = bool(wrap.use_lora and getattr(self, "merge_lora", False))
+        lora_targets = tuple(wrap.llama_model.targets) if wrap.use_lora else ()
+        targets = () if merge else lora_targets
+        r = self.model_hp["lora_r"] if (wrap.use_lora and not merge) else 0
         n_t = len(targets)
         kx = ((n_t * r + 7) // 8) * 8            # LoRA side columns appended to K (multiple of 8 for TMA strides)
         self.llm = dict(H=H, nh=nh, nkv=nkv, dh=dh, I=I, eps=c.get("rms_norm_eps", 1e-6), theta=float(c.get("rope_theta", 10000.0)),
@@ -119,6 +123,10 @@ class Engine:
                     wqkv[r0:r1, :H] = mod.base_layer.weight.detach().to(dev, act)
                     wqkv[r0:r1, H + ti * r: H + (ti + 1) * r] = (mod.lora_B["default"].weight.detach().float() * mod.scaling).to(dev, act)
                     a_cat[ti * r:(ti + 1) * r] = mod.lora_A["default"].weight.detach().to(dev, act)
+                elif merge and name in lora_targets:
+                    w = mod.base_layer.weight.detach().to(dev).float()
+                    w = w + mod.scaling * (mod.lora_B["default"].weight.detach().to(dev).float() @ mod.lora_A["default"].weight.detach().to(dev).float())
+                    wqkv[r0:r1, :H] = w.to(act)
                 else:
                     wqkv[r0:r1, :H] = mod.weight.detach().to(dev, act)
             if self.llm["fuse_rope"]:

@@ -47,6 +47,20 @@ def build(force=False, verbose=False):
     """Compiles csrc/*.cu -> libtcavp.so (sm_100a).  Cross-compiles fine on a box without a GPU."""
     if not force and not _stale():
         return LIB_PATH
+    # one builder at a time (torchrun starts N ranks at once): the others wait on the lock and then find a fresh library
+    import fcntl
+    os.makedirs(os.path.join(_HERE, "build"), exist_ok=True)
+    with open(os.path.join(_HERE, "build", ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():
+                return LIB_PATH
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose):
     objdir = os.path.join(_HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
@@ -65,10 +79,12 @@ def build(force=False, verbose=False):
         if verbose and out:
             print(out)
         objs.append(obj)
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs]
+    tmp = LIB_PATH + f".tmp{os.getpid()}"
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp, *objs]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
+    os.replace(tmp, LIB_PATH)       # atomic: a concurrent loader never sees a half-written library
     return LIB_PATH
 
 

@@ -360,9 +360,18 @@ class MultiModalTrajectoryModel(nn.Module):
     def engine(self):
         sig = self._signature()
         if self._engine is None or sig != self._engine_sig:
-            self._engine = Engine(self, self.compute_dtype)
+            self._engine = Engine(self, self.compute_dtype, merge_lora=getattr(self, "_merge_lora", False))
             self._engine_sig = sig
         return self._engine
+
+    def merge_lora_for_inference(self, enabled=True):
+        """Serve-time option: fold every LoRA pair into its base weight when the inference engine packs the backbone
+        (W' = W + (alpha / r) B A, peft's merge semantics), so the decoder runs without the rank-r side path.  The module's own
+        parameters (and state_dict()) are untouched; training always uses the unmerged form."""
+        if bool(enabled) != getattr(self, "_merge_lora", False):
+            self._merge_lora = bool(enabled)
+            self._engine = None
+        return self
 
     # ---- forward -----------------------------------------------------------------------------------
     def forward(self, x, vision_embs, context_str, lane_polygon_batch, lane_polygon_len, y=None, norm_stat=None, input_ids=None,
