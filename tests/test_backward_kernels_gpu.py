@@ -355,3 +355,41 @@ def test_attention_bwd_tensor_core(ops, B, H, Tq, Tk, dh, causal, masked):
         err = float((got - want).abs().max()) / (float(want.abs().max()) + 1e-12)
         assert err < 2e-2, (name, err)
         assert torch.isfinite(got).all(), name
+
+
+@pytest.mark.parametrize("B,H,Tq,Tk,dh,masked", [(3, 2, 25, 144, 384, False), (2, 2, 50, 144, 384, True), (2, 2, 12, 40, 2048, False),
+                                                 (2, 2, 64, 250, 128, True)])
+@pytest.mark.parametrize("dkv", ["bf16", "fp32"])
+def test_attention_bwd_few_queries_wide_heads(ops, B, H, Tq, Tk, dh, masked, dkv):
+    """tcavp_attention_bwd_owned on the LTSF cross-attention shape (few queries, head_dim = H/2): tensor-core kernel, one CTA per
+    (batch, head), dq / dk / dv stored directly (dk / dv in the caller's dtype, here straight into a packed [K | V] gradient buffer)."""
+    td = torch.bfloat16
+    q = _rand(B, Tq, H, dh, seed=50).to(td).float().requires_grad_(True)
+    k = _rand(B, Tk, H, dh, seed=51).to(td).float().requires_grad_(True)
+    v = _rand(B, Tk, H, dh, seed=52).to(td).float().requires_grad_(True)
+    valid = torch.ones(B, Tk, dtype=torch.bool)
+    if masked:
+        for b in range(B):
+            valid[b, Tk - 1 - 5 * b:] = False
+    scale = dh ** -0.5
+    s = (torch.einsum("bihd,bjhd->bhij", q, k) * scale).masked_fill(~valid[:, None, None, :], float("-inf"))
+    o = torch.einsum("bhij,bjhd->bihd", torch.softmax(s, dim=-1), v)
+    do = _rand(B, Tq, H, dh, seed=53).to(td)
+    o.backward(do.float())
+    qd, kd, vd, dod = (t.detach().to(td).to(DEV).contiguous() for t in (q, k, v, do))
+    dq = torch.full_like(qd, float("nan"))
+    E = H * dh
+    dkv_buf = torch.full((B * Tk, 2 * E), float("nan"), device=DEV, dtype=torch.bfloat16 if dkv == "bf16" else torch.float32)
+    km = valid.to(torch.int32).to(DEV) if masked else None
+    sq, sk = (Tq * E, E), (Tk * E, E)
+    assert ops.attention_bwd_owned_ok(qd, H=H, Hkv=H, Tq=Tq, Tk=Tk, dh=dh, o=None)
+    n0 = ops.launch_count()
+    ops.attention_bwd_owned(qd, kd, vd, dod, dq, dkv_buf, dkv_buf[:, E:], B=B, H=H, Tq=Tq, Tk=Tk, dh=dh, q_strides=sq, k_strides=sk, v_strides=sk,
+                            do_strides=sq, dq_strides=sq, dk_strides=(Tk * 2 * E, 2 * E), dv_strides=(Tk * 2 * E, 2 * E), scale=scale, key_mask=km)
+    assert ops.launch_count() - n0 == 1
+    got_k = dkv_buf[:, :E].float().cpu().view(B, Tk, H, dh)
+    got_v = dkv_buf[:, E:].float().cpu().view(B, Tk, H, dh)
+    for name, got, want in (("dq", dq.float().cpu(), q.grad), ("dk", got_k, k.grad), ("dv", got_v, v.grad)):
+        assert torch.isfinite(got).all(), name
+        err = float((got - want).abs().max()) / (float(want.abs().max()) + 1e-12)
+        assert err < 2e-2, (name, err)

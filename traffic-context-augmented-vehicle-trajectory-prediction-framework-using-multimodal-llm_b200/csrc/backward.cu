@@ -645,6 +645,8 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_kernel(tcavp_attn_args a, co
 }
 }  // namespace ab
 
+int attention_x_bwd_launch(const tcavp_attn_args& a, const void* dout, long long do_sb, long long do_st, void* dq, long long dq_sb, long long dq_st,
+                           void* dk, long long dk_sb, long long dk_st, void* dv, long long dv_sb, long long dv_st, int dkv_dtype, cudaStream_t stream);
 int dw_tc_launch(const void* Y, int ldy, const void* X, int ldx, const float* scale, float* out, int ldo, long long M, int N, int K,
                  cudaStream_t stream);
 int attention_bwd_tc_launch(const tcavp_attn_args& a, const void* dout, long long do_sb, long long do_st, void* dq, long long dq_sb,
@@ -957,9 +959,14 @@ extern "C" int tcavp_attention_bwd_owned(const tcavp_attn_args* a, const void* d
   TCAVP_REQUIRE(a->B >= 0 && a->H > 0 && a->H == a->Hkv && a->Tq > 0 && a->Tk > 0, "tcavp_attention_bwd_owned: bad shape (needs H == Hkv)");
   TCAVP_REQUIRE(!a->causal || a->Tq == a->Tk, "tcavp_attention_bwd_owned: causal needs Tq == Tk");
   if (a->B == 0) return TCAVP_OK;
-  TCAVP_REQUIRE(a->q && a->k && a->v && a->out && dout && dq && dk && dv && DT_OK(dkv_dtype), "tcavp_attention_bwd_owned: bad pointer/dtype");
-  const int rc = attention_bwd_tc_launch(*a, dout, do_sb, do_st, dq, dq_sb, dq_st, dk, dk_sb, dk_st, dv, dv_sb, dv_st, dkv_dtype, STREAM(stream));
-  if (rc > 0) return fail_arg("tcavp_attention_bwd_owned: shape not covered by the tensor-core kernel (bf16, head_dim 16/32/64/96/128, Tq, Tk <= 256)");
+  TCAVP_REQUIRE(a->q && a->k && a->v && dout && dq && dk && dv && DT_OK(dkv_dtype), "tcavp_attention_bwd_owned: bad pointer/dtype");
+  int rc = 1;
+  if (a->out) rc = attention_bwd_tc_launch(*a, dout, do_sb, do_st, dq, dq_sb, dq_st, dk, dk_sb, dk_st, dv, dv_sb, dv_st, dkv_dtype, STREAM(stream));
+  if (rc > 0)   // few queries against wide heads (LTSF cross-attention): head_dim % 64 == 0, Tq <= 64, no causal mask
+    rc = attention_x_bwd_launch(*a, dout, do_sb, do_st, dq, dq_sb, dq_st, dk, dk_sb, dk_st, dv, dv_sb, dv_st, dkv_dtype, STREAM(stream));
+  if (rc > 0)
+    return fail_arg("tcavp_attention_bwd_owned: shape not covered (bf16 and either head_dim 16/32/64/96/128 with Tq, Tk <= 256 and the forward "
+                    "output in args->out, or head_dim %% 64 == 0 with Tq <= 64, Tk <= 256, not causal)");
   return rc;
 }
 

@@ -480,9 +480,13 @@ def attention_bwd(q, k, v, dout, dq, dk, dv, *, B, H, Hkv, Tq, Tk, dh, q_strides
                                                    _ll(dv_strides[0]), _ll(dv_strides[1]), _stream()), "tcavp_attention_bwd")
 
 
-def attention_bwd_owned_ok(q, *, H, Hkv, Tq, Tk, dh, o):
+def attention_bwd_owned_ok(q, *, H, Hkv, Tq, Tk, dh, o, causal=False):
     """True when tcavp_attention_bwd_owned (tensor-core kernel, dk / dv stored directly in the activation dtype) covers the shape."""
-    return o is not None and q.dtype == torch.bfloat16 and H == Hkv and dh in (16, 32, 64, 96, 128) and max(Tq, Tk) <= 256
+    if q.dtype != torch.bfloat16 or H != Hkv:
+        return False
+    if o is not None and dh in (16, 32, 64, 96, 128) and max(Tq, Tk) <= 256:
+        return True
+    return dh % 64 == 0 and Tq <= 64 and Tk <= 256 and not causal
 
 
 def attention_bwd_owned(q, k, v, dout, dq, dk, dv, *, B, H, Tq, Tk, dh, q_strides, k_strides, v_strides, do_strides, dq_strides,
@@ -496,12 +500,14 @@ def attention_bwd_owned(q, k, v, dout, dq, dk, dv, *, B, H, Tq, Tk, dh, q_stride
     a.q, (a.q_sb, a.q_st) = q.data_ptr(), q_strides
     a.k, (a.k_sb, a.k_st) = k.data_ptr(), k_strides
     a.v, (a.v_sb, a.v_st) = v.data_ptr(), v_strides
-    a.out, (a.o_sb, a.o_st) = o.data_ptr(), o_strides
+    if o is not None:
+        a.out, (a.o_sb, a.o_st) = o.data_ptr(), o_strides
     a.dtype, a.scale, a.causal = dt(q), scale, int(causal)
     if key_mask is not None:
         a.key_mask = key_mask.data_ptr()
     fl = 10.0 * B * H * Tq * Tk * dh * (0.5 if causal else 1.0)
-    with _Timed(f"attn_bwd_tc_kernel[dh{dh},q{Tq},k{Tk}]", fl, 0.0):
+    small = o is not None and dh in (16, 32, 64, 96, 128) and max(Tq, Tk) <= 256
+    with _Timed(f"attn_{'bwd_tc' if small else 'x_bwd'}_kernel[dh{dh},q{Tq},k{Tk}]", fl, 0.0):
         _lib.check(_lib.load().tcavp_attention_bwd_owned(byref(a), _p(dout), _ll(do_strides[0]), _ll(do_strides[1]), _p(dq), _ll(dq_strides[0]),
                                                          _ll(dq_strides[1]), _p(dk), _ll(dk_strides[0]), _ll(dk_strides[1]), _p(dv),
                                                          _ll(dv_strides[0]), _ll(dv_strides[1]), dt(dk), _stream()), "tcavp_attention_bwd_owned")
