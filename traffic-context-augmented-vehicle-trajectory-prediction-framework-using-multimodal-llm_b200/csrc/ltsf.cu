@@ -60,6 +60,102 @@ __global__ void __launch_bounds__(256) nlinear_decode_kernel(const void* __restr
   }
 }
 
+// Register-tiled variants for a compile-time T_in: a thread owns one channel of NB scenes, so the history (and its projection)
+// lives in registers and every weight load (coalesced over channels, L1/L2 resident) feeds NB FMAs instead of one.
+constexpr int NB = 4;
+
+template <int T>
+__global__ void __launch_bounds__(256) ltsf_encode_tiled_kernel(const float* __restrict__ x, const float* __restrict__ wt,
+                                                                const float* __restrict__ bt, const float* __restrict__ we,
+                                                                const float* __restrict__ be, const float* __restrict__ pos,
+                                                                void* __restrict__ enc, int out_dtype, int B, int F, int C) {
+  const int c = threadIdx.x % C;
+  const int slot = threadIdx.x / C, slots = blockDim.x / C;
+  const long long b0 = ((long long)blockIdx.x * slots + slot) * NB;
+  if (b0 >= B) return;
+  float xp[NB][T];
+  const float btc = __ldg(bt + c);
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    const long long b = b0 + j < B ? b0 + j : B - 1;
+#pragma unroll
+    for (int s = 0; s < T; ++s) xp[j][s] = btc;
+    for (int f = 0; f < F; ++f) {
+      const float w = __ldg(wt + c * F + f);
+#pragma unroll
+      for (int s = 0; s < T; ++s) xp[j][s] = fmaf(w, __ldg(x + ((size_t)b * F + f) * T + s), xp[j][s]);
+    }
+  }
+  float last[NB];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    last[j] = xp[j][T - 1];
+#pragma unroll
+    for (int s = 0; s < T; ++s) xp[j][s] -= last[j];
+  }
+#pragma unroll 1
+  for (int t = 0; t < T; ++t) {
+    const float base = __ldg(be + (size_t)t * C + c) + __ldg(pos + (size_t)t * C + c);
+    float acc[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) acc[j] = base + last[j];
+#pragma unroll
+    for (int s = 0; s < T; ++s) {
+      const float w = __ldg(we + ((size_t)t * T + s) * C + c);
+#pragma unroll
+      for (int j = 0; j < NB; ++j) acc[j] = fmaf(w, xp[j][s], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j)
+      if (b0 + j < B) store_from_f(enc, ((size_t)(b0 + j) * T + t) * C + c, out_dtype, acc[j]);
+  }
+}
+
+template <int T>
+__global__ void __launch_bounds__(256) nlinear_decode_tiled_kernel(const void* __restrict__ enc, int enc_dtype, const float* __restrict__ wd,
+                                                                   const float* __restrict__ bd, const void* __restrict__ adj, int adj_dtype,
+                                                                   void* __restrict__ dec, int out_dtype, int B, int C, int To) {
+  const int c = threadIdx.x % C;
+  const int slot = threadIdx.x / C, slots = blockDim.x / C;
+  const long long b0 = ((long long)blockIdx.x * slots + slot) * NB;
+  if (b0 >= B) return;
+  float e[NB][T], last[NB];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    const long long b = b0 + j < B ? b0 + j : B - 1;
+#pragma unroll
+    for (int s = 0; s < T; ++s) e[j][s] = load_as_f(enc, ((size_t)b * T + s) * C + c, enc_dtype);
+    last[j] = e[j][T - 1];
+#pragma unroll
+    for (int s = 0; s < T; ++s) e[j][s] -= last[j];
+  }
+  // grid.y splits the horizon: more resident warps to hide the L2 / DRAM latency of the weight, lane-adjust and output traffic
+  const int t_per = (To + gridDim.y - 1) / gridDim.y;
+  const int t_lo = blockIdx.y * t_per, t_hi = min(To, t_lo + t_per);
+#pragma unroll 2
+  for (int t = t_lo; t < t_hi; ++t) {
+    const float base = __ldg(bd + (size_t)t * C + c);
+    float acc[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) acc[j] = base + last[j];
+#pragma unroll
+    for (int s = 0; s < T; ++s) {
+      const float w = __ldg(wd + ((size_t)t * T + s) * C + c);
+#pragma unroll
+      for (int j = 0; j < NB; ++j) acc[j] = fmaf(w, e[j][s], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      if (b0 + j < B) {
+        const size_t o = ((size_t)(b0 + j) * To + t) * C + c;
+        float v = acc[j];
+        if (adj) v += load_as_f(adj, o, adj_dtype);
+        store_from_f(dec, o, out_dtype, v);
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ float block_sum(float v, float* scratch) {
   v = warp_sum(v);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -84,7 +180,7 @@ __device__ __forceinline__ void scene_error(float px, float py, float gx, float 
 }
 
 // reference scripts/train.py:801-805 (fusion_layer, out_proj), 941-943 (+last input position), 945-962, 1302-1322.
-// One block per scene (grid-stride); warp w handles time steps w, w+8, ...; C <= 128, C % 32 == 0.
+// One block per scene (grid-stride); warp w handles time steps 4w .. 4w+3, 4w+32 .., ...; C <= 128, C % 32 == 0.
 // w1t / w2t are the transposed 64x64 weights ([in][out]) staged in shared memory: lanes read consecutive
 // outputs (conflict-free) while the input activation is a broadcast.
 template <int CPL>  // channels per lane = C / 32
@@ -100,8 +196,8 @@ __global__ void __launch_bounds__(256) fusion_head_kernel(const void* __restrict
   extern __shared__ float sm[];
   float* w1t = sm;                 // [C][C] : w1t[i*C + o] = w1[o*C + i]
   float* w2t = w1t + C * C;
-  float* act = w2t + C * C;        // [8 warps][C]
-  float* red = act + 8 * C;        // [8][4]
+  float* act = w2t + C * C;        // [8 warps][C][4 rows]
+  float* red = act + 8 * 4 * C;    // [8][4]
   for (int i = threadIdx.x; i < C * C; i += blockDim.x) {
     const int o = i / C, k = i % C;
     w1t[k * C + o] = __ldg(w1 + i);
@@ -109,66 +205,101 @@ __global__ void __launch_bounds__(256) fusion_head_kernel(const void* __restrict
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* my = act + warp * C;
+  // Each warp takes RW = 4 time steps at once: the activations of the four rows sit interleaved in shared memory ([k][4], one
+  // 16-byte broadcast read per k), so one pass over a weight matrix feeds 4 x CPL FMAs per two weight reads.
+  constexpr int RW = 4;
+  float4* my4 = reinterpret_cast<float4*>(act + warp * RW * C);     // [C] x (4 rows)
+  float* my = act + warp * RW * C;
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     float s_sqx = 0.f, s_sqy = 0.f, s_dist = 0.f, s_fde = 0.f;
-    for (int t = warp; t < T_out; t += 8) {
-      const size_t row = (size_t)b * T_out + t;
-      float v[CPL];
-      float s = 0.f;
+    for (int t0 = warp * RW; t0 < T_out; t0 += 8 * RW) {
+      float v[RW][CPL];
 #pragma unroll
-      for (int e = 0; e < CPL; ++e) {
-        v[e] = load_as_f(fused, row * C + lane + 32 * e, in_dtype);
-        s += v[e];
-      }
-      const float mean = warp_sum(s) / C;
-      float q = 0.f;
+      for (int r = 0; r < RW; ++r) {
+        const int t = t0 + r < T_out ? t0 + r : T_out - 1;          // tail rows recompute the last step (never stored)
+        const size_t row = (size_t)b * T_out + t;
+        float sum = 0.f;
 #pragma unroll
-      for (int e = 0; e < CPL; ++e) q += (v[e] - mean) * (v[e] - mean);
-      const float rstd = rsqrtf(warp_sum(q) / C + 1e-5f);
+        for (int e = 0; e < CPL; ++e) {
+          v[r][e] = load_as_f(fused, row * C + lane + 32 * e, in_dtype);
+          sum += v[r][e];
+        }
+        const float mean = warp_sum(sum) / C;
+        float q = 0.f;
 #pragma unroll
-      for (int e = 0; e < CPL; ++e) {
-        const int c = lane + 32 * e;
-        my[c] = (v[e] - mean) * rstd * __ldg(ln_w + c) + __ldg(ln_b + c);
+        for (int e = 0; e < CPL; ++e) q += (v[r][e] - mean) * (v[r][e] - mean);
+        const float rstd = rsqrtf(warp_sum(q) / C + 1e-5f);
+#pragma unroll
+        for (int e = 0; e < CPL; ++e) {
+          const int c = lane + 32 * e;
+          my[c * RW + r] = (v[r][e] - mean) * rstd * __ldg(ln_w + c) + __ldg(ln_b + c);
+        }
       }
       __syncwarp();
-      float h[CPL];
+      float h[RW][CPL];
 #pragma unroll
-      for (int e = 0; e < CPL; ++e) h[e] = __ldg(b1 + lane + 32 * e);
+      for (int e = 0; e < CPL; ++e) {
+        const float bb = __ldg(b1 + lane + 32 * e);
+#pragma unroll
+        for (int r = 0; r < RW; ++r) h[r][e] = bb;
+      }
       for (int k = 0; k < C; ++k) {
-        const float a = my[k];
+        const float4 a = my4[k];
 #pragma unroll
-        for (int e = 0; e < CPL; ++e) h[e] = fmaf(w1t[k * C + lane + 32 * e], a, h[e]);
+        for (int e = 0; e < CPL; ++e) {
+          const float w = w1t[k * C + lane + 32 * e];
+          h[0][e] = fmaf(w, a.x, h[0][e]);
+          h[1][e] = fmaf(w, a.y, h[1][e]);
+          h[2][e] = fmaf(w, a.z, h[2][e]);
+          h[3][e] = fmaf(w, a.w, h[3][e]);
+        }
       }
       __syncwarp();
 #pragma unroll
-      for (int e = 0; e < CPL; ++e) my[lane + 32 * e] = fmaxf(h[e], 0.f);
-      __syncwarp();
+      for (int e = 0; e < CPL; ++e)
 #pragma unroll
-      for (int e = 0; e < CPL; ++e) h[e] = __ldg(b2 + lane + 32 * e);
-      for (int k = 0; k < C; ++k) {
-        const float a = my[k];
-#pragma unroll
-        for (int e = 0; e < CPL; ++e) h[e] = fmaf(w2t[k * C + lane + 32 * e], a, h[e]);
-      }
+        for (int r = 0; r < RW; ++r) my[(lane + 32 * e) * RW + r] = fmaxf(h[r][e], 0.f);
       __syncwarp();
-      float o0 = 0.f, o1 = 0.f;
 #pragma unroll
       for (int e = 0; e < CPL; ++e) {
-        const int c = lane + 32 * e;
-        o0 = fmaf(__ldg(wo + c), h[e], o0);
-        o1 = fmaf(__ldg(wo + C + c), h[e], o1);
+        const float bb = __ldg(b2 + lane + 32 * e);
+#pragma unroll
+        for (int r = 0; r < RW; ++r) h[r][e] = bb;
       }
-      o0 = warp_sum(o0) + __ldg(bo) + __ldg(x + ((size_t)b * 2 + 0) * T_in + T_in - 1);
-      o1 = warp_sum(o1) + __ldg(bo + 1) + __ldg(x + ((size_t)b * 2 + 1) * T_in + T_in - 1);
-      if (lane == 0) {
-        decoded[((size_t)b * 2 + 0) * T_out + t] = o0;
-        decoded[((size_t)b * 2 + 1) * T_out + t] = o1;
-        if (y) {
-          float sqx, sqy, dist;
-          scene_error(o0, o1, y[((size_t)b * 2 + 0) * T_out + t], y[((size_t)b * 2 + 1) * T_out + t], norm_stat + (size_t)b * 4, sqx, sqy, dist);
-          s_sqx += sqx; s_sqy += sqy; s_dist += dist;
-          if (t == T_out - 1) s_fde = dist;
+      for (int k = 0; k < C; ++k) {
+        const float4 a = my4[k];
+#pragma unroll
+        for (int e = 0; e < CPL; ++e) {
+          const float w = w2t[k * C + lane + 32 * e];
+          h[0][e] = fmaf(w, a.x, h[0][e]);
+          h[1][e] = fmaf(w, a.y, h[1][e]);
+          h[2][e] = fmaf(w, a.z, h[2][e]);
+          h[3][e] = fmaf(w, a.w, h[3][e]);
+        }
+      }
+      __syncwarp();
+      const float xl0 = __ldg(x + ((size_t)b * 2 + 0) * T_in + T_in - 1), xl1 = __ldg(x + ((size_t)b * 2 + 1) * T_in + T_in - 1);
+#pragma unroll
+      for (int r = 0; r < RW; ++r) {
+        float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+        for (int e = 0; e < CPL; ++e) {
+          const int c = lane + 32 * e;
+          o0 = fmaf(__ldg(wo + c), h[r][e], o0);
+          o1 = fmaf(__ldg(wo + C + c), h[r][e], o1);
+        }
+        o0 = warp_sum(o0) + __ldg(bo) + xl0;
+        o1 = warp_sum(o1) + __ldg(bo + 1) + xl1;
+        const int t = t0 + r;
+        if (lane == 0 && t < T_out) {
+          decoded[((size_t)b * 2 + 0) * T_out + t] = o0;
+          decoded[((size_t)b * 2 + 1) * T_out + t] = o1;
+          if (y) {
+            float sqx, sqy, dist;
+            scene_error(o0, o1, y[((size_t)b * 2 + 0) * T_out + t], y[((size_t)b * 2 + 1) * T_out + t], norm_stat + (size_t)b * 4, sqx, sqy, dist);
+            s_sqx += sqx; s_sqy += sqy; s_dist += dist;
+            if (t == T_out - 1) s_fde = dist;
+          }
         }
       }
     }
@@ -230,6 +361,23 @@ extern "C" int tcavp_ltsf_encode(const float* x, const float* wt, const float* b
   TCAVP_REQUIRE(B >= 0 && F > 0 && C > 0 && T_in > 0 && T_in <= MAX_T_IN, "tcavp_ltsf_encode: bad shape (T_in=%d, max %d)", T_in, MAX_T_IN);
   if (B == 0) return TCAVP_OK;
   TCAVP_REQUIRE(x && wt && bt && we && be && pos && enc && DT_OK(out_dtype), "tcavp_ltsf_encode: bad pointer/dtype");
+  if (C <= 256 && 256 % C == 0) {      // register-tiled kernels for the history lengths the reference's drivers use
+    const int per_block = (256 / C) * NB;
+    const int grid = (B + per_block - 1) / per_block;
+#define TCAVP_ENC(T)                                                                                                          \
+  case T:                                                                                                                      \
+    ltsf_encode_tiled_kernel<T><<<grid, 256, 0, STREAM(stream)>>>(x, wt, bt, we, be, pos, enc, out_dtype, B, F, C);              \
+    return check_launch("ltsf_encode_kernel")
+    switch (T_in) {
+      TCAVP_ENC(6);
+      TCAVP_ENC(10);
+      TCAVP_ENC(15);
+      TCAVP_ENC(18);
+      TCAVP_ENC(20);
+      default: break;
+    }
+#undef TCAVP_ENC
+  }
   const long long total = (long long)B * C;
   ltsf_encode_kernel<<<(int)((total + 127) / 128), 128, 0, STREAM(stream)>>>(x, wt, bt, we, be, pos, enc, out_dtype, B, F, C, T_in);
   return check_launch("ltsf_encode_kernel");
@@ -240,6 +388,25 @@ extern "C" int tcavp_nlinear_decode(const void* enc, int enc_dtype, const float*
   TCAVP_REQUIRE(B >= 0 && C > 0 && T_in > 0 && T_in <= MAX_T_IN && T_out > 0, "tcavp_nlinear_decode: bad shape");
   if (B == 0) return TCAVP_OK;
   TCAVP_REQUIRE(enc && wd && bd && dec && DT_OK(enc_dtype) && DT_OK(out_dtype) && (!lane_adj || DT_OK(adj_dtype)), "tcavp_nlinear_decode: bad pointer/dtype");
+  if (C <= 256 && 256 % C == 0) {
+    const int per_block = (256 / C) * NB;
+    const int grid = (B + per_block - 1) / per_block;
+    int ty = (sm_count() * 6 + grid - 1) / grid;          // aim at ~6 blocks per SM
+    ty = ty < 1 ? 1 : (ty > (T_out + 3) / 4 ? (T_out + 3) / 4 : ty);
+#define TCAVP_DEC(T)                                                                                                                          \
+  case T:                                                                                                                                      \
+    nlinear_decode_tiled_kernel<T><<<dim3(grid, ty), 256, 0, STREAM(stream)>>>(enc, enc_dtype, wd, bd, lane_adj, adj_dtype, dec, out_dtype, B, C, T_out);  \
+    return check_launch("nlinear_decode_kernel")
+    switch (T_in) {
+      TCAVP_DEC(6);
+      TCAVP_DEC(10);
+      TCAVP_DEC(15);
+      TCAVP_DEC(18);
+      TCAVP_DEC(20);
+      default: break;
+    }
+#undef TCAVP_DEC
+  }
   const long long total = (long long)B * C;
   nlinear_decode_kernel<<<(int)((total + 127) / 128), 128, 0, STREAM(stream)>>>(enc, enc_dtype, wd, bd, lane_adj, adj_dtype, dec, out_dtype, B, C, T_in, T_out);
   return check_launch("nlinear_decode_kernel");
@@ -254,8 +421,8 @@ extern "C" int tcavp_fusion_head(const void* fused, int in_dtype, const float* l
   if (B == 0) return TCAVP_OK;
   TCAVP_REQUIRE(fused && ln_w && ln_b && w1 && b1 && w2 && b2 && wo && bo && x && decoded && DT_OK(in_dtype), "tcavp_fusion_head: bad pointer/dtype");
   TCAVP_REQUIRE(!y || (norm_stat && metrics), "tcavp_fusion_head: y needs norm_stat and metrics");
-  const size_t smem = (size_t)(2 * C * C + 8 * C + 32) * sizeof(float);
-  const int grid = B < sm_count() * 2 ? B : sm_count() * 2;
+  const size_t smem = (size_t)(2 * C * C + 8 * 4 * C + 32) * sizeof(float);
+  const int grid = B < sm_count() * 5 ? B : sm_count() * 5;      // 41 KB of shared memory per block: five resident blocks per SM
 #define LAUNCH(CPL)                                                                                                            \
   do {                                                                                                                         \
     TCAVP_CUDA(cudaFuncSetAttribute(fusion_head_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
