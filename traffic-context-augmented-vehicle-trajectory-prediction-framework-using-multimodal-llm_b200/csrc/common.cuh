@@ -81,6 +81,8 @@ struct EpilogueParams {
   int remap_gi, remap_go, remap_off;
   const float* rope; int rope_L, rope_dh, rope_cols;   // fused rotary embedding on adjacent column pairs
   const float* row_scale;                              // per-row factor applied to the raw accumulators (fused RMSNorm)
+  float* sumsq_out;                                    // += sum of squares of the final output row (fused RMSNorm statistics)
+  const float* row_sumsq; float ss_inv, ss_eps;        // row factor rsqrt(row_sumsq[m] * ss_inv + ss_eps) (alternative to row_scale)
   __nv_bfloat16* aux; int ld_aux;                      // SwiGLU only: raw (row-scaled) gate/up accumulators for the backward pass
 };
 

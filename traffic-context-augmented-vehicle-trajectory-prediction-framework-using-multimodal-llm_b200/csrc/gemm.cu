@@ -161,7 +161,8 @@ enum { EPI_VEC_OUT = 1, EPI_VEC_RES = 2, EPI_VEC_BIAS = 4,
 
 // Epilogue of 32 accumulator columns [nacc0, nacc0+32) of row m for one thread.  The interior-tile path (full chunk,
 // 16-byte aligned rows) is branch-light and fully vectorised; ragged edges take the scalar path.
-__device__ __forceinline__ void epilogue_chunk(const EpilogueParams& p, int m, int pos, int nacc0, const uint32_t (&r)[32], float rs, int flags) {
+__device__ __forceinline__ void epilogue_chunk(const EpilogueParams& p, int m, int pos, int nacc0, const uint32_t (&r)[32], float rs, int flags,
+                                               float& ssq) {
   if (m >= p.M) return;
   const int mo = remap_row(p.remap_gi, p.remap_go, p.remap_off, m);
   float o[32];
@@ -257,6 +258,11 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueParams& p, int m, i
       for (int j = 0; j < 32; ++j)
         if (j < cnt && n0 + j < p.N) o[j] += load_as_f(p.residual, (size_t)mo * p.ldr + n0 + j, p.res_dtype);
     }
+  }
+  if (p.sumsq_out) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < cnt && (full || n0 + j < p.N)) ssq = fmaf(o[j], o[j], ssq);
   }
   if ((flags & EPI_VEC_OUT) && full) {
     if (p.out_dtype == TCAVP_BF16) {
@@ -409,15 +415,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       mbar_wait(tmem_full_bar + 8 * acc, (it >> 1) & 1);
       tc_fence_after();
       const int m = m0 + quarter * 32 + lane;
-      const float rs = (ep.row_scale && m < M) ? __ldg(ep.row_scale + m) : 1.f;
+      float rs = 1.f;
+      if (m < M) {
+        if (ep.row_scale) rs = __ldg(ep.row_scale + m);
+        else if (ep.row_sumsq) rs = rsqrtf(__ldg(ep.row_sumsq + m) * ep.ss_inv + ep.ss_eps);
+      }
+      float ssq = 0.f;
       const int pos = ep.rope_cols > 0 ? m % ep.rope_L : 0;
 #pragma unroll 1
       for (int c = chunk0; c < BLOCK_N / 32; c += NUM_EPI_WARPS / 4) {
         if (n0 + c * 32 >= Nacc) break;   // warp-uniform
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + c * 32, r);
-        epilogue_chunk(ep, m, pos, n0 + c * 32, r, rs, flags);
+        epilogue_chunk(ep, m, pos, n0 + c * 32, r, rs, flags, ssq);
       }
+      if (ep.sumsq_out && m < M) atomicAdd(ep.sumsq_out + remap_row(ep.remap_gi, ep.remap_go, ep.remap_off, m), ssq);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty_bar + 8 * acc);
@@ -604,7 +616,12 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       mbar_wait(tmem_full_bar + 8 * acc, (it >> 1) & 1);
       tc_fence_after();
       const int m = m0 + quarter * 32 + lane;
-      const float rs = (ep.row_scale && m < M) ? __ldg(ep.row_scale + m) : 1.f;
+      float rs = 1.f;
+      if (m < M) {
+        if (ep.row_scale) rs = __ldg(ep.row_scale + m);
+        else if (ep.row_sumsq) rs = rsqrtf(__ldg(ep.row_sumsq + m) * ep.ss_inv + ep.ss_eps);
+      }
+      float ssq = 0.f;
       const int pos = ep.rope_cols > 0 ? m % ep.rope_L : 0;
       if (!(flags & DBG_NO_EPI)) {
 #pragma unroll 1
@@ -612,8 +629,9 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           if (n0 + c * 32 >= Nacc) break;   // warp-uniform
           uint32_t r[32];
           tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + c * 32, r);
-          epilogue_chunk(ep, m, pos, n0 + c * 32, r, rs, flags);
+          epilogue_chunk(ep, m, pos, n0 + c * 32, r, rs, flags, ssq);
         }
+        if (ep.sumsq_out && m < M) atomicAdd(ep.sumsq_out + remap_row(ep.remap_gi, ep.remap_go, ep.remap_off, m), ssq);
       }
       tc_fence_before();
       __syncwarp();
@@ -842,6 +860,11 @@ extern "C" int tcavp_gemm(const tcavp_gemm_args* a, tcavp_stream_t stream_) {
   ep.remap_gi = a->remap_gi; ep.remap_go = a->remap_go; ep.remap_off = a->remap_off;
   ep.row_scale = a->row_scale;
   ep.rope = a->rope_cos_sin; ep.rope_L = a->rope_L; ep.rope_dh = a->rope_dh; ep.rope_cols = a->rope_cos_sin ? a->rope_cols : 0;
+  ep.sumsq_out = a->sumsq_out;
+  ep.row_sumsq = a->row_sumsq; ep.ss_inv = a->sumsq_inv_cols; ep.ss_eps = a->sumsq_eps;
+  TCAVP_REQUIRE(!(a->row_scale && a->row_sumsq), "tcavp_gemm: row_scale and row_sumsq are exclusive");
+  TCAVP_REQUIRE((!a->sumsq_out && !a->row_sumsq) || a->in_dtype == TCAVP_BF16, "tcavp_gemm: sumsq_out / row_sumsq need bf16 operands");
+  TCAVP_REQUIRE(!a->sumsq_out || a->act != TCAVP_ACT_SWIGLU, "tcavp_gemm: sumsq_out is not defined for the SwiGLU epilogue");
   ep.aux = reinterpret_cast<__nv_bfloat16*>(a->aux_out); ep.ld_aux = a->ld_aux;
   if (ep.aux) {
     TCAVP_REQUIRE(a->act == TCAVP_ACT_SWIGLU && a->in_dtype == TCAVP_BF16, "tcavp_gemm: aux_out needs act SWIGLU and bf16 operands");

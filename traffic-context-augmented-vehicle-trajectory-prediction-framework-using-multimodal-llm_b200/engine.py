@@ -284,20 +284,35 @@ class Engine:
         attn = self._new(M, nh * dh)
         mid = self._new(M, I)
         rope = (table, L, dh, (nh + nkv) * dh) if m["fuse_rope"] else None
-        for ly in m["layers"]:
-            ops.row_rstd(xs, rstd, rows=M, cols=H, ldx=Kx, eps=m["eps"])
+        # RMSNorm statistics ride on the GEMMs that write the residual stream: o_proj / down_proj add each row's sum of squares
+        # into a zeroed [2 * layers, M] table and the next projection turns it into rstd in its epilogue, so the only separate
+        # pass over the residual stream is the one before the first layer (bf16 tensor-core path; fp32 keeps tcavp_row_rstd).
+        nl = len(m["layers"])
+        fuse_ss = self.act == torch.bfloat16 and not os.environ.get("TCAVP_NO_FUSE_RSTD")
+        ss = torch.zeros(2 * nl, M, dtype=torch.float32, device=self.dev) if fuse_ss else None
+        for li, ly in enumerate(m["layers"]):
+            if fuse_ss and li > 0:
+                norm1 = dict(row_sumsq=(ss[2 * li - 1], H, m["eps"]))
+            else:
+                ops.row_rstd(xs, rstd, rows=M, cols=H, ldx=Kx, eps=m["eps"])
+                norm1 = dict(row_scale=rstd)
             if kx:
                 ops.gemm(xs, ly["a_cat"], xs[:, H:], M=M, N=m["n_lora"], K=H, lda=Kx, ldo=Kx)
-            ops.gemm(xs, ly["wqkv"], qkv, M=M, N=nqkv, K=Kx, lda=Kx, rope=rope, row_scale=rstd)
+            ops.gemm(xs, ly["wqkv"], qkv, M=M, N=nqkv, K=Kx, lda=Kx, rope=rope, **norm1)
             if rope is None:
                 ops.rope_(qkv, rows=M, L=L, ld=nqkv, n_q_heads=nh, n_k_heads=nkv, dh=dh, table=table)
             ops.attention(qkv, qkv[:, nh * dh:], qkv[:, (nh + nkv) * dh:], attn, B=B, H=nh, Hkv=nkv, Tq=L, Tk=L, dh=dh,
                           q_strides=(L * nqkv, nqkv), k_strides=(L * nqkv, nqkv), v_strides=(L * nqkv, nqkv),
                           o_strides=(L * nh * dh, nh * dh), scale=dh ** -0.5, causal=True, key_mask=mask)
-            ops.gemm(attn, ly["wo"], x, ldo=Kx, residual=x, ldr=Kx)
-            ops.row_rstd(xs, rstd, rows=M, cols=H, ldx=Kx, eps=m["eps"])
-            ops.gemm(xs, ly["wgu"], mid, M=M, K=H, lda=Kx, act=ops.ACT_SWIGLU, row_scale=rstd)
-            ops.gemm(mid, ly["wdown"], x, ldo=Kx, residual=x, ldr=Kx)
+            if fuse_ss:
+                ops.gemm(attn, ly["wo"], x, ldo=Kx, residual=x, ldr=Kx, sumsq_out=ss[2 * li])
+                ops.gemm(xs, ly["wgu"], mid, M=M, K=H, lda=Kx, act=ops.ACT_SWIGLU, row_sumsq=(ss[2 * li], H, m["eps"]))
+                ops.gemm(mid, ly["wdown"], x, ldo=Kx, residual=x, ldr=Kx, sumsq_out=ss[2 * li + 1] if li + 1 < nl else None)
+            else:
+                ops.gemm(attn, ly["wo"], x, ldo=Kx, residual=x, ldr=Kx)
+                ops.row_rstd(xs, rstd, rows=M, cols=H, ldx=Kx, eps=m["eps"])
+                ops.gemm(xs, ly["wgu"], mid, M=M, K=H, lda=Kx, act=ops.ACT_SWIGLU, row_scale=rstd)
+                ops.gemm(mid, ly["wdown"], x, ldo=Kx, residual=x, ldr=Kx)
         return ops.rmsnorm(xs, m["norm"], self._new(M, H), eps=m["eps"], rows=M, cols=H, ldi=Kx)
 
     def ltsf_encode(self, x, B):

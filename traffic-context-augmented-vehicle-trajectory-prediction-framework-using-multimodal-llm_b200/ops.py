@@ -26,6 +26,7 @@ class GemmArgs(Structure):
                 ("remap_gi", c_int), ("remap_go", c_int), ("remap_off", c_int),
                 ("rope_cos_sin", c_void_p), ("rope_L", c_int), ("rope_dh", c_int), ("rope_cols", c_int),
                 ("row_scale", c_void_p),
+                ("sumsq_out", c_void_p), ("row_sumsq", c_void_p), ("sumsq_inv_cols", c_float), ("sumsq_eps", c_float),
                 ("aux_out", c_void_p), ("ld_aux", c_int)]
 
 
@@ -128,7 +129,7 @@ def _need_cuda(*ts):
 
 
 def gemm(a, w, out, *, M=None, N=None, K=None, lda=None, ldw=None, ldo=None, bias=None, residual=None, ldr=None,
-         act=ACT_NONE, remap=(0, 0, 0), rope=None, row_scale=None, aux_out=None):
+         act=ACT_NONE, remap=(0, 0, 0), rope=None, row_scale=None, aux_out=None, sumsq_out=None, row_sumsq=None):
     """out = act(a @ w.T + bias) + residual.  a: [M, >=K] row-major (lda = a.stride(0)), w: [N, >=K]."""
     _need_cuda(a, w, out, bias, residual)
     g = GemmArgs()
@@ -152,6 +153,15 @@ def gemm(a, w, out, *, M=None, N=None, K=None, lda=None, ldw=None, ldo=None, bia
         if row_scale.dtype != torch.float32:
             raise TypeError("gemm: row_scale must be fp32")
         g.row_scale = row_scale.data_ptr()
+    if sumsq_out is not None:   # += per-row sum of squares of the final output (fp32 [rows], zeroed by the caller)
+        if sumsq_out.dtype != torch.float32:
+            raise TypeError("gemm: sumsq_out must be fp32")
+        g.sumsq_out = sumsq_out.data_ptr()
+    if row_sumsq is not None:   # (tensor fp32 [M], columns, eps): row factor rsqrt(sumsq / columns + eps)
+        t, ncols, eps = row_sumsq
+        if t.dtype != torch.float32:
+            raise TypeError("gemm: row_sumsq must be fp32")
+        g.row_sumsq, g.sumsq_inv_cols, g.sumsq_eps = t.data_ptr(), 1.0 / ncols, eps
     if aux_out is not None:  # SwiGLU: raw gate/up accumulators (bf16, interleaved) for the backward pass
         if aux_out.dtype != torch.bfloat16:
             raise TypeError("gemm: aux_out must be bf16")
