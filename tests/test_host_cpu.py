@@ -100,3 +100,33 @@ def test_c_abi_library_exports_every_declared_symbol(lib_built):
     assert lib_built.tcavp_version() == 100
     import tcavp_b200.lib as L
     assert declared == set(L.EXPORTS)
+
+
+def test_collate_matches_the_reference_collate_fn():
+    """tcavp_b200.custom_collate_fn against the output of the UNMODIFIED reference custom_collate_fn (scripts/train.py:301-347) on
+    the same samples (golden minted by oracle/make_collate_golden.py): same keys, values, dtypes; plus the packed extras."""
+    import torch
+    import tcavp_b200 as T
+    g = torch.load(os.path.join(ROOT, "tests", "golden", "collate_b5.pt"), weights_only=False)
+    got = T.custom_collate_fn(g["samples"], pin=False)
+    want = g["collated"]
+    assert set(want) <= set(got)
+    for k, v in want.items():
+        if torch.is_tensor(v):
+            assert got[k].dtype == v.dtype and got[k].shape == v.shape, k
+            assert torch.equal(got[k], v), k
+        else:
+            assert got[k] == v, k
+    assert got["lane_polygon_len_t"].tolist() == want["lane_polygon_len"] and got["lane_polygon_len_t"].dtype == torch.int32
+    assert torch.allclose(got["norm_stat_t"], torch.tensor(want["norm_stat"], dtype=torch.float32))
+    # one arena: every tensor is a 16-byte aligned view of the same buffer, and a (CPU) round trip through to_device keeps the values
+    base = got.arena.data_ptr()
+    for key, shape, dtype, off, nb in got.plan:
+        assert got[key].data_ptr() == base + off and off % 16 == 0
+    moved = got.to_device("cpu")
+    for k, v in want.items():
+        if torch.is_tensor(v):
+            assert torch.equal(moved[k], v), k
+    # ragged / single-sample batches
+    one = T.custom_collate_fn(g["samples"][3:4], pin=False)
+    assert one["input_ids"].shape == (1, 12) and one["labels"].min() >= 0
