@@ -649,6 +649,331 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// Quad variant: a 4-CTA cluster = TWO CTA pairs on vertically adjacent 256-row tiles that share the W tile.  Each CTA stages its
+// own 128 rows of A and ONE QUARTER (64 rows) of the W tile, which TMA multicasts into the same-rank CTA of the other pair, so an
+// SM fetches 24 KB per k-block from L2 instead of 32 KB (the L2 -> SM path is the largest data-movement energy term of the
+// power-capped mainloop).  A stage is released only when BOTH pairs' MMAs have read it (empty barriers count 2, commits are
+// multicast to all four CTAs); everything else is the pair kernel.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d_pair_mc(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_mask(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // shared::cta address with the CTA-in-pair bit cleared = the pair leader's copy
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_quad_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, EpilogueParams ep,
+                    int M, int Nacc, int K, int flags) {
+  using C = PairCfg<BLOCK_N>;
+  constexpr int PAIR_M = 2 * BLOCK_M, QUAD_M = 4 * BLOCK_M, QUARTER_N = BLOCK_N / 4;
+  const uint32_t rank4 = cluster_ctarank();
+  const uint32_t pr = rank4 >> 1, r = rank4 & 1;     // pair within the cluster, rank within the pair
+  const bool leader = r == 0;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_base + C::STAGES * A_STAGE_BYTES;
+  const uint32_t bars = smem_base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t full_bar = bars;
+  const uint32_t empty_bar = bars + 8 * C::STAGES;
+  const uint32_t tmem_full_bar = bars + 16 * C::STAGES;
+  const uint32_t tmem_empty_bar = tmem_full_bar + 16;
+  const uint32_t tmem_slot = tmem_empty_bar + 16;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_n = (Nacc + BLOCK_N - 1) / BLOCK_N;
+  const int tiles_m = (M + QUAD_M - 1) / QUAD_M;
+  const int num_units = tiles_m * tiles_n;
+  const int unit0 = blockIdx.x >> 2, unit_stride = gridDim.x >> 2;
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  const uint16_t pair_mask = (uint16_t)(3u << (2 * pr));        // both CTAs of my pair
+  const uint16_t col_mask = (uint16_t)((1u << r) | (4u << r));   // the CTAs of both pairs that hold W half r
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 2);        // one commit from each pair's MMA thread
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tmem_full_bar + 8 * s, 1);
+      mbar_init(tmem_empty_bar + 8 * s, 2 * NUM_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (all four CTAs) =====================
+    if (lane == 0) {
+      const uint32_t leader_full = full_bar & PEER_BIT_MASK;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = unit0; unit < num_units; unit += unit_stride) {
+        const int m0 = (unit / tiles_n) * QUAD_M + (int)pr * PAIR_M + (int)r * BLOCK_M;
+        const int n0 = (unit % tiles_n) * BLOCK_N + (int)r * C::HALF_N + (int)pr * QUARTER_N;   // my quarter of the W tile
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          if (leader) mbar_expect_tx(full_bar + 8 * stage, 2 * C::STAGE_BYTES);
+          tma_load_2d_pair(smem_a + stage * A_STAGE_BYTES, &tma_a, leader_full + 8 * stage, kb * BLOCK_K, m0);
+          tma_load_2d_pair_mc(smem_b + stage * C::B_STAGE_BYTES + pr * (QUARTER_N * BLOCK_K * 2), &tma_b, leader_full + 8 * stage, kb * BLOCK_K, n0,
+                              col_mask);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (the leader CTA of each pair) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(PAIR_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int unit = unit0; unit < num_units; unit += unit_stride, ++it) {
+        const int acc = it & 1;
+        mbar_wait(tmem_empty_bar + 8 * acc, ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar + 8 * stage, phase);
+          tc_fence_after();
+          const int k_left = K - kb * BLOCK_K;
+          const int ksteps = k_left >= BLOCK_K ? BLOCK_K / UMMA_K : (k_left + UMMA_K - 1) / UMMA_K;
+          const uint32_t a_addr = smem_a + stage * A_STAGE_BYTES;
+          const uint32_t b_addr = smem_b + stage * C::B_STAGE_BYTES;
+          for (int k = 0; k < ksteps; ++k) {
+            umma_bf16_pair(tmem_d, umma_smem_desc(a_addr + k * UMMA_K * 2), umma_smem_desc(b_addr + k * UMMA_K * 2), idesc,
+                           (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_pair_mask(empty_bar + 8 * stage, (uint16_t)0xF);       // the stage is also written by the other pair's producers
+          if (kb == num_kb - 1) umma_commit_pair_mask(tmem_full_bar + 8 * acc, pair_mask);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2.., every CTA drains its own 128 rows) =====================
+    const int quarter = warp & 3;
+    const int chunk0 = (warp - 2) >> 2;
+    const uint32_t leader_tmem_empty = mapa_shared(tmem_empty_bar, 2 * pr);
+    int it = 0;
+    for (int unit = unit0; unit < num_units; unit += unit_stride, ++it) {
+      const int acc = it & 1;
+      const int m0 = (unit / tiles_n) * QUAD_M + (int)pr * PAIR_M + (int)r * BLOCK_M;
+      const int n0 = (unit % tiles_n) * BLOCK_N;
+      mbar_wait(tmem_full_bar + 8 * acc, (it >> 1) & 1);
+      tc_fence_after();
+      const int m = m0 + quarter * 32 + lane;
+      float rs = 1.f;
+      if (m < M) {
+        if (ep.row_scale) rs = __ldg(ep.row_scale + m);
+        else if (ep.row_sumsq) rs = rsqrtf(__ldg(ep.row_sumsq + m) * ep.ss_inv + ep.ss_eps);
+      }
+      float ssq = 0.f;
+      const int pos = ep.rope_cols > 0 ? m % ep.rope_L : 0;
+#pragma unroll 1
+      for (int c = chunk0; c < BLOCK_N / 32; c += NUM_EPI_WARPS / 4) {
+        if (n0 + c * 32 >= Nacc) break;   // warp-uniform
+        uint32_t rr[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + c * 32, rr);
+        epilogue_chunk(ep, m, pos, n0 + c * 32, rr, rs, flags, ssq);
+      }
+      if (ep.sumsq_out && m < M) atomicAdd(ep.sumsq_out + remap_row(ep.remap_gi, ep.remap_go, ep.remap_off, m), ssq);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(leader_tmem_empty + 8 * acc);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Wide variant for long contractions (K >= 2048: down_proj, every 7B-class projection): a CTA pair computes a 512 x 256 tile,
+// each CTA accumulating 256 x 256 fp32 = ALL 512 TMEM columns (rows [0,128) in columns [0,256), rows [128,256) in [256,512)).
+// Per k-block an SM stages 32 KB of A + 16 KB of W for 8.4 MFLOP (175 FLOP per staged byte against 128 for the pair kernel,
+// and one W fetch from shared memory feeds two 128-row MMAs), which is what the power-capped mainloop pays for.  The price is
+// a single accumulator buffer: the epilogue of a tile is not hidden behind the next tile's MMAs (only behind its TMA prefetch),
+// ~4-8k cycles against >= 32 x 1024 cycles of MMAs per tile at K >= 2048.
+// ------------------------------------------------------------------------------------------------
+struct WideCfg {
+  static constexpr int BLOCK_N = 256, HALF_N = 128;
+  static constexpr int A_BYTES = 2 * A_STAGE_BYTES;                 // 256 rows x 64 x bf16
+  static constexpr int B_BYTES = HALF_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;             // 48 KB
+  static constexpr int STAGES = 4;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_wide_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, EpilogueParams ep,
+                    int M, int Nacc, int K, int flags) {
+  using C = WideCfg;
+  constexpr int CTA_M = 2 * BLOCK_M, PAIR_M = 4 * BLOCK_M;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_base + C::STAGES * C::A_BYTES;
+  const uint32_t bars = smem_base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t full_bar = bars;
+  const uint32_t empty_bar = bars + 8 * C::STAGES;
+  const uint32_t tmem_full_bar = bars + 16 * C::STAGES;   // 1 x 8 (+8 pad)
+  const uint32_t tmem_empty_bar = tmem_full_bar + 16;     // 2 x 8: one per 128-row half
+  const uint32_t tmem_slot = tmem_empty_bar + 16;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_n = (Nacc + C::BLOCK_N - 1) / C::BLOCK_N;
+  const int tiles_m = (M + PAIR_M - 1) / PAIR_M;
+  const int num_units = tiles_m * tiles_n;
+  const int unit0 = blockIdx.x >> 1, unit_stride = gridDim.x >> 1;
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    for (int h = 0; h < 2; ++h) mbar_init(tmem_empty_bar + 8 * h, 2 * NUM_EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      const uint32_t leader_full = mapa_shared(full_bar, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = unit0; unit < num_units; unit += unit_stride) {
+        const int m0 = (unit / tiles_n) * PAIR_M + (int)cta_rank * CTA_M;
+        const int n0 = (unit % tiles_n) * C::BLOCK_N + (int)cta_rank * C::HALF_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          if (leader) mbar_expect_tx(full_bar + 8 * stage, 2 * C::STAGE_BYTES);
+          tma_load_2d_pair(smem_a + stage * C::A_BYTES, &tma_a, leader_full + 8 * stage, kb * BLOCK_K, m0);              // 256 rows
+          tma_load_2d_pair(smem_b + stage * C::B_BYTES, &tma_b, leader_full + 8 * stage, kb * BLOCK_K, n0);              // 128 rows
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(2 * BLOCK_M, C::BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int unit = unit0; unit < num_units; unit += unit_stride, ++it) {
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar + 8 * stage, phase);
+          tc_fence_after();
+          const int k_left = K - kb * BLOCK_K;
+          const int ksteps = k_left >= BLOCK_K ? BLOCK_K / UMMA_K : (k_left + UMMA_K - 1) / UMMA_K;
+          const uint32_t a_addr = smem_a + stage * C::A_BYTES;
+          const uint32_t b_addr = smem_b + stage * C::B_BYTES;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (kb == 0) {     // this half's accumulator columns must have been drained by the previous tile's epilogue
+              mbar_wait(tmem_empty_bar + 8 * h, (it & 1) ^ 1);
+              tc_fence_after();
+            }
+            for (int k = 0; k < ksteps; ++k) {
+              umma_bf16_pair(tmem_base + h * C::BLOCK_N, umma_smem_desc(a_addr + h * A_STAGE_BYTES + k * UMMA_K * 2),
+                             umma_smem_desc(b_addr + k * UMMA_K * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit_pair(empty_bar + 8 * stage);
+          if (kb == num_kb - 1) umma_commit_pair(tmem_full_bar);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: every CTA drains its own 256 rows, half by half =====================
+    const int quarter = warp & 3;
+    const int chunk0 = (warp - 2) >> 2;
+    const uint32_t leader_tmem_empty = mapa_shared(tmem_empty_bar, 0);
+    int it = 0;
+    for (int unit = unit0; unit < num_units; unit += unit_stride, ++it) {
+      const int m_cta = (unit / tiles_n) * PAIR_M + (int)cta_rank * CTA_M;
+      const int n0 = (unit % tiles_n) * C::BLOCK_N;
+      mbar_wait(tmem_full_bar, it & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int m = m_cta + h * BLOCK_M + quarter * 32 + lane;
+        float rs = 1.f;
+        if (m < M) {
+          if (ep.row_scale) rs = __ldg(ep.row_scale + m);
+          else if (ep.row_sumsq) rs = rsqrtf(__ldg(ep.row_sumsq + m) * ep.ss_inv + ep.ss_eps);
+        }
+        float ssq = 0.f;
+        const int pos = ep.rope_cols > 0 ? m % ep.rope_L : 0;
+#pragma unroll 1
+        for (int c = chunk0; c < C::BLOCK_N / 32; c += NUM_EPI_WARPS / 4) {
+          if (n0 + c * 32 >= Nacc) break;   // warp-uniform
+          uint32_t rr[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + h * C::BLOCK_N + c * 32, rr);
+          epilogue_chunk(ep, m, pos, n0 + c * 32, rr, rs, flags, ssq);
+        }
+        if (ep.sumsq_out && m < M) atomicAdd(ep.sumsq_out + remap_row(ep.remap_gi, ep.remap_go, ep.remap_off, m), ssq);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(leader_tmem_empty + 8 * h);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side: TMA descriptors through the driver entry point (no link-time dependency on libcuda)
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -689,13 +1014,14 @@ static int make_map(CUtensorMap* map, const void* base, int rows, int cols, int 
   return TCAVP_OK;
 }
 
-// TCAVP_GEMM_CLUSTER (A/B testing): 1 = no clusters, 2 = 2-CTA clusters with TMA multicast of W, 3 = CTA pairs (cta_group::2, default)
+// TCAVP_GEMM_CLUSTER (A/B testing): 1 = no clusters, 2 = 2-CTA clusters with TMA multicast of W, 3 = CTA pairs (cta_group::2, default),
+// 4 = two CTA pairs per 4-CTA cluster sharing the W tile through TMA multicast
 static int cluster_pref() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("TCAVP_GEMM_CLUSTER");
     v = e ? atoi(e) : 3;
-    if (v < 1 || v > 3) v = 3;
+    if (v < 1 || v > 4) v = 3;
   }
   return v;
 }
@@ -767,6 +1093,90 @@ static int launch_tc_pair(const tcavp_gemm_args& a, const EpilogueParams& ep, cu
   cfg.numAttrs = 1;
   TCAVP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<BLOCK_N>, ma, mb, ep, a.M, a.N, a.K, flags));
   return check_launch("gemm_tc_pair_kernel");
+}
+
+template <int BLOCK_N>
+static int launch_tc_quad(const tcavp_gemm_args& a, const EpilogueParams& ep, cudaStream_t stream) {
+  using C = PairCfg<BLOCK_N>;
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, a.A, a.M, a.K, a.lda, BLOCK_M);
+  if (rc) return rc;
+  rc = make_map(&mb, a.W, a.N, a.K, a.ldw, BLOCK_N / 4);
+  if (rc) return rc;
+  TCAVP_CUDA(cudaFuncSetAttribute(gemm_tc_quad_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  TCAVP_CUDA(cudaFuncSetAttribute(gemm_tc_quad_kernel<BLOCK_N>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
+  const int tiles_m = (a.M + 4 * BLOCK_M - 1) / (4 * BLOCK_M), tiles_n = (a.N + BLOCK_N - 1) / BLOCK_N;
+  const int units = tiles_m * tiles_n;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 4;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  static int max_quads = 0;       // co-resident 4-CTA clusters (GPC boundaries may leave a few SMs unused)
+  if (max_quads == 0) {
+    cfg.gridDim = dim3(sm_count() / 4 * 4);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_quad_kernel<BLOCK_N>, &cfg) != cudaSuccess || n <= 0) n = sm_count() / 4 - 2;
+    max_quads = n;
+  }
+  const int grid = (units < max_quads ? units : max_quads) * 4;
+  cfg.gridDim = dim3(grid);
+  const size_t osz = ep.out_dtype == TCAVP_BF16 ? 2 : 4, rsz = ep.res_dtype == TCAVP_BF16 ? 2 : 4;
+  int flags = 0;
+  if (((size_t)ep.ldo * osz) % 32 == 0 && (reinterpret_cast<uintptr_t>(ep.out) % 32) == 0) flags |= EPI_VEC_OUT;
+  if (ep.residual && ((size_t)ep.ldr * rsz) % 32 == 0 && (reinterpret_cast<uintptr_t>(ep.residual) % 32) == 0) flags |= EPI_VEC_RES;
+  if (ep.bias && (reinterpret_cast<uintptr_t>(ep.bias) % 16) == 0) flags |= EPI_VEC_BIAS;
+  TCAVP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_quad_kernel<BLOCK_N>, ma, mb, ep, a.M, a.N, a.K, flags));
+  return check_launch("gemm_tc_quad_kernel");
+}
+
+static int launch_tc_wide(const tcavp_gemm_args& a, const EpilogueParams& ep, cudaStream_t stream) {
+  using C = WideCfg;
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, a.A, a.M, a.K, a.lda, 2 * BLOCK_M);
+  if (rc) return rc;
+  rc = make_map(&mb, a.W, a.N, a.K, a.ldw, C::HALF_N);
+  if (rc) return rc;
+  TCAVP_CUDA(cudaFuncSetAttribute(gemm_tc_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  const int tiles_m = (a.M + 4 * BLOCK_M - 1) / (4 * BLOCK_M), tiles_n = (a.N + C::BLOCK_N - 1) / C::BLOCK_N;
+  const int units = tiles_m * tiles_n;
+  const int max_pairs = sm_count() / 2;
+  const int grid = (units < max_pairs ? units : max_pairs) * 2;
+  const size_t osz = ep.out_dtype == TCAVP_BF16 ? 2 : 4, rsz = ep.res_dtype == TCAVP_BF16 ? 2 : 4;
+  int flags = 0;
+  if (((size_t)ep.ldo * osz) % 32 == 0 && (reinterpret_cast<uintptr_t>(ep.out) % 32) == 0) flags |= EPI_VEC_OUT;
+  if (ep.residual && ((size_t)ep.ldr * rsz) % 32 == 0 && (reinterpret_cast<uintptr_t>(ep.residual) % 32) == 0) flags |= EPI_VEC_RES;
+  if (ep.bias && (reinterpret_cast<uintptr_t>(ep.bias) % 16) == 0) flags |= EPI_VEC_BIAS;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TCAVP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_wide_kernel, ma, mb, ep, a.M, a.N, a.K, flags));
+  return check_launch("gemm_tc_wide_kernel");
+}
+
+static int wide_min_k() {   // TCAVP_GEMM_WIDE_K: contractions at least this long use the 512 x 256 pair tile (0 disables it)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TCAVP_GEMM_WIDE_K");
+    v = e ? atoi(e) : 2048;
+    if (v < 0) v = 0;
+  }
+  return v;
 }
 
 }  // namespace tc
@@ -886,7 +1296,10 @@ extern "C" int tcavp_gemm(const tcavp_gemm_args* a, tcavp_stream_t stream_) {
     if (a->N <= 64) return tc::launch_tc<64, 1>(*a, ep, stream);
     if (a->N <= 128) return tc::launch_tc<128, 1>(*a, ep, stream);
     // large problems: CTA pairs (one 256 x 256 tile per TPC), or 2-CTA clusters sharing the W tile through TMA multicast
-    if (tc::cluster_pref() == 3 && a->M >= 16 * tc::BLOCK_M) return tc::launch_tc_pair<256>(*a, ep, stream);
+    if (tc::cluster_pref() >= 3 && tc::wide_min_k() > 0 && a->K >= tc::wide_min_k() && a->M >= 64 * tc::BLOCK_M)
+      return tc::launch_tc_wide(*a, ep, stream);
+    if (tc::cluster_pref() == 4 && a->M >= 32 * tc::BLOCK_M) return tc::launch_tc_quad<256>(*a, ep, stream);
+    if (tc::cluster_pref() >= 3 && a->M >= 16 * tc::BLOCK_M) return tc::launch_tc_pair<256>(*a, ep, stream);
     if (tc::cluster_pref() == 2 && a->M >= 16 * tc::BLOCK_M) return tc::launch_tc<256, 2>(*a, ep, stream);
     return tc::launch_tc<256, 1>(*a, ep, stream);
   }
