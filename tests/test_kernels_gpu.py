@@ -360,3 +360,72 @@ def test_fused_rmsnorm_gemm(ops, dtype):
     torch.testing.assert_close(out.cpu(), torch.nn.functional.silu(want[:, 0::2]) * want[:, 1::2], **tol)
     o2 = ops.rmsnorm(d, g.to(DEV), torch.empty(M, H, device=DEV), eps=1e-6, rows=M, cols=H, ldi=H + kx)
     torch.testing.assert_close(o2.cpu(), R.rms_norm(xs[:, :H].float(), g, 1e-6), **tol)
+
+
+# ---- large problems: the CTA-pair (cta_group::2) kernel (M >= 2048, N > 128) and the wide 512 x 256 kernel (K >= 2048, M >= 8192) ----
+LARGE = [(4173, 768, 768), (2048, 384, 200), (9000, 512, 2048 + 64), (8192 + 77, 300 + 4, 4096), (16384, 256, 2048)]
+
+
+@pytest.mark.parametrize("M,N,K", LARGE)
+def test_gemm_large_bias_residual(ops, M, N, K):
+    a, w = _rand(M, K, seed=1, scale=0.5).bfloat16(), _rand(N, K, seed=2, scale=K ** -0.5).bfloat16()
+    bias, res = _rand(N, seed=3), _rand(M, N, seed=4).bfloat16()
+    want = a.float() @ w.float().t() + bias + res.float()
+    for td in (torch.bfloat16, torch.float32):
+        out = torch.full((M, N + 16), float("nan"), dtype=td, device=DEV)
+        ops.gemm(a.to(DEV), w.to(DEV), out, bias=bias.to(DEV), residual=res.to(DEV), N=N, ldo=N + 16)
+        torch.testing.assert_close(out[:, :N].float().cpu(), want, rtol=2e-2 if td == torch.bfloat16 else 1e-3, atol=2e-2)
+        assert torch.isnan(out[:, N:].float()).all()          # nothing written past the logical width
+    relu = ops.gemm(a.to(DEV), w.to(DEV), torch.empty(M, N, dtype=torch.bfloat16, device=DEV), bias=bias.to(DEV), act=ops.ACT_RELU)
+    torch.testing.assert_close(relu.float().cpu(), torch.relu(a.float() @ w.float().t() + bias), rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("M,H,I", [(4200, 256, 384), (8300, 2048, 128)])
+def test_gemm_large_norm_chain(ops, M, H, I):
+    """Decoder sub-block plumbing at kernel-variant sizes: a producer GEMM (+residual) accumulates each output row's sum of squares
+    (sumsq_out); the consumer applies rsqrt(sumsq / H + eps) as its row factor (row_sumsq) with the SwiGLU epilogue and stashes the raw
+    gate/up accumulators (aux_out) — against oracle rms_norm + projections in fp32."""
+    kx = 16
+    x0 = _rand(M, H, seed=1).bfloat16()
+    w0 = _rand(H, H, seed=2, scale=H ** -0.5).bfloat16()
+    g, wgu = 1 + 0.1 * _rand(H, seed=3), _rand(2 * I, H, seed=4, scale=H ** -0.5)
+    wf = (wgu * g[None, :]).bfloat16()
+    xs = torch.zeros(M, H + kx, dtype=torch.bfloat16, device=DEV)
+    xs[:, :H] = x0.to(DEV)
+    a = _rand(M, H, seed=5).bfloat16()
+    ss = torch.zeros(M, device=DEV)
+    ops.gemm(a.to(DEV), w0.to(DEV), xs[:, :H], ldo=H + kx, residual=xs[:, :H], ldr=H + kx, sumsq_out=ss)       # x1 = x0 + a W0^T (in place)
+    x1 = (x0.float() + a.float() @ w0.float().t())
+    torch.testing.assert_close(xs[:, :H].float().cpu(), x1, rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(ss.cpu(), (x1 ** 2).sum(-1), rtol=2e-3, atol=1e-2)
+    x1b = xs[:, :H].float().cpu()                                            # the rounded values the consumer actually reads
+    aux = torch.empty(M, 2 * I, dtype=torch.bfloat16, device=DEV)
+    mid = ops.gemm(xs, wf.to(DEV), torch.empty(M, I, dtype=torch.bfloat16, device=DEV), M=M, K=H, lda=H + kx, act=ops.ACT_SWIGLU,
+                   row_sumsq=(ss, H, 1e-6), aux_out=aux)
+    rstd = torch.rsqrt((x1 ** 2).mean(-1) + 1e-6)
+    gu = (x1b @ wf.float().t()) * rstd[:, None]
+    torch.testing.assert_close(aux.float().cpu(), gu, rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(mid.float().cpu(), torch.nn.functional.silu(gu[:, 0::2]) * gu[:, 1::2], rtol=3e-2, atol=2e-2)
+
+
+def test_gemm_large_fused_rope_and_lora_extension(ops):
+    """QKV projection shape of the 768-class backbone at full row count: K-extended rows [x | x A^T] against [W | s B] with RoPE in the
+    epilogue of the pair kernel."""
+    nh, dh, L, B, H, r = 12, 64, 144, 16, 768, 16
+    M, N, Kx = B * L, 3 * nh * dh, H + r
+    x = torch.zeros(M, Kx, dtype=torch.bfloat16)
+    x[:, :H] = _rand(M, H, seed=1).bfloat16()
+    A = _rand(r, H, seed=2, scale=H ** -0.5).bfloat16()
+    x[:, H:] = (x[:, :H].float() @ A.float().t()).bfloat16()
+    w = torch.cat([_rand(N, H, seed=3, scale=H ** -0.5), _rand(N, r, seed=4, scale=0.1)], dim=1).bfloat16()
+    hp = torch.stack([torch.arange(dh // 2), torch.arange(dh // 2) + dh // 2], dim=1).reshape(-1)
+    perm = torch.cat([h * dh + hp for h in range(2 * nh)] + [torch.arange(2 * nh * dh, N)])
+    table = ops.rope_table(L, dh, 10000.0, DEV, layout=1)
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(x.to(DEV), w[perm].contiguous().to(DEV), out, rope=(table, L, dh, 2 * nh * dh))
+    y = (x.float() @ w.float().t()).view(B, L, N)
+    cos, sin = R.rope_cos_sin(L, dh, 10000.0)
+    qk = y[..., : 2 * nh * dh].reshape(B, L, 2 * nh, dh)
+    qk = qk * cos[None, :, None, :] + R.rotate_half(qk) * sin[None, :, None, :]
+    want = torch.cat([qk.reshape(B, L, -1), y[..., 2 * nh * dh:]], dim=-1).view(M, N)[:, perm]
+    torch.testing.assert_close(out.float().cpu(), want, rtol=2e-2, atol=2e-2)
