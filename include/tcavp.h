@@ -90,11 +90,13 @@ typedef struct tcavp_gemm_args {
   const float* rope_cos_sin; int rope_L, rope_dh, rope_cols;
   const float* row_scale;
   /* Fused RMSNorm statistics across GEMMs (bf16 tensor-core path): a producer GEMM adds sum_n out[m', n]^2 of its final
-   * (post-residual) output rows into sumsq_out[m'] (fp32, zeroed by the caller); a consumer GEMM given row_sumsq applies
-   * rsqrt(row_sumsq[m] * sumsq_inv_cols + sumsq_eps) to the raw accumulators exactly like row_scale.  Removes the separate
-   * tcavp_row_rstd pass over the residual stream between decoder sub-blocks (HF:53-70 LlamaRMSNorm). */
-  float* sumsq_out;
-  const float* row_sumsq; float sumsq_inv_cols, sumsq_eps;
+   * (post-residual) output rows into sumsq_out[m'] — unsigned 64-bit FIXED POINT with 20 fractional bits (zeroed by the caller):
+   * integer atomics make the sum independent of the order in which tiles finish, so results stay bit-reproducible and scenes
+   * stay independent of their batch.  A consumer GEMM given row_sumsq applies rsqrt(row_sumsq[m] * 2^-20 * sumsq_inv_cols +
+   * sumsq_eps) to the raw accumulators exactly like row_scale.  Removes the separate tcavp_row_rstd pass over the residual
+   * stream between decoder sub-blocks (HF:53-70 LlamaRMSNorm). */
+  unsigned long long* sumsq_out;
+  const unsigned long long* row_sumsq; float sumsq_inv_cols, sumsq_eps;
   void* aux_out; int ld_aux;   /* SWIGLU + bf16 operands only: also store the raw (row-scaled) gate/up accumulators, interleaved
                                   [M', N] bf16, for the backward pass (the fine-tune step stashes them; NULL otherwise) */
 } tcavp_gemm_args;

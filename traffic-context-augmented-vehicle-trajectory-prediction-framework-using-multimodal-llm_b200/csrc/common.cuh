@@ -81,8 +81,8 @@ struct EpilogueParams {
   int remap_gi, remap_go, remap_off;
   const float* rope; int rope_L, rope_dh, rope_cols;   // fused rotary embedding on adjacent column pairs
   const float* row_scale;                              // per-row factor applied to the raw accumulators (fused RMSNorm)
-  float* sumsq_out;                                    // += sum of squares of the final output row (fused RMSNorm statistics)
-  const float* row_sumsq; float ss_inv, ss_eps;        // row factor rsqrt(row_sumsq[m] * ss_inv + ss_eps) (alternative to row_scale)
+  unsigned long long* sumsq_out;                       // += sum of squares of the final output row, Q44.20 fixed point (order-independent)
+  const unsigned long long* row_sumsq; float ss_inv, ss_eps;   // row factor rsqrt(row_sumsq[m] * 2^-20 * ss_inv + ss_eps) (alternative to row_scale)
   __nv_bfloat16* aux; int ld_aux;                      // SwiGLU only: raw (row-scaled) gate/up accumulators for the backward pass
 };
 
@@ -99,6 +99,14 @@ __device__ __forceinline__ void epilogue_store(const EpilogueParams& p, int m, i
   if (p.act == TCAVP_ACT_RELU) v = fmaxf(v, 0.f);
   if (p.residual) v += load_as_f(p.residual, (size_t)mo * p.ldr + n, p.res_dtype);
   store_from_f(p.out, (size_t)mo * p.ldo + n, p.out_dtype, v);
+}
+
+constexpr float SUMSQ_FIX = 1048576.f;   // 2^20
+__device__ __forceinline__ void sumsq_add(unsigned long long* dst, float partial) {
+  atomicAdd(dst, __float2ull_rn(fminf(partial, 1e12f) * SUMSQ_FIX));
+}
+__device__ __forceinline__ float sumsq_rstd(const unsigned long long* src, float inv_cols, float eps) {
+  return rsqrtf((float)__ldg(src) * (1.f / SUMSQ_FIX) * inv_cols + eps);
 }
 
 void count_launch();

@@ -418,7 +418,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       float rs = 1.f;
       if (m < M) {
         if (ep.row_scale) rs = __ldg(ep.row_scale + m);
-        else if (ep.row_sumsq) rs = rsqrtf(__ldg(ep.row_sumsq + m) * ep.ss_inv + ep.ss_eps);
+        else if (ep.row_sumsq) rs = sumsq_rstd(ep.row_sumsq + m, ep.ss_inv, ep.ss_eps);
       }
       float ssq = 0.f;
       const int pos = ep.rope_cols > 0 ? m % ep.rope_L : 0;
@@ -429,7 +429,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + c * 32, r);
         epilogue_chunk(ep, m, pos, n0 + c * 32, r, rs, flags, ssq);
       }
-      if (ep.sumsq_out && m < M) atomicAdd(ep.sumsq_out + remap_row(ep.remap_gi, ep.remap_go, ep.remap_off, m), ssq);
+      if (ep.sumsq_out && m < M) sumsq_add(ep.sumsq_out + remap_row(ep.remap_gi, ep.remap_go, ep.remap_off, m), ssq);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty_bar + 8 * acc);
@@ -619,7 +619,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       float rs = 1.f;
       if (m < M) {
         if (ep.row_scale) rs = __ldg(ep.row_scale + m);
-        else if (ep.row_sumsq) rs = rsqrtf(__ldg(ep.row_sumsq + m) * ep.ss_inv + ep.ss_eps);
+        else if (ep.row_sumsq) rs = sumsq_rstd(ep.row_sumsq + m, ep.ss_inv, ep.ss_eps);
       }
       float ssq = 0.f;
       const int pos = ep.rope_cols > 0 ? m % ep.rope_L : 0;
@@ -631,7 +631,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + c * 32, r);
           epilogue_chunk(ep, m, pos, n0 + c * 32, r, rs, flags, ssq);
         }
-        if (ep.sumsq_out && m < M) atomicAdd(ep.sumsq_out + remap_row(ep.remap_gi, ep.remap_go, ep.remap_off, m), ssq);
+        if (ep.sumsq_out && m < M) sumsq_add(ep.sumsq_out + remap_row(ep.remap_gi, ep.remap_go, ep.remap_off, m), ssq);
       }
       tc_fence_before();
       __syncwarp();
@@ -785,7 +785,7 @@ gemm_tc_quad_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       float rs = 1.f;
       if (m < M) {
         if (ep.row_scale) rs = __ldg(ep.row_scale + m);
-        else if (ep.row_sumsq) rs = rsqrtf(__ldg(ep.row_sumsq + m) * ep.ss_inv + ep.ss_eps);
+        else if (ep.row_sumsq) rs = sumsq_rstd(ep.row_sumsq + m, ep.ss_inv, ep.ss_eps);
       }
       float ssq = 0.f;
       const int pos = ep.rope_cols > 0 ? m % ep.rope_L : 0;
@@ -796,7 +796,7 @@ gemm_tc_quad_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + c * 32, rr);
         epilogue_chunk(ep, m, pos, n0 + c * 32, rr, rs, flags, ssq);
       }
-      if (ep.sumsq_out && m < M) atomicAdd(ep.sumsq_out + remap_row(ep.remap_gi, ep.remap_go, ep.remap_off, m), ssq);
+      if (ep.sumsq_out && m < M) sumsq_add(ep.sumsq_out + remap_row(ep.remap_gi, ep.remap_go, ep.remap_off, m), ssq);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(leader_tmem_empty + 8 * acc);
@@ -945,7 +945,7 @@ gemm_tc_wide_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         float rs = 1.f;
         if (m < M) {
           if (ep.row_scale) rs = __ldg(ep.row_scale + m);
-          else if (ep.row_sumsq) rs = rsqrtf(__ldg(ep.row_sumsq + m) * ep.ss_inv + ep.ss_eps);
+          else if (ep.row_sumsq) rs = sumsq_rstd(ep.row_sumsq + m, ep.ss_inv, ep.ss_eps);
         }
         float ssq = 0.f;
         const int pos = ep.rope_cols > 0 ? m % ep.rope_L : 0;
@@ -956,7 +956,7 @@ gemm_tc_wide_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + h * C::BLOCK_N + c * 32, rr);
           epilogue_chunk(ep, m, pos, n0 + c * 32, rr, rs, flags, ssq);
         }
-        if (ep.sumsq_out && m < M) atomicAdd(ep.sumsq_out + remap_row(ep.remap_gi, ep.remap_go, ep.remap_off, m), ssq);
+        if (ep.sumsq_out && m < M) sumsq_add(ep.sumsq_out + remap_row(ep.remap_gi, ep.remap_go, ep.remap_off, m), ssq);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(leader_tmem_empty + 8 * h);
@@ -1182,68 +1182,153 @@ static int wide_min_k() {   // TCAVP_GEMM_WIDE_K: contractions at least this lon
 }  // namespace tc
 
 // ------------------------------------------------------------------------------------------------
-// fp32 SIMT kernel: 64x64 output tile, 16-deep K slices, 4x4 outputs per thread
+// fp32 SIMT kernel (exact FFMA accumulation: the rtol 1e-4 parity mode and the fp32 temporal / fusion layers).
+// BM x BN output tile, 16-deep K slices, 256 threads as a 16 x 16 grid of (BM/16) x (BN/16) register tiles read from shared
+// memory with 16-byte loads; the next K slice is fetched into registers while the current one is multiplied, so the global
+// latency is hidden inside a CTA.  Tile shapes: 128x128 (8x8 per thread) for big problems, 64x64, and 32x64 / 16x64 when the
+// 64x64 grid would not fill the GPU (e.g. post_mlp: 4096 x 64 outputs with K = 3200).
 // ------------------------------------------------------------------------------------------------
 namespace simt {
-constexpr int BM = 64, BN = 64, BK = 16;
+constexpr int BK = 16;
 
-template <typename T>
+template <typename T, int BM, int BN>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, int ldw,
-                                                        EpilogueParams ep, int M, int Nacc, int K) {
-  __shared__ float As[BK][BM + 4];
-  __shared__ float Ws[BK][BN + 4];
+                                                        EpilogueParams ep, int M, int Nacc, int K, int vec4) {
+  constexpr int TM = BM / 16, TN = BN / 16;
+  constexpr int LA = (BM * BK + 255) / 256, LW = (BN * BK + 255) / 256;     // elements fetched per thread and slice
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Ws[BK][BN + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += BK) {
+  float acc[TM][TN];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int e = threadIdx.x + i * 256;      // 0..1023
-      const int r = e >> 4, c = e & 15;         // row within tile, k within slice
-      const int gm = m0 + r, gn = n0 + r, gk = k0 + c;
-      As[c][r] = (gm < M && gk < K) ? Cvt<T>::to_f(A[(size_t)gm * lda + gk]) : 0.f;
-      Ws[c][r] = (gn < Nacc && gk < K) ? Cvt<T>::to_f(W[(size_t)gn * ldw + gk]) : 0.f;
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int jn = 0; jn < TN; ++jn) acc[i][jn] = 0.f;
+  float ra[LA], rw[LW];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < LA; ++i) {
+      const int e = threadIdx.x + i * 256, r = e >> 4, c = e & 15;
+      const int gm = m0 + r, gk = k0 + c;
+      ra[i] = (e < BM * BK && gm < M && gk < K) ? Cvt<T>::to_f(A[(size_t)gm * lda + gk]) : 0.f;
     }
-    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < LW; ++i) {
+      const int e = threadIdx.x + i * 256, r = e >> 4, c = e & 15;
+      const int gn = n0 + r, gk = k0 + c;
+      rw[i] = (e < BN * BK && gn < Nacc && gk < K) ? Cvt<T>::to_f(W[(size_t)gn * ldw + gk]) : 0.f;
+    }
+  };
+  auto publish = [&]() {
+#pragma unroll
+    for (int i = 0; i < LA; ++i) {
+      const int e = threadIdx.x + i * 256;
+      if (e < BM * BK) As[e & 15][e >> 4] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < LW; ++i) {
+      const int e = threadIdx.x + i * 256;
+      if (e < BN * BK) Ws[e & 15][e >> 4] = rw[i];
+    }
+  };
+  fetch(0);
+  publish();
+  __syncthreads();
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    const bool more = k0 + BK < K;
+    if (more) fetch(k0 + BK);
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
-      float a[4], w[4];
+      float a[TM], w[TN];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+      for (int i = 0; i < TM; ++i) a[i] = As[k][ty * TM + i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) w[j] = Ws[k][tx * 4 + j];
+      for (int jn = 0; jn < TN; ++jn) w[jn] = Ws[k][tx * TN + jn];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        for (int jn = 0; jn < TN; ++jn) acc[i][jn] = fmaf(a[i], w[jn], acc[i][jn]);
     }
     __syncthreads();
+    if (more) {
+      publish();
+      __syncthreads();
+    }
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + ty * TM + i;
     if (m >= M) continue;
     const int mo = remap_row(ep.remap_gi, ep.remap_go, ep.remap_off, m);
-    const int n = n0 + tx * 4;
     if (ep.row_scale) {
       const float rs = __ldg(ep.row_scale + m);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] *= rs;
+      for (int jn = 0; jn < TN; ++jn) acc[i][jn] *= rs;
     }
-    if (ep.act == TCAVP_ACT_SWIGLU) {
-      epilogue_store(ep, m, mo, n / 2, silu_f(acc[i][0]) * acc[i][1]);
-      epilogue_store(ep, m, mo, n / 2 + 1, silu_f(acc[i][2]) * acc[i][3]);
-    } else if (ep.rope_cols > 0 && n < ep.rope_cols) {
-      const float4 t = __ldg(reinterpret_cast<const float4*>(ep.rope) + (size_t)((n % ep.rope_dh) >> 2) * ep.rope_L + (m % ep.rope_L));
-      epilogue_store(ep, m, mo, n, acc[i][0] * t.x - acc[i][1] * t.y);
-      epilogue_store(ep, m, mo, n + 1, acc[i][1] * t.x + acc[i][0] * t.y);
-      epilogue_store(ep, m, mo, n + 2, acc[i][2] * t.z - acc[i][3] * t.w);
-      epilogue_store(ep, m, mo, n + 3, acc[i][3] * t.z + acc[i][2] * t.w);
-    } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) epilogue_store(ep, m, mo, n + j, acc[i][j]);
+    for (int q = 0; q < TN / 4; ++q) {     // four adjacent accumulator columns at a time (SwiGLU pairs / RoPE quads stay together)
+      const int n = n0 + tx * TN + 4 * q;
+      const float c0 = acc[i][4 * q], c1 = acc[i][4 * q + 1], c2 = acc[i][4 * q + 2], c3 = acc[i][4 * q + 3];
+      if (ep.act == TCAVP_ACT_SWIGLU) {
+        epilogue_store(ep, m, mo, n / 2, silu_f(c0) * c1);
+        epilogue_store(ep, m, mo, n / 2 + 1, silu_f(c2) * c3);
+      } else if (ep.rope_cols > 0 && n < ep.rope_cols) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(ep.rope) + (size_t)((n % ep.rope_dh) >> 2) * ep.rope_L + (m % ep.rope_L));
+        epilogue_store(ep, m, mo, n, c0 * t.x - c1 * t.y);
+        epilogue_store(ep, m, mo, n + 1, c1 * t.x + c0 * t.y);
+        epilogue_store(ep, m, mo, n + 2, c2 * t.z - c3 * t.w);
+        epilogue_store(ep, m, mo, n + 3, c3 * t.z + c2 * t.w);
+      } else if (vec4 && n + 3 < ep.N) {     // four adjacent outputs: one 16-byte (fp32) / 8-byte (bf16) store
+        float v[4] = {c0, c1, c2, c3};
+        if (ep.bias) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
+          v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+        }
+        if (ep.act == TCAVP_ACT_RELU) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+        }
+        if (ep.residual) {
+          if (ep.res_dtype == TCAVP_F32) {
+            const float4 rr = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.residual) + (size_t)mo * ep.ldr + n);
+            v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
+          } else {
+            const uint2 rr = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(ep.residual) + (size_t)mo * ep.ldr + n);
+            v[0] += __uint_as_float(rr.x << 16); v[1] += __uint_as_float(rr.x & 0xffff0000u);
+            v[2] += __uint_as_float(rr.y << 16); v[3] += __uint_as_float(rr.y & 0xffff0000u);
+          }
+        }
+        if (ep.out_dtype == TCAVP_F32) {
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (size_t)mo * ep.ldo + n) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+          uint2 u;
+          u.x = tc::pack_bf16(v[0], v[1]);
+          u.y = tc::pack_bf16(v[2], v[3]);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)mo * ep.ldo + n) = u;
+        }
+      } else {
+        epilogue_store(ep, m, mo, n, c0);
+        epilogue_store(ep, m, mo, n + 1, c1);
+        epilogue_store(ep, m, mo, n + 2, c2);
+        epilogue_store(ep, m, mo, n + 3, c3);
+      }
     }
   }
+}
+
+template <typename T, int BM, int BN>
+static void launch_simt(const tcavp_gemm_args& a, const EpilogueParams& ep, cudaStream_t stream) {
+  dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM);
+  // vector epilogue: rows of out / residual / bias start on 16-byte (fp32) or 8-byte (bf16) boundaries
+  auto al = [](const void* p, int ld, int dtype) {
+    const size_t esz = dtype == TCAVP_BF16 ? 2 : 4;
+    return p == nullptr || (reinterpret_cast<uintptr_t>(p) % (4 * esz) == 0 && ((size_t)ld * esz) % (4 * esz) == 0);
+  };
+  const int vec4 = (ep.act == TCAVP_ACT_NONE || ep.act == TCAVP_ACT_RELU) && ep.rope_cols == 0 && al(ep.out, ep.ldo, ep.out_dtype) &&
+                   al(ep.residual, ep.ldr, ep.res_dtype) && (ep.bias == nullptr || reinterpret_cast<uintptr_t>(ep.bias) % 16 == 0);
+  gemm_simt_kernel<T, BM, BN><<<grid, 256, 0, stream>>>(reinterpret_cast<const T*>(a.A), a.lda, reinterpret_cast<const T*>(a.W), a.ldw, ep, a.M,
+                                                        a.N, a.K, vec4);
 }
 }  // namespace simt
 }  // namespace tcavp
@@ -1296,7 +1381,9 @@ extern "C" int tcavp_gemm(const tcavp_gemm_args* a, tcavp_stream_t stream_) {
     if (a->N <= 64) return tc::launch_tc<64, 1>(*a, ep, stream);
     if (a->N <= 128) return tc::launch_tc<128, 1>(*a, ep, stream);
     // large problems: CTA pairs (one 256 x 256 tile per TPC), or 2-CTA clusters sharing the W tile through TMA multicast
-    if (tc::cluster_pref() >= 3 && tc::wide_min_k() > 0 && a->K >= tc::wide_min_k() && a->M >= 64 * tc::BLOCK_M)
+    // wide tile: long contraction AND at least ~4 waves of 512 x 256 tiles (coarser tiles quantise worse on mid-size problems)
+    if (tc::cluster_pref() >= 3 && tc::wide_min_k() > 0 && a->K >= tc::wide_min_k() && a->M >= 64 * tc::BLOCK_M &&
+        (long long)((a->M + 511) / 512) * ((a->N + 255) / 256) >= 4LL * (sm_count() / 2))
       return tc::launch_tc_wide(*a, ep, stream);
     if (tc::cluster_pref() == 4 && a->M >= 32 * tc::BLOCK_M) return tc::launch_tc_quad<256>(*a, ep, stream);
     if (tc::cluster_pref() >= 3 && a->M >= 16 * tc::BLOCK_M) return tc::launch_tc_pair<256>(*a, ep, stream);
@@ -1304,9 +1391,13 @@ extern "C" int tcavp_gemm(const tcavp_gemm_args* a, tcavp_stream_t stream_) {
     return tc::launch_tc<256, 1>(*a, ep, stream);
   }
   if (a->in_dtype == TCAVP_F32) {
-    dim3 grid((a->N + simt::BN - 1) / simt::BN, (a->M + simt::BM - 1) / simt::BM);
-    simt::gemm_simt_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(a->A), a->lda,
-                                                            reinterpret_cast<const float*>(a->W), a->ldw, ep, a->M, a->N, a->K);
+    const long long t64 = (long long)((a->N + 63) / 64) * ((a->M + 63) / 64);
+    const long long t128 = (long long)((a->N + 127) / 128) * ((a->M + 127) / 128);
+    const int sms = sm_count();
+    if (a->N >= 128 && t128 >= 2LL * sms) simt::launch_simt<float, 128, 128>(*a, ep, stream);
+    else if (t64 >= sms) simt::launch_simt<float, 64, 64>(*a, ep, stream);
+    else if (t64 * 2 >= sms) simt::launch_simt<float, 32, 64>(*a, ep, stream);
+    else simt::launch_simt<float, 16, 64>(*a, ep, stream);
     return check_launch("gemm_simt_kernel");
   }
   return fail_arg("tcavp_gemm: unsupported in_dtype %d", a->in_dtype);

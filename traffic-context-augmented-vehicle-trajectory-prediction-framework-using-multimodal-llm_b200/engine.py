@@ -285,11 +285,12 @@ class Engine:
         mid = self._new(M, I)
         rope = (table, L, dh, (nh + nkv) * dh) if m["fuse_rope"] else None
         # RMSNorm statistics ride on the GEMMs that write the residual stream: o_proj / down_proj add each row's sum of squares
-        # into a zeroed [2 * layers, M] table and the next projection turns it into rstd in its epilogue, so the only separate
+        # into a zeroed [2 * layers, M] fixed-point table (integer atomics: order-independent, bit-reproducible) and the next projection
+        # turns it into rstd in its epilogue, so the only separate
         # pass over the residual stream is the one before the first layer (bf16 tensor-core path; fp32 keeps tcavp_row_rstd).
         nl = len(m["layers"])
         fuse_ss = self.act == torch.bfloat16 and not os.environ.get("TCAVP_NO_FUSE_RSTD")
-        ss = torch.zeros(2 * nl, M, dtype=torch.float32, device=self.dev) if fuse_ss else None
+        ss = torch.zeros(2 * nl, M, dtype=torch.int64, device=self.dev) if fuse_ss else None
         for li, ly in enumerate(m["layers"]):
             if fuse_ss and li > 0:
                 norm1 = dict(row_sumsq=(ss[2 * li - 1], H, m["eps"]))

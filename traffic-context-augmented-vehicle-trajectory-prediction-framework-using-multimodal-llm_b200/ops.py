@@ -153,14 +153,14 @@ def gemm(a, w, out, *, M=None, N=None, K=None, lda=None, ldw=None, ldo=None, bia
         if row_scale.dtype != torch.float32:
             raise TypeError("gemm: row_scale must be fp32")
         g.row_scale = row_scale.data_ptr()
-    if sumsq_out is not None:   # += per-row sum of squares of the final output (fp32 [rows], zeroed by the caller)
-        if sumsq_out.dtype != torch.float32:
-            raise TypeError("gemm: sumsq_out must be fp32")
+    if sumsq_out is not None:   # += per-row sum of squares of the final output (int64 Q44.20 [rows], zeroed by the caller)
+        if sumsq_out.dtype != torch.int64:
+            raise TypeError("gemm: sumsq_out must be int64 (64-bit fixed point, 20 fractional bits)")
         g.sumsq_out = sumsq_out.data_ptr()
-    if row_sumsq is not None:   # (tensor fp32 [M], columns, eps): row factor rsqrt(sumsq / columns + eps)
+    if row_sumsq is not None:   # (tensor int64 Q44.20 [M], columns, eps): row factor rsqrt(sumsq / columns + eps)
         t, ncols, eps = row_sumsq
-        if t.dtype != torch.float32:
-            raise TypeError("gemm: row_sumsq must be fp32")
+        if t.dtype != torch.int64:
+            raise TypeError("gemm: row_sumsq must be int64 (64-bit fixed point, 20 fractional bits)")
         g.row_sumsq, g.sumsq_inv_cols, g.sumsq_eps = t.data_ptr(), 1.0 / ncols, eps
     if aux_out is not None:  # SwiGLU: raw gate/up accumulators (bf16, interleaved) for the backward pass
         if aux_out.dtype != torch.bfloat16:
