@@ -429,3 +429,26 @@ def test_gemm_large_fused_rope_and_lora_extension(ops):
     qk = qk * cos[None, :, None, :] + R.rotate_half(qk) * sin[None, :, None, :]
     want = torch.cat([qk.reshape(B, L, -1), y[..., 2 * nh * dh:]], dim=-1).view(M, N)[:, perm]
     torch.testing.assert_close(out.float().cpu(), want, rtol=2e-2, atol=2e-2)
+
+
+def test_gemm_wide_kernel_sampled_rows(ops):
+    """The 512 x 256 pair tile (K >= 2048 and >= 4 waves of tiles) at a 7B-like shape; the CPU check samples rows (incl. the first / last
+    row of several 128-row halves) instead of forming the whole product."""
+    M, N, K = 40960 + 37, 1024, 2048 + 64
+    g = torch.Generator(device=DEV).manual_seed(5)
+    a = (torch.randn(M, K, device=DEV, generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device=DEV, generator=g) * K ** -0.5).bfloat16()
+    bias = torch.randn(N, device=DEV, generator=g)
+    res = torch.randn(M, N, device=DEV, generator=g).bfloat16()
+    ss = torch.zeros(M, dtype=torch.int64, device=DEV)
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(a, w, out, bias=bias, residual=res, sumsq_out=ss)
+    rows = torch.randint(0, M, (384,), generator=torch.Generator().manual_seed(6))
+    rows[:10] = torch.tensor([0, 127, 128, 255, 256, 511, 512, 40959, 40960, M - 1])
+    rows = rows.to(DEV)
+    want = a[rows].float() @ w.float().t() + bias + res[rows].float()
+    torch.testing.assert_close(out[rows].float(), want, rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(ss[rows].double().mul(2.0 ** -20).float(), (want ** 2).sum(-1), rtol=3e-3, atol=1e-1)
+    sw = ops.gemm(a, w, torch.empty(M, N // 2, dtype=torch.bfloat16, device=DEV), act=ops.ACT_SWIGLU)
+    y = a[rows].float() @ w.float().t()
+    torch.testing.assert_close(sw[rows].float(), torch.nn.functional.silu(y[:, 0::2]) * y[:, 1::2], rtol=3e-2, atol=2e-2)
