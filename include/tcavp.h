@@ -103,6 +103,11 @@ typedef struct tcavp_gemm_args {
 
 int tcavp_gemm(const tcavp_gemm_args* args, tcavp_stream_t stream);
 
+/* fp32 rows -> bf16 [hi | hi | lo] (3 * cols columns; hi = bf16(x), lo = bf16(x - hi)).  Against weights packed [hi | lo | hi] one
+ * bf16 tcavp_gemm over K = 3 * cols returns the fp32 product to ~2^-16 relative with fp32 accumulation — the tensor-core route for
+ * the narrow fp32 layers of the temporal encoder / decoder (train.py:674-686, 784-790) in bf16 compute mode. */
+int tcavp_split_bf16x3(const float* x, int ldx, void* out, int ldo, long long rows, int cols, tcavp_stream_t stream);
+
 /* ---- attention ----------------------------------------------------------------------------------
  * out[b, i, h, :] = softmax_j( scale * q[b,i,h,:].k[b,j,hk,:] + mask ) . v[b,j,hk,:],  hk = h / (H/Hkv)
  *

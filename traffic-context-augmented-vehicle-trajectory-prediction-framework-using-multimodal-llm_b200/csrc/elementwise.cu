@@ -112,6 +112,33 @@ static int grid_for(long long total, int block) {
 
 }  // namespace tcavp
 
+namespace tcavp {
+// fp32 -> three bf16 column blocks [hi | hi | lo] with hi = bf16(x), lo = bf16(x - hi): against weights packed [hi | lo | hi]
+// one bf16 tensor-core GEMM over 3K columns returns x_hi w_hi + x_hi w_lo + x_lo w_hi, i.e. the fp32 product to ~2^-16 relative
+// (fp32 accumulation).  Used for the few-MFLOP fp32 temporal / fusion layers in bf16 compute mode; the exact-fp32 parity mode keeps FFMA.
+__global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ out, int ldo, long long rows,
+                                                     int cols) {
+  const int q = cols >> 2;
+  const long long total = rows * q;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / q;
+    const int c = (int)(i % q) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(x + (size_t)r * ldx + c);
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      hi[e] = __float2bfloat16_rn(f[e]);
+      lo[e] = __float2bfloat16_rn(f[e] - __bfloat162float(hi[e]));
+    }
+    __nv_bfloat16* o = out + (size_t)r * ldo + c;
+    *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(hi);
+    *reinterpret_cast<uint2*>(o + cols) = *reinterpret_cast<const uint2*>(hi);
+    *reinterpret_cast<uint2*>(o + 2 * cols) = *reinterpret_cast<const uint2*>(lo);
+  }
+}
+}  // namespace tcavp
+
 using namespace tcavp;
 #define STREAM(s) reinterpret_cast<cudaStream_t>(s)
 #define DT_OK(d) ((d) == TCAVP_F32 || (d) == TCAVP_BF16)
@@ -186,4 +213,13 @@ extern "C" int tcavp_masked_mean(const void* x, int in_dtype, const int32_t* len
   const long long n = (long long)B * D;
   masked_mean_kernel<<<(int)((n + 255) / 256), 256, 0, STREAM(stream)>>>(x, in_dtype, len, out, out_dtype, B, P, D);
   return check_launch("masked_mean_kernel");
+}
+
+extern "C" int tcavp_split_bf16x3(const float* x, int ldx, void* out, int ldo, long long rows, int cols, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(rows >= 0 && cols > 0 && cols % 4 == 0 && ldx >= cols && ldx % 4 == 0 && ldo >= 3 * cols && ldo % 4 == 0,
+                "tcavp_split_bf16x3: bad shape (cols=%d must be a multiple of 4, ldx=%d, ldo=%d)", cols, ldx, ldo);
+  if (rows == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(x && out && reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 8 == 0, "tcavp_split_bf16x3: bad pointer");
+  split3_kernel<<<grid_for(rows * (cols / 4), 256), 256, 0, STREAM(stream)>>>(x, ldx, reinterpret_cast<__nv_bfloat16*>(out), ldo, rows, cols);
+  return check_launch("split3_kernel");
 }

@@ -16,16 +16,20 @@ def _f32(t, dev):
 
 class _Lin:
     """Packed linear: weight in the activation dtype ([N, K] row-major), bias in fp32."""
-    __slots__ = ("w", "b", "N", "K", "wT")
+    __slots__ = ("w", "b", "N", "K", "wT", "w3")
 
     def __init__(self, w, b, act, dev):
         self.w = w.detach().to(device=dev, dtype=act).contiguous()
         self.b = None if b is None else _f32(b, dev)
         self.N, self.K = self.w.shape
         self.wT = None   # [K, N] copy used by the backward pass (train_engine.py)
+        self.w3 = None   # [N, 3K] bf16 [hi | lo | hi] split of an fp32 weight (Engine._split_small)
 
 
 class Engine:
+    # fp32 ("small") layers of the temporal path run on the tensor cores through a bf16 hi/lo split in bf16 compute mode
+    SPLIT_SMALL = True
+
     def __init__(self, model, compute_dtype="bf16", merge_lora=False):
         p0 = next(model.ltsf.parameters())
         self.merge_lora = merge_lora
@@ -53,6 +57,25 @@ class Engine:
 
     def _ln(self, m):
         return (_f32(m.weight, self.dev), _f32(m.bias, self.dev), m.eps)
+
+    def _split_small(self, *lins):
+        """Packs [w_hi | w_lo | w_hi] (bf16) next to an fp32 weight: x3 = [x_hi | x_hi | x_lo] (tcavp_split_bf16x3) against it in ONE
+        bf16 tensor-core GEMM gives x_hi w_hi + x_hi w_lo + x_lo w_hi = the fp32 product to ~2^-16 relative, fp32 accumulation."""
+        if not (self.SPLIT_SMALL and self.act == torch.bfloat16 and not os.environ.get("TCAVP_NO_SPLIT_SMALL")):
+            return
+        for L in lins:
+            if L is not None and L.w.dtype == torch.float32 and L.K % 8 == 0:
+                hi = L.w.to(torch.bfloat16)
+                lo = (L.w - hi.float()).to(torch.bfloat16)
+                L.w3 = torch.cat([hi, lo, hi], dim=1).contiguous()
+
+    def _gemm_small(self, x, L, out, **kw):
+        """Linear map of the fp32 temporal path: split-bf16 tensor-core GEMM when packed (bf16 compute mode), exact FFMA otherwise."""
+        if L.w3 is not None and x.dtype == torch.float32 and x.is_contiguous():
+            M = x.shape[0]
+            x3 = ops.split3(x, self._new(M, 3 * L.K, dtype=torch.bfloat16), rows=M, cols=L.K)
+            return ops.gemm(x3, L.w3, out, bias=L.b, **kw)
+        return ops.gemm(x, L.w, out, bias=L.b, **kw)
 
     def _enc_layer(self, l):
         return dict(sa=self._mha(l.self_attn), l1=_Lin(l.linear1.weight, l.linear1.bias, self.act, self.dev),
@@ -176,6 +199,8 @@ class Engine:
         if d.use_post_mlp:
             self.lt["post"] = (_Lin(d.post_mlp[0].weight[:, perm], d.post_mlp[0].bias, small, dev),
                                _Lin(d.post_mlp[3].weight[perm], d.post_mlp[3].bias[perm], small, dev))
+        self._split_small(self.lt["mha"]["qkv"], self.lt["mha"]["out"], self.lt["f0"], self.lt["f3"], self.lt["lane_fc"],
+                          *(self.lt["post"] or ()))
 
     # ---- building blocks --------------------------------------------------------------------------
     def _new(self, *shape, dtype=None):
@@ -185,7 +210,7 @@ class Engine:
         """x: (B*T, E) -> attention output (B*T, E) (before out_proj)."""
         E, heads = mha["E"], mha["heads"]
         T = rows_per_b
-        qkv = ops.gemm(x, mha["qkv"].w, self._new(B * T, 3 * E, dtype=x.dtype), bias=mha["qkv"].b)
+        qkv = self._gemm_small(x, mha["qkv"], self._new(B * T, 3 * E, dtype=x.dtype))
         out = self._new(B * T, E, dtype=x.dtype)
         dh = E // heads
         ops.attention(qkv, qkv[:, E:], qkv[:, 2 * E:], out, B=B, H=heads, Hkv=heads, Tq=T, Tk=T, dh=dh,
@@ -322,21 +347,21 @@ class Engine:
         e0 = ops.ltsf_encode(x, lt["wt"], lt["bt"], lt["we"], lt["be"], lt["pos"], self._new(B * T, C, dtype=sm), B=B, F=2, C=C, T_in=T)
         xn = self._ln_res(e0, lt["n1"])
         a = self._self_attention(xn, T, B, lt["mha"])
-        y = ops.gemm(a, lt["mha"]["out"].w, self._new(B * T, C, dtype=sm), bias=lt["mha"]["out"].b, residual=xn)
+        y = self._gemm_small(a, lt["mha"]["out"], self._new(B * T, C, dtype=sm), residual=xn)
         r = self._ln_res(y, lt["n2"])
-        h = ops.gemm(r, lt["f0"].w, self._new(B * T, lt["f0"].N, dtype=sm), bias=lt["f0"].b, act=ops.ACT_RELU)
-        return ops.gemm(h, lt["f3"].w, self._new(B * T, C, dtype=sm), bias=lt["f3"].b, residual=r)
+        h = self._gemm_small(r, lt["f0"], self._new(B * T, lt["f0"].N, dtype=sm), act=ops.ACT_RELU)
+        return self._gemm_small(h, lt["f3"], self._new(B * T, C, dtype=sm), residual=r)
 
     def ltsf_decode(self, enc, poly_emb, fh, x, B, L, y=None, norm_stat=None):
         """reference scripts/train.py:767-806 + 941-943 (+ 945-962 / 1302-1322 when y is given)."""
         lt, C, T, To, sm = self.lt, self.C, self.T_in, self.T_out, self.small
         H = self.llm["H"]
-        adj = ops.gemm(poly_emb, lt["lane_fc"].w, self._new(B, To * C, dtype=sm), bias=lt["lane_fc"].b)
+        adj = self._gemm_small(poly_emb, lt["lane_fc"], self._new(B, To * C, dtype=sm))
         dec = ops.nlinear_decode(enc, lt["wd"], lt["bd"], adj, self._new(B, To * C, dtype=sm), B=B, C=C, T_in=T, T_out=To)
         if lt["post"] is not None:
             p0, p3 = lt["post"]
-            h = ops.gemm(dec, p0.w, self._new(B, p0.N, dtype=sm), bias=p0.b, act=ops.ACT_RELU)
-            dec = ops.gemm(h, p3.w, self._new(B, To * C, dtype=sm), bias=p3.b)
+            h = self._gemm_small(dec, p0, self._new(B, p0.N, dtype=sm), act=ops.ACT_RELU)
+            dec = self._gemm_small(h, p3, self._new(B, To * C, dtype=sm))
         dec_t = dec.view(B * To, C)                  # fp32 residual path of the regression head
         dq = dec_t if self.act == sm else ops.cast(dec_t, self._new(B * To, C), rows=B * To, cols=C)
         q = ops.gemm(dq, lt["dec_proj"].w, self._new(B * To, H), bias=lt["dec_proj"].b)

@@ -280,6 +280,16 @@ def cast(x, out, *, rows, cols, ldi=None, ldo=None, in_row_mod=0):
     return out
 
 
+def split3(x, out, *, rows, cols):
+    """fp32 [rows, cols] -> bf16 [rows, 3 * cols] = [hi | hi | lo] (see tcavp_split_bf16x3)."""
+    _need_cuda(x, out)
+    if x.dtype != torch.float32 or out.dtype != torch.bfloat16:
+        raise TypeError("split3: fp32 in, bf16 out")
+    with _Timed("split3_kernel", 0.0, float(rows * cols * (4 + 6))):
+        _lib.check(_lib.load().tcavp_split_bf16x3(_p(x), x.stride(0), _p(out), out.stride(0), _ll(rows), cols, _stream()), "tcavp_split_bf16x3")
+    return out
+
+
 def poly_embed(polygon, lens, w, bias, pos, out, key_mask, *, B, P, D):
     _need_cuda(polygon, lens, w, bias, pos, out, key_mask)
     with _Timed("poly_embed_kernel", 0.0, float(B * P * (8 + 4 + D * out.element_size()))):

@@ -24,6 +24,8 @@ def _pad8(n):
 
 
 class TrainEngine(Engine):
+    SPLIT_SMALL = False      # the fine-tune step keeps the fp32 layers in exact FFMA (their weights are re-packed every step)
+
     def __init__(self, model, compute_dtype="bf16"):
         super().__init__(model, compute_dtype)
         self.model = model
