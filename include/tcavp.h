@@ -33,7 +33,7 @@ typedef void* tcavp_stream_t; /* cudaStream_t */
 
 enum { TCAVP_F32 = 0, TCAVP_BF16 = 1 };
 enum { TCAVP_OK = 0, TCAVP_ERR_ARG = -1, TCAVP_ERR_CUDA = -2, TCAVP_ERR_UNSUPPORTED = -3 };
-enum { TCAVP_ACT_NONE = 0, TCAVP_ACT_RELU = 1, TCAVP_ACT_SWIGLU = 2 };
+enum { TCAVP_ACT_NONE = 0, TCAVP_ACT_RELU = 1, TCAVP_ACT_SWIGLU = 2, TCAVP_ACT_SWIGLU_BWD = 3 };
 
 /* ---- library ------------------------------------------------------------------------------- */
 const char* tcavp_last_error(void);
@@ -97,8 +97,12 @@ typedef struct tcavp_gemm_args {
    * stream between decoder sub-blocks (HF:53-70 LlamaRMSNorm). */
   unsigned long long* sumsq_out;
   const unsigned long long* row_sumsq; float sumsq_inv_cols, sumsq_eps;
-  void* aux_out; int ld_aux;   /* SWIGLU + bf16 operands only: also store the raw (row-scaled) gate/up accumulators, interleaved
-                                  [M', N] bf16, for the backward pass (the fine-tune step stashes them; NULL otherwise) */
+  void* aux_out; int ld_aux;   /* bf16 operands only.  SWIGLU: also store the raw (row-scaled) gate/up accumulators, interleaved
+                                  [M', N] bf16, for the backward pass (the fine-tune step stashes them; NULL otherwise).
+                                  SWIGLU_BWD (fine-tune step): INPUT — the stashed (gate, up) pairs [M', 2N]; the N accumulator
+                                  columns are d(mid) and the epilogue writes the 2N interleaved columns (d gate, d up) to `out`
+                                  (bf16, ldo >= 2N): d gate = d u s (1 + g (1 - s)), d up = d g s, s = sigmoid(g) — the backward of
+                                  HF LlamaMLP's act_fn(gate) * up (HF:190) fused into the down_proj^T GEMM. */
 } tcavp_gemm_args;
 
 int tcavp_gemm(const tcavp_gemm_args* args, tcavp_stream_t stream);

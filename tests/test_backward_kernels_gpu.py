@@ -393,3 +393,22 @@ def test_attention_bwd_few_queries_wide_heads(ops, B, H, Tq, Tk, dh, masked, dkv
         assert torch.isfinite(got).all(), name
         err = float((got - want).abs().max()) / (float(want.abs().max()) + 1e-12)
         assert err < 2e-2, (name, err)
+
+
+@pytest.mark.parametrize("M,I,H", [(4300, 384, 256), (300, 64, 128), (9000, 1024, 2112)])
+def test_swiglu_backward_fused_into_the_gemm(ops, M, I, H):
+    """act = SWIGLU_BWD: d(mid) = dx . W_down (the GEMM) never leaves the tile; the epilogue turns it into interleaved (d gate, d up) from the
+    stashed (gate, up) pairs — against autograd through silu(gate) * up followed by the down projection."""
+    dx = _rand(M, H, seed=60, scale=0.5).bfloat16()
+    wdT = _rand(I, H, seed=61, scale=H ** -0.5).bfloat16()          # W_down^T : [I, H]  (d mid = dx . W_down = dx @ wdT.T)
+    gu = _rand(M, 2 * I, seed=62).bfloat16()
+    g = gu[:, 0::2].float().requires_grad_(True)
+    u = gu[:, 1::2].float().requires_grad_(True)
+    mid = torch.nn.functional.silu(g) * u
+    dmid = dx.float() @ wdT.float().t()
+    mid.backward(dmid)
+    out = torch.empty(M, 2 * I, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(dx.to(DEV), wdT.to(DEV), out, act=ops.ACT_SWIGLU_BWD, aux_out=gu.to(DEV))
+    got = out.float().cpu()
+    torch.testing.assert_close(got[:, 0::2], g.grad, rtol=3e-2, atol=3e-2)
+    torch.testing.assert_close(got[:, 1::2], u.grad, rtol=3e-2, atol=3e-2)

@@ -165,6 +165,26 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueParams& p, int m, i
                                                float& ssq) {
   if (m >= p.M) return;
   const int mo = remap_row(p.remap_gi, p.remap_go, p.remap_off, m);
+  if (p.act == TCAVP_ACT_SWIGLU_BWD) {
+    // accumulators = d(mid) for 32 hidden units; (gate, up) pairs come from the forward stash, (d gate, d up) pairs go out
+    if (nacc0 >= p.N) return;
+    const __nv_bfloat16* gp = p.aux + (size_t)mo * p.ld_aux + 2 * nacc0;
+    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)mo * p.ldo + 2 * nacc0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {          // 8 hidden units = 16 bf16 = 32 bytes per step
+      uint32_t gu[8], du[8];
+      ldg256(gp + q * 16, gu);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float g = __uint_as_float(gu[e] << 16), u = __uint_as_float(gu[e] & 0xffff0000u);
+        const float d = __uint_as_float(r[q * 8 + e]) * rs;
+        const float sg = __fdividef(1.f, 1.f + ex2_approx(-1.4426950408889634f * g));
+        du[e] = pack_bf16(d * u * sg * (1.f + g * (1.f - sg)), d * g * sg);
+      }
+      stg256(op + q * 16, du);
+    }
+    return;
+  }
   float o[32];
   int cnt, n0;
   if (p.act == TCAVP_ACT_SWIGLU) {
@@ -1341,7 +1361,16 @@ extern "C" int tcavp_gemm(const tcavp_gemm_args* a, tcavp_stream_t stream_) {
   if (a->M == 0) return TCAVP_OK;
   TCAVP_REQUIRE(a->A && a->W && a->out, "tcavp_gemm: null A/W/out");
   TCAVP_REQUIRE(a->lda >= a->K && a->ldw >= a->K, "tcavp_gemm: lda/ldw smaller than K");
-  TCAVP_REQUIRE(a->act == TCAVP_ACT_NONE || a->act == TCAVP_ACT_RELU || a->act == TCAVP_ACT_SWIGLU, "tcavp_gemm: bad act %d", a->act);
+  TCAVP_REQUIRE(a->act == TCAVP_ACT_NONE || a->act == TCAVP_ACT_RELU || a->act == TCAVP_ACT_SWIGLU || a->act == TCAVP_ACT_SWIGLU_BWD,
+                "tcavp_gemm: bad act %d", a->act);
+  if (a->act == TCAVP_ACT_SWIGLU_BWD) {
+    TCAVP_REQUIRE(a->in_dtype == TCAVP_BF16 && a->out_dtype == TCAVP_BF16 && a->aux_out && !a->bias && !a->residual && !a->rope_cos_sin &&
+                      !a->sumsq_out && a->remap_gi == 0,
+                  "tcavp_gemm: SWIGLU_BWD needs bf16 operands / output, the (gate, up) stash in aux_out and no other epilogue term");
+    TCAVP_REQUIRE(a->N % 32 == 0 && a->ldo >= 2 * a->N && a->ld_aux >= 2 * a->N && a->ldo % 16 == 0 && a->ld_aux % 16 == 0 &&
+                      reinterpret_cast<uintptr_t>(a->out) % 32 == 0 && reinterpret_cast<uintptr_t>(a->aux_out) % 32 == 0,
+                  "tcavp_gemm: SWIGLU_BWD needs N %% 32 == 0, ldo / ld_aux >= 2N and multiples of 16, 32-byte aligned out / aux_out");
+  }
   TCAVP_REQUIRE(a->act != TCAVP_ACT_SWIGLU || (a->N % 2 == 0), "tcavp_gemm: SwiGLU needs an even number of interleaved rows");
   TCAVP_REQUIRE(a->out_dtype == TCAVP_F32 || a->out_dtype == TCAVP_BF16, "tcavp_gemm: bad out_dtype");
   TCAVP_REQUIRE(!a->residual || a->res_dtype == TCAVP_F32 || a->res_dtype == TCAVP_BF16, "tcavp_gemm: bad res_dtype");
@@ -1361,7 +1390,7 @@ extern "C" int tcavp_gemm(const tcavp_gemm_args* a, tcavp_stream_t stream_) {
   TCAVP_REQUIRE((!a->sumsq_out && !a->row_sumsq) || a->in_dtype == TCAVP_BF16, "tcavp_gemm: sumsq_out / row_sumsq need bf16 operands");
   TCAVP_REQUIRE(!a->sumsq_out || a->act != TCAVP_ACT_SWIGLU, "tcavp_gemm: sumsq_out is not defined for the SwiGLU epilogue");
   ep.aux = reinterpret_cast<__nv_bfloat16*>(a->aux_out); ep.ld_aux = a->ld_aux;
-  if (ep.aux) {
+  if (ep.aux && a->act != TCAVP_ACT_SWIGLU_BWD) {
     TCAVP_REQUIRE(a->act == TCAVP_ACT_SWIGLU && a->in_dtype == TCAVP_BF16, "tcavp_gemm: aux_out needs act SWIGLU and bf16 operands");
     TCAVP_REQUIRE(a->N % 32 == 0 && a->ld_aux >= a->N && a->ld_aux % 16 == 0 && reinterpret_cast<uintptr_t>(a->aux_out) % 32 == 0,
                   "tcavp_gemm: aux_out needs N %% 32 == 0, ld_aux >= N, ld_aux %% 16 == 0 and a 32-byte aligned pointer");

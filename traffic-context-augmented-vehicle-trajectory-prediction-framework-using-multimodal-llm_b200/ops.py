@@ -10,7 +10,7 @@ import torch
 from . import lib as _lib
 
 F32, BF16 = 0, 1
-ACT_NONE, ACT_RELU, ACT_SWIGLU = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_SWIGLU, ACT_SWIGLU_BWD = 0, 1, 2, 3
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 
 

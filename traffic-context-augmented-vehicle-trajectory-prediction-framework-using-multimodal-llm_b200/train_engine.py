@@ -412,8 +412,12 @@ class TrainEngine(Engine):
         for i in reversed(range(len(ctxs))):
             xs, rstd1, qkv, attn, xs2, rstd2, gu, mid = ctxs[i]
             ly = m["layers"][i]
-            dmid = ops.gemm(dx, ly["wdownT"], self._new(M, I))
-            dgu = ops.swiglu_bwd(dmid, gu, self._new(M, 2 * I), rows=M, I=I)
+            if self.act == torch.bfloat16 and I % 32 == 0:
+                # d(mid) never leaves the tile: the down_proj^T GEMM's epilogue reads the stashed (gate, up) pairs and writes (d gate, d up)
+                dgu = ops.gemm(dx, ly["wdownT"], self._new(M, 2 * I), act=ops.ACT_SWIGLU_BWD, aux_out=gu)
+            else:
+                dmid = ops.gemm(dx, ly["wdownT"], self._new(M, I))
+                dgu = ops.swiglu_bwd(dmid, gu, self._new(M, 2 * I), rows=M, I=I)
             dn2 = ops.gemm(dgu, ly["wguT"], self._new(M, H))
             dx2 = ops.rmsnorm_bwd(dn2, xs2, self._new(M, H), rows=M, cols=H, eps=m["eps"], add=dx, ldx=Kx)
             dattn = ops.gemm(dx2, ly["woT"], self._new(M, nq))
