@@ -270,6 +270,11 @@ int tcavp_traj_loss_bwd(const float* decoded, const float* y, const float* norm_
  * (row_scale optional: the RMSNorm rstd of the folded-norm form). */
 int tcavp_skinny_dw(const void* Y, int ldy, int y_dtype, const void* Z, int ldz, int z_dtype, const float* row_scale, float* out, int ldo,
                     long long M, int N, int J, tcavp_stream_t stream);
+/* Best-of-K candidate reduction (reference scripts/test.py:1336-1368): candidates (B, K, 2, T_out) fp32, y (B, 2, T_out), norm_stat (B, 4).
+ * per_scene[b] = (min_k ADE, min_k FDE, min_k RMSE) after de-normalisation; totals[0..2] += their sums over the batch (caller zeroes). */
+int tcavp_best_of_k(const float* candidates, const float* y, const float* norm_stat, float* per_scene, float* totals, int B, int K, int T_out,
+                    tcavp_stream_t stream);
+
 /* Weight gradient of a linear map (autograd of F.linear, reference loop im_kim_train_GRN.py:1039):
  * out[n][k] += sum_m dY[m][n] * X[m][k], out fp32 [N, ldo] (caller zero-initialises; M-slices are combined with atomics), dY / X in
  * their row-major [M, *] layouts (fp32 or bf16, may differ) — no transposed copies.  fp32 FFMA: meant for the narrow fp32 layers

@@ -346,3 +346,22 @@ def compress_grad(g, big=50_000):
         return {"full": g.clone()}
     g2 = g.reshape(g.shape[0], -1)
     return {"head": g2[:4].clone(), "rowsum": g2.double().sum(1).float(), "colsum": g2.double().sum(0).float(), "shape": tuple(g.shape)}
+
+
+def best_of_k(candidates, y, norm_stat):
+    """reference scripts/test.py:1336-1368: candidates (B, K, 2, T) -> (min ADE, min FDE, min RMSE) per scene."""
+    B = candidates.shape[0]
+    ns = torch.tensor(norm_stat, dtype=torch.float32) if not torch.is_tensor(norm_stat) else norm_stat.float()
+    min_x, max_x, min_y, max_y = (ns[:, i].view(B, 1, 1) for i in range(4))
+    rx, ry = max_x - min_x, max_y - min_y
+    pred = candidates.clone().float()
+    pred[..., 0, :] = pred[..., 0, :] * rx + min_x
+    pred[..., 1, :] = pred[..., 1, :] * ry + min_y
+    yd = y.clone().float().unsqueeze(1)
+    yd[..., 0, :] = yd[..., 0, :] * rx + min_x
+    yd[..., 1, :] = yd[..., 1, :] * ry + min_y
+    errors = torch.sqrt(((pred - yd) ** 2).sum(dim=2))
+    ade = errors.mean(dim=-1)
+    fde = errors[..., -1]
+    rmse = torch.sqrt(torch.mean((pred - yd) ** 2, dim=[2, 3]))
+    return ade.min(dim=1).values, fde.min(dim=1).values, rmse.min(dim=1).values

@@ -452,3 +452,17 @@ def test_gemm_wide_kernel_sampled_rows(ops):
     sw = ops.gemm(a, w, torch.empty(M, N // 2, dtype=torch.bfloat16, device=DEV), act=ops.ACT_SWIGLU)
     y = a[rows].float() @ w.float().t()
     torch.testing.assert_close(sw[rows].float(), torch.nn.functional.silu(y[:, 0::2]) * y[:, 1::2], rtol=3e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("B,K,T", [(7, 10, 25), (300, 3, 50), (1, 1, 1), (5, 20, 40)])
+def test_best_of_k_reduction(ops, B, K, T):
+    """tcavp_best_of_k against the restated candidate reduction of the reference's best-of-K evaluation (scripts/test.py:1336-1368)."""
+    cand, y = torch.rand(B, K, 2, T, generator=torch.Generator().manual_seed(1)), torch.rand(B, 2, T, generator=torch.Generator().manual_seed(2))
+    ns = [(100.0 + i, 900.0 + 3 * i, 700.0 + i, 760.0 + 2 * i) for i in range(B)]
+    want = R.best_of_k(cand, y, ns)
+    per = torch.empty(B, 3, device=DEV)
+    tot = torch.zeros(3, device=DEV)
+    ops.best_of_k(cand.to(DEV), y.to(DEV), torch.tensor(ns, device=DEV), per, tot, B=B, K=K, T_out=T)
+    for i in range(3):
+        torch.testing.assert_close(per[:, i].cpu(), want[i], rtol=1e-4, atol=1e-3)
+        torch.testing.assert_close(tot[i].cpu(), want[i].sum(), rtol=1e-4, atol=1e-2)

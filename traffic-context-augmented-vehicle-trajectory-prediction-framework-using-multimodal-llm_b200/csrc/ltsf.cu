@@ -350,6 +350,49 @@ __global__ void __launch_bounds__(128) traj_metrics_kernel(const float* __restri
   }
 }
 
+
+// Best-of-K candidate reduction (reference scripts/test.py:1336-1368, seed_fix_train.py:1183-1243): K candidate trajectories per scene
+// -> de-normalise, per-candidate ADE / FDE / RMSE, minimum over the candidates, batch sums.  One warp per (scene, candidate) pass,
+// one block per scene; candidates (B, K, 2, T), y (B, 2, T), norm_stat (B, 4) = (min_x, max_x, min_y, max_y).
+__global__ void __launch_bounds__(256) best_of_k_kernel(const float* __restrict__ cand, const float* __restrict__ y, const float* __restrict__ ns,
+                                                        float* __restrict__ per_scene, float* __restrict__ totals, int B, int K, int T) {
+  __shared__ float best[8][3];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    const float min_x = ns[(size_t)b * 4], max_x = ns[(size_t)b * 4 + 1], min_y = ns[(size_t)b * 4 + 2], max_y = ns[(size_t)b * 4 + 3];
+    const float rx = max_x - min_x, ry = max_y - min_y;
+    float m_ade = INFINITY, m_fde = INFINITY, m_rmse = INFINITY;
+    for (int k = warp; k < K; k += 8) {
+      const float* c = cand + ((size_t)b * K + k) * 2 * T;
+      float sd = 0.f, sq = 0.f, last = 0.f;
+      for (int t = lane; t < T; t += 32) {
+        const float dx = (c[t] * rx + min_x) - (y[(size_t)b * 2 * T + t] * rx + min_x);
+        const float dy = (c[T + t] * ry + min_y) - (y[(size_t)b * 2 * T + T + t] * ry + min_y);
+        const float e2 = dx * dx + dy * dy;
+        const float e = sqrtf(e2);
+        sd += e;
+        sq += e2;
+        if (t == T - 1) last = e;
+      }
+      sd = warp_sum(sd);
+      sq = warp_sum(sq);
+      last = warp_sum(last);
+      m_ade = fminf(m_ade, sd / (float)T);
+      m_fde = fminf(m_fde, last);
+      m_rmse = fminf(m_rmse, sqrtf(sq / (2.f * (float)T)));
+    }
+    __syncthreads();
+    if (lane == 0) { best[warp][0] = m_ade; best[warp][1] = m_fde; best[warp][2] = m_rmse; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      float v = INFINITY;
+      for (int w = 0; w < 8; ++w) v = fminf(v, best[w][threadIdx.x]);
+      if (per_scene) per_scene[(size_t)b * 3 + threadIdx.x] = v;
+      if (totals) atomicAdd(totals + threadIdx.x, v);
+    }
+  }
+}
+
 }  // namespace tcavp
 
 using namespace tcavp;
@@ -444,4 +487,14 @@ extern "C" int tcavp_traj_metrics(const float* decoded, const float* y, const fl
   const int grid = B < sm_count() * 8 ? B : sm_count() * 8;
   traj_metrics_kernel<<<grid, 128, 0, STREAM(stream)>>>(decoded, y, norm_stat, metrics, per_scene, B, T_out);
   return check_launch("traj_metrics_kernel");
+}
+
+extern "C" int tcavp_best_of_k(const float* candidates, const float* y, const float* norm_stat, float* per_scene, float* totals, int B, int K,
+                               int T_out, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(B >= 0 && K > 0 && T_out > 0, "tcavp_best_of_k: bad shape");
+  if (B == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(candidates && y && norm_stat && (per_scene || totals), "tcavp_best_of_k: null pointer");
+  const int grid = B < sm_count() * 8 ? B : sm_count() * 8;
+  best_of_k_kernel<<<grid, 256, 0, STREAM(stream)>>>(candidates, y, norm_stat, per_scene, totals, B, K, T_out);
+  return check_launch("best_of_k_kernel");
 }

@@ -364,6 +364,22 @@ class MultiModalTrajectoryModel(nn.Module):
             self._engine_sig = sig
         return self._engine
 
+    @torch.no_grad()
+    def best_of_k_metrics(self, candidates, y, norm_stat):
+        """The reduction of the reference's best-of-K evaluation (scripts/test.py:1336-1368): `candidates` (B, K, 2, T_out) are K decoded
+        trajectories per scene (e.g. from K stochastic forward passes), returns dict(min_ade[B], min_fde[B], min_rmse[B], sums[3]) on
+        the device without a host sync.  (The candidate generation itself — MC-dropout passes — is not part of this package.)"""
+        dev = next(self.ltsf.parameters()).device
+        c = candidates.to(device=dev, dtype=torch.float32).contiguous()
+        B, K, _, T = c.shape
+        yy = y.to(device=dev, dtype=torch.float32).contiguous()
+        ns = norm_stat if torch.is_tensor(norm_stat) else torch.tensor(norm_stat, dtype=torch.float32)
+        ns = ns.to(device=dev, dtype=torch.float32).reshape(B, 4).contiguous()
+        per = torch.empty(B, 3, dtype=torch.float32, device=dev)
+        tot = torch.zeros(3, dtype=torch.float32, device=dev)
+        ops.best_of_k(c, yy, ns, per, tot, B=B, K=K, T_out=T)
+        return dict(min_ade=per[:, 0], min_fde=per[:, 1], min_rmse=per[:, 2], sums=tot)
+
     def merge_lora_for_inference(self, enabled=True):
         """Serve-time option: fold every LoRA pair into its base weight when the inference engine packs the backbone
         (W' = W + (alpha / r) B A, peft's merge semantics), so the decoder runs without the rank-r side path.  The module's own

@@ -337,6 +337,15 @@ def traj_metrics(decoded, y, norm_stat, metrics, per_scene, *, B, T_out):
                "tcavp_traj_metrics")
 
 
+def best_of_k(candidates, y, norm_stat, per_scene, totals, *, B, K, T_out):
+    """min over K candidates of ADE / FDE / RMSE per scene (+ batch sums); candidates (B, K, 2, T_out) fp32."""
+    _need_cuda(candidates, y, norm_stat, per_scene, totals)
+    with _Timed("best_of_k_kernel", 0.0, float(B * (K + 1) * 2 * T_out * 4)):
+        _lib.check(_lib.load().tcavp_best_of_k(_p(candidates), _p(y), _p(norm_stat), _p(per_scene), _p(totals), B, K, T_out, _stream()),
+                   "tcavp_best_of_k")
+    return per_scene, totals
+
+
 def launch_count():
     return int(_lib.load().tcavp_launch_count())
 
