@@ -157,7 +157,7 @@ __device__ __forceinline__ void ldg256(const void* p, uint32_t (&v)[8]) {
 }
 
 enum { EPI_VEC_OUT = 1, EPI_VEC_RES = 2, EPI_VEC_BIAS = 4,
-       DBG_NO_TMA = 16, DBG_NO_MMA = 32, DBG_NO_EPI = 64 };   // TCAVP_GEMM_DEBUG: ablation switches for profiling (results are garbage)
+       DBG_NO_TMA = 16, DBG_NO_MMA = 32, DBG_NO_EPI = 64, DBG_NO_STORE = 128 };   // TCAVP_GEMM_DEBUG: ablation switches for profiling (results are garbage)
 
 // Epilogue of 32 accumulator columns [nacc0, nacc0+32) of row m for one thread.  The interior-tile path (full chunk,
 // 16-byte aligned rows) is branch-light and fully vectorised; ragged edges take the scalar path.
@@ -283,6 +283,14 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueParams& p, int m, i
 #pragma unroll
     for (int j = 0; j < 32; ++j)
       if (j < cnt && (full || n0 + j < p.N)) ssq = fmaf(o[j], o[j], ssq);
+  }
+  if (flags & DBG_NO_STORE) {      // profiling ablation: everything but the global stores (keeps the math alive through ssq)
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < cnt) t += o[j];
+    ssq += t;
+    return;
   }
   if ((flags & EPI_VEC_OUT) && full) {
     if (p.out_dtype == TCAVP_BF16) {
@@ -652,6 +660,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           epilogue_chunk(ep, m, pos, n0 + c * 32, r, rs, flags, ssq);
         }
         if (ep.sumsq_out && m < M) sumsq_add(ep.sumsq_out + remap_row(ep.remap_gi, ep.remap_go, ep.remap_off, m), ssq);
+        if ((flags & DBG_NO_STORE) && ssq == 123456.789f) reinterpret_cast<float*>(ep.out)[0] = ssq;   // keeps the ablated math alive
       }
       tc_fence_before();
       __syncwarp();
@@ -1098,7 +1107,7 @@ static int launch_tc_pair(const tcavp_gemm_args& a, const EpilogueParams& ep, cu
   if (((size_t)ep.ldo * osz) % 32 == 0 && (reinterpret_cast<uintptr_t>(ep.out) % 32) == 0) flags |= EPI_VEC_OUT;
   if (ep.residual && ((size_t)ep.ldr * rsz) % 32 == 0 && (reinterpret_cast<uintptr_t>(ep.residual) % 32) == 0) flags |= EPI_VEC_RES;
   if (ep.bias && (reinterpret_cast<uintptr_t>(ep.bias) % 16) == 0) flags |= EPI_VEC_BIAS;
-  if (const char* e = getenv("TCAVP_GEMM_DEBUG")) flags |= atoi(e) & (DBG_NO_TMA | DBG_NO_MMA | DBG_NO_EPI);
+  if (const char* e = getenv("TCAVP_GEMM_DEBUG")) flags |= atoi(e) & (DBG_NO_TMA | DBG_NO_MMA | DBG_NO_EPI | DBG_NO_STORE);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(NUM_THREADS);
