@@ -195,6 +195,7 @@ def run_ours(args):
     d["lens"] = torch.tensor(s["poly_len"], dtype=torch.int32, device=dev)
     d["ns"] = torch.tensor(s["norm_stat"], dtype=torch.float32, device=dev)
     red = torch.zeros(3, dtype=torch.float32, device=dev)
+    max_poly = int(max(s["poly_len"]))     # dataset metadata (lane sizes are 14 / 22 / 32 / 33 points, reference graph.py): host-known
     frozen = args.workload == "cfg5"     # backbone output precomputed (ablation_study_without_lora.py path): encoder + fusion only
     fh_dev = fh_host = None
     if frozen:
@@ -204,7 +205,7 @@ def run_ours(args):
 
     def step():
         o = eng.forward(d["x"], d["vision"], d["polygon"], d["lens"], d["input_ids"], d["attention_mask"], y=d["y"], norm_stat=d["ns"],
-                        final_hidden=fh_dev)
+                        final_hidden=fh_dev, max_poly_len=max_poly)
         if world > 1:
             red[0], red[1], red[2] = o["sum_ade"], o["sum_fde"], float(B)
             dist.all_reduce(red)

@@ -243,9 +243,15 @@ class Engine:
         return self._ln_res(y, L["n2"])
 
     # ---- sub-models ---------------------------------------------------------------------------------
-    def poly_forward(self, polygon, lens):
-        """reference scripts/train.py:362-383 -> (B, D) fp32."""
+    def poly_forward(self, polygon, lens, max_len=None):
+        """reference scripts/train.py:362-383 -> (B, D) fp32.  `max_len` (host-known upper bound of lane_polygon_len): rows past the
+        longest polygon are pure padding — masked as keys, skipped by the masked mean — so the encoder runs on the first
+        round_up(max_len, 16) points only."""
         p = self.poly
+        if max_len is not None:
+            Pp = max(16, (int(max_len) + 15) // 16 * 16)
+            if Pp < polygon.shape[1]:
+                polygon = polygon[:, :Pp].contiguous()
         B, P, D = polygon.shape[0], polygon.shape[1], p["D"]
         x = self._new(B * P, D, dtype=torch.float32)
         kmask = torch.empty(B, P, dtype=torch.int32, device=self.dev)
@@ -388,7 +394,7 @@ class Engine:
 
     @torch.no_grad()
     def forward(self, x, vision, polygon, poly_len, input_ids, attention_mask, y=None, norm_stat=None, final_hidden=None,
-                keep_intermediates=False):
+                keep_intermediates=False, max_poly_len=None):
         dev = self.dev
         if dev.type != "cuda":
             raise ops._lib.TcavpError("the model must be on a CUDA device (there is no CPU fallback): model.to('cuda')")
@@ -396,6 +402,8 @@ class Engine:
         B = x.shape[0]
         polygon = self._dev_f32(polygon)
         lens = poly_len if torch.is_tensor(poly_len) else torch.tensor(list(poly_len), dtype=torch.int32)
+        if max_poly_len is None and not lens.is_cuda and lens.numel() > 0:
+            max_poly_len = int(lens.max())          # host-resident lengths (the reference passes a Python list): no device sync needed
         lens = lens.to(device=dev, dtype=torch.int32, non_blocking=True)
         if y is not None and norm_stat is not None:
             y = self._dev_f32(y)
@@ -403,7 +411,7 @@ class Engine:
         else:
             y = norm_stat = None
         out = {}
-        poly_emb = self.poly_forward(polygon, lens)
+        poly_emb = self.poly_forward(polygon, lens, max_poly_len)
         if final_hidden is None:
             vision = vision.to(dev, non_blocking=True)
             if vision.dtype not in (torch.float32, torch.bfloat16):
