@@ -201,6 +201,37 @@ class Engine:
                                _Lin(d.post_mlp[3].weight[perm], d.post_mlp[3].bias[perm], small, dev))
         self._split_small(self.lt["mha"]["qkv"], self.lt["mha"]["out"], self.lt["f0"], self.lt["f3"], self.lt["lane_fc"],
                           *(self.lt["post"] or ()))
+        self._absorb_cross(d.cross_attn)
+
+    def _absorb_cross(self, mha):
+        """Few queries (T_out) against many keys (L) in the fusion cross-attention (train.py:793-798): instead of projecting all L
+        positions to K and V, the projections are absorbed into the query / output side —
+            scores_h = Q_h K_h^T = (Q_h Wk_h) X^T            (the key bias is constant along the softmax axis and drops out)
+            out_h    = P_h V_h   = (P_h X) Wv_h^T + bv_h      (rows of P sum to 1)
+        so attention runs with keys = values = X (the backbone output, read in place, one shared 'KV head' of width H) and the two
+        small projections fold into q_proj / out_proj:  Q' = q (Wk_h^T Wq_h)^T + bq_h Wk_h,  co = Z [Wo_h Wv_h]^T + (Wo bv + bo).
+        Removes the [B L, 2H] K/V projection (the largest GEMM of the fusion block) and its round trip through HBM.  Exact algebra;
+        used in bf16 compute mode (the fp32 parity mode keeps the reference's operation order)."""
+        self.lt["absorb"] = None
+        if not (self.SPLIT_SMALL and self.act == torch.bfloat16 and not os.environ.get("TCAVP_NO_ABSORB")):
+            return
+        E, heads = mha.embed_dim, mha.num_heads
+        dh = E // heads
+        if E % 64 or self.T_out > 64:
+            return
+        W = mha.in_proj_weight.detach().to(self.dev).float()
+        bvec = mha.in_proj_bias.detach().to(self.dev).float()
+        Wq, Wk, Wv = W[:E], W[E:2 * E], W[2 * E:]
+        bq, bv = bvec[:E], bvec[2 * E:]
+        Wo, bo = mha.out_proj.weight.detach().to(self.dev).float(), mha.out_proj.bias.detach().to(self.dev).float()
+        mq, cq, mo = [], [], []
+        for h in range(heads):
+            sl = slice(h * dh, (h + 1) * dh)
+            mq.append(Wk[sl].t() @ Wq[sl])            # [E, E]:  Q'_h = q . (Wk_h^T Wq_h)^T
+            cq.append(bq[sl] @ Wk[sl])                # [E]
+            mo.append(Wo[:, sl] @ Wv[sl])             # [E, E]:  co += Z_h . (Wo_h Wv_h)^T
+        self.lt["absorb"] = dict(mq=torch.cat(mq, 0).to(self.act).contiguous(), cq=torch.cat(cq, 0).contiguous(),
+                                 mo=torch.cat(mo, 1).to(self.act).contiguous(), co=(Wo @ bv + bo).contiguous(), E=E, heads=heads, dh=dh)
 
     # ---- building blocks --------------------------------------------------------------------------
     def _new(self, *shape, dtype=None):
@@ -371,8 +402,17 @@ class Engine:
         dec_t = dec.view(B * To, C)                  # fp32 residual path of the regression head
         dq = dec_t if self.act == sm else ops.cast(dec_t, self._new(B * To, C), rows=B * To, cols=C)
         q = ops.gemm(dq, lt["dec_proj"].w, self._new(B * To, H), bias=lt["dec_proj"].b)
-        a = self._cross_attention(q, To, fh, L, B, lt["cross"])
-        co = ops.gemm(a, lt["cross"]["out"].w, self._new(B * To, H), bias=lt["cross"]["out"].b)
+        ab = lt.get("absorb")
+        if ab is not None and fh.dtype == self.act and To <= 64 and L <= 256:
+            E, heads = ab["E"], ab["heads"]
+            qp = ops.gemm(q, ab["mq"], self._new(B * To, heads * E), bias=ab["cq"])
+            z = self._new(B * To, heads * E)
+            ops.attention(qp, fh, fh, z, B=B, H=heads, Hkv=1, Tq=To, Tk=L, dh=E, q_strides=(To * heads * E, heads * E), k_strides=(L * E, E),
+                          v_strides=(L * E, E), o_strides=(To * heads * E, heads * E), scale=ab["dh"] ** -0.5)
+            co = ops.gemm(z, ab["mo"], self._new(B * To, H), bias=ab["co"])
+        else:
+            a = self._cross_attention(q, To, fh, L, B, lt["cross"])
+            co = ops.gemm(a, lt["cross"]["out"].w, self._new(B * To, H), bias=lt["cross"]["out"].b)
         fused = ops.gemm(co, lt["dec_unproj"].w, self._new(B * To, C, dtype=sm), bias=lt["dec_unproj"].b, residual=dec_t)
         decoded = torch.empty(B, 2, To, dtype=torch.float32, device=self.dev)
         out = {"decoded": decoded}
