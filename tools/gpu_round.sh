@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU-box session: parity tests, default bench (+ reference arm), cfg3 / cfg5 / train benches, launch list + full ncu captures.
-TAG=${1:-r01p}
+TAG=${1:-r01z}
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/t_${TAG}.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/t_${TAG}.log
 python bench.py > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err; echo "bench rc=$?"

@@ -169,7 +169,9 @@ def gemm(a, w, out, *, M=None, N=None, K=None, lda=None, ldw=None, ldo=None, bia
     if rope is not None:     # (table, L, dh, cols)
         g.rope_cos_sin, g.rope_L, g.rope_dh, g.rope_cols = rope[0].data_ptr(), rope[1], rope[2], rope[3]
     if g.in_dtype == BF16:
-        if g.N > 128 and g.M >= 2048:      # mirrors tcavp_gemm's dispatch: CTA-pair (cta_group::2) kernel for the large problems
+        if g.N > 128 and g.K >= 2048 and g.M >= 8192 and ((g.M + 511) // 512) * ((g.N + 255) // 256) >= 4 * 74:
+            kern = "gemm_tc_wide_kernel[N%d,K%d]" % (g.N, g.K)     # mirrors tcavp_gemm's dispatch (long contraction, >= 4 waves of tiles)
+        elif g.N > 128 and g.M >= 2048:    # CTA-pair (cta_group::2) kernel for the large problems
             kern = "gemm_tc_pair_kernel<256>[N%d,K%d]" % (g.N, g.K)
         else:
             kern = "gemm_tc_kernel<%d>[N%d,K%d]" % (32 if g.N <= 32 else 64 if g.N <= 64 else 128 if g.N <= 128 else 256, g.N, g.K)
