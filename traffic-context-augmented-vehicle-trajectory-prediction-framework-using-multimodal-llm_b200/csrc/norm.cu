@@ -252,6 +252,42 @@ static bool aligned_rows(const void* p, int ld, int dtype) {
 
 }  // namespace tcavp
 
+namespace tcavp {
+// Register-resident RMSNorm for rows of <= 1024 elements: the row is read once (NV 8-element vectors per lane).
+template <int NV>
+__global__ void __launch_bounds__(256) rmsnorm_reg_kernel(const void* __restrict__ x, const float* __restrict__ w, void* __restrict__ out, int rows,
+                                                          int cols, int ldi, int ldo, float eps, int in_dtype, int out_dtype) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const size_t base = (size_t)row * ldi, obase = (size_t)row * ldo;
+  float v[NV][8];
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    if (c < cols) {
+      load8(x, base + c, in_dtype, v[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) q += v[i][e] * v[i][e];
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / cols + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    if (c < cols) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + c)), w1 = __ldg(reinterpret_cast<const float4*>(w + c + 4));
+      const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      float o8[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o8[e] = v[i][e] * rstd * ww[e];
+      store8(out, obase + c, out_dtype, o8);
+    }
+  }
+}
+}  // namespace tcavp
+
 extern "C" int tcavp_layernorm(const void* x, const void* residual, const float* w, const float* b, void* out, int rows,
                                int cols, float eps, int in_dtype, int out_dtype, int remap_gi, int remap_go, int remap_off,
                                const float* rowvec, tcavp_stream_t stream_) {
@@ -312,7 +348,12 @@ extern "C" int tcavp_rmsnorm(const void* x, int ldi, const float* w, void* out, 
   const bool vec = cols % 8 == 0 && aligned_rows(x, ldi, in_dtype) && aligned_rows(out, ldo, out_dtype);
   const int wpb = 8;
   const int grid = (rows + wpb - 1) / wpb;
-  if (vec)
+  if (vec && cols <= 1024 && reinterpret_cast<uintptr_t>(w) % 16 == 0) {
+    if (cols <= 256) rmsnorm_reg_kernel<1><<<grid, wpb * 32, 0, stream>>>(x, w, out, rows, cols, ldi, ldo, eps, in_dtype, out_dtype);
+    else if (cols <= 512) rmsnorm_reg_kernel<2><<<grid, wpb * 32, 0, stream>>>(x, w, out, rows, cols, ldi, ldo, eps, in_dtype, out_dtype);
+    else if (cols <= 768) rmsnorm_reg_kernel<3><<<grid, wpb * 32, 0, stream>>>(x, w, out, rows, cols, ldi, ldo, eps, in_dtype, out_dtype);
+    else rmsnorm_reg_kernel<4><<<grid, wpb * 32, 0, stream>>>(x, w, out, rows, cols, ldi, ldo, eps, in_dtype, out_dtype);
+  } else if (vec)
     rmsnorm_kernel<true><<<grid, wpb * 32, 0, stream>>>(x, w, out, rows, cols, ldi, ldo, eps, in_dtype, out_dtype);
   else
     rmsnorm_kernel<false><<<grid, wpb * 32, 0, stream>>>(x, w, out, rows, cols, ldi, ldo, eps, in_dtype, out_dtype);
