@@ -255,7 +255,7 @@ def run_ours(args):
     def e2e_step():
         if frozen:
             r = model.predict_with_metrics(h["x"], None, h["polygon"], h["lens"], h["y"], h["ns"], None, None,
-                                           final_hidden=h["fh"].to(dev, non_blocking=True))
+                                           final_hidden=h["fh"])
         else:
             r = model.predict_with_metrics(h["x"], h["vision"], h["polygon"], h["lens"], h["y"], h["ns"], h["input_ids"], h["attention_mask"])
         dec_host.copy_(r["decoded"], non_blocking=True)

@@ -451,7 +451,30 @@ class Engine:
         else:
             y = norm_stat = None
         out = {}
+        # Host-resident (pinned) bulk inputs travel on a side stream while the polygon / temporal encoders — which only need the
+        # small tensors already queued above — run on the compute stream; the compute stream joins right before the first consumer.
+        bulk = [t for t in ((vision, input_ids, attention_mask) if final_hidden is None else (final_hidden,)) if torch.is_tensor(t) and not t.is_cuda]
+        copied = None
+        if bulk and all(t.is_pinned() for t in bulk):
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(device=dev)
+            main = torch.cuda.current_stream()
+            self._copy_stream.wait_stream(main)
+            with torch.cuda.stream(self._copy_stream):
+                moved = {id(t): t.to(dev, non_blocking=True) for t in bulk}
+                copied = torch.cuda.Event()
+                copied.record()
+            for t in moved.values():
+                t.record_stream(main)
+            pick = lambda t: moved.get(id(t), t) if torch.is_tensor(t) else t      # noqa: E731
+            if final_hidden is None:
+                vision, input_ids, attention_mask = pick(vision), pick(input_ids), pick(attention_mask)
+            else:
+                final_hidden = pick(final_hidden)
         poly_emb = self.poly_forward(polygon, lens, max_poly_len)
+        enc = self.ltsf_encode(x, B)
+        if copied is not None:
+            torch.cuda.current_stream().wait_event(copied)
         if final_hidden is None:
             vision = vision.to(dev, non_blocking=True)
             if vision.dtype not in (torch.float32, torch.bfloat16):
@@ -471,7 +494,6 @@ class Engine:
             fh = final_hidden.to(device=dev, dtype=self.act).contiguous()
             L = fh.shape[1]
             fh = fh.view(B * L, -1)
-        enc = self.ltsf_encode(x, B)
         out.update(self.ltsf_decode(enc, poly_emb, fh, x, B, L, y, norm_stat))
         if y is not None:
             m = out["metrics"]
