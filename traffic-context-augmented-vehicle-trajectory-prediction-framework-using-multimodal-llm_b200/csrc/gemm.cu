@@ -1,10 +1,15 @@
-// tcavp_gemm: out = act(A . W^T + bias) + residual, with row remap.
+// tcavp_gemm: out = act(A . W^T + bias) + residual, with row remap and the fused epilogues of include/tcavp.h
+// (RMSNorm row factor / statistics, RoPE, SwiGLU forward + stash, SwiGLU backward).
 //
-//   bf16 : persistent, warp-specialised tcgen05 kernel.  One elected thread issues TMA loads
-//          (cp.async.bulk.tensor, 128-byte swizzle) into a multi-stage shared-memory ring, one elected
-//          thread issues tcgen05.mma (UMMA 128 x BLOCK_N x 16, bf16 -> fp32) into one of two TMEM
-//          accumulator buffers, four epilogue warps drain the other buffer with tcgen05.ld and apply the
-//          fused epilogue, so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   bf16 : persistent, warp-specialised tcgen05 kernels.  Warp 0: one elected thread issues TMA loads (cp.async.bulk.tensor,
+//          128-byte swizzle) into a multi-stage shared-memory ring; warp 1: one elected thread issues tcgen05.mma (bf16 -> fp32)
+//          into TMEM; 16 epilogue warps drain TMEM with tcgen05.ld, apply the fused epilogue and store 32 bytes per lane.
+//          Variants, picked by tcavp_gemm from the problem shape:
+//            gemm_tc_kernel<BN, CM>   one CTA per 128 x BN tile (BN 32..256), double-buffered accumulators; CM = 2 multicasts W
+//            gemm_tc_pair_kernel<256> CTA pair (cta_group::2) on a 256 x 256 tile, double-buffered accumulators (the default for
+//                                     large problems: the epilogue of tile i overlaps the MMAs of tile i+1)
+//            gemm_tc_wide_kernel      CTA pair on a 512 x 256 tile, all 512 TMEM columns, for long contractions (K >= 2048)
+//            gemm_tc_quad_kernel<256> two pairs per 4-CTA cluster sharing W by multicast (A/B option only)
 //   fp32 : SIMT FFMA kernel with exact fp32 accumulation (the rtol 1e-4 parity mode; no TF32).
 //
 // LoRA (peft lora.Linear, reference scripts/train.py:432-440) is expressed by the caller as extra K columns
