@@ -333,7 +333,7 @@ def run_ours(args):
 TRAIN_WORKLOADS = {
     # name: (model preset, scenes per GPU per step, L_text)  — BASELINE.json configs[3]: LoRA fine-tune step, data parallel
     "cfg2": ("cfg1", 512, 128),
-    "cfg3": ("cfg3", 64, 128),
+    "cfg3": ("cfg3", 128, 128),    # 103 GiB of the 180 GB at 128 scenes / GPU / step
 }
 
 
