@@ -254,7 +254,7 @@ def _ltsf_sd(C, T, To, seed=0):
     return sd
 
 
-@pytest.mark.parametrize("T,To", [(15, 25), (6, 12), (30, 30)])
+@pytest.mark.parametrize("T,To", [(15, 25), (6, 12), (30, 30), (18, 30), (10, 20), (20, 50), (15, 50)])
 def test_ltsf_encode_and_nlinear_decode(ops, T, To):
     B, C = 7, 64
     sd = _ltsf_sd(C, T, To)

@@ -99,3 +99,28 @@ def test_merged_lora_matches_the_side_path(lib_built, dtype, tol):
     torch.testing.assert_close(merged, side, rtol=tol, atol=tol)
     torch.testing.assert_close(merged, fix["out"]["decoded"], rtol=tol, atol=tol)
     assert set(m.state_dict()) == keys
+
+
+def test_collated_batch_runs_through_the_model(lib_built):
+    """tcavp_b200.custom_collate_fn -> ScenePack.to_device -> forward: the packed length / norm tensors and the reference's list-typed
+    entries give the same result, and both match the golden output of the unmodified reference on the same scenes."""
+    import tcavp_b200 as T
+    fix = load_golden("tiny_b6")
+    m = build_filled_model(fix, "fp32", "cuda")
+    i = fix["inputs"]
+    B = i["x"].shape[0]
+    samples = [dict(traj_emb=i["x"][b].t().contiguous(), target_traj=i["y"][b].t().contiguous(), vision_emb=i["vision"][b],
+                    lane_polygon=i["polygon"][b], lane_polygon_len=int(i["poly_len"][b]), norm_stat=tuple(i["norm_stat"][b]),
+                    context_str="c", answer_str="a", track_id=b, input_ids=i["input_ids"][b], attention_mask=i["attention_mask"][b],
+                    labels=i["input_ids"][b]) for b in range(B)]
+    pack = T.custom_collate_fn(samples)
+    dev = pack.to_device("cuda")
+    with torch.no_grad():
+        a = m(dev["traj_emb"], dev["vision_emb"], pack["context_str"], dev["lane_polygon"], pack["lane_polygon_len"], input_ids=dev["input_ids"],
+              attention_mask=dev["attention_mask"])
+        l2, b2 = m(dev["traj_emb"], dev["vision_emb"], pack["context_str"], dev["lane_polygon"], dev["lane_polygon_len_t"], y=dev["target_traj"],
+                   norm_stat=dev["norm_stat_t"], input_ids=dev["input_ids"], attention_mask=dev["attention_mask"])
+    torch.cuda.synchronize()
+    torch.testing.assert_close(a.cpu(), fix["out"]["decoded"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(b2.cpu(), a.cpu(), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(l2.cpu(), fix["out"]["loss"], rtol=1e-4, atol=0)
