@@ -26,6 +26,11 @@ FIXTURES = {
     "tiny_b6": ("tiny", {}, 6, 24, 11, 101, [0, 64, 1, 33, 14, 22], "scripts/train.py"),
     "cfg1_b8": ("cfg1", {}, 8, 128, 7, 3, None, "scripts/train.py"),
     "cfg5_b32": ("cfg5", {}, 32, 128, 5, 9, None, "scripts/train.py"),
+    # 7B-class geometry (H 4096, 32 heads of 128, I 11008, LoRA r 16) cut to 2 decoder layers and a 4096-entry vocabulary so the
+    # unmodified reference finishes on the authoring container's CPU (~10 min); 16 scenes = 2304 rows reach the CTA-pair GEMM.
+    "cfg3l2_b16": ("cfg3", {"base_model_name": dict(vocab_size=4096, hidden_size=4096, intermediate_size=11008, num_hidden_layers=2,
+                                                   num_attention_heads=32, num_key_value_heads=32, head_dim=128, rms_norm_eps=1e-5,
+                                                   rope_theta=10000.0)}, 16, 128, 13, 17, None, "scripts/train.py"),
 }
 
 

@@ -17,7 +17,7 @@ def _forward(fix, dtype, keep=True):
     return m, {k: (v.float().cpu() if torch.is_tensor(v) else v) for k, v in out.items()}
 
 
-@pytest.mark.parametrize("name", ["tiny_b6", "cfg1_b8", "cfg5_b32"])
+@pytest.mark.parametrize("name", ["tiny_b6", "cfg1_b8", "cfg5_b32", "cfg3l2_b16"])
 def test_fp32_forward_matches_reference(name, lib_built):
     fix = load_golden(name)
     _, o = _forward(fix, "fp32")
@@ -40,7 +40,7 @@ def test_fp32_forward_matches_reference(name, lib_built):
     torch.testing.assert_close(o["fde"], g["fde"], rtol=1e-4, atol=1e-2)
 
 
-@pytest.mark.parametrize("name", ["tiny_b6", "cfg1_b8", "cfg5_b32"])
+@pytest.mark.parametrize("name", ["tiny_b6", "cfg1_b8", "cfg5_b32", "cfg3l2_b16"])
 def test_bf16_forward_matches_reference(name, lib_built):
     fix = load_golden(name)
     _, o = _forward(fix, "bf16")
