@@ -31,6 +31,10 @@ FIXTURES = {
     "cfg3l2_b16": ("cfg3", {"base_model_name": dict(vocab_size=4096, hidden_size=4096, intermediate_size=11008, num_hidden_layers=2,
                                                    num_attention_heads=32, num_key_value_heads=32, head_dim=128, rms_norm_eps=1e-5,
                                                    rope_theta=10000.0)}, 16, 128, 13, 17, None, "scripts/train.py"),
+    # grouped-query attention (Llama-3.2-1B geometry: 32 query heads on 8 KV heads, rope_theta 5e5), two layers, ragged text
+    "gqa_l2_b32": ("cfg1", {"lora_r": 16, "base_model_name": dict(vocab_size=4096, hidden_size=2048, intermediate_size=8192, num_hidden_layers=2,
+                                                                 num_attention_heads=32, num_key_value_heads=8, head_dim=64, rms_norm_eps=1e-5,
+                                                                 rope_theta=500000.0)}, 32, 96, 21, 23, None, "scripts/train.py"),
 }
 
 
