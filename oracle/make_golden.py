@@ -105,20 +105,28 @@ def make(name):
     print(f"{name}: {os.path.getsize(path) / 1e6:.2f} MB  loss={float(loss):.4f} ade={float(ade.mean()):.4f} fde={float(fde.mean()):.4f}")
 
 
+# name -> (model preset, B, l_text, polygon lengths)
+GRAD_FIXTURES = {
+    "tiny_b5_grads": ("tiny", 5, 24, [64, 1, 33, 14, 22]),
+    # the real 768-class geometry (12 layers, 12 heads of 64, L = 144, LoRA r 8): gradients are stored compressed (restated.compress_grad)
+    "cfg1_b3_grads": ("cfg1", 3, 128, [33, 14, 22]),
+}
+
+
 def make_grads(name="tiny_b5_grads"):
-    """Gradients of the UNMODIFIED reference model (eval mode = every dropout off, autograd on) for the tiny preset:
+    """Gradients of the UNMODIFIED reference model (eval mode = every dropout off, autograd on):
     the pin of the fine-tune step (reference scripts/im_kim_train_GRN.py:1029-1039)."""
     from oracle import restated
-    mc = dict(T.MODEL_PRESETS["tiny"])
+    preset, B, l_text, poly_len = GRAD_FIXTURES[name]
+    mc = dict(T.MODEL_PRESETS[preset])
     lc = T.resolve_llama(mc["base_model_name"])
     mod = ref_loader.load_reference("scripts/train.py", lc)
     model = ref_loader.build_reference_model(mod, mc, lc)
     sd = model.state_dict()
     T.deterministic_fill_(sd, 13)
     model.load_state_dict(sd, strict=True)
-    B, l_text = 5, 24
-    s = T.make_scenes(B, mc["seq_len"], mc["out_len"], vision_dim=mc["vision_dim"], l_text=l_text, vocab=lc["vocab_size"], seed=77)
-    poly_len = [64, 1, 33, 14, 22]        # no empty polygon: the reference's own gradients are NaN there (all-masked softmax)
+    s = T.make_scenes(B, mc["seq_len"], mc["out_len"], vision_dim=mc.get("vision_dim", 512), l_text=l_text, vocab=lc["vocab_size"], seed=77)
+    poly_len = list(poly_len)             # no empty polygon: the reference's own gradients are NaN there (all-masked softmax)
     g = torch.Generator().manual_seed(78)
     pts = torch.rand(B, 64, 2, generator=g) * torch.tensor([3839.0, 750.0]) + torch.tensor([0.0, 700.0])
     keep = torch.arange(64)[None, :] < torch.tensor(poly_len)[:, None]
@@ -152,5 +160,5 @@ def make_grads(name="tiny_b5_grads"):
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
-    for n in (sys.argv[1:] or list(FIXTURES) + ["tiny_b5_grads"]):
+    for n in (sys.argv[1:] or list(FIXTURES) + list(GRAD_FIXTURES)):
         make_grads(n) if n.endswith("_grads") else make(n)

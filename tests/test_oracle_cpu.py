@@ -66,9 +66,10 @@ def _check_against_compressed(got, want, rtol, atol, key):
     torch.testing.assert_close(g2.double().sum(0).float(), want["colsum"], rtol=rtol, atol=atol + 1e-4 * scale, msg=lambda m: f"{key} colsum: {m}")
 
 
-def test_restated_gradients_match_reference_autograd():
+@pytest.mark.parametrize("name", ["tiny_b5_grads", "cfg1_b3_grads"])
+def test_restated_gradients_match_reference_autograd(name):
     """Pins the fine-tune oracle: autograd through oracle/restated.py == gradients of the unmodified reference model."""
-    fix = load_golden("tiny_b5_grads")
+    fix = load_golden(name)
     m = T.MultiModalTrajectoryModel(**fix["model_cfg"])
     sd = m.state_dict()
     T.deterministic_fill_(sd, fix["weight_seed"])
