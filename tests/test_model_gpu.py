@@ -128,3 +128,26 @@ def test_collated_batch_runs_through_the_model(lib_built):
     torch.testing.assert_close(a.cpu(), fix["out"]["decoded"], rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(b2.cpu(), a.cpu(), rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(l2.cpu(), fix["out"]["loss"], rtol=1e-4, atol=0)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_frozen_backbone_path_reuses_supplied_final_hidden(lib_built, dtype):
+    """cfg5 / ablation_study_without_lora.py path: with the backbone output supplied, only the encoders + fusion + head run, and the
+    result equals the full forward that produced that backbone output (fp32: also the reference golden)."""
+    from tcavp_b200 import ops
+    fix = load_golden("cfg5_b32")
+    m = build_filled_model(fix, dtype, "cuda")
+    i = fix["inputs"]
+    e = m.engine()
+    full = e.forward(i["x"], i["vision"], i["polygon"], i["poly_len"], i["input_ids"], i["attention_mask"], y=i["y"], norm_stat=i["norm_stat"],
+                     keep_intermediates=True)
+    fh = full["final_hidden"].to(torch.bfloat16 if dtype == "bf16" else torch.float32)
+    n0 = ops.launch_count()
+    part = e.forward(i["x"], None, i["polygon"], i["poly_len"], None, None, y=i["y"], norm_stat=i["norm_stat"], final_hidden=fh)
+    n_part = ops.launch_count() - n0
+    torch.cuda.synchronize()
+    torch.testing.assert_close(part["decoded"], full["decoded"], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(part["sum_ade"], full["sum_ade"], rtol=1e-5, atol=1e-3)
+    assert n_part < 80                                  # no Q-Former / decoder-stack launches
+    if dtype == "fp32":
+        torch.testing.assert_close(part["decoded"].cpu(), fix["out"]["decoded"], rtol=1e-4, atol=5e-4)
