@@ -151,3 +151,31 @@ def test_frozen_backbone_path_reuses_supplied_final_hidden(lib_built, dtype):
     assert n_part < 80                                  # no Q-Former / decoder-stack launches
     if dtype == "fp32":
         torch.testing.assert_close(part["decoded"].cpu(), fix["out"]["decoded"], rtol=1e-4, atol=5e-4)
+
+
+def test_tokenizer_branch_with_an_attached_tokenizer(lib_built):
+    """reference scripts/train.py:556-575 (the branch the V2 forward, im_kim_train_GRN.py:793-795, always takes): without input_ids the
+    prompts are tokenised inside forward() — right-padded, attention mask from the tokenizer — and give the same result as passing
+    the same ids / mask explicitly."""
+    fix = load_golden("tiny_b6")
+    m = build_filled_model(fix, "fp32", "cuda")
+    i = fix["inputs"]
+    ids, am = i["input_ids"], i["attention_mask"]
+
+    class Tok:                       # stands in for AutoTokenizer (no hub offline): "b" -> row b of the fixture's padded ids / mask
+        pad_token, eos_token = None, "</s>"
+
+        def __call__(self, texts, return_tensors="pt", padding=True, truncation=True):
+            assert return_tensors == "pt" and padding and truncation          # the reference's call (train.py:558)
+            rows = [int(t) for t in texts]
+            return {"input_ids": ids[rows].clone(), "attention_mask": am[rows].clone()}
+    with pytest.raises(NotImplementedError):
+        m(i["x"].cuda(), i["vision"].cuda(), ["0"] * 6, i["polygon"].cuda(), i["poly_len"])
+    m.mllm.tokenizer = Tok()
+    ctx = [str(b) for b in range(i["x"].shape[0])]
+    with torch.no_grad():
+        got = m(i["x"].cuda(), i["vision"].cuda(), ctx, i["polygon"].cuda(), i["poly_len"])
+        want = m(i["x"].cuda(), i["vision"].cuda(), ctx, i["polygon"].cuda(), i["poly_len"], input_ids=ids.cuda(), attention_mask=am.cuda())
+    assert m.mllm.tokenizer.pad_token == "</s>"
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(got.cpu(), fix["out"]["decoded"], rtol=1e-4, atol=1e-4)

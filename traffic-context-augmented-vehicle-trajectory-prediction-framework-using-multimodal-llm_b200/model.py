@@ -396,7 +396,17 @@ class MultiModalTrajectoryModel(nn.Module):
         internal CE loss, which the reference discards (train.py:547-554).  `lane_polygon_len` / `norm_stat` may be
         Python lists (as the reference's collate produces) or device tensors."""
         if input_ids is None or attention_mask is None:
-            raise NotImplementedError("tokenizer branch (train.py:556-575) needs a hub tokenizer; pass input_ids and attention_mask")
+            # tokenizer branch (train.py:556-575; the V2 forward of im_kim_train_GRN.py:793-795 always takes it): context_str is tokenised
+            # here exactly like the reference (padding=True, truncation=True).  There is no hub access to build the tokenizer from
+            # base_model_name, so the caller attaches one: `model.mllm.tokenizer = AutoTokenizer.from_pretrained(...)`.
+            tok = self.mllm.tokenizer
+            if tok is None:
+                raise NotImplementedError("tokenizer branch (train.py:556-575): attach a tokenizer (model.mllm.tokenizer = ...) or pass "
+                                          "input_ids and attention_mask")
+            if getattr(tok, "pad_token", None) is None and getattr(tok, "eos_token", None) is not None:
+                tok.pad_token = tok.eos_token                                    # train.py:501-502
+            enc = tok(list(context_str), return_tensors="pt", padding=True, truncation=True)
+            input_ids, attention_mask = enc["input_ids"], enc["attention_mask"]
         if torch.is_grad_enabled() and y is not None and norm_stat is not None and any(p.requires_grad for p in self.parameters()):
             return self._train_step(x, vision_embs, lane_polygon_batch, lane_polygon_len, y, norm_stat, input_ids, attention_mask)
         eng = self.engine()
