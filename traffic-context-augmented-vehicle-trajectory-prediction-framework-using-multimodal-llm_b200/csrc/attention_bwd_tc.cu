@@ -16,7 +16,6 @@
 namespace tcavp {
 namespace fb {
 
-constexpr int KB = 64;
 constexpr int PAD = 8;
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
@@ -40,7 +39,8 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-template <int DH, int MAXT, int MINB>
+// KB = keys per block of the query-outer pass (48 when that pads Tk to fewer dead keys, e.g. L = 144 = 3 x 48; 64 otherwise).
+template <int DH, int MAXT, int MINB, int KB>
 __global__ void __launch_bounds__(MAXT, MINB) attn_bwd_tc_kernel(tcavp_attn_args a, const __nv_bfloat16* __restrict__ dout, long long do_sb,
                                                                  long long do_st, __nv_bfloat16* __restrict__ dq, long long dq_sb,
                                                                  long long dq_st, void* __restrict__ dk, long long dk_sb, long long dk_st,
@@ -371,7 +371,9 @@ int attention_bwd_tc_launch(const tcavp_attn_args& a, const void* dout, long lon
       dq_sb % 2 || dq_st % 2 || dk_sb % 2 || dk_st % 2 || dv_sb % 2 || dv_st % 2)
     return 1;
   const int tq_pad = (a.Tq + 15) / 16 * 16;
-  const int tk_pad = (a.Tk + fb::KB - 1) / fb::KB * fb::KB;
+  auto pad_to = [](int n, int m) { return (n + m - 1) / m * m; };
+  const int kb = pad_to(a.Tk, 48) < pad_to(a.Tk, 64) ? 48 : 64;
+  const int tk_pad = pad_to(a.Tk, kb);
   const int nqs = (a.Tq + 15) / 16, nks = (a.Tk + 15) / 16;
   const int slabs = nqs > nks ? nqs : nks;
   int warps = (slabs + 1) / 2;
@@ -379,12 +381,17 @@ int attention_bwd_tc_launch(const tcavp_attn_args& a, const void* dout, long lon
   const size_t smem = (size_t)2 * (tq_pad + tk_pad) * (a.dh + fb::PAD) * 2 + (size_t)3 * tq_pad * 4 + (size_t)tk_pad * 4;
   if (smem > 220 * 1024) return 1;
   const dim3 grid(a.B * a.H);
-#define TCAVP_BWD(DH, MAXT, MINB)                                                                                                           \
+#define TCAVP_BWD_KB(DH, MAXT, MINB, KB_)                                                                                                   \
   do {                                                                                                                                      \
-    TCAVP_CUDA(cudaFuncSetAttribute(fb::attn_bwd_tc_kernel<DH, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
-    fb::attn_bwd_tc_kernel<DH, MAXT, MINB><<<grid, warps * 32, smem, stream>>>(                                                             \
+    TCAVP_CUDA(cudaFuncSetAttribute(fb::attn_bwd_tc_kernel<DH, MAXT, MINB, KB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+    fb::attn_bwd_tc_kernel<DH, MAXT, MINB, KB_><<<grid, warps * 32, smem, stream>>>(                                                        \
         a, reinterpret_cast<const __nv_bfloat16*>(dout), do_sb, do_st, reinterpret_cast<__nv_bfloat16*>(dq), dq_sb, dq_st, dk, dk_sb, dk_st, \
-        dv, dv_sb, dv_st, dkv_dtype == TCAVP_BF16 ? 1 : 0, tq_pad, tk_pad);                                                                                                  \
+        dv, dv_sb, dv_st, dkv_dtype == TCAVP_BF16 ? 1 : 0, tq_pad, tk_pad);                                                                  \
+  } while (0)
+#define TCAVP_BWD(DH, MAXT, MINB)                      \
+  do {                                                 \
+    if (kb == 48) TCAVP_BWD_KB(DH, MAXT, MINB, 48);    \
+    else TCAVP_BWD_KB(DH, MAXT, MINB, 64);             \
   } while (0)
   if (a.dh == 64) {
     if (warps <= 5) TCAVP_BWD(64, 160, 2);
@@ -399,6 +406,7 @@ int attention_bwd_tc_launch(const tcavp_attn_args& a, const void* dout, long lon
     TCAVP_BWD(16, 256, 2);
   }
 #undef TCAVP_BWD
+#undef TCAVP_BWD_KB
   return check_launch("attn_bwd_tc_kernel");
 }
 
