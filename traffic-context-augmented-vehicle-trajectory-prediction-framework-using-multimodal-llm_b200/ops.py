@@ -470,7 +470,8 @@ def traj_loss_bwd(decoded, y, norm_stat, d_o, *, B, T_out, gscale=None):
 def skinny_dw(Y, Z, out, *, M, N, J, ldy=None, ldz=None, ldo=None, row_scale=None):
     """out[n][j] += sum_m row_scale[m] * Y[m][n] * Z[m][j]   (out fp32)."""
     _need_cuda(Y, Z, out, row_scale)
-    _call("tcavp_skinny_dw", "skinny_dw_kernel", _p(Y), N if ldy is None else ldy, dt(Y), _p(Z), J if ldz is None else ldz, dt(Z),
+    tc = Y.dtype == torch.bfloat16 and Z.dtype == torch.bfloat16 and N % 8 == 0 and J % 8 == 0
+    _call("tcavp_skinny_dw", "dw_tc_kernel[lora]" if tc else "skinny_dw_kernel", _p(Y), N if ldy is None else ldy, dt(Y), _p(Z), J if ldz is None else ldz, dt(Z),
           _p(row_scale), _p(out), J if ldo is None else ldo, _ll(M), N, J, flops=2.0 * M * N * J, nbytes=float(M * N * Y.element_size()))
     return out
 
@@ -480,7 +481,9 @@ def dw(dy, x, out, *, M, N, K, lddy=None, ldx=None, ldo=None):
     _need_cuda(dy, x, out)
     if out.dtype != torch.float32:
         raise TypeError("dw: out must be fp32")
-    _call("tcavp_dw", "dw_simt_kernel", _p(dy), dy.stride(0) if lddy is None else lddy, dt(dy), _p(x), x.stride(0) if ldx is None else ldx, dt(x),
+    tc = (dy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and N % 8 == 0 and K % 8 == 0 and dy.data_ptr() % 16 == 0 and
+          x.data_ptr() % 16 == 0 and (dy.stride(0) if lddy is None else lddy) % 8 == 0 and (x.stride(0) if ldx is None else ldx) % 8 == 0)
+    _call("tcavp_dw", "dw_tc_kernel" if tc else "dw_simt_kernel", _p(dy), dy.stride(0) if lddy is None else lddy, dt(dy), _p(x), x.stride(0) if ldx is None else ldx, dt(x),
           _p(out), out.stride(0) if ldo is None else ldo, _ll(M), N, K, flops=2.0 * M * N * K,
           nbytes=float(M * (N * dy.element_size() + K * x.element_size())))
     return out
