@@ -25,13 +25,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # stdout carries exactly ONE JSON line: everything else a library writes to fd 1 (e.g. NCCL's version banner) goes to stderr.
-_JSON_OUT = os.fdopen(os.dup(1), "w")
-os.dup2(2, 1)
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """Called from the command-line entry only (importing this module has no side effects)."""
+    global _JSON_OUT
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
 
 def emit(obj):
-    _JSON_OUT.write(json.dumps(obj) + "\n")
-    _JSON_OUT.flush()
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
 
 
 METRIC = "predicted scenes/sec (forward + ADE/FDE)"
@@ -501,6 +508,7 @@ if __name__ == "__main__":
     ap.add_argument("--merge-lora", action="store_true", help="serve-time option: fold LoRA into the base weights at pack time (not the default "
                     "benchmark configuration: the reference runs the unmerged peft form)")
     a = ap.parse_args()
+    _claim_stdout()
     if a.impl == "reference":
         run_reference(a)
     elif a.mode == "train":
