@@ -16,8 +16,11 @@ dev = torch.device("cuda:0")
 torch.manual_seed(0)
 SHAPES = [  # (M, N, K)  incl. ragged M / N / K tails
     (2048, 256, 64), (2048, 512, 768), (4096 + 77, 768, 768), (147456, 2304, 784), (147456, 768, 768), (147456, 6144, 768),
-    (147456, 768, 3072), (2048 + 130, 320, 200), (36864, 12288, 4096), (36864, 4096, 4096),
+    (147456, 768, 3072), (2048 + 130, 320, 200), (36864, 12288, 4096), (36864, 4096, 4096), (36864, 22016, 4096), (36864, 4096, 11008),
+    (36864 + 300, 11008 + 64, 4096),
 ]
+if "--big" in sys.argv:      # the 7B-class shapes only (W larger than the L2 panel budget: TCAVP_GEMM_PANEL_MB A/B)
+    SHAPES = [s for s in SHAPES if s[2] >= 4096]
 timing = "--time" in sys.argv
 for (M, N, K) in SHAPES:
     a = (torch.randn(M, K, device=dev) * 0.5).bfloat16()

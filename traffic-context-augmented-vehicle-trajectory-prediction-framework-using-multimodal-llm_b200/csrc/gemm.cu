@@ -161,8 +161,35 @@ __device__ __forceinline__ void ldg256(const void* p, uint32_t (&v)[8]) {
                : "l"(p));
 }
 
+// Tile order of the persistent kernels.  Units are swept n-fastest inside PANELS of `pw` n-tiles: the W rows of a panel stay resident in
+// L2 while every row block of A streams past them once, so W is read from DRAM once and A once per panel.  With pw >= tiles_n (any
+// problem whose whole W fits in L2, e.g. the 768-class shapes) this is the plain row-major order.  Without panels a 7B-class gate/up
+// GEMM (W = 180 MB > L2) re-read W for every 512-row block: 12.7 GB of DRAM reads per launch against 0.5 GB algorithmic.
+__device__ __forceinline__ void unit_to_tile(int u, int tiles_mg, int tiles_n, int pw, int& mg, int& nt) {
+  if (pw >= tiles_n) {
+    mg = u / tiles_n;
+    nt = u % tiles_n;
+    return;
+  }
+  const int per_panel = tiles_mg * pw;
+  const int full = tiles_n / pw;
+  int p = u / per_panel, r, w;
+  if (p < full) {
+    r = u - p * per_panel;
+    w = pw;
+  } else {
+    p = full;
+    r = u - full * per_panel;
+    w = tiles_n - full * pw;
+  }
+  mg = r / w;
+  nt = p * pw + r % w;
+}
+constexpr int PANEL_SHIFT = 16;   // flags >> PANEL_SHIFT = panel width in n-tiles (0: no panels)
+
 enum { EPI_VEC_OUT = 1, EPI_VEC_RES = 2, EPI_VEC_BIAS = 4,
-       DBG_NO_TMA = 16, DBG_NO_MMA = 32, DBG_NO_EPI = 64, DBG_NO_STORE = 128 };   // TCAVP_GEMM_DEBUG: ablation switches for profiling (results are garbage)
+       DBG_NO_TMA = 16, DBG_NO_MMA = 32, DBG_NO_EPI = 64, DBG_NO_STORE = 128,
+       L2_W_LAST = 256, L2_A_FIRST = 512 };      // L2 eviction priority of the TMA loads of a panelled problem (TCAVP_GEMM_L2HINT)   // TCAVP_GEMM_DEBUG: ablation switches for profiling (results are garbage)
 
 // Epilogue of 32 accumulator columns [nacc0, nacc0+32) of row m for one thread.  The interior-tile path (full chunk,
 // 16-byte aligned rows) is branch-light and fully vectorised; ragged edges take the scalar path.
@@ -358,6 +385,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int num_units = ((tiles_m + CM - 1) / CM) * tiles_n;
   const int unit0 = blockIdx.x / CM, unit_stride = gridDim.x / CM;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  const int pw = (flags >> PANEL_SHIFT) > 0 ? (flags >> PANEL_SHIFT) : tiles_n;   // n-tiles per L2-resident panel of W
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
@@ -388,8 +416,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int unit = unit0; unit < num_units; unit += unit_stride) {
-        const int m0 = ((unit / tiles_n) * CM + (int)cta_rank) * BLOCK_M;
-        const int n0 = (unit % tiles_n) * BLOCK_N;
+        int mg, nt;
+        unit_to_tile(unit, num_units / tiles_n, tiles_n, pw, mg, nt);
+        const int m0 = (mg * CM + (int)cta_rank) * BLOCK_M;
+        const int n0 = nt * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           mbar_expect_tx(full_bar + 8 * stage, C::STAGE_BYTES);
@@ -443,8 +473,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     int it = 0;
     for (int unit = unit0; unit < num_units; unit += unit_stride, ++it) {
       const int acc = it & 1;
-      const int m0 = ((unit / tiles_n) * CM + (int)cta_rank) * BLOCK_M;
-      const int n0 = (unit % tiles_n) * BLOCK_N;
+      int mg, nt;
+      unit_to_tile(unit, num_units / tiles_n, tiles_n, pw, mg, nt);
+      const int m0 = (mg * CM + (int)cta_rank) * BLOCK_M;
+      const int n0 = nt * BLOCK_N;
       mbar_wait(tmem_full_bar + 8 * acc, (it >> 1) & 1);
       tc_fence_after();
       const int m = m0 + quarter * 32 + lane;
@@ -497,6 +529,21 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
       : "memory");
+}
+// ... with an L2 eviction-priority policy: the W panel of a problem larger than L2 is loaded evict_last so that the A rows and the
+// output lines streaming through L2 do not push it out between waves of tiles (without it a 58 MB panel was re-read every wave).
+__device__ __forceinline__ void tma_load_2d_pair_hint(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy(int kind) {   // 0 normal, 1 evict_last, 2 evict_first
+  uint64_t p;
+  if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
 }
 __device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -552,6 +599,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const int num_units = tiles_m * tiles_n;
   const int unit0 = blockIdx.x >> 1, unit_stride = gridDim.x >> 1;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  const int pw = (flags >> PANEL_SHIFT) > 0 ? (flags >> PANEL_SHIFT) : tiles_n;   // n-tiles per L2-resident panel of W
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
@@ -580,19 +628,28 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
       const uint32_t leader_full = mapa_shared(full_bar, 0);
+      const bool hinted = (flags & (L2_W_LAST | L2_A_FIRST)) != 0;
+      const uint64_t pol_w = l2_policy((flags & L2_W_LAST) ? 1 : 0), pol_a = l2_policy((flags & L2_A_FIRST) ? 2 : 0);
       int stage = 0;
       uint32_t phase = 0;
       for (int unit = unit0; unit < num_units; unit += unit_stride) {
-        const int m0 = (unit / tiles_n) * PAIR_M + (int)cta_rank * BLOCK_M;
-        const int n0 = (unit % tiles_n) * BLOCK_N + (int)cta_rank * C::HALF_N;
+        int mg, nt;
+        unit_to_tile(unit, tiles_m, tiles_n, pw, mg, nt);
+        const int m0 = mg * PAIR_M + (int)cta_rank * BLOCK_M;
+        const int n0 = nt * BLOCK_N + (int)cta_rank * C::HALF_N;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           if (flags & DBG_NO_TMA) {
             if (leader) mbar_arrive(full_bar + 8 * stage);
           } else {
             if (leader) mbar_expect_tx(full_bar + 8 * stage, 2 * C::STAGE_BYTES);
-            tma_load_2d_pair(smem_a + stage * A_STAGE_BYTES, &tma_a, leader_full + 8 * stage, kb * BLOCK_K, m0);
-            tma_load_2d_pair(smem_b + stage * C::B_STAGE_BYTES, &tma_b, leader_full + 8 * stage, kb * BLOCK_K, n0);
+            if (hinted) {
+              tma_load_2d_pair_hint(smem_a + stage * A_STAGE_BYTES, &tma_a, leader_full + 8 * stage, kb * BLOCK_K, m0, pol_a);
+              tma_load_2d_pair_hint(smem_b + stage * C::B_STAGE_BYTES, &tma_b, leader_full + 8 * stage, kb * BLOCK_K, n0, pol_w);
+            } else {
+              tma_load_2d_pair(smem_a + stage * A_STAGE_BYTES, &tma_a, leader_full + 8 * stage, kb * BLOCK_K, m0);
+              tma_load_2d_pair(smem_b + stage * C::B_STAGE_BYTES, &tma_b, leader_full + 8 * stage, kb * BLOCK_K, n0);
+            }
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -644,8 +701,10 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     int it = 0;
     for (int unit = unit0; unit < num_units; unit += unit_stride, ++it) {
       const int acc = it & 1;
-      const int m0 = (unit / tiles_n) * PAIR_M + (int)cta_rank * BLOCK_M;
-      const int n0 = (unit % tiles_n) * BLOCK_N;
+      int mg, nt;
+      unit_to_tile(unit, tiles_m, tiles_n, pw, mg, nt);
+      const int m0 = mg * PAIR_M + (int)cta_rank * BLOCK_M;
+      const int n0 = nt * BLOCK_N;
       mbar_wait(tmem_full_bar + 8 * acc, (it >> 1) & 1);
       tc_fence_after();
       const int m = m0 + quarter * 32 + lane;
@@ -729,6 +788,7 @@ gemm_tc_quad_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const int num_units = tiles_m * tiles_n;
   const int unit0 = blockIdx.x >> 2, unit_stride = gridDim.x >> 2;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  const int pw = (flags >> PANEL_SHIFT) > 0 ? (flags >> PANEL_SHIFT) : tiles_n;   // n-tiles per L2-resident panel of W
   const uint16_t pair_mask = (uint16_t)(3u << (2 * pr));        // both CTAs of my pair
   const uint16_t col_mask = (uint16_t)((1u << r) | (4u << r));   // the CTAs of both pairs that hold W half r
 
@@ -762,8 +822,10 @@ gemm_tc_quad_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       for (int unit = unit0; unit < num_units; unit += unit_stride) {
-        const int m0 = (unit / tiles_n) * QUAD_M + (int)pr * PAIR_M + (int)r * BLOCK_M;
-        const int n0 = (unit % tiles_n) * BLOCK_N + (int)r * C::HALF_N + (int)pr * QUARTER_N;   // my quarter of the W tile
+        int mg, nt;
+        unit_to_tile(unit, tiles_m, tiles_n, pw, mg, nt);
+        const int m0 = mg * QUAD_M + (int)pr * PAIR_M + (int)r * BLOCK_M;
+        const int n0 = nt * BLOCK_N + (int)r * C::HALF_N + (int)pr * QUARTER_N;   // my quarter of the W tile
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           if (leader) mbar_expect_tx(full_bar + 8 * stage, 2 * C::STAGE_BYTES);
@@ -811,8 +873,10 @@ gemm_tc_quad_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     int it = 0;
     for (int unit = unit0; unit < num_units; unit += unit_stride, ++it) {
       const int acc = it & 1;
-      const int m0 = (unit / tiles_n) * QUAD_M + (int)pr * PAIR_M + (int)r * BLOCK_M;
-      const int n0 = (unit % tiles_n) * BLOCK_N;
+      int mg, nt;
+      unit_to_tile(unit, tiles_m, tiles_n, pw, mg, nt);
+      const int m0 = mg * QUAD_M + (int)pr * PAIR_M + (int)r * BLOCK_M;
+      const int n0 = nt * BLOCK_N;
       mbar_wait(tmem_full_bar + 8 * acc, (it >> 1) & 1);
       tc_fence_after();
       const int m = m0 + quarter * 32 + lane;
@@ -890,6 +954,7 @@ gemm_tc_wide_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const int num_units = tiles_m * tiles_n;
   const int unit0 = blockIdx.x >> 1, unit_stride = gridDim.x >> 1;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  const int pw = (flags >> PANEL_SHIFT) > 0 ? (flags >> PANEL_SHIFT) : tiles_n;   // n-tiles per L2-resident panel of W
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
@@ -916,16 +981,25 @@ gemm_tc_wide_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
       const uint32_t leader_full = mapa_shared(full_bar, 0);
+      const bool hinted = (flags & (L2_W_LAST | L2_A_FIRST)) != 0;
+      const uint64_t pol_w = l2_policy((flags & L2_W_LAST) ? 1 : 0), pol_a = l2_policy((flags & L2_A_FIRST) ? 2 : 0);
       int stage = 0;
       uint32_t phase = 0;
       for (int unit = unit0; unit < num_units; unit += unit_stride) {
-        const int m0 = (unit / tiles_n) * PAIR_M + (int)cta_rank * CTA_M;
-        const int n0 = (unit % tiles_n) * C::BLOCK_N + (int)cta_rank * C::HALF_N;
+        int mg, nt;
+        unit_to_tile(unit, tiles_m, tiles_n, pw, mg, nt);
+        const int m0 = mg * PAIR_M + (int)cta_rank * CTA_M;
+        const int n0 = nt * C::BLOCK_N + (int)cta_rank * C::HALF_N;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           if (leader) mbar_expect_tx(full_bar + 8 * stage, 2 * C::STAGE_BYTES);
-          tma_load_2d_pair(smem_a + stage * C::A_BYTES, &tma_a, leader_full + 8 * stage, kb * BLOCK_K, m0);              // 256 rows
-          tma_load_2d_pair(smem_b + stage * C::B_BYTES, &tma_b, leader_full + 8 * stage, kb * BLOCK_K, n0);              // 128 rows
+          if (hinted) {
+            tma_load_2d_pair_hint(smem_a + stage * C::A_BYTES, &tma_a, leader_full + 8 * stage, kb * BLOCK_K, m0, pol_a);
+            tma_load_2d_pair_hint(smem_b + stage * C::B_BYTES, &tma_b, leader_full + 8 * stage, kb * BLOCK_K, n0, pol_w);
+          } else {
+            tma_load_2d_pair(smem_a + stage * C::A_BYTES, &tma_a, leader_full + 8 * stage, kb * BLOCK_K, m0);              // 256 rows
+            tma_load_2d_pair(smem_b + stage * C::B_BYTES, &tma_b, leader_full + 8 * stage, kb * BLOCK_K, n0);              // 128 rows
+          }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -969,8 +1043,10 @@ gemm_tc_wide_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     const uint32_t leader_tmem_empty = mapa_shared(tmem_empty_bar, 0);
     int it = 0;
     for (int unit = unit0; unit < num_units; unit += unit_stride, ++it) {
-      const int m_cta = (unit / tiles_n) * PAIR_M + (int)cta_rank * CTA_M;
-      const int n0 = (unit % tiles_n) * C::BLOCK_N;
+      int mg, nt;
+      unit_to_tile(unit, tiles_m, tiles_n, pw, mg, nt);
+      const int m_cta = mg * PAIR_M + (int)cta_rank * CTA_M;
+      const int n0 = nt * C::BLOCK_N;
       mbar_wait(tmem_full_bar, it & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -1060,6 +1136,37 @@ static int cluster_pref() {
   return v;
 }
 
+// Panel width (n-tiles) of the persistent tile order + L2 hints, packed into the kernel's flags (see unit_to_tile).
+// A panel of W is sized to stay in L2 (TCAVP_GEMM_PANEL_MB, default 40 of the 126 MB; loaded evict_last) while A streams past it.
+// Modelled DRAM reads: W + A x panels with panels, A + (W rows one wave of resident units touches) x waves without (ncu: without
+// evict_last even a 33 MB W is re-streamed by most waves) - the smaller one decides.  TCAVP_GEMM_L2HINT: 0 none, 1 W evict_last
+// (default), 2 also A evict_first.
+static int panel_flags(long long M, long long N, long long K, int unit_m, int tile_n, int resident_units, bool can_hint) {
+  static long long budget = -1;
+  static int hint = -1;
+  if (budget < 0) {
+    const char* e = getenv("TCAVP_GEMM_PANEL_MB");
+    budget = (e ? atoll(e) : 40) << 20;
+    e = getenv("TCAVP_GEMM_L2HINT");
+    hint = e ? atoi(e) : 1;
+  }
+  const long long w_bytes = N * K * 2, a_bytes = M * K * 2;
+  const int hint_flags = !can_hint || hint <= 0 ? 0 : (hint >= 2 ? (L2_W_LAST | L2_A_FIRST) : L2_W_LAST);
+  if (budget <= 0) return 0;
+  if (w_bytes <= budget) return w_bytes * 4 > budget ? hint_flags : 0;     // whole W is one resident panel (tiny W: nothing to protect)
+  const long long tiles_n = (N + tile_n - 1) / tile_n, tiles_m = (M + unit_m - 1) / unit_m;
+  long long pw = budget / ((long long)tile_n * K * 2);
+  if (pw < 1) pw = 1;
+  const long long panels = (tiles_n + pw - 1) / pw;
+  pw = (tiles_n + panels - 1) / panels;          // equal-width panels
+  const long long waves = (tiles_m * tiles_n + resident_units - 1) / resident_units;
+  const long long rows_per_wave = resident_units >= tiles_n ? tiles_n : resident_units;   // n-tiles of W one wave touches
+  const long long plain = a_bytes + waves * rows_per_wave * tile_n * K * 2;
+  const long long panelled = w_bytes + a_bytes * panels;
+  if (panelled >= plain || pw >= tiles_n || pw > 0x7fff) return 0;
+  return ((int)pw << PANEL_SHIFT) | hint_flags;
+}
+
 template <int BLOCK_N, int CM>
 static int launch_tc(const tcavp_gemm_args& a, const EpilogueParams& ep, cudaStream_t stream) {
   using C = Cfg<BLOCK_N>;
@@ -1090,6 +1197,7 @@ static int launch_tc(const tcavp_gemm_args& a, const EpilogueParams& ep, cudaStr
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  flags |= panel_flags(a.M, a.N, a.K, BLOCK_M * CM, BLOCK_N, max_clusters, false);
   TCAVP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, CM>, ma, mb, ep, a.M, a.N, a.K, flags));
   return check_launch("gemm_tc_kernel");
 }
@@ -1125,6 +1233,7 @@ static int launch_tc_pair(const tcavp_gemm_args& a, const EpilogueParams& ep, cu
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  flags |= panel_flags(a.M, a.N, a.K, 2 * BLOCK_M, BLOCK_N, max_pairs, true);
   TCAVP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<BLOCK_N>, ma, mb, ep, a.M, a.N, a.K, flags));
   return check_launch("gemm_tc_pair_kernel");
 }
@@ -1166,6 +1275,7 @@ static int launch_tc_quad(const tcavp_gemm_args& a, const EpilogueParams& ep, cu
   if (((size_t)ep.ldo * osz) % 32 == 0 && (reinterpret_cast<uintptr_t>(ep.out) % 32) == 0) flags |= EPI_VEC_OUT;
   if (ep.residual && ((size_t)ep.ldr * rsz) % 32 == 0 && (reinterpret_cast<uintptr_t>(ep.residual) % 32) == 0) flags |= EPI_VEC_RES;
   if (ep.bias && (reinterpret_cast<uintptr_t>(ep.bias) % 16) == 0) flags |= EPI_VEC_BIAS;
+  flags |= panel_flags(a.M, a.N, a.K, 4 * BLOCK_M, BLOCK_N, max_quads, false);
   TCAVP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_quad_kernel<BLOCK_N>, ma, mb, ep, a.M, a.N, a.K, flags));
   return check_launch("gemm_tc_quad_kernel");
 }
@@ -1199,6 +1309,7 @@ static int launch_tc_wide(const tcavp_gemm_args& a, const EpilogueParams& ep, cu
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  flags |= panel_flags(a.M, a.N, a.K, 4 * BLOCK_M, C::BLOCK_N, max_pairs, true);
   TCAVP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_wide_kernel, ma, mb, ep, a.M, a.N, a.K, flags));
   return check_launch("gemm_tc_wide_kernel");
 }
