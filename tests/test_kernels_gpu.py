@@ -454,6 +454,19 @@ def test_gemm_wide_kernel_sampled_rows(ops):
     torch.testing.assert_close(sw[rows].float(), torch.nn.functional.silu(y[:, 0::2]) * y[:, 1::2], rtol=3e-2, atol=2e-2)
 
 
+@pytest.mark.parametrize("pw", [1, 3, 5])
+def test_gemm_panel_tile_order(ops, pw):
+    """Panel-major tile order of the persistent tcgen05 kernels (W larger than L2): forced panel widths, every kernel variant, ragged
+    edges, whole output compared.  The width is read once per process, so the check runs as a script (tools/panel_order_check.py)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, TCAVP_GEMM_PANEL_FORCE=str(pw))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "panel_order_check.py")], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "panel_order_check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize("B,K,T", [(7, 10, 25), (300, 3, 50), (1, 1, 1), (5, 20, 40)])
 def test_best_of_k_reduction(ops, B, K, T):
     """tcavp_best_of_k against the restated candidate reduction of the reference's best-of-K evaluation (scripts/test.py:1336-1368)."""

@@ -1143,13 +1143,16 @@ static int cluster_pref() {
 // (default), 2 also A evict_first.
 static int panel_flags(long long M, long long N, long long K, int unit_m, int tile_n, int resident_units, bool can_hint) {
   static long long budget = -1;
-  static int hint = -1;
+  static int hint = -1, force = 0;
   if (budget < 0) {
-    const char* e = getenv("TCAVP_GEMM_PANEL_MB");
-    budget = (e ? atoll(e) : 40) << 20;
-    e = getenv("TCAVP_GEMM_L2HINT");
+    const char* e = getenv("TCAVP_GEMM_L2HINT");
     hint = e ? atoi(e) : 1;
+    e = getenv("TCAVP_GEMM_PANEL_FORCE");      // test hook: this many n-tiles per panel whatever the problem size
+    force = e ? atoi(e) : 0;
+    e = getenv("TCAVP_GEMM_PANEL_MB");
+    budget = (e ? atoll(e) : 40) << 20;
   }
+  if (force > 0 && force <= 0x7fff) return (force << PANEL_SHIFT) | (can_hint && hint > 0 ? L2_W_LAST : 0);
   const long long w_bytes = N * K * 2, a_bytes = M * K * 2;
   const int hint_flags = !can_hint || hint <= 0 ? 0 : (hint >= 2 ? (L2_W_LAST | L2_A_FIRST) : L2_W_LAST);
   if (budget <= 0) return 0;
