@@ -155,6 +155,13 @@ __device__ __forceinline__ void stg256(void* p, const uint32_t (&v)[8]) {
                "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
+// ... streaming form for outputs far larger than L2 (panelled 7B-class GEMMs): the written lines are the first to leave L2, so they do not
+// push out the W panel the next wave of tiles needs.
+__device__ __forceinline__ void stg256_stream(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.L1::no_allocate.L2::evict_first.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 __device__ __forceinline__ void ldg256(const void* p, uint32_t (&v)[8]) {
   asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -188,8 +195,8 @@ __device__ __forceinline__ void unit_to_tile(int u, int tiles_mg, int tiles_n, i
 constexpr int PANEL_SHIFT = 16;   // flags >> PANEL_SHIFT = panel width in n-tiles (0: no panels)
 
 enum { EPI_VEC_OUT = 1, EPI_VEC_RES = 2, EPI_VEC_BIAS = 4,
-       DBG_NO_TMA = 16, DBG_NO_MMA = 32, DBG_NO_EPI = 64, DBG_NO_STORE = 128,
-       L2_W_LAST = 256, L2_A_FIRST = 512 };      // L2 eviction priority of the TMA loads of a panelled problem (TCAVP_GEMM_L2HINT)   // TCAVP_GEMM_DEBUG: ablation switches for profiling (results are garbage)
+       DBG_NO_TMA = 16, DBG_NO_MMA = 32, DBG_NO_EPI = 64, DBG_NO_STORE = 128,   // TCAVP_GEMM_DEBUG: ablation switches for profiling (results are garbage)
+       L2_W_LAST = 256, L2_A_FIRST = 512, L2_OUT_FIRST = 1024 };      // L2 eviction priorities of a panelled problem (TCAVP_GEMM_L2HINT)
 
 // Epilogue of 32 accumulator columns [nacc0, nacc0+32) of row m for one thread.  The interior-tile path (full chunk,
 // 16-byte aligned rows) is branch-light and fully vectorised; ragged edges take the scalar path.
@@ -333,7 +340,8 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueParams& p, int m, i
           uint32_t u[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) u[e] = pack_bf16(o[q * 16 + 2 * e], o[q * 16 + 2 * e + 1]);
-          stg256(op + q * 16, u);
+          if (flags & L2_OUT_FIRST) stg256_stream(op + q * 16, u);
+          else stg256(op + q * 16, u);
         }
       }
     } else {
@@ -1139,14 +1147,14 @@ static int cluster_pref() {
 // Panel width (n-tiles) of the persistent tile order + L2 hints, packed into the kernel's flags (see unit_to_tile).
 // A panel of W is sized to stay in L2 (TCAVP_GEMM_PANEL_MB, default 40 of the 126 MB; loaded evict_last) while A streams past it.
 // Modelled DRAM reads: W + A x panels with panels, A + (W rows one wave of resident units touches) x waves without (ncu: without
-// evict_last even a 33 MB W is re-streamed by most waves) - the smaller one decides.  TCAVP_GEMM_L2HINT: 0 none, 1 W evict_last
-// (default), 2 also A evict_first.
+// evict_last even a 33 MB W is re-streamed by most waves) - the smaller one decides.  TCAVP_GEMM_L2HINT: 0 none, 1 W evict_last,
+// 2 also A evict_first, 3 (default) W evict_last + streaming (evict_first) output stores.
 static int panel_flags(long long M, long long N, long long K, int unit_m, int tile_n, int resident_units, bool can_hint) {
   static long long budget = -1;
   static int hint = -1, force = 0;
   if (budget < 0) {
     const char* e = getenv("TCAVP_GEMM_L2HINT");
-    hint = e ? atoi(e) : 1;
+    hint = e ? atoi(e) : 3;
     e = getenv("TCAVP_GEMM_PANEL_FORCE");      // test hook: this many n-tiles per panel whatever the problem size
     force = e ? atoi(e) : 0;
     e = getenv("TCAVP_GEMM_PANEL_MB");
@@ -1154,7 +1162,9 @@ static int panel_flags(long long M, long long N, long long K, int unit_m, int ti
   }
   if (force > 0 && force <= 0x7fff) return (force << PANEL_SHIFT) | (can_hint && hint > 0 ? L2_W_LAST : 0);
   const long long w_bytes = N * K * 2, a_bytes = M * K * 2;
-  const int hint_flags = !can_hint || hint <= 0 ? 0 : (hint >= 2 ? (L2_W_LAST | L2_A_FIRST) : L2_W_LAST);
+  // streaming stores only for outputs the next kernel cannot find in L2 anyway (> 2 x L2 of bf16)
+  const int out_first = M * N * 2 > (256ll << 20) ? L2_OUT_FIRST : 0;
+  const int hint_flags = !can_hint || hint <= 0 ? 0 : (hint == 2 ? (L2_W_LAST | L2_A_FIRST) : hint >= 3 ? (L2_W_LAST | out_first) : L2_W_LAST);
   if (budget <= 0) return 0;
   if (w_bytes <= budget) return w_bytes * 4 > budget ? hint_flags : 0;     // whole W is one resident panel (tiny W: nothing to protect)
   const long long tiles_n = (N + tile_n - 1) / tile_n, tiles_m = (M + unit_m - 1) / unit_m;
