@@ -1144,6 +1144,16 @@ static int cluster_pref() {
   return v;
 }
 
+// Vector-path switches of the epilogue: 256-bit output / residual accesses need 32-byte aligned rows, the bias loads 16-byte alignment.
+static int epilogue_flags(const EpilogueParams& ep) {
+  const size_t osz = ep.out_dtype == TCAVP_BF16 ? 2 : 4, rsz = ep.res_dtype == TCAVP_BF16 ? 2 : 4;
+  int flags = 0;
+  if (((size_t)ep.ldo * osz) % 32 == 0 && (reinterpret_cast<uintptr_t>(ep.out) % 32) == 0) flags |= EPI_VEC_OUT;
+  if (ep.residual && ((size_t)ep.ldr * rsz) % 32 == 0 && (reinterpret_cast<uintptr_t>(ep.residual) % 32) == 0) flags |= EPI_VEC_RES;
+  if (ep.bias && (reinterpret_cast<uintptr_t>(ep.bias) % 16) == 0) flags |= EPI_VEC_BIAS;
+  return flags;
+}
+
 // Panel width (n-tiles) of the persistent tile order + L2 hints, packed into the kernel's flags (see unit_to_tile).
 // A panel of W is sized to stay in L2 (TCAVP_GEMM_PANEL_MB, default 40 of the 126 MB; loaded evict_last) while A streams past it.
 // Modelled DRAM reads: W + A x panels with panels, A + (W rows one wave of resident units touches) x waves without (ncu: without
@@ -1193,11 +1203,7 @@ static int launch_tc(const tcavp_gemm_args& a, const EpilogueParams& ep, cudaStr
   const int units = ((tiles_m + CM - 1) / CM) * tiles_n;
   const int max_clusters = sm_count() / CM;
   const int grid = (units < max_clusters ? units : max_clusters) * CM;
-  const size_t osz = ep.out_dtype == TCAVP_BF16 ? 2 : 4, rsz = ep.res_dtype == TCAVP_BF16 ? 2 : 4;
-  int flags = 0;
-  if (((size_t)ep.ldo * osz) % 32 == 0 && (reinterpret_cast<uintptr_t>(ep.out) % 32) == 0) flags |= EPI_VEC_OUT;
-  if (ep.residual && ((size_t)ep.ldr * rsz) % 32 == 0 && (reinterpret_cast<uintptr_t>(ep.residual) % 32) == 0) flags |= EPI_VEC_RES;
-  if (ep.bias && (reinterpret_cast<uintptr_t>(ep.bias) % 16) == 0) flags |= EPI_VEC_BIAS;
+  int flags = epilogue_flags(ep);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(NUM_THREADS);
@@ -1228,11 +1234,7 @@ static int launch_tc_pair(const tcavp_gemm_args& a, const EpilogueParams& ep, cu
   const int units = tiles_m * tiles_n;
   const int max_pairs = sm_count() / 2;
   const int grid = (units < max_pairs ? units : max_pairs) * 2;
-  const size_t osz = ep.out_dtype == TCAVP_BF16 ? 2 : 4, rsz = ep.res_dtype == TCAVP_BF16 ? 2 : 4;
-  int flags = 0;
-  if (((size_t)ep.ldo * osz) % 32 == 0 && (reinterpret_cast<uintptr_t>(ep.out) % 32) == 0) flags |= EPI_VEC_OUT;
-  if (ep.residual && ((size_t)ep.ldr * rsz) % 32 == 0 && (reinterpret_cast<uintptr_t>(ep.residual) % 32) == 0) flags |= EPI_VEC_RES;
-  if (ep.bias && (reinterpret_cast<uintptr_t>(ep.bias) % 16) == 0) flags |= EPI_VEC_BIAS;
+  int flags = epilogue_flags(ep);
   if (const char* e = getenv("TCAVP_GEMM_DEBUG")) flags |= atoi(e) & (DBG_NO_TMA | DBG_NO_MMA | DBG_NO_EPI | DBG_NO_STORE);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
@@ -1283,11 +1285,7 @@ static int launch_tc_quad(const tcavp_gemm_args& a, const EpilogueParams& ep, cu
   }
   const int grid = (units < max_quads ? units : max_quads) * 4;
   cfg.gridDim = dim3(grid);
-  const size_t osz = ep.out_dtype == TCAVP_BF16 ? 2 : 4, rsz = ep.res_dtype == TCAVP_BF16 ? 2 : 4;
-  int flags = 0;
-  if (((size_t)ep.ldo * osz) % 32 == 0 && (reinterpret_cast<uintptr_t>(ep.out) % 32) == 0) flags |= EPI_VEC_OUT;
-  if (ep.residual && ((size_t)ep.ldr * rsz) % 32 == 0 && (reinterpret_cast<uintptr_t>(ep.residual) % 32) == 0) flags |= EPI_VEC_RES;
-  if (ep.bias && (reinterpret_cast<uintptr_t>(ep.bias) % 16) == 0) flags |= EPI_VEC_BIAS;
+  int flags = epilogue_flags(ep);
   flags |= panel_flags(a.M, a.N, a.K, 4 * BLOCK_M, BLOCK_N, max_quads, false);
   TCAVP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_quad_kernel<BLOCK_N>, ma, mb, ep, a.M, a.N, a.K, flags));
   return check_launch("gemm_tc_quad_kernel");
@@ -1305,11 +1303,7 @@ static int launch_tc_wide(const tcavp_gemm_args& a, const EpilogueParams& ep, cu
   const int units = tiles_m * tiles_n;
   const int max_pairs = sm_count() / 2;
   const int grid = (units < max_pairs ? units : max_pairs) * 2;
-  const size_t osz = ep.out_dtype == TCAVP_BF16 ? 2 : 4, rsz = ep.res_dtype == TCAVP_BF16 ? 2 : 4;
-  int flags = 0;
-  if (((size_t)ep.ldo * osz) % 32 == 0 && (reinterpret_cast<uintptr_t>(ep.out) % 32) == 0) flags |= EPI_VEC_OUT;
-  if (ep.residual && ((size_t)ep.ldr * rsz) % 32 == 0 && (reinterpret_cast<uintptr_t>(ep.residual) % 32) == 0) flags |= EPI_VEC_RES;
-  if (ep.bias && (reinterpret_cast<uintptr_t>(ep.bias) % 16) == 0) flags |= EPI_VEC_BIAS;
+  int flags = epilogue_flags(ep);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(NUM_THREADS);
