@@ -46,6 +46,11 @@ long long tcavp_launch_count(void);
  * (device memory) — the true average SM clock while other kernels run next to it. */
 int tcavp_clock_probe(unsigned long long* out2, unsigned long long ns, tcavp_stream_t stream);
 
+/* Host-only test aid (no device work): the tile order of the persistent tcgen05 GEMM kernels.  For unit = 0 .. tiles_m*tiles_n-1 writes the
+ * row-block index to mg[unit] and the n-tile index to nt[unit]; `panel_w` n-tiles per L2-resident W panel (>= tiles_n: row-major order).
+ * Same function the kernels run (csrc/gemm.cu: unit_to_tile). */
+int tcavp_gemm_tile_order(int tiles_m, int tiles_n, int panel_w, int* mg, int* nt);
+
 /* ---- dense contraction with fused epilogue --------------------------------------------------
  * out[m', n] = act( sum_k A[m,k] * W[n,k] + bias[n] ) + residual[m', n]
  *

@@ -102,6 +102,29 @@ def test_c_abi_library_exports_every_declared_symbol(lib_built):
     assert declared == set(L.EXPORTS)
 
 
+def test_gemm_tile_order_is_a_panel_major_bijection(lib_built):
+    """csrc/gemm.cu: unit_to_tile through its host entry point (no device work): every (row block, n-tile) is visited exactly once, panels
+    of `pw` n-tiles are swept one after the other (all row blocks inside a panel before the next panel), n fastest inside a row block."""
+    import ctypes
+    import itertools
+    for tm, tn, pw in itertools.chain([(1, 1, 1), (72, 86, 18), (72, 86, 29), (7, 5, 2), (3, 16, 16), (3, 16, 100), (41, 17, 3), (5, 9, 4)],
+                                      ((tm, tn, pw) for tm in (1, 2, 6) for tn in (1, 2, 7, 12) for pw in (1, 2, 5, 12))):
+        n = tm * tn
+        mg, nt = (ctypes.c_int * n)(), (ctypes.c_int * n)()
+        assert lib_built.tcavp_gemm_tile_order(tm, tn, pw, mg, nt) == 0
+        tiles = list(zip(mg, nt))
+        assert sorted(tiles) == [(a, b) for a in range(tm) for b in range(tn)], (tm, tn, pw)
+        if pw >= tn:
+            assert tiles == [(a, b) for a in range(tm) for b in range(tn)]
+            continue
+        panels = [b // pw for _, b in tiles]
+        assert panels == sorted(panels), "panels are swept in order"
+        for p in set(panels):
+            inside = [t for t in tiles if t[1] // pw == p]
+            assert inside == sorted(inside), "row-major (n fastest) inside a panel"
+    assert lib_built.tcavp_gemm_tile_order(0, 4, 1, None, None) != 0
+
+
 def test_collate_matches_the_reference_collate_fn():
     """tcavp_b200.custom_collate_fn against the output of the UNMODIFIED reference custom_collate_fn (scripts/train.py:301-347) on
     the same samples (golden minted by oracle/make_collate_golden.py): same keys, values, dtypes; plus the packed extras."""

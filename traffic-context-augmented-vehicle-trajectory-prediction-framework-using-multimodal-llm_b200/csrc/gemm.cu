@@ -172,7 +172,7 @@ __device__ __forceinline__ void ldg256(const void* p, uint32_t (&v)[8]) {
 // L2 while every row block of A streams past them once, so W is read from DRAM once and A once per panel.  With pw >= tiles_n (any
 // problem whose whole W fits in L2, e.g. the 768-class shapes) this is the plain row-major order.  Without panels a 7B-class gate/up
 // GEMM (W = 180 MB > L2) re-read W for every 512-row block: 12.7 GB of DRAM reads per launch against 0.5 GB algorithmic.
-__device__ __forceinline__ void unit_to_tile(int u, int tiles_mg, int tiles_n, int pw, int& mg, int& nt) {
+__host__ __device__ __forceinline__ void unit_to_tile(int u, int tiles_mg, int tiles_n, int pw, int& mg, int& nt) {
   if (pw >= tiles_n) {
     mg = u / tiles_n;
     nt = u % tiles_n;
@@ -1484,6 +1484,12 @@ static void launch_simt(const tcavp_gemm_args& a, const EpilogueParams& ep, cuda
 }
 }  // namespace simt
 }  // namespace tcavp
+
+extern "C" int tcavp_gemm_tile_order(int tiles_m, int tiles_n, int panel_w, int* mg, int* nt) {
+  TCAVP_REQUIRE(tiles_m > 0 && tiles_n > 0 && panel_w > 0 && mg != nullptr && nt != nullptr, "tcavp_gemm_tile_order: bad arguments");
+  for (int u = 0; u < tiles_m * tiles_n; ++u) tcavp::tc::unit_to_tile(u, tiles_m, tiles_n, panel_w, mg[u], nt[u]);
+  return 0;
+}
 
 extern "C" int tcavp_gemm(const tcavp_gemm_args* a, tcavp_stream_t stream_) {
   using namespace tcavp;
