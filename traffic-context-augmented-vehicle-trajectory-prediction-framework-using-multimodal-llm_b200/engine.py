@@ -459,7 +459,8 @@ class Engine:
             if getattr(self, "_copy_stream", None) is None:
                 self._copy_stream = torch.cuda.Stream(device=dev)
             main = torch.cuda.current_stream()
-            self._copy_stream.wait_stream(main)
+            # no wait on `main`: the sources are host buffers and the destinations are fresh allocations of the copy stream, so the copy
+            # of call i+1 may run under the kernels of call i (a caller that enqueues the next batch before reading the last result)
             with torch.cuda.stream(self._copy_stream):
                 moved = {id(t): t.to(dev, non_blocking=True) for t in bulk}
                 copied = torch.cuda.Event()
