@@ -130,6 +130,30 @@ def test_collated_batch_runs_through_the_model(lib_built):
     torch.testing.assert_close(l2.cpu(), fix["out"]["loss"], rtol=1e-4, atol=0)
 
 
+def test_evaluate_loop_matches_the_reference_test_loop(lib_built):
+    """tcavp_b200.evaluate (pipelined, device-side running sums) over ragged collated batches of a golden scene set: mean ADE / FDE equal
+    the per-scene values of the unmodified reference's test loop (train.py:1302-1322), decoded trajectories arrive in order, pinned
+    host batches and device-resident batches give the same result."""
+    import tcavp_b200 as T
+    fix = load_golden("tiny_b6")
+    m = build_filled_model(fix, "fp32", "cuda")
+    i, g = fix["inputs"], fix["out"]
+    B = i["x"].shape[0]
+    samples = [dict(traj_emb=i["x"][b].t().contiguous(), target_traj=i["y"][b].t().contiguous(), vision_emb=i["vision"][b],
+                    lane_polygon=i["polygon"][b], lane_polygon_len=int(i["poly_len"][b]), norm_stat=tuple(i["norm_stat"][b]),
+                    context_str="c", answer_str="a", track_id=b, input_ids=i["input_ids"][b], attention_mask=i["attention_mask"][b],
+                    labels=i["input_ids"][b]) for b in range(B)]
+    host = [T.custom_collate_fn(samples[a:a + 4]) for a in range(0, B, 4)]        # 4 + 2 scenes
+    seen = []
+    res = T.evaluate(m, host, on_decoded=lambda b, d: seen.append(d.clone()))
+    assert res["n"] == B
+    assert abs(res["ade"] - float(g["ade"].double().mean())) <= 1e-4 * float(g["ade"].mean()) + 1e-3
+    assert abs(res["fde"] - float(g["fde"].double().mean())) <= 1e-4 * float(g["fde"].mean()) + 1e-3
+    torch.testing.assert_close(torch.cat(seen), g["decoded"], rtol=1e-4, atol=1e-4)
+    on_dev = T.evaluate(m, [p.to_device("cuda") for p in host])
+    assert abs(on_dev["sum_ade"] - res["sum_ade"]) <= 1e-5 * res["sum_ade"] and on_dev["n"] == B
+
+
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 def test_frozen_backbone_path_reuses_supplied_final_hidden(lib_built, dtype):
     """cfg5 / ablation_study_without_lora.py path: with the backbone output supplied, only the encoders + fusion + head run, and the

@@ -8,3 +8,4 @@ from . import ops  # noqa: F401,E402
 from . import distributed  # noqa: F401,E402
 from .finetune import FineTuner  # noqa: F401,E402
 from .collate import custom_collate_fn, ScenePack  # noqa: F401,E402
+from .evaluate import evaluate  # noqa: F401,E402
