@@ -34,7 +34,12 @@ FIXTURES = {
     # grouped-query attention (Llama-3.2-1B geometry: 32 query heads on 8 KV heads, rope_theta 5e5), two layers, ragged text
     "gqa_l2_b32": ("cfg1", {"lora_r": 16, "base_model_name": dict(vocab_size=4096, hidden_size=2048, intermediate_size=8192, num_hidden_layers=2,
                                                                  num_attention_heads=32, num_key_value_heads=8, head_dim=64, rms_norm_eps=1e-5,
-                                                                 rope_theta=500000.0)}, 32, 96, 21, 23, None, "scripts/train.py"),
+                                                                 rope_theta=500000.0)}, 32, 96, 23, 23, None, "scripts/train.py"),   # weight seed picked so FDE (645 px) is not degenerate against ADE (411 px)
+    # the reference's own hard-coded backbone (scripts/train.py:1347 "meta-llama/Llama-3.2-1B"): GQA 32/8, rope_theta 5e5 with the
+    # llama3 frequency scaling (through the real HF LlamaRotaryEmbedding), TIED input / output embeddings, LoRA r 8 (the reference's
+    # default) — cut to two layers and an 8192-entry vocabulary so the fixture stays small and fast
+    "llama32_1b_l2_b8": ("cfg1", {"base_model_name": dict(T.LLAMA_PRESETS["llama-3.2-1b"], num_hidden_layers=2, vocab_size=8192)},
+                         8, 128, 31, 37, None, "scripts/train.py"),
 }
 
 
@@ -105,11 +110,14 @@ def make(name):
     print(f"{name}: {os.path.getsize(path) / 1e6:.2f} MB  loss={float(loss):.4f} ade={float(ade.mean()):.4f} fde={float(fde.mean()):.4f}")
 
 
-# name -> (model preset, B, l_text, polygon lengths)
+# name -> (model preset, B, l_text, polygon lengths[, ctor overrides])
 GRAD_FIXTURES = {
     "tiny_b5_grads": ("tiny", 5, 24, [64, 1, 33, 14, 22]),
     # the real 768-class geometry (12 layers, 12 heads of 64, L = 144, LoRA r 8): gradients are stored compressed (restated.compress_grad)
     "cfg1_b3_grads": ("cfg1", 3, 128, [33, 14, 22]),
+    # 7B-class geometry (H 4096, 32 heads of 128, I 11008, LoRA r 16), two decoder layers: the backward through W^T at K = 11008 / 22016
+    # (the wide GEMM) and the 67 M-parameter cross-attention of the fusion block
+    "cfg3l2_b4_grads": ("cfg3", 4, 128, [33, 14, 22, 32], {"base_model_name": FIXTURES["cfg3l2_b16"][1]["base_model_name"]}),
 }
 
 
@@ -117,8 +125,9 @@ def make_grads(name="tiny_b5_grads"):
     """Gradients of the UNMODIFIED reference model (eval mode = every dropout off, autograd on):
     the pin of the fine-tune step (reference scripts/im_kim_train_GRN.py:1029-1039)."""
     from oracle import restated
-    preset, B, l_text, poly_len = GRAD_FIXTURES[name]
+    preset, B, l_text, poly_len, *over = GRAD_FIXTURES[name]
     mc = dict(T.MODEL_PRESETS[preset])
+    mc.update(over[0] if over else {})
     lc = T.resolve_llama(mc["base_model_name"])
     mod = ref_loader.load_reference("scripts/train.py", lc)
     model = ref_loader.build_reference_model(mod, mc, lc)

@@ -43,14 +43,19 @@ def hf_llama_config(llama_cfg: dict):
               num_key_value_heads=c.get("num_key_value_heads", c["num_attention_heads"]),
               head_dim=c.get("head_dim", c["hidden_size"] // c["num_attention_heads"]),
               rms_norm_eps=c.get("rms_norm_eps", 1e-6), max_position_embeddings=c.get("max_position_embeddings", 2048),
-              tie_word_embeddings=False, attention_bias=False, mlp_bias=False)
-    cfg = LlamaConfig(**kw)
+              tie_word_embeddings=bool(c.get("tie_word_embeddings", False)), attention_bias=False, mlp_bias=False)
     theta = float(c.get("rope_theta", 10000.0))
+    rs = c.get("rope_scaling")
+    if rs:       # e.g. Llama-3.2-1B: {"rope_type": "llama3", factor, low_freq_factor, high_freq_factor, original_max_position_embeddings}
+        kw["rope_parameters"] = dict(rs, rope_theta=theta)
+    cfg = LlamaConfig(**kw)
     # transformers 5.x keeps theta inside rope_parameters; older versions as an attribute
     if getattr(cfg, "rope_parameters", None) is not None:
         cfg.rope_parameters["rope_theta"] = theta
     else:
         cfg.rope_theta = theta
+        if rs:
+            cfg.rope_scaling = dict(rs)
     return cfg
 
 

@@ -149,9 +149,28 @@ def _lora_linear(sd, p, x, scaling):
     return y
 
 
-def rope_cos_sin(L, dh, theta):
-    """HF:73-136 LlamaRotaryEmbedding, default rope type, positions 0..L-1 (inputs_embeds path: HF:392-397)."""
+def llama3_scale_inv_freq(inv, rs):
+    """transformers modeling_rope_utils._compute_llama3_parameters (rope_type "llama3", Llama-3.1 / 3.2), restated per frequency:
+    long wavelengths (> ctx / low_freq_factor) are slowed by `factor`, short ones (< ctx / high_freq_factor) are untouched, the band
+    in between blends the two.  Pinned by the llama32_1b_l2_b8 golden (minted through the real HF LlamaRotaryEmbedding)."""
+    ctx, f, lo, hi = rs["original_max_position_embeddings"], rs["factor"], rs["low_freq_factor"], rs["high_freq_factor"]
+    out = inv.clone()
+    for j in range(inv.numel()):
+        w = inv[j:j + 1]                                     # keep fp32 tensor arithmetic (same rounding as HF's vectorised form)
+        wavelen = 2 * math.pi / w
+        if bool(wavelen > ctx / lo):
+            out[j] = (w / f)[0]
+        elif not bool(wavelen < ctx / hi):
+            s = (ctx / wavelen - lo) / (hi - lo)
+            out[j] = ((1 - s) * w / f + s * w)[0]
+    return out
+
+
+def rope_cos_sin(L, dh, theta, rope_scaling=None):
+    """HF:73-136 LlamaRotaryEmbedding, default / llama3 rope type, positions 0..L-1 (inputs_embeds path: HF:392-397)."""
     inv = 1.0 / (theta ** (torch.arange(0, dh, 2, dtype=torch.int64).float() / dh))
+    if rope_scaling and rope_scaling.get("rope_type", "default") == "llama3":
+        inv = llama3_scale_inv_freq(inv, rope_scaling)
     fr = torch.arange(L, dtype=torch.float32)[:, None] * inv[None, :]
     emb = torch.cat([fr, fr], dim=-1)
     return emb.cos(), emb.sin()
@@ -170,7 +189,7 @@ def llama_stack(sd, llama_cfg, embeds, attn_mask, lora_scaling, p=None):
     nkv = llama_cfg.get("num_key_value_heads", nh)
     dh = llama_cfg.get("head_dim", H // nh)
     eps = llama_cfg.get("rms_norm_eps", 1e-6)
-    cos, sin = rope_cos_sin(L, dh, float(llama_cfg.get("rope_theta", 10000.0)))
+    cos, sin = rope_cos_sin(L, dh, float(llama_cfg.get("rope_theta", 10000.0)), llama_cfg.get("rope_scaling"))
     causal = torch.tril(torch.ones(L, L, dtype=torch.bool))
     allowed = causal[None, :, :] & attn_mask.bool()[:, None, :]           # HF:399 create_causal_mask
     x = embeds
@@ -296,14 +315,19 @@ def ade_fde(decoded, y, norm_stat):
 
 @torch.no_grad()
 def forward(sd, cfg, llama_cfg, x, vision, polygon, poly_len, input_ids, attention_mask, y=None, norm_stat=None,
-            final_hidden=None):
+            final_hidden=None, with_lm_head=False):
     """cfg: reference ctor kwargs (seq_len, out_len, lane_polygon_nhead, q_nhead, ltsf_nhead, lora_r, lora_alpha).
-    Returns a dict with every intermediate the golden fixtures record."""
+    Returns a dict with every intermediate the golden fixtures record.  `with_lm_head`: also evaluate the vocabulary logits the
+    shipped reference always computes and throws away (HF:487-491 via train.py:445-453, 547-554) — timing only ("as shipped")."""
     sd = {k: v.float() if v.is_floating_point() else v for k, v in sd.items()}
     out = {}
     out["poly_emb"] = lane_polygon_encoder(sd, polygon, poly_len, cfg.get("lane_polygon_nhead", 4))
     if final_hidden is None:
         out["final_hidden"], out["image_tokens"] = mllm_forward(sd, cfg, llama_cfg, vision, input_ids, attention_mask)
+        if with_lm_head:
+            lp = find_llm_prefix(sd)
+            head = lp[: -len("model.")] + "lm_head.weight"
+            out["logits_absmax"] = linear(out["final_hidden"], sd[head]).abs().max()
     else:
         out["final_hidden"] = final_hidden
     enc = ltsf_encoder(sd, x)

@@ -29,10 +29,10 @@ def setup(lib_built):
     return m, cfg, lc, sd, s, d
 
 
-def _run(m, d, idx=None):
+def _run(m, d, idx=None, keep=False):
     sel = (lambda t: t) if idx is None else (lambda t: t[idx].contiguous())
     o = m.engine().forward(sel(d["x"]), sel(d["vision"]), sel(d["polygon"]), sel(d["lens"]), sel(d["input_ids"]), sel(d["attention_mask"]),
-                           y=sel(d["y"]), norm_stat=sel(d["ns"]))
+                           y=sel(d["y"]), norm_stat=sel(d["ns"]), keep_intermediates=keep)
     torch.cuda.synchronize()
     return o
 
@@ -48,13 +48,17 @@ def _close(a, b, what):
 
 def test_full_batch_oracle_spot_check(setup):
     m, cfg, lc, sd, s, d = setup
-    full = _run(m, d)
+    full = _run(m, d, keep=True)
     idx = [0, 1, 511, 1023]
     want = restated.forward({k: v.clone() for k, v in sd.items()}, cfg, lc, s["x"][idx], s["vision"][idx], s["polygon"][idx],
                             [s["poly_len"][i] for i in idx], s["input_ids"][idx], s["attention_mask"][idx], s["y"][idx],
                             [s["norm_stat"][i] for i in idx])
     got = full["decoded"][idx].float().cpu()
     torch.testing.assert_close(got, want["decoded"], rtol=2e-2, atol=2e-2)            # north-star bf16 tolerance on coordinates
+    # the backbone output itself (12 layers of the kernels that are 85 % of the step), same band as tests/test_model_gpu.py
+    fh = full["final_hidden"][idx].float().cpu()
+    rel = float((fh.double() - want["final_hidden"].double()).norm() / want["final_hidden"].double().norm())
+    assert rel < 1.0e-2, ("final_hidden relative L2 at full size", rel)
     ade = full["ade"][idx].cpu()
     assert float(((ade - want["ade"]).abs() / want["ade"]).max()) < 5e-3 * 4, (ade, want["ade"])   # per-scene ADE (mean ADE is within 0.5 %)
     assert abs(float(ade.mean()) - float(want["ade"].mean())) / float(want["ade"].mean()) < 5e-3

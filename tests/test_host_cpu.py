@@ -48,6 +48,82 @@ def test_checkpoint_key_translation():
     torch.testing.assert_close(m2.state_dict()[k], m.state_dict()[k.replace("llama_model.model", "llama_model.base_model.model.model").replace("q_proj.weight", "q_proj.base_layer.weight")])
 
 
+def test_mllm_level_load_and_direct_variant():
+    """reference scripts/train.py:1137-1138 restores a stage-1 checkpoint with `model.mllm.load_state_dict(sd, strict=True)`: the key
+    translation must also run there.  llm_variant="direct" writes the V2 key layout (im_kim_train_GRN.py:444-455) on save."""
+    cfg = dict(T.MODEL_PRESETS["tiny"])
+    m = T.MultiModalTrajectoryModel(**cfg)
+    sd = m.mllm.state_dict()
+    v2 = {k.replace("llama_wrapper.llama_model.", "llama_model.").replace(".base_layer.", "."): v.clone() + 2.0 for k, v in sd.items()}
+    assert any(k.startswith("llama_model.") for k in v2)
+    ref = {k: v.clone() for k, v in sd.items()}
+    m.mllm.load_state_dict(v2, strict=True)
+    for k, v in m.mllm.state_dict().items():
+        torch.testing.assert_close(v, ref[k] + 2.0, msg=k)
+    d = T.MultiModalTrajectoryModel(**cfg, llm_variant="direct")
+    keys = set(d.state_dict())
+    assert not any("llama_wrapper" in k for k in keys) and any(k.startswith("mllm.llama_model.base_model.model.") for k in keys)
+    assert {k.replace("mllm.llama_model.", "mllm.llama_wrapper.llama_model.") for k in keys} == set(m.state_dict())
+    d.load_state_dict(d.state_dict(), strict=True)            # its own layout round-trips
+    m.load_state_dict(d.state_dict(), strict=True)            # and loads into the train.py layout
+    with pytest.raises(ValueError):
+        T.MultiModalTrajectoryModel(**cfg, llm_variant="nope")
+    # a plain (no-peft) backbone checkpoint into a LoRA model: keys gain base_model.model. / .base_layer (adapters stay missing)
+    cfg2 = dict(cfg, use_lora=False)
+    plain = T.MultiModalTrajectoryModel(**cfg2).state_dict()
+    res = m.load_state_dict(plain, strict=False)
+    assert not res.unexpected_keys and all("lora_" in k for k in res.missing_keys)
+
+
+def test_reference_backbone_name_resolves_with_llama3_rope_and_tied_embeddings():
+    """The one name the reference hard-codes (scripts/train.py:1347) builds the real geometry: GQA 32/8, llama3 rope scaling, tied
+    lm_head / embed_tokens, vocabulary 128256 — constructed on the meta device (1.24 G parameters), with the reference's args dict."""
+    from tcavp_b200.config import rope_inv_freq
+    args = dict(seq_len=6, out_len=30, individual=True, feature_size=2, d_model=64, lane_polygon_d_model=64, lane_polygon_nhead=4,
+                lane_polygon_layers=2, max_polygon_points=64, use_post_mlp=True, post_mlp_hidden_dim=64,
+                base_model_name="meta-llama/Llama-3.2-1B", use_lora=True, lora_r=8, lora_alpha=32, lora_dropout=0.1, vision_dim=512,
+                q_hidden_size=768, q_nhead=8, q_enc_layers=4, q_dec_layers=4, q_num_query_tokens=16, ltsf_nhead=2, ltsf_dropout=0.1)
+    m = T.MultiModalTrajectoryModel(**args, llm_device="meta", llm_param_dtype=torch.bfloat16)
+    c = m.mllm.llama_wrapper.config
+    assert (c["hidden_size"], c["num_hidden_layers"], c["num_attention_heads"], c["num_key_value_heads"], c["vocab_size"]) == (2048, 16, 32, 8, 128256)
+    assert m.llama_hidden_size == 2048 and isinstance(m.mllm.q_proj, torch.nn.Linear)
+    lm = m.mllm.llama_wrapper.causal_lm()
+    assert lm.lm_head.weight is lm.model.embed_tokens.weight
+    sd = m.state_dict()
+    pre = "mllm.llama_wrapper.llama_model.base_model.model."
+    assert sd[pre + "lm_head.weight"].shape == sd[pre + "model.embed_tokens.weight"].shape == (128256, 2048)
+    assert pre + "model.layers.15.self_attn.v_proj.lora_B.default.weight" in sd
+    n_llm = sum(p.numel() for n, p in m.named_parameters() if "llama_model" in n and "lora_" not in n)
+    assert n_llm == 1235814400                                                # the published parameter count of Llama-3.2-1B
+    inv = rope_inv_freq(c)
+    plain = 1.0 / (500000.0 ** (torch.arange(0, 64, 2).float() / 64))
+    assert torch.equal(inv[:8], plain[:8])                                    # short wavelengths untouched
+    torch.testing.assert_close(inv[-1], plain[-1] / 32.0)                     # long wavelengths slowed by `factor`
+    assert (inv <= plain).all() and (inv >= plain / 32.0 - 1e-12).all()
+    # a tied-embedding checkpoint without lm_head.weight (HF safetensors layout) still loads strictly
+    small = T.MultiModalTrajectoryModel(**dict(T.MODEL_PRESETS["tiny"], base_model_name=dict(T.LLAMA_PRESETS["llama-tiny"], tie_word_embeddings=True)))
+    ck = {k: v.clone() for k, v in small.state_dict().items() if not k.endswith("lm_head.weight")}
+    small.load_state_dict(ck, strict=True)
+    with pytest.raises(KeyError):
+        T.resolve_llama("no-such/backbone")
+
+
+def test_collate_survives_dataloader_workers_and_rewrapping():
+    """custom_collate_fn inside DataLoader worker processes (no pinning there: CUDA must not initialise in a forked child) and
+    through the mapping re-wrap a pinning loader performs: arena + plan are ordinary entries, pack_to_device still works."""
+    g = torch.load(os.path.join(ROOT, "tests", "golden", "collate_b5.pt"), weights_only=False)
+    dl = torch.utils.data.DataLoader(g["samples"], batch_size=3, shuffle=False, num_workers=2, collate_fn=T.custom_collate_fn)
+    batches = list(dl)
+    assert [b["traj_emb"].shape[0] for b in batches] == [3, 2]
+    want = T.custom_collate_fn(g["samples"][:3], pin=False)
+    rewrapped = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in batches[0].items()}     # what pin_memory=True hands back
+    moved = T.pack_to_device(rewrapped, "cpu")
+    for k, v in want.items():
+        if torch.is_tensor(v) and not k.startswith("_"):
+            assert torch.equal(moved[k], v) and torch.equal(batches[0][k], v), k
+    assert moved["lane_polygon_len"] == want["lane_polygon_len"]
+
+
 def test_engine_packing_shapes():
     from tcavp_b200.engine import Engine
     m = T.MultiModalTrajectoryModel(**T.MODEL_PRESETS["tiny"])

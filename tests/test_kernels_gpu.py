@@ -479,3 +479,18 @@ def test_best_of_k_reduction(ops, B, K, T):
     for i in range(3):
         torch.testing.assert_close(per[:, i].cpu(), want[i], rtol=1e-4, atol=1e-3)
         torch.testing.assert_close(tot[i].cpu(), want[i].sum(), rtol=1e-4, atol=1e-2)
+
+
+def test_model_best_of_k_metrics_entry_point(lib_built):
+    """MultiModalTrajectoryModel.best_of_k_metrics (the public entry of the reference's best-of-K reduction, scripts/test.py:1336-1368)
+    with host tensors and a list-typed norm_stat, against the restated reduction."""
+    import tcavp_b200 as T
+    m = T.MultiModalTrajectoryModel(**T.MODEL_PRESETS["tiny"]).to(DEV)
+    B, K, To = 9, 6, 12
+    cand, y = torch.rand(B, K, 2, To, generator=torch.Generator().manual_seed(3)), torch.rand(B, 2, To, generator=torch.Generator().manual_seed(4))
+    ns = [(50.0 + i, 700.0 + 5 * i, 710.0 + i, 790.0 + 3 * i) for i in range(B)]
+    got = m.best_of_k_metrics(cand, y, ns)
+    want = R.best_of_k(cand, y, ns)
+    for key, w in zip(("min_ade", "min_fde", "min_rmse"), want):
+        torch.testing.assert_close(got[key].cpu(), w, rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(got["sums"].cpu(), torch.stack([w.sum() for w in want]), rtol=1e-4, atol=1e-2)

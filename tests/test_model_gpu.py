@@ -17,16 +17,31 @@ def _forward(fix, dtype, keep=True):
     return m, {k: (v.float().cpu() if torch.is_tensor(v) else v) for k, v in out.items()}
 
 
-@pytest.mark.parametrize("name", ["tiny_b6", "cfg1_b8", "cfg5_b32", "cfg3l2_b16", "gqa_l2_b32"])
+FIXTURES = ["tiny_b6", "cfg1_b8", "cfg5_b32", "cfg3l2_b16", "gqa_l2_b32", "llama32_1b_l2_b8"]
+
+
+def _expected_image_rows(m, g):
+    """fused[:, :Q] of the first scenes from the golden Q-Former output: q_proj (Identity when H == 768) + vision modality embedding
+    (reference scripts/train.py:520-522), evaluated in fp64 on the host."""
+    it = g["image_tokens"].double()
+    mllm = m.mllm
+    if isinstance(mllm.q_proj, torch.nn.Linear):
+        it = it @ mllm.q_proj.weight.detach().double().cpu().t() + mllm.q_proj.bias.detach().double().cpu()
+    return (it + mllm.vision_modality_embedding.detach().double().cpu()).float()
+
+
+@pytest.mark.parametrize("name", FIXTURES)
 def test_fp32_forward_matches_reference(name, lib_built):
     fix = load_golden(name)
-    _, o = _forward(fix, "fp32")
+    m, o = _forward(fix, "fp32")
     g = fix["out"]
     tol = dict(rtol=1e-4, atol=1e-4)
     # the lane-polygon encoder's first softmax sees logits ~1e6 (raw pixel inputs, train.py:364): two correct fp32
     # evaluation orders differ by ~1e-3 there, so its embedding gets a wider absolute tolerance
     torch.testing.assert_close(o["poly_emb"], g["poly_emb"], rtol=1e-3, atol=2e-3)
     torch.testing.assert_close(o["enc"], g["enc"], **tol)
+    want_img = _expected_image_rows(m, g)
+    torch.testing.assert_close(o["image_tokens_plus_mod"][:want_img.shape[0]], want_img, rtol=1e-4, atol=2e-4)
     n = g["final_hidden_head"].shape[0]
     torch.testing.assert_close(o["final_hidden"][:n], g["final_hidden_head"], rtol=1e-4, atol=2e-4)
     torch.testing.assert_close(o["final_hidden"].mean(-1), g["final_hidden_rowmean"], **tol)
@@ -40,19 +55,65 @@ def test_fp32_forward_matches_reference(name, lib_built):
     torch.testing.assert_close(o["fde"], g["fde"], rtol=1e-4, atol=1e-2)
 
 
-@pytest.mark.parametrize("name", ["tiny_b6", "cfg1_b8", "cfg5_b32", "cfg3l2_b16", "gqa_l2_b32"])
-def test_bf16_forward_matches_reference(name, lib_built):
-    fix = load_golden(name)
-    _, o = _forward(fix, "bf16")
-    g = fix["out"]
+# bf16 bands on the backbone itself (the decoded coordinates alone cannot see it: 5 % noise on final_hidden moves them by < 1e-2).
+# final_hidden is post-RMSNorm, O(1) per element: relative L2 of the stored head rows, and every row mean / mean |.| of the whole
+# batch.  Calibrated on B200 (tools/bf16_error_probe.py): the bf16 stack sits at 3-6e-3 relative L2; the injected-error test below
+# keeps the band honest.
+BF16_REL_L2 = 1.0e-2
+BF16_IMG_REL_L2 = 1.0e-2
+
+
+def _rel_l2(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm())
+
+
+def _check_bf16(m, o, g):
     torch.testing.assert_close(o["decoded"], g["decoded"], rtol=2e-2, atol=2e-2)
     ade, fde = float(o["ade"].mean()), float(o["fde"].mean())
     g_ade, g_fde = float(g["ade"].mean()), float(g["fde"].mean())
-    assert abs(ade - g_ade) / g_ade < 5e-3, (ade, g_ade)
-    # FDE within 0.5 % too — of the displacement scale of the fixture: with seeded random weights the GQA fixture's mean FDE (51 px) is
-    # a seventh of its mean ADE (342 px), so a bf16 coordinate error of 1.6e-3 of a 100-1500 px range is ~1 % of that FDE while being
-    # 0.1 % of the ADE; the other fixtures (FDE >= ADE / 3) meet 0.5 % of their own FDE
-    assert abs(fde - g_fde) / max(g_fde, g_ade / 3) < 5e-3, (fde, g_fde, g_ade)
+    assert abs(ade - g_ade) / g_ade < 5e-3, (ade, g_ade)               # north star: ADE / FDE within 0.5 %
+    assert abs(fde - g_fde) / g_fde < 5e-3, (fde, g_fde)
+    want_img = _expected_image_rows(m, g)
+    r_img = _rel_l2(o["image_tokens_plus_mod"][:want_img.shape[0]], want_img)
+    assert r_img < BF16_IMG_REL_L2, ("image tokens", r_img)
+    n = g["final_hidden_head"].shape[0]
+    r_fh = _rel_l2(o["final_hidden"][:n], g["final_hidden_head"])
+    assert r_fh < BF16_REL_L2, ("final_hidden relative L2", r_fh)
+    fh = o["final_hidden"]
+    absmean = g["final_hidden_absmean"]
+    # per-row statistics over the WHOLE batch (every scene, every position): mean within a bf16 band of the row's magnitude
+    assert float(((fh.mean(-1) - g["final_hidden_rowmean"]).abs() / absmean).max()) < 2e-2
+    assert float(((fh.abs().mean(-1) - absmean).abs() / absmean).max()) < 2e-2
+    assert float((fh[:n] - g["final_hidden_head"]).abs().max()) < 0.25 * float(g["final_hidden_head"].abs().max())
+    return dict(img=r_img, fh=r_fh)
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_bf16_forward_matches_reference(name, lib_built):
+    fix = load_golden(name)
+    m, o = _forward(fix, "bf16")
+    _check_bf16(m, o, fix["out"])
+
+
+@pytest.mark.parametrize("name", ["cfg1_b8", "gqa_l2_b32"])
+def test_bf16_check_catches_an_injected_backbone_error(name, lib_built):
+    """The bf16 bands must see the backbone: 2 % multiplicative noise on the weights of ONE decoder layer (which the decoded
+    coordinates alone absorb) has to fail the check."""
+    fix = load_golden(name)
+    m = build_filled_model(fix, "bf16", "cuda")
+    layer = m.mllm.llama_wrapper.causal_lm().model.layers[1]
+    g = torch.Generator(device="cuda").manual_seed(5)
+    with torch.no_grad():
+        for p in layer.parameters():
+            if p.dim() == 2:
+                p.mul_(1.0 + 0.02 * torch.randn(p.shape, generator=g, device="cuda"))
+    i = fix["inputs"]
+    o = m.engine().forward(i["x"], i["vision"], i["polygon"], i["poly_len"], i["input_ids"], i["attention_mask"], y=i["y"],
+                           norm_stat=i["norm_stat"], keep_intermediates=True)
+    torch.cuda.synchronize()
+    o = {k: (v.float().cpu() if torch.is_tensor(v) else v) for k, v in o.items()}
+    with pytest.raises(AssertionError):
+        _check_bf16(m, o, fix["out"])
 
 
 def test_public_forward_signature_and_outputs(lib_built):

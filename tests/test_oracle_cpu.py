@@ -19,7 +19,7 @@ def _run(fix):
                             i["input_ids"], i["attention_mask"], i["y"], i["norm_stat"])
 
 
-@pytest.mark.parametrize("name", ["tiny_b6", "cfg1_b8", "cfg5_b32", "cfg3l2_b16", "gqa_l2_b32"])
+@pytest.mark.parametrize("name", ["tiny_b6", "cfg1_b8", "cfg5_b32", "cfg3l2_b16", "gqa_l2_b32", "llama32_1b_l2_b8"])
 def test_restatement_matches_reference_golden(name):
     fix = load_golden(name)
     o, g = _run(fix), fix["out"]
@@ -66,7 +66,7 @@ def _check_against_compressed(got, want, rtol, atol, key):
     torch.testing.assert_close(g2.double().sum(0).float(), want["colsum"], rtol=rtol, atol=atol + 1e-4 * scale, msg=lambda m: f"{key} colsum: {m}")
 
 
-@pytest.mark.parametrize("name", ["tiny_b5_grads", "cfg1_b3_grads"])
+@pytest.mark.parametrize("name", ["tiny_b5_grads", "cfg1_b3_grads", "cfg3l2_b4_grads"])
 def test_restated_gradients_match_reference_autograd(name):
     """Pins the fine-tune oracle: autograd through oracle/restated.py == gradients of the unmodified reference model."""
     fix = load_golden(name)

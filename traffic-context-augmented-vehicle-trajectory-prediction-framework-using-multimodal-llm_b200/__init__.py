@@ -7,5 +7,5 @@ from .model import MultiModalTrajectoryModel  # noqa: F401,E402
 from . import ops  # noqa: F401,E402
 from . import distributed  # noqa: F401,E402
 from .finetune import FineTuner  # noqa: F401,E402
-from .collate import custom_collate_fn, ScenePack  # noqa: F401,E402
+from .collate import custom_collate_fn, pack_to_device, ScenePack  # noqa: F401,E402
 from .evaluate import evaluate  # noqa: F401,E402

@@ -25,22 +25,41 @@ def _arena(spec, pin):
         plan.append((key, shape, dtype, off, nbytes))
         off += (nbytes + 15) // 16 * 16
     buf = torch.empty(max(off, 16), dtype=torch.uint8)
-    if pin and torch.cuda.is_available():
+    # a DataLoader worker process must not touch CUDA (pin_memory() initialises it in the forked child): workers hand over pageable
+    # memory and the loader's own pin_memory thread (DataLoader(pin_memory=True)) pins the arena in the parent
+    if pin and torch.utils.data.get_worker_info() is None and torch.cuda.is_available():
         buf = buf.pin_memory()
     views = {key: buf[o:o + nb].view(dtype).view(*shape) for key, shape, dtype, o, nb in plan}
     return buf, views
 
 
 class ScenePack(dict):
-    """The collated batch (reference keys) plus its pinned arena; `to_device` moves the numeric part with a single async copy."""
+    """The collated batch (reference keys) plus its arena; `to_device` moves the numeric part with a single async copy.
+    The arena and its layout travel as ordinary entries (`_arena`, `_plan`), so they survive `DataLoader(pin_memory=True)`, which
+    rebuilds mappings entry by entry (and pins `_arena` like any other tensor)."""
+
+    @property
+    def arena(self):
+        return self.get("_arena")
+
+    @property
+    def plan(self):
+        return self.get("_plan")
 
     def to_device(self, device, non_blocking=True):
-        dbuf = self.arena.to(device, non_blocking=non_blocking)
-        out = ScenePack({k: v for k, v in self.items() if not torch.is_tensor(v)})
-        for key, shape, dtype, o, nb in self.plan:
-            out[key] = dbuf[o:o + nb].view(dtype).view(*shape)
-        out.arena, out.plan = dbuf, self.plan
-        return out
+        return pack_to_device(self, device, non_blocking)
+
+
+def pack_to_device(batch, device, non_blocking=True):
+    """`ScenePack.to_device` for any mapping that carries `_arena` / `_plan` (e.g. the plain dict a pinning DataLoader hands back).
+    After the loader's re-wrap the per-key tensors no longer alias the arena, but both hold the same bytes: the arena is what moves."""
+    arena, plan = batch["_arena"], batch["_plan"]
+    dbuf = arena.to(device, non_blocking=non_blocking)
+    out = ScenePack({k: v for k, v in batch.items() if not torch.is_tensor(v)})
+    for key, shape, dtype, o, nb in plan:
+        out[key] = dbuf[o:o + nb].view(dtype).view(*shape)
+    out["_arena"] = dbuf
+    return out
 
 
 def custom_collate_fn(batch, pin=True):
@@ -74,11 +93,11 @@ def custom_collate_fn(batch, pin=True):
     out["norm_stat"] = [b["norm_stat"] for b in batch]
     for k in _STRS:
         out[k] = [b[k] for b in batch]
-    out.arena = buf
+    out["_arena"] = buf
     off, plan = 0, []
     for key, shape, dtype in spec:
         nb = v[key].numel() * v[key].element_size()
         plan.append((key, shape, dtype, off, nb))
         off += (nb + 15) // 16 * 16
-    out.plan = plan
+    out["_plan"] = [tuple(p) for p in plan]
     return out

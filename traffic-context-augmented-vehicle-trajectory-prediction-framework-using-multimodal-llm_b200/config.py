@@ -16,15 +16,53 @@ LLAMA_PRESETS = {
     "llama-1b-gqa": dict(vocab_size=32000, hidden_size=2048, intermediate_size=8192, num_hidden_layers=16,
                          num_attention_heads=32, num_key_value_heads=8, head_dim=64, rms_norm_eps=1e-5,
                          rope_theta=500000.0),
+    # meta-llama/Llama-3.2-1B — the one backbone name the reference hard-codes (scripts/train.py:1347).  Values from the public
+    # model card / config.json: GQA 32/8, head_dim 64, rope_theta 5e5 with the "llama3" frequency scaling,
+    # tied input / output embeddings, vocabulary 128256.
+    "llama-3.2-1b": dict(vocab_size=128256, hidden_size=2048, intermediate_size=8192, num_hidden_layers=16,
+                         num_attention_heads=32, num_key_value_heads=8, head_dim=64, rms_norm_eps=1e-5,
+                         rope_theta=500000.0, max_position_embeddings=131072, tie_word_embeddings=True,
+                         rope_scaling=dict(rope_type="llama3", factor=32.0, low_freq_factor=1.0, high_freq_factor=4.0,
+                                           original_max_position_embeddings=8192)),
     # tiny shape for golden fixtures that carry their full state_dict
     "llama-tiny": dict(vocab_size=97, hidden_size=128, intermediate_size=256, num_hidden_layers=2,
                        num_attention_heads=4, num_key_value_heads=2, head_dim=32, rms_norm_eps=1e-6,
                        rope_theta=10000.0),
 }
 _ALIASES = {
-    "meta-llama/Llama-2-7b-hf": "llama-7b", "meta-llama/Llama-7B": "llama-7b",
+    "meta-llama/Llama-2-7b-hf": "llama-7b", "meta-llama/Llama-7B": "llama-7b", "meta-llama/Llama-2-7b": "llama-7b",
+    "huggyllama/llama-7b": "llama-7b",
+    "meta-llama/Llama-3.2-1B": "llama-3.2-1b", "meta-llama/Llama-3.2-1B-Instruct": "llama-3.2-1b",
     "gpt2-small-class": "llama-768",
 }
+
+
+def rope_inv_freq(cfg):
+    """inv_freq[dh/2] (fp32, host) exactly as transformers computes it: HF:86-88 for the default rope and
+    `modeling_rope_utils._compute_llama3_parameters` for rope_scaling = {"rope_type": "llama3", ...} (Llama-3.1 / 3.2:
+    wavelengths longer than original_ctx / low_freq_factor are divided by `factor`, those shorter than
+    original_ctx / high_freq_factor are kept, the band in between is interpolated)."""
+    import math
+
+    import torch
+    dh = cfg.get("head_dim") or cfg["hidden_size"] // cfg["num_attention_heads"]
+    theta = float(cfg.get("rope_theta", 10000.0))
+    inv = 1.0 / (theta ** (torch.arange(0, dh, 2, dtype=torch.int64).to(dtype=torch.float) / dh))
+    rs = cfg.get("rope_scaling") or None
+    if not rs or rs.get("rope_type", rs.get("type", "default")) == "default":
+        return inv
+    kind = rs.get("rope_type", rs.get("type"))
+    if kind != "llama3":
+        raise NotImplementedError(f"rope_scaling type {kind!r} (only 'default' and 'llama3' are implemented)")
+    factor, lo, hi = rs["factor"], rs["low_freq_factor"], rs["high_freq_factor"]
+    old_ctx = rs["original_max_position_embeddings"]
+    low_wl, high_wl = old_ctx / lo, old_ctx / hi
+    wavelen = 2 * math.pi / inv
+    inv_l = torch.where(wavelen > low_wl, inv / factor, inv)
+    smooth = (old_ctx / wavelen - lo) / (hi - lo)
+    smoothed = (1 - smooth) * inv_l / factor + smooth * inv_l
+    is_medium = ~(wavelen < high_wl) * ~(wavelen > low_wl)
+    return torch.where(is_medium, smoothed, inv_l)
 
 
 def resolve_llama(name_or_cfg):

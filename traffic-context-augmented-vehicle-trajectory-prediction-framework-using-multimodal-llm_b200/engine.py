@@ -6,6 +6,7 @@ import os
 import torch
 
 from . import ops
+from .config import rope_inv_freq
 
 _ACT = {"bf16": torch.bfloat16, "fp32": torch.float32}
 
@@ -123,7 +124,7 @@ class Engine:
         r = self.model_hp["lora_r"] if (wrap.use_lora and not merge) else 0
         n_t = len(targets)
         kx = ((n_t * r + 7) // 8) * 8            # LoRA side columns appended to K (multiple of 8 for TMA strides)
-        self.llm = dict(H=H, nh=nh, nkv=nkv, dh=dh, I=I, eps=c.get("rms_norm_eps", 1e-6), theta=float(c.get("rope_theta", 10000.0)),
+        self.llm = dict(H=H, nh=nh, nkv=nkv, dh=dh, I=I, eps=c.get("rms_norm_eps", 1e-6), theta=rope_inv_freq(c),
                         kx=kx, n_lora=n_t * r, vocab=c["vocab_size"], layers=[],
                         embed=lm.model.embed_tokens.weight.detach().to(dev, act).contiguous(), norm=_f32(lm.model.norm.weight, dev))
         nq, nk = nh * dh, nkv * dh

@@ -4,8 +4,12 @@ The reference evaluates on rank 0 only and, per batch, runs the forward, de-norm
 ADE / FDE with ~20 small launches and synchronises twice with `.item()` (scripts/train.py:1277-1326; the best-of-K variant is
 scripts/test.py:1298-1372).  `evaluate` keeps the same result — mean ADE / FDE over all scenes — with the device busy throughout:
 
-  * every rank walks its own batches (shard the dataset with a DistributedSampler exactly as the reference builds its loader,
-    or with `distributed.scene_shard`); nothing is exchanged while batches run;
+  * every rank walks its own batches — shard the scene range with `distributed.scene_shard` (contiguous, sizes differ by at most
+    one, no duplicates).  A `DistributedSampler` with the default `drop_last=False` PADS the index list with repeated samples when
+    len(dataset) % world != 0; the all-reduced sums would then count those scenes twice, so use `scene_shard` or a
+    non-padding sampler.  Nothing is exchanged while batches run;
+  * EVERY rank must call `evaluate` (it ends with a collective): do not keep the reference's `if local_rank == 0:` guard around it
+    (train.py:1255) — a lone rank would wait in the all-reduce forever;
   * forward + metric reduction are one call (`predict_with_metrics`); the running (sum ADE, sum FDE, scenes) stay on the device,
     so there is no per-batch host sync;
   * batches are pipelined two deep: batch i+1 is enqueued (its bulk inputs cross PCIe on the engine's copy stream) before the host

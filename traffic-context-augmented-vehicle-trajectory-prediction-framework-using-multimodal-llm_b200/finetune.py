@@ -16,7 +16,7 @@ from .distributed import FlatGradBucket
 
 
 class FineTuner:
-    def __init__(self, model, lr=5e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, group=None, use_cuda_graph=True):
+    def __init__(self, model, lr=5e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, group=None, use_cuda_graph=True, max_graphs=8):
         self.model, self.group = model, group
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
         named = model.trainable_named_parameters()
@@ -43,9 +43,12 @@ class FineTuner:
         self.steps = 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.use_cuda_graph = use_cuda_graph
-        self._graph = None
-        self._static = None
-        self._sig = None
+        # one captured graph (+ its static input buffers and output tensors) per input-shape signature: the reference collate pads the
+        # prompt to the longest sequence of each batch (train.py:323-325), so L_text moves from step to step and a single-slot cache would
+        # re-capture almost every step.  Least-recently-used entries are dropped beyond `max_graphs` (each holds one step's activations).
+        self._graphs = {}
+        self.max_graphs = max_graphs
+        self.captures = 0
         self.launches_per_step = 0    # libtcavp launches of one forward + backward (captured launches are replayed, not re-counted)
 
     @property
@@ -89,26 +92,37 @@ class FineTuner:
             self.launches_per_step = ops.launch_count() - n0
             return r
         sig = tuple((k, tuple(v.shape), v.dtype) for k, v in inp.items())
-        if self._graph is None or sig != self._sig:
+        ent = self._graphs.pop(sig, None)
+        if ent is None:
             # static input buffers + two eager steps on a side stream (lazy packing, cudaFuncSetAttribute, allocator warm-up), then capture
-            self._static = {k: v.clone() for k, v in inp.items()}
+            static = {k: v.clone() for k, v in inp.items()}
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
                 for _ in range(2):
-                    self._fwd_bwd(self._static)
+                    self._fwd_bwd(static)
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             n0 = ops.launch_count()
             with torch.cuda.graph(g):
-                self._out = self._fwd_bwd(self._static)
-            self.launches_per_step = ops.launch_count() - n0
-            self._graph, self._sig = g, sig
+                out = self._fwd_bwd(static)
+            ent = (g, static, out, ops.launch_count() - n0)
+            self.captures += 1
+            while len(self._graphs) >= max(1, self.max_graphs):
+                self._graphs.pop(next(iter(self._graphs)))        # dicts keep insertion order: the first key is the least recently used
+        self._graphs[sig] = ent                                   # (re-)inserted last = most recently used
+        g, static, out, self.launches_per_step = ent
         for k, v in inp.items():
-            self._static[k].copy_(v, non_blocking=True)
-        self._graph.replay()
-        return self._out
+            static[k].copy_(v, non_blocking=True)
+        g.replay()
+        # the graph's output tensors are overwritten by the next replay: hand out copies
+        return out[0].clone(), out[1].clone()
+
+    def all_reduce_only(self):
+        """The step's collective on its own (bench.py times it outside the step to report what the exchange costs)."""
+        if self.world > 1:
+            dist.all_reduce(self.bucket.flat, op=dist.ReduceOp.SUM, group=self.group)
 
     def step(self, x, vision_embs, context_str, lane_polygon_batch, lane_polygon_len, y, norm_stat, input_ids, attention_mask):
         """One optimisation step on this rank's shard of the batch; returns (loss, decoded) like the reference forward."""

@@ -11,6 +11,7 @@ import torch.nn as nn
 
 import warnings
 
+from . import ops
 from .config import resolve_llama
 from .engine import Engine
 from .train_engine import TrainEngine
@@ -26,6 +27,7 @@ class _FineTuneStep(torch.autograd.Function):
     def forward(ctx, eng, inputs, *params):
         out = eng.train_forward(**inputs)
         ctx.eng = eng
+        ctx.stash = out.pop("_ctx")        # this call's activations (not the engine's single "last forward" slot)
         ctx.names = [n for n, _ in eng.params]
         ctx.mark_non_differentiable(out["decoded"])
         ctx.set_materialize_grads(False)
@@ -35,7 +37,10 @@ class _FineTuneStep(torch.autograd.Function):
     def backward(ctx, gloss, _gdec):
         if gloss is None:
             return (None, None) + (None,) * len(ctx.names)
-        grads = ctx.eng.train_backward(gloss)
+        stash, ctx.stash = ctx.stash, None
+        if stash is None:
+            raise RuntimeError("tcavp_b200: backward through the same fine-tune step twice (activations are freed after the first pass)")
+        grads = ctx.eng.train_backward(gloss, ctx=stash)
         res = []
         for (name, p) in ctx.eng.params:
             g = grads.get(name)
@@ -133,6 +138,9 @@ class LlamaForCausalLMW(nn.Module):
             for m in self.modules():
                 if isinstance(m, (nn.Linear, nn.Embedding)):
                     m.weight.normal_(0.0, std)
+        if c.get("tie_word_embeddings", False):
+            # HF tie_weights(): lm_head.weight IS embed_tokens.weight (Llama-3.2-1B); state_dict() still lists both keys
+            self.lm_head.weight = self.model.embed_tokens.weight
 
     def get_input_embeddings(self):
         return self.model.embed_tokens
@@ -299,8 +307,11 @@ class MultiModalTrajectoryModel(nn.Module):
                  lane_polygon_layers=2, max_polygon_points=64, use_post_mlp=True, post_mlp_hidden_dim=64,
                  base_model_name="meta-llama/Llama-7B", use_lora=True, lora_r=8, lora_alpha=32, lora_dropout=0.1, vision_dim=512,
                  q_hidden_size=768, q_nhead=8, q_enc_layers=4, q_dec_layers=4, q_num_query_tokens=16, ltsf_nhead=1,
-                 ltsf_dropout=0.1, *, compute_dtype="bf16", llm_param_dtype=None, llm_device=None):
+                 ltsf_dropout=0.1, *, compute_dtype="bf16", llm_param_dtype=None, llm_device=None, llm_variant="wrapper"):
         super().__init__()
+        if llm_variant not in ("wrapper", "direct"):
+            raise ValueError("llm_variant must be 'wrapper' (train.py key layout) or 'direct' (im_kim_train_GRN.py key layout)")
+        self.llm_variant = llm_variant
         if feature_size != 2:
             raise NotImplementedError("feature_size must be 2 ((x, y) trajectories)")
         kw = {}
@@ -324,28 +335,61 @@ class MultiModalTrajectoryModel(nn.Module):
         self._train_sig = None
         self._warned_dropout = False
         self._register_load_state_dict_pre_hook(self._translate_keys)
+        self.mllm._register_load_state_dict_pre_hook(self._translate_mllm_keys_hook)
+        self._register_state_dict_hook(self._variant_keys)
 
     # ---- checkpoint interop -----------------------------------------------------
     def _translate_keys(self, state_dict, prefix, *args):
-        """Accepts (a) the V2 layout `mllm.llama_model.` (im_kim_train_GRN.py:444-455) and (b) the peft<0.7 layout
+        """load_state_dict pre-hook of the whole model (keys `mllm.…`)."""
+        self._translate_mllm_keys(state_dict, prefix + "mllm.")
+
+    def _translate_mllm_keys_hook(self, state_dict, prefix, *args):
+        """load_state_dict pre-hook of `model.mllm` — the reference restores stage-1 checkpoints with
+        `model.mllm.load_state_dict(sd, strict=True)` (train.py:1137-1138), which never reaches the top-level hook."""
+        self._translate_mllm_keys(state_dict, prefix)
+
+    def _translate_mllm_keys(self, state_dict, root):
+        """Accepts (a) the V2 layout `llama_model.` directly under mllm (im_kim_train_GRN.py:444-455) and (b) the peft<0.7 layout
         without `.base_layer` (implied by ablation_study_without_lora.py:1071-1079); (c) a LoRA checkpoint loaded into
-        a use_lora=False model is stripped exactly like the reference's adjust_state_dict."""
-        want_lora = self.mllm.llama_wrapper.use_lora
+        a use_lora=False model is stripped exactly like the reference's adjust_state_dict; (d) a checkpoint of a tied-embedding
+        backbone that omits `lm_head.weight` (HF safetensors of Llama-3.2-1B) gets it aliased from `embed_tokens.weight`."""
+        wrap = self.mllm.llama_wrapper
+        want_lora = wrap.use_lora
         for k in list(state_dict.keys()):
+            if not k.startswith(root):
+                continue
             nk = k
-            if nk.startswith(prefix + "mllm.llama_model."):
-                nk = prefix + "mllm.llama_wrapper.llama_model." + nk[len(prefix + "mllm.llama_model."):]
+            if nk.startswith(root + "llama_model."):
+                nk = root + "llama_wrapper.llama_model." + nk[len(root + "llama_model."):]
+            if not nk.startswith(root + "llama_wrapper."):
+                continue
             if not want_lora:
                 if "lora_A" in nk or "lora_B" in nk:
                     del state_dict[k]
                     continue
                 nk = nk.replace("llama_model.base_model.model.", "llama_model.").replace(".base_layer.", ".")
             else:
-                for t in self.mllm.llama_wrapper.llama_model.targets:
+                if "llama_model.base_model.model." not in nk:       # a plain (no-peft) backbone checkpoint into a LoRA model
+                    nk = nk.replace("llama_wrapper.llama_model.", "llama_wrapper.llama_model.base_model.model.", 1)
+                for t in wrap.llama_model.targets:
                     if nk.endswith(f".self_attn.{t}.weight"):
                         nk = nk[: -len("weight")] + "base_layer.weight"
             if nk != k:
                 state_dict[nk] = state_dict.pop(k)
+        if wrap.config.get("tie_word_embeddings", False):
+            base = root + "llama_wrapper.llama_model." + ("base_model.model." if want_lora else "")
+            if base + "lm_head.weight" not in state_dict and base + "model.embed_tokens.weight" in state_dict:
+                state_dict[base + "lm_head.weight"] = state_dict[base + "model.embed_tokens.weight"]
+
+    def _variant_keys(self, module, state_dict, prefix, local_metadata):
+        """state_dict hook for llm_variant="direct": keys are written as `mllm.llama_model.*` (the V2 module tree of
+        im_kim_train_GRN.py:444-455, which has no wrapper class between mllm and the HF / peft model)."""
+        if self.llm_variant != "direct":
+            return state_dict
+        a, b = prefix + "mllm.llama_wrapper.llama_model.", prefix + "mllm.llama_model."
+        for k in [k for k in state_dict if k.startswith(a)]:
+            state_dict[b + k[len(a):]] = state_dict.pop(k)
+        return state_dict
 
     # ---- engine management -------------------------------------------------------------------------
     def set_compute_dtype(self, name):

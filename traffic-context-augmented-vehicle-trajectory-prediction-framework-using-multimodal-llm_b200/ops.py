@@ -242,8 +242,14 @@ def row_rstd(x, out, *, rows, cols, ldx, eps):
 
 
 def rope_table(L, dh, theta, device, layout=0):
-    # HF:86-88 inv_freq, evaluated on the host exactly as transformers does
-    inv = (1.0 / (theta ** (torch.arange(0, dh, 2, dtype=torch.int64).float() / dh))).to(device)
+    """cos / sin table for positions [0, L).  `theta`: the rope base (plain rope, HF:86-88 inv_freq evaluated on the host exactly as
+    transformers does) or a precomputed fp32 inv_freq[dh/2] tensor (config.rope_inv_freq: llama3 frequency scaling)."""
+    if torch.is_tensor(theta):
+        if theta.numel() != dh // 2:
+            raise ValueError(f"rope_table: inv_freq has {theta.numel()} entries, head_dim {dh} needs {dh // 2}")
+        inv = theta.to(device=device, dtype=torch.float32).contiguous()
+    else:
+        inv = (1.0 / (theta ** (torch.arange(0, dh, 2, dtype=torch.int64).float() / dh))).to(device)
     t = torch.empty((L, dh // 2, 2) if layout == 0 else (dh // 4, L, 4), dtype=torch.float32, device=device)
     with _Timed("rope_table_kernel"):
         _lib.check(_lib.load().tcavp_rope_table(_p(t), _p(inv), L, dh, layout, _stream()), "tcavp_rope_table")

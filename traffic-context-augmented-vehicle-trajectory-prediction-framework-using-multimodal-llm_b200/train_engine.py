@@ -580,14 +580,22 @@ class TrainEngine(Engine):
         enc, c_enc = self._ltsf_enc_fwd(x, B)
         out, c_dec = self._ltsf_dec_fwd(enc, poly_emb, fh, x, B, L, y, norm_stat)
         out["loss"] = out["metrics"][4]
-        self._ctx = (c_poly, c_qf, c_llm, c_enc, c_dec, B, L, Q, H, ids.shape[1])
+        # the stash travels with the result (model.py keeps it on the autograd node), so two forwards may be in flight before either
+        # backward runs (gradient accumulation over micro-batches, two losses summed); `_ctx` is only the default of train_backward
+        out["_ctx"] = self._ctx = (c_poly, c_qf, c_llm, c_enc, c_dec, B, L, Q, H, ids.shape[1])
         return out
 
     @torch.no_grad()
-    def train_backward(self, gloss=None):
-        """Runs the backward pass of the last train_forward; returns {reference parameter name: fp32 gradient}."""
-        c_poly, c_qf, c_llm, c_enc, c_dec, B, L, Q, H, L_text = self._ctx
-        self._ctx = None
+    def train_backward(self, gloss=None, ctx=None):
+        """Runs the backward pass of a train_forward (`ctx` = its out["_ctx"]; default: the last one); returns
+        {reference parameter name: fp32 gradient}."""
+        if ctx is None:
+            ctx = self._ctx
+        if ctx is None:
+            raise ops._lib.TcavpError("train_backward: no forward pass to differentiate (or its activations were already consumed)")
+        c_poly, c_qf, c_llm, c_enc, c_dec, B, L, Q, H, L_text = ctx
+        if ctx is self._ctx:
+            self._ctx = None
         self.G = {}
         if gloss is not None:
             gloss = gloss.detach().to(device=self.dev, dtype=torch.float32).reshape(1).contiguous()
