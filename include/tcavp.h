@@ -140,6 +140,10 @@ typedef struct tcavp_attn_args {
   float scale;
   int causal;
   const int32_t* key_mask;
+  /* dropout on the attention probabilities (nn.MultiheadAttention(dropout=p) in train mode: train.py:663, 754 and the nn.Transformer
+   * layers of train.py:358, 402-405): P_drop = keep(b, h, i, j) ? P / (1 - p) : 0, applied after the softmax (row sums on the undropped
+   * P).  drop_thresh == 0 disables it.  See tcavp_dropout for the mask function; element index = ((b*H + h)*Tq + i)*Tk + j. */
+  const uint32_t* drop_seed; uint32_t drop_site; uint32_t drop_thresh; float drop_scale;
 } tcavp_attn_args;
 
 int tcavp_attention(const tcavp_attn_args* args, tcavp_stream_t stream);
@@ -304,6 +308,20 @@ int tcavp_attention_bwd_owned(const tcavp_attn_args* args, const void* dout, lon
  * gradient first (1/world_size after a sum all-reduce). */
 int tcavp_adamw(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1, float beta2,
                 float eps, float weight_decay, int step, float grad_scale, tcavp_stream_t stream);
+
+/* ---- dropout (train mode: lora_dropout train.py:432-440 -> peft lora.Linear; nn.Dropout of train.py:664-671, 745-750; the
+ * dropout / dropout1 / dropout2 / dropout3 of torch's nn.TransformerEncoderLayer / DecoderLayer, train.py:358, 402-405) --------------
+ * Counter-based mask, a pure function of (seed, site, element index) — nothing is stored, the backward pass regenerates it:
+ *     mix(x)  : x ^= x >> 16; x *= 0x7feb352d; x ^= x >> 15; x *= 0x846ca68b; x ^= x >> 16          (32-bit)
+ *     key     = mix(seed[0] ^ mix(site + 0x9E3779B9 * (seed[1] + 1)))
+ *     u       = mix(idx_lo ^ key);  if idx_hi != 0: u = mix(u ^ idx_hi * 0x85EBCA6B)
+ *     keep    = u >= thresh                         thresh = round(p * 2^32)
+ * `seed` is a DEVICE pointer to two uint32 (base seed, step counter) so a captured CUDA graph draws fresh masks on every replay.
+ *     out[r, c] = (accumulate ? out[r, c] : 0) + (residual ? residual[r, c] : 0) + (keep(r * cols + c) ? in[r, c] * scale : 0)
+ * (scale = 1 / (1 - p) for the forward pass; the same call on a gradient is the backward pass).  in == out is allowed. */
+int tcavp_dropout(const void* in, int ldi, int in_dtype, const void* residual, int ldr, int res_dtype, void* out, int ldo, int out_dtype,
+                  long long rows, int cols, const uint32_t* seed, uint32_t site, uint32_t thresh, float scale, int accumulate,
+                  tcavp_stream_t stream);
 
 #ifdef __cplusplus
 }

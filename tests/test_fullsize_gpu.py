@@ -58,7 +58,7 @@ def test_full_batch_oracle_spot_check(setup):
     # the backbone output itself (12 layers of the kernels that are 85 % of the step), same band as tests/test_model_gpu.py
     fh = full["final_hidden"][idx].float().cpu()
     rel = float((fh.double() - want["final_hidden"].double()).norm() / want["final_hidden"].double().norm())
-    assert rel < 1.0e-2, ("final_hidden relative L2 at full size", rel)
+    assert rel < 1.5e-2, ("final_hidden relative L2 at full size", rel)         # test_model_gpu.bf16_rel_l2_band(12 layers)
     ade = full["ade"][idx].cpu()
     assert float(((ade - want["ade"]).abs() / want["ade"]).max()) < 5e-3 * 4, (ade, want["ade"])   # per-scene ADE (mean ADE is within 0.5 %)
     assert abs(float(ade.mean()) - float(want["ade"].mean())) / float(want["ade"].mean()) < 5e-3

@@ -57,10 +57,14 @@ def test_fp32_forward_matches_reference(name, lib_built):
 
 # bf16 bands on the backbone itself (the decoded coordinates alone cannot see it: 5 % noise on final_hidden moves them by < 1e-2).
 # final_hidden is post-RMSNorm, O(1) per element: relative L2 of the stored head rows, and every row mean / mean |.| of the whole
-# batch.  Calibrated on B200 (tools/bf16_error_probe.py): the bf16 stack sits at 3-6e-3 relative L2; the injected-error test below
-# keeps the band honest.
-BF16_REL_L2 = 1.0e-2
-BF16_IMG_REL_L2 = 1.0e-2
+# batch.  Calibrated on B200 (tools/bf16_error_probe.py, profiles/bf16_probe_r02.txt): the bf16 stack sits at 6.0-6.5e-3 relative L2
+# after two decoder layers and 1.03-1.09e-2 after twelve (bf16 rounding of the residual stream accumulates with depth); 1 % / 2 %
+# multiplicative noise on ONE layer's weights gives 1.1-1.6e-2 / 1.8-2.6e-2, which the injected-error test below must catch.
+def bf16_rel_l2_band(n_layers):
+    return 9.0e-3 + 5.0e-4 * n_layers        # 1.0e-2 at 2 layers, 1.5e-2 at 12
+
+
+BF16_IMG_REL_L2 = 1.0e-2                     # Q-Former output (8 post-norm layers): measured 5.0-5.9e-3
 
 
 def _rel_l2(a, b):
@@ -78,7 +82,8 @@ def _check_bf16(m, o, g):
     assert r_img < BF16_IMG_REL_L2, ("image tokens", r_img)
     n = g["final_hidden_head"].shape[0]
     r_fh = _rel_l2(o["final_hidden"][:n], g["final_hidden_head"])
-    assert r_fh < BF16_REL_L2, ("final_hidden relative L2", r_fh)
+    n_layers = len(m.mllm.llama_wrapper.causal_lm().model.layers)
+    assert r_fh < bf16_rel_l2_band(n_layers), ("final_hidden relative L2", r_fh, n_layers)
     fh = o["final_hidden"]
     absmean = g["final_hidden_absmean"]
     # per-row statistics over the WHOLE batch (every scene, every position): mean within a bf16 band of the row's magnitude

@@ -36,6 +36,10 @@ __global__ void __launch_bounds__(128) attn_warp_kernel(tcavp_attn_args a) {
   }
   float m = -INFINITY, l = 0.f;
   const int kend = a.causal ? i + 1 : a.Tk;
+  // dropout on the probabilities (train mode): the PV product uses keep ? p / (1 - p_drop) : 0, the row sum the undropped p
+  const bool drop = a.drop_thresh != 0;
+  const uint32_t dkey = drop ? drop_key(a.drop_seed, a.drop_site) : 0u;
+  const unsigned long long drow = (unsigned long long)w * (unsigned long long)a.Tk;     // w = (b*H + h)*Tq + i
   for (int j0 = 0; j0 < kend; j0 += 4) {
     float s[4];
     bool ok[4];
@@ -73,6 +77,10 @@ __global__ void __launch_bounds__(128) attn_warp_kernel(tcavp_attn_args a) {
       ps += p[u];
     }
     l = l * corr + ps;
+    if (drop) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) p[u] = drop_keep(dkey, drow + (unsigned)(j0 + u), a.drop_thresh) ? p[u] * a.drop_scale : 0.f;
+    }
 #pragma unroll
     for (int e = 0; e < NE; ++e) acc[e] *= corr;
 #pragma unroll
@@ -117,7 +125,10 @@ __global__ void __launch_bounds__(128) attn_row_kernel(tcavp_attn_args a) {
   }
   for (int j = threadIdx.x; j < a.Tk; j += blockDim.x) sM[j] = !a.key_mask || a.key_mask[(size_t)b * a.Tk + j] != 0;
   __syncthreads();
+  const bool drop = a.drop_thresh != 0;
+  const uint32_t dkey = drop ? drop_key(a.drop_seed, a.drop_site) : 0u;
   for (int i = threadIdx.x; i < a.Tq; i += blockDim.x) {
+    const unsigned long long drow = ((unsigned long long)blockIdx.x * a.Tq + i) * (unsigned long long)a.Tk;   // blockIdx.x = b*H + h
     const T* q = reinterpret_cast<const T*>(a.q) + (size_t)b * a.q_sb + (size_t)i * a.q_st + (size_t)h * DH;
     float qr[DH], acc[DH];
 #pragma unroll
@@ -141,8 +152,10 @@ __global__ void __launch_bounds__(128) attn_row_kernel(tcavp_attn_args a) {
       }
       const float s = s0 + s1;
       const float mn = fmaxf(m, s);
-      const float corr = __expf(m - mn), p = __expf(s - mn);
+      const float corr = __expf(m - mn);
+      float p = __expf(s - mn);
       l = l * corr + p;
+      if (drop) p = drop_keep(dkey, drow + (unsigned)j, a.drop_thresh) ? p * a.drop_scale : 0.f;
       const float4* vj = reinterpret_cast<const float4*>(sV + (size_t)j * DH);
 #pragma unroll
       for (int d4 = 0; d4 < DH / 4; ++d4) {
@@ -198,8 +211,10 @@ extern "C" int tcavp_attention(const tcavp_attn_args* a, tcavp_stream_t stream_)
   TCAVP_REQUIRE(a->q && a->k && a->v && a->out, "tcavp_attention: null tensor");
   TCAVP_REQUIRE(!a->causal || a->Tq == a->Tk, "tcavp_attention: causal needs Tq == Tk");
   TCAVP_REQUIRE(a->dtype == TCAVP_F32 || a->dtype == TCAVP_BF16, "tcavp_attention: bad dtype");
+  TCAVP_REQUIRE(a->drop_thresh == 0 || (a->drop_seed != nullptr && a->drop_scale > 0.f), "tcavp_attention: dropout needs a device seed and a scale");
   if (a->dtype == TCAVP_BF16) {
-    int rc = a->dh > 128 ? attention_x_launch(*a, stream) : attention_tc_launch(*a, stream);
+    // the tensor-core kernels have no dropout path: train-mode attention of the small modules (poly / Q-Former / LTSF) takes the SIMT kernels
+    int rc = a->drop_thresh != 0 ? 1 : (a->dh > 128 ? attention_x_launch(*a, stream) : attention_tc_launch(*a, stream));
     if (rc <= 0) return rc;
     return launch_warp<__nv_bfloat16>(*a, stream);
   }

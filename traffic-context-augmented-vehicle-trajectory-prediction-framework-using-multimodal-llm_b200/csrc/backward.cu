@@ -593,13 +593,35 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_kernel(tcavp_attn_args a, co
       l = warp_sum(l);
       const float inv = l > 0.f ? 1.f / l : 0.f;
       float dsum = 0.f;
-      for (int j = lane; j < Tk; j += 32) {
-        const float p = sP[i * Tk + j] * inv;
-        sP[i * Tk + j] = p;
-        dsum += p * sdS[i * Tk + j];
+      if (a.drop_thresh == 0) {
+        for (int j = lane; j < Tk; j += 32) {
+          const float p = sP[i * Tk + j] * inv;
+          sP[i * Tk + j] = p;
+          dsum += p * sdS[i * Tk + j];
+        }
+        dsum = warp_sum(dsum);
+        for (int j = lane; j < Tk; j += 32) sdS[i * Tk + j] = a.scale * sP[i * Tk + j] * (sdS[i * Tk + j] - dsum);
+      } else {
+        // O = P_d V with P_d = keep ? P / (1 - p_drop) : 0:  dP = mask-scaled (dO V^T),  D = sum_j P dP,  dS = scale P (dP - D),
+        // and dV uses P_d (kept in sP for phase C)
+        const uint32_t dkey = drop_key(a.drop_seed, a.drop_site);
+        const unsigned long long drow = ((unsigned long long)bh * a.Tq + (unsigned)(q0 + i)) * (unsigned long long)Tk;
+        for (int j = lane; j < Tk; j += 32) {
+          const float p = sP[i * Tk + j] * inv;
+          const float f = (q0 + i < a.Tq && drop_keep(dkey, drow + (unsigned)j, a.drop_thresh)) ? a.drop_scale : 0.f;
+          const float dp = f * sdS[i * Tk + j];
+          dsum += p * dp;
+          sdS[i * Tk + j] = dp;
+          sP[i * Tk + j] = p;
+        }
+        dsum = warp_sum(dsum);
+        for (int j = lane; j < Tk; j += 32) {
+          const float p = sP[i * Tk + j];
+          const float f = (q0 + i < a.Tq && drop_keep(dkey, drow + (unsigned)j, a.drop_thresh)) ? a.drop_scale : 0.f;
+          sdS[i * Tk + j] = a.scale * p * (sdS[i * Tk + j] - dsum);
+          sP[i * Tk + j] = p * f;
+        }
       }
-      dsum = warp_sum(dsum);
-      for (int j = lane; j < Tk; j += 32) sdS[i * Tk + j] = a.scale * sP[i * Tk + j] * (sdS[i * Tk + j] - dsum);
     }
   }
   // ---- phase C: dQ, dK, dV per head-dim chunk ----
@@ -927,7 +949,8 @@ extern "C" int tcavp_attention_bwd(const tcavp_attn_args* a, const void* dout, l
   TCAVP_REQUIRE(!a->causal || a->Tq == a->Tk, "tcavp_attention_bwd: causal needs Tq == Tk");
   if (a->B == 0) return TCAVP_OK;
   TCAVP_REQUIRE(a->q && a->k && a->v && dout && dq && dk && dv && DT_OK(a->dtype), "tcavp_attention_bwd: bad pointer/dtype");
-  {   // tensor-core path: bf16, MHA, small head, forward output available (args->out)
+  TCAVP_REQUIRE(a->drop_thresh == 0 || (a->drop_seed != nullptr && a->drop_scale > 0.f), "tcavp_attention_bwd: dropout needs a device seed and a scale");
+  if (a->drop_thresh == 0) {   // tensor-core path: bf16, MHA, small head, forward output available (args->out); no dropout path there
     const int rc = attention_bwd_tc_launch(*a, dout, do_sb, do_st, dq, dq_sb, dq_st, dk, dk_sb, dk_st, dv, dv_sb, dv_st, TCAVP_F32, STREAM(stream));
     if (rc <= 0) return rc;
   }
@@ -960,6 +983,7 @@ extern "C" int tcavp_attention_bwd_owned(const tcavp_attn_args* a, const void* d
   TCAVP_REQUIRE(!a->causal || a->Tq == a->Tk, "tcavp_attention_bwd_owned: causal needs Tq == Tk");
   if (a->B == 0) return TCAVP_OK;
   TCAVP_REQUIRE(a->q && a->k && a->v && dout && dq && dk && dv && DT_OK(dkv_dtype), "tcavp_attention_bwd_owned: bad pointer/dtype");
+  TCAVP_REQUIRE(a->drop_thresh == 0, "tcavp_attention_bwd_owned: no dropout path (use tcavp_attention_bwd)");
   int rc = 1;
   if (a->out) rc = attention_bwd_tc_launch(*a, dout, do_sb, do_st, dq, dq_sb, dq_st, dk, dk_sb, dk_st, dv, dv_sb, dv_st, dkv_dtype, STREAM(stream));
   if (rc > 0)   // few queries against wide heads (LTSF cross-attention): head_dim % 64 == 0, Tq <= 64, no causal mask

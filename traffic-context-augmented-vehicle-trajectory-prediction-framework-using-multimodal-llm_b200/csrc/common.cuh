@@ -109,6 +109,23 @@ __device__ __forceinline__ float sumsq_rstd(const unsigned long long* src, float
   return rsqrtf((float)__ldg(src) * (1.f / SUMSQ_FIX) * inv_cols + eps);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Counter-based dropout mask (include/tcavp.h: tcavp_dropout): a pure function of (seed, site, element index).
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint32_t drop_key(const uint32_t* seed, uint32_t site) {
+  return mix32(__ldg(seed) ^ mix32(site + 0x9E3779B9U * (__ldg(seed + 1) + 1U)));
+}
+__device__ __forceinline__ bool drop_keep(uint32_t key, unsigned long long idx, uint32_t thresh) {
+  uint32_t u = mix32((uint32_t)idx ^ key);
+  const uint32_t hi = (uint32_t)(idx >> 32);
+  if (hi) u = mix32(u ^ (hi * 0x85EBCA6BU));
+  return u >= thresh;
+}
+
 void count_launch();
 
 }  // namespace tcavp

@@ -114,6 +114,59 @@ __global__ void __launch_bounds__(256) cast_vec_kernel(const void* __restrict__ 
   }
 }
 
+// Counter-based dropout (include/tcavp.h): out = [out +] [residual +] keep(r * cols + c) ? in * scale : 0.  Eight columns per thread
+// on the vector path (16-byte bf16 / 32-byte fp32 accesses); the mask is recomputed from (seed, site, index), never stored.
+template <int V>
+__global__ void __launch_bounds__(256) dropout_kernel(const void* in, int ldi, int in_dtype, const void* __restrict__ res, int ldr,
+                                                      int res_dtype, void* out, int ldo, int out_dtype, long long rows, int cols,
+                                                      const uint32_t* __restrict__ seed, uint32_t site, uint32_t thresh, float scale, int accumulate) {
+  const uint32_t key = drop_key(seed, site);
+  const int per = cols / V;
+  const long long total = rows * per;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / per;
+    const int c = (int)(i % per) * V;
+    float v[V], o[V];
+    if (V == 8) {
+      if (in_dtype == TCAVP_BF16) {
+        const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(in) + (size_t)r * ldi + c);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          v[2 * e] = __uint_as_float(w[e] << 16);
+          v[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+        }
+      } else {
+        const float4* p4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(in) + (size_t)r * ldi + c);
+        const float4 a = p4[0], b = p4[1];
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      }
+    } else {
+      v[0] = load_as_f(in, (size_t)r * ldi + c, in_dtype);
+    }
+    const unsigned long long base = (unsigned long long)r * (unsigned long long)cols + (unsigned long long)c;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      o[e] = drop_keep(key, base + e, thresh) ? v[e] * scale : 0.f;
+      if (res) o[e] += load_as_f(res, (size_t)r * ldr + c + e, res_dtype);
+      if (accumulate) o[e] += load_as_f(out, (size_t)r * ldo + c + e, out_dtype);
+    }
+    if (V == 8 && out_dtype == TCAVP_BF16) {
+      uint4 u;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + (size_t)r * ldo + c) = u;
+    } else if (V == 8) {
+      float4* p4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (size_t)r * ldo + c);
+      p4[0] = make_float4(o[0], o[1], o[2], o[3]);
+      p4[1] = make_float4(o[4], o[5], o[6], o[7]);
+    } else {
+      store_from_f(out, (size_t)r * ldo + c, out_dtype, o[0]);
+    }
+  }
+}
+
 __global__ void poly_embed_kernel(const float* __restrict__ poly, const int32_t* __restrict__ len, const float* __restrict__ w,
                                   const float* __restrict__ bias, const float* __restrict__ pos, void* __restrict__ out,
                                   int out_dtype, int32_t* __restrict__ key_mask, int B, int P, int D) {
@@ -240,6 +293,26 @@ extern "C" int tcavp_cast(const void* in, int ldi, int in_dtype, void* out, int 
   }
   cast_kernel<<<grid_for((long long)rows * cols, 256), 256, 0, STREAM(stream)>>>(in, ldi, in_dtype, out, ldo, out_dtype, rows, cols, in_row_mod);
   return check_launch("cast_kernel");
+}
+
+extern "C" int tcavp_dropout(const void* in, int ldi, int in_dtype, const void* residual, int ldr, int res_dtype, void* out, int ldo, int out_dtype,
+                             long long rows, int cols, const uint32_t* seed, uint32_t site, uint32_t thresh, float scale, int accumulate,
+                             tcavp_stream_t stream) {
+  TCAVP_REQUIRE(rows >= 0 && cols > 0 && ldi >= cols && ldo >= cols && (!residual || ldr >= cols), "tcavp_dropout: bad shape");
+  if (rows == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(in && out && seed && DT_OK(in_dtype) && DT_OK(out_dtype) && (!residual || DT_OK(res_dtype)), "tcavp_dropout: bad pointer/dtype");
+  auto al = [](const void* p, int ld, int dtype) {
+    const size_t esz = dtype == TCAVP_BF16 ? 2 : 4;
+    return reinterpret_cast<uintptr_t>(p) % 16 == 0 && ((size_t)ld * esz) % 16 == 0;
+  };
+  if (cols % 8 == 0 && al(in, ldi, in_dtype) && al(out, ldo, out_dtype)) {
+    dropout_kernel<8><<<grid_for(rows * (cols / 8), 256), 256, 0, STREAM(stream)>>>(in, ldi, in_dtype, residual, ldr, res_dtype, out, ldo, out_dtype,
+                                                                                  rows, cols, seed, site, thresh, scale, accumulate);
+  } else {
+    dropout_kernel<1><<<grid_for(rows * cols, 256), 256, 0, STREAM(stream)>>>(in, ldi, in_dtype, residual, ldr, res_dtype, out, ldo, out_dtype, rows,
+                                                                            cols, seed, site, thresh, scale, accumulate);
+  }
+  return check_launch("dropout_kernel");
 }
 
 extern "C" int tcavp_poly_embed(const float* polygon, const int32_t* len, const float* w, const float* bias, const float* pos,
