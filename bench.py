@@ -408,9 +408,9 @@ def measure_train(ctx, workload, steps, warmup, scenes=0, dropout=None):
         B = scenes
     over = {} if dropout is None else dict(lora_dropout=dropout, ltsf_dropout=dropout)
     model, cfg = build_model(preset, dev, over=over)
-    model.train()
-    if dropout is not None and hasattr(model, "set_transformer_dropout"):
-        model.set_transformer_dropout(dropout)
+    model.train()        # the reference's fine-tune step runs in train() mode: lora / ltsf / nn.Transformer dropout 0.1
+    if dropout is not None:
+        model.set_dropout(dropout)
     lc = T.resolve_llama(cfg["base_model_name"])
     s = scenes_for(cfg, B, l_text, 1234 + rank, lc["vocab_size"])
     d = {k: s[k].to(dev) for k in ("x", "y", "vision", "polygon", "input_ids", "attention_mask")}
@@ -463,7 +463,9 @@ def measure_train(ctx, workload, steps, warmup, scenes=0, dropout=None):
     peak_gb = torch.cuda.max_memory_allocated() / 2 ** 30
     pk = peaks()
     roof, _ = _roofline(prof, pk, ms / steps, 1, {"breakdown": "one eager step after the timed region (the timed steps replay a CUDA graph)"})
-    p_drop = {"lora": cfg.get("lora_dropout", 0.1), "ltsf": cfg.get("ltsf_dropout", 0.1), "applied": bool(getattr(ft, "dropout_active", False))}
+    probs = model.train_engine()._dropout_probs()
+    p_drop = {"lora": probs.get(("llm", "lora_q"), 0.0), "ltsf": probs.get(("ltsf", "ffn"), 0.0), "transformer_layers": probs.get(("qenc", "ffn"), 0.0),
+              "applied": bool(ft.dropout_active), "masks": "counter-based (seed, step, site, element), regenerated in the backward pass"}
     out = {
         "metric": "LoRA fine-tune tokens/sec (forward + backward + grad all-reduce + AdamW)", "value": round(value, 1), "unit": "tokens/s",
         "n_gpus": world, "steps": steps, "warmup": max(warmup, 3), "ms_per_step": round(ms / steps, 3),

@@ -121,11 +121,27 @@ GRAD_FIXTURES = {
 }
 
 
+# train-mode fixtures: name -> (p = 0 fixture it shares model / inputs with, dropout seed, step)
+DROP_FIXTURES = {
+    "tiny_b5_grads_drop": ("tiny_b5_grads", 20261, 3),
+    "cfg1_b3_grads_drop": ("cfg1_b3_grads", 77001, 11),
+}
+
+
 def make_grads(name="tiny_b5_grads"):
-    """Gradients of the UNMODIFIED reference model (eval mode = every dropout off, autograd on):
-    the pin of the fine-tune step (reference scripts/im_kim_train_GRN.py:1029-1039)."""
+    """Gradients of the UNMODIFIED reference model (autograd on): the pin of the fine-tune step (reference
+    scripts/im_kim_train_GRN.py:1029-1039).  Plain fixtures run in eval mode (every dropout off); `*_drop` fixtures run in train()
+    mode — the reference's lora_dropout = ltsf_dropout = 0.1 and torch's 0.1 in every nn.Transformer layer — with torch's Bernoulli
+    draw replaced by the counter-based mask of include/tcavp.h (oracle/dropout.py: patch_reference_dropout)."""
+    from oracle import dropout as OD
     from oracle import restated
-    preset, B, l_text, poly_len, *over = GRAD_FIXTURES[name]
+    drop = None
+    if name in DROP_FIXTURES:
+        base, dseed, dstep = DROP_FIXTURES[name]
+        drop = (dseed, dstep)
+    else:
+        base = name
+    preset, B, l_text, poly_len, *over = GRAD_FIXTURES[base]
     mc = dict(T.MODEL_PRESETS[preset])
     mc.update(over[0] if over else {})
     lc = T.resolve_llama(mc["base_model_name"])
@@ -143,13 +159,25 @@ def make_grads(name="tiny_b5_grads"):
     # The reference's own fp32 backward is noise-dominated in the first lane-polygon attention (raw-pixel inputs give logits
     # ~1e6: its fp32 gradients of pos_embedding / input_proj / layer-0 in_proj differ by 20-30 % from its fp64 gradients, while
     # every other tensor agrees to 1e-6).  The pin is therefore the UNMODIFIED reference run in float64.
-    with torch.no_grad():
+    import contextlib
+    n_llm = lc["num_hidden_layers"]
+
+    def patched():
+        if drop is None:
+            return contextlib.nullcontext()
+        return OD.patch_reference_dropout(OD.DropOracle(drop[0], drop[1], {}), OD.reference_call_sequence(mc, n_llm))
+    if drop is not None:
+        model.train()
+    with torch.no_grad(), patched():
         loss32, _ = model(s["x"], s["vision"], s["context_str"], s["polygon"], s["poly_len"], y=s["y"], norm_stat=s["norm_stat"],
                           input_ids=s["input_ids"], attention_mask=s["attention_mask"], labels=None)
     model = model.double()
     model.zero_grad()
-    loss, decoded = model(s["x"].double(), s["vision"].double(), s["context_str"], s["polygon"].double(), s["poly_len"], y=s["y"].double(),
-                          norm_stat=s["norm_stat"], input_ids=s["input_ids"], attention_mask=s["attention_mask"], labels=None)
+    with patched() as st:
+        loss, decoded = model(s["x"].double(), s["vision"].double(), s["context_str"], s["polygon"].double(), s["poly_len"], y=s["y"].double(),
+                              norm_stat=s["norm_stat"], input_ids=s["input_ids"], attention_mask=s["attention_mask"], labels=None)
+    if drop is not None:
+        print(f"  train mode: {st['calls']} dropout calls mapped to sites")
     loss.backward()
     assert abs(float(loss) - float(loss32)) < 1e-4 * float(loss), (float(loss), float(loss32))
     grads = {k: p.grad for k, p in model.named_parameters() if p.requires_grad and p.grad is not None}
@@ -159,6 +187,8 @@ def make_grads(name="tiny_b5_grads"):
            "inputs": {k: s[k] for k in ("x", "y", "vision", "polygon", "poly_len", "norm_stat", "input_ids", "attention_mask")},
            "loss": loss.detach().float(), "loss_fp32_run": loss32.detach(), "decoded": decoded.detach().float(), "n_trainable": len(grads),
            "precision": "reference executed in float64 (see make_grads)",
+           "dropout": None if drop is None else {"seed": drop[0], "step": drop[1], "probs": {f"{k[0]}.{k[1]}": v for k, v in OD.default_probs(mc).items()},
+                                                  "mode": "train(): counter-based masks of include/tcavp.h substituted for torch's RNG"},
            "grads": {k: restated.compress_grad(v) for k, v in grads.items()},
            "versions": {"torch": str(torch.__version__), "transformers": __import__("transformers").__version__}}
     path = os.path.join(GOLDEN_DIR, name + ".pt")
@@ -169,5 +199,5 @@ def make_grads(name="tiny_b5_grads"):
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
-    for n in (sys.argv[1:] or list(FIXTURES) + list(GRAD_FIXTURES)):
-        make_grads(n) if n.endswith("_grads") else make(n)
+    for n in (sys.argv[1:] or list(FIXTURES) + list(GRAD_FIXTURES) + list(DROP_FIXTURES)):
+        make_grads(n) if "_grads" in n else make(n)

@@ -39,9 +39,35 @@ def rms_norm(x, w, eps):
     return w * (xf * torch.rsqrt(var + eps)).to(x.dtype)
 
 
-def mha(q_in, k_in, v_in, w_in, b_in, w_out, b_out, nheads, key_padding_mask=None):
+# Train-mode dropout: oracle/dropout.py's DropOracle, set by `with dropout(...)`; None = eval mode (every p = 0, the default).
+DROP = None
+
+
+def _D(t, mod, layer, kind):
+    """One dropout site (identity in eval mode); `t` is in the canonical batch-major layout."""
+    return t if DROP is None else DROP.apply(t, mod, layer, kind)
+
+
+class dropout:
+    """with restated.dropout(DropOracle(...)): forward(...)   — runs the restatement in train mode with those masks."""
+
+    def __init__(self, oracle):
+        self.oracle = oracle
+
+    def __enter__(self):
+        global DROP
+        self.prev, DROP = DROP, self.oracle
+        return self.oracle
+
+    def __exit__(self, *a):
+        global DROP
+        DROP = self.prev
+
+
+def mha(q_in, k_in, v_in, w_in, b_in, w_out, b_out, nheads, key_padding_mask=None, site=None):
     """torch: F.multi_head_attention_forward (packed in_proj, batch-first view here).
-    q_in (B,Tq,E), k_in/v_in (B,Tk,E); key_padding_mask (B,Tk) bool, True = ignore."""
+    q_in (B,Tq,E), k_in/v_in (B,Tk,E); key_padding_mask (B,Tk) bool, True = ignore.  site = (module, layer, kind) of the
+    dropout on the attention probabilities (train mode)."""
     B, Tq, E = q_in.shape
     Tk = k_in.shape[1]
     dh = E // nheads
@@ -54,6 +80,8 @@ def mha(q_in, k_in, v_in, w_in, b_in, w_out, b_out, nheads, key_padding_mask=Non
     if key_padding_mask is not None:
         s = s.masked_fill(key_padding_mask[:, None, None, :], float("-inf"))
     p = torch.softmax(s, dim=-1)
+    if site is not None:
+        p = _D(p, *site)
     o = (p @ v).transpose(1, 2).reshape(B, Tq, E)
     return linear(o, w_out, b_out)
 
@@ -62,27 +90,29 @@ def _g(sd, prefix, name):
     return sd[prefix + name]
 
 
-def encoder_layer(sd, p, x, nheads, key_padding_mask=None):
-    """torch: nn.TransformerEncoderLayer, norm_first=False, activation=relu, eval (dropout off)."""
+def encoder_layer(sd, p, x, nheads, key_padding_mask=None, mod=None, li=0):
+    """torch: nn.TransformerEncoderLayer, norm_first=False, activation=relu:
+    x = norm1(x + dropout1(sa(x))); x = norm2(x + dropout2(linear2(dropout(relu(linear1(x))))))   (dropout sites: train mode only)."""
     a = mha(x, x, x, sd[p + "self_attn.in_proj_weight"], sd[p + "self_attn.in_proj_bias"],
-            sd[p + "self_attn.out_proj.weight"], sd[p + "self_attn.out_proj.bias"], nheads, key_padding_mask)
-    x = layer_norm(x + a, sd[p + "norm1.weight"], sd[p + "norm1.bias"])
-    f = linear(torch.relu(linear(x, sd[p + "linear1.weight"], sd[p + "linear1.bias"])),
-               sd[p + "linear2.weight"], sd[p + "linear2.bias"])
-    return layer_norm(x + f, sd[p + "norm2.weight"], sd[p + "norm2.bias"])
+            sd[p + "self_attn.out_proj.weight"], sd[p + "self_attn.out_proj.bias"], nheads, key_padding_mask, site=(mod, li, "sa_attn"))
+    x = layer_norm(x + _D(a, mod, li, "drop1"), sd[p + "norm1.weight"], sd[p + "norm1.bias"])
+    h = _D(torch.relu(linear(x, sd[p + "linear1.weight"], sd[p + "linear1.bias"])), mod, li, "ffn")
+    f = linear(h, sd[p + "linear2.weight"], sd[p + "linear2.bias"])
+    return layer_norm(x + _D(f, mod, li, "drop2"), sd[p + "norm2.weight"], sd[p + "norm2.bias"])
 
 
-def decoder_layer(sd, p, x, mem, nheads):
+def decoder_layer(sd, p, x, mem, nheads, li=0):
     """torch: nn.TransformerDecoderLayer, norm_first=False, relu, no masks (reference train.py:413)."""
+    mod = "qdec"
     a = mha(x, x, x, sd[p + "self_attn.in_proj_weight"], sd[p + "self_attn.in_proj_bias"],
-            sd[p + "self_attn.out_proj.weight"], sd[p + "self_attn.out_proj.bias"], nheads)
-    x = layer_norm(x + a, sd[p + "norm1.weight"], sd[p + "norm1.bias"])
+            sd[p + "self_attn.out_proj.weight"], sd[p + "self_attn.out_proj.bias"], nheads, site=(mod, li, "sa_attn"))
+    x = layer_norm(x + _D(a, mod, li, "drop1"), sd[p + "norm1.weight"], sd[p + "norm1.bias"])
     c = mha(x, mem, mem, sd[p + "multihead_attn.in_proj_weight"], sd[p + "multihead_attn.in_proj_bias"],
-            sd[p + "multihead_attn.out_proj.weight"], sd[p + "multihead_attn.out_proj.bias"], nheads)
-    x = layer_norm(x + c, sd[p + "norm2.weight"], sd[p + "norm2.bias"])
-    f = linear(torch.relu(linear(x, sd[p + "linear1.weight"], sd[p + "linear1.bias"])),
-               sd[p + "linear2.weight"], sd[p + "linear2.bias"])
-    return layer_norm(x + f, sd[p + "norm3.weight"], sd[p + "norm3.bias"])
+            sd[p + "multihead_attn.out_proj.weight"], sd[p + "multihead_attn.out_proj.bias"], nheads, site=(mod, li, "ca_attn"))
+    x = layer_norm(x + _D(c, mod, li, "drop2"), sd[p + "norm2.weight"], sd[p + "norm2.bias"])
+    h = _D(torch.relu(linear(x, sd[p + "linear1.weight"], sd[p + "linear1.bias"])), mod, li, "ffn")
+    f = linear(h, sd[p + "linear2.weight"], sd[p + "linear2.bias"])
+    return layer_norm(x + _D(f, mod, li, "drop3"), sd[p + "norm3.weight"], sd[p + "norm3.bias"])
 
 
 def _count_layers(sd, prefix):
@@ -103,7 +133,7 @@ def lane_polygon_encoder(sd, polygon, poly_len, nheads=4, p="lane_polygon_encode
     lens = torch.as_tensor(list(poly_len), dtype=torch.long)
     pad = torch.arange(P)[None, :] >= lens[:, None]                       # train.py:366-370
     for i in range(_count_layers(sd, p + "encoder.layers.")):
-        x = encoder_layer(sd, f"{p}encoder.layers.{i}.", x, nheads, pad)
+        x = encoder_layer(sd, f"{p}encoder.layers.{i}.", x, nheads, pad, mod="poly", li=i)
     valid = (~pad).to(x.dtype)[:, :, None]                                # train.py:373-382 masked mean, 0 if len==0
     x = torch.nan_to_num(x, nan=0.0)  # rows with len==0 are all-masked (NaN softmax) and discarded by the reference
     s = (x * valid).sum(1)
@@ -119,10 +149,10 @@ def qformer(sd, vision, nheads=8, p="mllm.qformer."):
     B = vision.shape[0]
     x = linear(vision, sd[p + "vision_proj.weight"], sd[p + "vision_proj.bias"])
     for i in range(_count_layers(sd, p + "encoder.layers.")):
-        x = encoder_layer(sd, f"{p}encoder.layers.{i}.", x, nheads)
+        x = encoder_layer(sd, f"{p}encoder.layers.{i}.", x, nheads, mod="qenc", li=i)
     q = sd[p + "query_tokens"].unsqueeze(0).expand(B, -1, -1)
     for i in range(_count_layers(sd, p + "decoder.layers.")):
-        q = decoder_layer(sd, f"{p}decoder.layers.{i}.", q, x, nheads)
+        q = decoder_layer(sd, f"{p}decoder.layers.{i}.", q, x, nheads, li=i)
     return q
 
 
@@ -139,13 +169,14 @@ def find_llm_prefix(sd):
     raise KeyError("no embed_tokens in state_dict")
 
 
-def _lora_linear(sd, p, x, scaling):
-    """peft lora.Linear.forward (eval): base(x) + B(A(x)) * alpha/r.  Accepts peft>=0.7 (.base_layer) and
-    the older layout without it (reference ablation_study_without_lora.py:1071-1079)."""
+def _lora_linear(sd, p, x, scaling, site=None):
+    """peft lora.Linear.forward: base(x) + B(A(dropout(x))) * alpha/r (dropout in train mode only).  Accepts peft>=0.7 (.base_layer)
+    and the older layout without it (reference ablation_study_without_lora.py:1071-1079)."""
     w = sd.get(p + "base_layer.weight", sd.get(p + "weight"))
     y = linear(x, w)
     if p + "lora_A.default.weight" in sd:
-        y = y + linear(linear(x, sd[p + "lora_A.default.weight"]), sd[p + "lora_B.default.weight"]) * scaling
+        xd = x if site is None else _D(x, *site)
+        y = y + linear(linear(xd, sd[p + "lora_A.default.weight"]), sd[p + "lora_B.default.weight"]) * scaling
     return y
 
 
@@ -196,9 +227,9 @@ def llama_stack(sd, llama_cfg, embeds, attn_mask, lora_scaling, p=None):
     for i in range(llama_cfg["num_hidden_layers"]):
         lp = f"{p}layers.{i}."
         h = rms_norm(x, sd[lp + "input_layernorm.weight"], eps)
-        q = _lora_linear(sd, lp + "self_attn.q_proj.", h, lora_scaling).view(B, L, nh, dh).transpose(1, 2)
-        k = _lora_linear(sd, lp + "self_attn.k_proj.", h, lora_scaling).view(B, L, nkv, dh).transpose(1, 2)
-        v = _lora_linear(sd, lp + "self_attn.v_proj.", h, lora_scaling).view(B, L, nkv, dh).transpose(1, 2)
+        q = _lora_linear(sd, lp + "self_attn.q_proj.", h, lora_scaling, ("llm", i, "lora_q")).view(B, L, nh, dh).transpose(1, 2)
+        k = _lora_linear(sd, lp + "self_attn.k_proj.", h, lora_scaling, ("llm", i, "lora_k")).view(B, L, nkv, dh).transpose(1, 2)
+        v = _lora_linear(sd, lp + "self_attn.v_proj.", h, lora_scaling, ("llm", i, "lora_v")).view(B, L, nkv, dh).transpose(1, 2)
         q = q * cos + rotate_half(q) * sin                                  # HF:146-170
         k = k * cos + rotate_half(k) * sin
         if nkv != nh:
@@ -261,10 +292,11 @@ def self_attention_block(sd, enc, nheads, p="ltsf.attn_block."):
     x = enc.permute(0, 2, 1)                                                # (B,T,E) batch-first view of (T,B,E)
     xn = layer_norm(x, sd[p + "norm1.weight"], sd[p + "norm1.bias"])
     a = mha(xn, xn, xn, sd[p + "mha.in_proj_weight"], sd[p + "mha.in_proj_bias"],
-            sd[p + "mha.out_proj.weight"], sd[p + "mha.out_proj.bias"], nheads)
-    r = layer_norm(xn + a, sd[p + "norm2.weight"], sd[p + "norm2.bias"])
-    f = linear(torch.relu(linear(r, sd[p + "ffn.0.weight"], sd[p + "ffn.0.bias"])), sd[p + "ffn.3.weight"], sd[p + "ffn.3.bias"])
-    return (r + f).permute(0, 2, 1)
+            sd[p + "mha.out_proj.weight"], sd[p + "mha.out_proj.bias"], nheads, site=("ltsf", 0, "sa_attn"))
+    r = layer_norm(xn + _D(a, "ltsf", 0, "drop1"), sd[p + "norm2.weight"], sd[p + "norm2.bias"])
+    h = _D(torch.relu(linear(r, sd[p + "ffn.0.weight"], sd[p + "ffn.0.bias"])), "ltsf", 0, "ffn")
+    f = linear(h, sd[p + "ffn.3.weight"], sd[p + "ffn.3.bias"])
+    return (r + _D(f, "ltsf", 0, "drop2")).permute(0, 2, 1)
 
 
 def ltsf_decoder(sd, enc, poly_emb, final_hidden, out_len, p="ltsf.decoder."):
@@ -275,12 +307,12 @@ def ltsf_decoder(sd, enc, poly_emb, final_hidden, out_len, p="ltsf.decoder."):
     dec = torch.einsum("cot,bct->bco", W, enc - last) + Bv[None] + last
     dec = dec + linear(poly_emb, sd[p + "lane_fc.weight"], sd[p + "lane_fc.bias"]).view(B, C, out_len)
     if p + "post_mlp.0.weight" in sd:                                       # replaces, no residual (787-791)
-        h = torch.relu(linear(dec.reshape(B, -1), sd[p + "post_mlp.0.weight"], sd[p + "post_mlp.0.bias"]))
+        h = _D(torch.relu(linear(dec.reshape(B, -1), sd[p + "post_mlp.0.weight"], sd[p + "post_mlp.0.bias"])), "dec", 0, "post")
         dec = linear(h, sd[p + "post_mlp.3.weight"], sd[p + "post_mlp.3.bias"]).view(B, C, out_len)
     dec_t = dec.permute(0, 2, 1)                                            # (B,T_out,C)
     q = linear(dec_t, sd[p + "dec_proj.weight"], sd[p + "dec_proj.bias"])
     cross = mha(q, final_hidden, final_hidden, sd[p + "cross_attn.in_proj_weight"], sd[p + "cross_attn.in_proj_bias"],
-                sd[p + "cross_attn.out_proj.weight"], sd[p + "cross_attn.out_proj.bias"], 2)   # no key mask (798)
+                sd[p + "cross_attn.out_proj.weight"], sd[p + "cross_attn.out_proj.bias"], 2, site=("dec", 0, "cross_attn"))   # no key mask (798)
     fused = dec_t + linear(cross, sd[p + "dec_unproj.weight"], sd[p + "dec_unproj.bias"])
     f = layer_norm(fused, sd[p + "fusion_layer.0.weight"], sd[p + "fusion_layer.0.bias"])
     f = linear(torch.relu(linear(f, sd[p + "fusion_layer.1.weight"], sd[p + "fusion_layer.1.bias"])),

@@ -82,3 +82,55 @@ def test_restated_gradients_match_reference_autograd(name):
     for k, want in fix["grads"].items():
         ref_scale = float((want["full"] if "full" in want else want["head"]).abs().max()) + 1e-8
         _check_against_compressed(grads[k], want, rtol=2e-3, atol=2e-4 * ref_scale + 1e-6, key=k)
+
+
+@pytest.mark.parametrize("name", ["tiny_b5_grads_drop", "cfg1_b3_grads_drop"])
+def test_restated_train_mode_dropout_matches_reference(name):
+    """Train mode: the restatement with oracle/dropout.py's masks at its dropout sites == the UNMODIFIED reference in train() mode with
+    the same masks substituted for torch's RNG (fixture minted through patch_reference_dropout, which also checks that the reference
+    makes exactly the dropout calls reference_call_sequence lists, in that order)."""
+    from oracle import dropout as OD
+    fix = load_golden(name)
+    m = T.MultiModalTrajectoryModel(**fix["model_cfg"])
+    sd = m.state_dict()
+    T.deterministic_fill_(sd, fix["weight_seed"])
+    i = fix["inputs"]
+    orc = OD.DropOracle(fix["dropout"]["seed"], fix["dropout"]["step"], OD.default_probs(fix["model_cfg"]))
+    with restated.dropout(orc):
+        loss, decoded, grads = restated.loss_and_grads(sd, fix["model_cfg"], fix["llama_cfg"], i["x"], i["vision"], i["polygon"], i["poly_len"],
+                                                       i["input_ids"], i["attention_mask"], i["y"], i["norm_stat"])
+    assert restated.DROP is None
+    torch.testing.assert_close(loss, fix["loss"], rtol=1e-5, atol=0)
+    torch.testing.assert_close(decoded, fix["decoded"], rtol=1e-4, atol=1e-5)
+    lc = fix["llama_cfg"]
+    assert len(orc.used) == len(OD.reference_call_sequence(fix["model_cfg"], lc["num_hidden_layers"]))
+    for k, want in fix["grads"].items():
+        ref_scale = float((want["full"] if "full" in want else want["head"]).abs().max()) + 1e-8
+        _check_against_compressed(grads[k], want, rtol=2e-3, atol=2e-4 * ref_scale + 1e-6, key=k)
+    # and it is a different function from the eval-mode one
+    eval_loss = load_golden(name.replace("_drop", ""))["loss"]
+    assert abs(float(loss) - float(eval_loss)) > 1e-3 * float(eval_loss)
+
+
+def test_dropout_mask_function_and_site_table():
+    """The host restatement of the mask function: keep rate, independence across sites / steps, 64-bit indices; and the site-id table
+    of the product (train_engine.py) is the one the oracle uses."""
+    import numpy as np
+    from oracle import dropout as OD
+    from tcavp_b200 import ops, train_engine as TE
+    assert TE.MOD == OD.MOD and TE.KIND == OD.KIND
+    assert TE.site_id("qdec", 3, "ca_attn") == OD.site_id("qdec", 3, "ca_attn") == (3 << 20) | (3 << 8) | 4
+    assert ops.drop_threshold(0.1) == OD.drop_threshold(0.1) == 429496730 and ops.drop_threshold(0.0) == 0
+    n = 1 << 20
+    a = OD.keep_mask(5, 0, OD.site_id("llm", 0, "lora_q"), 0.1, n)
+    assert abs(a.mean() - 0.9) < 2e-3
+    b = OD.keep_mask(5, 0, OD.site_id("llm", 0, "lora_v"), 0.1, n)
+    c = OD.keep_mask(5, 1, OD.site_id("llm", 0, "lora_q"), 0.1, n)
+    for other in (b, c):
+        assert abs((a & other).mean() - 0.81) < 3e-3                      # independent draws
+    assert OD.keep_mask(5, 0, 7, 0.0, 1000).all() and not OD.keep_mask(5, 0, 7, 0.999999, 1000).all()
+    assert np.array_equal(a[:4096], OD.keep_mask(5, 0, OD.site_id("llm", 0, "lora_q"), 0.1, 4096))     # a pure function of the index
+    # lag-1 / row-structured correlations of consecutive indices stay at the noise floor
+    x = a.astype(np.float64) - a.mean()
+    for lag in (1, 2, 64, 768, 4096):
+        assert abs((x[:-lag] * x[lag:]).mean() / x.var()) < 5e-3, lag

@@ -1,6 +1,7 @@
 """Fine-tune step parity: gradients of every trainable tensor from the hand-written CUDA backward
 against (a) the golden gradients minted from the unmodified reference and (b) autograd through the CPU oracle on the same
-inputs.  Dropout is 0 on both sides (reference scripts/im_kim_train_GRN.py:1029-1040 semantics otherwise)."""
+inputs.  These fixtures run in eval mode (every dropout off, reference scripts/im_kim_train_GRN.py:1029-1040 semantics otherwise);
+train mode with the reference's dropout at every site is tests/test_dropout_gpu.py."""
 import pytest
 import torch
 
@@ -34,7 +35,9 @@ def _model(fix, dtype, frozen_mllm=False):
     if frozen_mllm:                                     # reference scripts/train.py:1141-1142
         for p in m.mllm.parameters():
             p.requires_grad_(False)
-    return m.to("cuda").train()
+    # p = 0 goldens were minted in eval mode (every dropout off, autograd on); `*_drop` goldens in train() mode
+    m = m.to("cuda")
+    return m.train() if fix.get("dropout") else m.eval()
 
 
 def _step(m, i):

@@ -23,7 +23,7 @@ sel = slice(rank * 2, rank * 2 + 2)
 def model():
     m = T.MultiModalTrajectoryModel(**fix["model_cfg"], compute_dtype="fp32")
     sd = m.state_dict(); T.deterministic_fill_(sd, fix["weight_seed"]); m.load_state_dict(sd, strict=True)
-    return m.cuda().train()
+    return m.cuda().eval()      # deterministic comparison: every dropout off (train mode draws rank-dependent masks)
 
 
 def batch(s):

@@ -50,6 +50,12 @@ class FineTuner:
         self.max_graphs = max_graphs
         self.captures = 0
         self.launches_per_step = 0    # libtcavp launches of one forward + backward (captured launches are replayed, not re-counted)
+        # train() mode applies the reference's dropout at every site (counter-based masks; the step counter lives on the device and is
+        # advanced inside the captured graph).  Ranks draw different masks, as DDP ranks with different RNG offsets do.
+        self.dropout_active = model.dropout_active()
+        if self.dropout_active:
+            rank = dist.get_rank(group) if dist.is_initialized() else 0
+            model.set_dropout_seed((torch.initial_seed() + 7919 * rank) & 0x7FFFFFFF, 0)
 
     @property
     def payload_bytes(self):

@@ -20,7 +20,7 @@ EXPORTS = [
     "tcavp_last_error", "tcavp_version", "tcavp_device_info", "tcavp_launch_count", "tcavp_clock_probe", "tcavp_gemm_tile_order", "tcavp_gemm", "tcavp_attention",
     "tcavp_layernorm", "tcavp_rmsnorm", "tcavp_row_rstd", "tcavp_rope", "tcavp_rope_table", "tcavp_embed_text", "tcavp_add_rowvec",
     "tcavp_cast", "tcavp_split_bf16x3", "tcavp_poly_embed", "tcavp_masked_mean", "tcavp_ltsf_encode", "tcavp_nlinear_decode",
-    "tcavp_fusion_head", "tcavp_traj_metrics", "tcavp_best_of_k",
+    "tcavp_fusion_head", "tcavp_traj_metrics", "tcavp_best_of_k", "tcavp_dropout",
     # fine-tune step
     "tcavp_transpose", "tcavp_period_sum", "tcavp_relu_bwd", "tcavp_axpby", "tcavp_swiglu", "tcavp_swiglu_bwd", "tcavp_layernorm_bwd",
     "tcavp_rmsnorm_bwd", "tcavp_rope_adjacent", "tcavp_copy_rows", "tcavp_masked_mean_bwd", "tcavp_nlinear_bwd", "tcavp_head_assemble",

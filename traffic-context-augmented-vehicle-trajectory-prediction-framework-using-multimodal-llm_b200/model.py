@@ -9,8 +9,6 @@ import math
 import torch
 import torch.nn as nn
 
-import warnings
-
 from . import ops
 from .config import resolve_llama
 from .engine import Engine
@@ -236,8 +234,10 @@ class SelfAttentionBlock(nn.Module):
         self.nhead = nhead
         self.norm1 = nn.LayerNorm(embed_dim)
         self.mha = nn.MultiheadAttention(embed_dim, num_heads=nhead, dropout=dropout_rate)
+        self.dropout1 = nn.Dropout(dropout_rate)
         self.ffn = nn.Sequential(nn.Linear(embed_dim, embed_dim * 4), nn.ReLU(), nn.Dropout(dropout_rate),
                                  nn.Linear(embed_dim * 4, embed_dim))
+        self.dropout2 = nn.Dropout(dropout_rate)
         self.norm2 = nn.LayerNorm(embed_dim)
 
 
@@ -333,7 +333,6 @@ class MultiModalTrajectoryModel(nn.Module):
         self._engine_sig = None
         self._train_engine = None
         self._train_sig = None
-        self._warned_dropout = False
         self._register_load_state_dict_pre_hook(self._translate_keys)
         self.mllm._register_load_state_dict_pre_hook(self._translate_mllm_keys_hook)
         self._register_state_dict_hook(self._variant_keys)
@@ -453,6 +452,14 @@ class MultiModalTrajectoryModel(nn.Module):
             input_ids, attention_mask = enc["input_ids"], enc["attention_mask"]
         if torch.is_grad_enabled() and y is not None and norm_stat is not None and any(p.requires_grad for p in self.parameters()):
             return self._train_step(x, vision_embs, lane_polygon_batch, lane_polygon_len, y, norm_stat, input_ids, attention_mask)
+        if self.training and self.dropout_active():
+            # train() mode without a gradient (the reference's best-of-K evaluation: `with torch.no_grad(): model.train()`, test.py:1308-1338):
+            # one stochastic pass — every dropout site of the reference draws a fresh mask
+            out = self.train_engine().train_forward(x=x, vision=vision_embs, polygon=lane_polygon_batch, poly_len=lane_polygon_len,
+                                                    input_ids=input_ids, attention_mask=attention_mask, y=y, norm_stat=norm_stat, keep=False)
+            if y is not None and norm_stat is not None:
+                return out["loss"], out["decoded"]
+            return out["decoded"]
         eng = self.engine()
         out = eng.forward(x, vision_embs, lane_polygon_batch, lane_polygon_len, input_ids, attention_mask, y=y, norm_stat=norm_stat)
         if y is not None and norm_stat is not None:
@@ -474,11 +481,46 @@ class MultiModalTrajectoryModel(nn.Module):
             self._train_sig = sig
         return self._train_engine
 
+    # ---- dropout (train mode) --------------------------------------------------------------------------
+    def dropout_active(self):
+        """True when a train-mode pass would drop anything (model.training and some site with p > 0)."""
+        return self.training and any(p > 0.0 for p in self.train_engine()._dropout_probs().values())
+
+    def set_dropout_seed(self, seed, step=0):
+        """Masks are a pure function of (seed, step, site, element): the next train-mode pass uses (seed, step), the one after it
+        step + 1, ...  Without a call the base seed is torch.initial_seed()."""
+        self.train_engine().set_dropout_seed(seed, step)
+        return self
+
+    def set_dropout(self, p):
+        """Sets every dropout probability of the model (lora_dropout, ltsf_dropout and the nn.Transformer layers' default 0.1) to `p`."""
+        for m in self.modules():
+            if isinstance(m, nn.Dropout):
+                m.p = float(p)
+            elif isinstance(m, nn.MultiheadAttention):
+                m.dropout = float(p)
+            elif isinstance(m, LoraLinearW):
+                m.lora_dropout_p = float(p)
+        return self
+
+    @torch.no_grad()
+    def best_of_k(self, x, vision_embs, lane_polygon_batch, lane_polygon_len, y, norm_stat, input_ids, attention_mask, num_candidates=10):
+        """The reference's best-of-K evaluation of one batch (scripts/test.py:1308-1368): `num_candidates` stochastic passes in train()
+        mode without gradients, then min-over-candidates ADE / FDE / RMSE per scene.  Returns best_of_k_metrics' dict plus the
+        candidates (B, K, 2, T_out)."""
+        was = self.training
+        self.train()
+        try:
+            cands = [self(x, vision_embs, None, lane_polygon_batch, lane_polygon_len, input_ids=input_ids, attention_mask=attention_mask)
+                     for _ in range(num_candidates)]
+        finally:
+            self.train(was)
+        c = torch.stack(cands, dim=1)
+        out = self.best_of_k_metrics(c, y, norm_stat)
+        out["candidates"] = c
+        return out
+
     def _train_step(self, x, vision_embs, lane_polygon_batch, lane_polygon_len, y, norm_stat, input_ids, attention_mask):
-        if self.training and not self._warned_dropout:
-            self._warned_dropout = True
-            warnings.warn("tcavp_b200: dropout (lora_dropout / ltsf_dropout / nn.Transformer dropout) is not applied in the fine-tune "
-                          "step; gradients match the reference with every dropout p = 0")
         eng = self.train_engine()
         inputs = dict(x=x, vision=vision_embs, polygon=lane_polygon_batch, poly_len=lane_polygon_len, input_ids=input_ids,
                       attention_mask=attention_mask, y=y, norm_stat=norm_stat)

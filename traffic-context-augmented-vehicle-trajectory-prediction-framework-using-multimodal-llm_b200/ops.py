@@ -3,7 +3,7 @@
 torch is used for device memory and streams only: every function here hands raw device pointers to
 libtcavp.so and raises TcavpError on a non-zero return code.  Nothing falls back to torch math."""
 import ctypes
-from ctypes import POINTER, Structure, byref, c_float, c_int, c_longlong, c_void_p
+from ctypes import POINTER, Structure, byref, c_float, c_int, c_longlong, c_uint32, c_void_p
 
 import torch
 
@@ -36,7 +36,33 @@ class AttnArgs(Structure):
                 ("k", c_void_p), ("k_sb", c_longlong), ("k_st", c_longlong),
                 ("v", c_void_p), ("v_sb", c_longlong), ("v_st", c_longlong),
                 ("out", c_void_p), ("o_sb", c_longlong), ("o_st", c_longlong),
-                ("dtype", c_int), ("scale", c_float), ("causal", c_int), ("key_mask", c_void_p)]
+                ("dtype", c_int), ("scale", c_float), ("causal", c_int), ("key_mask", c_void_p),
+                ("drop_seed", c_void_p), ("drop_site", c_uint32), ("drop_thresh", c_uint32), ("drop_scale", c_float)]
+
+
+class Drop:
+    """One dropout site of a train-mode pass: (device seed tensor uint32[2], site id, p).  The mask is a pure function of
+    (seed, site, element index) — include/tcavp.h: tcavp_dropout — so the backward pass re-creates it from the same Drop."""
+    __slots__ = ("seed", "site", "p", "thresh", "scale")
+
+    def __init__(self, seed, site, p):
+        if seed.dtype != torch.int32 or seed.numel() != 2 or not seed.is_cuda:
+            raise TypeError("Drop: seed must be a CUDA int32[2] tensor (base seed, step counter)")
+        if not 0.0 <= p < 1.0:
+            raise ValueError(f"dropout p = {p}")
+        self.seed, self.site, self.p = seed, int(site), float(p)
+        self.thresh = drop_threshold(p)
+        self.scale = 1.0 / (1.0 - p)
+
+
+def drop_threshold(p):
+    """uint32 threshold of the mask function: an element is kept when its 32-bit hash >= thresh, P(drop) = thresh / 2^32."""
+    return min(max(int(round(float(p) * 4294967296.0)), 0), 4294967295)
+
+
+def _set_drop(a, drop):
+    if drop is not None and drop.thresh:
+        a.drop_seed, a.drop_site, a.drop_thresh, a.drop_scale = drop.seed.data_ptr(), drop.site, drop.thresh, drop.scale
 
 
 _PROF = None
@@ -184,7 +210,7 @@ def gemm(a, w, out, *, M=None, N=None, K=None, lda=None, ldw=None, ldo=None, bia
 
 
 def attention(q, k, v, out, *, B, H, Hkv, Tq, Tk, dh, q_strides, k_strides, v_strides, o_strides, scale, causal=False,
-              key_mask=None):
+              key_mask=None, drop=None):
     """q/k/v/out are tensors whose data_ptr() is element (0,0,0,0); *_strides = (batch stride, time stride) in elements."""
     _need_cuda(q, k, v, out, key_mask)
     a = AttnArgs()
@@ -198,7 +224,10 @@ def attention(q, k, v, out, *, B, H, Hkv, Tq, Tk, dh, q_strides, k_strides, v_st
         if key_mask.dtype != torch.int32:
             raise TypeError("attention: key_mask must be int32")
         a.key_mask = key_mask.data_ptr()
-    if a.dtype == BF16 and dh in (16, 32, 64, 96, 128) and max(Tq, Tk) <= 256:
+    _set_drop(a, drop)
+    if a.drop_thresh:
+        kern = f"attn_{'row' if dh in (16, 32) and Tk <= 128 else 'warp'}_kernel[dropout,dh{dh},q{Tq},k{Tk}]"
+    elif a.dtype == BF16 and dh in (16, 32, 64, 96, 128) and max(Tq, Tk) <= 256:
         kern = f"attn_flash_kernel[dh{dh},q{Tq},k{Tk}]"
     elif a.dtype == BF16 and dh > 128 and dh % 64 == 0 and Tq <= 64 and Tk <= 256 and not causal:
         kern = "attn_x_kernel"
@@ -354,6 +383,19 @@ def best_of_k(candidates, y, norm_stat, per_scene, totals, *, B, K, T_out):
     return per_scene, totals
 
 
+def dropout(x, out, drop, *, rows, cols, ldi=None, ldo=None, residual=None, ldr=None, accumulate=False, scale=None):
+    """out = [out +] [residual +] (keep ? x * scale : 0) with the counter-based mask of `drop` (tcavp_dropout); scale defaults to
+    1 / (1 - p); x is out is allowed.  The same call on a gradient is the backward pass."""
+    _need_cuda(x, out, residual)
+    with _Timed("dropout_kernel", 0.0, float(rows * cols * (x.element_size() + out.element_size() * (2 if accumulate else 1) +
+                                                             (residual.element_size() if residual is not None else 0)))):
+        _lib.check(_lib.load().tcavp_dropout(_p(x), cols if ldi is None else ldi, dt(x), _p(residual), (cols if ldr is None else ldr),
+                                             0 if residual is None else dt(residual), _p(out), cols if ldo is None else ldo, dt(out),
+                                             c_longlong(rows), cols, _p(drop.seed), c_uint32(drop.site), c_uint32(drop.thresh),
+                                             c_float(drop.scale if scale is None else scale), int(accumulate), _stream()), "tcavp_dropout")
+    return out
+
+
 def launch_count():
     return int(_lib.load().tcavp_launch_count())
 
@@ -496,7 +538,7 @@ def dw(dy, x, out, *, M, N, K, lddy=None, ldx=None, ldo=None):
 
 
 def attention_bwd(q, k, v, dout, dq, dk, dv, *, B, H, Hkv, Tq, Tk, dh, q_strides, k_strides, v_strides, do_strides, dq_strides,
-                  dk_strides, dv_strides, scale, causal=False, key_mask=None, o=None, o_strides=None):
+                  dk_strides, dv_strides, scale, causal=False, key_mask=None, o=None, o_strides=None, drop=None):
     """dk / dv: fp32 accumulators (zeroed by the caller).  o = the forward output (enables the tensor-core kernel)."""
     _need_cuda(q, k, v, dout, dq, dk, dv, key_mask, o)
     if dk.dtype != torch.float32 or dv.dtype != torch.float32:
@@ -509,10 +551,11 @@ def attention_bwd(q, k, v, dout, dq, dk, dv, *, B, H, Hkv, Tq, Tk, dh, q_strides
     a.dtype, a.scale, a.causal = dt(q), scale, int(causal)
     if key_mask is not None:
         a.key_mask = key_mask.data_ptr()
+    _set_drop(a, drop)
     tc = False
     if o is not None:
         a.out, (a.o_sb, a.o_st) = o.data_ptr(), o_strides
-        tc = a.dtype == BF16 and H == Hkv and dh in (16, 32, 64, 96, 128) and max(Tq, Tk) <= 256
+        tc = a.dtype == BF16 and H == Hkv and dh in (16, 32, 64, 96, 128) and max(Tq, Tk) <= 256 and not a.drop_thresh
     fl = 10.0 * B * H * Tq * Tk * dh * (0.5 if causal else 1.0)
     with _Timed(f"attn_bwd_{'tc_' if tc else ''}kernel[dh{dh},q{Tq},k{Tk}]", fl, 0.0):
         _lib.check(_lib.load().tcavp_attention_bwd(byref(a), _p(dout), _ll(do_strides[0]), _ll(do_strides[1]), _p(dq), _ll(dq_strides[0]),

@@ -10,7 +10,9 @@ inference engine (new buffers per block instead of in-place reuse, so every acti
   * attention / LayerNorm / RMSNorm / SwiGLU / RoPE / NLinear / masked-mean / head backward kernels.
 Gradients are produced in the reference's state_dict layout (fp32) and handed to torch through ONE autograd.Function
 (model.py), so `loss.backward(); optimizer.step()` and DistributedDataParallel hooks work unchanged.
-Dropout is treated as p = 0 (gradient parity with the reference is only defined there)."""
+Dropout (train mode, every site of the reference: lora_dropout, ltsf_dropout, the nn.Transformer layers' 0.1) uses the counter-based
+mask of tcavp_dropout — a pure function of (seed, site, element) that the backward pass re-creates, nothing is stored — see
+`DropPlan`.  With `model.eval()` or every p = 0 the step is the deterministic one the p = 0 goldens pin."""
 import math
 
 import torch
@@ -21,6 +23,40 @@ from .engine import Engine, _Lin, _f32
 
 def _pad8(n):
     return (n + 7) // 8 * 8
+
+
+# ---- dropout sites ------------------------------------------------------------------------------------------------------
+# site id = module << 20 | layer << 8 | kind.  The oracle (oracle/dropout.py) derives the same ids from the ORDER in which the
+# reference's forward calls F.dropout / scaled_dot_product_attention, so masks are bit-identical on both sides.
+MOD = dict(poly=1, qenc=2, qdec=3, llm=4, ltsf=5, dec=6)
+KIND = dict(sa_attn=0, drop1=1, ffn=2, drop2=3, ca_attn=4, drop3=5, post=6, cross_attn=7, lora_q=8, lora_k=9, lora_v=10)
+
+
+def site_id(mod, layer, kind):
+    return (MOD[mod] << 20) | (layer << 8) | KIND[kind]
+
+
+class DropPlan:
+    """The dropout sites of ONE train-mode forward pass: `plan(mod, layer, kind)` -> ops.Drop or None (p = 0 / eval mode).
+    All sites share one device seed tensor that is private to the pass, so the backward pass regenerates the same masks even if
+    another forward ran in between."""
+
+    def __init__(self, seed, probs):
+        self.seed, self.probs = seed, probs
+        self._cache = {}
+
+    def __call__(self, mod, layer, kind):
+        p = self.probs.get((mod, kind), 0.0) if self.seed is not None else 0.0
+        if p <= 0.0:
+            return None
+        key = (mod, layer, kind)
+        if key not in self._cache:
+            self._cache[key] = ops.Drop(self.seed, site_id(mod, layer, kind), p)
+        return self._cache[key]
+
+    @property
+    def active(self):
+        return self.seed is not None and any(p > 0.0 for p in self.probs.values())
 
 
 class TrainEngine(Engine):
@@ -34,6 +70,9 @@ class TrainEngine(Engine):
         self._flags()
         self._bwd_packed = False
         self._names()
+        self._seed_state = None       # CUDA int32[2]: (base seed, step counter); bumped on the device after every train-mode forward
+        self._seed_inc = None
+        self.drop = DropPlan(None, {})
 
     # ---- bookkeeping --------------------------------------------------------------------------------
     def _flags(self):
@@ -51,6 +90,72 @@ class TrainEngine(Engine):
         self.params = self.model.trainable_named_parameters()
         wrap = self.model.mllm.llama_wrapper
         self.llm_prefix = "mllm.llama_wrapper.llama_model." + ("base_model.model." if wrap.use_lora else "") + "model.layers."
+
+    # ---- dropout plumbing -----------------------------------------------------------------------------
+    def set_dropout_seed(self, base, step=0):
+        """The next train-mode forward draws its masks from (base, step); every forward after it from step + 1, + 2, ..."""
+        if self.dev.type != "cuda":
+            raise ops._lib.TcavpError("dropout needs the model on a CUDA device")
+        v = torch.tensor([int(base) & 0x7FFFFFFF, int(step) & 0x7FFFFFFF], dtype=torch.int32)
+        if self._seed_state is None:
+            self._seed_state = v.to(self.dev)
+            self._seed_inc = torch.tensor([0, 1], dtype=torch.int32, device=self.dev)
+        else:
+            self._seed_state.copy_(v)
+
+    def _dropout_probs(self):
+        """p of every site, read from the container modules (the reference passes lora_dropout / ltsf_dropout to its constructors,
+        train.py:432-440, 663-671, 745-754; nn.TransformerEncoderLayer / DecoderLayer keep torch's default 0.1, train.py:358, 402-405)."""
+        m = self.model
+        pr = {}
+
+        def tl(mod, layers, dec=False):
+            if len(layers) == 0:
+                return
+            l = layers[0]
+            pr[(mod, "sa_attn")], pr[(mod, "drop1")] = float(l.self_attn.dropout), float(l.dropout1.p)
+            pr[(mod, "ffn")], pr[(mod, "drop2")] = float(l.dropout.p), float(l.dropout2.p)
+            if dec:
+                pr[(mod, "ca_attn")], pr[(mod, "drop3")] = float(l.multihead_attn.dropout), float(l.dropout3.p)
+        tl("poly", m.lane_polygon_encoder.encoder.layers)
+        tl("qenc", m.mllm.qformer.encoder.layers)
+        tl("qdec", m.mllm.qformer.decoder.layers, dec=True)
+        ab = m.ltsf.attn_block
+        pr[("ltsf", "sa_attn")] = float(ab.mha.dropout)
+        pr[("ltsf", "drop1")], pr[("ltsf", "ffn")], pr[("ltsf", "drop2")] = float(ab.dropout1.p), float(ab.ffn[2].p), float(ab.dropout2.p)
+        d = m.ltsf.decoder
+        pr[("dec", "cross_attn")] = float(d.cross_attn.dropout)
+        if d.use_post_mlp:
+            pr[("dec", "post")] = float(d.post_mlp[2].p)
+        wrap = m.mllm.llama_wrapper
+        if wrap.use_lora:
+            layer0 = wrap.causal_lm().model.layers[0].self_attn
+            for t in wrap.llama_model.targets:
+                pr[("llm", "lora_" + t[0])] = float(getattr(layer0, t).lora_dropout_p)
+        return pr
+
+    def _begin_pass(self):
+        """Builds the DropPlan of this forward: active only in train mode with some p > 0; the pass gets a private copy of the seed."""
+        probs = self._dropout_probs() if self.model.training else {}
+        if not any(p > 0.0 for p in probs.values()):
+            self.drop = DropPlan(None, {})
+            return
+        if self._seed_state is None:
+            self.set_dropout_seed(torch.initial_seed() & 0x7FFFFFFF, 0)
+        seed = self._seed_state.clone()
+        self._seed_state.add_(self._seed_inc)         # device-side: a captured CUDA graph advances the step on every replay
+        self.drop = DropPlan(seed, probs)
+
+    def _drop_res(self, t, drop, residual):
+        """residual + dropout(t), in place on t (the sub-layer output is not needed un-dropped)."""
+        return ops.dropout(t, t, drop, rows=t.shape[0], cols=t.shape[1], ldi=t.stride(0), ldo=t.stride(0), residual=residual,
+                           ldr=None if residual is None else residual.stride(0))
+
+    def _drop_grad(self, dy, drop):
+        """Gradient through a dropout site: the same mask and scale on a copy of dy (dy itself still feeds the residual branch)."""
+        if drop is None:
+            return dy
+        return ops.dropout(dy, self._new(*dy.shape, dtype=dy.dtype), drop, rows=dy.shape[0], cols=dy.shape[1], ldi=dy.stride(0))
 
     @torch.no_grad()
     def sync_params(self):
@@ -92,6 +197,28 @@ class TrainEngine(Engine):
             if "wqkvT" in ly:
                 ly["wqkvT"][H:, :] = ext.t().to(self.act)
             ly["a_catT"] = ly["a_cat"].t().contiguous()
+            # lora_dropout (peft lora.Linear: lora_A(dropout(x)), train.py:432-440): every target sees its own mask of the normalised input,
+            # so the side product is one masked copy + one skinny GEMM per target.  The masked copy is exact (x or 0); the 1 / (1 - p)
+            # factor rides on the per-target weight ([A'_t ; 0] rows of the other targets zeroed, so the GEMMs accumulate).
+            ly.pop("a_cat_t", None)
+            drops = self._lora_drops(0)
+            if drops:
+                ly["a_cat_t"], ly["a_catT_t"] = [], []
+                for ti, d in enumerate(drops):
+                    w = torch.zeros_like(ly["a_cat"])
+                    w[ti * r:(ti + 1) * r] = (ly["a_cat"][ti * r:(ti + 1) * r].float() * d.scale).to(self.act)
+                    ly["a_cat_t"].append(w)
+                    ly["a_catT_t"].append(w.t().contiguous())
+
+    def _lora_drops(self, li):
+        """[ops.Drop per LoRA target] of decoder layer `li`, or None when lora_dropout is inactive."""
+        L = self.llm
+        if not L["kx"] or not self.drop.active:
+            return None
+        ds = [self.drop("llm", li, "lora_" + t[0]) for t in L["targets"]]
+        if all(d is None for d in ds):
+            return None
+        return [d if d is not None else ops.Drop(self.drop.seed, site_id("llm", li, "lora_" + t[0]), 0.0) for d, t in zip(ds, L["targets"])]
 
     def _g(self, name, shape):
         """Zero-initialised fp32 gradient buffer for reference parameter `name`.  When the caller registered a target view for
@@ -155,9 +282,9 @@ class TrainEngine(Engine):
 
     # ---- attention backward into packed gradient buffers ------------------------------------------------
     def _attn_bwd(self, q, k, v, do, *, B, H, Hkv, Tq, Tk, dh, qs, ks, vs, dos, dq, dqs, dk_out, dv_out, ld_kv, scale, causal=False,
-                  key_mask=None, o=None):
+                  key_mask=None, o=None, drop=None):
         """dq is written in place (strides dqs); dk / dv are accumulated in fp32 and cast into dk_out / dv_out (row stride ld_kv)."""
-        if ops.attention_bwd_owned_ok(q, H=H, Hkv=Hkv, Tq=Tq, Tk=Tk, dh=dh, o=o, causal=causal):
+        if drop is None and ops.attention_bwd_owned_ok(q, H=H, Hkv=Hkv, Tq=Tq, Tk=Tk, dh=dh, o=o, causal=causal):
             # one CTA owns all key rows of a head: dk / dv land directly in the packed gradient buffer (no fp32 staging, no casts)
             kvs = (Tk * ld_kv, ld_kv)
             ops.attention_bwd_owned(q, k, v, do, dq, dk_out, dv_out, B=B, H=H, Tq=Tq, Tk=Tk, dh=dh, q_strides=qs, k_strides=ks, v_strides=vs,
@@ -169,48 +296,50 @@ class TrainEngine(Engine):
         dv = torch.zeros(B * Tk, wk, dtype=torch.float32, device=self.dev)
         ops.attention_bwd(q, k, v, do, dq, dk, dv, B=B, H=H, Hkv=Hkv, Tq=Tq, Tk=Tk, dh=dh, q_strides=qs, k_strides=ks, v_strides=vs,
                           do_strides=dos, dq_strides=dqs, dk_strides=(Tk * wk, wk), dv_strides=(Tk * wk, wk), scale=scale, causal=causal,
-                          key_mask=key_mask, o=o, o_strides=dos)
+                          key_mask=key_mask, o=o, o_strides=dos, drop=drop)
         ops.cast(dk, dk_out, rows=B * Tk, cols=wk, ldo=ld_kv)
         ops.cast(dv, dv_out, rows=B * Tk, cols=wk, ldo=ld_kv)
 
-    def _self_attn_fwd(self, x, T, B, mha, key_mask=None):
+    def _self_attn_fwd(self, x, T, B, mha, key_mask=None, drop=None):
         E, heads = mha["E"], mha["heads"]
         qkv = ops.gemm(x, mha["qkv"].w, self._new(B * T, 3 * E, dtype=x.dtype), bias=mha["qkv"].b)
         a = self._new(B * T, E, dtype=x.dtype)
         dh = E // heads
         ops.attention(qkv, qkv[:, E:], qkv[:, 2 * E:], a, B=B, H=heads, Hkv=heads, Tq=T, Tk=T, dh=dh, q_strides=(T * 3 * E, 3 * E),
-                      k_strides=(T * 3 * E, 3 * E), v_strides=(T * 3 * E, 3 * E), o_strides=(T * E, E), scale=dh ** -0.5, key_mask=key_mask)
+                      k_strides=(T * 3 * E, 3 * E), v_strides=(T * 3 * E, 3 * E), o_strides=(T * E, E), scale=dh ** -0.5, key_mask=key_mask,
+                      drop=drop)
         return qkv, a
 
-    def _self_attn_bwd(self, da, qkv, x, T, B, mha, pre, key_mask=None, dx_residual=None, train=True, o=None):
+    def _self_attn_bwd(self, da, qkv, x, T, B, mha, pre, key_mask=None, dx_residual=None, train=True, o=None, drop=None):
         """-> dx (gradient w.r.t. the block input through the qkv projection, + dx_residual)."""
         E, heads = mha["E"], mha["heads"]
         dh = E // heads
         dqkv = self._new(B * T, 3 * E, dtype=qkv.dtype)
         s3 = (T * 3 * E, 3 * E)
         self._attn_bwd(qkv, qkv[:, E:], qkv[:, 2 * E:], da, B=B, H=heads, Hkv=heads, Tq=T, Tk=T, dh=dh, qs=s3, ks=s3, vs=s3, dos=(T * E, E),
-                       dq=dqkv, dqs=s3, dk_out=dqkv[:, E:], dv_out=dqkv[:, 2 * E:], ld_kv=3 * E, scale=dh ** -0.5, key_mask=key_mask, o=o)
+                       dq=dqkv, dqs=s3, dk_out=dqkv[:, E:], dv_out=dqkv[:, 2 * E:], ld_kv=3 * E, scale=dh ** -0.5, key_mask=key_mask, o=o,
+                       drop=drop)
         return self._lin_bwd(dqkv, x, mha["qkv"], pre + "in_proj_weight", pre + "in_proj_bias", dx_residual=dx_residual, train=train)
 
-    def _cross_attn_fwd(self, xq, Tq, mem, Tk, B, mha):
+    def _cross_attn_fwd(self, xq, Tq, mem, Tk, B, mha, drop=None):
         E, heads = mha["E"], mha["heads"]
         dh = E // heads
         q = ops.gemm(xq, mha["q"].w, self._new(B * Tq, E), bias=mha["q"].b)
         kv = ops.gemm(mem, mha["kv"].w, self._new(B * Tk, 2 * E), bias=mha["kv"].b)
         a = self._new(B * Tq, E)
         ops.attention(q, kv, kv[:, E:], a, B=B, H=heads, Hkv=heads, Tq=Tq, Tk=Tk, dh=dh, q_strides=(Tq * E, E), k_strides=(Tk * 2 * E, 2 * E),
-                      v_strides=(Tk * 2 * E, 2 * E), o_strides=(Tq * E, E), scale=dh ** -0.5)
+                      v_strides=(Tk * 2 * E, 2 * E), o_strides=(Tq * E, E), scale=dh ** -0.5, drop=drop)
         return q, kv, a
 
     def _cross_attn_bwd(self, da, q, kv, xq, Tq, mem, Tk, B, mha, pre, *, need_dmem=True, dmem_residual=None, dxq_residual=None, train=True,
-                        o=None):
+                        o=None, drop=None):
         E, heads = mha["E"], mha["heads"]
         dh = E // heads
         dq = self._new(B * Tq, E, dtype=q.dtype)
         dkv = self._new(B * Tk, 2 * E, dtype=kv.dtype)
         s2 = (Tk * 2 * E, 2 * E)
         self._attn_bwd(q, kv, kv[:, E:], da, B=B, H=heads, Hkv=heads, Tq=Tq, Tk=Tk, dh=dh, qs=(Tq * E, E), ks=s2, vs=s2, dos=(Tq * E, E),
-                       dq=dq, dqs=(Tq * E, E), dk_out=dkv, dv_out=dkv[:, E:], ld_kv=2 * E, scale=dh ** -0.5, o=o)
+                       dq=dq, dqs=(Tq * E, E), dk_out=dkv, dv_out=dkv[:, E:], ld_kv=2 * E, scale=dh ** -0.5, o=o, drop=drop)
         dw = db = None
         if train:
             dw, db = self._g(pre + "in_proj_weight", (3 * E, E)), self._g(pre + "in_proj_bias", (3 * E,))
@@ -221,51 +350,76 @@ class TrainEngine(Engine):
         return dxq, dmem
 
     # ---- post-norm transformer layers (torch nn.TransformerEncoderLayer / DecoderLayer) ------------------
-    def _enc_fwd(self, x, T, B, L, key_mask=None, sa_f32=None):
+    # torch: x = norm1(x + dropout1(self_attn(x)));  x = norm2(x + dropout2(linear2(dropout(relu(linear1(x))))))   (+ the attention
+    # module's own dropout on the probabilities).  `mod` / `li` name the dropout sites (DropPlan); with no active site the residual
+    # add stays fused in the GEMM epilogue.
+    def _sub_out(self, a, lin, residual, drop, out_dtype=None):
+        """residual + dropout(a . W^T + b)"""
+        if drop is None:
+            return ops.gemm(a, lin.w, self._new(a.shape[0], lin.N, dtype=out_dtype or residual.dtype), bias=lin.b, residual=residual)
+        t = ops.gemm(a, lin.w, self._new(a.shape[0], lin.N, dtype=out_dtype or residual.dtype), bias=lin.b)
+        return self._drop_res(t, drop, residual)
+
+    def _enc_fwd(self, x, T, B, L, key_mask=None, sa_f32=None, mod=None, li=0):
+        D = (lambda kind: self.drop(mod, li, kind)) if mod else (lambda kind: None)
         sa = sa_f32 if sa_f32 is not None else L["sa"]
-        qkv, a = self._self_attn_fwd(x, T, B, sa, key_mask)
-        y1 = ops.gemm(a, sa["out"].w, self._new(*x.shape, dtype=x.dtype), bias=sa["out"].b, residual=x)
+        qkv, a = self._self_attn_fwd(x, T, B, sa, key_mask, drop=D("sa_attn"))
+        y1 = self._sub_out(a, sa["out"], x, D("drop1"))
         x1 = self._ln_res(y1, L["n1"], out=self._new(*x.shape))
         h = ops.gemm(x1, L["l1"].w, self._new(x.shape[0], L["l1"].N), bias=L["l1"].b, act=ops.ACT_RELU)
-        y2 = ops.gemm(h, L["l2"].w, self._new(*x.shape), bias=L["l2"].b, residual=x1)
+        if D("ffn") is not None:
+            self._drop_res(h, D("ffn"), None)
+        y2 = self._sub_out(h, L["l2"], x1, D("drop2"), out_dtype=self.act)
         x2 = self._ln_res(y2, L["n2"])
         return x2, (x, qkv, a, y1, x1, h, y2, sa)
 
-    def _enc_bwd(self, dx2, ctx, T, B, L, pre, key_mask=None, need_dx=True, train=True):
+    def _enc_bwd(self, dx2, ctx, T, B, L, pre, key_mask=None, need_dx=True, train=True, mod=None, li=0):
+        D = (lambda kind: self.drop(mod, li, kind)) if mod else (lambda kind: None)
         x, qkv, a, y1, x1, h, y2, sa = ctx
         dy2 = self._ln_bwd(dx2, y2, L["n2"], pre + "norm2.weight", pre + "norm2.bias", train=train)
-        dh = self._lin_bwd(dy2, h, L["l2"], pre + "linear2.weight", pre + "linear2.bias", train=train)
+        dh = self._lin_bwd(self._drop_grad(dy2, D("drop2")), h, L["l2"], pre + "linear2.weight", pre + "linear2.bias", train=train)
+        if D("ffn") is not None:          # h = dropout(relu(z)): h > 0 only where the unit was kept, so relu_bwd on the dropped h gates both
+            self._drop_res(dh, D("ffn"), None)
         dpre = self._relu_bwd(dh, h)
         dx1 = self._lin_bwd(dpre, x1, L["l1"], pre + "linear1.weight", pre + "linear1.bias", dx_residual=dy2, train=train)
         dy1 = self._ln_bwd(dx1, y1, L["n1"], pre + "norm1.weight", pre + "norm1.bias", train=train)
-        da = self._lin_bwd(dy1, a, sa["out"], pre + "self_attn.out_proj.weight", pre + "self_attn.out_proj.bias", train=train)
+        da = self._lin_bwd(self._drop_grad(dy1, D("drop1")), a, sa["out"], pre + "self_attn.out_proj.weight", pre + "self_attn.out_proj.bias",
+                           train=train)
         if not need_dx and not train:
             return None
-        return self._self_attn_bwd(da, qkv, x, T, B, sa, pre + "self_attn.", key_mask, dx_residual=dy1, train=train, o=a)
+        return self._self_attn_bwd(da, qkv, x, T, B, sa, pre + "self_attn.", key_mask, dx_residual=dy1, train=train, o=a, drop=D("sa_attn"))
 
-    def _dec_fwd(self, t, Q, mem, Tv, B, L):
-        qkv, a = self._self_attn_fwd(t, Q, B, L["sa"])
-        y1 = ops.gemm(a, L["sa"]["out"].w, self._new(*t.shape), bias=L["sa"]["out"].b, residual=t)
+    def _dec_fwd(self, t, Q, mem, Tv, B, L, li=0):
+        D = lambda kind: self.drop("qdec", li, kind)     # noqa: E731
+        qkv, a = self._self_attn_fwd(t, Q, B, L["sa"], drop=D("sa_attn"))
+        y1 = self._sub_out(a, L["sa"]["out"], t, D("drop1"))
         t1 = self._ln_res(y1, L["n1"])
-        q, kv, c = self._cross_attn_fwd(t1, Q, mem, Tv, B, L["ca"])
-        y2 = ops.gemm(c, L["ca"]["out"].w, self._new(*t.shape), bias=L["ca"]["out"].b, residual=t1)
+        q, kv, c = self._cross_attn_fwd(t1, Q, mem, Tv, B, L["ca"], drop=D("ca_attn"))
+        y2 = self._sub_out(c, L["ca"]["out"], t1, D("drop2"))
         t2 = self._ln_res(y2, L["n2"])
         h = ops.gemm(t2, L["l1"].w, self._new(t.shape[0], L["l1"].N), bias=L["l1"].b, act=ops.ACT_RELU)
-        y3 = ops.gemm(h, L["l2"].w, self._new(*t.shape), bias=L["l2"].b, residual=t2)
+        if D("ffn") is not None:
+            self._drop_res(h, D("ffn"), None)
+        y3 = self._sub_out(h, L["l2"], t2, D("drop3"))
         return y3, (t, qkv, a, y1, t1, q, kv, c, y2, t2, h)
 
-    def _dec_bwd(self, dy3, ctx, Q, mem, Tv, B, L, pre, dmem):
+    def _dec_bwd(self, dy3, ctx, Q, mem, Tv, B, L, pre, dmem, li=0):
         """dy3: gradient w.r.t. y3 (the input of norm3).  Returns (dt, dmem accumulated)."""
+        D = lambda kind: self.drop("qdec", li, kind)     # noqa: E731
         t, qkv, a, y1, t1, q, kv, c, y2, t2, h = ctx
-        dh = self._lin_bwd(dy3, h, L["l2"], pre + "linear2.weight", pre + "linear2.bias")
+        dh = self._lin_bwd(self._drop_grad(dy3, D("drop3")), h, L["l2"], pre + "linear2.weight", pre + "linear2.bias")
+        if D("ffn") is not None:
+            self._drop_res(dh, D("ffn"), None)
         dpre = self._relu_bwd(dh, h)
         dt2 = self._lin_bwd(dpre, t2, L["l1"], pre + "linear1.weight", pre + "linear1.bias", dx_residual=dy3)
         dy2 = self._ln_bwd(dt2, y2, L["n2"], pre + "norm2.weight", pre + "norm2.bias")
-        dc = self._lin_bwd(dy2, c, L["ca"]["out"], pre + "multihead_attn.out_proj.weight", pre + "multihead_attn.out_proj.bias")
-        dt1, dmem = self._cross_attn_bwd(dc, q, kv, t1, Q, mem, Tv, B, L["ca"], pre + "multihead_attn.", dmem_residual=dmem, dxq_residual=dy2, o=c)
+        dc = self._lin_bwd(self._drop_grad(dy2, D("drop2")), c, L["ca"]["out"], pre + "multihead_attn.out_proj.weight",
+                           pre + "multihead_attn.out_proj.bias")
+        dt1, dmem = self._cross_attn_bwd(dc, q, kv, t1, Q, mem, Tv, B, L["ca"], pre + "multihead_attn.", dmem_residual=dmem, dxq_residual=dy2, o=c,
+                                         drop=D("ca_attn"))
         dy1 = self._ln_bwd(dt1, y1, L["n1"], pre + "norm1.weight", pre + "norm1.bias")
-        da = self._lin_bwd(dy1, a, L["sa"]["out"], pre + "self_attn.out_proj.weight", pre + "self_attn.out_proj.bias")
-        dt = self._self_attn_bwd(da, qkv, t, Q, B, L["sa"], pre + "self_attn.", dx_residual=dy1, o=a)
+        da = self._lin_bwd(self._drop_grad(dy1, D("drop1")), a, L["sa"]["out"], pre + "self_attn.out_proj.weight", pre + "self_attn.out_proj.bias")
+        dt = self._self_attn_bwd(da, qkv, t, Q, B, L["sa"], pre + "self_attn.", dx_residual=dy1, o=a, drop=D("sa_attn"))
         return dt, dmem
 
     # ---- lane polygon encoder (reference scripts/train.py:362-383) ----------------------------------------
@@ -277,7 +431,7 @@ class TrainEngine(Engine):
         ops.poly_embed(polygon, lens, p["w"], p["b"], p["pos"], x0, kmask, B=B, P=P, D=D)
         x, ctxs = x0, []
         for i, L in enumerate(p["layers"]):
-            x, c = self._enc_fwd(x, P, B, L, kmask, sa_f32=p["sa0_f32"] if i == 0 else None)
+            x, c = self._enc_fwd(x, P, B, L, kmask, sa_f32=p["sa0_f32"] if i == 0 else None, mod="poly", li=i)
             ctxs.append(c)
         if not p["layers"] and x.dtype != self.act:
             x = ops.cast(x, self._new(B * P, D), rows=B * P, cols=D)
@@ -290,7 +444,7 @@ class TrainEngine(Engine):
         pre = "lane_polygon_encoder."
         dx = ops.masked_mean_bwd(demb, lens, self._new(B * P, D, dtype=xdt), B=B, P=P, D=D)
         for i in reversed(range(len(ctxs))):
-            dx = self._enc_bwd(dx, ctxs[i], P, B, p["layers"][i], f"{pre}encoder.layers.{i}.", kmask)
+            dx = self._enc_bwd(dx, ctxs[i], P, B, p["layers"][i], f"{pre}encoder.layers.{i}.", kmask, mod="poly", li=i)
         # x0[b,p,:] = W . pt + bias + pos[p]   (train.py:364-365)
         M = B * P
         ops.period_sum(dx, self._g(pre + "input_proj.bias", (D,)), rows=M, cols=D)
@@ -308,13 +462,13 @@ class TrainEngine(Engine):
             v = ops.cast(v, self._new(B * Tv, Dv), rows=B * Tv, cols=Dv)
         x = ops.gemm(v, q["vproj"].w, self._new(B * Tv, Hq), bias=q["vproj"].b)
         enc = []
-        for L in q["enc"]:
-            x, c = self._enc_fwd(x, Tv, B, L)
+        for i, L in enumerate(q["enc"]):
+            x, c = self._enc_fwd(x, Tv, B, L, mod="qenc", li=i)
             enc.append(c)
         t = ops.cast(q["query"], self._new(B * Q, Hq), rows=B * Q, cols=Hq, in_row_mod=Q)
         dec = []
-        for L in q["dec"]:
-            y3, c = self._dec_fwd(t, Q, x, Tv, B, L)
+        for i, L in enumerate(q["dec"]):
+            y3, c = self._dec_fwd(t, Q, x, Tv, B, L, li=i)
             t = self._ln_res(y3, L["n3"])
             dec.append((c, y3))
         if q["qproj"] is not None:
@@ -339,13 +493,13 @@ class TrainEngine(Engine):
             c, y3 = dec[i]
             L = q["dec"][i]
             dy3 = self._ln_bwd(dt, y3, L["n3"], f"{pre}decoder.layers.{i}.norm3.weight", f"{pre}decoder.layers.{i}.norm3.bias")
-            dt, dmem = self._dec_bwd(dy3, c, Q, x, Tv, B, L, f"{pre}decoder.layers.{i}.", dmem)
+            dt, dmem = self._dec_bwd(dy3, c, Q, x, Tv, B, L, f"{pre}decoder.layers.{i}.", dmem, li=i)
         ops.period_sum(dt, self._g(pre + "query_tokens", (Q, Hq)), rows=B * Q, cols=Hq, period=Q)
         if dmem is None:    # no decoder layers: the encoder output is unused
             return
         dx = dmem
         for i in reversed(range(len(enc))):
-            dx = self._enc_bwd(dx, enc[i], Tv, B, q["enc"][i], f"{pre}encoder.layers.{i}.")
+            dx = self._enc_bwd(dx, enc[i], Tv, B, q["enc"][i], f"{pre}encoder.layers.{i}.", mod="qenc", li=i)
         self._lin_bwd(dx, v, q["vproj"], pre + "vision_proj.weight", pre + "vision_proj.bias", need_dx=False)
 
     # ---- LoRA-Llama stack (HF:375-427 + peft lora.Linear) -----------------------------------------------------
@@ -370,9 +524,17 @@ class TrainEngine(Engine):
         xs = self._new_xs(M)
         ops.cast(fused.view(M, H), xs, rows=M, cols=H, ldi=H, ldo=Kx)
         ctxs = []
-        for ly in m["layers"]:
+        xm = None
+        for li, ly in enumerate(m["layers"]):
             rstd1 = ops.row_rstd(xs, torch.empty(M, dtype=torch.float32, device=self.dev), rows=M, cols=H, ldx=Kx, eps=m["eps"])
-            if kx:
+            drops = self._lora_drops(li)
+            if kx and drops:
+                if xm is None:
+                    xm = self._new(M, H)
+                for ti, d in enumerate(drops):
+                    ops.dropout(xs, xm, d, rows=M, cols=H, ldi=Kx, ldo=H, scale=1.0)
+                    ops.gemm(xm, ly["a_cat_t"][ti], xs[:, H:], M=M, N=m["n_lora"], K=H, ldo=Kx, residual=None if ti == 0 else xs[:, H:], ldr=Kx)
+            elif kx:
                 ops.gemm(xs, ly["a_cat"], xs[:, H:], M=M, N=m["n_lora"], K=H, lda=Kx, ldo=Kx)
             qkv = ops.gemm(xs, ly["wqkv"], self._new(M, nqkv), M=M, N=nqkv, K=Kx, lda=Kx, rope=rope, row_scale=rstd1)
             attn = self._new(M, nq)
@@ -405,6 +567,7 @@ class TrainEngine(Engine):
         nqkv = nq + 2 * nk
         sq = (L * nqkv, nqkv)
         dx = ops.rmsnorm_bwd(dfh, xs_last, self._new(M, H), rows=M, cols=H, eps=m["eps"], w=m["norm"], ldx=Kx)
+        xm = None
         wrap = self.model.mllm.llama_wrapper
         if m["fuse_rope"] and "qk_inv_perm" not in m:
             m["qk_inv_perm"] = torch.argsort(m["qk_perm"])
@@ -427,11 +590,21 @@ class TrainEngine(Engine):
                            o=attn)
             ops.rope_adjacent_(dqkv, rows=M, L=L, ld=nqkv, cols=nq + nk, dh=dh, table=table, inverse=True)
             dxs = ops.gemm(dqkv, ly["wqkvT"], self._new(M, Kx))            # [dn1 | dTn]
+            drops = self._lora_drops(i)
+            if drops and xm is None:
+                xm = self._new(M, H)
             if kx and self.tr_lora:
                 dext = torch.zeros(nqkv, kx, dtype=torch.float32, device=self.dev)
                 ops.skinny_dw(dqkv, xs[:, H:], dext, M=M, N=nqkv, J=kx, ldy=nqkv, ldz=Kx, row_scale=rstd1)
                 dAp = torch.zeros(H, kx, dtype=torch.float32, device=self.dev)
-                ops.skinny_dw(xs, dxs[:, H:], dAp, M=M, N=H, J=kx, ldy=Kx, ldz=Kx, row_scale=rstd1)
+                if drops:      # dA'_t = s_t * sum_m rstd[m] (mask_t o x)[m, :]^T dTn_t[m, :]: one masked copy + one reduction per target
+                    for ti, d in enumerate(drops):
+                        ops.dropout(xs, xm, d, rows=M, cols=H, ldi=Kx, ldo=H, scale=1.0)
+                        dAt = torch.zeros(H, kx, dtype=torch.float32, device=self.dev)
+                        ops.skinny_dw(xm, dxs[:, H:], dAt, M=M, N=H, J=kx, ldy=H, ldz=Kx, row_scale=rstd1)
+                        dAp[:, ti * r:(ti + 1) * r] = dAt[:, ti * r:(ti + 1) * r] * d.scale
+                else:
+                    ops.skinny_dw(xs, dxs[:, H:], dAp, M=M, N=H, J=kx, ldy=Kx, ldz=Kx, row_scale=rstd1)
                 if inv_perm is not None:
                     dext = dext[inv_perm]
                 layer = wrap.causal_lm().model.layers[i].self_attn
@@ -441,7 +614,11 @@ class TrainEngine(Engine):
                     pre = f"{self.llm_prefix}{i}.self_attn.{name}."
                     self.G[pre + "lora_B.default.weight"] = (dext[r0:r1, ti * r:(ti + 1) * r] * mod.scaling).contiguous()
                     self.G[pre + "lora_A.default.weight"] = (dAp[:, ti * r:(ti + 1) * r] * ly["ln1"][:, None]).t().contiguous()
-            if kx:
+            if kx and drops:    # dn1 += mask_t o (dTn_t . s_t A'_t) per target
+                for ti, d in enumerate(drops):
+                    tmp = ops.gemm(dxs[:, H:], ly["a_catT_t"][ti], xm, M=M, N=H, K=kx, lda=Kx, ldo=H)
+                    ops.dropout(tmp, dxs, d, rows=M, cols=H, ldi=H, ldo=Kx, scale=1.0, accumulate=True)
+            elif kx:
                 ops.gemm(dxs[:, H:], ly["a_catT"], dxs, M=M, N=H, K=kx, lda=Kx, ldo=Kx, residual=dxs, ldr=Kx)    # dn1 += dTn . A'
             dx = ops.rmsnorm_bwd(dxs, xs, self._new(M, H), rows=M, cols=H, eps=m["eps"], add=dx2, lddy=Kx, ldx=Kx)
         return dx      # gradient w.r.t. the fused input embeddings (M, H)
@@ -452,24 +629,31 @@ class TrainEngine(Engine):
         xT = ops.transpose(x, self._new(B * T, 2, dtype=sm), rows=2, cols=T, batch=B, in_bstride=2 * T, out_bstride=2 * T)
         xp = ops.gemm(xT, lt["wt"], self._new(B * T, C, dtype=sm), bias=lt["bt"])
         e0 = ops.nlinear_decode(xp, lt["we"], lt["be_pos"], None, self._new(B * T, C, dtype=sm), B=B, C=C, T_in=T, T_out=T)
+        # reference SelfAttentionBlock (train.py:674-686): res1 = x_norm + dropout1(mha(x_norm)); out = norm2(res1) + dropout2(ffn(norm2(res1)))
+        D = lambda kind: self.drop("ltsf", 0, kind)     # noqa: E731
         xn = self._ln_res(e0, lt["n1"])
-        qkv, a = self._self_attn_fwd(xn, T, B, lt["mha"])
-        y = ops.gemm(a, lt["mha"]["out"].w, self._new(B * T, C, dtype=sm), bias=lt["mha"]["out"].b, residual=xn)
+        qkv, a = self._self_attn_fwd(xn, T, B, lt["mha"], drop=D("sa_attn"))
+        y = self._sub_out(a, lt["mha"]["out"], xn, D("drop1"), out_dtype=sm)
         r = self._ln_res(y, lt["n2"])
         h = ops.gemm(r, lt["f0"].w, self._new(B * T, lt["f0"].N, dtype=sm), bias=lt["f0"].b, act=ops.ACT_RELU)
-        enc = ops.gemm(h, lt["f3"].w, self._new(B * T, C, dtype=sm), bias=lt["f3"].b, residual=r)
+        if D("ffn") is not None:
+            self._drop_res(h, D("ffn"), None)
+        enc = self._sub_out(h, lt["f3"], r, D("drop2"), out_dtype=sm)
         return enc, (xT, xp, e0, xn, qkv, a, y, r, h, B)
 
     def _ltsf_enc_bwd(self, denc, ctx):
         xT, xp, e0, xn, qkv, a, y, r, h, B = ctx
         lt, C, T = self.lt, self.C, self.T_in
         pre = "ltsf.attn_block."
-        dh = self._lin_bwd(denc, h, lt["f3"], pre + "ffn.3.weight", pre + "ffn.3.bias")
+        D = lambda kind: self.drop("ltsf", 0, kind)     # noqa: E731
+        dh = self._lin_bwd(self._drop_grad(denc, D("drop2")), h, lt["f3"], pre + "ffn.3.weight", pre + "ffn.3.bias")
+        if D("ffn") is not None:
+            self._drop_res(dh, D("ffn"), None)
         dpre = self._relu_bwd(dh, h)
         dr = self._lin_bwd(dpre, r, lt["f0"], pre + "ffn.0.weight", pre + "ffn.0.bias", dx_residual=denc)
         dy = self._ln_bwd(dr, y, lt["n2"], pre + "norm2.weight", pre + "norm2.bias")
-        da = self._lin_bwd(dy, a, lt["mha"]["out"], pre + "mha.out_proj.weight", pre + "mha.out_proj.bias")
-        dxn = self._self_attn_bwd(da, qkv, xn, T, B, lt["mha"], pre + "mha.", dx_residual=dy, o=a)
+        da = self._lin_bwd(self._drop_grad(dy, D("drop1")), a, lt["mha"]["out"], pre + "mha.out_proj.weight", pre + "mha.out_proj.bias")
+        dxn = self._self_attn_bwd(da, qkv, xn, T, B, lt["mha"], pre + "mha.", dx_residual=dy, o=a, drop=D("sa_attn"))
         de0 = self._ln_bwd(dxn, e0, lt["n1"], pre + "norm1.weight", pre + "norm1.bias")
         # e0 = NLinear(xp; we, be) + pos   (bias and positional table share the [T, C] gradient)
         gb = torch.zeros(T, C, dtype=torch.float32, device=self.dev)
@@ -492,11 +676,13 @@ class TrainEngine(Engine):
         if lt["post"] is not None:
             p0, p3 = lt["post"]
             hp = ops.gemm(dec0, p0.w, self._new(B, p0.N, dtype=sm), bias=p0.b, act=ops.ACT_RELU)
+            if self.drop("dec", 0, "post") is not None:                                   # post_mlp: Linear, ReLU, Dropout, Linear (train.py:745-750)
+                self._drop_res(hp, self.drop("dec", 0, "post"), None)
             dec = ops.gemm(hp, p3.w, self._new(B, To * C, dtype=sm), bias=p3.b)
         dec_t = dec.view(B * To, C)
         dq = dec_t if self.act == sm else ops.cast(dec_t, self._new(B * To, C), rows=B * To, cols=C)
         q0 = ops.gemm(dq, lt["dec_proj"].w, self._new(B * To, H), bias=lt["dec_proj"].b)
-        q, kv, a = self._cross_attn_fwd(q0, To, fh, L, B, lt["cross"])
+        q, kv, a = self._cross_attn_fwd(q0, To, fh, L, B, lt["cross"], drop=self.drop("dec", 0, "cross_attn"))
         co = ops.gemm(a, lt["cross"]["out"].w, self._new(B * To, H), bias=lt["cross"]["out"].b)
         fused = ops.gemm(co, lt["dec_unproj"].w, self._new(B * To, C, dtype=sm), bias=lt["dec_unproj"].b, residual=dec_t)
         f = self._ln_res(fused, lt["fl_ln"])
@@ -507,9 +693,11 @@ class TrainEngine(Engine):
         f2 = ops.gemm(h1, l2.w, self._new(B * To, C, dtype=sm), bias=l2.b)
         o = ops.gemm(f2, lo.w, self._new(B * To, 2, dtype=sm), bias=lo.b)
         decoded = ops.head_assemble(o, x, torch.empty(B, 2, To, dtype=torch.float32, device=self.dev), B=B, T_in=T, T_out=To)
-        metrics = torch.zeros(8, dtype=torch.float32, device=self.dev)
-        per_scene = torch.empty(B, 2, dtype=torch.float32, device=self.dev)
-        ops.traj_metrics(decoded, y, norm_stat, metrics, per_scene, B=B, T_out=To)
+        metrics = per_scene = None
+        if y is not None:
+            metrics = torch.zeros(8, dtype=torch.float32, device=self.dev)
+            per_scene = torch.empty(B, 2, dtype=torch.float32, device=self.dev)
+            ops.traj_metrics(decoded, y, norm_stat, metrics, per_scene, B=B, T_out=To)
         ctx = (enc, poly_emb, fh, adj, dec0, hp, dec_t, dq, q0, q, kv, a, co, fused, f, l1, l2, lo, h1, f2, decoded, y, norm_stat, B, L)
         return dict(decoded=decoded, metrics=metrics, per_scene=per_scene), ctx
 
@@ -533,12 +721,15 @@ class TrainEngine(Engine):
         # fused = dec_t + dec_unproj(co)
         dco = self._lin_bwd(dfused, co, lt["dec_unproj"], pre + "dec_unproj.weight", pre + "dec_unproj.bias", dx_dtype=self.act)
         da = self._lin_bwd(dco, a, lt["cross"]["out"], pre + "cross_attn.out_proj.weight", pre + "cross_attn.out_proj.bias")
-        dq0, dfh = self._cross_attn_bwd(da, q, kv, q0, To, fh, L, B, lt["cross"], pre + "cross_attn.", need_dmem=need_dfh)
+        dq0, dfh = self._cross_attn_bwd(da, q, kv, q0, To, fh, L, B, lt["cross"], pre + "cross_attn.", need_dmem=need_dfh,
+                                        drop=self.drop("dec", 0, "cross_attn"))
         ddec_t = self._lin_bwd(dq0, dq, lt["dec_proj"], pre + "dec_proj.weight", pre + "dec_proj.bias", dx_dtype=sm, dx_residual=dfused)
         ddec = ddec_t.view(B, To * C)
         if lt["post"] is not None:
             p0, p3 = lt["post"]
             dhp = self._lin_bwd(ddec, hp, p3, "_post3_w", "_post3_b")
+            if self.drop("dec", 0, "post") is not None:
+                self._drop_res(dhp, self.drop("dec", 0, "post"), None)
             dpre = self._relu_bwd(dhp, hp)
             ddec0 = self._lin_bwd(dpre, dec0, p0, "_post0_w", pre + "post_mlp.0.bias")
         else:
@@ -552,18 +743,23 @@ class TrainEngine(Engine):
 
     # ---- whole step -----------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def train_forward(self, x, vision, polygon, poly_len, input_ids, attention_mask, y, norm_stat):
+    def train_forward(self, x, vision, polygon, poly_len, input_ids, attention_mask, y=None, norm_stat=None, keep=True):
+        """`keep=False`: a stochastic pass that will not be differentiated (best-of-K candidates) — the activation stash is dropped."""
         dev = self.dev
         if dev.type != "cuda":
             raise ops._lib.TcavpError("the model must be on a CUDA device (there is no CPU fallback): model.to('cuda')")
+        self._begin_pass()
         self.sync_params()
         x = self._dev_f32(x)
         B = x.shape[0]
         polygon = self._dev_f32(polygon)
         lens = poly_len if torch.is_tensor(poly_len) else torch.tensor(list(poly_len), dtype=torch.int32)
         lens = lens.to(device=dev, dtype=torch.int32)
-        y = self._dev_f32(y)
-        norm_stat = self._dev_f32(norm_stat).view(B, 4)
+        if y is not None and norm_stat is not None:
+            y = self._dev_f32(y)
+            norm_stat = self._dev_f32(norm_stat).view(B, 4)
+        else:
+            y = norm_stat = None
         poly_emb, c_poly = self._poly_fwd(polygon, lens)
         vision = vision.to(dev)
         if vision.dtype not in (torch.float32, torch.bfloat16):
@@ -579,10 +775,14 @@ class TrainEngine(Engine):
         fh, c_llm = self._llm_fwd(fused, mask, B, L)
         enc, c_enc = self._ltsf_enc_fwd(x, B)
         out, c_dec = self._ltsf_dec_fwd(enc, poly_emb, fh, x, B, L, y, norm_stat)
-        out["loss"] = out["metrics"][4]
+        if y is not None:
+            out["loss"] = out["metrics"][4]
+        if not keep:
+            self._ctx = None
+            return out
         # the stash travels with the result (model.py keeps it on the autograd node), so two forwards may be in flight before either
         # backward runs (gradient accumulation over micro-batches, two losses summed); `_ctx` is only the default of train_backward
-        out["_ctx"] = self._ctx = (c_poly, c_qf, c_llm, c_enc, c_dec, B, L, Q, H, ids.shape[1])
+        out["_ctx"] = self._ctx = (c_poly, c_qf, c_llm, c_enc, c_dec, B, L, Q, H, ids.shape[1], self.drop)
         return out
 
     @torch.no_grad()
@@ -593,7 +793,7 @@ class TrainEngine(Engine):
             ctx = self._ctx
         if ctx is None:
             raise ops._lib.TcavpError("train_backward: no forward pass to differentiate (or its activations were already consumed)")
-        c_poly, c_qf, c_llm, c_enc, c_dec, B, L, Q, H, L_text = ctx
+        c_poly, c_qf, c_llm, c_enc, c_dec, B, L, Q, H, L_text, self.drop = ctx        # the masks of THAT forward pass
         if ctx is self._ctx:
             self._ctx = None
         self.G = {}
