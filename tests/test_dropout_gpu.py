@@ -91,6 +91,16 @@ def test_attention_dropout_forward_and_backward(lib_built, dtype, B, H, Tq, Tk, 
     torch.testing.assert_close(dq.float().cpu(), gq, **btol)
     torch.testing.assert_close(dk.cpu(), gk, **btol)
     torch.testing.assert_close(dv.cpu(), gv, **btol)
+    if ops.attention_bwd_owned_ok(qd, H=H, Hkv=H, Tq=Tq, Tk=Tk, dh=dh, o=out):
+        # the "owned" form the fine-tune step uses (one CTA owns every key row: dk / dv stored directly in bf16)
+        dq2 = torch.empty(B, Tq, E, dtype=dtype, device=DEV)
+        dk2, dv2 = torch.empty(B, Tk, E, dtype=dtype, device=DEV), torch.empty(B, Tk, E, dtype=dtype, device=DEV)
+        ops.attention_bwd_owned(qd, kd, vd, dod, dq2, dk2, dv2, B=B, H=H, Tq=Tq, Tk=Tk, dh=dh, q_strides=st(Tq), k_strides=st(Tk), v_strides=st(Tk),
+                                do_strides=st(Tq), dq_strides=st(Tq), dk_strides=st(Tk), dv_strides=st(Tk), scale=scale, key_mask=kmd, o=out,
+                                o_strides=st(Tq), drop=d)
+        torch.testing.assert_close(dq2.float().cpu(), gq, **btol)
+        torch.testing.assert_close(dk2.float().cpu(), gk, rtol=5e-2, atol=5e-2 * float(gk.abs().max()))
+        torch.testing.assert_close(dv2.float().cpu(), gv, rtol=5e-2, atol=5e-2 * float(gv.abs().max()))
 
 
 def _drop_oracle(fix):

@@ -213,8 +213,7 @@ extern "C" int tcavp_attention(const tcavp_attn_args* a, tcavp_stream_t stream_)
   TCAVP_REQUIRE(a->dtype == TCAVP_F32 || a->dtype == TCAVP_BF16, "tcavp_attention: bad dtype");
   TCAVP_REQUIRE(a->drop_thresh == 0 || (a->drop_seed != nullptr && a->drop_scale > 0.f), "tcavp_attention: dropout needs a device seed and a scale");
   if (a->dtype == TCAVP_BF16) {
-    // the tensor-core kernels have no dropout path: train-mode attention of the small modules (poly / Q-Former / LTSF) takes the SIMT kernels
-    int rc = a->drop_thresh != 0 ? 1 : (a->dh > 128 ? attention_x_launch(*a, stream) : attention_tc_launch(*a, stream));
+    int rc = a->dh > 128 ? attention_x_launch(*a, stream) : attention_tc_launch(*a, stream);
     if (rc <= 0) return rc;
     return launch_warp<__nv_bfloat16>(*a, stream);
   }

@@ -102,6 +102,11 @@ __global__ void __launch_bounds__(MAXT, MINB) attn_bwd_tc_kernel(tcavp_attn_args
   const int bn_row = (lane & 7) + ((lane >> 4) << 3), bn_col = ((lane >> 3) & 1) * 8;
   const int bk_row = (lane & 7) + (((lane >> 3) & 1) << 3), bk_col = (lane >> 4) * 8;
   const float sl2 = a.scale * 1.4426950408889634f;
+  // train-mode dropout (O = P_d V, P_d = keep ? P / (1 - p_drop) : 0): dP = f o (dO V^T) with f = keep ? 1 / (1 - p_drop) : 0,
+  // D_i = dO_i . O_i is unchanged, dV uses P_d.  The mask is regenerated from (seed, site, ((b*H + h)*Tq + i)*Tk + j).
+  const bool drop = a.drop_thresh != 0;
+  const uint32_t dkey = drop ? drop_key(a.drop_seed, a.drop_site) : 0u;
+  const unsigned long long dbase = (unsigned long long)blockIdx.x * a.Tq * (unsigned long long)a.Tk;
 
   // =========================== pass B: statistics, D and dQ (query-outer) ===========================
   const int nqs = (a.Tq + 15) / 16;
@@ -227,8 +232,13 @@ __global__ void __launch_bounds__(MAXT, MINB) attn_bwd_tc_kernel(tcavp_attn_args
             const bool okj = sMask[j] != 0;
             const float p_lo = (okj && (!a.causal || j <= r_lo)) ? ex2(s[n][e] * sl2 - rm_lo) * il_lo : 0.f;
             const float p_hi = (okj && (!a.causal || j <= r_hi)) ? ex2(s[n][2 + e] * sl2 - rm_hi) * il_hi : 0.f;
-            ds[e] = a.scale * p_lo * (dp[n][e] - d_lo);
-            ds[2 + e] = a.scale * p_hi * (dp[n][2 + e] - d_hi);
+            float g_lo = dp[n][e], g_hi = dp[n][2 + e];
+            if (drop) {
+              g_lo = drop_keep(dkey, dbase + (unsigned long long)r_lo * a.Tk + (unsigned)j, a.drop_thresh) ? g_lo * a.drop_scale : 0.f;
+              g_hi = drop_keep(dkey, dbase + (unsigned long long)r_hi * a.Tk + (unsigned)j, a.drop_thresh) ? g_hi * a.drop_scale : 0.f;
+            }
+            ds[e] = a.scale * p_lo * (g_lo - d_lo);
+            ds[2 + e] = a.scale * p_hi * (g_hi - d_hi);
           }
           pf[n >> 1][(n & 1) * 2] = pack2(ds[0], ds[1]);
           pf[n >> 1][(n & 1) * 2 + 1] = pack2(ds[2], ds[3]);
@@ -301,8 +311,19 @@ __global__ void __launch_bounds__(MAXT, MINB) attn_bwd_tc_kernel(tcavp_attn_args
             const float m = sM[i], il = sIL[i], D = sD[i];
             p[e] = (ok_lo && (!a.causal || j_lo <= i)) ? ex2(st[n][e] * sl2 - m) * il : 0.f;
             p[2 + e] = (ok_hi && (!a.causal || j_hi <= i)) ? ex2(st[n][2 + e] * sl2 - m) * il : 0.f;
-            ds[e] = a.scale * p[e] * (dpt[n][e] - D);
-            ds[2 + e] = a.scale * p[2 + e] * (dpt[n][2 + e] - D);
+            float g_lo = dpt[n][e], g_hi = dpt[n][2 + e];
+            float f_lo = 1.f, f_hi = 1.f;
+            if (drop) {
+              const unsigned long long irow = dbase + (unsigned long long)i * a.Tk;
+              f_lo = drop_keep(dkey, irow + (unsigned)j_lo, a.drop_thresh) ? a.drop_scale : 0.f;
+              f_hi = drop_keep(dkey, irow + (unsigned)j_hi, a.drop_thresh) ? a.drop_scale : 0.f;
+              g_lo *= f_lo;
+              g_hi *= f_hi;
+            }
+            ds[e] = a.scale * p[e] * (g_lo - D);
+            ds[2 + e] = a.scale * p[2 + e] * (g_hi - D);
+            p[e] *= f_lo;            // dV_J += P_d^T dO
+            p[2 + e] *= f_hi;
           }
           pT[n * 2] = pack2(p[0], p[1]);
           pT[n * 2 + 1] = pack2(p[2], p[3]);

@@ -103,6 +103,8 @@ __global__ void __launch_bounds__(MAXT, MINB) attn_flash_kernel(tcavp_attn_args 
   // V (transposed, x4 = keys [0,8)/[8,16) x dims [0,8)/[8,16)):
   const int v_row = (lane & 7) + (((lane >> 3) & 1) << 3), v_col = (lane >> 4) * 8;
   const float sl2 = a.scale * 1.4426950408889634f;   // softmax in base 2
+  const bool drop = a.drop_thresh != 0;
+  const uint32_t dkey = drop ? drop_key(a.drop_seed, a.drop_site) : 0u;
   __nv_bfloat16* go = reinterpret_cast<__nv_bfloat16*>(a.out) + (size_t)b * a.o_sb + (size_t)h * DH;
 #pragma unroll 1
   for (int pass = 0; pass < 2; ++pass) {
@@ -134,6 +136,9 @@ __global__ void __launch_bounds__(MAXT, MINB) attn_flash_kernel(tcavp_attn_args 
 #pragma unroll
   for (int n = 0; n < NT; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
   float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+  // train-mode dropout on the probabilities: P.V uses keep ? p / (1 - p_drop) : 0, the row sums the undropped p (warp-uniform switch)
+  const unsigned long long drow_lo = ((unsigned long long)blockIdx.x * a.Tq + (unsigned)r_lo) * (unsigned long long)a.Tk;
+  const unsigned long long drow_hi = drow_lo + 8ull * (unsigned long long)a.Tk;
 
   const int k_end = a.causal ? min(a.Tk, row0 + 16) : a.Tk;   // keys this warp can ever see
   for (int kb = 0; kb < k_end; kb += KB) {
@@ -190,10 +195,17 @@ __global__ void __launch_bounds__(MAXT, MINB) attn_flash_kernel(tcavp_attn_args 
     uint32_t pf[KB / 16][4];
 #pragma unroll
     for (int n = 0; n < KB / 8; ++n) {
-      const float p0 = ex2(s[n][0] - ref_lo), p1 = ex2(s[n][1] - ref_lo);
-      const float p2 = ex2(s[n][2] - ref_hi), p3 = ex2(s[n][3] - ref_hi);
+      float p0 = ex2(s[n][0] - ref_lo), p1 = ex2(s[n][1] - ref_lo);
+      float p2 = ex2(s[n][2] - ref_hi), p3 = ex2(s[n][3] - ref_hi);
       ps_lo += p0 + p1;
       ps_hi += p2 + p3;
+      if (drop) {
+        const unsigned j = (unsigned)(kb + n * 8 + t4 * 2);
+        p0 = drop_keep(dkey, drow_lo + j, a.drop_thresh) ? p0 * a.drop_scale : 0.f;
+        p1 = drop_keep(dkey, drow_lo + j + 1, a.drop_thresh) ? p1 * a.drop_scale : 0.f;
+        p2 = drop_keep(dkey, drow_hi + j, a.drop_thresh) ? p2 * a.drop_scale : 0.f;
+        p3 = drop_keep(dkey, drow_hi + j + 1, a.drop_thresh) ? p3 * a.drop_scale : 0.f;
+      }
       // accumulator layout of two adjacent n8 tiles == A-operand layout of one k16 step
       pf[n >> 1][(n & 1) * 2] = pack2(p0, p1);
       pf[n >> 1][(n & 1) * 2 + 1] = pack2(p2, p3);

@@ -141,6 +141,9 @@ __global__ void __launch_bounds__(THREADS, 2) attn_x_kernel(tcavp_attn_args a, i
   const float sl2 = a.scale * 1.4426950408889634f;
   const int32_t* km = a.key_mask ? a.key_mask + (size_t)b * a.Tk : nullptr;
   const int r_lo = mt * 16 + g, r_hi = r_lo + 8;
+  const bool drop = a.drop_thresh != 0;       // dropout on the probabilities (train mode), mask index ((b*H + h)*Tq + i)*Tk + j
+  const uint32_t dkey = drop ? drop_key(a.drop_seed, a.drop_site) : 0u;
+  const unsigned long long dbase = (unsigned long long)blockIdx.x * a.Tq * (unsigned long long)a.Tk;
   float mx_lo = -INFINITY, mx_hi = -INFINITY;
 #pragma unroll
   for (int p = 0; p < MAXP; ++p) {
@@ -185,10 +188,15 @@ __global__ void __launch_bounds__(THREADS, 2) attn_x_kernel(tcavp_attn_args a, i
         const int col = (pair0 + p) * 16 + t * 8 + t4 * 2;
         const float p0 = exp2f(acc[2 * p + t][0] - ref_lo), p1 = exp2f(acc[2 * p + t][1] - ref_lo);
         const float p2 = exp2f(acc[2 * p + t][2] - ref_hi), p3 = exp2f(acc[2 * p + t][3] - ref_hi);
-        const uint32_t lo = pack2(p0, p1), hi = pack2(p2, p3);
+        uint32_t lo = pack2(p0, p1), hi = pack2(p2, p3);
         // the row sum is taken over the ROUNDED probabilities phase 2 multiplies with
         sum_lo += __uint_as_float(lo << 16) + __uint_as_float(lo & 0xffff0000u);
         sum_hi += __uint_as_float(hi << 16) + __uint_as_float(hi & 0xffff0000u);
+        if (drop) {      // train mode: the P.V product sees keep ? p / (1 - p_drop) : 0 (row sums above stay undropped)
+          const unsigned long long i_lo_ = dbase + (unsigned long long)r_lo * a.Tk + (unsigned)col, i_hi_ = dbase + (unsigned long long)r_hi * a.Tk + (unsigned)col;
+          lo = pack2(drop_keep(dkey, i_lo_, a.drop_thresh) ? p0 * a.drop_scale : 0.f, drop_keep(dkey, i_lo_ + 1, a.drop_thresh) ? p1 * a.drop_scale : 0.f);
+          hi = pack2(drop_keep(dkey, i_hi_, a.drop_thresh) ? p2 * a.drop_scale : 0.f, drop_keep(dkey, i_hi_ + 1, a.drop_thresh) ? p3 * a.drop_scale : 0.f);
+        }
         *reinterpret_cast<uint32_t*>(sP + (size_t)r_lo * ldp + col) = lo;
         *reinterpret_cast<uint32_t*>(sP + (size_t)r_hi * ldp + col) = hi;
       }
@@ -355,6 +363,9 @@ __global__ void __launch_bounds__(THREADS) attn_x_bwd_kernel(tcavp_attn_args a, 
   const float sl2 = a.scale * 1.4426950408889634f;
   const int32_t* km = a.key_mask ? a.key_mask + (size_t)b * a.Tk : nullptr;
   const int r_lo = mt * 16 + g, r_hi = r_lo + 8;
+  const bool drop = a.drop_thresh != 0;       // dropout on the probabilities (train mode), mask index ((b*H + h)*Tq + i)*Tk + j
+  const uint32_t dkey = drop ? drop_key(a.drop_seed, a.drop_site) : 0u;
+  const unsigned long long dbase = (unsigned long long)blockIdx.x * a.Tq * (unsigned long long)a.Tk;
   float mx_lo = -INFINITY, mx_hi = -INFINITY;
 #pragma unroll
   for (int p = 0; p < MAXP; ++p) {
@@ -390,6 +401,22 @@ __global__ void __launch_bounds__(THREADS) attn_x_bwd_kernel(tcavp_attn_args a, 
   }
   const float ref_lo = m_lo == -INFINITY ? 0.f : m_lo, ref_hi = m_hi == -INFINITY ? 0.f : m_hi;
   __syncthreads();
+  if (drop) {     // dP = f o (dO V^T), f = keep ? 1 / (1 - p_drop) : 0
+#pragma unroll
+    for (int p = 0; p < MAXP; ++p) {
+      if (p < my_pairs) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const unsigned col = (unsigned)((pair0 + p) * 16 + t * 8 + t4 * 2 + e);
+            acd[2 * p + t][e] = drop_keep(dkey, dbase + (unsigned long long)r_lo * a.Tk + col, a.drop_thresh) ? acd[2 * p + t][e] * a.drop_scale : 0.f;
+            acd[2 * p + t][2 + e] = drop_keep(dkey, dbase + (unsigned long long)r_hi * a.Tk + col, a.drop_thresh) ? acd[2 * p + t][2 + e] * a.drop_scale : 0.f;
+          }
+        }
+      }
+    }
+  }
   // unnormalised probabilities replace the scores; partial (sum p, sum p * dP) per row
   float l_lo = 0.f, l_hi = 0.f, pd_lo = 0.f, pd_hi = 0.f;
 #pragma unroll
@@ -444,8 +471,16 @@ __global__ void __launch_bounds__(THREADS) attn_x_bwd_kernel(tcavp_attn_args a, 
         const int col = (pair0 + p) * 16 + t * 8 + t4 * 2;
         const float p0 = acs[2 * p + t][0] * i_lo, p1 = acs[2 * p + t][1] * i_lo;
         const float p2 = acs[2 * p + t][2] * i_hi, p3 = acs[2 * p + t][3] * i_hi;
-        *reinterpret_cast<uint32_t*>(sP + (size_t)r_lo * ldp + col) = pack2(p0, p1);
-        *reinterpret_cast<uint32_t*>(sP + (size_t)r_hi * ldp + col) = pack2(p2, p3);
+        if (drop) {     // dV = P_d^T dO
+          const unsigned long long i_lo_ = dbase + (unsigned long long)r_lo * a.Tk + (unsigned)col, i_hi_ = dbase + (unsigned long long)r_hi * a.Tk + (unsigned)col;
+          *reinterpret_cast<uint32_t*>(sP + (size_t)r_lo * ldp + col) =
+              pack2(drop_keep(dkey, i_lo_, a.drop_thresh) ? p0 * a.drop_scale : 0.f, drop_keep(dkey, i_lo_ + 1, a.drop_thresh) ? p1 * a.drop_scale : 0.f);
+          *reinterpret_cast<uint32_t*>(sP + (size_t)r_hi * ldp + col) =
+              pack2(drop_keep(dkey, i_hi_, a.drop_thresh) ? p2 * a.drop_scale : 0.f, drop_keep(dkey, i_hi_ + 1, a.drop_thresh) ? p3 * a.drop_scale : 0.f);
+        } else {
+          *reinterpret_cast<uint32_t*>(sP + (size_t)r_lo * ldp + col) = pack2(p0, p1);
+          *reinterpret_cast<uint32_t*>(sP + (size_t)r_hi * ldp + col) = pack2(p2, p3);
+        }
         *reinterpret_cast<uint32_t*>(sdS + (size_t)r_lo * ldp + col) =
             pack2(a.scale * p0 * (acd[2 * p + t][0] - D_lo), a.scale * p1 * (acd[2 * p + t][1] - D_lo));
         *reinterpret_cast<uint32_t*>(sdS + (size_t)r_hi * ldp + col) =

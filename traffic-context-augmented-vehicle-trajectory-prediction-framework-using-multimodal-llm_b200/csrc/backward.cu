@@ -950,7 +950,7 @@ extern "C" int tcavp_attention_bwd(const tcavp_attn_args* a, const void* dout, l
   if (a->B == 0) return TCAVP_OK;
   TCAVP_REQUIRE(a->q && a->k && a->v && dout && dq && dk && dv && DT_OK(a->dtype), "tcavp_attention_bwd: bad pointer/dtype");
   TCAVP_REQUIRE(a->drop_thresh == 0 || (a->drop_seed != nullptr && a->drop_scale > 0.f), "tcavp_attention_bwd: dropout needs a device seed and a scale");
-  if (a->drop_thresh == 0) {   // tensor-core path: bf16, MHA, small head, forward output available (args->out); no dropout path there
+  {   // tensor-core path: bf16, MHA, small head, forward output available (args->out)
     const int rc = attention_bwd_tc_launch(*a, dout, do_sb, do_st, dq, dq_sb, dq_st, dk, dk_sb, dk_st, dv, dv_sb, dv_st, TCAVP_F32, STREAM(stream));
     if (rc <= 0) return rc;
   }
@@ -983,7 +983,7 @@ extern "C" int tcavp_attention_bwd_owned(const tcavp_attn_args* a, const void* d
   TCAVP_REQUIRE(!a->causal || a->Tq == a->Tk, "tcavp_attention_bwd_owned: causal needs Tq == Tk");
   if (a->B == 0) return TCAVP_OK;
   TCAVP_REQUIRE(a->q && a->k && a->v && dout && dq && dk && dv && DT_OK(dkv_dtype), "tcavp_attention_bwd_owned: bad pointer/dtype");
-  TCAVP_REQUIRE(a->drop_thresh == 0, "tcavp_attention_bwd_owned: no dropout path (use tcavp_attention_bwd)");
+  TCAVP_REQUIRE(a->drop_thresh == 0 || (a->drop_seed != nullptr && a->drop_scale > 0.f), "tcavp_attention_bwd_owned: dropout needs a device seed and a scale");
   int rc = 1;
   if (a->out) rc = attention_bwd_tc_launch(*a, dout, do_sb, do_st, dq, dq_sb, dq_st, dk, dk_sb, dk_st, dv, dv_sb, dv_st, dkv_dtype, STREAM(stream));
   if (rc > 0)   // few queries against wide heads (LTSF cross-attention): head_dim % 64 == 0, Tq <= 64, no causal mask

@@ -225,9 +225,7 @@ def attention(q, k, v, out, *, B, H, Hkv, Tq, Tk, dh, q_strides, k_strides, v_st
             raise TypeError("attention: key_mask must be int32")
         a.key_mask = key_mask.data_ptr()
     _set_drop(a, drop)
-    if a.drop_thresh:
-        kern = f"attn_{'row' if dh in (16, 32) and Tk <= 128 else 'warp'}_kernel[dropout,dh{dh},q{Tq},k{Tk}]"
-    elif a.dtype == BF16 and dh in (16, 32, 64, 96, 128) and max(Tq, Tk) <= 256:
+    if a.dtype == BF16 and dh in (16, 32, 64, 96, 128) and max(Tq, Tk) <= 256:
         kern = f"attn_flash_kernel[dh{dh},q{Tq},k{Tk}]"
     elif a.dtype == BF16 and dh > 128 and dh % 64 == 0 and Tq <= 64 and Tk <= 256 and not causal:
         kern = "attn_x_kernel"
@@ -555,7 +553,7 @@ def attention_bwd(q, k, v, dout, dq, dk, dv, *, B, H, Hkv, Tq, Tk, dh, q_strides
     tc = False
     if o is not None:
         a.out, (a.o_sb, a.o_st) = o.data_ptr(), o_strides
-        tc = a.dtype == BF16 and H == Hkv and dh in (16, 32, 64, 96, 128) and max(Tq, Tk) <= 256 and not a.drop_thresh
+        tc = a.dtype == BF16 and H == Hkv and dh in (16, 32, 64, 96, 128) and max(Tq, Tk) <= 256
     fl = 10.0 * B * H * Tq * Tk * dh * (0.5 if causal else 1.0)
     with _Timed(f"attn_bwd_{'tc_' if tc else ''}kernel[dh{dh},q{Tq},k{Tk}]", fl, 0.0):
         _lib.check(_lib.load().tcavp_attention_bwd(byref(a), _p(dout), _ll(do_strides[0]), _ll(do_strides[1]), _p(dq), _ll(dq_strides[0]),
@@ -573,7 +571,7 @@ def attention_bwd_owned_ok(q, *, H, Hkv, Tq, Tk, dh, o, causal=False):
 
 
 def attention_bwd_owned(q, k, v, dout, dq, dk, dv, *, B, H, Tq, Tk, dh, q_strides, k_strides, v_strides, do_strides, dq_strides,
-                        dk_strides, dv_strides, scale, causal=False, key_mask=None, o=None, o_strides=None):
+                        dk_strides, dv_strides, scale, causal=False, key_mask=None, o=None, o_strides=None, drop=None):
     """dk / dv are written (not accumulated) in their own dtype, e.g. straight into the packed d(qkv) buffer."""
     _need_cuda(q, k, v, dout, dq, dk, dv, key_mask, o)
     if dk.dtype != dv.dtype:
@@ -588,6 +586,7 @@ def attention_bwd_owned(q, k, v, dout, dq, dk, dv, *, B, H, Tq, Tk, dh, q_stride
     a.dtype, a.scale, a.causal = dt(q), scale, int(causal)
     if key_mask is not None:
         a.key_mask = key_mask.data_ptr()
+    _set_drop(a, drop)
     fl = 10.0 * B * H * Tq * Tk * dh * (0.5 if causal else 1.0)
     small = o is not None and dh in (16, 32, 64, 96, 128) and max(Tq, Tk) <= 256
     with _Timed(f"attn_{'bwd_tc' if small else 'x_bwd'}_kernel[dh{dh},q{Tq},k{Tk}]", fl, 0.0):

@@ -284,12 +284,12 @@ class TrainEngine(Engine):
     def _attn_bwd(self, q, k, v, do, *, B, H, Hkv, Tq, Tk, dh, qs, ks, vs, dos, dq, dqs, dk_out, dv_out, ld_kv, scale, causal=False,
                   key_mask=None, o=None, drop=None):
         """dq is written in place (strides dqs); dk / dv are accumulated in fp32 and cast into dk_out / dv_out (row stride ld_kv)."""
-        if drop is None and ops.attention_bwd_owned_ok(q, H=H, Hkv=Hkv, Tq=Tq, Tk=Tk, dh=dh, o=o, causal=causal):
+        if ops.attention_bwd_owned_ok(q, H=H, Hkv=Hkv, Tq=Tq, Tk=Tk, dh=dh, o=o, causal=causal):
             # one CTA owns all key rows of a head: dk / dv land directly in the packed gradient buffer (no fp32 staging, no casts)
             kvs = (Tk * ld_kv, ld_kv)
             ops.attention_bwd_owned(q, k, v, do, dq, dk_out, dv_out, B=B, H=H, Tq=Tq, Tk=Tk, dh=dh, q_strides=qs, k_strides=ks, v_strides=vs,
                                     do_strides=dos, dq_strides=dqs, dk_strides=kvs, dv_strides=kvs, scale=scale, causal=causal,
-                                    key_mask=key_mask, o=o, o_strides=dos)
+                                    key_mask=key_mask, o=o, o_strides=dos, drop=drop)
             return
         wk = Hkv * dh
         dk = torch.zeros(B * Tk, wk, dtype=torch.float32, device=self.dev)
