@@ -136,6 +136,14 @@ ATTN_CASES = [
     (2, 12, 12, 144, 144, 64, True, True),  # LLM 768-class
     (2, 4, 2, 40, 40, 32, True, True),      # tiny GQA
     (1, 8, 2, 70, 70, 128, True, True),     # 7B-style head_dim with GQA
+    # tcgen05 / TMEM kernel (attention_tm.cu): causal, head_dim 64 / 128, 128 <= L <= 256
+    (3, 12, 12, 144, 144, 64, True, True),  # L = 144: tile A = rows 16..143, tile B = rows 0..15; ragged key masks
+    (2, 8, 2, 144, 144, 128, True, True),   # 7B head_dim, GQA, two 64-column boxes per operand
+    (2, 4, 4, 128, 128, 64, True, False),   # exactly one tile
+    (2, 4, 2, 160, 160, 64, True, True),    # 32-row tile B
+    (1, 4, 4, 256, 256, 64, True, True),    # both tiles full
+    (2, 2, 2, 136, 136, 64, True, True),    # L not a multiple of 16: padded key columns / query rows come from the next scene
+    (2, 2, 1, 176, 176, 128, True, False),  # head_dim 128 with a 48-row tile B
 ]
 
 
@@ -155,6 +163,50 @@ def test_attention(ops, B, H, Hkv, Tq, Tk, dh, causal, masked, dtype):
                   scale=dh ** -0.5, causal=causal, key_mask=None if km is None else km.to(DEV))
     tol = dict(rtol=1e-4, atol=1e-5) if dtype == "fp32" else dict(rtol=2e-2, atol=2e-2)
     torch.testing.assert_close(out.float().cpu(), want, **tol)
+
+
+@pytest.mark.parametrize("nh,nkv,dh,B", [(12, 12, 64, 160), (32, 8, 128, 20)])
+def test_llm_attention_tcgen05_on_the_packed_qkv_layout(ops, nh, nkv, dh, B):
+    """The engine's call: q / k / v are column slices of one packed [B L, (nh + 2 nkv) dh] activation, more (scene, head) items than
+    SMs (persistent loop, both stages of the TMA ring), ragged key masks — against the reference and against the mma.sync kernel."""
+    import os
+    import subprocess
+    L = 144
+    nq, nk = nh * dh, nkv * dh
+    g = torch.Generator().manual_seed(nh)
+    qkv = (torch.randn(B * L, nq + 2 * nk, generator=g) * 0.7).to(torch.bfloat16)
+    lens = torch.randint(100, L + 1, (B,), generator=g)
+    km = (torch.arange(L)[None, :] < lens[:, None]).int()
+    n_ref = 3                                             # the reference on a few scenes only (host)
+    q, k, v = (t.float().view(B, L, -1, dh) for t in (qkv[:, :nq], qkv[:, nq:nq + nk], qkv[:, nq + nk:]))
+    want = _attn_ref(q[:n_ref], k[:n_ref], v[:n_ref], dh ** -0.5, True, km[:n_ref])
+    d = qkv.to(DEV)
+    out = torch.empty(B * L, nq, dtype=torch.bfloat16, device=DEV)
+    n0 = ops.launch_count()
+    ops.attention(d, d[:, nq:], d[:, nq + nk:], out, B=B, H=nh, Hkv=nkv, Tq=L, Tk=L, dh=dh, q_strides=(L * (nq + 2 * nk), nq + 2 * nk),
+                  k_strides=(L * (nq + 2 * nk), nq + 2 * nk), v_strides=(L * (nq + 2 * nk), nq + 2 * nk), o_strides=(L * nq, nq), scale=dh ** -0.5,
+                  causal=True, key_mask=km.to(DEV))
+    assert ops.launch_count() - n0 == 1
+    got = out.float().cpu().view(B, L, nh, dh)
+    torch.testing.assert_close(got[:n_ref], want, rtol=2e-2, atol=2e-2)
+    # every scene against the mma.sync kernel (TCAVP_ATTN_TCGEN05=0 is read once per process: ask a child process)
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "gpurun_out")
+    os.makedirs(path, exist_ok=True)
+    torch.save(dict(qkv=qkv, km=km, nh=nh, nkv=nkv, dh=dh, B=B, L=L), os.path.join(path, "attn_ab_in.pt"))
+    code = ("import sys, torch; sys.path.insert(0, %r); import tcavp_b200 as T; from tcavp_b200 import ops\n"
+            "z = torch.load(%r); d = z['qkv'].cuda(); nh, nkv, dh, B, L = z['nh'], z['nkv'], z['dh'], z['B'], z['L']; nq, nk = nh * dh, nkv * dh\n"
+            "out = torch.empty(B * L, nq, dtype=torch.bfloat16, device='cuda'); s = (L * (nq + 2 * nk), nq + 2 * nk)\n"
+            "ops.attention(d, d[:, nq:], d[:, nq + nk:], out, B=B, H=nh, Hkv=nkv, Tq=L, Tk=L, dh=dh, q_strides=s, k_strides=s, v_strides=s, "
+            "o_strides=(L * nq, nq), scale=dh ** -0.5, causal=True, key_mask=z['km'].cuda())\n"
+            "torch.save(out.cpu(), %r)\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(path, "attn_ab_in.pt"),
+                                              os.path.join(path, "attn_ab_out.pt"))
+    import sys
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, TCAVP_ATTN_TCGEN05="0"), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    old = torch.load(os.path.join(path, "attn_ab_out.pt")).float().view(B, L, nh, dh)
+    torch.testing.assert_close(got, old, rtol=2e-2, atol=2e-2)
+    for f in ("attn_ab_in.pt", "attn_ab_out.pt"):
+        os.remove(os.path.join(path, f))
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])

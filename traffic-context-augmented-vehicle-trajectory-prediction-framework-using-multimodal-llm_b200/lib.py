@@ -12,7 +12,7 @@ _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libtcavp.so")
 INCLUDE = os.path.join(_ROOT, "include")
-SOURCES = ["api.cu", "gemm.cu", "attention.cu", "attention_tc.cu", "attention_x.cu", "norm.cu", "elementwise.cu", "ltsf.cu", "backward.cu", "attention_bwd_tc.cu", "dw_tc.cu"]
+SOURCES = ["api.cu", "gemm.cu", "attention.cu", "attention_tc.cu", "attention_tm.cu", "attention_x.cu", "norm.cu", "elementwise.cu", "ltsf.cu", "backward.cu", "attention_bwd_tc.cu", "dw_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I", INCLUDE]
 

@@ -3,6 +3,7 @@
 torch is used for device memory and streams only: every function here hands raw device pointers to
 libtcavp.so and raises TcavpError on a non-zero return code.  Nothing falls back to torch math."""
 import ctypes
+import os as _os
 from ctypes import POINTER, Structure, byref, c_float, c_int, c_longlong, c_uint32, c_void_p
 
 import torch
@@ -225,7 +226,10 @@ def attention(q, k, v, out, *, B, H, Hkv, Tq, Tk, dh, q_strides, k_strides, v_st
             raise TypeError("attention: key_mask must be int32")
         a.key_mask = key_mask.data_ptr()
     _set_drop(a, drop)
-    if a.dtype == BF16 and dh in (16, 32, 64, 96, 128) and max(Tq, Tk) <= 256:
+    if (a.dtype == BF16 and causal and dh in (64, 128) and Tq == Tk and 128 <= Tq <= 256 and not a.drop_thresh and q_strides[0] == Tq * q_strides[1]
+            and k_strides[0] == Tk * k_strides[1] and v_strides[0] == Tk * v_strides[1] and _os.environ.get("TCAVP_ATTN_TCGEN05", "1") != "0"):
+        kern = f"attn_tm_kernel[dh{dh},L{Tq}]"          # tcgen05 / TMEM / TMA (attention_tm.cu)
+    elif a.dtype == BF16 and dh in (16, 32, 64, 96, 128) and max(Tq, Tk) <= 256:
         kern = f"attn_flash_kernel[dh{dh},q{Tq},k{Tk}]"
     elif a.dtype == BF16 and dh > 128 and dh % 64 == 0 and Tq <= 64 and Tk <= 256 and not causal:
         kern = "attn_x_kernel"
