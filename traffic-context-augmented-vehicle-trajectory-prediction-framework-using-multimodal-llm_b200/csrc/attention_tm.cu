@@ -20,7 +20,7 @@
 namespace tcavp {
 namespace tm {
 
-constexpr int THREADS = 384;      // 12 warps: 0 TMA, 1 MMA (+ TMEM owner), 2-3 idle, 4-7 softmax A, 8-11 softmax B
+constexpr int THREADS = 384;      // 12 warps: 0 TMA, 1 MMA (+ TMEM owner), 2-3 idle, 4-7 softmax of slot 0, 8-11 softmax of slot 1
 constexpr int BOXC = 64;          // bf16 columns per TMA box = 128 bytes = one swizzle row
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -86,14 +86,20 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
       "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+// tcgen05.ld is asynchronous: several loads are issued back to back and ONE tcgen05.wait::ld covers them (a wait per load would expose
+// the TMEM round trip 18 times per score row).  `tmem_ld_fence` ties the destination registers to the wait so no use can move above it.
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
         "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_fence(uint32_t (&r)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) asm volatile("" : "+r"(r[i]));
 }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
@@ -118,55 +124,88 @@ __device__ __forceinline__ void stg256(void* p, const uint32_t (&v)[8]) {
 
 struct Geo {
   int B, H, Hkv, L, L16, NB;          // NB = L16 - 128: rows / keys of tile B (0: no tile B)
-  int stages;
+  int stages, slots;                  // shared-memory ring depth; items in flight per CTA (each slot owns a TMEM region + 4 softmax warps)
   uint32_t box_bytes, stage_bytes;    // one [L16 x 64] box; Q + K + V of one item
-  uint32_t sb_col, oa_col, ob_col;    // TMEM columns of S_B, O_A, O_B (S_A sits at 0)
+  uint32_t sb_col, o_col, slot_cols;  // per slot: S_A at +0, S_B at +sb_col, O (O_B, then O_A) at +o_col
   float sl2;                          // softmax scale * log2(e)
   const int32_t* key_mask;
   __nv_bfloat16* out; long long o_sb, o_st;
 };
 
-// One softmax thread = one query row of a tile.  `q`: the row's query index, `ncols`: key columns of the tile (multiple of 16),
-// `s_col` / `o_col`: TMEM columns of the tile's scores and output.
-template <int DH>
-__device__ __forceinline__ void softmax_tile(const Geo& g, uint32_t tmem_lane_base, uint32_t s_col, uint32_t o_col, int q, int ncols, int warp_kmax,
-                                             const uint32_t* s_mask, uint32_t s_full, uint32_t p_ready, uint32_t o_full, uint32_t o_free,
-                                             uint32_t phase, int b, int h, int lane) {
-  // keys this warp can ever see (causal): units of 16 columns, warp-uniform
+// Valid-key bits of the 16 score columns [16u, 16u + 16) for query row q: key-padding bits AND the causal bound j <= q.
+__device__ __forceinline__ uint32_t unit_bits(const uint32_t* s_mask, int u, int q) {
+  const uint32_t key16 = (s_mask[u >> 1] >> ((u & 1) * 16)) & 0xFFFFu;
+  const int n_ok = q - u * 16 + 1;                       // leading columns the causal mask allows
+  const uint32_t c16 = n_ok >= 16 ? 0xFFFFu : (n_ok <= 0 ? 0u : ((1u << n_ok) - 1u));
+  return key16 & c16;
+}
+
+// Softmax of one score row per thread (TMEM lane = row): two sweeps over the row's scores (row max, then exp2 / row sum / P), each in
+// batches of 64 columns — four x16 loads in flight, one wait.  The bf16 probabilities overwrite the score columns (P aliases S).  A
+// 16-column unit whose keys are all attendable for every row of the warp (the common case left of the causal diagonal) takes a
+// select-free path.  `q`: query index of the row, `ncols`: key columns of the tile, `warp_kmax`: largest key any row of the warp sees.
+// Returns the row sum.
+__device__ __forceinline__ float softmax_rows(const Geo& g, uint32_t srow, int q, int ncols, int warp_kmax, const uint32_t* s_mask) {
   const int nu = min(ncols, (warp_kmax + 16) & ~15) >> 4;
   const int nu_all = ncols >> 4;
-  mbar_wait(s_full, phase);
-  tc_fence_after();
-  const uint32_t srow = tmem_lane_base + s_col;
+  const int nbatch = (nu + 3) >> 2;
   float m = -INFINITY;
-  for (int u = 0; u < nu; ++u) {
-    uint32_t r[16];
-    tmem_ld16(srow + u * 16, r);
-    const uint32_t bits = s_mask[u >> 1] >> ((u & 1) * 16);
+  for (int bt = 0; bt < nbatch; ++bt) {
+    uint32_t r[4][16];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      const int j = u * 16 + c;
-      const bool ok = ((bits >> c) & 1u) && j <= q;
-      m = fmaxf(m, ok ? __uint_as_float(r[c]) : -INFINITY);
+    for (int i = 0; i < 4; ++i) tmem_ld16_issue(srow + (bt * 4 + i) * 16, r[i]);   // unconditional: columns past `nu` stay inside the 512 and are skipped below
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int u = bt * 4 + i;
+      if (u < nu) {
+        tmem_ld_fence(r[i]);
+        const uint32_t vb = unit_bits(s_mask, u, q);
+        if (__all_sync(0xffffffffu, vb == 0xFFFFu)) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) m = fmaxf(m, __uint_as_float(r[i][c]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) m = fmaxf(m, ((vb >> c) & 1u) ? __uint_as_float(r[i][c]) : -INFINITY);
+        }
+      }
     }
   }
   const float mref = m == -INFINITY ? 0.f : m * g.sl2;
   float l = 0.f;
-  for (int u = 0; u < nu; ++u) {
-    uint32_t r[16], pk[8];
-    tmem_ld16(srow + u * 16, r);
-    const uint32_t bits = s_mask[u >> 1] >> ((u & 1) * 16);
+  for (int bt = 0; bt < nbatch; ++bt) {
+    uint32_t r[4][16];
 #pragma unroll
-    for (int c = 0; c < 16; c += 2) {
-      const int j = u * 16 + c;
-      const float p0 = (((bits >> c) & 1u) && j <= q) ? ex2(fmaf(__uint_as_float(r[c]), g.sl2, -mref)) : 0.f;
-      const float p1 = (((bits >> (c + 1)) & 1u) && j + 1 <= q) ? ex2(fmaf(__uint_as_float(r[c + 1]), g.sl2, -mref)) : 0.f;
-      const uint32_t w = pack2(p0, p1);
-      // the row sum is taken over the ROUNDED probabilities the P.V product multiplies with
-      l += __uint_as_float(w << 16) + __uint_as_float(w & 0xffff0000u);
-      pk[c >> 1] = w;
+    for (int i = 0; i < 4; ++i) tmem_ld16_issue(srow + (bt * 4 + i) * 16, r[i]);
+    tmem_ld_wait();
+    // every score column of this batch is in registers: the bf16 probabilities may now overwrite score columns (8u + 8 <= 16u + 16,
+    // and the batch's own columns have been read)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int u = bt * 4 + i;
+      if (u < nu) {
+        tmem_ld_fence(r[i]);
+        uint32_t pk[8];
+        const uint32_t vb = unit_bits(s_mask, u, q);
+        if (__all_sync(0xffffffffu, vb == 0xFFFFu)) {
+#pragma unroll
+          for (int c = 0; c < 16; c += 2) {
+            const float p0 = ex2(fmaf(__uint_as_float(r[i][c]), g.sl2, -mref)), p1 = ex2(fmaf(__uint_as_float(r[i][c + 1]), g.sl2, -mref));
+            l += p0 + p1;
+            pk[c >> 1] = pack2(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 16; c += 2) {
+            const float p0 = ((vb >> c) & 1u) ? ex2(fmaf(__uint_as_float(r[i][c]), g.sl2, -mref)) : 0.f;
+            const float p1 = ((vb >> (c + 1)) & 1u) ? ex2(fmaf(__uint_as_float(r[i][c + 1]), g.sl2, -mref)) : 0.f;
+            l += p0 + p1;
+            pk[c >> 1] = pack2(p0, p1);
+          }
+        }
+        tmem_st8(srow + u * 8, pk);
+      }
     }
-    tmem_st8(srow + u * 8, pk);      // P (bf16 pairs) overwrites score columns that were already consumed: 8u + 8 <= 16u + 16
   }
   {
     const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
@@ -174,61 +213,79 @@ __device__ __forceinline__ void softmax_tile(const Geo& g, uint32_t tmem_lane_ba
   }
   tmem_st_wait();
   tc_fence_before();
-  __syncwarp();
-  if (lane == 0) mbar_arrive(p_ready);
-  // ---- O = P V is on its way: drain it, normalise, store ----
-  mbar_wait(o_full, phase);
-  tc_fence_after();
+  return l;
+}
+
+// Drains one output row per thread: O / row sum -> bf16 -> global (128 or 256 contiguous bytes per row).
+template <int DH>
+__device__ __forceinline__ void drain_rows(const Geo& g, uint32_t orow, float l, int q, int b, int h) {
   const float inv = l > 0.f ? 1.f / l : 0.f;
   __nv_bfloat16* op = g.out + (size_t)b * g.o_sb + (size_t)q * g.o_st + (size_t)h * DH;
   const bool live = q < g.L;
 #pragma unroll
-  for (int c0 = 0; c0 < DH; c0 += 16) {
-    uint32_t r[16], w[8];
-    tmem_ld16(tmem_lane_base + o_col + c0, r);
+  for (int c0 = 0; c0 < DH; c0 += 64) {
+    uint32_t r[4][16];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) w[e] = pack2(__uint_as_float(r[2 * e]) * inv, __uint_as_float(r[2 * e + 1]) * inv);
-    if (live) stg256(op + c0, w);
+    for (int i = 0; i < 4; ++i) tmem_ld16_issue(orow + c0 + i * 16, r[i]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      tmem_ld_fence(r[i]);
+      uint32_t w[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) w[e] = pack2(__uint_as_float(r[i][2 * e]) * inv, __uint_as_float(r[i][2 * e + 1]) * inv);
+      if (live) stg256(op + c0 + i * 16, w);
+    }
   }
   tc_fence_before();
-  __syncwarp();
-  if (lane == 0) mbar_arrive(o_free);
 }
+
+// Barrier block (8 bytes each) behind the stage ring:  per stage: qkv_full, qkv_empty, mask_ready;  per slot: s_full, pb_ready, pa_ready,
+// ob_full, ob_drained, oa_full, o_free.
+constexpr int MAX_STAGES = 4, MAX_SLOTS = 2;
+constexpr uint32_t BAR_FULL = 0, BAR_EMPTY = 8 * MAX_STAGES, BAR_MASK = 16 * MAX_STAGES, BAR_SLOT = 24 * MAX_STAGES;
+constexpr uint32_t SL_SFULL = 0, SL_PB = 8, SL_PA = 16, SL_OBFULL = 24, SL_OBDRAINED = 32, SL_OAFULL = 40, SL_OFREE = 48, SL_BYTES = 56;
+constexpr uint32_t BAR_BYTES = BAR_SLOT + MAX_SLOTS * SL_BYTES + 8;     // + the TMEM base address slot
 
 template <int DH>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_tm_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k, const __grid_constant__ CUtensorMap tma_v, Geo g) {
   constexpr int NBOX = DH / BOXC;      // 64-column boxes per operand
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint32_t s_mask[12][8];   // per warp: key-valid bits of the current item
+  __shared__ uint32_t s_mask[MAX_STAGES][8];    // per stage: key-valid bits of the item's scene (written by the producer warp)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = smem_base + g.stages * g.stage_bytes;
-  const uint32_t qkv_full = bars, qkv_empty = bars + 16;             // [2] each
-  const uint32_t sa_full = bars + 32, sb_full = bars + 40, pa_ready = bars + 48, pb_ready = bars + 56;
-  const uint32_t oa_full = bars + 64, ob_full = bars + 72, oa_free = bars + 80, ob_free = bars + 88;
-  const uint32_t tmem_slot = bars + 96;
+  const uint32_t tmem_slot = bars + BAR_SLOT + MAX_SLOTS * SL_BYTES;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nbw = (g.NB + 31) >> 5;                                   // softmax-B warps with live rows
+  const int nbw = (g.NB + 31) >> 5;                                   // warps of a slot with live tile-B rows
   const int n_items = g.B * g.H;
+  const int my_items = blockIdx.x < n_items ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  // (scene, head) of this CTA's n-th item without a division per item: it = blockIdx.x + n * gridDim.x
+  const int step_b = (int)gridDim.x / g.H, step_h = (int)gridDim.x % g.H;
+  const int b0 = (int)blockIdx.x / g.H, h0 = (int)blockIdx.x % g.H;
+  const int hrep = g.H / g.Hkv;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_q)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_k)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_v)) : "memory");
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(qkv_full + 8 * s, 1);
-      mbar_init(qkv_empty + 8 * s, 1);
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      mbar_init(bars + BAR_FULL + 8 * s, 1);
+      mbar_init(bars + BAR_EMPTY + 8 * s, 1);
+      mbar_init(bars + BAR_MASK + 8 * s, 1);
     }
-    mbar_init(sa_full, 1);
-    mbar_init(sb_full, 1);
-    mbar_init(pa_ready, 4);
-    mbar_init(pb_ready, nbw > 0 ? nbw : 1);
-    mbar_init(oa_full, 1);
-    mbar_init(ob_full, 1);
-    mbar_init(oa_free, 4);
-    mbar_init(ob_free, nbw > 0 ? nbw : 1);
+    for (int k = 0; k < MAX_SLOTS; ++k) {
+      const uint32_t sb = bars + BAR_SLOT + k * SL_BYTES;
+      mbar_init(sb + SL_SFULL, 1);
+      mbar_init(sb + SL_PB, nbw > 0 ? nbw : 1);
+      mbar_init(sb + SL_PA, 4);
+      mbar_init(sb + SL_OBFULL, 1);
+      mbar_init(sb + SL_OBDRAINED, nbw > 0 ? nbw : 1);
+      mbar_init(sb + SL_OAFULL, 1);
+      mbar_init(sb + SL_OFREE, 4);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -241,99 +298,139 @@ attn_tm_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int n = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
-        const int s = n % g.stages;
-        const uint32_t use = (uint32_t)(n / g.stages);
-        const int b = it / g.H, h = it % g.H, hk = h / (g.H / g.Hkv);
-        mbar_wait(qkv_empty + 8 * s, (use & 1u) ^ 1u);
-        mbar_expect_tx(qkv_full + 8 * s, g.stage_bytes);
+    // ===================== TMA producer (+ the scene's key-valid bits, off the softmax warps' critical path) =====================
+    int b = b0, h = h0, s = 0;
+    uint32_t use = 0;
+    for (int n = 0; n < my_items; ++n) {
+      if (lane == 0) mbar_wait(bars + BAR_EMPTY + 8 * s, (use & 1u) ^ 1u);   // also frees the stage's mask words (read before P is ready)
+      __syncwarp();
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {                                          // HF:399: padding keys are masked for every query
+        const int j = w * 32 + lane;
+        const bool ok = j < g.L && (!g.key_mask || __ldg(g.key_mask + (size_t)b * g.L + j) != 0);
+        const uint32_t bits = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) s_mask[s][w] = bits;
+      }
+      if (lane == 0) {
+        mbar_arrive(bars + BAR_MASK + 8 * s);
+        const uint32_t full = bars + BAR_FULL + 8 * s;
+        mbar_expect_tx(full, g.stage_bytes);
         const uint32_t st = smem_base + s * g.stage_bytes;
+        const int hk = h / hrep;
 #pragma unroll
         for (int c = 0; c < NBOX; ++c) {
-          tma_load_2d(st + c * g.box_bytes, &tma_q, qkv_full + 8 * s, h * DH + c * BOXC, b * g.L);
-          tma_load_2d(st + (NBOX + c) * g.box_bytes, &tma_k, qkv_full + 8 * s, hk * DH + c * BOXC, b * g.L);
-          tma_load_2d(st + (2 * NBOX + c) * g.box_bytes, &tma_v, qkv_full + 8 * s, hk * DH + c * BOXC, b * g.L);
+          tma_load_2d(st + c * g.box_bytes, &tma_q, full, h * DH + c * BOXC, b * g.L);
+          tma_load_2d(st + (NBOX + c) * g.box_bytes, &tma_k, full, hk * DH + c * BOXC, b * g.L);
+          tma_load_2d(st + (2 * NBOX + c) * g.box_bytes, &tma_v, full, hk * DH + c * BOXC, b * g.L);
         }
       }
+      __syncwarp();
+      b += step_b; h += step_h;
+      if (h >= g.H) { h -= g.H; ++b; }
+      if (++s == g.stages) { s = 0; ++use; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // Software pipeline over this CTA's items with a skew of (slots - 1):  iteration n issues S(n) = Q K^T of item n, then the P.V
+    // products of item n - (slots - 1), whose softmax ran while S(n) was being issued / computed.  tcgen05.mma executes in issue order,
+    // so an accumulator region is never overwritten before the products that read it (issued earlier by this thread) have retired.
     if (lane == 0) {
       const uint32_t id_sa = idesc_f16(128, g.L16, 0), id_sb = idesc_f16(128, g.NB > 0 ? g.NB : 16, 0), id_pv = idesc_f16(128, DH, 1);
       const int qa0 = g.L16 - 128;      // first query row of tile A
-      int n = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
-        const int s = n % g.stages;
-        const uint32_t use = (uint32_t)(n / g.stages), ph = (uint32_t)(n & 1);
-        const uint32_t sq = smem_base + s * g.stage_bytes, sk = sq + NBOX * g.box_bytes, sv = sk + NBOX * g.box_bytes;
-        mbar_wait(qkv_full + 8 * s, use & 1u);
-        tc_fence_after();
-        // S_A = Q[qa0 .. qa0+128) . K^T over all L16 keys.  The previous item's P.V products (issued by this thread, executed in
-        // order) have consumed the columns these accumulators overwrite.
-#pragma unroll
-        for (int k = 0; k < DH / 16; ++k) {
-          const uint32_t boff = (uint32_t)(k >> 2) * g.box_bytes + (uint32_t)(k & 3) * 32u;
-          umma_ss(tmem_base, desc_kmajor(sq + boff + (uint32_t)qa0 * 128u), desc_kmajor(sk + boff), id_sa, k != 0);
-        }
-        umma_commit(sa_full);
-        if (g.NB > 0) {
-#pragma unroll
-          for (int k = 0; k < DH / 16; ++k) {
-            const uint32_t boff = (uint32_t)(k >> 2) * g.box_bytes + (uint32_t)(k & 3) * 32u;
-            umma_ss(tmem_base + g.sb_col, desc_kmajor(sq + boff), desc_kmajor(sk + boff), id_sb, k != 0);
-          }
-          umma_commit(sb_full);
-          // O_B = P_B . V[0 .. NB)
-          mbar_wait(pb_ready, ph);
-          mbar_wait(ob_free, ph ^ 1u);
+      const int skew = g.slots - 1;
+      for (int n = 0; n < my_items + skew; ++n) {
+        if (n < my_items) {
+          const int s = n % g.stages, k = n % g.slots;
+          const uint32_t use = (uint32_t)(n / g.stages);
+          const uint32_t sq = smem_base + s * g.stage_bytes, sk = sq + NBOX * g.box_bytes;
+          const uint32_t tS = tmem_base + k * g.slot_cols, sbar = bars + BAR_SLOT + k * SL_BYTES;
+          mbar_wait(bars + BAR_FULL + 8 * s, use & 1u);
           tc_fence_after();
-          for (int kk = 0; kk < g.NB / 16; ++kk)
-            umma_ts(tmem_base + g.ob_col, tmem_base + g.sb_col + kk * 8, desc_mnmajor(sv + (uint32_t)kk * 2048u, g.box_bytes), id_pv, kk != 0);
-          umma_commit(ob_full);
+#pragma unroll
+          for (int kk = 0; kk < DH / 16; ++kk) {        // S_A = Q[qa0 .. qa0 + 128) . K^T over all L16 keys
+            const uint32_t boff = (uint32_t)(kk >> 2) * g.box_bytes + (uint32_t)(kk & 3) * 32u;
+            umma_ss(tS, desc_kmajor(sq + boff + (uint32_t)qa0 * 128u), desc_kmajor(sk + boff), id_sa, kk != 0);
+          }
+          if (g.NB > 0) {
+#pragma unroll
+            for (int kk = 0; kk < DH / 16; ++kk) {      // S_B = Q[0 .. 128) . K[0 .. NB)^T
+              const uint32_t boff = (uint32_t)(kk >> 2) * g.box_bytes + (uint32_t)(kk & 3) * 32u;
+              umma_ss(tS + g.sb_col, desc_kmajor(sq + boff), desc_kmajor(sk + boff), id_sb, kk != 0);
+            }
+          }
+          umma_commit(sbar + SL_SFULL);
         }
-        // O_A = P_A . V
-        mbar_wait(pa_ready, ph);
-        mbar_wait(oa_free, ph ^ 1u);
-        tc_fence_after();
-        for (int kk = 0; kk < g.L16 / 16; ++kk)
-          umma_ts(tmem_base + g.oa_col, tmem_base + kk * 8, desc_mnmajor(sv + (uint32_t)kk * 2048u, g.box_bytes), id_pv, kk != 0);
-        umma_commit(oa_full);
-        umma_commit(qkv_empty + 8 * s);      // every MMA that reads this stage has retired when this arrives
+        const int m = n - skew;
+        if (m >= 0) {
+          const int s = m % g.stages, k = m % g.slots;
+          const uint32_t ph = (uint32_t)(m / g.slots) & 1u;
+          const uint32_t sv = smem_base + s * g.stage_bytes + 2 * NBOX * g.box_bytes;
+          const uint32_t tS = tmem_base + k * g.slot_cols, tO = tS + g.o_col, sbar = bars + BAR_SLOT + k * SL_BYTES;
+          mbar_wait(sbar + SL_OFREE, ph ^ 1u);          // the slot's previous output has been drained
+          if (g.NB > 0) {                               // O_B = P_B . V[0 .. NB)
+            mbar_wait(sbar + SL_PB, ph);
+            tc_fence_after();
+            for (int kk = 0; kk < g.NB / 16; ++kk)
+              umma_ts(tO, tS + g.sb_col + kk * 8, desc_mnmajor(sv + (uint32_t)kk * 2048u, g.box_bytes), id_pv, kk != 0);
+            umma_commit(sbar + SL_OBFULL);
+          }
+          mbar_wait(sbar + SL_PA, ph);                  // O_A = P_A . V   (into the columns O_B was drained from)
+          if (g.NB > 0) mbar_wait(sbar + SL_OBDRAINED, ph);
+          tc_fence_after();
+          for (int kk = 0; kk < g.L16 / 16; ++kk)
+            umma_ts(tO, tS + kk * 8, desc_mnmajor(sv + (uint32_t)kk * 2048u, g.box_bytes), id_pv, kk != 0);
+          umma_commit(sbar + SL_OAFULL);
+          umma_commit(bars + BAR_EMPTY + 8 * s);        // every MMA that reads this stage has retired when this arrives
+        }
       }
     }
-  } else if (warp >= 4) {
-    // ===================== softmax / output warps =====================
-    const bool tile_a = warp < 8;
-    const int wq = warp & 3;                                  // TMEM lane quarter of this warp
-    const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
+  } else if (warp >= 4 && ((warp - 4) >> 2) < g.slots) {
+    // ===================== softmax / output warps: slot k = (warp - 4) / 4, TMEM lane quarter wq = warp % 4 =====================
+    const int k = (warp - 4) >> 2, wq = warp & 3;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16) + k * g.slot_cols;
+    const uint32_t sbar = bars + BAR_SLOT + k * SL_BYTES;
     const int qa0 = g.L16 - 128;
-    if (tile_a || wq < nbw) {
-      int n = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
-        const int b = it / g.H, h = it % g.H;
-        // key-valid bits of this scene (HF:399: padding keys are masked for every query)
-#pragma unroll
-        for (int w = 0; w < 8; ++w) {
-          const int j = w * 32 + lane;
-          const bool ok = j < g.L && (!g.key_mask || g.key_mask[(size_t)b * g.L + j] != 0);
-          const uint32_t bits = __ballot_sync(0xffffffffu, ok);
-          if (lane == 0) s_mask[warp][w] = bits;
-        }
+    const bool has_b = wq < nbw;
+    // this slot's items: n = k, k + slots, ...
+    int b = b0, h = h0;
+    for (int i = 0; i < k; ++i) {
+      b += step_b; h += step_h;
+      if (h >= g.H) { h -= g.H; ++b; }
+    }
+    int j = 0;
+    for (int n = k; n < my_items; n += g.slots, ++j) {
+      const int st = n % g.stages;
+      const uint32_t ph = (uint32_t)j & 1u;
+      mbar_wait(bars + BAR_MASK + 8 * st, (uint32_t)(n / g.stages) & 1u);
+      mbar_wait(sbar + SL_SFULL, ph);
+      tc_fence_after();
+      float l_b = 0.f;
+      const int qb = wq * 32 + lane;                    // tile B row = query index
+      if (has_b) {
+        // rows >= NB of tile B are not part of the problem: their query index is pushed past L so nothing is stored for them
+        l_b = softmax_rows(g, lane_base + g.sb_col, qb < g.NB ? qb : g.L + qb, g.NB, min(wq * 32 + 31, g.NB - 1), s_mask[st]);
         __syncwarp();
-        const uint32_t ph = (uint32_t)(n & 1);
-        if (tile_a) {
-          const int q = qa0 + wq * 32 + lane;
-          softmax_tile<DH>(g, lane_base, 0u, g.oa_col, q, g.L16, qa0 + wq * 32 + 31, s_mask[warp], sa_full, pa_ready, oa_full, oa_free, ph, b, h, lane);
-        } else {
-          const int q = wq * 32 + lane;
-          // rows >= NB of tile B are not part of the problem: q is pushed past L so nothing is stored for them
-          softmax_tile<DH>(g, lane_base, g.sb_col, g.ob_col, q < g.NB ? q : g.L + q, g.NB, min(wq * 32 + 31, g.NB - 1), s_mask[warp], sb_full,
-                           pb_ready, ob_full, ob_free, ph, b, h, lane);
-        }
+        if (lane == 0) mbar_arrive(sbar + SL_PB);
+      }
+      const int qa = qa0 + wq * 32 + lane;
+      const float l_a = softmax_rows(g, lane_base, qa, g.L16, qa0 + wq * 32 + 31, s_mask[st]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sbar + SL_PA);
+      if (has_b) {
+        mbar_wait(sbar + SL_OBFULL, ph);
+        tc_fence_after();
+        drain_rows<DH>(g, lane_base + g.o_col, l_b, qb < g.NB ? qb : g.L + qb, b, h);
         __syncwarp();
+        if (lane == 0) mbar_arrive(sbar + SL_OBDRAINED);
+      }
+      mbar_wait(sbar + SL_OAFULL, ph);
+      tc_fence_after();
+      drain_rows<DH>(g, lane_base + g.o_col, l_a, qa, b, h);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sbar + SL_OFREE);
+      for (int i = 0; i < g.slots; ++i) {
+        b += step_b; h += step_h;
+        if (h >= g.H) { h -= g.H; ++b; }
       }
     }
   }
@@ -400,12 +497,23 @@ int attention_tm_launch(const tcavp_attn_args& a, cudaStream_t stream) {
   g.B = a.B; g.H = a.H; g.Hkv = a.Hkv; g.L = L; g.L16 = L16; g.NB = NB;
   g.box_bytes = (uint32_t)L16 * 128u;
   g.stage_bytes = 3u * (uint32_t)(a.dh / BOXC) * g.box_bytes;
-  g.stages = 2u * g.stage_bytes + 2048u <= 225u * 1024u ? 2 : 1;
-  if ((size_t)g.stages * g.stage_bytes + 2048 > 225 * 1024) return 1;
-  g.sb_col = (uint32_t)((L16 + 31) / 32 * 32);
-  g.oa_col = g.sb_col + (uint32_t)(NB > 0 ? (NB + 31) / 32 * 32 : 0);
-  g.ob_col = g.oa_col + (uint32_t)a.dh;
-  if (g.ob_col + (uint32_t)(NB > 0 ? a.dh : 0) > 512u) return 1;
+  // TMEM per item in flight: S_A (L16 columns), S_B (NB columns) right behind it, one output region (O_B, then O_A)
+  g.sb_col = (uint32_t)L16;
+  g.o_col = (uint32_t)((L16 + NB + 31) / 32 * 32);
+  g.slot_cols = g.o_col + (uint32_t)a.dh;
+  if (g.slot_cols > 512u) return 1;
+  static int max_slots = -1;
+  if (max_slots < 0) {
+    const char* e = getenv("TCAVP_ATTN_SLOTS");       // 1: one item in flight per CTA (A/B runs)
+    max_slots = e ? atoi(e) : MAX_SLOTS;
+    if (max_slots < 1 || max_slots > MAX_SLOTS) max_slots = MAX_SLOTS;
+  }
+  const int fit = (int)((225u * 1024u - 2048u) / g.stage_bytes);     // stages that fit in shared memory
+  if (fit < 1) return 1;
+  g.slots = (2u * g.slot_cols <= 512u && fit >= 2 && max_slots >= 2) ? 2 : 1;
+  g.stages = fit >= 2 * g.slots ? 2 * g.slots : (fit >= g.slots ? (fit / g.slots) * g.slots : 1);
+  if (g.stages > MAX_STAGES) g.stages = MAX_STAGES;
+  if (g.stages < g.slots) g.slots = 1;
   g.sl2 = a.scale * 1.4426950408889634f;
   g.key_mask = a.key_mask;
   g.out = reinterpret_cast<__nv_bfloat16*>(a.out); g.o_sb = a.o_sb; g.o_st = a.o_st;
@@ -415,7 +523,7 @@ int attention_tm_launch(const tcavp_attn_args& a, cudaStream_t stream) {
       make_map(&mv, a.v, rows, a.Hkv * a.dh, a.v_st, L16))
     return 1;
   // at least 118 KB so that a second CTA can never become co-resident on an SM (each CTA allocates all 512 TMEM columns)
-  size_t smem = (size_t)g.stages * g.stage_bytes + 256 + 1024;
+  size_t smem = (size_t)g.stages * g.stage_bytes + BAR_BYTES + 1024;
   if (smem < 118 * 1024) smem = 118 * 1024;
   const int items = a.B * a.H;
   const int grid = items < sm_count() ? items : sm_count();
