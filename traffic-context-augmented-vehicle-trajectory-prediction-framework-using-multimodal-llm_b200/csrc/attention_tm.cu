@@ -302,17 +302,16 @@ attn_tm_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
     int b = b0, h = h0, s = 0;
     uint32_t use = 0;
     for (int n = 0; n < my_items; ++n) {
-      if (lane == 0) mbar_wait(bars + BAR_EMPTY + 8 * s, (use & 1u) ^ 1u);   // also frees the stage's mask words (read before P is ready)
-      __syncwarp();
+      // key-valid words of the scene: every load is issued before the first ballot (a ballot per load would serialise eight global
+      // round trips per item and make this warp the bottleneck of the whole pipeline), and before the wait on the stage
+      int kv[8];
 #pragma unroll
       for (int w = 0; w < 8; ++w) {                                          // HF:399: padding keys are masked for every query
         const int j = w * 32 + lane;
-        const bool ok = j < g.L && (!g.key_mask || __ldg(g.key_mask + (size_t)b * g.L + j) != 0);
-        const uint32_t bits = __ballot_sync(0xffffffffu, ok);
-        if (lane == 0) s_mask[s][w] = bits;
+        kv[w] = j < g.L ? (g.key_mask ? __ldg(g.key_mask + (size_t)b * g.L + j) : 1) : 0;
       }
       if (lane == 0) {
-        mbar_arrive(bars + BAR_MASK + 8 * s);
+        mbar_wait(bars + BAR_EMPTY + 8 * s, (use & 1u) ^ 1u);                // also frees the stage's mask words (read before P is ready)
         const uint32_t full = bars + BAR_FULL + 8 * s;
         mbar_expect_tx(full, g.stage_bytes);
         const uint32_t st = smem_base + s * g.stage_bytes;
@@ -324,6 +323,13 @@ attn_tm_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
           tma_load_2d(st + (2 * NBOX + c) * g.box_bytes, &tma_v, full, hk * DH + c * BOXC, b * g.L);
         }
       }
+      __syncwarp();
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const uint32_t bits = __ballot_sync(0xffffffffu, kv[w] != 0);
+        if (lane == 0) s_mask[s][w] = bits;
+      }
+      if (lane == 0) mbar_arrive(bars + BAR_MASK + 8 * s);
       __syncwarp();
       b += step_b; h += step_h;
       if (h >= g.H) { h -= g.H; ++b; }
