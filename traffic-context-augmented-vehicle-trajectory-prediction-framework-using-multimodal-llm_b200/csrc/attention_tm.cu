@@ -141,23 +141,24 @@ __device__ __forceinline__ uint32_t unit_bits(const uint32_t* s_mask, int u, int
 }
 
 // Softmax of one score row per thread (TMEM lane = row): two sweeps over the row's scores (row max, then exp2 / row sum / P), each in
-// batches of 64 columns — four x16 loads in flight, one wait.  The bf16 probabilities overwrite the score columns (P aliases S).  A
+// batches of 32 columns — two x16 loads in flight, one wait (larger batches cost more in instruction-cache misses than they hide).  The bf16 probabilities overwrite the score columns (P aliases S).  A
 // 16-column unit whose keys are all attendable for every row of the warp (the common case left of the causal diagonal) takes a
 // select-free path.  `q`: query index of the row, `ncols`: key columns of the tile, `warp_kmax`: largest key any row of the warp sees.
 // Returns the row sum.
-__device__ __forceinline__ float softmax_rows(const Geo& g, uint32_t srow, int q, int ncols, int warp_kmax, const uint32_t* s_mask) {
+// (__noinline__: tile A and tile B share one copy — ten warps in different places of a 60 KB kernel thrash the instruction caches)
+__device__ __noinline__ float softmax_rows(const Geo& g, uint32_t srow, int q, int ncols, int warp_kmax, const uint32_t* s_mask) {
   const int nu = min(ncols, (warp_kmax + 16) & ~15) >> 4;
   const int nu_all = ncols >> 4;
-  const int nbatch = (nu + 3) >> 2;
+  const int nbatch = (nu + 1) >> 1;
   float m = -INFINITY;
   for (int bt = 0; bt < nbatch; ++bt) {
-    uint32_t r[4][16];
+    uint32_t r[2][16];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) tmem_ld16_issue(srow + (bt * 4 + i) * 16, r[i]);   // unconditional: columns past `nu` stay inside the 512 and are skipped below
+    for (int i = 0; i < 2; ++i) tmem_ld16_issue(srow + (bt * 2 + i) * 16, r[i]);   // unconditional: columns past `nu` stay inside the 512 and are skipped below
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int u = bt * 4 + i;
+    for (int i = 0; i < 2; ++i) {
+      const int u = bt * 2 + i;
       if (u < nu) {
         tmem_ld_fence(r[i]);
         const uint32_t vb = unit_bits(s_mask, u, q);
@@ -174,15 +175,15 @@ __device__ __forceinline__ float softmax_rows(const Geo& g, uint32_t srow, int q
   const float mref = m == -INFINITY ? 0.f : m * g.sl2;
   float l = 0.f;
   for (int bt = 0; bt < nbatch; ++bt) {
-    uint32_t r[4][16];
+    uint32_t r[2][16];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) tmem_ld16_issue(srow + (bt * 4 + i) * 16, r[i]);
+    for (int i = 0; i < 2; ++i) tmem_ld16_issue(srow + (bt * 2 + i) * 16, r[i]);
     tmem_ld_wait();
     // every score column of this batch is in registers: the bf16 probabilities may now overwrite score columns (8u + 8 <= 16u + 16,
     // and the batch's own columns have been read)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int u = bt * 4 + i;
+    for (int i = 0; i < 2; ++i) {
+      const int u = bt * 2 + i;
       if (u < nu) {
         tmem_ld_fence(r[i]);
         uint32_t pk[8];
@@ -218,7 +219,7 @@ __device__ __forceinline__ float softmax_rows(const Geo& g, uint32_t srow, int q
 
 // Drains one output row per thread: O / row sum -> bf16 -> global (128 or 256 contiguous bytes per row).
 template <int DH>
-__device__ __forceinline__ void drain_rows(const Geo& g, uint32_t orow, float l, int q, int b, int h) {
+__device__ __noinline__ void drain_rows(const Geo& g, uint32_t orow, float l, int q, int b, int h) {
   const float inv = l > 0.f ? 1.f / l : 0.f;
   __nv_bfloat16* op = g.out + (size_t)b * g.o_sb + (size_t)q * g.o_st + (size_t)h * DH;
   const bool live = q < g.L;
