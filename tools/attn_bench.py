@@ -50,7 +50,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         run()
     else:
-        for flag, slots in (("1", "2"), ("1", "1"), ("0", "1")):
-            print(f"--- TCAVP_ATTN_TCGEN05={flag} TCAVP_ATTN_SLOTS={slots}", flush=True)
-            subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=dict(os.environ, TCAVP_ATTN_TCGEN05=flag, TCAVP_ATTN_SLOTS=slots),
-                           check=False)
+        for flag, slots, ub in (("1", "2", "1"), ("1", "2", "2"), ("1", "1", "1"), ("0", "1", "1")):
+            print(f"--- TCAVP_ATTN_TCGEN05={flag} TCAVP_ATTN_SLOTS={slots} TCAVP_ATTN_UB={ub}", flush=True)
+            subprocess.run([sys.executable, os.path.abspath(__file__), "child"],
+                           env=dict(os.environ, TCAVP_ATTN_TCGEN05=flag, TCAVP_ATTN_SLOTS=slots, TCAVP_ATTN_UB=ub), check=False)

@@ -141,24 +141,25 @@ __device__ __forceinline__ uint32_t unit_bits(const uint32_t* s_mask, int u, int
 }
 
 // Softmax of one score row per thread (TMEM lane = row): two sweeps over the row's scores (row max, then exp2 / row sum / P), each in
-// batches of 32 columns — two x16 loads in flight, one wait (larger batches cost more in instruction-cache misses than they hide).  The bf16 probabilities overwrite the score columns (P aliases S).  A
+// batches of UB x 16 columns (UB x16 loads in flight, one wait; larger batches cost more in instruction-cache misses than they hide).  The bf16 probabilities overwrite the score columns (P aliases S).  A
 // 16-column unit whose keys are all attendable for every row of the warp (the common case left of the causal diagonal) takes a
 // select-free path.  `q`: query index of the row, `ncols`: key columns of the tile, `warp_kmax`: largest key any row of the warp sees.
 // Returns the row sum.
 // (__noinline__: tile A and tile B share one copy — ten warps in different places of a 60 KB kernel thrash the instruction caches)
+template <int UB>
 __device__ __noinline__ float softmax_rows(const Geo& g, uint32_t srow, int q, int ncols, int warp_kmax, const uint32_t* s_mask) {
   const int nu = min(ncols, (warp_kmax + 16) & ~15) >> 4;
   const int nu_all = ncols >> 4;
-  const int nbatch = (nu + 1) >> 1;
+  const int nbatch = (nu + UB - 1) / UB;
   float m = -INFINITY;
   for (int bt = 0; bt < nbatch; ++bt) {
-    uint32_t r[2][16];
+    uint32_t r[UB][16];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) tmem_ld16_issue(srow + (bt * 2 + i) * 16, r[i]);   // unconditional: columns past `nu` stay inside the 512 and are skipped below
+    for (int i = 0; i < UB; ++i) tmem_ld16_issue(srow + (bt * UB + i) * 16, r[i]);   // unconditional: columns past `nu` stay inside the 512 and are skipped below
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int u = bt * 2 + i;
+    for (int i = 0; i < UB; ++i) {
+      const int u = bt * UB + i;
       if (u < nu) {
         tmem_ld_fence(r[i]);
         const uint32_t vb = unit_bits(s_mask, u, q);
@@ -175,15 +176,15 @@ __device__ __noinline__ float softmax_rows(const Geo& g, uint32_t srow, int q, i
   const float mref = m == -INFINITY ? 0.f : m * g.sl2;
   float l = 0.f;
   for (int bt = 0; bt < nbatch; ++bt) {
-    uint32_t r[2][16];
+    uint32_t r[UB][16];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) tmem_ld16_issue(srow + (bt * 2 + i) * 16, r[i]);
+    for (int i = 0; i < UB; ++i) tmem_ld16_issue(srow + (bt * UB + i) * 16, r[i]);
     tmem_ld_wait();
     // every score column of this batch is in registers: the bf16 probabilities may now overwrite score columns (8u + 8 <= 16u + 16,
     // and the batch's own columns have been read)
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int u = bt * 2 + i;
+    for (int i = 0; i < UB; ++i) {
+      const int u = bt * UB + i;
       if (u < nu) {
         tmem_ld_fence(r[i]);
         uint32_t pk[8];
@@ -248,7 +249,7 @@ constexpr uint32_t BAR_FULL = 0, BAR_EMPTY = 8 * MAX_STAGES, BAR_MASK = 16 * MAX
 constexpr uint32_t SL_SFULL = 0, SL_PB = 8, SL_PA = 16, SL_OBFULL = 24, SL_OBDRAINED = 32, SL_OAFULL = 40, SL_OFREE = 48, SL_BYTES = 56;
 constexpr uint32_t BAR_BYTES = BAR_SLOT + MAX_SLOTS * SL_BYTES + 8;     // + the TMEM base address slot
 
-template <int DH>
+template <int DH, int UB>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_tm_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k, const __grid_constant__ CUtensorMap tma_v, Geo g) {
   constexpr int NBOX = DH / BOXC;      // 64-column boxes per operand
@@ -415,12 +416,12 @@ attn_tm_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant_
       const int qb = wq * 32 + lane;                    // tile B row = query index
       if (has_b) {
         // rows >= NB of tile B are not part of the problem: their query index is pushed past L so nothing is stored for them
-        l_b = softmax_rows(g, lane_base + g.sb_col, qb < g.NB ? qb : g.L + qb, g.NB, min(wq * 32 + 31, g.NB - 1), s_mask[st]);
+        l_b = softmax_rows<UB>(g, lane_base + g.sb_col, qb < g.NB ? qb : g.L + qb, g.NB, min(wq * 32 + 31, g.NB - 1), s_mask[st]);
         __syncwarp();
         if (lane == 0) mbar_arrive(sbar + SL_PB);
       }
       const int qa = qa0 + wq * 32 + lane;
-      const float l_a = softmax_rows(g, lane_base, qa, g.L16, qa0 + wq * 32 + 31, s_mask[st]);
+      const float l_a = softmax_rows<UB>(g, lane_base, qa, g.L16, qa0 + wq * 32 + 31, s_mask[st]);
       __syncwarp();
       if (lane == 0) mbar_arrive(sbar + SL_PA);
       if (has_b) {
@@ -534,13 +535,23 @@ int attention_tm_launch(const tcavp_attn_args& a, cudaStream_t stream) {
   if (smem < 118 * 1024) smem = 118 * 1024;
   const int items = a.B * a.H;
   const int grid = items < sm_count() ? items : sm_count();
-  if (a.dh == 64) {
-    TCAVP_CUDA(cudaFuncSetAttribute(attn_tm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_tm_kernel<64><<<grid, THREADS, smem, stream>>>(mq, mk, mv, g);
-  } else {
-    TCAVP_CUDA(cudaFuncSetAttribute(attn_tm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_tm_kernel<128><<<grid, THREADS, smem, stream>>>(mq, mk, mv, g);
+  static int ub = -1;
+  if (ub < 0) {
+    const char* e = getenv("TCAVP_ATTN_UB");           // score columns per tcgen05.ld batch / 16 (A/B runs)
+    ub = e ? atoi(e) : 1;
   }
+#define TCAVP_TM(DH_, UB_)                                                                                              \
+  do {                                                                                                                  \
+    TCAVP_CUDA(cudaFuncSetAttribute(attn_tm_kernel<DH_, UB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    attn_tm_kernel<DH_, UB_><<<grid, THREADS, smem, stream>>>(mq, mk, mv, g);                                           \
+  } while (0)
+  // one 16-column unit per batch is the fastest (smallest loop bodies: 202 us against 211 us with two units on the 768-class shape)
+  if (a.dh == 64) {
+    if (ub == 2) TCAVP_TM(64, 2); else TCAVP_TM(64, 1);
+  } else {
+    if (ub == 2) TCAVP_TM(128, 2); else TCAVP_TM(128, 1);
+  }
+#undef TCAVP_TM
   return check_launch("attn_tm_kernel");
 }
 
