@@ -90,10 +90,17 @@ def test_fp32_gradients_match_reference(lib_built, name):
             _check_against_compressed(got[k], want, rtol=0.3 if ill else 5e-3, atol=(0.3 if ill else band) * scale + 1e-6, key=k)
             assert err < (0.3 if ill else 2 * band), (k, err)
         except AssertionError as e:
-            failures.append((k, err, str(e)[:300]))
+            # where does the error sit?  (a ReLU unit whose pre-activation is ~0 for one token flips between fp32 evaluation orders and
+            # moves exactly one row of linear1.weight / one entry of linear1.bias)
+            d = (got[k].float().cpu() - full).abs().reshape(full.shape[0], -1) / (float(full.abs().max()) + 1e-8)
+            rows = d.max(dim=1).values
+            top = torch.topk(rows, min(4, rows.numel()))
+            failures.append((k, err, str(e)[:200], {"rows_over_band": int((rows > band).sum()), "n_rows": int(rows.numel()),
+                                                    "top_rows": [(int(i), float(v)) for v, i in zip(top.values, top.indices)],
+                                                    "frac_elems_over_band": float((d > band).float().mean())}))
     top = sorted(worst.items(), key=lambda kv: -kv[1])[:8]
     print("worst relative-to-max gradient errors:", top)
-    _report(f"grads_fp32_{name}", {"worst": top, "failures": [(k, e) for k, e, _ in failures]})
+    _report(f"grads_fp32_{name}", {"worst": top, "failures": [(f[0], f[1], f[3]) for f in failures]})
     assert not failures, failures[:5]
 
 
