@@ -229,3 +229,65 @@ def test_collate_matches_the_reference_collate_fn():
     # ragged / single-sample batches
     one = T.custom_collate_fn(g["samples"][3:4], pin=False)
     assert one["input_ids"].shape == (1, 12) and one["labels"].min() >= 0
+
+
+def test_prompt_cache_reproduces_the_reference_tokenisation_recipe():
+    """PromptCache.encode against the recipe of reference scripts/train.py:211-238 on a toy tokenizer: same ids / mask / labels,
+    truncation at max_length, and the prompt is tokenised once per distinct text."""
+    import torch
+
+    class Tok:                                  # whitespace tokenizer with the HF call signature the reference uses
+        calls = 0
+
+        def __call__(self, text, truncation=True, max_length=512, return_tensors="pt", add_special_tokens=False):
+            assert truncation and return_tensors == "pt" and add_special_tokens is False
+            Tok.calls += 1
+            ids = [(sum(map(ord, w)) % 997) + 1 for w in text.split()][:max_length]
+            return {"input_ids": torch.tensor([ids], dtype=torch.long), "attention_mask": torch.ones(1, len(ids), dtype=torch.long)}
+
+    tok = Tok()
+
+    def reference_recipe(prompt, answer, max_length):
+        p, a = tok(prompt, max_length=max_length), tok(answer, max_length=max_length)
+        ids = torch.cat([p["input_ids"], a["input_ids"]], dim=1)
+        mask = torch.cat([p["attention_mask"], a["attention_mask"]], dim=1)
+        labels = torch.full_like(ids, -100)
+        n = p["input_ids"].size(1)
+        labels[:, n:] = ids[:, n:]
+        return ids[0, :max_length], mask[0, :max_length], labels[0, :max_length]
+
+    prompts = [f"You are analyzing track_id={t} . Describe lane site speed neighbours Answer:" for t in (3, 3, 3, 7, 7)]
+    answers = [f"vehicle in lane {i} at speed {10 + i} with {i} neighbours " * (1 + i) for i in range(5)]
+    for max_length in (512, 12):
+        cache = T.PromptCache(tok, max_length=max_length)
+        Tok.calls = 0
+        got = [cache.encode(p, a) for p, a in zip(prompts, answers)]
+        assert Tok.calls == 5 + 2 and cache.misses == 2 and cache.hits == 3          # 5 answers + 2 distinct prompts
+        for g, p, a in zip(got, prompts, answers):
+            ids, mask, labels = reference_recipe(p, a, max_length)
+            assert torch.equal(g["input_ids"], ids) and torch.equal(g["attention_mask"], mask) and torch.equal(g["labels"], labels)
+            assert g["input_ids"].shape[0] <= max_length
+
+
+def test_trainable_and_lora_only_checkpoints_round_trip():
+    cfg = dict(T.MODEL_PRESETS["tiny"])
+    a, b = T.MultiModalTrajectoryModel(**cfg), T.MultiModalTrajectoryModel(**cfg)
+    T.deterministic_fill_(a.state_dict(), 5)
+    T.deterministic_fill_(b.state_dict(), 6)
+    tsd = a.trainable_state_dict()
+    assert set(tsd) == {n for n, p in a.named_parameters() if p.requires_grad}
+    assert not any("llama_model" in k and "lora_" not in k for k in tsd)
+    assert sum(v.numel() for v in tsd.values()) < 0.9 * sum(v.numel() for v in a.state_dict().values())
+    b.load_trainable_state_dict(tsd)
+    for k, v in b.state_dict().items():
+        assert torch.equal(v, a.state_dict()[k]) == (k in tsd), k           # trainables copied, frozen backbone untouched
+    with pytest.raises(RuntimeError):
+        b.load_trainable_state_dict({k: v for k, v in list(tsd.items())[1:]})
+    lsd = a.lora_state_dict()
+    assert all(k.startswith("base_model.model.model.layers.") and ".default." not in k for k in lsd) and len(lsd) == 2 * 2 * 2
+    c = T.MultiModalTrajectoryModel(**cfg)
+    c.load_lora_state_dict(lsd)
+    for k, v in a.lora_state_dict(peft_format=False).items():
+        assert torch.equal(c.state_dict()[k], v)
+    with pytest.raises(RuntimeError):
+        c.load_lora_state_dict({k: v for k, v in list(lsd.items())[:-1]})

@@ -9,3 +9,5 @@ from . import distributed  # noqa: F401,E402
 from .finetune import FineTuner  # noqa: F401,E402
 from .collate import custom_collate_fn, pack_to_device, ScenePack  # noqa: F401,E402
 from .evaluate import evaluate  # noqa: F401,E402
+from .prompt_cache import PromptCache  # noqa: F401,E402
+from .generate import generate_batch, generate_ids  # noqa: F401,E402

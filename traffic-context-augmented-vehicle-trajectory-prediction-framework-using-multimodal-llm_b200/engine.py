@@ -115,6 +115,7 @@ class Engine:
         wrap = mllm.llama_wrapper
         c = wrap.config
         lm = wrap.causal_lm()
+        self._lm_head_param, self._embed_param = lm.lm_head.weight, lm.model.embed_tokens.weight
         act, dev = self.act, self.dev
         H, nh, nkv, dh, I = c["hidden_size"], c["num_attention_heads"], c["num_key_value_heads"], c["head_dim"], c["intermediate_size"]
         # serve-time option: W' = W + (alpha/r) B A merged at pack time — no side path, K stays H
@@ -426,6 +427,43 @@ class Engine:
         if y is not None:
             out.update(metrics=metrics, per_scene=per_scene)
         return out
+
+    # ---- text-generation side path (generate.py) -------------------------------------------------------
+    def lm_head(self):
+        """[V, H] vocabulary projection in the activation dtype (HF:487-491); never used by forward() — its logits are discarded there."""
+        if self.llm.get("lm_head") is None:
+            w = self._lm_head_param
+            tied = w.data_ptr() == self._embed_param.data_ptr()
+            self.llm["lm_head"] = self.llm["embed"] if tied else w.detach().to(self.dev, self.act).contiguous()
+        return self.llm["lm_head"]
+
+    @torch.no_grad()
+    def token_embeds(self, ids, text_modality=False):
+        """ids (B, T) int64 -> (B, T, H) embedding rows, optionally + text_modality_embedding."""
+        B, T = ids.shape
+        H = self.llm["H"]
+        out = self._new(B, T, H)
+        if not hasattr(self, "_zero_mod"):
+            self._zero_mod = torch.zeros(H, dtype=torch.float32, device=self.dev)
+        ops.embed_text(ids.to(device=self.dev, dtype=torch.int64).contiguous(), None, self.llm["embed"], self.text_mod if text_modality else self._zero_mod,
+                       out, None, B=B, L_text=T, n_img=0, H=H)
+        return out
+
+    @torch.no_grad()
+    def prefix_embeds(self, vision, prompt_ids):
+        """Image tokens (+ vision modality) followed by the prompt embeddings (+ text modality): reference train.py:585-598."""
+        vision = vision.to(self.dev)
+        if vision.dtype not in (torch.float32, torch.bfloat16):
+            vision = vision.float()
+        ids = prompt_ids.to(device=self.dev, dtype=torch.int64).contiguous()
+        B, Lp = ids.shape
+        Q, H = self.qf["Q"], self.llm["H"]
+        L = Q + Lp
+        fused = self._new(B, L, H)
+        mask = torch.empty(B, L, dtype=torch.int32, device=self.dev)
+        self.qformer_into(vision.contiguous(), fused, L)
+        ops.embed_text(ids, None, self.llm["embed"], self.text_mod, fused, mask, B=B, L_text=Lp, n_img=Q, H=H)
+        return fused
 
     # ---- full forward -------------------------------------------------------------------------------
     def _dev_f32(self, t):

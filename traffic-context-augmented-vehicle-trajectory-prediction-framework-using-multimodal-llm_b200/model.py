@@ -222,8 +222,15 @@ class LlamaMultiModal(nn.Module):
         self.text_modality_embedding = nn.Parameter(torch.randn(1, 1, self.llama_hidden_size))
         self.tokenizer = None   # no hub access: callers pass input_ids / attention_mask (train.py:524 branch)
 
-    def generate_batch(self, *a, **k):
-        raise NotImplementedError("text generation (reference scripts/train.py:577-654) is outside the hot path (SURVEY.md §8f)")
+    def generate_batch(self, vision_embs, prompt_ids, tokenizer, max_new_tokens=128, temperature=0.9, top_k=40, top_p=0.9, device="cuda"):
+        """reference scripts/train.py:577-654 (the per-epoch sample generation of train.py:1231-1241): sampled continuation of the
+        prompt after the image-token prefix, decoded with `tokenizer`.  Runs on the owning model's engine — see generate.py."""
+        owner = self._owner() if getattr(self, "_owner", None) is not None else None
+        if owner is None:
+            raise RuntimeError("generate_batch needs the MultiModalTrajectoryModel that owns this module (its engine runs the decoder)")
+        from .generate import generate_batch
+        return generate_batch(owner, vision_embs, prompt_ids, tokenizer, max_new_tokens=max_new_tokens, temperature=temperature, top_k=top_k,
+                              top_p=top_p, device=device)
 
 
 class SelfAttentionBlock(nn.Module):
@@ -323,6 +330,8 @@ class MultiModalTrajectoryModel(nn.Module):
         self.mllm = LlamaMultiModal(base_model_name, use_lora, lora_r, lora_alpha, lora_dropout, vision_dim, q_hidden_size, q_nhead,
                                     q_enc_layers, q_dec_layers, q_num_query_tokens, **kw)
         self.llama_hidden_size = self.mllm.llama_hidden_size
+        import weakref
+        object.__setattr__(self.mllm, "_owner", weakref.ref(self))          # generate_batch runs on this model's engine (not a submodule link)
         self.ltsf = TransformerLTSF(seq_len, out_len, individual, feature_size, d_model, lane_polygon_d_model, use_post_mlp,
                                     post_mlp_hidden_dim, ltsf_nhead, ltsf_dropout, self.llama_hidden_size, 2, feature_size)
         self.feature_size, self.out_len, self.seq_len, self.d_model = feature_size, out_len, seq_len, d_model
@@ -389,6 +398,48 @@ class MultiModalTrajectoryModel(nn.Module):
         for k in [k for k in state_dict if k.startswith(a)]:
             state_dict[b + k[len(a):]] = state_dict.pop(k)
         return state_dict
+
+    # ---- trainable-only / LoRA-only checkpoints -----------------------------------------
+    def trainable_state_dict(self):
+        """Only what the fine-tune step changes: LoRA A / B, Q-Former, q_proj, modality embeddings, LTSF, lane-polygon encoder (the
+        reference writes the full fp32 state dict every time it improves, 27 GB at the 7B shape: train.py:1219-1224)."""
+        keep = {n for n, _ in self.trainable_named_parameters()}
+        return {k: v for k, v in self.state_dict().items() if k in keep}
+
+    def load_trainable_state_dict(self, state_dict, strict=True):
+        """Inverse of trainable_state_dict(): every trainable tensor must be present (strict), frozen backbone weights stay as they are."""
+        want = {n for n, _ in self.trainable_named_parameters()}
+        if strict:
+            missing, extra = sorted(want - set(state_dict)), sorted(set(state_dict) - set(self.state_dict()))
+            if missing or extra:
+                raise RuntimeError(f"load_trainable_state_dict: missing {missing[:5]} ({len(missing)}), unexpected {extra[:5]} ({len(extra)})")
+        res = self.load_state_dict(state_dict, strict=False)
+        self._engine = None
+        return res
+
+    def lora_state_dict(self, peft_format=True):
+        """LoRA adapter tensors only.  peft_format: keys as `peft.get_peft_model_state_dict` writes them into adapter_model.safetensors —
+        relative to the peft model (`base_model.model...`) and without the adapter name (`lora_A.weight`, not `lora_A.default.weight`)."""
+        pre = "mllm.llama_wrapper.llama_model."
+        out = {}
+        for k, v in self.state_dict().items():
+            if "lora_A" in k or "lora_B" in k:
+                out[k[len(pre):].replace(".default.", ".") if peft_format else k] = v
+        return out
+
+    def load_lora_state_dict(self, state_dict, peft_format=True):
+        pre = "mllm.llama_wrapper.llama_model."
+        sd = {}
+        for k, v in state_dict.items():
+            if peft_format:
+                k = pre + k.replace(".lora_A.weight", ".lora_A.default.weight").replace(".lora_B.weight", ".lora_B.default.weight")
+            sd[k] = v
+        want = {k for k in self.state_dict() if "lora_A" in k or "lora_B" in k}
+        if set(sd) != want:
+            raise RuntimeError(f"load_lora_state_dict: key mismatch (missing {sorted(want - set(sd))[:3]}, unexpected {sorted(set(sd) - want)[:3]})")
+        res = self.load_state_dict(sd, strict=False)
+        self._engine = None
+        return res
 
     # ---- engine management -------------------------------------------------------------------------
     def set_compute_dtype(self, name):
