@@ -194,14 +194,20 @@ __host__ __device__ __forceinline__ void unit_to_tile(int u, int tiles_mg, int t
 }
 constexpr int PANEL_SHIFT = 16;   // flags >> PANEL_SHIFT = panel width in n-tiles (0: no panels)
 
-enum { EPI_VEC_OUT = 1, EPI_VEC_RES = 2, EPI_VEC_BIAS = 4,
+enum { EPI_VEC_OUT = 1, EPI_VEC_RES = 2, EPI_VEC_BIAS = 4, EPI_TMA_OUT = 8,    // EPI_TMA_OUT: bf16 output staged in shared memory, stored by TMA
        DBG_NO_TMA = 16, DBG_NO_MMA = 32, DBG_NO_EPI = 64, DBG_NO_STORE = 128,   // TCAVP_GEMM_DEBUG: ablation switches for profiling (results are garbage)
        L2_W_LAST = 256, L2_A_FIRST = 512, L2_OUT_FIRST = 1024 };      // L2 eviction priorities of a panelled problem (TCAVP_GEMM_L2HINT)
 
 // Epilogue of 32 accumulator columns [nacc0, nacc0+32) of row m for one thread.  The interior-tile path (full chunk,
 // 16-byte aligned rows) is branch-light and fully vectorised; ragged edges take the scalar path.
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// `stage_row` / `half` / `lane` (EPI_TMA_OUT only): shared-memory address of this lane's row in the warp's staging tile, which half of
+// the warp's 64 accumulator columns this call covers, and the lane (= row of the 32-row tile, for the swizzle).
 __device__ __forceinline__ void epilogue_chunk(const EpilogueParams& p, int m, int pos, int nacc0, const uint32_t (&r)[32], float rs, int flags,
-                                               float& ssq) {
+                                               float& ssq, uint32_t stage_row = 0, int half = 0, int lane = 0) {
   if (m >= p.M) return;
   const int mo = remap_row(p.remap_gi, p.remap_go, p.remap_off, m);
   if (p.act == TCAVP_ACT_SWIGLU_BWD) {
@@ -329,6 +335,27 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueParams& p, int m, i
     for (int j = 0; j < 32; ++j)
       if (j < cnt) t += o[j];
     ssq += t;
+    return;
+  }
+  if (flags & EPI_TMA_OUT) {
+    // bf16 rows of the warp's 32 x 64 (SwiGLU: 32 x 32) output tile in the swizzled layout the TMA store expects: 16-byte chunk j of
+    // row r sits at chunk j ^ (r & 7) of a 128-byte row (SWIZZLE_128B) / j ^ ((r >> 1) & 3) of a 64-byte row (SWIZZLE_64B).
+    // Columns past N are written too (their accumulators come from zero-filled weight rows) and clipped by the store.
+    if (cnt == 32) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = half * 4 + q;
+        sts128(stage_row + (uint32_t)((j ^ (lane & 7)) << 4), pack_bf16(o[q * 8], o[q * 8 + 1]), pack_bf16(o[q * 8 + 2], o[q * 8 + 3]),
+               pack_bf16(o[q * 8 + 4], o[q * 8 + 5]), pack_bf16(o[q * 8 + 6], o[q * 8 + 7]));
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int j = half * 2 + q;
+        sts128(stage_row + (uint32_t)((j ^ ((lane >> 1) & 3)) << 4), pack_bf16(o[q * 8], o[q * 8 + 1]), pack_bf16(o[q * 8 + 2], o[q * 8 + 3]),
+               pack_bf16(o[q * 8 + 4], o[q * 8 + 5]), pack_bf16(o[q * 8 + 6], o[q * 8 + 7]));
+      }
+    }
     return;
   }
   if ((flags & EPI_VEC_OUT) && full) {
@@ -570,21 +597,32 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool TMA_OUT = false>
 struct PairCfg {
   static constexpr int HALF_N = BLOCK_N / 2;
   static constexpr int B_STAGE_BYTES = HALF_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = BLOCK_N >= 256 ? 6 : 8;
+  static constexpr int OUT_BYTES = TMA_OUT ? NUM_EPI_WARPS * 4096 : 0;     // one 32 x 64 bf16 staging tile per epilogue warp
+  static constexpr int STAGES = BLOCK_N >= 256 ? (TMA_OUT ? 5 : 6) : 8;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_BYTES + 256 + 1024;
 };
 
-template <int BLOCK_N>
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+
+// TMA_OUT: the epilogue warps do not store to global memory themselves.  Each warp owns 32 rows x 64 adjacent accumulator columns of
+// the tile, writes its bf16 results into a private 4 KB swizzled staging tile and lets one lane issue a cp.async.bulk.tensor store
+// (the copy engine writes full 128-byte lines and clips the tensor edges); the staging tile is reused once the previous store has
+// read it (cp.async.bulk.wait_group.read).  One operand stage is given up for the staging tiles.
+template <int BLOCK_N, bool TMA_OUT = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, EpilogueParams ep,
-                    int M, int Nacc, int K, int flags) {
-  using C = PairCfg<BLOCK_N>;
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_o,
+                    EpilogueParams ep, int M, int Nacc, int K, int flags) {
+  using C = PairCfg<BLOCK_N, TMA_OUT>;
   constexpr int PAIR_M = 2 * BLOCK_M;
   const uint32_t cta_rank = cluster_ctarank();
   const bool leader = cta_rank == 0;
@@ -592,7 +630,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_base + C::STAGES * A_STAGE_BYTES;
-  const uint32_t bars = smem_base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t smem_out = smem_base + C::STAGES * C::STAGE_BYTES;          // TMA_OUT: NUM_EPI_WARPS x 4 KB staging tiles (1024-byte aligned)
+  const uint32_t bars = smem_out + C::OUT_BYTES;
   const uint32_t full_bar = bars;                         // leader's copy is the live one
   const uint32_t empty_bar = bars + 8 * C::STAGES;        // per CTA, signalled by the multicast commit
   const uint32_t tmem_full_bar = bars + 16 * C::STAGES;   // per CTA, signalled by the multicast commit
@@ -706,6 +745,9 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     const int quarter = warp & 3;
     const int chunk0 = (warp - 2) >> 2;
     const uint32_t leader_tmem_empty = mapa_shared(tmem_empty_bar, 0);
+    const uint32_t my_stage = smem_out + (uint32_t)(warp - 2) * 4096u;
+    const bool swiglu = ep.act == TCAVP_ACT_SWIGLU;
+    const uint32_t stage_row = my_stage + (uint32_t)lane * (swiglu ? 64u : 128u);
     int it = 0;
     for (int unit = unit0; unit < num_units; unit += unit_stride, ++it) {
       const int acc = it & 1;
@@ -724,12 +766,36 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       float ssq = 0.f;
       const int pos = ep.rope_cols > 0 ? m % ep.rope_L : 0;
       if (!(flags & DBG_NO_EPI)) {
+        if (TMA_OUT) {
+          // this warp: accumulator columns [n0 + 64 chunk0, + 64) of rows [m0 + 32 quarter, + 32)
+          const int c_first = 2 * chunk0;
+          if (n0 + c_first * 32 < Nacc) {                       // warp-uniform
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous store has read the staging tile
+            __syncwarp();
 #pragma unroll 1
-        for (int c = chunk0; c < BLOCK_N / 32; c += NUM_EPI_WARPS / 4) {
-          if (n0 + c * 32 >= Nacc) break;   // warp-uniform
-          uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + c * 32, r);
-          epilogue_chunk(ep, m, pos, n0 + c * 32, r, rs, flags, ssq);
+            for (int hh = 0; hh < 2; ++hh) {
+              const int c = c_first + hh;
+              if (n0 + c * 32 >= Nacc) break;
+              uint32_t r[32];
+              tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + c * 32, r);
+              epilogue_chunk(ep, m, pos, n0 + c * 32, r, rs, flags, ssq, stage_row, hh, lane);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              const int col_acc = n0 + c_first * 32;
+              tma_store_2d(&tma_o, my_stage, swiglu ? col_acc >> 1 : col_acc, m0 + quarter * 32);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int c = chunk0; c < BLOCK_N / 32; c += NUM_EPI_WARPS / 4) {
+            if (n0 + c * 32 >= Nacc) break;   // warp-uniform
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + c * 32, r);
+            epilogue_chunk(ep, m, pos, n0 + c * 32, r, rs, flags, ssq);
+          }
         }
         if (ep.sumsq_out && m < M) sumsq_add(ep.sumsq_out + remap_row(ep.remap_gi, ep.remap_go, ep.remap_off, m), ssq);
         if ((flags & DBG_NO_STORE) && ssq == 123456.789f) reinterpret_cast<float*>(ep.out)[0] = ssq;   // keeps the ablated math alive
@@ -738,6 +804,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(leader_tmem_empty + 8 * acc);
     }
+    if (TMA_OUT && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // stores complete before the CTA retires
   }
 
   tc_fence_before();
@@ -1221,25 +1288,69 @@ static int launch_tc(const tcavp_gemm_args& a, const EpilogueParams& ep, cudaStr
   return check_launch("gemm_tc_kernel");
 }
 
+// TCAVP_GEMM_TMASTORE: 1 (default) = bf16 outputs leave through shared memory + TMA stores (pair kernel), 0 = 256-bit global stores.
+// Measured A/B on B200 (profiles/gemm_tmastore_ab_r02.txt): within +-1 % of each other on the K = 768 shapes — the kernel runs at the
+// 1 kW cap either way; the TMA form is kept as the default because it frees the epilogue warps' LSU work and writes whole lines.
+static int tma_store_pref() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TCAVP_GEMM_TMASTORE");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+
+// [rows, cols] bf16 output view for the TMA-store epilogue: box = 32 rows x box_cols (64: SWIZZLE_128B, 32: SWIZZLE_64B)
+static int make_out_map(CUtensorMap* map, void* base, int rows, int cols, int ld, int box_cols) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+    return TCAVP_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, 32u};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (output) failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld);
+    return TCAVP_ERR_CUDA;
+  }
+  return TCAVP_OK;
+}
+
 template <int BLOCK_N>
 static int launch_tc_pair(const tcavp_gemm_args& a, const EpilogueParams& ep, cudaStream_t stream) {
-  using C = PairCfg<BLOCK_N>;
-  CUtensorMap ma, mb;
+  // TMA-store epilogue: bf16 output rows in place (no row remap), 16-byte aligned rows, not the SwiGLU-backward form
+  const bool tma_out = tma_store_pref() && ep.out_dtype == TCAVP_BF16 && ep.remap_gi == 0 && ep.act != TCAVP_ACT_SWIGLU_BWD &&
+                       (ep.ldo % 8) == 0 && reinterpret_cast<uintptr_t>(ep.out) % 16 == 0;
+  CUtensorMap ma, mb, mo;
   int rc = make_map(&ma, a.A, a.M, a.K, a.lda, BLOCK_M);
   if (rc) return rc;
-  rc = make_map(&mb, a.W, a.N, a.K, a.ldw, C::HALF_N);
+  rc = make_map(&mb, a.W, a.N, a.K, a.ldw, BLOCK_N / 2);
   if (rc) return rc;
-  TCAVP_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  if (tma_out) {
+    rc = make_out_map(&mo, ep.out, ep.M, ep.N, ep.ldo, ep.act == TCAVP_ACT_SWIGLU ? 32 : 64);
+    if (rc) return rc;
+  } else {
+    mo = ma;      // unused by the kernel
+  }
+  const int smem_bytes = tma_out ? PairCfg<BLOCK_N, true>::SMEM_BYTES : PairCfg<BLOCK_N, false>::SMEM_BYTES;
+  if (tma_out) TCAVP_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<BLOCK_N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  else TCAVP_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<BLOCK_N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   const int tiles_m = (a.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), tiles_n = (a.N + BLOCK_N - 1) / BLOCK_N;
   const int units = tiles_m * tiles_n;
   const int max_pairs = sm_count() / 2;
   const int grid = (units < max_pairs ? units : max_pairs) * 2;
   int flags = epilogue_flags(ep);
+  if (tma_out) flags |= EPI_TMA_OUT;
   if (const char* e = getenv("TCAVP_GEMM_DEBUG")) flags |= atoi(e) & (DBG_NO_TMA | DBG_NO_MMA | DBG_NO_EPI | DBG_NO_STORE);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(NUM_THREADS);
-  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1249,7 +1360,8 @@ static int launch_tc_pair(const tcavp_gemm_args& a, const EpilogueParams& ep, cu
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   flags |= panel_flags(a.M, a.N, a.K, 2 * BLOCK_M, BLOCK_N, max_pairs, true);
-  TCAVP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<BLOCK_N>, ma, mb, ep, a.M, a.N, a.K, flags));
+  if (tma_out) TCAVP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<BLOCK_N, true>, ma, mb, mo, ep, a.M, a.N, a.K, flags));
+  else TCAVP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<BLOCK_N, false>, ma, mb, mo, ep, a.M, a.N, a.K, flags));
   return check_launch("gemm_tc_pair_kernel");
 }
 
