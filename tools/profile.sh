@@ -4,7 +4,7 @@
 # Each ncu pass only runs after the same command exited 0 without ncu.  Numbers printed under ncu are never bench values.
 set -u
 TAG=${1:-r01}; shift || true
-CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline ${BENCH_ARGS:-}"
+CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-secondary ${BENCH_ARGS:-}"
 mkdir -p gpurun_out
 $CMD > gpurun_out/plain_${TAG}.json 2> gpurun_out/plain_${TAG}.err || { echo "plain run failed"; tail -5 gpurun_out/plain_${TAG}.err; exit 1; }
 if [ "${LIST:-1}" = "1" ]; then
