@@ -267,11 +267,12 @@ def measure_infer(ctx, workload, steps, warmup, e2e=True, scenes=0, merge_lora=F
 
     def step():
         o = eng.forward(d["x"], d["vision"], d["polygon"], d["lens"], d["input_ids"], d["attention_mask"], y=d["y"], norm_stat=d["ns"],
-                        final_hidden=fh_dev, max_poly_len=max_poly)
+                        final_hidden=fh_dev, max_poly_len=max_poly, cuda_graph=graph)
         if world > 1:        # per-rank running sums; ONE all-reduce per evaluation pass, inside the timed region
             red.add_(torch.stack((o["sum_ade"], o["sum_fde"], b_dev)))
         return o
 
+    graph = bool(ctx.args.cuda_graph)          # one cudaGraphLaunch per step instead of ~200 kernel launches (fixed batch shape)
     for _ in range(max(warmup, 3)):
         o = step()
     if world > 1:
@@ -297,9 +298,14 @@ def measure_infer(ctx, workload, steps, warmup, e2e=True, scenes=0, merge_lora=F
     # ---- profiling pass (untimed): the same steps again with CUDA events around every launch ---------------
     n_prof = min(steps, 3)
     prof = ops.LaunchProfiler()
+    graph = False                              # the profiling pass needs the individual launches
+    lp0 = ops.launch_count()
     with prof:
         for _ in range(n_prof):
             step()
+    graph = bool(ctx.args.cuda_graph)
+    if graph:                                  # replayed launches are not seen by the library's counter: one eager step's count x steps
+        launches = (ops.launch_count() - lp0) // n_prof * steps
     torch.cuda.synchronize()
     red.zero_()
 
@@ -324,9 +330,11 @@ def measure_infer(ctx, workload, steps, warmup, e2e=True, scenes=0, merge_lora=F
 
         def e2e_enqueue(slot):
             if frozen:
-                r = model.predict_with_metrics(h["x"], None, h["polygon"], h["lens"], h["y"], h["ns"], None, None, final_hidden=h["fh"])
+                r = model.predict_with_metrics(h["x"], None, h["polygon"], h["lens"], h["y"], h["ns"], None, None, final_hidden=h["fh"],
+                                               max_poly_len=max_poly, cuda_graph=graph)
             else:
-                r = model.predict_with_metrics(h["x"], h["vision"], h["polygon"], h["lens"], h["y"], h["ns"], h["input_ids"], h["attention_mask"])
+                r = model.predict_with_metrics(h["x"], h["vision"], h["polygon"], h["lens"], h["y"], h["ns"], h["input_ids"], h["attention_mask"],
+                                               max_poly_len=max_poly, cuda_graph=graph)
             dec_host[slot].copy_(r["decoded"], non_blocking=True)
             met_host[slot].copy_(r["metrics"], non_blocking=True)
             done[slot].record()
@@ -375,6 +383,7 @@ def measure_infer(ctx, workload, steps, warmup, e2e=True, scenes=0, merge_lora=F
                                 f"{workload}: {cfg['base_model_name']} backbone, LoRA r={cfg.get('lora_r', 8)}, bf16 inference, ") +
                                f"{B} scenes/GPU/step, T_in {cfg['seq_len']} -> T_out {cfg['out_len']}, L = 16 image + {l_text} text tokens",
                    "scenes_per_gpu": B, "seq_len": Lseq, "parallelism": f"scene-parallel x{world}",
+                   "launch": "one CUDA-graph replay per step (captured once per batch shape)" if graph else "eager kernel launches",
                    "timing": "value: CUDA events around the K steps, nothing else inside" + (" but one metric all-reduce after the last step" if world > 1 else "") +
                              "; roofline: separate profiling pass; e2e: host wall clock",
                    "l2": "per-step working set (>= 1 GB of activations) is far larger than the 126 MB L2; no explicit flush",
@@ -632,6 +641,7 @@ if __name__ == "__main__":
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--scenes", type=int, default=0, help="override scenes per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=64, help="scenes per CPU forward (BASELINE.json configs[0]: 64)")
+    ap.add_argument("--cuda-graph", type=int, default=1, help="1: replay the inference forward from a CUDA graph (one launch per step), 0: eager launches")
     ap.add_argument("--no-secondary", action="store_true", help="headline workload only (skip cfg3 / cfg5 / fine-tune secondaries)")
     ap.add_argument("--secondary-steps", type=int, default=5)
     ap.add_argument("--dropout", type=float, default=None, help="--mode train: override lora / ltsf / transformer dropout p (default: the reference's 0.1)")

@@ -269,3 +269,28 @@ def test_tokenizer_branch_with_an_attached_tokenizer(lib_built):
     assert m.mllm.tokenizer.pad_token == "</s>"
     torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(got.cpu(), fix["out"]["decoded"], rtol=1e-4, atol=1e-4)
+
+
+def test_cuda_graph_replay_equals_eager_forward(lib_built):
+    """predict_with_metrics(cuda_graph=True): the forward captured once per batch shape and replayed — same results as the eager
+    launches for new inputs of the same shape (device-resident and pinned-host inputs), a second shape gets its own graph."""
+    fix = load_golden("tiny_b6")
+    m = build_filled_model(fix, "bf16", "cuda")
+    i = fix["inputs"]
+    lens = torch.tensor(i["poly_len"], dtype=torch.int32)
+    ns = torch.tensor(i["norm_stat"], dtype=torch.float32)
+
+    def args(sel, dev):
+        f = (lambda t: t[sel].contiguous().cuda()) if dev else (lambda t: t[sel].contiguous().pin_memory())
+        return (f(i["x"]), f(i["vision"]), f(i["polygon"]), f(lens), f(i["y"]), f(ns), f(i["input_ids"]), f(i["attention_mask"]))
+    for sel in (slice(0, 4), slice(2, 6), slice(0, 6)):             # two batches of one shape, then another shape
+        for dev in (True, False):
+            a = args(sel, dev)
+            eager = {k: v.clone() for k, v in m.predict_with_metrics(*a, max_poly_len=64).items() if torch.is_tensor(v)}
+            for _ in range(2):
+                got = m.predict_with_metrics(*a, max_poly_len=64, cuda_graph=True)
+                torch.cuda.synchronize()
+                torch.testing.assert_close(got["decoded"], eager["decoded"], rtol=0, atol=0)
+                torch.testing.assert_close(got["metrics"], eager["metrics"], rtol=1e-5, atol=1e-5)
+                torch.testing.assert_close(got["ade"], eager["ade"], rtol=1e-6, atol=1e-6)
+    assert len(m.engine()._graphs) == 2

@@ -473,7 +473,10 @@ class Engine:
 
     @torch.no_grad()
     def forward(self, x, vision, polygon, poly_len, input_ids, attention_mask, y=None, norm_stat=None, final_hidden=None,
-                keep_intermediates=False, max_poly_len=None):
+                keep_intermediates=False, max_poly_len=None, cuda_graph=False):
+        """`cuda_graph`: replay the ~200 launches of one forward from a CUDA graph captured per input-shape signature (serving loops
+        with a fixed batch shape).  The returned tensors are then the graph's static outputs: consume (or copy) them before the next
+        call with the same shapes."""
         dev = self.dev
         if dev.type != "cuda":
             raise ops._lib.TcavpError("the model must be on a CUDA device (there is no CPU fallback): model.to('cuda')")
@@ -489,7 +492,6 @@ class Engine:
             norm_stat = self._dev_f32(norm_stat).view(B, 4)
         else:
             y = norm_stat = None
-        out = {}
         # Host-resident (pinned) bulk inputs travel on a side stream while the polygon / temporal encoders — which only need the
         # small tensors already queued above — run on the compute stream; the compute stream joins right before the first consumer.
         bulk = [t for t in ((vision, input_ids, attention_mask) if final_hidden is None else (final_hidden,)) if torch.is_tensor(t) and not t.is_cuda]
@@ -511,27 +513,75 @@ class Engine:
                 vision, input_ids, attention_mask = pick(vision), pick(input_ids), pick(attention_mask)
             else:
                 final_hidden = pick(final_hidden)
+        if final_hidden is None:
+            vision = vision.to(dev, non_blocking=True)
+            if vision.dtype not in (torch.float32, torch.bfloat16):
+                vision = vision.float()
+            vision = vision.contiguous()
+            input_ids = input_ids.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
+            attention_mask = attention_mask.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
+        else:
+            final_hidden = final_hidden.to(device=dev, dtype=self.act, non_blocking=True).contiguous()
+        dev_in = dict(x=x, vision=vision, polygon=polygon, lens=lens, input_ids=input_ids, attention_mask=attention_mask, y=y, norm_stat=norm_stat,
+                      final_hidden=final_hidden)
+        if cuda_graph and not keep_intermediates:
+            return self._forward_graphed(dev_in, max_poly_len, copied)
+        return self._forward_device(dev_in, max_poly_len, copied, keep_intermediates)
+
+    def _forward_graphed(self, dev_in, max_poly_len, copied):
+        """One CUDA graph per (shapes, dtypes, max_poly_len) signature; inputs are copied into the graph's static buffers (device to
+        device, a few tens of MB) and the ~200 kernel launches of the forward become one cudaGraphLaunch."""
+        sig = tuple((k, None if v is None else (tuple(v.shape), v.dtype)) for k, v in dev_in.items()) + (max_poly_len,)
+        cache = self.__dict__.setdefault("_graphs", {})
+        ent = cache.pop(sig, None)
+        if copied is not None:
+            torch.cuda.current_stream().wait_event(copied)
+        if ent is None:
+            static = {k: (None if v is None else v.clone()) for k, v in dev_in.items()}
+            side = torch.cuda.Stream(device=self.dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):                 # lazy packing, rope tables, cudaFuncSetAttribute, allocator warm-up
+                    self._forward_device(static, max_poly_len, None, False)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._forward_device(static, max_poly_len, None, False)
+            ent = (g, static, out)
+            while len(cache) >= 4:
+                cache.pop(next(iter(cache)))
+        cache[sig] = ent
+        g, static, out = ent
+        for k, v in dev_in.items():
+            if v is not None:
+                static[k].copy_(v, non_blocking=True)
+        g.replay()
+        return out
+
+    def _forward_device(self, d, max_poly_len, copied, keep_intermediates):
+        """The device part of forward(): every input already lives on the device (capturable in a CUDA graph)."""
+        dev = self.dev
+        x, vision, polygon, lens, y, norm_stat, final_hidden = d["x"], d["vision"], d["polygon"], d["lens"], d["y"], d["norm_stat"], d["final_hidden"]
+        B = x.shape[0]
+        out = {}
         poly_emb = self.poly_forward(polygon, lens, max_poly_len)
         enc = self.ltsf_encode(x, B)
         if copied is not None:
             torch.cuda.current_stream().wait_event(copied)
         if final_hidden is None:
-            vision = vision.to(dev, non_blocking=True)
-            if vision.dtype not in (torch.float32, torch.bfloat16):
-                vision = vision.float()
-            ids = input_ids.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
-            am = attention_mask.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
+            ids, am = d["input_ids"], d["attention_mask"]
             Q, H = self.qf["Q"], self.llm["H"]
             L = Q + ids.shape[1]
             fused = self._new(B, L, H)
             mask = torch.empty(B, L, dtype=torch.int32, device=dev)
-            self.qformer_into(vision.contiguous(), fused, L)
+            self.qformer_into(vision, fused, L)
             ops.embed_text(ids, am, self.llm["embed"], self.text_mod, fused, mask, B=B, L_text=ids.shape[1], n_img=Q, H=H)
             if keep_intermediates:
                 out["image_tokens_plus_mod"] = fused[:, :Q].float()
             fh = self.llm_forward(fused, mask, B, L)
         else:
-            fh = final_hidden.to(device=dev, dtype=self.act).contiguous()
+            fh = final_hidden
             L = fh.shape[1]
             fh = fh.view(B * L, -1)
         out.update(self.ltsf_decode(enc, poly_emb, fh, x, B, L, y, norm_stat))

@@ -579,11 +579,13 @@ class MultiModalTrajectoryModel(nn.Module):
 
     @torch.no_grad()
     def predict_with_metrics(self, x, vision_embs, lane_polygon_batch, lane_polygon_len, y, norm_stat, input_ids, attention_mask,
-                             final_hidden=None, max_poly_len=None):
+                             final_hidden=None, max_poly_len=None, cuda_graph=False):
         """forward + the reference's test-loop reduction (train.py:1302-1322) in one pass.
         Returns dict(decoded, loss, sum_ade, sum_fde, ade[B], fde[B]) — all device tensors, no host sync.
         `max_poly_len`: host-known upper bound of lane_polygon_len when the lengths live on the device (padding rows are skipped).
         `final_hidden` (B, L, H): precomputed backbone output — the frozen-backbone path of
-        scripts/ablation_study_without_lora.py (encoder + fusion only; vision / token inputs are then ignored)."""
+        scripts/ablation_study_without_lora.py (encoder + fusion only; vision / token inputs are then ignored).
+        `cuda_graph`: replay the forward from a CUDA graph captured per batch shape (fixed-shape serving / evaluation loops); the
+        returned tensors are then reused by the next call with the same shapes — copy what you keep."""
         return self.engine().forward(x, vision_embs, lane_polygon_batch, lane_polygon_len, input_ids, attention_mask, y=y,
-                                     norm_stat=norm_stat, final_hidden=final_hidden, max_poly_len=max_poly_len)
+                                     norm_stat=norm_stat, final_hidden=final_hidden, max_poly_len=max_poly_len, cuda_graph=cuda_graph)
