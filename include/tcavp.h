@@ -42,6 +42,9 @@ int tcavp_version(void);
 int tcavp_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 long long tcavp_launch_count(void);
+/* Name of the kernel the calling thread's most recent entry-point call launched last (static string; "" before the first launch).
+ * Test aid: proves which variant a shape was routed to (e.g. the tcgen05 kernel rather than its mma.sync fallback). */
+const char* tcavp_last_kernel(void);
 /* Profiling aid: one warp spins for `ns` nanoseconds on `stream` and writes (elapsed SM cycles, elapsed ns) to out2[0..1]
  * (device memory) — the true average SM clock while other kernels run next to it. */
 int tcavp_clock_probe(unsigned long long* out2, unsigned long long ns, tcavp_stream_t stream);

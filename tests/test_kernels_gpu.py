@@ -165,6 +165,35 @@ def test_attention(ops, B, H, Hkv, Tq, Tk, dh, causal, masked, dtype):
     torch.testing.assert_close(out.float().cpu(), want, **tol)
 
 
+@pytest.mark.parametrize("B,Tq,Tk,dh", [
+    (5, 25, 144, 768),      # cfg2: 25-step horizon against the 144-token fused sequence, 768-class hidden size
+    (300, 50, 144, 768),    # cfg5: 50-step horizon, more scenes than SMs (two items per CTA: accumulator-buffer parities, ring wrap-around)
+    (3, 64, 256, 256),      # full query tile, widest key tile (TMEM columns 0..511 all used), two output chunks
+    (4, 12, 40, 128),       # one output chunk per scene (the running chunk counter alternates buffers across scenes), Tk not a multiple of 16
+    (2, 25, 144, 4096),     # 7B-class hidden size: 64 phase-1 stages and 32 output chunks per scene
+])
+def test_cross_attention_tcgen05_two_heads_on_a_shared_kv_head(ops, B, Tq, Tk, dh):
+    """The absorbed fusion cross-attention (engine.py: Engine._absorb_cross; reference train.py:793-798): two query heads of width dh
+    against keys = values = the backbone output, attention_xt.cu (tcgen05 / TMEM / TMA)."""
+    q = (_rand(B, Tq, 2, dh, seed=11) * 0.5).bfloat16()
+    x = _rand(B, Tk, 1, dh, seed=12).bfloat16()
+    scale = (dh // 2) ** -0.5 / 8
+    want = _attn_ref(q.float(), x.float(), x.float(), scale, False, None)
+    xd = x.to(DEV)
+    out = torch.full((B, Tq, 2, dh), float("nan"), dtype=torch.bfloat16, device=DEV)
+    n0 = ops.launch_count()
+    ops.attention(q.to(DEV), xd, xd, out, B=B, H=2, Hkv=1, Tq=Tq, Tk=Tk, dh=dh, q_strides=(Tq * 2 * dh, 2 * dh), k_strides=(Tk * dh, dh),
+                  v_strides=(Tk * dh, dh), o_strides=(Tq * 2 * dh, 2 * dh), scale=scale)
+    assert ops.launch_count() == n0 + 1 and ops.last_kernel() == "attn_xt_kernel"      # not the mma.sync fallback
+    torch.testing.assert_close(out.float().cpu(), want, rtol=2e-2, atol=2e-2)
+    # the rows of the padded 64-row query tiles are never stored: a guard band behind the output stays untouched
+    guard = torch.full((B * Tq + 8, 2 * dh), 7.0, dtype=torch.bfloat16, device=DEV)
+    ops.attention(q.to(DEV), xd, xd, guard, B=B, H=2, Hkv=1, Tq=Tq, Tk=Tk, dh=dh, q_strides=(Tq * 2 * dh, 2 * dh), k_strides=(Tk * dh, dh),
+                  v_strides=(Tk * dh, dh), o_strides=(Tq * 2 * dh, 2 * dh), scale=scale)
+    assert bool((guard[B * Tq:] == 7.0).all())
+    torch.testing.assert_close(guard[:B * Tq].view(B, Tq, 2, dh).float().cpu(), want, rtol=2e-2, atol=2e-2)
+
+
 @pytest.mark.parametrize("nh,nkv,dh,B", [(12, 12, 64, 160), (32, 8, 128, 20)])
 def test_llm_attention_tcgen05_on_the_packed_qkv_layout(ops, nh, nkv, dh, B):
     """The engine's call: q / k / v are column slices of one packed [B L, (nh + 2 nkv) dh] activation, more (scene, head) items than

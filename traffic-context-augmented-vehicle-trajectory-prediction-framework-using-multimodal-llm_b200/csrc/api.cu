@@ -7,6 +7,7 @@ namespace tcavp {
 
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
+static thread_local const char* g_last_kernel = "";
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -25,6 +26,7 @@ int fail_arg(const char* fmt, ...) {
 
 int check_launch(const char* what) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  g_last_kernel = what;
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {
     (void)cudaGetLastError();
@@ -77,6 +79,7 @@ int tcavp_clock_probe(unsigned long long* out2, unsigned long long ns, tcavp_str
 const char* tcavp_last_error(void) { return tcavp::g_err; }
 int tcavp_version(void) { return 100; }
 long long tcavp_launch_count(void) { return tcavp::g_launches.load(); }
+const char* tcavp_last_kernel(void) { return tcavp::g_last_kernel; }
 
 int tcavp_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;

@@ -12,6 +12,7 @@ namespace tcavp {
 int attention_tc_launch(const tcavp_attn_args& a, cudaStream_t stream);   // attention_tc.cu; returns 1 if not applicable
 int attention_tm_launch(const tcavp_attn_args& a, cudaStream_t stream);   // attention_tm.cu (tcgen05 / TMEM / TMA); returns 1 if not applicable
 int attention_x_launch(const tcavp_attn_args& a, cudaStream_t stream);    // attention_x.cu;  returns 1 if not applicable
+int attention_xt_launch(const tcavp_attn_args& a, cudaStream_t stream);   // attention_xt.cu (tcgen05: two heads on one shared K = V head); returns 1 if not applicable
 
 template <typename T, int NE>   // NE = ceil(dh / 32) head-dim elements per lane
 __global__ void __launch_bounds__(128) attn_warp_kernel(tcavp_attn_args a) {
@@ -214,7 +215,13 @@ extern "C" int tcavp_attention(const tcavp_attn_args* a, tcavp_stream_t stream_)
   TCAVP_REQUIRE(a->dtype == TCAVP_F32 || a->dtype == TCAVP_BF16, "tcavp_attention: bad dtype");
   TCAVP_REQUIRE(a->drop_thresh == 0 || (a->drop_seed != nullptr && a->drop_scale > 0.f), "tcavp_attention: dropout needs a device seed and a scale");
   if (a->dtype == TCAVP_BF16) {
-    int rc = a->dh > 128 ? attention_x_launch(*a, stream) : attention_tm_launch(*a, stream);
+    int rc = 1;
+    if (a->dh > 128) {
+      rc = attention_xt_launch(*a, stream);
+      if (rc > 0) rc = attention_x_launch(*a, stream);
+    } else {
+      rc = attention_tm_launch(*a, stream);
+    }
     if (rc > 0 && a->dh <= 128) rc = attention_tc_launch(*a, stream);
     if (rc <= 0) return rc;
     return launch_warp<__nv_bfloat16>(*a, stream);

@@ -1005,7 +1005,7 @@ struct WideCfg {
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_wide_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, EpilogueParams ep,
-                    int M, int Nacc, int K, int flags) {
+                    int M, int Nacc, int K, int flags, int split_g) {
   using C = WideCfg;
   constexpr int CTA_M = 2 * BLOCK_M, PAIR_M = 4 * BLOCK_M;
   const uint32_t cta_rank = cluster_ctarank();
@@ -1017,7 +1017,7 @@ gemm_tc_wide_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const uint32_t bars = smem_base + C::STAGES * C::STAGE_BYTES;
   const uint32_t full_bar = bars;
   const uint32_t empty_bar = bars + 8 * C::STAGES;
-  const uint32_t tmem_full_bar = bars + 16 * C::STAGES;   // 1 x 8 (+8 pad)
+  const uint32_t tmem_full_bar = bars + 16 * C::STAGES;   // 2 x 8: one per 128-row half
   const uint32_t tmem_empty_bar = tmem_full_bar + 16;     // 2 x 8: one per 128-row half
   const uint32_t tmem_slot = tmem_empty_bar + 16;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
@@ -1038,8 +1038,10 @@ gemm_tc_wide_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       mbar_init(full_bar + 8 * s, 1);
       mbar_init(empty_bar + 8 * s, 1);
     }
-    mbar_init(tmem_full_bar, 1);
-    for (int h = 0; h < 2; ++h) mbar_init(tmem_empty_bar + 8 * h, 2 * NUM_EPI_WARPS);
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(tmem_full_bar + 8 * h, 1);
+      mbar_init(tmem_empty_bar + 8 * h, 2 * NUM_EPI_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -1083,31 +1085,51 @@ gemm_tc_wide_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && lane == 0) {
       constexpr uint32_t idesc = umma_idesc(2 * BLOCK_M, C::BLOCK_N);
+      // Order of the (k-block, row half) MMAs of a tile.  The first `g` and the last `g` k-blocks are issued HALF-MAJOR (half 0 of all g
+      // k-blocks, then half 1): at the end of a tile half 0's accumulator is complete - and its drain starts - g k-blocks of half-1 MMAs
+      // before the tile ends, and at the start of the next tile half 0 is re-armed first while half 1 is still draining.  Each half's
+      // drain overlaps g x 512 cycles of tensor work on the other half instead of stalling the pipe (single accumulator buffer: all 512
+      // TMEM columns hold this tile).  The k-blocks in between are issued k-major, which frees a stage after every k-block.
+      int g = split_g < C::STAGES ? split_g : C::STAGES;
+      if (2 * g > num_kb) g = num_kb / 2;
+      if (g < 1) g = 1;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       for (int unit = unit0; unit < num_units; unit += unit_stride, ++it) {
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full_bar + 8 * stage, phase);
-          tc_fence_after();
-          const int k_left = K - kb * BLOCK_K;
-          const int ksteps = k_left >= BLOCK_K ? BLOCK_K / UMMA_K : (k_left + UMMA_K - 1) / UMMA_K;
-          const uint32_t a_addr = smem_a + stage * C::A_BYTES;
-          const uint32_t b_addr = smem_b + stage * C::B_BYTES;
-#pragma unroll
+        int kb0 = 0;
+        while (kb0 < num_kb) {
+          const int gn = (kb0 == 0 || kb0 + g >= num_kb) ? (kb0 + g <= num_kb ? g : num_kb - kb0) : 1;
+          const bool last = kb0 + gn == num_kb;
+#pragma unroll 1
           for (int h = 0; h < 2; ++h) {
-            if (kb == 0) {     // this half's accumulator columns must have been drained by the previous tile's epilogue
-              mbar_wait(tmem_empty_bar + 8 * h, (it & 1) ^ 1);
-              tc_fence_after();
+            int st = stage;
+            uint32_t ph = phase;
+            for (int j = 0; j < gn; ++j) {
+              const int kb = kb0 + j;
+              if (h == 0) {
+                mbar_wait(full_bar + 8 * st, ph);
+                tc_fence_after();
+              }
+              if (kb == 0) {     // this half's accumulator columns must have been drained by the previous tile's epilogue
+                mbar_wait(tmem_empty_bar + 8 * h, (it & 1) ^ 1);
+                tc_fence_after();
+              }
+              const int k_left = K - kb * BLOCK_K;
+              const int ksteps = k_left >= BLOCK_K ? BLOCK_K / UMMA_K : (k_left + UMMA_K - 1) / UMMA_K;
+              const uint32_t a_addr = smem_a + st * C::A_BYTES + h * A_STAGE_BYTES;
+              const uint32_t b_addr = smem_b + st * C::B_BYTES;
+              for (int k = 0; k < ksteps; ++k) {
+                umma_bf16_pair(tmem_base + h * C::BLOCK_N, umma_smem_desc(a_addr + k * UMMA_K * 2), umma_smem_desc(b_addr + k * UMMA_K * 2), idesc,
+                               (kb | k) != 0 ? 1u : 0u);
+              }
+              if (h == 1) umma_commit_pair(empty_bar + 8 * st);
+              if (++st == C::STAGES) { st = 0; ph ^= 1; }
             }
-            for (int k = 0; k < ksteps; ++k) {
-              umma_bf16_pair(tmem_base + h * C::BLOCK_N, umma_smem_desc(a_addr + h * A_STAGE_BYTES + k * UMMA_K * 2),
-                             umma_smem_desc(b_addr + k * UMMA_K * 2), idesc, (kb | k) != 0 ? 1u : 0u);
-            }
+            if (last) umma_commit_pair(tmem_full_bar + 8 * h);
+            if (h == 1) { stage = st; phase = ph; }
           }
-          umma_commit_pair(empty_bar + 8 * stage);
-          if (kb == num_kb - 1) umma_commit_pair(tmem_full_bar);
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          kb0 += gn;
         }
       }
     }
@@ -1122,10 +1144,10 @@ gemm_tc_wide_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       unit_to_tile(unit, tiles_m, tiles_n, pw, mg, nt);
       const int m_cta = mg * PAIR_M + (int)cta_rank * CTA_M;
       const int n0 = nt * C::BLOCK_N;
-      mbar_wait(tmem_full_bar, it & 1);
-      tc_fence_after();
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
+        mbar_wait(tmem_full_bar + 8 * h, it & 1);
+        tc_fence_after();
         const int m = m_cta + h * BLOCK_M + quarter * 32 + lane;
         float rs = 1.f;
         if (m < M) {
@@ -1403,6 +1425,19 @@ static int launch_tc_quad(const tcavp_gemm_args& a, const EpilogueParams& ep, cu
   return check_launch("gemm_tc_quad_kernel");
 }
 
+// TCAVP_GEMM_WIDE_SPLIT: k-blocks at the head and tail of a tile that the wide kernel issues half-major (1 = plain k-major order).
+// Measured on B200 (profiles/wide_split_ab_r02v.txt, same box, A-B-A-B): K = 3072 down_proj 775 -> 766 us, 7B o_proj 1263 -> 1258 us with 4;
+// on K = 768 the wide tile gains 13 % from it (gate/up 844 -> 954 TF/s) but the double-buffered pair kernel stays ahead (1041 TF/s).
+static int wide_split() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TCAVP_GEMM_WIDE_SPLIT");
+    v = e ? atoi(e) : 4;
+    if (v < 1) v = 1;
+  }
+  return v;
+}
+
 static int launch_tc_wide(const tcavp_gemm_args& a, const EpilogueParams& ep, cudaStream_t stream) {
   using C = WideCfg;
   CUtensorMap ma, mb;
@@ -1429,7 +1464,7 @@ static int launch_tc_wide(const tcavp_gemm_args& a, const EpilogueParams& ep, cu
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   flags |= panel_flags(a.M, a.N, a.K, 4 * BLOCK_M, C::BLOCK_N, max_pairs, true);
-  TCAVP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_wide_kernel, ma, mb, ep, a.M, a.N, a.K, flags));
+  TCAVP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_wide_kernel, ma, mb, ep, a.M, a.N, a.K, flags, wide_split()));
   return check_launch("gemm_tc_wide_kernel");
 }
 

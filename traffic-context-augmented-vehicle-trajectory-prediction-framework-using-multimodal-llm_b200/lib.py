@@ -12,12 +12,12 @@ _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libtcavp.so")
 INCLUDE = os.path.join(_ROOT, "include")
-SOURCES = ["api.cu", "gemm.cu", "attention.cu", "attention_tc.cu", "attention_tm.cu", "attention_x.cu", "norm.cu", "elementwise.cu", "ltsf.cu", "backward.cu", "attention_bwd_tc.cu", "dw_tc.cu"]
+SOURCES = ["api.cu", "gemm.cu", "attention.cu", "attention_tc.cu", "attention_tm.cu", "attention_x.cu", "attention_xt.cu", "norm.cu", "elementwise.cu", "ltsf.cu", "backward.cu", "attention_bwd_tc.cu", "dw_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I", INCLUDE]
 
 EXPORTS = [
-    "tcavp_last_error", "tcavp_version", "tcavp_device_info", "tcavp_launch_count", "tcavp_clock_probe", "tcavp_gemm_tile_order", "tcavp_gemm", "tcavp_attention",
+    "tcavp_last_error", "tcavp_version", "tcavp_device_info", "tcavp_launch_count", "tcavp_last_kernel", "tcavp_clock_probe", "tcavp_gemm_tile_order", "tcavp_gemm", "tcavp_attention",
     "tcavp_layernorm", "tcavp_rmsnorm", "tcavp_row_rstd", "tcavp_rope", "tcavp_rope_table", "tcavp_embed_text", "tcavp_add_rowvec",
     "tcavp_cast", "tcavp_split_bf16x3", "tcavp_poly_embed", "tcavp_masked_mean", "tcavp_ltsf_encode", "tcavp_nlinear_decode",
     "tcavp_fusion_head", "tcavp_traj_metrics", "tcavp_best_of_k", "tcavp_dropout",
@@ -103,6 +103,7 @@ def load():
             lib = ctypes.CDLL(LIB_PATH)
             lib.tcavp_last_error.restype = ctypes.c_char_p
             lib.tcavp_launch_count.restype = ctypes.c_longlong
+            lib.tcavp_last_kernel.restype = ctypes.c_char_p
             for name in EXPORTS:
                 getattr(lib, name)   # AttributeError if a declared symbol is not exported
             _lib = lib

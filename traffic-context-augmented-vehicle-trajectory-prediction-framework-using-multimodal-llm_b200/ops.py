@@ -402,6 +402,11 @@ def launch_count():
     return int(_lib.load().tcavp_launch_count())
 
 
+def last_kernel():
+    """Name of the kernel the most recent op on this thread launched last (which variant a shape was routed to)."""
+    return _lib.load().tcavp_last_kernel().decode()
+
+
 def device_info():
     sm, maj, mnr = c_int(), c_int(), c_int()
     _lib.check(_lib.load().tcavp_device_info(byref(sm), byref(maj), byref(mnr)), "tcavp_device_info")
