@@ -226,6 +226,13 @@ int tcavp_fusion_head(const void* fused, int in_dtype, const float* ln_w, const 
                       const float* b1, const float* w2, const float* b2, const float* wo, const float* bo,
                       const float* x, float* decoded, const float* y, const float* norm_stat, float* metrics,
                       float* per_scene, int B, int C, int T_in, int T_out, tcavp_stream_t stream);
+/* Same contract for d_model = 64 on the tensor cores (mma.sync tiles over (scene, step) rows, weights resident in shared memory,
+ * split-bf16 operands: three products per linear, fp32 accumulation, relative error ~2^-16) — what the bf16 compute mode calls;
+ * tcavp_fusion_head stays the exact-fp32 FFMA path of the rtol 1e-4 parity mode. */
+int tcavp_fusion_head_tc(const void* fused, int in_dtype, const float* ln_w, const float* ln_b, const float* w1,
+                      const float* b1, const float* w2, const float* b2, const float* wo, const float* bo,
+                      const float* x, float* decoded, const float* y, const float* norm_stat, float* metrics,
+                      float* per_scene, int B, int C, int T_in, int T_out, tcavp_stream_t stream);
 /* Same metrics for an existing prediction (train.py:1302-1322; RMSE: ablation_study_without_lora.py:1237). */
 int tcavp_traj_metrics(const float* decoded, const float* y, const float* norm_stat, float* metrics, float* per_scene,
                        int B, int T_out, tcavp_stream_t stream);
@@ -282,6 +289,19 @@ int tcavp_traj_loss_bwd(const float* decoded, const float* y, const float* norm_
  * (row_scale optional: the RMSNorm rstd of the folded-norm form). */
 int tcavp_skinny_dw(const void* Y, int ldy, int y_dtype, const void* Z, int ldz, int z_dtype, const float* row_scale, float* out, int ldo,
                     long long M, int N, int J, tcavp_stream_t stream);
+/* peft lora.Linear in train() mode (train.py:432-440, lora_dropout): every target module t (q_proj, k_proj, v_proj) applies lora_A to
+ * dropout(x) with its OWN mask keep_t(m H + h) = tcavp_dropout's mask function at site sites[t] / threshold thresh[t].  These three
+ * entry points regenerate the masks on the operand fragments, so the masked copies of the [M, H] input never exist in memory.
+ * sites / thresh are HOST arrays of n_targets entries; r (LoRA rank) is 8 or 16, n_targets <= 4; all tensors bf16 except out of da.
+ *   lora_a_drop : T[m, j]   = sum_h keep_{j / r}(m H + h) x[m, h] A[j, h]           A: [n_targets r, H] (caller folds 1 / (1 - p) in); T = out[:, 0 : n_targets r)
+ *   lora_dx_drop: dx[m, h] += sum_t keep_t(m H + h) sum_{j in target t} dT[m, j] A[j, h]
+ *   lora_da_drop: out[h, j] += sum_m row_scale[m] keep_{j / r}(m H + h) x[m, h] dT[m, j]   (fp32 [H, ldo], zero-initialised by the caller) */
+int tcavp_lora_a_drop(const void* x, int ldx, const void* A, int lda, void* out, int ldo, long long M, int H, int r, int n_targets,
+                      const uint32_t* seed, const uint32_t* sites, const uint32_t* thresh, tcavp_stream_t stream);
+int tcavp_lora_dx_drop(const void* dT, int lddt, const void* A, int lda, void* dx, int lddx, long long M, int H, int r, int n_targets,
+                       const uint32_t* seed, const uint32_t* sites, const uint32_t* thresh, tcavp_stream_t stream);
+int tcavp_lora_da_drop(const void* x, int ldx, const void* dT, int lddt, const float* row_scale, float* out, int ldo, long long M, int H, int r,
+                       int n_targets, const uint32_t* seed, const uint32_t* sites, const uint32_t* thresh, tcavp_stream_t stream);
 /* Best-of-K candidate reduction (reference scripts/test.py:1336-1368): candidates (B, K, 2, T_out) fp32, y (B, 2, T_out), norm_stat (B, 4).
  * per_scene[b] = (min_k ADE, min_k FDE, min_k RMSE) after de-normalisation; totals[0..2] += their sums over the batch (caller zeroes). */
 int tcavp_best_of_k(const float* candidates, const float* y, const float* norm_stat, float* per_scene, float* totals, int B, int K, int T_out,

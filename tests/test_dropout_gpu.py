@@ -52,6 +52,49 @@ def test_dropout_kernel_mask_is_the_oracle_mask(lib_built, dtype, rows, cols, ld
         assert not torch.equal(out != 0, keep)
 
 
+@pytest.mark.parametrize("M,H,r,probs,ld_extra", [
+    (300, 768, 8, (0.1, 0.1), 16),            # 768-class: q_proj + v_proj (peft default targets), K-extended rows [H + 16]
+    (77, 128, 16, (0.1, 0.0, 0.3), 48),       # rank 16, three targets, one of them without dropout, ragged row tile
+    (1000, 4096, 16, (0.1, 0.1), 32),         # 7B geometry
+    (130, 64, 8, (0.5, 0.1, 0.1, 0.2), 32),   # four targets, a single 64-column stage
+])
+def test_fused_lora_dropout_kernels(lib_built, M, H, r, probs, ld_extra):
+    """peft lora.Linear in train mode (train.py:432-440): lora_A(dropout(x)) with one mask per target.  The fused kernels (csrc/lora_drop.cu,
+    masked fragments in dw_tc.cu) against the literal form built from the oracle's masks — forward product, input gradient, lora_A gradient."""
+    from tcavp_b200 import ops
+    n = len(probs)
+    NL, Kx = n * r, H + ld_extra
+    g = torch.Generator().manual_seed(M + H)
+    xs = torch.randn(M, Kx, generator=g).bfloat16().to(DEV)                 # K-extended residual rows [x | side columns]
+    A = (torch.randn(NL, H, generator=g) * 0.05).bfloat16().to(DEV)
+    dT = torch.randn(M, Kx, generator=g).bfloat16().to(DEV)                 # [dn1 | dT] as the QKV^T GEMM leaves it
+    rstd = (torch.rand(M, generator=g) + 0.5).to(DEV)
+    seed = _seed(4242, 3)
+    sites = [OD.site_id("llm", 5 + t // 3, "lora_" + "qkv"[t % 3]) for t in range(n)]
+    drops = [ops.Drop(seed, s_, p) for s_, p in zip(sites, probs)]
+    keep = [torch.from_numpy(OD.keep_mask(4242, 3, s_, p, M * H)).view(M, H).to(DEV).float() if p > 0 else torch.ones(M, H, device=DEV)
+            for s_, p in zip(sites, probs)]
+    x = xs[:, :H].float()
+    # forward: T[:, t r : (t + 1) r] = (mask_t o x) A_t^T; the columns behind NL keep their contents
+    out = xs.clone()
+    ops.lora_a_drop(out, A, out[:, H:], drops, M=M, H=H, r=r, ldx=Kx, ldo=Kx)
+    want = torch.cat([(keep[t] * x) @ A[t * r:(t + 1) * r].float().t() for t in range(n)], 1)
+    torch.testing.assert_close(out[:, H:H + NL].float(), want, rtol=2e-2, atol=2e-2 * float(want.abs().max()))
+    assert torch.equal(out[:, :H], xs[:, :H]) and torch.equal(out[:, H + NL:], xs[:, H + NL:])
+    # input gradient: dx += sum_t mask_t o (dT_t A_t), in place on the first H columns
+    dx = dT.clone()
+    ops.lora_dx_drop(dx[:, H:], A, dx, drops, M=M, H=H, r=r, lddt=Kx, lddx=Kx)
+    want = dT[:, :H].float() + sum(keep[t] * (dT[:, H + t * r:H + (t + 1) * r].float() @ A[t * r:(t + 1) * r].float()) for t in range(n))
+    torch.testing.assert_close(dx[:, :H].float(), want, rtol=2e-2, atol=2e-2 * float(want.abs().max()))
+    assert torch.equal(dx[:, H:], dT[:, H:])
+    # lora_A gradient: dA[h, j] = sum_m rstd[m] mask_t(m, h) x[m, h] dT[m, j]
+    dA = torch.zeros(H, NL, dtype=torch.float32, device=DEV)
+    ops.lora_da_drop(xs, dT[:, H:], dA, drops, M=M, H=H, r=r, ldx=Kx, lddt=Kx, row_scale=rstd)
+    dTs = (dT[:, H:H + NL].float() * rstd[:, None]).bfloat16().float()      # the kernel applies the row factor to the narrow operand in bf16
+    want = torch.cat([(keep[t] * x).t() @ dTs[:, t * r:(t + 1) * r] for t in range(n)], 1)
+    torch.testing.assert_close(dA, want, rtol=2e-2, atol=1e-2 * float(want.abs().max()))
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("B,H,Tq,Tk,dh,masked", [(3, 4, 33, 33, 16, True), (2, 2, 15, 15, 32, False), (2, 8, 16, 15, 96, False), (2, 2, 12, 40, 64, False),
                                                  (2, 2, 25, 144, 384, False)])

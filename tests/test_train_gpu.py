@@ -231,7 +231,10 @@ def test_finetuner_matches_the_reference_loop(lib_built, graph):
         l2.backward()
         if step == 0:      # same weights on both sides: the flat-bucket gradients are the autograd gradients
             torch.cuda.synchronize()
-            for (n, p), v in zip(m.trainable_named_parameters(), ft.bucket.views):
+            assert sorted(ft.names) == sorted(n for n, _ in m.trainable_named_parameters())
+            n_late = sum(v.numel() for n, v in zip(ft.names, ft.bucket.views) if n.startswith("mllm."))
+            assert n_late == ft.n_late and all(n.startswith("mllm.") == (k < sum(x.startswith("mllm.") for x in ft.names)) for k, n in enumerate(ft.names))
+            for n, v in zip(ft.names, ft.bucket.views):      # flat layout: mllm.* first (final late), the early-final slice behind it
                 g = dict(m_ref.named_parameters())[n].grad
                 if not n.startswith(ILL):
                     torch.testing.assert_close(v, g, rtol=2e-3, atol=1e-6 + 1e-4 * float(g.abs().max()), msg=lambda s, n=n: f"{n}: {s}")

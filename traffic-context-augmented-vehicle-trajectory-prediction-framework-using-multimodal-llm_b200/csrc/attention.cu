@@ -215,13 +215,8 @@ extern "C" int tcavp_attention(const tcavp_attn_args* a, tcavp_stream_t stream_)
   TCAVP_REQUIRE(a->dtype == TCAVP_F32 || a->dtype == TCAVP_BF16, "tcavp_attention: bad dtype");
   TCAVP_REQUIRE(a->drop_thresh == 0 || (a->drop_seed != nullptr && a->drop_scale > 0.f), "tcavp_attention: dropout needs a device seed and a scale");
   if (a->dtype == TCAVP_BF16) {
-    int rc = 1;
-    if (a->dh > 128) {
-      rc = attention_xt_launch(*a, stream);
-      if (rc > 0) rc = attention_x_launch(*a, stream);
-    } else {
-      rc = attention_tm_launch(*a, stream);
-    }
+    int rc = attention_xt_launch(*a, stream);       // two heads on one shared K = V head (checks its own shape conditions first)
+    if (rc > 0) rc = a->dh > 128 ? attention_x_launch(*a, stream) : attention_tm_launch(*a, stream);
     if (rc > 0 && a->dh <= 128) rc = attention_tc_launch(*a, stream);
     if (rc <= 0) return rc;
     return launch_warp<__nv_bfloat16>(*a, stream);

@@ -31,10 +31,19 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool v
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
 
-template <int BK>
+// DROP: the rows of Y carry a per-target dropout mask (peft lora_dropout: target t = output column block [t r, (t + 1) r) sees
+// keep_t(m N + n) ? Y[m][n] : 0 — include/tcavp.h: tcavp_lora_da_drop).  The masks are regenerated on the A fragments in registers, one
+// masked copy of the fragment per target, so the masked activations never exist in memory.
+struct DropSpec {
+  const uint32_t* seed;
+  uint32_t site[4], thresh[4];
+  int r, n;
+};
+
+template <int BK, bool DROP>
 __global__ void __launch_bounds__(THREADS) dw_tc_kernel(const __nv_bfloat16* __restrict__ Y, int ldy, const __nv_bfloat16* __restrict__ X, int ldx,
                                                         const float* __restrict__ scale, float* __restrict__ out, int ldo, long long M, int N, int K,
-                                                        int m_per_block) {
+                                                        int m_per_block, DropSpec ds) {
   constexpr int LDY = BN + PAD, LDX = BK + PAD;
   constexpr int YV = MS * BN / 8 / THREADS;                 // 16-byte vectors of the Y slab per thread (2)
   constexpr int XV = (MS * BK / 8 + THREADS - 1) / THREADS;   // ... of the X slab (1 for BK <= 64, 2 for BK = 128)
@@ -122,12 +131,41 @@ __global__ void __launch_bounds__(THREADS) dw_tc_kernel(const __nv_bfloat16* __r
     for (int ms = 0; ms < MS / 16; ++ms) {
       uint32_t af[4];
       ldsm_x4_t(sY_u + (uint32_t)((buf * MS * LDY + (ms * 16 + a_m) * LDY + warp * 16 + a_n) * 2), af[0], af[1], af[2], af[3]);
+      if (DROP) {
+        uint32_t bq[BK / 16][4];
 #pragma unroll
-      for (int kp = 0; kp < BK / 16; ++kp) {
-        uint32_t b0, b1, b2, b3;
-        ldsm_x4_t(sX_u + (uint32_t)((buf * MS * LDX + (ms * 16 + b_m) * LDX + kp * 16 + b_k) * 2), b0, b1, b2, b3);
-        mma16816(acc[2 * kp], af, b0, b1);
-        mma16816(acc[2 * kp + 1], af, b2, b3);
+        for (int kp = 0; kp < BK / 16; ++kp)
+          ldsm_x4_t(sX_u + (uint32_t)((buf * MS * LDX + (ms * 16 + b_m) * LDX + kp * 16 + b_k) * 2), bq[kp][0], bq[kp][1], bq[kp][2], bq[kp][3]);
+        // fragment element (register i, half e): n = n0 + 16 warp + g + 8 (i & 1),  m = slab row 16 ms + 2 t4 + e + 8 (i >> 1)
+        const unsigned long long mrow = (unsigned long long)(m0 + (long long)s * MS + ms * 16 + (lane & 3) * 2);
+        const unsigned int ncol = (unsigned int)(n0 + warp * 16 + (lane >> 2));
+        int cur = -1;
+        uint32_t mf[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int i = 0; i < BK / 8; ++i) {
+          if (k0 + i * 8 < K) {
+            const int t = (k0 + i * 8) / ds.r;
+            if (t != cur) {
+              cur = t;
+              const uint32_t key = drop_key(ds.seed, ds.site[t]), th = ds.thresh[t];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const unsigned long long idx = (mrow + (unsigned)((q >> 1) * 8)) * (unsigned long long)N + ncol + (unsigned)((q & 1) * 8);
+                const uint32_t keep = (drop_keep(key, idx, th) ? 0x0000FFFFu : 0u) | (drop_keep(key, idx + (unsigned long long)N, th) ? 0xFFFF0000u : 0u);
+                mf[q] = af[q] & keep;
+              }
+            }
+            mma16816(acc[i], mf, bq[i >> 1][(i & 1) * 2], bq[i >> 1][(i & 1) * 2 + 1]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int kp = 0; kp < BK / 16; ++kp) {
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4_t(sX_u + (uint32_t)((buf * MS * LDX + (ms * 16 + b_m) * LDX + kp * 16 + b_k) * 2), b0, b1, b2, b3);
+          mma16816(acc[2 * kp], af, b0, b1);
+          mma16816(acc[2 * kp + 1], af, b2, b3);
+        }
       }
     }
     __syncthreads();                 // everyone is done with `buf`; the scaled X slab of s+1 can be published into buf^1
@@ -153,9 +191,8 @@ __global__ void __launch_bounds__(THREADS) dw_tc_kernel(const __nv_bfloat16* __r
 
 }  // namespace dwtc
 
-// Returns 1 when the operands are not covered (caller uses the FFMA kernel), <= 0 otherwise.
-int dw_tc_launch(const void* Y, int ldy, const void* X, int ldx, const float* scale, float* out, int ldo, long long M, int N, int K,
-                 cudaStream_t stream) {
+static int dw_tc_launch_impl(const void* Y, int ldy, const void* X, int ldx, const float* scale, float* out, int ldo, long long M, int N, int K,
+                             const dwtc::DropSpec* ds, cudaStream_t stream) {
   if (N % 8 || K % 8 || ldy % 8 || ldx % 8 || reinterpret_cast<uintptr_t>(Y) % 16 || reinterpret_cast<uintptr_t>(X) % 16) return 1;
   const int bk = K <= 32 ? 32 : (K <= 64 || K % 128 ? 64 : 128);
   const int tn = (N + dwtc::BN - 1) / dwtc::BN, tk = (K + bk - 1) / bk;
@@ -169,10 +206,39 @@ int dw_tc_launch(const void* Y, int ldy, const void* X, int ldx, const float* sc
   const dim3 grid(tk, tn, (unsigned)nz);
   const __nv_bfloat16* y = reinterpret_cast<const __nv_bfloat16*>(Y);
   const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(X);
-  if (bk == 32) dwtc::dw_tc_kernel<32><<<grid, dwtc::THREADS, 0, stream>>>(y, ldy, x, ldx, scale, out, ldo, M, N, K, (int)mper);
-  else if (bk == 64) dwtc::dw_tc_kernel<64><<<grid, dwtc::THREADS, 0, stream>>>(y, ldy, x, ldx, scale, out, ldo, M, N, K, (int)mper);
-  else dwtc::dw_tc_kernel<128><<<grid, dwtc::THREADS, 0, stream>>>(y, ldy, x, ldx, scale, out, ldo, M, N, K, (int)mper);
+  if (ds) {
+    if (bk == 128) return 1;
+    if (bk == 32) dwtc::dw_tc_kernel<32, true><<<grid, dwtc::THREADS, 0, stream>>>(y, ldy, x, ldx, scale, out, ldo, M, N, K, (int)mper, *ds);
+    else dwtc::dw_tc_kernel<64, true><<<grid, dwtc::THREADS, 0, stream>>>(y, ldy, x, ldx, scale, out, ldo, M, N, K, (int)mper, *ds);
+    return check_launch("dw_tc_drop_kernel");
+  }
+  dwtc::DropSpec none = {};
+  if (bk == 32) dwtc::dw_tc_kernel<32, false><<<grid, dwtc::THREADS, 0, stream>>>(y, ldy, x, ldx, scale, out, ldo, M, N, K, (int)mper, none);
+  else if (bk == 64) dwtc::dw_tc_kernel<64, false><<<grid, dwtc::THREADS, 0, stream>>>(y, ldy, x, ldx, scale, out, ldo, M, N, K, (int)mper, none);
+  else dwtc::dw_tc_kernel<128, false><<<grid, dwtc::THREADS, 0, stream>>>(y, ldy, x, ldx, scale, out, ldo, M, N, K, (int)mper, none);
   return check_launch("dw_tc_kernel");
 }
 
+// Returns 1 when the operands are not covered (caller uses the FFMA kernel), <= 0 otherwise.
+int dw_tc_launch(const void* Y, int ldy, const void* X, int ldx, const float* scale, float* out, int ldo, long long M, int N, int K,
+                 cudaStream_t stream) {
+  return dw_tc_launch_impl(Y, ldy, X, ldx, scale, out, ldo, M, N, K, nullptr, stream);
+}
+
 }  // namespace tcavp
+
+// peft lora.Linear in train mode, gradient of lora_A (include/tcavp.h).
+extern "C" int tcavp_lora_da_drop(const void* x, int ldx, const void* dT, int lddt, const float* row_scale, float* out, int ldo, long long M, int H,
+                                  int r, int n_targets, const uint32_t* seed, const uint32_t* sites, const uint32_t* thresh, tcavp_stream_t stream) {
+  using namespace tcavp;
+  TCAVP_REQUIRE(M >= 0 && H > 0 && (r == 8 || r == 16) && n_targets >= 1 && n_targets <= 4 && ldo >= r * n_targets,
+                "tcavp_lora_da_drop: bad shape (H=%d r=%d targets=%d)", H, r, n_targets);
+  if (M == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(x && dT && out && seed && sites && thresh, "tcavp_lora_da_drop: null pointer");
+  dwtc::DropSpec ds = {};
+  ds.seed = seed; ds.r = r; ds.n = n_targets;
+  for (int t = 0; t < n_targets; ++t) { ds.site[t] = sites[t]; ds.thresh[t] = thresh[t]; }
+  const int rc = dw_tc_launch_impl(x, ldx, dT, lddt, row_scale, out, ldo, M, H, r * n_targets, &ds, reinterpret_cast<cudaStream_t>(stream));
+  if (rc > 0) return fail_arg("tcavp_lora_da_drop: operands must be bf16 with 16-byte aligned rows (H %% 8, ldx %% 8, lddt %% 8)");
+  return rc;
+}

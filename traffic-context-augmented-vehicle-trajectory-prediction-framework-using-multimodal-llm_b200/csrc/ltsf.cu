@@ -111,17 +111,20 @@ __global__ void __launch_bounds__(256) ltsf_encode_tiled_kernel(const float* __r
   }
 }
 
+// (two scenes per thread and three resident CTAs per SM: with four scenes the 115 registers per thread left 16 warps per SM, and the kernel was
+// bound by the latency of its own weight / lane-adjust loads: 22 % issue utilisation, 9 % of the DRAM bandwidth)
+constexpr int NBD = 2;
 template <int T>
-__global__ void __launch_bounds__(256) nlinear_decode_tiled_kernel(const void* __restrict__ enc, int enc_dtype, const float* __restrict__ wd,
+__global__ void __launch_bounds__(256, 3) nlinear_decode_tiled_kernel(const void* __restrict__ enc, int enc_dtype, const float* __restrict__ wd,
                                                                    const float* __restrict__ bd, const void* __restrict__ adj, int adj_dtype,
                                                                    void* __restrict__ dec, int out_dtype, int B, int C, int To) {
   const int c = threadIdx.x % C;
   const int slot = threadIdx.x / C, slots = blockDim.x / C;
-  const long long b0 = ((long long)blockIdx.x * slots + slot) * NB;
+  const long long b0 = ((long long)blockIdx.x * slots + slot) * NBD;
   if (b0 >= B) return;
-  float e[NB][T], last[NB];
+  float e[NBD][T], last[NBD];
 #pragma unroll
-  for (int j = 0; j < NB; ++j) {
+  for (int j = 0; j < NBD; ++j) {
     const long long b = b0 + j < B ? b0 + j : B - 1;
 #pragma unroll
     for (int s = 0; s < T; ++s) e[j][s] = load_as_f(enc, ((size_t)b * T + s) * C + c, enc_dtype);
@@ -135,17 +138,17 @@ __global__ void __launch_bounds__(256) nlinear_decode_tiled_kernel(const void* _
 #pragma unroll 2
   for (int t = t_lo; t < t_hi; ++t) {
     const float base = __ldg(bd + (size_t)t * C + c);
-    float acc[NB];
+    float acc[NBD];
 #pragma unroll
-    for (int j = 0; j < NB; ++j) acc[j] = base + last[j];
+    for (int j = 0; j < NBD; ++j) acc[j] = base + last[j];
 #pragma unroll
     for (int s = 0; s < T; ++s) {
       const float w = __ldg(wd + ((size_t)t * T + s) * C + c);
 #pragma unroll
-      for (int j = 0; j < NB; ++j) acc[j] = fmaf(w, e[j][s], acc[j]);
+      for (int j = 0; j < NBD; ++j) acc[j] = fmaf(w, e[j][s], acc[j]);
     }
 #pragma unroll
-    for (int j = 0; j < NB; ++j) {
+    for (int j = 0; j < NBD; ++j) {
       if (b0 + j < B) {
         const size_t o = ((size_t)(b0 + j) * To + t) * C + c;
         float v = acc[j];
@@ -324,6 +327,214 @@ __global__ void __launch_bounds__(256) fusion_head_kernel(const void* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tensor-core form of the fusion head for d_model = 64 (the bf16 compute mode; the FFMA kernel above stays the exact fp32 path).
+// The two 64 x 64 fusion_layer linears are batched as mma.sync m16n8k16 tiles over (scene, step) rows with the weights resident in
+// shared memory; fp32-class accuracy comes from the split-bf16 form (x = hi + lo, three products hi.hi + lo.hi + hi.lo, fp32
+// accumulation: relative error ~2^-16).  A warp owns a 16-row tile from the fused-feature load to the ADE / FDE contribution:
+// LayerNorm on the A-fragment layout (a row lives in one quad: two shuffles), linear 1 + ReLU, the accumulator fragments re-packed
+// in registers as the next A operand (no shared-memory round trip), linear 2, out_proj as a quad reduction, de-normalised errors
+// into per-scene shared-memory accumulators.  A CTA owns GROUP consecutive scenes, so a scene's ADE / FDE never crosses CTAs.
+// ------------------------------------------------------------------------------------------------
+namespace fh {
+constexpr int C = 64, LDW = C + 8, GROUP = 8;
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// (a, b) -> packed bf16 pair of the high parts and of the residuals
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - __low2float(h), b - __high2float(h));
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// acc[nt][.] += A . W^T for the 16 x 64 tile held as split fragments; W (hi / lo) in shared memory as [out][in] rows of LDW elements
+__device__ __forceinline__ void linear64(float (&acc)[8][4], const uint32_t (&ahi)[4][4], const uint32_t (&alo)[4][4], const __nv_bfloat16* whi,
+                                         const __nv_bfloat16* wlo, int g, int t4) {
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+      const int o = (nt * 8 + g) * LDW + kt * 16 + t4 * 2;
+      const uint32_t h0 = *reinterpret_cast<const uint32_t*>(whi + o), h1 = *reinterpret_cast<const uint32_t*>(whi + o + 8);
+      const uint32_t l0 = *reinterpret_cast<const uint32_t*>(wlo + o), l1 = *reinterpret_cast<const uint32_t*>(wlo + o + 8);
+      mma16816(acc[nt], ahi[kt], h0, h1);
+      mma16816(acc[nt], alo[kt], h0, h1);
+      mma16816(acc[nt], ahi[kt], l0, l1);
+    }
+  }
+}
+}  // namespace fh
+
+__global__ void __launch_bounds__(256) fusion_head_tc_kernel(const void* __restrict__ fused, int in_dtype, const float* __restrict__ ln_w,
+                                                             const float* __restrict__ ln_b, const float* __restrict__ w1,
+                                                             const float* __restrict__ b1, const float* __restrict__ w2,
+                                                             const float* __restrict__ b2, const float* __restrict__ wo,
+                                                             const float* __restrict__ bo, const float* __restrict__ x,
+                                                             float* __restrict__ decoded, const float* __restrict__ y,
+                                                             const float* __restrict__ norm_stat, float* __restrict__ metrics,
+                                                             float* __restrict__ per_scene, int B, int T_in, int T_out) {
+  using namespace fh;
+  __shared__ __align__(16) __nv_bfloat16 sw[4][C * LDW];      // w1 hi, w1 lo, w2 hi, w2 lo
+  __shared__ float sv[6][C];                                   // ln_w, ln_b, b1, b2, wo[0], wo[1]
+  __shared__ float sacc[GROUP][4];                             // per scene of the group: sum sq_x, sum sq_y, sum dist, fde
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x) {
+    const int o = i / C, k = i % C;
+    uint32_t hi, lo;
+    split2(__ldg(w1 + i), 0.f, hi, lo);
+    sw[0][o * LDW + k] = __ushort_as_bfloat16((unsigned short)(hi & 0xffffu));
+    sw[1][o * LDW + k] = __ushort_as_bfloat16((unsigned short)(lo & 0xffffu));
+    split2(__ldg(w2 + i), 0.f, hi, lo);
+    sw[2][o * LDW + k] = __ushort_as_bfloat16((unsigned short)(hi & 0xffffu));
+    sw[3][o * LDW + k] = __ushort_as_bfloat16((unsigned short)(lo & 0xffffu));
+  }
+  if (threadIdx.x < C) {
+    const int c = threadIdx.x;
+    sv[0][c] = __ldg(ln_w + c); sv[1][c] = __ldg(ln_b + c); sv[2][c] = __ldg(b1 + c); sv[3][c] = __ldg(b2 + c);
+    sv[4][c] = __ldg(wo + c); sv[5][c] = __ldg(wo + C + c);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t4 = lane & 3;
+  const float bo0 = __ldg(bo), bo1 = __ldg(bo + 1);
+  const int ngroups = (B + GROUP - 1) / GROUP;
+  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const int b_lo = grp * GROUP, nb = min(GROUP, B - b_lo);
+    const int rows = nb * T_out;
+    __syncthreads();                       // weights staged (first pass) / the previous group's accumulators consumed
+    if (threadIdx.x < GROUP * 4) (&sacc[0][0])[threadIdx.x] = 0.f;
+    __syncthreads();
+    for (int tile = warp; tile * 16 < rows; tile += 8) {
+      const int r0 = tile * 16 + g, r1 = r0 + 8;                   // rows of the group this thread's fragments hold
+      // ---- load + LayerNorm (train.py:759-764 norm of fusion_layer) on the A-fragment layout
+      float v[2][16];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = min(h ? r1 : r0, rows - 1);                  // tail rows recompute the last row (never stored)
+        const size_t base = ((size_t)b_lo * T_out + r) * C;
+#pragma unroll
+        for (int kt = 0; kt < 4; ++kt) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int c = kt * 16 + q * 8 + t4 * 2;
+            if (in_dtype == TCAVP_F32) {
+              const float2 f = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(fused) + base + c);
+              v[h][kt * 4 + q * 2] = f.x; v[h][kt * 4 + q * 2 + 1] = f.y;
+            } else {
+              const __nv_bfloat162 f = *reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const __nv_bfloat16*>(fused) + base + c);
+              v[h][kt * 4 + q * 2] = __low2float(f); v[h][kt * 4 + q * 2 + 1] = __high2float(f);
+            }
+          }
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) sum += v[h][e];
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        const float mean = sum * (1.f / C);
+        float qs = 0.f;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) qs += (v[h][e] - mean) * (v[h][e] - mean);
+        qs += __shfl_xor_sync(0xffffffffu, qs, 1);
+        qs += __shfl_xor_sync(0xffffffffu, qs, 2);
+        const float rstd = rsqrtf(qs * (1.f / C) + 1e-5f);
+#pragma unroll
+        for (int kt = 0; kt < 4; ++kt)
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int c = kt * 16 + q * 8 + t4 * 2 + e;
+              v[h][kt * 4 + q * 2 + e] = (v[h][kt * 4 + q * 2 + e] - mean) * rstd * sv[0][c] + sv[1][c];
+            }
+      }
+      uint32_t ahi[4][4], alo[4][4];
+#pragma unroll
+      for (int kt = 0; kt < 4; ++kt) {
+        // fragment registers: (row g, cols 2 t4 + {0, 1}), (row g + 8, same), (row g, cols + 8), (row g + 8, cols + 8)
+        split2(v[0][kt * 4], v[0][kt * 4 + 1], ahi[kt][0], alo[kt][0]);
+        split2(v[1][kt * 4], v[1][kt * 4 + 1], ahi[kt][1], alo[kt][1]);
+        split2(v[0][kt * 4 + 2], v[0][kt * 4 + 3], ahi[kt][2], alo[kt][2]);
+        split2(v[1][kt * 4 + 2], v[1][kt * 4 + 3], ahi[kt][3], alo[kt][3]);
+      }
+      // ---- linear 1 + ReLU (train.py:801 fusion_layer[0..1])
+      float acc[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        acc[nt][0] = acc[nt][2] = sv[2][nt * 8 + t4 * 2];
+        acc[nt][1] = acc[nt][3] = sv[2][nt * 8 + t4 * 2 + 1];
+      }
+      linear64(acc, ahi, alo, sw[0], sw[1], g, t4);
+      // accumulator tiles (2 kt, 2 kt + 1) are exactly the A fragment of k-step kt of the next product
+#pragma unroll
+      for (int kt = 0; kt < 4; ++kt) {
+        split2(fmaxf(acc[2 * kt][0], 0.f), fmaxf(acc[2 * kt][1], 0.f), ahi[kt][0], alo[kt][0]);
+        split2(fmaxf(acc[2 * kt][2], 0.f), fmaxf(acc[2 * kt][3], 0.f), ahi[kt][1], alo[kt][1]);
+        split2(fmaxf(acc[2 * kt + 1][0], 0.f), fmaxf(acc[2 * kt + 1][1], 0.f), ahi[kt][2], alo[kt][2]);
+        split2(fmaxf(acc[2 * kt + 1][2], 0.f), fmaxf(acc[2 * kt + 1][3], 0.f), ahi[kt][3], alo[kt][3]);
+      }
+      // ---- linear 2 (fusion_layer[2]) and out_proj (train.py:803) as a quad reduction
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        acc[nt][0] = acc[nt][2] = sv[3][nt * 8 + t4 * 2];
+        acc[nt][1] = acc[nt][3] = sv[3][nt * 8 + t4 * 2 + 1];
+      }
+      linear64(acc, ahi, alo, sw[2], sw[3], g, t4);
+      float o[2][2] = {{0.f, 0.f}, {0.f, 0.f}};       // [row half][coordinate]
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int c = nt * 8 + t4 * 2;
+        const float wx0 = sv[4][c], wx1 = sv[4][c + 1], wy0 = sv[5][c], wy1 = sv[5][c + 1];
+        o[0][0] = fmaf(wx0, acc[nt][0], fmaf(wx1, acc[nt][1], o[0][0]));
+        o[0][1] = fmaf(wy0, acc[nt][0], fmaf(wy1, acc[nt][1], o[0][1]));
+        o[1][0] = fmaf(wx0, acc[nt][2], fmaf(wx1, acc[nt][3], o[1][0]));
+        o[1][1] = fmaf(wy0, acc[nt][2], fmaf(wy1, acc[nt][3], o[1][1]));
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+          o[h][f] += __shfl_xor_sync(0xffffffffu, o[h][f], 1);
+          o[h][f] += __shfl_xor_sync(0xffffffffu, o[h][f], 2);
+        }
+      // ---- + last observed position (train.py:941-943), store, error statistics (train.py:945-962, 1302-1322): lanes t4 = 0, 1 take one row each
+      if (t4 < 2) {
+        const int r = t4 ? r1 : r0;
+        if (r < rows) {
+          const int sb = r / T_out, t = r - sb * T_out, b = b_lo + sb;
+          const float px = o[t4][0] + bo0 + __ldg(x + ((size_t)b * 2 + 0) * T_in + T_in - 1);
+          const float py = o[t4][1] + bo1 + __ldg(x + ((size_t)b * 2 + 1) * T_in + T_in - 1);
+          decoded[((size_t)b * 2 + 0) * T_out + t] = px;
+          decoded[((size_t)b * 2 + 1) * T_out + t] = py;
+          if (y) {
+            float sqx, sqy, dist;
+            scene_error(px, py, y[((size_t)b * 2 + 0) * T_out + t], y[((size_t)b * 2 + 1) * T_out + t], norm_stat + (size_t)b * 4, sqx, sqy, dist);
+            atomicAdd(&sacc[sb][0], sqx);
+            atomicAdd(&sacc[sb][1], sqy);
+            atomicAdd(&sacc[sb][2], dist);
+            if (t == T_out - 1) sacc[sb][3] = dist;
+          }
+        }
+      }
+    }
+    if (y) {   // uniform across the block
+      __syncthreads();
+      if (warp == 0) {
+        float sqx = 0.f, sqy = 0.f, ade = 0.f, fde = 0.f;
+        if (lane < nb) {
+          sqx = sacc[lane][0]; sqy = sacc[lane][1]; ade = sacc[lane][2] / (float)T_out; fde = sacc[lane][3];
+          if (per_scene) { per_scene[(size_t)(b_lo + lane) * 2] = ade; per_scene[(size_t)(b_lo + lane) * 2 + 1] = fde; }
+        }
+        sqx = warp_sum(sqx); sqy = warp_sum(sqy); ade = warp_sum(ade); fde = warp_sum(fde);
+        if (lane == 0) {
+          atomicAdd(metrics + 0, sqx); atomicAdd(metrics + 1, sqy); atomicAdd(metrics + 2, ade); atomicAdd(metrics + 3, fde);
+          atomicAdd(metrics + 4, (sqx + sqy) / ((float)B * (float)T_out));      // MSE_x + MSE_y (train.py:959-961)
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(128) traj_metrics_kernel(const float* __restrict__ decoded, const float* __restrict__ y,
                                                            const float* __restrict__ norm_stat, float* __restrict__ metrics,
                                                            float* __restrict__ per_scene, int B, int T_out) {
@@ -432,9 +643,9 @@ extern "C" int tcavp_nlinear_decode(const void* enc, int enc_dtype, const float*
   if (B == 0) return TCAVP_OK;
   TCAVP_REQUIRE(enc && wd && bd && dec && DT_OK(enc_dtype) && DT_OK(out_dtype) && (!lane_adj || DT_OK(adj_dtype)), "tcavp_nlinear_decode: bad pointer/dtype");
   if (C <= 256 && 256 % C == 0) {
-    const int per_block = (256 / C) * NB;
+    const int per_block = (256 / C) * NBD;
     const int grid = (B + per_block - 1) / per_block;
-    int ty = (sm_count() * 6 + grid - 1) / grid;          // aim at ~6 blocks per SM
+    int ty = (sm_count() * 9 + grid - 1) / grid;          // aim at ~3 waves of three resident blocks per SM
     ty = ty < 1 ? 1 : (ty > (T_out + 3) / 4 ? (T_out + 3) / 4 : ty);
 #define TCAVP_DEC(T)                                                                                                                          \
   case T:                                                                                                                                      \
@@ -477,6 +688,23 @@ extern "C" int tcavp_fusion_head(const void* fused, int in_dtype, const float* l
   else LAUNCH(4);
 #undef LAUNCH
   return check_launch("fusion_head_kernel");
+}
+
+extern "C" int tcavp_fusion_head_tc(const void* fused, int in_dtype, const float* ln_w, const float* ln_b, const float* w1,
+                                    const float* b1, const float* w2, const float* b2, const float* wo, const float* bo,
+                                    const float* x, float* decoded, const float* y, const float* norm_stat, float* metrics,
+                                    float* per_scene, int B, int C, int T_in, int T_out, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(B >= 0 && T_in > 0 && T_out > 0, "tcavp_fusion_head_tc: bad shape");
+  TCAVP_REQUIRE(C == 64, "tcavp_fusion_head_tc: d_model must be 64 (got %d); tcavp_fusion_head covers 32 / 64 / 128", C);
+  if (B == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(fused && ln_w && ln_b && w1 && b1 && w2 && b2 && wo && bo && x && decoded && DT_OK(in_dtype), "tcavp_fusion_head_tc: bad pointer/dtype");
+  TCAVP_REQUIRE(!y || (norm_stat && metrics), "tcavp_fusion_head_tc: y needs norm_stat and metrics");
+  TCAVP_REQUIRE(reinterpret_cast<uintptr_t>(fused) % 8 == 0, "tcavp_fusion_head_tc: fused must be 8-byte aligned");
+  const int groups = (B + fh::GROUP - 1) / fh::GROUP;
+  const int grid = groups < sm_count() * 4 ? groups : sm_count() * 4;
+  fusion_head_tc_kernel<<<grid, 256, 0, STREAM(stream)>>>(fused, in_dtype, ln_w, ln_b, w1, b1, w2, b2, wo, bo, x, decoded, y, norm_stat, metrics,
+                                                          per_scene, B, T_in, T_out);
+  return check_launch("fusion_head_tc_kernel");
 }
 
 extern "C" int tcavp_traj_metrics(const float* decoded, const float* y, const float* norm_stat, float* metrics, float* per_scene,

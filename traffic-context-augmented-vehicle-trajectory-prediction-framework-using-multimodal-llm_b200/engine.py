@@ -423,7 +423,8 @@ class Engine:
             metrics = torch.zeros(8, dtype=torch.float32, device=self.dev)
             per_scene = torch.empty(B, 2, dtype=torch.float32, device=self.dev)
         ops.fusion_head(fused, lt["fl_ln"][0], lt["fl_ln"][1], lt["fl_w1"], lt["fl_b1"], lt["fl_w2"], lt["fl_b2"], lt["wo"], lt["bo"], x,
-                        decoded, y=y, norm_stat=norm_stat, metrics=metrics, per_scene=per_scene, B=B, C=C, T_in=T, T_out=To)
+                        decoded, y=y, norm_stat=norm_stat, metrics=metrics, per_scene=per_scene, B=B, C=C, T_in=T, T_out=To,
+                        tensor_cores=self.act == torch.bfloat16 and self.SPLIT_SMALL and not os.environ.get("TCAVP_NO_SPLIT_SMALL"))
         if y is not None:
             out.update(metrics=metrics, per_scene=per_scene)
         return out

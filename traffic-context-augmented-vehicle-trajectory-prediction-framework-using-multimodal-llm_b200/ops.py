@@ -226,9 +226,15 @@ def attention(q, k, v, out, *, B, H, Hkv, Tq, Tk, dh, q_strides, k_strides, v_st
             raise TypeError("attention: key_mask must be int32")
         a.key_mask = key_mask.data_ptr()
     _set_drop(a, drop)
+    shared_kv = False
     if (a.dtype == BF16 and causal and dh in (64, 128) and Tq == Tk and 128 <= Tq <= 256 and not a.drop_thresh and q_strides[0] == Tq * q_strides[1]
             and k_strides[0] == Tk * k_strides[1] and v_strides[0] == Tk * v_strides[1] and _os.environ.get("TCAVP_ATTN_TCGEN05", "1") != "0"):
         kern = f"attn_tm_kernel[dh{dh},L{Tq}]"          # tcgen05 / TMEM / TMA (attention_tm.cu)
+    elif (a.dtype == BF16 and H == 2 and Hkv == 1 and k.data_ptr() == v.data_ptr() and tuple(k_strides) == tuple(v_strides) and not causal
+          and key_mask is None and not a.drop_thresh and Tq <= 64 and Tk <= 256 and dh % 128 == 0 and q_strides[0] == Tq * q_strides[1]
+          and k_strides[0] == Tk * k_strides[1] and _os.environ.get("TCAVP_ATTNX_TCGEN05", "1") != "0"):
+        kern = f"attn_xt_kernel[dh{dh},q{Tq},k{Tk}]"      # tcgen05: two heads on one shared K = V head (attention_xt.cu)
+        shared_kv = True
     elif a.dtype == BF16 and dh in (16, 32, 64, 96, 128) and max(Tq, Tk) <= 256:
         kern = f"attn_flash_kernel[dh{dh},q{Tq},k{Tk}]"
     elif a.dtype == BF16 and dh > 128 and dh % 64 == 0 and Tq <= 64 and Tk <= 256 and not causal:
@@ -238,7 +244,9 @@ def attention(q, k, v, out, *, B, H, Hkv, Tq, Tk, dh, q_strides, k_strides, v_st
     else:
         kern = f"attn_warp_kernel[dh{dh},q{Tq},k{Tk}]"
     fl = 4.0 * B * H * Tq * Tk * dh * (0.5 if causal else 1.0)
-    with _Timed(kern, fl, 2.0 * q.element_size() * B * dh * (H * Tq + Hkv * Tk)):
+    # algorithmic bytes: q read + out written + k and v read once (ONE pass when the keys are the values)
+    nbytes = q.element_size() * B * dh * (2.0 * H * Tq + (1.0 if shared_kv else 2.0) * Hkv * Tk)
+    with _Timed(kern, fl, nbytes):
         _lib.check(_lib.load().tcavp_attention(byref(a), _stream()), "tcavp_attention")
     return out
 
@@ -360,12 +368,16 @@ def nlinear_decode(enc, wd, bd, lane_adj, dec, *, B, C, T_in, T_out):
 
 
 def fusion_head(fused, ln_w, ln_b, w1, b1, w2, b2, wo, bo, x, decoded, *, y=None, norm_stat=None, metrics=None, per_scene=None,
-                B, C, T_in, T_out):
+                B, C, T_in, T_out, tensor_cores=False):
+    """`tensor_cores`: the split-bf16 mma.sync form (d_model 64; the bf16 compute mode) instead of the exact-fp32 FFMA kernel."""
     _need_cuda(fused, x, decoded, y, norm_stat, metrics, per_scene)
-    with _Timed("fusion_head_kernel", 0.0, float(B * T_out * C * fused.element_size() + B * 2 * T_out * 4 * (2 if y is not None else 1) + B * (2 * T_in * 4 + 16))):
-        _lib.check(_lib.load().tcavp_fusion_head(_p(fused), dt(fused), _p(ln_w), _p(ln_b), _p(w1), _p(b1), _p(w2), _p(b2), _p(wo), _p(bo),
-                                             _p(x), _p(decoded), _p(y), _p(norm_stat), _p(metrics), _p(per_scene), B, C, T_in, T_out,
-                                             _stream()), "tcavp_fusion_head")
+    tc = tensor_cores and C == 64
+    fn = _lib.load().tcavp_fusion_head_tc if tc else _lib.load().tcavp_fusion_head
+    with _Timed("fusion_head_tc_kernel" if tc else "fusion_head_kernel", 0.0,      # bandwidth-bound by design: reported against the HBM peak
+                float(B * T_out * C * fused.element_size() + B * 2 * T_out * 4 * (2 if y is not None else 1) + B * (2 * T_in * 4 + 16))):
+        _lib.check(fn(_p(fused), dt(fused), _p(ln_w), _p(ln_b), _p(w1), _p(b1), _p(w2), _p(b2), _p(wo), _p(bo),
+                      _p(x), _p(decoded), _p(y), _p(norm_stat), _p(metrics), _p(per_scene), B, C, T_in, T_out,
+                      _stream()), "tcavp_fusion_head")
     return decoded
 
 
@@ -395,6 +407,44 @@ def dropout(x, out, drop, *, rows, cols, ldi=None, ldo=None, residual=None, ldr=
                                              0 if residual is None else dt(residual), _p(out), cols if ldo is None else ldo, dt(out),
                                              c_longlong(rows), cols, _p(drop.seed), c_uint32(drop.site), c_uint32(drop.thresh),
                                              c_float(drop.scale if scale is None else scale), int(accumulate), _stream()), "tcavp_dropout")
+    return out
+
+
+def _drop_arrays(drops):
+    n = len(drops)
+    if not 1 <= n <= 4 or any(d.seed.data_ptr() != drops[0].seed.data_ptr() for d in drops):
+        raise ValueError("LoRA dropout: 1..4 targets sharing one device seed")
+    return n, (c_uint32 * n)(*[d.site for d in drops]), (c_uint32 * n)(*[d.thresh for d in drops])
+
+
+def lora_a_drop(x, a, out, drops, *, M, H, r, ldx=None, ldo=None):
+    """out[:, :len(drops) * r] = sum_h keep_t(m H + h) x[m, h] a[j, h] (target t = j // r): peft's lora_A(dropout(x)) for every target in
+    one pass over x (tcavp_lora_a_drop); `a` carries 1 / (1 - p)."""
+    _need_cuda(x, a, out)
+    n, sites, th = _drop_arrays(drops)
+    with _Timed("lora_a_drop_kernel", 0.0, float(M * H * x.element_size())):
+        _lib.check(_lib.load().tcavp_lora_a_drop(_p(x), x.stride(0) if ldx is None else ldx, _p(a), a.stride(0), _p(out), out.stride(0) if ldo is None else ldo,
+                                                 c_longlong(M), H, r, n, _p(drops[0].seed), sites, th, _stream()), "tcavp_lora_a_drop")
+    return out
+
+
+def lora_dx_drop(dT, a, dx, drops, *, M, H, r, lddt=None, lddx=None):
+    """dx[m, h] += sum_t keep_t(m H + h) (dT_t . a_t)[m, h] in place (tcavp_lora_dx_drop)."""
+    _need_cuda(dT, a, dx)
+    n, sites, th = _drop_arrays(drops)
+    with _Timed("lora_dx_drop_kernel", 0.0, float(2 * M * H * dx.element_size())):
+        _lib.check(_lib.load().tcavp_lora_dx_drop(_p(dT), dT.stride(0) if lddt is None else lddt, _p(a), a.stride(0), _p(dx), dx.stride(0) if lddx is None else lddx,
+                                                  c_longlong(M), H, r, n, _p(drops[0].seed), sites, th, _stream()), "tcavp_lora_dx_drop")
+    return dx
+
+
+def lora_da_drop(x, dT, out, drops, *, M, H, r, ldx=None, lddt=None, row_scale=None):
+    """out[h, j] += sum_m row_scale[m] keep_t(m H + h) x[m, h] dT[m, j] (fp32, zeroed by the caller; tcavp_lora_da_drop)."""
+    _need_cuda(x, dT, out, row_scale)
+    n, sites, th = _drop_arrays(drops)
+    with _Timed("dw_tc_drop_kernel", 0.0, float(M * H * x.element_size())):
+        _lib.check(_lib.load().tcavp_lora_da_drop(_p(x), x.stride(0) if ldx is None else ldx, _p(dT), dT.stride(0) if lddt is None else lddt, _p(row_scale),
+                                                  _p(out), out.stride(0), c_longlong(M), H, r, n, _p(drops[0].seed), sites, th, _stream()), "tcavp_lora_da_drop")
     return out
 
 

@@ -14,6 +14,7 @@ Dropout (train mode, every site of the reference: lora_dropout, ltsf_dropout, th
 mask of tcavp_dropout — a pure function of (seed, site, element) that the backward pass re-creates, nothing is stored — see
 `DropPlan`.  With `model.eval()` or every p = 0 the step is the deterministic one the p = 0 goldens pin."""
 import math
+import os
 
 import torch
 
@@ -201,14 +202,28 @@ class TrainEngine(Engine):
             # so the side product is one masked copy + one skinny GEMM per target.  The masked copy is exact (x or 0); the 1 / (1 - p)
             # factor rides on the per-target weight ([A'_t ; 0] rows of the other targets zeroed, so the GEMMs accumulate).
             ly.pop("a_cat_t", None)
+            ly.pop("a_cat_s", None)
             drops = self._lora_drops(0)
-            if drops:
+            if drops and self._lora_fused():
+                # fused form (csrc/lora_drop.cu): the masks are regenerated on the operand fragments; one matrix with every target's
+                # 1 / (1 - p) folded into its rows serves the forward product and the input gradient
+                sc = torch.cat([torch.full((r,), d.scale, dtype=torch.float32, device=self.dev) for d in drops])
+                ly["a_cat_s"] = (ly["a_cat"][:len(drops) * r].float() * sc[:, None]).to(self.act).contiguous()
+                ly["lora_scales"] = sc
+            elif drops:
                 ly["a_cat_t"], ly["a_catT_t"] = [], []
                 for ti, d in enumerate(drops):
                     w = torch.zeros_like(ly["a_cat"])
                     w[ti * r:(ti + 1) * r] = (ly["a_cat"][ti * r:(ti + 1) * r].float() * d.scale).to(self.act)
                     ly["a_cat_t"].append(w)
                     ly["a_catT_t"].append(w.t().contiguous())
+
+    def _lora_fused(self):
+        """lora_dropout through the fused kernels (bf16 compute, rank 8 / 16, hidden size a multiple of 64); TCAVP_LORA_DROP_FUSED=0
+        keeps the literal masked copy + skinny GEMM per target (A/B runs, and the fp32 parity mode)."""
+        L = self.llm
+        return (self.act == torch.bfloat16 and L["r"] in (8, 16) and L["H"] % 64 == 0 and 1 <= len(L["targets"]) <= 4
+                and os.environ.get("TCAVP_LORA_DROP_FUSED", "1") != "0")
 
     def _lora_drops(self, li):
         """[ops.Drop per LoRA target] of decoder layer `li`, or None when lora_dropout is inactive."""
@@ -528,7 +543,9 @@ class TrainEngine(Engine):
         for li, ly in enumerate(m["layers"]):
             rstd1 = ops.row_rstd(xs, torch.empty(M, dtype=torch.float32, device=self.dev), rows=M, cols=H, ldx=Kx, eps=m["eps"])
             drops = self._lora_drops(li)
-            if kx and drops:
+            if kx and drops and "a_cat_s" in ly:
+                ops.lora_a_drop(xs, ly["a_cat_s"], xs[:, H:], drops, M=M, H=H, r=m["r"], ldx=Kx, ldo=Kx)
+            elif kx and drops:
                 if xm is None:
                     xm = self._new(M, H)
                 for ti, d in enumerate(drops):
@@ -591,13 +608,17 @@ class TrainEngine(Engine):
             ops.rope_adjacent_(dqkv, rows=M, L=L, ld=nqkv, cols=nq + nk, dh=dh, table=table, inverse=True)
             dxs = ops.gemm(dqkv, ly["wqkvT"], self._new(M, Kx))            # [dn1 | dTn]
             drops = self._lora_drops(i)
-            if drops and xm is None:
+            fused = bool(drops) and "a_cat_s" in ly
+            if drops and not fused and xm is None:
                 xm = self._new(M, H)
             if kx and self.tr_lora:
                 dext = torch.zeros(nqkv, kx, dtype=torch.float32, device=self.dev)
                 ops.skinny_dw(dqkv, xs[:, H:], dext, M=M, N=nqkv, J=kx, ldy=nqkv, ldz=Kx, row_scale=rstd1)
                 dAp = torch.zeros(H, kx, dtype=torch.float32, device=self.dev)
-                if drops:      # dA'_t = s_t * sum_m rstd[m] (mask_t o x)[m, :]^T dTn_t[m, :]: one masked copy + one reduction per target
+                if fused:      # dA'_t = s_t * sum_m rstd[m] (mask_t o x)[m, :]^T dTn_t[m, :], masks regenerated on the fragments
+                    ops.lora_da_drop(xs, dxs[:, H:], dAp, drops, M=M, H=H, r=r, ldx=Kx, lddt=Kx, row_scale=rstd1)
+                    dAp[:, :len(drops) * r] *= ly["lora_scales"][None, :]
+                elif drops:    # ... or literally: one masked copy + one reduction per target
                     for ti, d in enumerate(drops):
                         ops.dropout(xs, xm, d, rows=M, cols=H, ldi=Kx, ldo=H, scale=1.0)
                         dAt = torch.zeros(H, kx, dtype=torch.float32, device=self.dev)
@@ -614,7 +635,9 @@ class TrainEngine(Engine):
                     pre = f"{self.llm_prefix}{i}.self_attn.{name}."
                     self.G[pre + "lora_B.default.weight"] = (dext[r0:r1, ti * r:(ti + 1) * r] * mod.scaling).contiguous()
                     self.G[pre + "lora_A.default.weight"] = (dAp[:, ti * r:(ti + 1) * r] * ly["ln1"][:, None]).t().contiguous()
-            if kx and drops:    # dn1 += mask_t o (dTn_t . s_t A'_t) per target
+            if kx and fused:    # dn1 += sum_t mask_t o (dTn_t . s_t A'_t), one pass
+                ops.lora_dx_drop(dxs[:, H:], ly["a_cat_s"], dxs, drops, M=M, H=H, r=r, lddt=Kx, lddx=Kx)
+            elif kx and drops:  # ... or per target: rank-r GEMM into a scratch buffer + masked accumulate
                 for ti, d in enumerate(drops):
                     tmp = ops.gemm(dxs[:, H:], ly["a_catT_t"][ti], xm, M=M, N=H, K=kx, lda=Kx, ldo=H)
                     ops.dropout(tmp, dxs, d, rows=M, cols=H, ldi=H, ldo=Kx, scale=1.0, accumulate=True)
@@ -789,6 +812,15 @@ class TrainEngine(Engine):
     def train_backward(self, gloss=None, ctx=None):
         """Runs the backward pass of a train_forward (`ctx` = its out["_ctx"]; default: the last one); returns
         {reference parameter name: fp32 gradient}."""
+        return self.train_backward_late(self.train_backward_early(gloss, ctx))
+
+    @torch.no_grad()
+    def train_backward_early(self, gloss=None, ctx=None):
+        """First part of the backward pass: regression head, cross-attention fusion, NLinear decoder, temporal encoder and lane-polygon
+        encoder.  Every gradient outside `mllm.*` is FINAL when this returns (state["early"]: name -> gradient), which is what lets a
+        data-parallel step start their all-reduce while the decoder-stack backward (the bulk of the step) still runs
+        (finetune.py: FineTuner; the reference gets the same overlap from DistributedDataParallel's buckets, train.py:1127-1132).
+        Returns the state `train_backward_late` continues from."""
         if ctx is None:
             ctx = self._ctx
         if ctx is None:
@@ -804,14 +836,25 @@ class TrainEngine(Engine):
             self._ltsf_enc_bwd(denc, c_enc)
         if self.tr_poly:
             self._poly_bwd(dpoly, c_poly)
+        early = self._unpack_grads()
+        return dict(early=early, dfh=dfh, ctx=ctx, drop=self.drop)
+
+    @torch.no_grad()
+    def train_backward_late(self, state):
+        """Second part: LoRA-Llama stack, text-modality embedding and Q-Former (`mllm.*` gradients); returns all gradients."""
+        c_poly, c_qf, c_llm, c_enc, c_dec, B, L, Q, H, L_text, _ = state["ctx"]
+        self.drop = state["drop"]
+        out = state["early"]
+        self.G = {}
         if self.need_llm_bwd:
-            dfused = self._llm_bwd(dfh, c_llm)
+            dfused = self._llm_bwd(state["dfh"], c_llm)
             if self.tr_text:
                 dtxt = ops.copy_rows(dfused, self._new(B * L_text, H), rows=B * L_text, cols=H, in_remap=(L_text, L, Q))
                 ops.period_sum(dtxt, self._g("mllm.text_modality_embedding", (1, 1, H)), rows=B * L_text, cols=H)
             if self.tr_qf:
                 self._qformer_bwd(dfused, c_qf, L)
-        return self._unpack_grads()
+        out.update({k: v for k, v in self.G.items() if not k.startswith("_")})
+        return out
 
     def _unpack_grads(self):
         """Packed-layout gradients -> reference state_dict layout (inverse of the pack-time permutations)."""
