@@ -449,6 +449,7 @@ def measure_train(ctx, workload, steps, warmup, scenes=0, dropout=None):
     ms = ctx.max_over_ranks(e0.elapsed_time(e1))
     # the collective alone (same buffer, same communicator), outside the timed region
     ar_ms = ar_exposed_ms = None
+    ar_ab = {"overlapped": [], "serial": []}
     if world > 1:
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ft.all_reduce_only()
@@ -469,6 +470,20 @@ def measure_train(ctx, workload, steps, warmup, scenes=0, dropout=None):
         a1.record()
         torch.cuda.synchronize()
         ar_exposed_ms = ms / steps - ctx.max_over_ranks(a0.elapsed_time(a1)) / n_x
+        # overlapped vs serial exchange, A-B-A-B in this process (same graphs, same GPUs, same clocks): ms per step, max over ranks
+        keep_overlap = ft.overlap
+        for rnd in range(2):
+            for mode in (True, False):
+                ft.overlap = mode
+                ft.step(d["x"], d["vision"], s["context_str"], d["polygon"], lens, d["y"], ns, d["input_ids"], d["attention_mask"])
+                ctx.barrier()
+                a0.record()
+                for _ in range(n_x):
+                    ft.step(d["x"], d["vision"], s["context_str"], d["polygon"], lens, d["y"], ns, d["input_ids"], d["attention_mask"])
+                a1.record()
+                torch.cuda.synchronize()
+                ar_ab["overlapped" if mode else "serial"].append(round(ctx.max_over_ranks(a0.elapsed_time(a1)) / n_x, 3))
+        ft.overlap = keep_overlap
     # per-kernel breakdown: ONE extra eager (un-captured) step outside the timed region, CUDA events around every launch
     prof = ops.LaunchProfiler()
     ft.use_cuda_graph = False
@@ -495,6 +510,7 @@ def measure_train(ctx, workload, steps, warmup, scenes=0, dropout=None):
                    "scenes_per_gpu": B, "seq_len": Lseq, "parallelism": f"data-parallel x{world}",
                    "allreduce_payload_bytes": ft.payload_bytes, "allreduce_alone_ms": None if ar_ms is None else round(ar_ms, 3),
                    "allreduce_exposed_ms": None if ar_exposed_ms is None else round(ar_exposed_ms, 3),
+                   "allreduce_overlap_ab_ms_per_step": ar_ab if world > 1 else None,
                    "allreduce": ("two NCCL all-reduces per step over one flat fp32 buffer: the slice outside mllm.* (%d bytes, final before the "
                                  "decoder-stack backward) runs under the second CUDA graph, the mllm.* slice after it; exposed = step - step without the collective"
                                  % ((ft.flat_p.numel() - ft.n_late) * 4)) if ft.overlap else "one NCCL all-reduce of the flat trainable-gradient buffer per step",

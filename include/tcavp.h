@@ -289,6 +289,12 @@ int tcavp_traj_loss_bwd(const float* decoded, const float* y, const float* norm_
  * (row_scale optional: the RMSNorm rstd of the folded-norm form). */
 int tcavp_skinny_dw(const void* Y, int ldy, int y_dtype, const void* Z, int ldz, int z_dtype, const float* row_scale, float* out, int ldo,
                     long long M, int N, int J, tcavp_stream_t stream);
+/* Feed-forward sub-layer of a d_model = 64 post-norm encoder layer in ONE kernel (torch nn.TransformerEncoderLayer: the lane-polygon
+ * encoder, train.py:358 — d_model 64, dim_feedforward F):  out = LayerNorm(x + linear2(relu(linear1(x)))) * ln_w + ln_b.
+ * x, out: bf16 [M, 64] (contiguous rows); w1: bf16 [F, 64]; w2: bf16 [64, F]; biases / LayerNorm parameters fp32; F % 128 == 0.
+ * tcgen05 / TMEM / TMA: the [M, F] hidden activation stays in tensor memory (bf16, A operand of the second product). */
+int tcavp_ffn64_ln(const void* x, const void* w1, const float* b1, const void* w2, const float* b2, const float* ln_w, const float* ln_b,
+                   float eps, void* out, long long M, int F, tcavp_stream_t stream);
 /* peft lora.Linear in train() mode (train.py:432-440, lora_dropout): every target module t (q_proj, k_proj, v_proj) applies lora_A to
  * dropout(x) with its OWN mask keep_t(m H + h) = tcavp_dropout's mask function at site sites[t] / threshold thresh[t].  These three
  * entry points regenerate the masks on the operand fragments, so the masked copies of the [M, H] input never exist in memory.

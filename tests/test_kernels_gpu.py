@@ -403,6 +403,30 @@ def test_fusion_head_and_metrics(ops, B, To, tc):
     torch.testing.assert_close(m2[:5].cpu(), m[:5], rtol=1e-4, atol=1e-3)
 
 
+@pytest.mark.parametrize("M,F", [
+    (4096, 2048),        # the lane-polygon encoder: 64 points x 64 scenes, nn.TransformerEncoderLayer's default dim_feedforward
+    (256 * 150 + 77, 2048),   # more 256-row steps than SMs (x double buffer, accumulator re-arm across steps) + a ragged last step
+    (300, 128),          # a single hidden chunk per step
+    (1000, 640),         # five chunks: odd chunk counts flip the barrier parities from step to step
+])
+def test_ffn64_layernorm_fused(ops, M, F):
+    """out = LayerNorm(x + linear2(relu(linear1(x)))) of a d_model = 64 post-norm encoder layer (reference train.py:358) in one tcgen05
+    kernel (ffn_tm.cu) against the two-GEMM + LayerNorm form in fp32 on the same bf16 operands."""
+    g = torch.Generator().manual_seed(M + F)
+    x = torch.randn(M, 64, generator=g).bfloat16()
+    w1 = (torch.randn(F, 64, generator=g) * 0.125).bfloat16()
+    w2 = (torch.randn(64, F, generator=g) * F ** -0.5).bfloat16()
+    b1, b2 = torch.randn(F, generator=g) * 0.1, torch.randn(64, generator=g) * 0.1
+    lw, lb = 1 + 0.1 * torch.randn(64, generator=g), 0.1 * torch.randn(64, generator=g)
+    h = torch.relu(x.float() @ w1.float().t() + b1).bfloat16().float()          # the kernel feeds the second product bf16 activations
+    want = torch.nn.functional.layer_norm((x.float() + h @ w2.float().t() + b2).bfloat16().float(), (64,), lw, lb, 1e-5)
+    out = torch.full((M + 4, 64), 9.0, dtype=torch.bfloat16, device=DEV)
+    ops.ffn64_ln(x.to(DEV), w1.to(DEV), b1.to(DEV), w2.to(DEV), b2.to(DEV), lw.to(DEV), lb.to(DEV), out[:M], eps=1e-5)
+    assert ops.last_kernel() == "ffn64_ln_kernel"
+    torch.testing.assert_close(out[:M].float().cpu(), want, rtol=2e-2, atol=2e-2)
+    assert bool((out[M:] == 9.0).all())          # rows of the padded last tile are never stored
+
+
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 @pytest.mark.parametrize("nh,nkv,dh", [(12, 12, 64), (4, 2, 32), (4, 2, 128)])
 def test_gemm_fused_rope(ops, dtype, nh, nkv, dh):

@@ -271,6 +271,10 @@ class Engine:
         a = self._self_attention(x, T, B, sa, key_mask)
         y = ops.gemm(a, sa["out"].w, self._new(*x.shape, dtype=x.dtype), bias=sa["out"].b, residual=x)
         x = self._ln_res(y, L["n1"], out=self._new(*x.shape))
+        if (x.dtype == torch.bfloat16 and x.shape[1] == 64 and L["l1"].N % 128 == 0 and L["l1"].N <= 8192 and L["l1"].b is not None
+                and L["l2"].b is not None and not os.environ.get("TCAVP_NO_FFN_FUSED")):
+            # d_model 64 (lane-polygon encoder): both linears, the residual and LayerNorm 2 in one tcgen05 kernel, hidden activation in TMEM
+            return ops.ffn64_ln(x, L["l1"].w, L["l1"].b, L["l2"].w, L["l2"].b, L["n2"][0], L["n2"][1], self._new(*x.shape), eps=L["n2"][2])
         h = ops.gemm(x, L["l1"].w, self._new(x.shape[0], L["l1"].N), bias=L["l1"].b, act=ops.ACT_RELU)
         y = ops.gemm(h, L["l2"].w, self._new(*x.shape), bias=L["l2"].b, residual=x)
         return self._ln_res(y, L["n2"])
@@ -424,7 +428,8 @@ class Engine:
             per_scene = torch.empty(B, 2, dtype=torch.float32, device=self.dev)
         ops.fusion_head(fused, lt["fl_ln"][0], lt["fl_ln"][1], lt["fl_w1"], lt["fl_b1"], lt["fl_w2"], lt["fl_b2"], lt["wo"], lt["bo"], x,
                         decoded, y=y, norm_stat=norm_stat, metrics=metrics, per_scene=per_scene, B=B, C=C, T_in=T, T_out=To,
-                        tensor_cores=self.act == torch.bfloat16 and self.SPLIT_SMALL and not os.environ.get("TCAVP_NO_SPLIT_SMALL"))
+                        tensor_cores=(self.act == torch.bfloat16 and self.SPLIT_SMALL and not os.environ.get("TCAVP_NO_SPLIT_SMALL")
+                                      and not os.environ.get("TCAVP_NO_HEAD_TC")))
         if y is not None:
             out.update(metrics=metrics, per_scene=per_scene)
         return out

@@ -12,7 +12,7 @@ _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libtcavp.so")
 INCLUDE = os.path.join(_ROOT, "include")
-SOURCES = ["api.cu", "gemm.cu", "attention.cu", "attention_tc.cu", "attention_tm.cu", "attention_x.cu", "attention_xt.cu", "norm.cu", "elementwise.cu", "ltsf.cu", "backward.cu", "attention_bwd_tc.cu", "dw_tc.cu", "lora_drop.cu"]
+SOURCES = ["api.cu", "gemm.cu", "attention.cu", "attention_tc.cu", "attention_tm.cu", "attention_x.cu", "attention_xt.cu", "norm.cu", "elementwise.cu", "ltsf.cu", "backward.cu", "attention_bwd_tc.cu", "dw_tc.cu", "lora_drop.cu", "ffn_tm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I", INCLUDE]
 
@@ -20,7 +20,7 @@ EXPORTS = [
     "tcavp_last_error", "tcavp_version", "tcavp_device_info", "tcavp_launch_count", "tcavp_last_kernel", "tcavp_clock_probe", "tcavp_gemm_tile_order", "tcavp_gemm", "tcavp_attention",
     "tcavp_layernorm", "tcavp_rmsnorm", "tcavp_row_rstd", "tcavp_rope", "tcavp_rope_table", "tcavp_embed_text", "tcavp_add_rowvec",
     "tcavp_cast", "tcavp_split_bf16x3", "tcavp_poly_embed", "tcavp_masked_mean", "tcavp_ltsf_encode", "tcavp_nlinear_decode",
-    "tcavp_fusion_head", "tcavp_fusion_head_tc", "tcavp_traj_metrics", "tcavp_best_of_k", "tcavp_dropout",
+    "tcavp_fusion_head", "tcavp_fusion_head_tc", "tcavp_ffn64_ln", "tcavp_traj_metrics", "tcavp_best_of_k", "tcavp_dropout",
     # fine-tune step
     "tcavp_transpose", "tcavp_period_sum", "tcavp_relu_bwd", "tcavp_axpby", "tcavp_swiglu", "tcavp_swiglu_bwd", "tcavp_layernorm_bwd",
     "tcavp_rmsnorm_bwd", "tcavp_rope_adjacent", "tcavp_copy_rows", "tcavp_masked_mean_bwd", "tcavp_nlinear_bwd", "tcavp_head_assemble",

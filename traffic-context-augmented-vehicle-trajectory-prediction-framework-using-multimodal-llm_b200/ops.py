@@ -381,6 +381,20 @@ def fusion_head(fused, ln_w, ln_b, w1, b1, w2, b2, wo, bo, x, decoded, *, y=None
     return decoded
 
 
+def ffn64_ln(x, w1, b1, w2, b2, ln_w, ln_b, out, *, eps=1e-5):
+    """out = LayerNorm(x + w2 relu(w1 x + b1) + b2) for d_model 64 in one tcgen05 kernel (tcavp_ffn64_ln); x, out bf16 [M, 64]."""
+    _need_cuda(x, w1, b1, w2, b2, ln_w, ln_b, out)
+    M, F = x.shape[0], w1.shape[0]
+    if x.dtype != torch.bfloat16 or w1.dtype != torch.bfloat16 or w2.dtype != torch.bfloat16 or out.dtype != torch.bfloat16:
+        raise TypeError("ffn64_ln: x, w1, w2, out must be bf16")
+    if x.shape[1] != 64 or tuple(w1.shape) != (F, 64) or tuple(w2.shape) != (64, F) or not (x.is_contiguous() and w1.is_contiguous() and w2.is_contiguous() and out.is_contiguous()):
+        raise ValueError("ffn64_ln: contiguous x [M, 64], w1 [F, 64], w2 [64, F]")
+    with _Timed("ffn64_ln_kernel[F%d]" % F, 4.0 * M * 64 * F, float(2 * M * 64 * 2 + 2 * F * 64 * 2)):
+        _lib.check(_lib.load().tcavp_ffn64_ln(_p(x), _p(w1), _p(b1), _p(w2), _p(b2), _p(ln_w), _p(ln_b), c_float(eps), _p(out), c_longlong(M), F,
+                                              _stream()), "tcavp_ffn64_ln")
+    return out
+
+
 def traj_metrics(decoded, y, norm_stat, metrics, per_scene, *, B, T_out):
     _need_cuda(decoded, y, norm_stat, metrics, per_scene)
     with _Timed("traj_metrics_kernel", 0.0, float(B * 2 * T_out * 4 * 2 + B * 24)):
