@@ -388,7 +388,8 @@ def measure_infer(ctx, workload, steps, warmup, e2e=True, scenes=0, merge_lora=F
                              "; roofline: separate profiling pass; e2e: host wall clock",
                    "l2": "per-step working set (>= 1 GB of activations) is far larger than the 126 MB L2; no explicit flush",
                    "lora": "merged into the base weights at pack time" if merge_lora else "unmerged (rank-r side path fused into the QKV GEMM)",
-                   "weights": "seeded random init (no checkpoints offline)", "ade_px": round(ade, 3), "fde_px": round(fde, 3)},
+                   "weights": "seeded random init (no checkpoints offline)", "ade_px": round(ade, 3), "fde_px": round(fde, 3),
+                   "gemm_route": ops._ROUTE["tuned"]},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof,
     }
     if e2e_block:
@@ -514,7 +515,7 @@ def measure_train(ctx, workload, steps, warmup, scenes=0, dropout=None):
                    "allreduce": ("two NCCL all-reduces per step over one flat fp32 buffer: the slice outside mllm.* (%d bytes, final before the "
                                  "decoder-stack backward) runs under the second CUDA graph, the mllm.* slice after it; exposed = step - step without the collective"
                                  % ((ft.flat_p.numel() - ft.n_late) * 4)) if ft.overlap else "one NCCL all-reduce of the flat trainable-gradient buffer per step",
-                   "trainable_params": ft.flat_p.numel(),
+                   "trainable_params": ft.flat_p.numel(), "gemm_route": ops._ROUTE["tuned"],
                    "loss_first_last": [round(losses[0], 3), round(losses[-1], 3)], "peak_mem_gib": round(peak_gb, 2)},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof}
     return out

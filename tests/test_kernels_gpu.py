@@ -542,9 +542,28 @@ def test_gemm_large_fused_rope_and_lora_extension(ops):
     torch.testing.assert_close(out.float().cpu(), want, rtol=2e-2, atol=2e-2)
 
 
-def test_gemm_wide_kernel_sampled_rows(ops):
+@pytest.mark.parametrize("wide", [True, False])
+def test_gemm_wide_kernel_sampled_rows(ops, wide):
     """The 512 x 256 pair tile (K >= 2048 and >= 4 waves of tiles) at a 7B-like shape; the CPU check samples rows (incl. the first / last
-    row of several 128-row halves) instead of forming the whole product."""
+    row of several 128-row halves) instead of forming the whole product.  Which kernel serves long contractions is tuned per board
+    (ops.autotune_gemm_route), so both are pinned here in turn (`wide` False: the 256 x 256 pair tile on the same problem)."""
+    import tcavp_b200.lib as L
+    ops.autotune_gemm_route()                         # whatever the process decided is restored below
+    old = L.load().tcavp_gemm_wide_min_k(2048 if wide else 0)
+    try:
+        _wide_kernel_case(ops, "gemm_tc_wide_kernel" if wide else "gemm_tc_pair_kernel")
+    finally:
+        L.load().tcavp_gemm_wide_min_k(old)
+
+
+def test_gemm_route_autotune_reports_a_decision(ops):
+    t = ops.autotune_gemm_route()
+    assert t["source"] in ("autotune", "TCAVP_GEMM_WIDE_K") and ops._ROUTE["wide_k"] in (0, 2048) or t["source"] == "TCAVP_GEMM_WIDE_K"
+    if t["source"] == "autotune":
+        assert t["wide_ms"] > 0 and t["pair_ms"] > 0 and t["long_k_kernel"] in ("gemm_tc_wide_kernel", "gemm_tc_pair_kernel")
+
+
+def _wide_kernel_case(ops, kernel):
     M, N, K = 40960 + 37, 1024, 2048 + 64
     g = torch.Generator(device=DEV).manual_seed(5)
     a = (torch.randn(M, K, device=DEV, generator=g) * 0.5).bfloat16()
@@ -554,6 +573,7 @@ def test_gemm_wide_kernel_sampled_rows(ops):
     ss = torch.zeros(M, dtype=torch.int64, device=DEV)
     out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
     ops.gemm(a, w, out, bias=bias, residual=res, sumsq_out=ss)
+    assert ops.last_kernel() == kernel
     rows = torch.randint(0, M, (384,), generator=torch.Generator().manual_seed(6))
     rows[:10] = torch.tensor([0, 127, 128, 255, 256, 511, 512, 40959, 40960, M - 1])
     rows = rows.to(DEV)

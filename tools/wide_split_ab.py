@@ -12,6 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 CONFIGS = [  # (label, env)
     ("pair (default routing)", {"TCAVP_GEMM_WIDE_K": "2048"}),
+    ("pair kernel for every shape", {"TCAVP_GEMM_WIDE_K": "0"}),
     ("wide k-major", {"TCAVP_GEMM_WIDE_K": "512", "TCAVP_GEMM_WIDE_SPLIT": "1"}),
     ("wide split 2", {"TCAVP_GEMM_WIDE_K": "512", "TCAVP_GEMM_WIDE_SPLIT": "2"}),
     ("wide split 3", {"TCAVP_GEMM_WIDE_K": "512", "TCAVP_GEMM_WIDE_SPLIT": "3"}),
@@ -19,7 +20,8 @@ CONFIGS = [  # (label, env)
 ]
 SHAPES = [  # (name, M, N, K, epilogue)
     ("gate/up", 147456, 6144, 768, "swiglu"), ("qkv", 147456, 2304, 784, "plain"), ("o_proj", 147456, 768, 768, "res"),
-    ("down", 147456, 768, 3072, "res"), ("7b o", 36864, 4096, 4096, "res"),
+    ("down", 147456, 768, 3072, "res"), ("7b o", 36864, 4096, 4096, "res"), ("7b gate/up", 36864, 22016, 4096, "swiglu"),
+    ("7b down", 36864, 4096, 11008, "res"),
 ]
 
 
@@ -70,8 +72,11 @@ if __name__ == "__main__":
     if "--child" in sys.argv:
         child()
         sys.exit(0)
+    only = [a for a in sys.argv[1:] if not a.startswith("--")]
     for rep in range(2):           # A-B-...-A-B: two passes so drift of the box shows
         for label, env in CONFIGS:
+            if only and not any(o in label for o in only):
+                continue
             print(f"[{label}] pass {rep}", flush=True)
             e = dict(os.environ); e.update(env)
             try:

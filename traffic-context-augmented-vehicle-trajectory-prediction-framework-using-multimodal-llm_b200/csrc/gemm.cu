@@ -1468,14 +1468,18 @@ static int launch_tc_wide(const tcavp_gemm_args& a, const EpilogueParams& ep, cu
   return check_launch("gemm_tc_wide_kernel");
 }
 
-static int wide_min_k() {   // TCAVP_GEMM_WIDE_K: contractions at least this long use the 512 x 256 pair tile (0 disables it)
-  static int v = -1;
-  if (v < 0) {
+// TCAVP_GEMM_WIDE_K: contractions at least this long use the 512 x 256 pair tile (0 disables it).  Without the variable the value is
+// tunable at run time (tcavp_gemm_wide_min_k): which of the two kernels wins on K >= 2048 differs from one B200 to the next (measured:
+// wide +6-15 % on 1 kW boards, pair +6-12 % on a 700 W board — profiles/wide_vs_pair_r02y.txt), so ops.py times both once per process.
+static int g_wide_k = -2;      // -2: not initialised
+static int wide_min_k() {
+  if (g_wide_k == -2) {
     const char* e = getenv("TCAVP_GEMM_WIDE_K");
-    v = e ? atoi(e) : 2048;
+    int v = e ? atoi(e) : 2048;
     if (v < 0) v = 0;
+    g_wide_k = v;
   }
-  return v;
+  return g_wide_k;
 }
 
 }  // namespace tc
@@ -1631,6 +1635,12 @@ static void launch_simt(const tcavp_gemm_args& a, const EpilogueParams& ep, cuda
 }
 }  // namespace simt
 }  // namespace tcavp
+
+extern "C" int tcavp_gemm_wide_min_k(int new_value) {
+  const int old = tcavp::tc::wide_min_k();
+  if (new_value >= 0) tcavp::tc::g_wide_k = new_value;
+  return old;
+}
 
 extern "C" int tcavp_gemm_tile_order(int tiles_m, int tiles_n, int panel_w, int* mg, int* nt) {
   TCAVP_REQUIRE(tiles_m > 0 && tiles_n > 0 && panel_w > 0 && mg != nullptr && nt != nullptr, "tcavp_gemm_tile_order: bad arguments");

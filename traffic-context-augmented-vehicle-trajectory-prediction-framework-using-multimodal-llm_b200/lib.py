@@ -17,7 +17,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-I", INCLUDE]
 
 EXPORTS = [
-    "tcavp_last_error", "tcavp_version", "tcavp_device_info", "tcavp_launch_count", "tcavp_last_kernel", "tcavp_clock_probe", "tcavp_gemm_tile_order", "tcavp_gemm", "tcavp_attention",
+    "tcavp_last_error", "tcavp_version", "tcavp_device_info", "tcavp_launch_count", "tcavp_last_kernel", "tcavp_clock_probe", "tcavp_gemm_tile_order", "tcavp_gemm_wide_min_k", "tcavp_gemm", "tcavp_attention",
     "tcavp_layernorm", "tcavp_rmsnorm", "tcavp_row_rstd", "tcavp_rope", "tcavp_rope_table", "tcavp_embed_text", "tcavp_add_rowvec",
     "tcavp_cast", "tcavp_split_bf16x3", "tcavp_poly_embed", "tcavp_masked_mean", "tcavp_ltsf_encode", "tcavp_nlinear_decode",
     "tcavp_fusion_head", "tcavp_fusion_head_tc", "tcavp_ffn64_ln", "tcavp_traj_metrics", "tcavp_best_of_k", "tcavp_dropout",

@@ -155,6 +155,66 @@ def _need_cuda(*ts):
             raise _lib.TcavpError("tcavp ops need CUDA tensors (there is no CPU fallback)")
 
 
+# Long contractions (K >= 2048: down_proj, every 7B-class projection, the dX GEMMs of the fine-tune step) have two tcgen05 kernels: the
+# 512 x 256 "wide" CTA-pair tile and the double-buffered 256 x 256 pair tile.  Which one wins is a property of the board, not of the shape:
+# wide is 6-15 % ahead on B200s running at the 1 kW cap, the pair tile 6-12 % ahead on a 700 W-capped one (profiles/wide_vs_pair_r02y.txt).
+# So the first long-K GEMM of a process times both for ~0.1 s each on this GPU and keeps the faster (TCAVP_GEMM_WIDE_K pins it instead).
+_ROUTE = {"wide_k": None, "tuned": None}
+
+
+def autotune_gemm_route(budget_ms=120.0):
+    """Sets the wide-kernel routing threshold of tcavp_gemm from a sustained A/B on the current device; returns the decision dict."""
+    lib = _lib.load()
+    env = _os.environ.get("TCAVP_GEMM_WIDE_K")
+    if env is not None or torch.cuda.is_current_stream_capturing():
+        if _ROUTE["wide_k"] is None:
+            _ROUTE["wide_k"] = int(lib.tcavp_gemm_wide_min_k(-1))
+            _ROUTE["tuned"] = {"source": "TCAVP_GEMM_WIDE_K" if env is not None else "default (stream capture in progress)"}
+        return _ROUTE["tuned"]
+    global _PROF
+    prof, _PROF = _PROF, None              # the probe launches are not part of any profiled step
+    launches0 = launch_count()
+    try:
+        dev = torch.cuda.current_device()
+        gen = torch.Generator(device="cuda").manual_seed(1)
+        shapes = [(32768, 768, 3072), (16384, 4096, 4096)]
+        ms = {2048: 0.0, 0: 0.0}
+        bufs = []
+        for (M, N, K) in shapes:
+            a = (torch.randn(M, K, device="cuda", generator=gen) * 0.5).bfloat16()
+            w = (torch.randn(N, K, device="cuda", generator=gen) * 0.05).bfloat16()
+            bufs.append((a, w, torch.empty(M, N, device="cuda", dtype=torch.bfloat16)))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for rnd in range(2):               # A-B-A-B: clock drift of the warming GPU hits both variants alike
+            for wk in (2048, 0):
+                lib.tcavp_gemm_wide_min_k(wk)
+                for (a, w, o) in bufs:
+                    g = GemmArgs()
+                    g.M, g.N, g.K = a.shape[0], w.shape[0], a.shape[1]
+                    g.A, g.lda, g.W, g.ldw, g.in_dtype = a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), BF16
+                    g.out, g.ldo, g.out_dtype, g.act = o.data_ptr(), o.stride(0), BF16, ACT_NONE
+                    _lib.check(lib.tcavp_gemm(byref(g), _stream()), "tcavp_gemm")
+                    e0.record()
+                    _lib.check(lib.tcavp_gemm(byref(g), _stream()), "tcavp_gemm")
+                    e1.record()
+                    e1.synchronize()
+                    n = max(3, min(400, int(budget_ms / 2 / max(e0.elapsed_time(e1), 1e-3))))
+                    e0.record()
+                    for _ in range(n):
+                        lib.tcavp_gemm(byref(g), _stream())
+                    e1.record()
+                    e1.synchronize()
+                    ms[wk] += e0.elapsed_time(e1) / n
+        wide_k = 2048 if ms[2048] <= ms[0] else 0
+        lib.tcavp_gemm_wide_min_k(wide_k)
+        _ROUTE["wide_k"] = wide_k
+        _ROUTE["tuned"] = {"source": "autotune", "device": dev, "wide_ms": round(ms[2048], 4), "pair_ms": round(ms[0], 4),
+                           "long_k_kernel": "gemm_tc_wide_kernel" if wide_k else "gemm_tc_pair_kernel", "probe_launches": launch_count() - launches0}
+    finally:
+        _PROF = prof
+    return _ROUTE["tuned"]
+
+
 def gemm(a, w, out, *, M=None, N=None, K=None, lda=None, ldw=None, ldo=None, bias=None, residual=None, ldr=None,
          act=ACT_NONE, remap=(0, 0, 0), rope=None, row_scale=None, aux_out=None, sumsq_out=None, row_sumsq=None):
     """out = act(a @ w.T + bias) + residual.  a: [M, >=K] row-major (lda = a.stride(0)), w: [N, >=K]."""
@@ -196,7 +256,10 @@ def gemm(a, w, out, *, M=None, N=None, K=None, lda=None, ldw=None, ldo=None, bia
     if rope is not None:     # (table, L, dh, cols)
         g.rope_cos_sin, g.rope_L, g.rope_dh, g.rope_cols = rope[0].data_ptr(), rope[1], rope[2], rope[3]
     if g.in_dtype == BF16:
-        if g.N > 128 and g.K >= 2048 and g.M >= 8192 and ((g.M + 511) // 512) * ((g.N + 255) // 256) >= 4 * 74:
+        long_k = g.N > 128 and g.K >= 2048 and g.M >= 8192 and ((g.M + 511) // 512) * ((g.N + 255) // 256) >= 4 * 74
+        if long_k and _ROUTE["wide_k"] is None:
+            autotune_gemm_route()
+        if long_k and _ROUTE["wide_k"] and g.K >= _ROUTE["wide_k"]:
             kern = "gemm_tc_wide_kernel[N%d,K%d]" % (g.N, g.K)     # mirrors tcavp_gemm's dispatch (long contraction, >= 4 waves of tiles)
         elif g.N > 128 and g.M >= 2048:    # CTA-pair (cta_group::2) kernel for the large problems
             kern = "gemm_tc_pair_kernel<256>[N%d,K%d]" % (g.N, g.K)
