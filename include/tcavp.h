@@ -337,6 +337,12 @@ int tcavp_attention_bwd(const tcavp_attn_args* args, const void* dout, long long
 int tcavp_attention_bwd_owned(const tcavp_attn_args* args, const void* dout, long long do_sb, long long do_st, void* dq, long long dq_sb,
                               long long dq_st, void* dk, long long dk_sb, long long dk_st, void* dv, long long dv_sb, long long dv_st,
                               int dkv_dtype, tcavp_stream_t stream);
+/* Stage-1 (CausalLM) objective on the labelled rows of a logits chunk — HF ForCausalLMLoss behind LlamaForCausalLM.forward(labels=...)
+ * (HF:487-491; reference scripts/check_generation.py:131-151): fp32 logits [rows, V] (row stride ld), targets int64 [rows] (already
+ * shifted, no -100 rows).  loss_sum[0] += sum_rows (logsumexp(row) - row[target]); when grad != NULL, grad[row, :] = (softmax(row) -
+ * onehot(target)) * scale in grad_dtype (TCAVP_F32 / TCAVP_BF16; scale = incoming gradient / number of labelled positions). */
+int tcavp_ce_loss(const float* logits, long long ld, const long long* targets, float* loss_sum, void* grad, long long ldg, int grad_dtype,
+                  long long rows, int V, float scale, tcavp_stream_t stream);
 /* Fused AdamW over flat fp32 buffers, torch.optim.AdamW semantics (im_kim_train_GRN.py:1008); grad_scale multiplies the
  * gradient first (1/world_size after a sum all-reduce). */
 int tcavp_adamw(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1, float beta2,

@@ -196,8 +196,62 @@ def make_grads(name="tiny_b5_grads"):
     print(f"{name}: {os.path.getsize(path) / 1e6:.2f} MB  loss={float(loss.detach()):.4f}  {len(grads)} gradient tensors")
 
 
+# stage-1 fixtures: name -> (model preset, B, l_text, prompt length)
+STAGE1_FIXTURES = {
+    "tiny_b5_stage1": ("tiny", 5, 24, 9),
+    "cfg1_b2_stage1": ("cfg1", 2, 128, 70),       # the 768-class geometry, vocabulary 32000
+}
+
+
+def make_stage1(name="tiny_b5_stage1"):
+    """Stage-1 (CausalLM) objective of the UNMODIFIED reference classes (scripts/train.py:516-547 builds exactly this call; the stage-1
+    script scripts/check_generation.py:131-151 returns its `outputs`): Q-Former image tokens + text embeddings (+ modality vectors) through
+    the peft-wrapped HF LlamaForCausalLM with labels -> outputs.loss, autograd gradients of every trainable mllm tensor.  float64 run,
+    eval mode (dropout off), like the other gradient fixtures."""
+    from oracle import restated
+    preset, B, l_text, prompt_len = STAGE1_FIXTURES[name]
+    mc = dict(T.MODEL_PRESETS[preset])
+    lc = T.resolve_llama(mc["base_model_name"])
+    mod = ref_loader.load_reference("scripts/train.py", lc)
+    model = ref_loader.build_reference_model(mod, mc, lc)
+    sd = model.state_dict()
+    T.deterministic_fill_(sd, 13)
+    model.load_state_dict(sd, strict=True)
+    s = T.make_scenes(B, mc["seq_len"], mc["out_len"], vision_dim=mc.get("vision_dim", 512), l_text=l_text, vocab=lc["vocab_size"], seed=79)
+    labels = restated.stage1_labels(s["input_ids"], s["attention_mask"], prompt_len)
+
+    def ref_loss(m, vision):
+        mm = m.mllm                                                   # the reference's LlamaMultiModal, its own sub-modules
+        img = mm.q_proj(mm.qformer(vision)) + mm.vision_modality_embedding
+        txt = mm.llama_wrapper.llama_model.get_input_embeddings()(s["input_ids"]) + mm.text_modality_embedding
+        fused = torch.cat([img, txt], dim=1)
+        fmask = torch.cat([torch.ones((B, img.size(1)), dtype=s["attention_mask"].dtype), s["attention_mask"]], dim=1)
+        flab = torch.full((B, img.size(1) + labels.size(1)), -100, dtype=labels.dtype)
+        flab[:, img.size(1):] = labels
+        return mm.llama_wrapper(inputs_embeds=fused, attention_mask=fmask, labels=flab, output_hidden_states=True).loss
+    model.eval()
+    with torch.no_grad():
+        loss32 = ref_loss(model, s["vision"])
+    model = model.double()
+    model.zero_grad()
+    loss = ref_loss(model, s["vision"].double())
+    loss.backward()
+    assert abs(float(loss) - float(loss32)) < 1e-4 * float(loss), (float(loss), float(loss32))
+    grads = {k: p.grad for k, p in model.named_parameters() if p.requires_grad and p.grad is not None}
+    assert grads and all(k.startswith("mllm.") for k in grads), [k for k in grads if not k.startswith("mllm.")][:3]
+    fix = {"name": name, "model_cfg": mc, "llama_cfg": lc, "weight_seed": 13,
+           "inputs": {"vision": s["vision"], "input_ids": s["input_ids"], "attention_mask": s["attention_mask"], "labels": labels},
+           "loss": loss.detach().float(), "loss_fp32_run": loss32.detach(), "n_tokens": int((labels != -100).sum()), "n_trainable": len(grads),
+           "precision": "reference executed in float64 (see make_stage1)",
+           "grads": {k: restated.compress_grad(v) for k, v in grads.items()},
+           "versions": {"torch": str(torch.__version__), "transformers": __import__("transformers").__version__}}
+    path = os.path.join(GOLDEN_DIR, name + ".pt")
+    torch.save(fix, path)
+    print(f"{name}: {os.path.getsize(path) / 1e6:.2f} MB  loss={float(loss.detach()):.4f}  {fix['n_tokens']} labelled tokens, {len(grads)} gradient tensors")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
-    for n in (sys.argv[1:] or list(FIXTURES) + list(GRAD_FIXTURES) + list(DROP_FIXTURES)):
-        make_grads(n) if "_grads" in n else make(n)
+    for n in (sys.argv[1:] or list(FIXTURES) + list(GRAD_FIXTURES) + list(DROP_FIXTURES) + list(STAGE1_FIXTURES)):
+        make_stage1(n) if n in STAGE1_FIXTURES else (make_grads(n) if "_grads" in n else make(n))

@@ -395,6 +395,43 @@ def loss_and_grads(sd, cfg, llama_cfg, x, vision, polygon, poly_len, input_ids, 
     return out["loss"].detach(), out["decoded"].detach(), {k: (g if g is not None else torch.zeros_like(sd[k])) for k, g in zip(keys, grads)}
 
 
+# --------------------------------------------------------------------------------------------------
+# stage 1: CausalLM objective (reference scripts/check_generation.py:131-151; the same call inside scripts/train.py:533-547)
+# --------------------------------------------------------------------------------------------------
+
+
+def stage1_labels(input_ids, attention_mask, prompt_len):
+    """Labels of a synthetic stage-1 batch: the answer part of every sequence (the reference's dataset masks the prompt and the padding
+    with -100)."""
+    lab = input_ids.clone()
+    lab[:, :prompt_len] = -100
+    lab[attention_mask == 0] = -100
+    return lab
+
+
+def causal_lm_loss(sd, cfg, llama_cfg, vision, input_ids, attention_mask, labels):
+    """HF LlamaForCausalLM.forward(inputs_embeds=[image tokens | text], labels=[-100 x n_img | labels]).loss (HF:487-491 ForCausalLMLoss:
+    logits upcast to fp32, position t scored against token t + 1, ignore_index -100, mean over the labelled positions)."""
+    fh, img = mllm_forward(sd, cfg, llama_cfg, vision, input_ids, attention_mask)
+    lp = find_llm_prefix(sd)
+    logits = linear(fh, sd[lp[: -len("model.")] + "lm_head.weight"]).float()
+    B, Q = img.shape[:2]
+    fused_labels = torch.cat([torch.full((B, Q), -100, dtype=labels.dtype), labels], dim=1)
+    return torch.nn.functional.cross_entropy(logits[:, :-1].reshape(-1, logits.shape[-1]), fused_labels[:, 1:].reshape(-1), ignore_index=-100)
+
+
+def stage1_loss_and_grads(sd, cfg, llama_cfg, vision, input_ids, attention_mask, labels, keys=None):
+    """(loss, {key: gradient}) of the stage-1 objective for the trainable mllm.* tensors (autograd through the restatement)."""
+    sd = {k: (v.detach().float().clone() if v.is_floating_point() else v) for k, v in sd.items()}
+    keys = list(keys) if keys is not None else [k for k in trainable_keys(sd) if k.startswith("mllm.")]
+    for k in keys:
+        sd[k].requires_grad_(True)
+    with torch.enable_grad():
+        loss = causal_lm_loss(sd, cfg, llama_cfg, vision, input_ids, attention_mask, labels)
+        grads = torch.autograd.grad(loss, [sd[k] for k in keys], allow_unused=True)
+    return loss.detach(), {k: (g if g is not None else torch.zeros_like(sd[k])) for k, g in zip(keys, grads)}
+
+
 def compress_grad(g, big=50_000):
     """Golden-fixture form of a gradient: full tensor when small, else first rows + row / column sums."""
     g = g.detach().float()

@@ -134,3 +134,22 @@ def test_dropout_mask_function_and_site_table():
     x = a.astype(np.float64) - a.mean()
     for lag in (1, 2, 64, 768, 4096):
         assert abs((x[:-lag] * x[lag:]).mean() / x.var()) < 5e-3, lag
+
+
+@pytest.mark.parametrize("name", ["tiny_b5_stage1", "cfg1_b2_stage1"])
+def test_restated_stage1_objective_matches_reference(name):
+    """Pins the stage-1 (CausalLM) oracle: restated.causal_lm_loss and its autograd gradients == `outputs.loss` of the unmodified reference
+    classes around HF's LlamaForCausalLM (reference scripts/check_generation.py:131-151, train.py:533-547) and its gradients."""
+    fix = load_golden(name)
+    m = T.MultiModalTrajectoryModel(**fix["model_cfg"])
+    sd = m.state_dict()
+    T.deterministic_fill_(sd, fix["weight_seed"])
+    i = fix["inputs"]
+    assert int((i["labels"] != -100).sum()) == fix["n_tokens"] > 0
+    loss, grads = restated.stage1_loss_and_grads(sd, fix["model_cfg"], fix["llama_cfg"], i["vision"], i["input_ids"], i["attention_mask"], i["labels"])
+    torch.testing.assert_close(loss, fix["loss"], rtol=1e-5, atol=0)
+    assert set(grads) == set(fix["grads"]) and len(grads) == fix["n_trainable"]
+    for k, want in fix["grads"].items():
+        ref = want["full"] if "full" in want else want["head"]
+        scale = float(ref.abs().max()) + 1e-8
+        _check_against_compressed(grads[k], want, rtol=2e-3, atol=2e-4 * scale + 1e-7, key=k)

@@ -12,7 +12,7 @@ _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libtcavp.so")
 INCLUDE = os.path.join(_ROOT, "include")
-SOURCES = ["api.cu", "gemm.cu", "attention.cu", "attention_tc.cu", "attention_tm.cu", "attention_x.cu", "attention_xt.cu", "norm.cu", "elementwise.cu", "ltsf.cu", "backward.cu", "attention_bwd_tc.cu", "dw_tc.cu", "lora_drop.cu", "ffn_tm.cu"]
+SOURCES = ["api.cu", "gemm.cu", "attention.cu", "attention_tc.cu", "attention_tm.cu", "attention_x.cu", "attention_xt.cu", "norm.cu", "elementwise.cu", "ltsf.cu", "backward.cu", "attention_bwd_tc.cu", "dw_tc.cu", "lora_drop.cu", "ffn_tm.cu", "ce.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I", INCLUDE]
 
@@ -25,7 +25,7 @@ EXPORTS = [
     "tcavp_transpose", "tcavp_period_sum", "tcavp_relu_bwd", "tcavp_axpby", "tcavp_swiglu", "tcavp_swiglu_bwd", "tcavp_layernorm_bwd",
     "tcavp_rmsnorm_bwd", "tcavp_rope_adjacent", "tcavp_copy_rows", "tcavp_masked_mean_bwd", "tcavp_nlinear_bwd", "tcavp_head_assemble",
     "tcavp_traj_loss_bwd", "tcavp_skinny_dw", "tcavp_dw", "tcavp_attention_bwd", "tcavp_attention_bwd_owned", "tcavp_adamw",
-    "tcavp_lora_a_drop", "tcavp_lora_dx_drop", "tcavp_lora_da_drop",
+    "tcavp_lora_a_drop", "tcavp_lora_dx_drop", "tcavp_lora_da_drop", "tcavp_ce_loss",
 ]
 
 

@@ -47,6 +47,41 @@ class _FineTuneStep(torch.autograd.Function):
             res.append(g)
         return (None, None) + tuple(res)
 
+class _Stage1Step(torch.autograd.Function):
+    """Autograd node of the stage-1 (CausalLM) objective: forward = TrainEngine.lm_forward, backward = TrainEngine.lm_backward."""
+
+    @staticmethod
+    def forward(ctx, eng, inputs, *params):
+        out = eng.lm_forward(**inputs)
+        ctx.eng = eng
+        ctx.stash = out.pop("_ctx")
+        ctx.set_materialize_grads(False)
+        return out["loss"].clone()
+
+    @staticmethod
+    def backward(ctx, gloss):
+        n = len(ctx.eng.params)
+        if gloss is None:
+            return (None, None) + (None,) * n
+        stash, ctx.stash = ctx.stash, None
+        if stash is None:
+            raise RuntimeError("tcavp_b200: backward through the same stage-1 step twice (activations are freed after the first pass)")
+        grads = ctx.eng.lm_backward(gloss, stash)
+        res = []
+        for (name, p) in ctx.eng.params:
+            g = grads.get(name)
+            res.append(None if g is None else g.reshape(p.shape).to(p.dtype))
+        return (None, None) + tuple(res)
+
+
+class CausalLMOutput:
+    """What the reference's stage-1 loop reads off the model call (scripts/check_generation.py: `outputs.loss`)."""
+    __slots__ = ("loss", "n_tokens", "logits")
+
+    def __init__(self, loss, n_tokens):
+        self.loss, self.n_tokens, self.logits = loss, n_tokens, None
+
+
 # --------------------------------------------------------------------------------------------------
 # parameter containers (names = reference names)
 # --------------------------------------------------------------------------------------------------
@@ -570,6 +605,20 @@ class MultiModalTrajectoryModel(nn.Module):
         out = self.best_of_k_metrics(c, y, norm_stat)
         out["candidates"] = c
         return out
+
+    def stage1_forward(self, vision_embs, input_ids, attention_mask, labels):
+        """The stage-1 model call of the reference (scripts/check_generation.py:131-151: Q-Former image tokens + prompt / answer tokens
+        through the LoRA-Llama CausalLM with `labels`): returns an object whose `.loss` is the token cross-entropy (HF:487-491 — shifted,
+        -100 ignored, mean over labelled tokens).  In grad mode the loss carries the hand-written backward (LoRA A / B, Q-Former,
+        q_proj, modality embeddings), so `outputs.loss.backward(); optimizer.step()` of that script works unchanged; under no_grad it is
+        the evaluation loss.  The vocabulary logits are never materialised beyond one row chunk (`.logits` is None)."""
+        eng = self.train_engine()
+        inputs = dict(vision=vision_embs, input_ids=input_ids, attention_mask=attention_mask, labels=labels)
+        if torch.is_grad_enabled() and any(p.requires_grad for _, p in eng.params):
+            loss = _Stage1Step.apply(eng, inputs, *[p for _, p in eng.params])
+            return CausalLMOutput(loss, None)
+        out = eng.lm_forward(**inputs, keep=False)
+        return CausalLMOutput(out["loss"], out["n_tokens"])
 
     def _train_step(self, x, vision_embs, lane_polygon_batch, lane_polygon_len, y, norm_stat, input_ids, attention_mask):
         eng = self.train_engine()

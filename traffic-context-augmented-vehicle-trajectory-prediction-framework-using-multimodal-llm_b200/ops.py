@@ -525,6 +525,21 @@ def lora_da_drop(x, dT, out, drops, *, M, H, r, ldx=None, lddt=None, row_scale=N
     return out
 
 
+def ce_loss(logits, targets, loss_sum, grad=None, *, scale=1.0):
+    """loss_sum[0] += sum over rows of (logsumexp(row) - row[target]); grad (optional, bf16 / fp32 [rows, V]) = (softmax - onehot) * scale."""
+    _need_cuda(logits, targets, loss_sum, grad)
+    if logits.dtype != torch.float32 or targets.dtype != torch.int64 or loss_sum.dtype != torch.float32:
+        raise TypeError("ce_loss: fp32 logits, int64 targets, fp32 loss_sum")
+    rows, V = logits.shape
+    if grad is not None and (grad.shape[0] != rows or grad.shape[1] < V):
+        raise ValueError("ce_loss: grad must be [rows, >= V]")
+    with _Timed("ce_loss_kernel", 0.0, float(rows * V * (4 + (grad.element_size() if grad is not None else 0)))):
+        _lib.check(_lib.load().tcavp_ce_loss(_p(logits), c_longlong(logits.stride(0)), _p(targets), _p(loss_sum), _p(grad),
+                                             c_longlong(grad.stride(0) if grad is not None else 0), dt(grad) if grad is not None else 0,
+                                             c_longlong(rows), V, c_float(scale), _stream()), "tcavp_ce_loss")
+    return loss_sum
+
+
 def launch_count():
     return int(_lib.load().tcavp_launch_count())
 

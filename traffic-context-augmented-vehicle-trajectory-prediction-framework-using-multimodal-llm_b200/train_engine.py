@@ -856,6 +856,85 @@ class TrainEngine(Engine):
         out.update({k: v for k, v in self.G.items() if not k.startswith("_")})
         return out
 
+    # ---- stage 1: CausalLM objective on the fused sequence (reference scripts/check_generation.py:131-151, train.py:533-547) ---------
+    @torch.no_grad()
+    def lm_forward(self, vision, input_ids, attention_mask, labels, keep=True):
+        """Token cross-entropy of LlamaForCausalLM.forward(inputs_embeds=[image tokens | text], labels=[-100 ... | labels]) (HF:487-491):
+        position t predicts token t + 1, image positions and -100 labels are ignored, mean over the labelled positions.  Only the
+        labelled rows go through lm_head (row chunks, fp32 logits, tcavp_ce_loss does loss + d(logits) in one kernel); the hidden-state
+        gradient is formed right away, so the [rows, vocab] logits never outlive a chunk.  Returns {"loss", "n_tokens", "_ctx"}."""
+        dev = self.dev
+        if dev.type != "cuda":
+            raise ops._lib.TcavpError("the model must be on a CUDA device (there is no CPU fallback): model.to('cuda')")
+        self._begin_pass()
+        self.sync_params()
+        vision = vision.to(dev)
+        if vision.dtype not in (torch.float32, torch.bfloat16):
+            vision = vision.float()
+        ids = input_ids.to(device=dev, dtype=torch.int64).contiguous()
+        am = attention_mask.to(device=dev, dtype=torch.int64).contiguous()
+        lab = labels.to(device=dev, dtype=torch.int64)
+        B, Lt = ids.shape
+        Q, H = self.qf["Q"], self.llm["H"]
+        L = Q + Lt
+        fused = self._new(B, L, H)
+        mask = torch.empty(B, L, dtype=torch.int32, device=dev)
+        c_qf = self._qformer_fwd(vision.contiguous(), fused, L)
+        ops.embed_text(ids, am, self.llm["embed"], self.text_mod, fused, mask, B=B, L_text=Lt, n_img=Q, H=H)
+        fh, c_llm = self._llm_fwd(fused, mask, B, L)
+        # target of fused position t = fused_labels[t + 1]; fused_labels = [-100] * Q ++ labels
+        tgt = torch.full((B, L), -100, dtype=torch.int64, device=dev)
+        tgt[:, Q - 1:L - 1] = lab
+        idx = (tgt.view(-1) != -100).nonzero().squeeze(1)                  # labelled rows (one host sync: their number sizes the chunks)
+        R = int(idx.numel())
+        loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
+        dh = None
+        if R:
+            hc = fh.view(B * L, H).index_select(0, idx)
+            t = tgt.view(-1).index_select(0, idx)
+            lm = self.lm_head()                                             # [V, H], tied to the embedding table when the checkpoint ties them
+            V = lm.shape[0]
+            V8 = (V + 7) // 8 * 8                                           # contraction length of the gradient GEMM (16-byte rows)
+            if keep:
+                if self.llm.get("lm_headT") is None:                        # [H, V8]: d(hidden) = d(logits) . W through the same GEMM
+                    wt = torch.zeros(H, V8, dtype=lm.dtype, device=dev)
+                    wt[:, :V] = lm.t()
+                    self.llm["lm_headT"] = wt
+                dh = self._new(R, H)
+            chunk = max(1, min(R, (256 << 20) // (V * 4)))                  # <= 256 MB of fp32 logits at a time
+            for r0 in range(0, R, chunk):
+                rc = min(chunk, R - r0)
+                logits = ops.gemm(hc[r0:r0 + rc], lm, self._new(rc, V, dtype=torch.float32))
+                g = (self._new(rc, V8) if V8 == V else torch.zeros(rc, V8, dtype=self.act, device=dev)) if keep else None
+                ops.ce_loss(logits, t[r0:r0 + rc], loss_sum, g, scale=1.0 / R)
+                if keep:
+                    ops.gemm(g, self.llm["lm_headT"], dh[r0:r0 + rc])
+        out = {"loss": (loss_sum / max(R, 1)).squeeze(0), "n_tokens": R}
+        if keep:
+            out["_ctx"] = (c_qf, c_llm, dh, idx, B, L, Q, H, Lt, self.drop)
+        return out
+
+    @torch.no_grad()
+    def lm_backward(self, gloss, ctx):
+        """Backward of lm_forward: d(loss)/d(final hidden) scattered to its rows, then the decoder-stack / text-modality / Q-Former backward
+        of the fine-tune step.  Returns {reference parameter name: fp32 gradient} (mllm.* only: nothing else is on this path)."""
+        c_qf, c_llm, dh, idx, B, L, Q, H, Lt, self.drop = ctx
+        self.G = {}
+        if not self.need_llm_bwd:
+            return {}
+        dfh = torch.zeros(B * L, H, dtype=self.act, device=self.dev)
+        if dh is not None:
+            if gloss is not None:
+                dh = dh * gloss.detach().to(device=self.dev, dtype=dh.dtype).reshape(1)
+            dfh.index_copy_(0, idx, dh)
+        dfused = self._llm_bwd(dfh, c_llm)
+        if self.tr_text:
+            dtxt = ops.copy_rows(dfused, self._new(B * Lt, H), rows=B * Lt, cols=H, in_remap=(Lt, L, Q))
+            ops.period_sum(dtxt, self._g("mllm.text_modality_embedding", (1, 1, H)), rows=B * Lt, cols=H)
+        if self.tr_qf:
+            self._qformer_bwd(dfused, c_qf, L)
+        return {k: v for k, v in self.G.items() if not k.startswith("_")}
+
     def _unpack_grads(self):
         """Packed-layout gradients -> reference state_dict layout (inverse of the pack-time permutations)."""
         G, C, T, To = self.G, self.C, self.T_in, self.T_out
