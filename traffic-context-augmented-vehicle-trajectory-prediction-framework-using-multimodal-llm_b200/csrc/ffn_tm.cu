@@ -249,6 +249,17 @@ ffn64_ln_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant
           int sn = s + 1;
           uint32_t usen = use;
           if (sn == g.stages) { sn = 0; ++usen; }
+          // the next chunk's score products go out as soon as the epilogue warps have READ this chunk's scores (not once they have
+          // finished with them): S(c + 1) runs on the pipe under the bias / ReLU / pack work of chunk c, so a block's epilogues run
+          // back to back instead of waiting a product latency per chunk
+          if (c + 1 < g.nch) {
+            mbar_wait(bars + BAR_WFULL + 8 * sn, usen & 1u);
+            for (int k = 0; k < 2; ++k) {
+              mbar_wait(bars + BAR_BLK + k * BK_BYTES + BK_SFREE, q & 1u);
+              tc_fence_after();
+              issue_s(k, sx, smem_base + sn * STAGE_BYTES);
+            }
+          }
           for (int k = 0; k < 2; ++k) {
             const uint32_t bb = bars + BAR_BLK + k * BK_BYTES;
             mbar_wait(bb + BK_PREADY, q & 1u);
@@ -260,15 +271,6 @@ ffn64_ln_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant
                       desc_kmajor(st + W1_BYTES + (uint32_t)(kk >> 2) * (W2_BYTES / 2) + (uint32_t)(kk & 3) * 32u), id_o, (c | kk) != 0);
             umma_commit(bb + BK_PFREE);
             if (c == g.nch - 1) umma_commit(bb + BK_OFULL);
-            if (c + 1 < g.nch) {
-              if (k == 0) {
-                mbar_wait(bars + BAR_WFULL + 8 * sn, usen & 1u);
-                tc_fence_after();
-              }
-              mbar_wait(bb + BK_SFREE, q & 1u);
-              tc_fence_after();
-              issue_s(k, sx, smem_base + sn * STAGE_BYTES);
-            }
           }
           umma_commit(bars + BAR_WEMPTY + 8 * s);      // every MMA reading this stage (S of this chunk, O of this chunk) has been issued
           s = sn; use = usen;
@@ -288,14 +290,14 @@ ffn64_ln_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant
       for (int c = 0; c < g.nch; ++c, ++q) {
         mbar_wait(bb + BK_SFULL, q & 1u);
         tc_fence_after();
-        if (q > 0) {                    // the product that read the previous chunk's activations has retired (it was issued before this
-          mbar_wait(bb + BK_PFREE, (q - 1) & 1u);      // chunk's score MMAs, so this never blocks in practice)
-          tc_fence_after();
-        }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t pk[32];
           relu_pack64(tS + h * 64, s_b1 + c * NC + h * 64, pk, h == 1, bb + BK_SFREE, lane);
+          if (h == 0 && q > 0) {        // the product that read the previous chunk's activations must have retired before they are overwritten
+            mbar_wait(bb + BK_PFREE, (q - 1) & 1u);
+            tc_fence_after();
+          }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const uint32_t w[8] = {pk[i * 8], pk[i * 8 + 1], pk[i * 8 + 2], pk[i * 8 + 3], pk[i * 8 + 4], pk[i * 8 + 5], pk[i * 8 + 6], pk[i * 8 + 7]};
