@@ -51,7 +51,7 @@ int tcavp_clock_probe(unsigned long long* out2, unsigned long long ns, tcavp_str
 
 /* Routing threshold of the two CTA-pair tcgen05 GEMM kernels: contractions with K >= the value run the 512 x 256 "wide" tile, shorter
  * ones the double-buffered 256 x 256 tile; 0 disables the wide kernel.  Returns the previous value; a negative argument only queries.
- * (Which kernel wins at K >= 2048 depends on the board's power limit; the Python front end times both once per process.) */
+ * (Which kernel wins at K >= 2048 differs from board to board; the Python front end times both once per process.) */
 int tcavp_gemm_wide_min_k(int new_value);
 /* Host-only test aid (no device work): the tile order of the persistent tcgen05 GEMM kernels.  For unit = 0 .. tiles_m*tiles_n-1 writes the
  * row-block index to mg[unit] and the n-tile index to nt[unit]; `panel_w` n-tiles per L2-resident W panel (>= tiles_n: row-major order).

@@ -1470,7 +1470,7 @@ static int launch_tc_wide(const tcavp_gemm_args& a, const EpilogueParams& ep, cu
 
 // TCAVP_GEMM_WIDE_K: contractions at least this long use the 512 x 256 pair tile (0 disables it).  Without the variable the value is
 // tunable at run time (tcavp_gemm_wide_min_k): which of the two kernels wins on K >= 2048 differs from one B200 to the next (measured:
-// wide +6-15 % on 1 kW boards, pair +6-12 % on a 700 W board — profiles/wide_vs_pair_r02y.txt), so ops.py times both once per process.
+// wide +6-15 % on some boards, pair +6-12 % on others of the same pool — profiles/wide_vs_pair_r02y.txt), so ops.py times both once per process.
 static int g_wide_k = -2;      // -2: not initialised
 static int wide_min_k() {
   if (g_wide_k == -2) {

@@ -157,7 +157,7 @@ def _need_cuda(*ts):
 
 # Long contractions (K >= 2048: down_proj, every 7B-class projection, the dX GEMMs of the fine-tune step) have two tcgen05 kernels: the
 # 512 x 256 "wide" CTA-pair tile and the double-buffered 256 x 256 pair tile.  Which one wins is a property of the board, not of the shape:
-# wide is 6-15 % ahead on B200s running at the 1 kW cap, the pair tile 6-12 % ahead on a 700 W-capped one (profiles/wide_vs_pair_r02y.txt).
+# wide is 6-15 % ahead on some B200s, the pair tile 6-12 % ahead on others of the same pool and power cap (profiles/wide_vs_pair_r02y.txt).
 # So the first long-K GEMM of a process times both for ~0.1 s each on this GPU and keeps the faster (TCAVP_GEMM_WIDE_K pins it instead).
 _ROUTE = {"wide_k": None, "tuned": None}
 
