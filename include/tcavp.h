@@ -33,7 +33,8 @@ typedef void* tcavp_stream_t; /* cudaStream_t */
 
 enum { TCAVP_F32 = 0, TCAVP_BF16 = 1 };
 enum { TCAVP_OK = 0, TCAVP_ERR_ARG = -1, TCAVP_ERR_CUDA = -2, TCAVP_ERR_UNSUPPORTED = -3 };
-enum { TCAVP_ACT_NONE = 0, TCAVP_ACT_RELU = 1, TCAVP_ACT_SWIGLU = 2, TCAVP_ACT_SWIGLU_BWD = 3 };
+enum { TCAVP_ACT_NONE = 0, TCAVP_ACT_RELU = 1, TCAVP_ACT_SWIGLU = 2, TCAVP_ACT_SWIGLU_BWD = 3,
+       TCAVP_ACT_GELU_TANH = 4 /* HF "gelu_new" (GPT-2 mlp.c_fc): 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))) */ };
 
 /* ---- library ------------------------------------------------------------------------------- */
 const char* tcavp_last_error(void);

@@ -91,12 +91,15 @@ __device__ __forceinline__ int remap_row(int gi, int go, int off, int m) {
 }
 
 __device__ __forceinline__ float silu_f(float g) { return g / (1.f + __expf(-g)); }
+// HF ACT2FN["gelu_new"] (GPT-2): tanh form of GELU
+__device__ __forceinline__ float gelu_tanh_f(float x) { return 0.5f * x * (1.f + tanhf(0.7978845608028654f * (x + 0.044715f * x * x * x))); }
 
 // Scalar epilogue (SIMT kernel and the ragged edges of the tensor-core kernel).
 __device__ __forceinline__ void epilogue_store(const EpilogueParams& p, int m, int mo, int n, float v) {
   if (m >= p.M || n >= p.N) return;
   if (p.bias) v += __ldg(p.bias + n);
   if (p.act == TCAVP_ACT_RELU) v = fmaxf(v, 0.f);
+  else if (p.act == TCAVP_ACT_GELU_TANH) v = gelu_tanh_f(v);
   if (p.residual) v += load_as_f(p.residual, (size_t)mo * p.ldr + n, p.res_dtype);
   store_from_f(p.out, (size_t)mo * p.ldo + n, p.out_dtype, v);
 }

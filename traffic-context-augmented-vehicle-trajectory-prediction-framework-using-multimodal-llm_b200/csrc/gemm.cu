@@ -289,6 +289,9 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueParams& p, int m, i
   if (p.act == TCAVP_ACT_RELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.f);
+  } else if (p.act == TCAVP_ACT_GELU_TANH) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[j] = gelu_tanh_f(o[j]);
   }
   if (p.residual) {
     if ((flags & EPI_VEC_RES) && full) {
@@ -1591,6 +1594,9 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A,
         if (ep.act == TCAVP_ACT_RELU) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+        } else if (ep.act == TCAVP_ACT_GELU_TANH) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] = gelu_tanh_f(v[e]);
         }
         if (ep.residual) {
           if (ep.res_dtype == TCAVP_F32) {
@@ -1628,7 +1634,7 @@ static void launch_simt(const tcavp_gemm_args& a, const EpilogueParams& ep, cuda
     const size_t esz = dtype == TCAVP_BF16 ? 2 : 4;
     return p == nullptr || (reinterpret_cast<uintptr_t>(p) % (4 * esz) == 0 && ((size_t)ld * esz) % (4 * esz) == 0);
   };
-  const int vec4 = (ep.act == TCAVP_ACT_NONE || ep.act == TCAVP_ACT_RELU) && ep.rope_cols == 0 && al(ep.out, ep.ldo, ep.out_dtype) &&
+  const int vec4 = (ep.act == TCAVP_ACT_NONE || ep.act == TCAVP_ACT_RELU || ep.act == TCAVP_ACT_GELU_TANH) && ep.rope_cols == 0 && al(ep.out, ep.ldo, ep.out_dtype) &&
                    al(ep.residual, ep.ldr, ep.res_dtype) && (ep.bias == nullptr || reinterpret_cast<uintptr_t>(ep.bias) % 16 == 0);
   gemm_simt_kernel<T, BM, BN><<<grid, 256, 0, stream>>>(reinterpret_cast<const T*>(a.A), a.lda, reinterpret_cast<const T*>(a.W), a.ldw, ep, a.M,
                                                         a.N, a.K, vec4);
@@ -1656,7 +1662,8 @@ extern "C" int tcavp_gemm(const tcavp_gemm_args* a, tcavp_stream_t stream_) {
   if (a->M == 0) return TCAVP_OK;
   TCAVP_REQUIRE(a->A && a->W && a->out, "tcavp_gemm: null A/W/out");
   TCAVP_REQUIRE(a->lda >= a->K && a->ldw >= a->K, "tcavp_gemm: lda/ldw smaller than K");
-  TCAVP_REQUIRE(a->act == TCAVP_ACT_NONE || a->act == TCAVP_ACT_RELU || a->act == TCAVP_ACT_SWIGLU || a->act == TCAVP_ACT_SWIGLU_BWD,
+  TCAVP_REQUIRE(a->act == TCAVP_ACT_NONE || a->act == TCAVP_ACT_RELU || a->act == TCAVP_ACT_SWIGLU || a->act == TCAVP_ACT_SWIGLU_BWD ||
+                    a->act == TCAVP_ACT_GELU_TANH,
                 "tcavp_gemm: bad act %d", a->act);
   if (a->act == TCAVP_ACT_SWIGLU_BWD) {
     TCAVP_REQUIRE(a->in_dtype == TCAVP_BF16 && a->out_dtype == TCAVP_BF16 && a->aux_out && !a->bias && !a->residual && !a->rope_cos_sin &&

@@ -11,7 +11,7 @@ import torch
 from . import lib as _lib
 
 F32, BF16 = 0, 1
-ACT_NONE, ACT_RELU, ACT_SWIGLU, ACT_SWIGLU_BWD = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_SWIGLU, ACT_SWIGLU_BWD, ACT_GELU_TANH = 0, 1, 2, 3, 4
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 
 
