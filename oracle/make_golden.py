@@ -40,6 +40,12 @@ FIXTURES = {
     # default) — cut to two layers and an 8192-entry vocabulary so the fixture stays small and fast
     "llama32_1b_l2_b8": ("cfg1", {"base_model_name": dict(T.LLAMA_PRESETS["llama-3.2-1b"], num_hidden_layers=2, vocab_size=8192)},
                          8, 128, 31, 37, None, "scripts/train.py"),
+    # GPT-2 architecture through the same AutoModelForCausalLM call (HF GPT2LMHeadModel; peft's default LoRA target c_attn, a Conv1D):
+    # the tiny shape with a full state_dict, and gpt2-small's geometry (768 / 12 heads / 3072, LayerNorm, wpe, gelu_new) cut to two
+    # layers and an 8192-entry vocabulary
+    "gpt2_tiny_b6": ("tiny", {"base_model_name": "gpt2-tiny"}, 6, 24, 41, 43, [0, 64, 1, 33, 14, 22], "scripts/train.py"),
+    "gpt2_l2_b8": ("cfg1", {"base_model_name": dict(T.LLAMA_PRESETS["gpt2"], num_hidden_layers=2, vocab_size=8192)},
+                   8, 128, 47, 53, None, "scripts/train.py"),
 }
 
 

@@ -52,6 +52,26 @@ class LoraLinear(nn.Module):
         return y + self.lora_B["default"](self.lora_A["default"](self.lora_dropout["default"](x))) * self.scaling
 
 
+class LoraConv1D(nn.Module):
+    """peft lora.Linear around transformers' Conv1D (peft sets fan_in_fan_out=True for GPT-2's c_attn): the base layer keeps its
+    [in, out] weight and bias, the adapters are ordinary bias-free Linears —  y = base(x) + lora_B(lora_A(dropout(x))) * alpha / r."""
+
+    def __init__(self, base, r: int, alpha: float, dropout: float):
+        super().__init__()
+        nx, nf = base.weight.shape
+        self.base_layer = base
+        self.lora_dropout = nn.ModuleDict({"default": nn.Dropout(dropout) if dropout > 0 else nn.Identity()})
+        self.lora_A = nn.ModuleDict({"default": nn.Linear(nx, r, bias=False)})
+        self.lora_B = nn.ModuleDict({"default": nn.Linear(r, nf, bias=False)})
+        nn.init.kaiming_uniform_(self.lora_A["default"].weight, a=math.sqrt(5))
+        nn.init.zeros_(self.lora_B["default"].weight)
+        self.scaling = alpha / r
+
+    def forward(self, x):
+        y = self.base_layer(x)
+        return y + self.lora_B["default"](self.lora_A["default"](self.lora_dropout["default"](x))) * self.scaling
+
+
 class _LoraModel(nn.Module):
     def __init__(self, model):
         super().__init__()
@@ -68,6 +88,8 @@ class PeftModelForCausalLM(nn.Module):
             for name, child in list(parent.named_children()):
                 if name in targets and isinstance(child, nn.Linear):
                     setattr(parent, name, LoraLinear(child, cfg.r, cfg.lora_alpha, cfg.lora_dropout))
+                elif name in targets and type(child).__name__ == "Conv1D":
+                    setattr(parent, name, LoraConv1D(child, cfg.r, cfg.lora_alpha, cfg.lora_dropout))
         self.base_model = _LoraModel(model)
         self.config = model.config
         self.peft_config = {"default": cfg}

@@ -76,7 +76,14 @@ def load_reference(script: str = "scripts/train.py", llama_cfg: dict = None):
     cfg_holder = {"cfg": llama_cfg}
 
     def _from_pretrained(cls, name, **kw):
-        return LlamaForCausalLM(hf_llama_config(cfg_holder["cfg"]))
+        c = cfg_holder["cfg"]
+        if c.get("arch") == "gpt2":          # what AutoModelForCausalLM resolves a model_type "gpt2" checkpoint to
+            from transformers import GPT2Config, GPT2LMHeadModel
+            return GPT2LMHeadModel(GPT2Config(vocab_size=c["vocab_size"], n_positions=c["n_positions"], n_embd=c["hidden_size"],
+                                              n_layer=c["num_hidden_layers"], n_head=c["num_attention_heads"], n_inner=c["intermediate_size"],
+                                              activation_function="gelu_new", layer_norm_epsilon=c.get("layer_norm_epsilon", 1e-5),
+                                              resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0))
+        return LlamaForCausalLM(hf_llama_config(c))
 
     transformers.AutoModelForCausalLM.from_pretrained = classmethod(_from_pretrained)
     transformers.AutoTokenizer.from_pretrained = classmethod(lambda cls, name, **kw: _Tok())

@@ -162,11 +162,13 @@ def qformer(sd, vision, nheads=8, p="mllm.qformer."):
 
 
 def find_llm_prefix(sd):
-    """Returns (prefix up to and including 'model.' of LlamaModel, has_base_layer_keys)."""
+    """Prefix up to and including 'model.' of LlamaModel (or 'transformer.' of GPT2Model)."""
     for k in sd:
         if k.endswith("model.embed_tokens.weight"):
             return k[: -len("embed_tokens.weight")]
-    raise KeyError("no embed_tokens in state_dict")
+        if k.endswith("transformer.wte.weight"):
+            return k[: -len("wte.weight")]
+    raise KeyError("no embed_tokens / wte in state_dict")
 
 
 def _lora_linear(sd, p, x, scaling, site=None):
@@ -247,6 +249,41 @@ def llama_stack(sd, llama_cfg, embeds, attn_mask, lora_scaling, p=None):
     return rms_norm(x, sd[p + "norm.weight"], eps)
 
 
+def _conv1d(sd, p, x, scaling):
+    """transformers Conv1D (y = x W + b, W [in, out]) with an optional peft LoRA pair around it (fan_in_fan_out: the adapters are plain
+    Linears): base_layer.{weight, bias} + lora_B(lora_A(x)) alpha / r."""
+    if p + "base_layer.weight" in sd:
+        y = x @ sd[p + "base_layer.weight"] + sd[p + "base_layer.bias"]
+        return y + (x @ sd[p + "lora_A.default.weight"].t()) @ sd[p + "lora_B.default.weight"].t() * scaling
+    return x @ sd[p + "weight"] + sd[p + "bias"]
+
+
+def gpt2_stack(sd, cfg, embeds, attn_mask, lora_scaling, p=None):
+    """HF GPT2Model over inputs_embeds (modeling_gpt2.py: GPT2Model.forward / GPT2Block / GPT2Attention / GPT2MLP): + wpe[0..L), pre-norm
+    blocks with LayerNorm (bias), fused c_attn -> (q, k, v), causal + key-padding mask, scores / sqrt(dh), gelu_new MLP, ln_f.
+    Returns hidden_states[-1] (after ln_f)."""
+    p = p or find_llm_prefix(sd)
+    B, L, H = embeds.shape
+    nh = cfg["num_attention_heads"]
+    dh = H // nh
+    eps = cfg.get("layer_norm_epsilon", 1e-5)
+    allowed = torch.tril(torch.ones(L, L, dtype=torch.bool))[None] & attn_mask.bool()[:, None, :]
+    x = embeds + sd[p + "wpe.weight"][:L]
+    for i in range(cfg["num_hidden_layers"]):
+        bp = f"{p}h.{i}."
+        h = layer_norm(x, sd[bp + "ln_1.weight"], sd[bp + "ln_1.bias"], eps)
+        q, k, v = _conv1d(sd, bp + "attn.c_attn.", h, lora_scaling).split(H, dim=-1)
+        q, k, v = (t.view(B, L, nh, dh).transpose(1, 2) for t in (q, k, v))
+        s = (q @ k.transpose(-1, -2)) * (dh ** -0.5)
+        s = s.masked_fill(~allowed[:, None], float("-inf"))
+        a = (torch.softmax(s.float(), dim=-1).to(q.dtype) @ v).transpose(1, 2).reshape(B, L, H)
+        x = x + _conv1d(sd, bp + "attn.c_proj.", a, lora_scaling)
+        h = layer_norm(x, sd[bp + "ln_2.weight"], sd[bp + "ln_2.bias"], eps)
+        h = F.gelu(_conv1d(sd, bp + "mlp.c_fc.", h, lora_scaling), approximate="tanh")      # ACT2FN["gelu_new"]
+        x = x + _conv1d(sd, bp + "mlp.c_proj.", h, lora_scaling)
+    return layer_norm(x, sd[p + "ln_f.weight"], sd[p + "ln_f.bias"], eps)
+
+
 # --------------------------------------------------------------------------------------------------
 # reference scripts/train.py:504-554  LlamaMultiModal.forward (ids branch)
 # --------------------------------------------------------------------------------------------------
@@ -258,11 +295,12 @@ def mllm_forward(sd, cfg, llama_cfg, vision, input_ids, attention_mask, p="mllm.
         img = linear(img, sd[p + "q_proj.weight"], sd[p + "q_proj.bias"])
     img = img + sd[p + "vision_modality_embedding"]
     lp = find_llm_prefix(sd)
-    txt = sd[lp + "embed_tokens.weight"][input_ids] + sd[p + "text_modality_embedding"]
+    gpt2 = llama_cfg.get("arch") == "gpt2"
+    txt = sd[lp + ("wte.weight" if gpt2 else "embed_tokens.weight")][input_ids] + sd[p + "text_modality_embedding"]
     fused = torch.cat([img, txt], dim=1)
     mask = torch.cat([torch.ones(img.shape[:2], dtype=attention_mask.dtype), attention_mask], dim=1)
     scaling = cfg.get("lora_alpha", 32) / cfg.get("lora_r", 8)
-    return llama_stack(sd, llama_cfg, fused, mask, scaling, lp), img
+    return (gpt2_stack if gpt2 else llama_stack)(sd, llama_cfg, fused, mask, scaling, lp), img
 
 
 # --------------------------------------------------------------------------------------------------

@@ -17,7 +17,7 @@ def _forward(fix, dtype, keep=True):
     return m, {k: (v.float().cpu() if torch.is_tensor(v) else v) for k, v in out.items()}
 
 
-FIXTURES = ["tiny_b6", "cfg1_b8", "cfg5_b32", "cfg3l2_b16", "gqa_l2_b32", "llama32_1b_l2_b8"]
+FIXTURES = ["tiny_b6", "cfg1_b8", "cfg5_b32", "cfg3l2_b16", "gqa_l2_b32", "llama32_1b_l2_b8", "gpt2_tiny_b6", "gpt2_l2_b8"]
 
 
 def _expected_image_rows(m, g):
@@ -82,7 +82,8 @@ def _check_bf16(m, o, g):
     assert r_img < BF16_IMG_REL_L2, ("image tokens", r_img)
     n = g["final_hidden_head"].shape[0]
     r_fh = _rel_l2(o["final_hidden"][:n], g["final_hidden_head"])
-    n_layers = len(m.mllm.llama_wrapper.causal_lm().model.layers)
+    lm = m.mllm.llama_wrapper.causal_lm()
+    n_layers = len(lm.transformer.h if hasattr(lm, "transformer") else lm.model.layers)       # GPT-2 / Llama key layouts
     assert r_fh < bf16_rel_l2_band(n_layers), ("final_hidden relative L2", r_fh, n_layers)
     fh = o["final_hidden"]
     absmean = g["final_hidden_absmean"]

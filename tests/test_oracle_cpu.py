@@ -19,7 +19,7 @@ def _run(fix):
                             i["input_ids"], i["attention_mask"], i["y"], i["norm_stat"])
 
 
-@pytest.mark.parametrize("name", ["tiny_b6", "cfg1_b8", "cfg5_b32", "cfg3l2_b16", "gqa_l2_b32", "llama32_1b_l2_b8"])
+@pytest.mark.parametrize("name", ["tiny_b6", "cfg1_b8", "cfg5_b32", "cfg3l2_b16", "gqa_l2_b32", "llama32_1b_l2_b8", "gpt2_tiny_b6", "gpt2_l2_b8"])
 def test_restatement_matches_reference_golden(name):
     fix = load_golden(name)
     o, g = _run(fix), fix["out"]

@@ -31,7 +31,7 @@ if __name__ == "__main__":
     if "--child" in sys.argv:
         child([a for a in sys.argv[1:] if a != "--child"])
         sys.exit(0)
-    names = sys.argv[1:] or ["tiny_b6", "cfg1_b8", "cfg3l2_b16", "gqa_l2_b32", "llama32_1b_l2_b8", "cfg5_b32"]
+    names = sys.argv[1:] or ["tiny_b6", "cfg1_b8", "cfg3l2_b16", "gqa_l2_b32", "llama32_1b_l2_b8", "cfg5_b32", "gpt2_tiny_b6", "gpt2_l2_b8"]
     for label, env in COMBOS:
         print(f"[{label}]", flush=True)
         e = dict(os.environ); e.update(env)

@@ -24,6 +24,13 @@ LLAMA_PRESETS = {
                          rope_theta=500000.0, max_position_embeddings=131072, tie_word_embeddings=True,
                          rope_scaling=dict(rope_type="llama3", factor=32.0, low_freq_factor=1.0, high_freq_factor=4.0,
                                            original_max_position_embeddings=8192)),
+    # GPT-2 architecture (HF GPT2LMHeadModel through the same AutoModelForCausalLM call, reference scripts/train.py:427-431; peft's default
+    # LoRA target for model_type "gpt2" is the fused c_attn projection): LayerNorm with bias, learned position embeddings, Conv1D
+    # projections ([in, out] weights) with biases, gelu_new MLP, tied lm_head.  Values of the public gpt2 (small) config.json.
+    "gpt2": dict(arch="gpt2", vocab_size=50257, hidden_size=768, intermediate_size=3072, num_hidden_layers=12, num_attention_heads=12,
+                 n_positions=1024, layer_norm_epsilon=1e-5, tie_word_embeddings=True),
+    "gpt2-tiny": dict(arch="gpt2", vocab_size=97, hidden_size=128, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
+                      n_positions=64, layer_norm_epsilon=1e-5, tie_word_embeddings=True),
     # tiny shape for golden fixtures that carry their full state_dict
     "llama-tiny": dict(vocab_size=97, hidden_size=128, intermediate_size=256, num_hidden_layers=2,
                        num_attention_heads=4, num_key_value_heads=2, head_dim=32, rms_norm_eps=1e-6,
@@ -34,6 +41,7 @@ _ALIASES = {
     "huggyllama/llama-7b": "llama-7b",
     "meta-llama/Llama-3.2-1B": "llama-3.2-1b", "meta-llama/Llama-3.2-1B-Instruct": "llama-3.2-1b",
     "gpt2-small-class": "llama-768",
+    "openai-community/gpt2": "gpt2", "gpt2-small": "gpt2",
 }
 
 

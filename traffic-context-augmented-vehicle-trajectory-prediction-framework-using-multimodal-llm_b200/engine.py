@@ -111,9 +111,81 @@ class Engine:
         self.qf["vis_mod"] = vis
         self.text_mod = _f32(mllm.text_modality_embedding.reshape(-1), self.dev)
 
+    def _pack_gpt2(self, mllm):
+        """HF GPT2LMHeadModel (what AutoModelForCausalLM gives the reference for a GPT-2 checkpoint, scripts/train.py:427-431) with peft's
+        default LoRA target c_attn.  Conv1D weights are [in, out]: packed transposed to the [N, K] operand layout of tcavp_gemm; the
+        LoRA pair rides as extra K columns of the fused QKV weight ([ln_1(x) | ln_1(x) A^T] . [W^T | (alpha / r) B]^T), as in the Llama path."""
+        wrap = mllm.llama_wrapper
+        c = wrap.config
+        lm = wrap.causal_lm()
+        tr = lm.transformer
+        self._lm_head_param, self._embed_param = lm.lm_head.weight, tr.wte.weight
+        act, dev = self.act, self.dev
+        H, nh, I = c["hidden_size"], c["num_attention_heads"], c["intermediate_size"]
+        merge = bool(wrap.use_lora and getattr(self, "merge_lora", False))
+        r = self.model_hp["lora_r"] if (wrap.use_lora and not merge) else 0
+        kx = ((r + 7) // 8) * 8
+        self.llm = dict(arch="gpt2", H=H, nh=nh, nkv=nh, dh=H // nh, I=I, eps=c.get("layer_norm_epsilon", 1e-5), kx=kx, n_lora=r, r=r,
+                        vocab=c["vocab_size"], targets=("c_attn",) if r else (), layers=[], fuse_rope=False,
+                        embed=tr.wte.weight.detach().to(dev, act).contiguous(), wpe=tr.wpe.weight.detach().to(dev, act).contiguous(),
+                        norm=self._ln(tr.ln_f))
+        for blk in tr.h:
+            ca = blk.attn.c_attn
+            wqkv = torch.zeros(3 * H, H + kx, dtype=act, device=dev)
+            a_cat = None
+            if wrap.use_lora:
+                base_w, base_b = ca.base_layer.weight.detach().to(dev).float(), ca.base_layer.bias
+                A, Bm = ca.lora_A["default"].weight.detach().to(dev).float(), ca.lora_B["default"].weight.detach().to(dev).float()
+                if merge:
+                    wqkv[:, :H] = (base_w.t() + ca.scaling * (Bm @ A)).to(act)
+                else:
+                    wqkv[:, :H] = base_w.t().to(act)
+                    wqkv[:, H:H + r] = (Bm * ca.scaling).to(act)
+                    a_cat = torch.zeros(kx, H, dtype=act, device=dev)
+                    a_cat[:r] = A.to(act)
+            else:
+                base_b = ca.bias
+                wqkv[:, :H] = ca.weight.detach().to(dev).t().to(act)
+            lin = lambda cv: _Lin(cv.weight.detach().t(), cv.bias, act, dev)          # noqa: E731  Conv1D -> [N, K]
+            self.llm["layers"].append(dict(wqkv=wqkv, bqkv=_f32(base_b, dev), a_cat=a_cat, ln1=self._ln(blk.ln_1), ln2=self._ln(blk.ln_2),
+                                           proj=lin(blk.attn.c_proj), fc=lin(blk.mlp.c_fc), mproj=lin(blk.mlp.c_proj)))
+
+    def _gpt2_forward(self, fused, mask, B, L):
+        """HF GPT2Model over inputs_embeds: + wpe[0 .. L), pre-norm blocks (LayerNorm -> fused c_attn (+ LoRA) -> causal attention with the
+        key-padding mask -> c_proj + residual; LayerNorm -> c_fc + gelu_new -> c_proj + residual), ln_f.  Every projection is a
+        tcavp_gemm with its bias / activation / residual in the epilogue; the attention is the tcgen05 kernel of the Llama path (no RoPE)."""
+        m = self.llm
+        H, nh, dh, I, kx = m["H"], m["nh"], m["dh"], m["I"], m["kx"]
+        M, Kx = B * L, H + kx
+        if L > m["wpe"].shape[0]:
+            raise ops._lib.TcavpError(f"sequence length {L} exceeds the backbone's n_positions {m['wpe'].shape[0]}")
+        pos = ops.cast(m["wpe"], self._new(M, H), rows=M, cols=H, in_row_mod=L)          # position ids 0 .. L-1 in every scene
+        x = ops.axpby(fused.view(M, H), self._new(M, H), rows=M, cols=H, b=pos)
+        xs = torch.zeros(M, Kx, dtype=self.act, device=self.dev) if kx != m["n_lora"] else self._new(M, Kx)
+        h = self._new(M, H)
+        qkv, attn, mid = self._new(M, 3 * H), self._new(M, H), self._new(M, I)
+        for ly in m["layers"]:
+            ops.layernorm(x, ly["ln1"][0], ly["ln1"][1], h, eps=ly["ln1"][2])
+            if kx:
+                ops.cast(h, xs, rows=M, cols=H, ldi=H, ldo=Kx)
+                ops.gemm(xs, ly["a_cat"], xs[:, H:], M=M, N=m["n_lora"], K=H, lda=Kx, ldo=Kx)
+                ops.gemm(xs, ly["wqkv"], qkv, M=M, N=3 * H, K=Kx, lda=Kx, bias=ly["bqkv"])
+            else:
+                ops.gemm(h, ly["wqkv"], qkv, bias=ly["bqkv"])
+            ops.attention(qkv, qkv[:, H:], qkv[:, 2 * H:], attn, B=B, H=nh, Hkv=nh, Tq=L, Tk=L, dh=dh, q_strides=(L * 3 * H, 3 * H),
+                          k_strides=(L * 3 * H, 3 * H), v_strides=(L * 3 * H, 3 * H), o_strides=(L * H, H), scale=dh ** -0.5, causal=True,
+                          key_mask=mask)
+            ops.gemm(attn, ly["proj"].w, x, bias=ly["proj"].b, residual=x)
+            ops.layernorm(x, ly["ln2"][0], ly["ln2"][1], h, eps=ly["ln2"][2])
+            ops.gemm(h, ly["fc"].w, mid, bias=ly["fc"].b, act=ops.ACT_GELU_TANH)
+            ops.gemm(mid, ly["mproj"].w, x, bias=ly["mproj"].b, residual=x)
+        return ops.layernorm(x, m["norm"][0], m["norm"][1], self._new(M, H), eps=m["norm"][2])
+
     def _pack_llm(self, mllm):
         wrap = mllm.llama_wrapper
         c = wrap.config
+        if c.get("arch") == "gpt2":
+            return self._pack_gpt2(mllm)
         lm = wrap.causal_lm()
         self._lm_head_param, self._embed_param = lm.lm_head.weight, lm.model.embed_tokens.weight
         act, dev = self.act, self.dev
@@ -335,6 +407,8 @@ class Engine:
         """HF:375-427 LlamaModel over inputs_embeds with LoRA on q/k/v (in place on `fused`); returns the
         post-final-norm hidden states (= hidden_states[-1], reference scripts/train.py:553)."""
         m = self.llm
+        if m.get("arch") == "gpt2":
+            return self._gpt2_forward(fused, mask, B, L)
         H, nh, nkv, dh, I, kx = m["H"], m["nh"], m["nkv"], m["dh"], m["I"], m["kx"]
         M = B * L
         key = (L, dh, 1 if m["fuse_rope"] else 0)

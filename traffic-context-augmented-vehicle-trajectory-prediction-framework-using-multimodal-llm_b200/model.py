@@ -179,6 +179,84 @@ class LlamaForCausalLMW(nn.Module):
         return self.model.embed_tokens
 
 
+class _Conv1DW(nn.Module):
+    """transformers.pytorch_utils.Conv1D key layout: weight [in, out] (transposed w.r.t. nn.Linear), bias [out]."""
+
+    def __init__(self, nx, nf, **kw):
+        super().__init__()
+        self.in_features, self.out_features = nx, nf
+        self.weight = nn.Parameter(torch.empty(nx, nf, **kw).normal_(0.0, 0.02))
+        self.bias = nn.Parameter(torch.zeros(nf, **kw))
+
+
+class _GPT2AttnW(nn.Module):
+    def __init__(self, H, **kw):
+        super().__init__()
+        self.c_attn = _Conv1DW(H, 3 * H, **kw)
+        self.c_proj = _Conv1DW(H, H, **kw)
+
+
+class _GPT2MLPW(nn.Module):
+    def __init__(self, H, I, **kw):
+        super().__init__()
+        self.c_fc = _Conv1DW(H, I, **kw)
+        self.c_proj = _Conv1DW(I, H, **kw)
+
+
+class _GPT2BlockW(nn.Module):
+    def __init__(self, c, **kw):
+        super().__init__()
+        H, eps = c["hidden_size"], c.get("layer_norm_epsilon", 1e-5)
+        self.ln_1 = nn.LayerNorm(H, eps=eps, **kw)
+        self.attn = _GPT2AttnW(H, **kw)
+        self.ln_2 = nn.LayerNorm(H, eps=eps, **kw)
+        self.mlp = _GPT2MLPW(H, c["intermediate_size"], **kw)
+
+
+class _GPT2ModelW(nn.Module):
+    def __init__(self, c, **kw):
+        super().__init__()
+        H = c["hidden_size"]
+        self.wte = nn.Embedding(c["vocab_size"], H, **kw)
+        self.wpe = nn.Embedding(c["n_positions"], H, **kw)
+        self.h = nn.ModuleList([_GPT2BlockW(c, **kw) for _ in range(c["num_hidden_layers"])])
+        self.ln_f = nn.LayerNorm(H, eps=c.get("layer_norm_epsilon", 1e-5), **kw)
+
+
+class GPT2LMHeadModelW(nn.Module):
+    """Key layout of HF GPT2LMHeadModel: transformer.{wte, wpe, h.N.{ln_1, attn.c_attn, attn.c_proj, ln_2, mlp.c_fc, mlp.c_proj}, ln_f} +
+    lm_head.weight (tied to wte).  What `AutoModelForCausalLM.from_pretrained("gpt2")` gives the reference (scripts/train.py:427-431)."""
+
+    def __init__(self, c, **kw):
+        super().__init__()
+        self.config = dict(c)
+        self.transformer = _GPT2ModelW(c, **kw)
+        self.lm_head = nn.Linear(c["hidden_size"], c["vocab_size"], bias=False, **kw)
+        with torch.no_grad():
+            self.transformer.wte.weight.normal_(0.0, 0.02)
+            self.transformer.wpe.weight.normal_(0.0, 0.02)
+        if c.get("tie_word_embeddings", True):
+            self.lm_head.weight = self.transformer.wte.weight
+
+    def get_input_embeddings(self):
+        return self.transformer.wte
+
+
+class LoraConv1DW(nn.Module):
+    """peft lora.Linear around a Conv1D (fan_in_fan_out=True, what peft sets for GPT-2's c_attn): base_layer.{weight [in, out], bias},
+    lora_A.default.weight [r, in], lora_B.default.weight [out, r];  y = x W + b + (x A^T) B^T alpha / r."""
+
+    def __init__(self, base, r, alpha, dropout):
+        super().__init__()
+        kw = dict(device=base.weight.device, dtype=torch.float32)
+        self.base_layer = base
+        self.lora_A = nn.ModuleDict({"default": nn.Linear(base.in_features, r, bias=False, **kw)})
+        self.lora_B = nn.ModuleDict({"default": nn.Linear(r, base.out_features, bias=False, **kw)})
+        nn.init.kaiming_uniform_(self.lora_A["default"].weight, a=math.sqrt(5))
+        nn.init.zeros_(self.lora_B["default"].weight)
+        self.r, self.lora_alpha, self.scaling, self.lora_dropout_p = r, alpha, alpha / r, dropout
+
+
 class LoraLinearW(nn.Module):
     """peft >= 0.7 lora.Linear key layout: base_layer.weight, lora_A.default.weight, lora_B.default.weight."""
 
@@ -207,13 +285,18 @@ class PeftModelW(nn.Module):
 
     def __init__(self, model, r, alpha, dropout, target_modules=None):
         super().__init__()
-        self.targets = tuple(target_modules or self.TARGETS)
-        bad = [t for t in self.targets if t not in ("q_proj", "k_proj", "v_proj")]
+        gpt2 = isinstance(model, GPT2LMHeadModelW)
+        self.targets = tuple(target_modules or (("c_attn",) if gpt2 else self.TARGETS))       # peft's default mapping per model_type
+        ok = ("c_attn",) if gpt2 else ("q_proj", "k_proj", "v_proj")
+        bad = [t for t in self.targets if t not in ok]
         if bad:
-            raise NotImplementedError(f"LoRA targets {bad} are not supported (q_proj/k_proj/v_proj only)")
+            raise NotImplementedError(f"LoRA targets {bad} are not supported ({'/'.join(ok)} only)")
         for p in model.parameters():
             p.requires_grad_(False)
-        for layer in model.model.layers:
+        if gpt2:
+            for blk in model.transformer.h:
+                blk.attn.c_attn = LoraConv1DW(blk.attn.c_attn, r, alpha, dropout)
+        for layer in ([] if gpt2 else model.model.layers):
             for t in self.targets:
                 setattr(layer.self_attn, t, LoraLinearW(getattr(layer.self_attn, t), r, alpha, dropout))
         self.base_model = _LoraModelW(model)
@@ -231,7 +314,8 @@ class LlamaWithCrossAttnPEFT(nn.Module):
         cfg = resolve_llama(base_model_name)
         cfg.setdefault("num_key_value_heads", cfg["num_attention_heads"])
         cfg.setdefault("head_dim", cfg["hidden_size"] // cfg["num_attention_heads"])
-        self.llama_model = LlamaForCausalLMW(cfg, **kw)
+        # AutoModelForCausalLM resolves the class from the checkpoint's model_type: Llama by default, GPT-2 for arch = "gpt2"
+        self.llama_model = GPT2LMHeadModelW(cfg, **kw) if cfg.get("arch") == "gpt2" else LlamaForCausalLMW(cfg, **kw)
         self.use_lora = use_lora
         if use_lora:
             self.llama_model = PeftModelW(self.llama_model, lora_r, lora_alpha, lora_dropout)

@@ -64,6 +64,9 @@ class TrainEngine(Engine):
     SPLIT_SMALL = False      # the fine-tune step keeps the fp32 layers in exact FFMA (their weights are re-packed every step)
 
     def __init__(self, model, compute_dtype="bf16"):
+        if model.mllm.llama_wrapper.config.get("arch") == "gpt2":
+            raise NotImplementedError("GPT-2-arch backbones are inference-only here: the hand-written backward (fine-tune step, stage-1 "
+                                      "objective) covers the Llama architecture")
         super().__init__(model, compute_dtype)
         self.model = model
         self.G = {}
