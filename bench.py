@@ -46,6 +46,8 @@ UNIT = "scenes/s"
 WORKLOADS = {
     # name: (model preset, scenes per GPU per step, L_text)
     "cfg2": ("cfg1", 1024, 128),
+    # the same workload on the GPT-2 architecture (gpt2-small: 768 / 12 layers / 12 heads / 3072, vocabulary 50257; not a default secondary)
+    "cfg2-gpt2": ("cfg1-gpt2", 1024, 128),
     "cfg3": ("cfg3", 256, 128),
     # BASELINE.json configs[4]: encoder + fusion with a frozen backbone (final_hidden supplied, bf16), T_out 50, 4096 scenes
     "cfg5": ("cfg5", 4096, 128),
@@ -169,7 +171,11 @@ def scenes_for(cfg, B, l_text, seed, vocab):
 def gemm_flops_per_scene(cfg, lc, L):
     """Algorithmic FLOPs of the dense contractions per scene, LoRA included, lm_head excluded."""
     H, I, nl = lc["hidden_size"], lc["intermediate_size"], lc["num_hidden_layers"]
-    nh, nkv, dh = lc["num_attention_heads"], lc["num_key_value_heads"], lc["head_dim"]
+    nh = lc["num_attention_heads"]
+    nkv, dh = lc.get("num_key_value_heads", nh), lc.get("head_dim", H // nh)
+    if lc.get("arch") == "gpt2":         # c_attn (3H), c_proj, c_fc + mlp.c_proj (two H x I products, no gate), LoRA on c_attn
+        r = cfg.get("lora_r", 8) if cfg.get("use_lora", True) else 0
+        return L * nl * (2 * H * 3 * H + 2 * H * H + 2 * 2 * H * I + 2 * r * (H + 3 * H))
     per_tok = nl * (2 * H * (nh + 2 * nkv) * dh + 2 * nh * dh * H + 3 * 2 * H * I)
     r = cfg.get("lora_r", 8) if cfg.get("use_lora", True) else 0
     lora = nl * 2 * r * ((H + nh * dh) + (H + nkv * dh))

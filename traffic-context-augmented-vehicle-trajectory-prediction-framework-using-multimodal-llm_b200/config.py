@@ -87,6 +87,9 @@ def resolve_llama(name_or_cfg):
 MODEL_PRESETS = {
     "cfg1": dict(seq_len=15, out_len=25, individual=True, d_model=64, base_model_name="llama-768", use_lora=True,
                  lora_r=8, lora_alpha=32, ltsf_nhead=2),
+    # the same model on the GPT-2 architecture itself (HF gpt2-small: LayerNorm, wpe, Conv1D projections, gelu_new, c_attn LoRA)
+    "cfg1-gpt2": dict(seq_len=15, out_len=25, individual=True, d_model=64, base_model_name="gpt2", use_lora=True,
+                      lora_r=8, lora_alpha=32, ltsf_nhead=2),
     "cfg3": dict(seq_len=15, out_len=25, individual=True, d_model=64, base_model_name="llama-7b", use_lora=True,
                  lora_r=16, lora_alpha=32, ltsf_nhead=2),
     "cfg5": dict(seq_len=15, out_len=50, individual=True, d_model=64, base_model_name="llama-768", use_lora=False,

@@ -290,8 +290,14 @@ __device__ __forceinline__ void epilogue_chunk(const EpilogueParams& p, int m, i
 #pragma unroll
     for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.f);
   } else if (p.act == TCAVP_ACT_GELU_TANH) {
+    // bf16 outputs: the hardware tanh (MUFU.TANH, relative error ~2^-11) is below the output rounding; the fp32 SIMT path keeps tanhf
 #pragma unroll
-    for (int j = 0; j < 32; ++j) o[j] = gelu_tanh_f(o[j]);
+    for (int j = 0; j < 32; ++j) {
+      const float x = o[j];
+      float t;
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.7978845608028654f * fmaf(0.044715f * x * x, x, x)));
+      o[j] = 0.5f * x * (1.f + t);
+    }
   }
   if (p.residual) {
     if ((flags & EPI_VEC_RES) && full) {
