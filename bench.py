@@ -527,6 +527,71 @@ def measure_train(ctx, workload, steps, warmup, scenes=0, dropout=None):
     return out
 
 
+def measure_stage1(ctx, steps, warmup, scenes=0):
+    """Stage-1 (CausalLM) training step of the reference's scripts/check_generation.py loop at the 768-class shape: model.stage1_forward(...)
+    -> outputs.loss.backward() -> AdamW on the mllm.* tensors.  Metric: tokens/sec through the model (scenes x (16 image + L_text));
+    the labelled half of every sequence (64 answer tokens per scene) goes through lm_head (vocabulary 32000) in row chunks."""
+    import warnings
+
+    import tcavp_b200 as T
+    from tcavp_b200 import ops
+    rank, world, dev = ctx.rank, ctx.world, ctx.dev
+    preset, B, l_text = TRAIN_WORKLOADS["cfg2"]
+    if scenes:
+        B = scenes
+    model, cfg = build_model(preset, dev)
+    model.eval()          # the stage-1 script trains in train() mode; dropout is measured by --mode train — this line isolates the objective
+    lc = T.resolve_llama(cfg["base_model_name"])
+    s = scenes_for(cfg, B, l_text, 4321 + rank, lc["vocab_size"])
+    ids, am, vis = s["input_ids"].to(dev), s["attention_mask"].to(dev), s["vision"].to(dev)
+    labels = ids.clone()
+    labels[:, :l_text // 2] = -100
+    labels[am == 0] = -100
+    n_lab = int((labels != -100).sum())
+    warnings.simplefilter("ignore")
+    params = [p for n, p in model.named_parameters() if p.requires_grad and n.startswith("mllm.")]
+    opt = torch.optim.AdamW(params, lr=1e-4, fused=True)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        out = model.stage1_forward(vis, ids, am, labels)
+        out.loss.backward()
+        if world > 1:
+            for p in params:
+                if p.grad is not None:
+                    ctx.dist.all_reduce(p.grad)
+        opt.step()
+        return out.loss.detach()
+    losses = [float(step()) for _ in range(max(warmup, 3))]
+    ctx.barrier()
+    sampler = ClockSampler(ctx.local) if rank == 0 else None
+    n0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    ctx.barrier()
+    launches = ops.launch_count() - n0
+    clocks = sampler.stop() if sampler else None
+    ms = ctx.max_over_ranks(e0.elapsed_time(e1))
+    losses.append(float(loss))
+    prof = ops.LaunchProfiler()
+    with prof:
+        step()
+    torch.cuda.synchronize()
+    Lseq = 16 + l_text
+    roof, _ = _roofline(prof, peaks(), ms / steps, 1, {"breakdown": "one extra step after the timed region, CUDA events around every launch"})
+    return {"metric": "stage-1 (CausalLM) training tokens/sec (forward + loss + backward + AdamW)", "value": round(world * B * Lseq * steps / (ms / 1e3), 1),
+            "unit": "tokens/s", "n_gpus": world, "steps": steps, "warmup": max(warmup, 3), "ms_per_step": round(ms / steps, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"stage1-cfg2: {cfg['base_model_name']} backbone, LoRA r={cfg.get('lora_r', 8)}, bf16 compute / fp32 masters, {B} scenes/GPU/step, "
+                                   f"L = 16 image + {l_text} text tokens, {n_lab} labelled tokens/GPU/step through lm_head (vocabulary {lc['vocab_size']})",
+                       "scenes_per_gpu": B, "seq_len": Lseq, "labelled_tokens_per_gpu": n_lab, "loss_first_last": [round(losses[0], 3), round(losses[-1], 3)],
+                       "peak_mem_gib": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2), "gemm_route": ops._ROUTE["tuned"]},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof}
+
+
 def _brief(d):
     """Secondary workloads ride inside the headline line: keep the judged fields, trim the per-kernel table."""
     r = dict(d["roofline"])
@@ -673,7 +738,8 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="infer", choices=["infer", "train"], help="train: the LoRA fine-tune step (secondary metric)")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train", "stage1"],
+                    help="train: the LoRA fine-tune step (secondary metric); stage1: the CausalLM training step of scripts/check_generation.py")
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--scenes", type=int, default=0, help="override scenes per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=64, help="scenes per CPU forward (BASELINE.json configs[0]: 64)")
@@ -690,5 +756,11 @@ if __name__ == "__main__":
         run_reference(a)
     elif a.mode == "train":
         run_train(a)
+    elif a.mode == "stage1":
+        _ctx = _Ctx(a)
+        _out = measure_stage1(_ctx, a.steps, a.warmup, scenes=a.scenes)
+        if _ctx.rank == 0:
+            emit(_out)
+        _ctx.close()
     else:
         run_ours(a)
