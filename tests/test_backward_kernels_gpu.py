@@ -44,6 +44,17 @@ def test_transpose(ops, dtype, batch, rows, cols):
     assert torch.count_nonzero(out[:, :, rows:]) == 0
 
 
+@pytest.mark.parametrize("batch,rows,cols", [(1, 70, 34), (1, 1000, 64), (2, 144, 1536), (3, 65, 130), (1, 7, 2)])
+def test_transpose_bf16_tiles(ops, batch, rows, cols):
+    """bf16 -> bf16 (the 64 x 64-tile kernel with two-element accesses): exact, ragged tiles, odd row counts, padded output rows untouched."""
+    x = _rand(batch, rows, cols, seed=2).bfloat16()
+    ldo = (rows + 7) // 8 * 8
+    out = torch.full((batch, cols, ldo), 5.0, dtype=torch.bfloat16, device=DEV)
+    ops.transpose(x.to(DEV), out, rows=rows, cols=cols, ldo=ldo, batch=batch, in_bstride=rows * cols, out_bstride=cols * ldo)
+    assert torch.equal(out.cpu()[:, :, :rows], x.transpose(1, 2))
+    assert bool((out[:, :, rows:] == 5.0).all())
+
+
 @pytest.mark.parametrize("period", [1, 7, 16])
 def test_period_sum(ops, period):
     rows, cols = period * 37, 200

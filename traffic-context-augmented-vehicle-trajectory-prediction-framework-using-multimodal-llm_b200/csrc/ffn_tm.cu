@@ -11,6 +11,9 @@
 //               O + b2 + x -> LayerNorm over the 64 features (in the thread) -> bf16 -> one 128-byte row store
 //   warps 8-11  block B
 // TMEM: S_A | S_B (128 fp32 columns each) | P_A | P_B (64 columns of packed bf16) | O_A | O_B (64) = 512 columns.
+// What bounds it: every fp32 score is read out of TMEM once (tcgen05.ld: ~64 B / clk / SM) — 256 rows x F x 4 B = 2 MB per CTA step,
+// 32 K cycles, against 16 K cycles of MMA work; measured 177 us per launch at 262 144 rows = 1.5 x that floor.  Sixteen epilogue warps
+// (two per lane quarter and block) were tried and are no faster (192 us): the reads, not the per-warp chain, are the limit.
 #include <cuda.h>
 #include <stdlib.h>
 #include <mutex>
