@@ -626,10 +626,13 @@ def run_ours(args):
     if args.workload == "cfg2" and not args.no_secondary and not args.scenes and not args.merge_lora:
         sec = {}
         k2 = max(args.secondary_steps, 5)
-        for name, fn in (("cfg3", lambda: measure_infer(ctx, "cfg3", k2, 3, e2e=True)[0]),
+        extra = [("cfg2_gpt2", lambda: measure_infer(ctx, "cfg2-gpt2", k2, 3, e2e=True)[0])]      # the headline workload on the GPT-2 architecture
+        if ctx.world == 1:
+            extra.append(("stage1_cfg2", lambda: measure_stage1(ctx, k2, 3)))                    # CausalLM training step (single-GPU line)
+        for name, fn in [("cfg3", lambda: measure_infer(ctx, "cfg3", k2, 3, e2e=True)[0]),
                          ("cfg5", lambda: measure_infer(ctx, "cfg5", max(k2, 10), 3, e2e=True)[0]),
                          ("train_cfg2", lambda: measure_train(ctx, "cfg2", k2, 3)),
-                         ("train_cfg4", lambda: measure_train(ctx, "cfg3", k2, 3))):
+                         ("train_cfg4", lambda: measure_train(ctx, "cfg3", k2, 3))] + extra:
             try:
                 sec[name] = _brief(fn())
             except Exception as e:     # a secondary workload must never take the headline line down with it

@@ -13,6 +13,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 CONFIGS = [  # (label, env)
     ("pair (default routing)", {"TCAVP_GEMM_WIDE_K": "2048"}),
     ("pair kernel for every shape", {"TCAVP_GEMM_WIDE_K": "0"}),
+    ("tmastore off, pair kernel for every shape", {"TCAVP_GEMM_WIDE_K": "0", "TCAVP_GEMM_TMASTORE": "0"}),
     ("wide k-major", {"TCAVP_GEMM_WIDE_K": "512", "TCAVP_GEMM_WIDE_SPLIT": "1"}),
     ("wide split 2", {"TCAVP_GEMM_WIDE_K": "512", "TCAVP_GEMM_WIDE_SPLIT": "2"}),
     ("wide split 3", {"TCAVP_GEMM_WIDE_K": "512", "TCAVP_GEMM_WIDE_SPLIT": "3"}),
