@@ -261,6 +261,13 @@ int tcavp_axpby(const void* a, int lda, int a_dtype, float alpha, const void* b,
 /* SwiGLU on interleaved (gate, up) columns (HF:190) and its backward; gu / dgu are [rows, 2I], out / dout [rows, I]. */
 int tcavp_swiglu(const void* gu, void* out, int dtype, long long rows, int I, tcavp_stream_t stream);
 int tcavp_swiglu_bwd(const void* dout, const void* gu, void* dgu, int dtype, long long rows, int I, tcavp_stream_t stream);
+/* HF ACT2FN["gelu_new"] (GPT-2 mlp.act: 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))) on [rows, cols] as a pass of its own, and its
+ * backward on the stored pre-activation x: dx = dy * d gelu_new(x) / dx.  The fine-tune step of a GPT-2-arch backbone (HF
+ * modeling_gpt2.py GPT2MLP.forward, reached through reference scripts/train.py:445-453) keeps c_fc's output for the backward pass;
+ * inference applies the activation in the tcavp_gemm epilogue (TCAVP_ACT_GELU_TANH). */
+int tcavp_gelu_tanh(const void* x, int ldx, void* out, int ldo, int dtype, long long rows, int cols, tcavp_stream_t stream);
+int tcavp_gelu_tanh_bwd(const void* dy, int lddy, const void* x, int ldx, void* dx, int lddx, int dtype, long long rows, int cols,
+                        tcavp_stream_t stream);
 /* Backward of tcavp_layernorm (input x + residual): dx (optional), dw += sum_r dy*xhat, db += sum_r dy (optional pair). */
 int tcavp_layernorm_bwd(const void* dy, int dy_dtype, const void* x, const void* residual, int x_dtype, const float* w, int rows,
                         int cols, float eps, void* dx, int dx_dtype, float* dw, float* db, tcavp_stream_t stream);

@@ -23,7 +23,7 @@ import numpy as np
 import torch
 
 MOD = dict(poly=1, qenc=2, qdec=3, llm=4, ltsf=5, dec=6)
-KIND = dict(sa_attn=0, drop1=1, ffn=2, drop2=3, ca_attn=4, drop3=5, post=6, cross_attn=7, lora_q=8, lora_k=9, lora_v=10)
+KIND = dict(sa_attn=0, drop1=1, ffn=2, drop2=3, ca_attn=4, drop3=5, post=6, cross_attn=7, lora_q=8, lora_k=9, lora_v=10, lora_c=11)
 _M32 = np.uint64(0xFFFFFFFF)
 
 
@@ -90,11 +90,11 @@ def default_probs(model_cfg, transformer_p=0.1):
         pr[("ltsf", kind)] = tp
     pr[("dec", "post")] = pr[("dec", "cross_attn")] = tp
     if model_cfg.get("use_lora", True):
-        pr[("llm", "lora_q")] = pr[("llm", "lora_v")] = lp
+        pr[("llm", "lora_q")] = pr[("llm", "lora_v")] = pr[("llm", "lora_c")] = lp      # lora_c: the c_attn target of a GPT-2-arch backbone
     return pr
 
 
-def reference_call_sequence(model_cfg, n_llm_layers, lora_targets=("q_proj", "v_proj")):
+def reference_call_sequence(model_cfg, n_llm_layers, lora_targets=("q_proj", "v_proj"), arch="llama"):
     """[(module, layer, kind, layout)] in the order the reference's forward reaches its dropout calls (train mode):
     lane_polygon_encoder -> mllm (Q-Former encoder, decoder, LoRA-Llama) -> ltsf (attention block, decoder) — train.py:926-939.
     layout: "flat" = the tensor's own row-major order is the canonical one; "tbe" = (T, B, E) tensors of the batch_first=False
@@ -111,6 +111,9 @@ def reference_call_sequence(model_cfg, n_llm_layers, lora_targets=("q_proj", "v_
                     ("qdec", l, "ffn", "flat"), ("qdec", l, "drop3", "flat")])
     if model_cfg.get("use_lora", True):
         for l in range(n_llm_layers):                         # HF LlamaAttention.forward: q_proj, k_proj, v_proj in this order
+            if arch == "gpt2":                                # HF GPT2Attention.forward: one fused c_attn (peft's default target)
+                seq.append(("llm", l, "lora_c", "flat"))
+                continue
             for t in ("q_proj", "k_proj", "v_proj"):
                 if t in lora_targets:
                     seq.append(("llm", l, "lora_" + t[0], "flat"))

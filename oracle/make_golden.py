@@ -124,6 +124,9 @@ GRAD_FIXTURES = {
     # 7B-class geometry (H 4096, 32 heads of 128, I 11008, LoRA r 16), two decoder layers: the backward through W^T at K = 11008 / 22016
     # (the wide GEMM) and the 67 M-parameter cross-attention of the fusion block
     "cfg3l2_b4_grads": ("cfg3", 4, 128, [33, 14, 22, 32], {"base_model_name": FIXTURES["cfg3l2_b16"][1]["base_model_name"]}),
+    # GPT-2 architecture (HF GPT2LMHeadModel, peft LoRA on the fused c_attn Conv1D): the tiny shape and gpt2-small's geometry cut to two layers
+    "gpt2_tiny_b5_grads": ("tiny", 5, 24, [64, 1, 33, 14, 22], {"base_model_name": "gpt2-tiny"}),
+    "gpt2_l2_b3_grads": ("cfg1", 3, 128, [33, 14, 22], {"base_model_name": FIXTURES["gpt2_l2_b8"][1]["base_model_name"]}),
 }
 
 
@@ -131,6 +134,7 @@ GRAD_FIXTURES = {
 DROP_FIXTURES = {
     "tiny_b5_grads_drop": ("tiny_b5_grads", 20261, 3),
     "cfg1_b3_grads_drop": ("cfg1_b3_grads", 77001, 11),
+    "gpt2_tiny_b5_grads_drop": ("gpt2_tiny_b5_grads", 31337, 5),
 }
 
 
@@ -171,7 +175,7 @@ def make_grads(name="tiny_b5_grads"):
     def patched():
         if drop is None:
             return contextlib.nullcontext()
-        return OD.patch_reference_dropout(OD.DropOracle(drop[0], drop[1], {}), OD.reference_call_sequence(mc, n_llm))
+        return OD.patch_reference_dropout(OD.DropOracle(drop[0], drop[1], {}), OD.reference_call_sequence(mc, n_llm, arch=lc.get("arch", "llama")))
     if drop is not None:
         model.train()
     with torch.no_grad(), patched():
@@ -206,6 +210,7 @@ def make_grads(name="tiny_b5_grads"):
 STAGE1_FIXTURES = {
     "tiny_b5_stage1": ("tiny", 5, 24, 9),
     "cfg1_b2_stage1": ("cfg1", 2, 128, 70),       # the 768-class geometry, vocabulary 32000
+    "gpt2_tiny_b5_stage1": ("tiny", 5, 24, 9, {"base_model_name": "gpt2-tiny"}),      # HF GPT2LMHeadModel (tied lm_head) under the same call
 }
 
 
@@ -215,8 +220,9 @@ def make_stage1(name="tiny_b5_stage1"):
     the peft-wrapped HF LlamaForCausalLM with labels -> outputs.loss, autograd gradients of every trainable mllm tensor.  float64 run,
     eval mode (dropout off), like the other gradient fixtures."""
     from oracle import restated
-    preset, B, l_text, prompt_len = STAGE1_FIXTURES[name]
+    preset, B, l_text, prompt_len, *over = STAGE1_FIXTURES[name]
     mc = dict(T.MODEL_PRESETS[preset])
+    mc.update(over[0] if over else {})
     lc = T.resolve_llama(mc["base_model_name"])
     mod = ref_loader.load_reference("scripts/train.py", lc)
     model = ref_loader.build_reference_model(mod, mc, lc)

@@ -249,12 +249,13 @@ def llama_stack(sd, llama_cfg, embeds, attn_mask, lora_scaling, p=None):
     return rms_norm(x, sd[p + "norm.weight"], eps)
 
 
-def _conv1d(sd, p, x, scaling):
+def _conv1d(sd, p, x, scaling, site=None):
     """transformers Conv1D (y = x W + b, W [in, out]) with an optional peft LoRA pair around it (fan_in_fan_out: the adapters are plain
-    Linears): base_layer.{weight, bias} + lora_B(lora_A(x)) alpha / r."""
+    Linears): base_layer.{weight, bias} + lora_B(lora_A(dropout(x))) alpha / r (dropout in train mode only)."""
     if p + "base_layer.weight" in sd:
         y = x @ sd[p + "base_layer.weight"] + sd[p + "base_layer.bias"]
-        return y + (x @ sd[p + "lora_A.default.weight"].t()) @ sd[p + "lora_B.default.weight"].t() * scaling
+        xd = x if site is None else _D(x, *site)
+        return y + (xd @ sd[p + "lora_A.default.weight"].t()) @ sd[p + "lora_B.default.weight"].t() * scaling
     return x @ sd[p + "weight"] + sd[p + "bias"]
 
 
@@ -272,7 +273,7 @@ def gpt2_stack(sd, cfg, embeds, attn_mask, lora_scaling, p=None):
     for i in range(cfg["num_hidden_layers"]):
         bp = f"{p}h.{i}."
         h = layer_norm(x, sd[bp + "ln_1.weight"], sd[bp + "ln_1.bias"], eps)
-        q, k, v = _conv1d(sd, bp + "attn.c_attn.", h, lora_scaling).split(H, dim=-1)
+        q, k, v = _conv1d(sd, bp + "attn.c_attn.", h, lora_scaling, ("llm", i, "lora_c")).split(H, dim=-1)
         q, k, v = (t.view(B, L, nh, dh).transpose(1, 2) for t in (q, k, v))
         s = (q @ k.transpose(-1, -2)) * (dh ** -0.5)
         s = s.masked_fill(~allowed[:, None], float("-inf"))
@@ -452,7 +453,7 @@ def causal_lm_loss(sd, cfg, llama_cfg, vision, input_ids, attention_mask, labels
     logits upcast to fp32, position t scored against token t + 1, ignore_index -100, mean over the labelled positions)."""
     fh, img = mllm_forward(sd, cfg, llama_cfg, vision, input_ids, attention_mask)
     lp = find_llm_prefix(sd)
-    logits = linear(fh, sd[lp[: -len("model.")] + "lm_head.weight"]).float()
+    logits = linear(fh, sd[lp.rsplit(".", 2)[0] + ".lm_head.weight"]).float()       # "...model." (Llama) / "...transformer." (GPT-2) -> sibling lm_head
     B, Q = img.shape[:2]
     fused_labels = torch.cat([torch.full((B, Q), -100, dtype=labels.dtype), labels], dim=1)
     return torch.nn.functional.cross_entropy(logits[:, :-1].reshape(-1, logits.shape[-1]), fused_labels[:, 1:].reshape(-1), ignore_index=-100)

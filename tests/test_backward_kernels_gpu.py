@@ -89,6 +89,28 @@ def test_relu_bwd_axpby_swiglu(ops, dtype):
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("rows,cols,ld", [(129, 72, 72), (300, 3072, 3072), (33, 40, 48), (17, 37, 37)])
+def test_gelu_new_forward_and_backward(ops, dtype, rows, cols, ld):
+    """HF ACT2FN["gelu_new"] as its own pass + backward on the stored pre-activation (GPT-2 fine-tune step), vector and scalar paths,
+    padded rows — against torch's tanh GELU and autograd through it."""
+    td = _td(dtype)
+    x = (2.5 * _rand(rows, cols, seed=12)).to(td).float().requires_grad_(True)
+    want = torch.nn.functional.gelu(x, approximate="tanh")
+    dy = _rand(rows, cols, seed=13).to(td)
+    want.backward(dy.float())
+    xd = torch.zeros(rows, ld, dtype=td, device=DEV)
+    xd[:, :cols] = x.detach().to(td).to(DEV)
+    out = torch.full((rows, ld), 7.0, dtype=td, device=DEV)
+    ops.gelu_tanh(xd, out, rows=rows, cols=cols, ldx=ld, ldo=ld)
+    torch.testing.assert_close(out[:, :cols].cpu().float(), want.detach(), **_tol(dtype))
+    assert bool((out[:, cols:] == 7.0).all())
+    dyd = torch.zeros(rows, ld, dtype=td, device=DEV)
+    dyd[:, :cols] = dy.to(DEV)
+    ops.gelu_tanh_bwd(dyd, xd, dyd, rows=rows, cols=cols, lddy=ld, ldx=ld, lddx=ld)          # in place on the gradient, as the step uses it
+    torch.testing.assert_close(dyd[:, :cols].cpu().float(), x.grad, **_tol(dtype))
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 @pytest.mark.parametrize("rows,cols,with_res", [(37, 64, True), (300, 768, False), (5, 40, True)])
 def test_layernorm_bwd(ops, dtype, rows, cols, with_res):
     td = _td(dtype)

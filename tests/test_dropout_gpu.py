@@ -150,7 +150,7 @@ def _drop_oracle(fix):
     return OD.DropOracle(fix["dropout"]["seed"], fix["dropout"]["step"], OD.default_probs(fix["model_cfg"]))
 
 
-@pytest.mark.parametrize("name", ["tiny_b5_grads_drop", "cfg1_b3_grads_drop"])
+@pytest.mark.parametrize("name", ["tiny_b5_grads_drop", "cfg1_b3_grads_drop", "gpt2_tiny_b5_grads_drop"])
 def test_fp32_train_mode_gradients_match_reference(lib_built, name):
     """The whole fine-tune step in train() mode (p = 0.1 at every site of the reference) against the golden of the unmodified reference
     run with the same masks: loss, decoded, and the gradient of every trainable tensor."""

@@ -66,7 +66,7 @@ def _check_against_compressed(got, want, rtol, atol, key):
     torch.testing.assert_close(g2.double().sum(0).float(), want["colsum"], rtol=rtol, atol=atol + 1e-4 * scale, msg=lambda m: f"{key} colsum: {m}")
 
 
-@pytest.mark.parametrize("name", ["tiny_b5_grads", "cfg1_b3_grads", "cfg3l2_b4_grads"])
+@pytest.mark.parametrize("name", ["tiny_b5_grads", "cfg1_b3_grads", "cfg3l2_b4_grads", "gpt2_tiny_b5_grads", "gpt2_l2_b3_grads"])
 def test_restated_gradients_match_reference_autograd(name):
     """Pins the fine-tune oracle: autograd through oracle/restated.py == gradients of the unmodified reference model."""
     fix = load_golden(name)
@@ -84,7 +84,7 @@ def test_restated_gradients_match_reference_autograd(name):
         _check_against_compressed(grads[k], want, rtol=2e-3, atol=2e-4 * ref_scale + 1e-6, key=k)
 
 
-@pytest.mark.parametrize("name", ["tiny_b5_grads_drop", "cfg1_b3_grads_drop"])
+@pytest.mark.parametrize("name", ["tiny_b5_grads_drop", "cfg1_b3_grads_drop", "gpt2_tiny_b5_grads_drop"])
 def test_restated_train_mode_dropout_matches_reference(name):
     """Train mode: the restatement with oracle/dropout.py's masks at its dropout sites == the UNMODIFIED reference in train() mode with
     the same masks substituted for torch's RNG (fixture minted through patch_reference_dropout, which also checks that the reference
@@ -103,7 +103,7 @@ def test_restated_train_mode_dropout_matches_reference(name):
     torch.testing.assert_close(loss, fix["loss"], rtol=1e-5, atol=0)
     torch.testing.assert_close(decoded, fix["decoded"], rtol=1e-4, atol=1e-5)
     lc = fix["llama_cfg"]
-    assert len(orc.used) == len(OD.reference_call_sequence(fix["model_cfg"], lc["num_hidden_layers"]))
+    assert len(orc.used) == len(OD.reference_call_sequence(fix["model_cfg"], lc["num_hidden_layers"], arch=lc.get("arch", "llama")))
     for k, want in fix["grads"].items():
         ref_scale = float((want["full"] if "full" in want else want["head"]).abs().max()) + 1e-8
         _check_against_compressed(grads[k], want, rtol=2e-3, atol=2e-4 * ref_scale + 1e-6, key=k)
@@ -136,7 +136,7 @@ def test_dropout_mask_function_and_site_table():
         assert abs((x[:-lag] * x[lag:]).mean() / x.var()) < 5e-3, lag
 
 
-@pytest.mark.parametrize("name", ["tiny_b5_stage1", "cfg1_b2_stage1"])
+@pytest.mark.parametrize("name", ["tiny_b5_stage1", "cfg1_b2_stage1", "gpt2_tiny_b5_stage1"])
 def test_restated_stage1_objective_matches_reference(name):
     """Pins the stage-1 (CausalLM) oracle: restated.causal_lm_loss and its autograd gradients == `outputs.loss` of the unmodified reference
     classes around HF's LlamaForCausalLM (reference scripts/check_generation.py:131-151, train.py:533-547) and its gradients."""

@@ -25,7 +25,7 @@ def _oracle(fix):
     return restated.stage1_loss_and_grads(sd, fix["model_cfg"], fix["llama_cfg"], i["vision"], i["input_ids"], i["attention_mask"], i["labels"])
 
 
-@pytest.mark.parametrize("name", ["tiny_b5_stage1", "cfg1_b2_stage1"])
+@pytest.mark.parametrize("name", ["tiny_b5_stage1", "cfg1_b2_stage1", "gpt2_tiny_b5_stage1"])
 def test_fp32_stage1_loss_and_gradients_match_reference(lib_built, name):
     fix = load_golden(name)
     m = _model(fix, "fp32")
@@ -48,7 +48,7 @@ def test_fp32_stage1_loss_and_gradients_match_reference(lib_built, name):
     print("worst relative-to-max stage-1 gradient errors:", sorted(worst.items(), key=lambda kv: -kv[1])[:5])
 
 
-@pytest.mark.parametrize("name", ["tiny_b5_stage1", "cfg1_b2_stage1"])
+@pytest.mark.parametrize("name", ["tiny_b5_stage1", "cfg1_b2_stage1", "gpt2_tiny_b5_stage1"])
 def test_bf16_stage1_tracks_reference(lib_built, name):
     """bf16 compute (tcgen05 lm_head GEMMs in row chunks, fp32 logits, the fused loss / d(logits) kernel): loss within 2 %, gradient
     direction and size per tensor (cosine >= 0.98, norm within 10 %) for every tensor above the noise floor."""

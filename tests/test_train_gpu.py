@@ -59,7 +59,7 @@ def _oracle(fix):
                                    i["attention_mask"], i["y"], i["norm_stat"])
 
 
-@pytest.mark.parametrize("name", ["tiny_b5_grads", "cfg1_b3_grads", "cfg3l2_b4_grads"])
+@pytest.mark.parametrize("name", ["tiny_b5_grads", "cfg1_b3_grads", "cfg3l2_b4_grads", "gpt2_tiny_b5_grads", "gpt2_l2_b3_grads"])
 def test_fp32_gradients_match_reference(lib_built, name):
     fix = load_golden(name)
     m = _model(fix, "fp32")
@@ -116,7 +116,7 @@ def test_fp32_gradients_match_reference(lib_built, name):
         assert not failures, failures[:5]
 
 
-@pytest.mark.parametrize("name", ["tiny_b5_grads", "cfg1_b3_grads", "cfg3l2_b4_grads"])
+@pytest.mark.parametrize("name", ["tiny_b5_grads", "cfg1_b3_grads", "cfg3l2_b4_grads", "gpt2_tiny_b5_grads", "gpt2_l2_b3_grads"])
 def test_bf16_gradients_track_reference(lib_built, name):
     """bf16 storage: per-tensor direction and size of the gradient (cosine >= 0.98, norm within 10 %) for every tensor whose
     gradient is not itself at the noise floor."""

@@ -98,6 +98,54 @@ __global__ void relu_bwd_kernel(const void* __restrict__ dy, int lddy, const voi
   }
 }
 
+// HF ACT2FN["gelu_new"] (GPT-2 mlp.act) as a pass of its own, and its backward on the stored pre-activation (the fine-tune step of a
+// GPT-2-arch backbone keeps c_fc's output x; the inference path applies the activation in the GEMM epilogue instead).
+//   y = 0.5 x (1 + t),  t = tanh(c (x + a x^3));   dy/dx = 0.5 (1 + t) + 0.5 x (1 - t^2) c (1 + 3 a x^2)
+// bf16 tensors take the 16-byte path (8 elements per thread, hardware tanh: its 2^-11 relative error is below the output rounding);
+// fp32 tensors (the parity mode) use tanhf.
+template <bool BWD>
+__device__ __forceinline__ float gelu_new_eval(float x, float g, bool approx) {
+  const float u = 0.7978845608028654f * fmaf(0.044715f * x * x, x, x);
+  float t;
+  if (approx) asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  else t = tanhf(u);
+  if (!BWD) return 0.5f * x * (1.f + t);
+  return g * (0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * 0.7978845608028654f * fmaf(3.f * 0.044715f * x, x, 1.f));
+}
+template <bool BWD>
+__global__ void __launch_bounds__(256) gelu_new_kernel(const void* __restrict__ dy, int lddy, const void* __restrict__ x, int ldx,
+                                                       void* __restrict__ out, int ldo, int dtype, long long rows, int cols, int vec) {
+  if (vec) {      // bf16, cols / strides multiples of 8, 16-byte aligned bases
+    const int c8 = cols >> 3;
+    const long long total = rows * c8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const long long r = i / c8;
+      const int c = (int)(i % c8) << 3;
+      const uint4 xv = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(x) + (size_t)r * ldx + c);
+      uint4 gv = make_uint4(0, 0, 0, 0);
+      if (BWD) gv = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(dy) + (size_t)r * lddy + c);
+      const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float lo = gelu_new_eval<BWD>(__uint_as_float(xs[e] << 16), __uint_as_float(gs[e] << 16), true);
+        const float hi = gelu_new_eval<BWD>(__uint_as_float(xs[e] & 0xffff0000u), __uint_as_float(gs[e] & 0xffff0000u), true);
+        const __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
+        o[e] = *reinterpret_cast<const uint32_t*>(&pk);
+      }
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + (size_t)r * ldo + c) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    return;
+  }
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i % cols);
+    const float g = BWD ? load_as_f(dy, (size_t)r * lddy + c, dtype) : 0.f;
+    store_from_f(out, (size_t)r * ldo + c, dtype, gelu_new_eval<BWD>(load_as_f(x, (size_t)r * ldx + c, dtype), g, dtype == TCAVP_BF16));
+  }
+}
+
 __global__ void axpby_kernel(const void* __restrict__ a, int lda, int a_dtype, float alpha, const void* __restrict__ b, int ldb, int b_dtype,
                              float beta, void* __restrict__ out, int ldo, int out_dtype, long long rows, int cols) {
   const long long total = rows * cols;
@@ -774,6 +822,30 @@ extern "C" int tcavp_relu_bwd(const void* dy, int lddy, const void* y, int ldy, 
   TCAVP_REQUIRE(dy && y && dx && DT_OK(dtype), "tcavp_relu_bwd: bad pointer/dtype");
   relu_bwd_kernel<<<grid_cap((rows * cols + 255) / 256, 16), 256, 0, STREAM(stream)>>>(dy, lddy, y, ldy, dx, lddx, dtype, rows, cols);
   return check_launch("relu_bwd_kernel");
+}
+
+static int gelu_vec_ok(const void* a, int lda, const void* b, int ldb, const void* c, int ldc, int dtype, int cols) {
+  auto al = [](const void* p, int ld) { return !p || (reinterpret_cast<uintptr_t>(p) % 16 == 0 && ld % 8 == 0); };
+  return dtype == TCAVP_BF16 && cols % 8 == 0 && al(a, lda) && al(b, ldb) && al(c, ldc);
+}
+extern "C" int tcavp_gelu_tanh(const void* x, int ldx, void* out, int ldo, int dtype, long long rows, int cols, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(rows >= 0 && cols > 0 && ldx >= cols && ldo >= cols, "tcavp_gelu_tanh: bad shape");
+  if (rows == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(x && out && DT_OK(dtype), "tcavp_gelu_tanh: bad pointer/dtype");
+  const int vec = gelu_vec_ok(nullptr, 0, x, ldx, out, ldo, dtype, cols);
+  const long long work = vec ? rows * (cols / 8) : rows * cols;
+  gelu_new_kernel<false><<<grid_cap((work + 255) / 256, 16), 256, 0, STREAM(stream)>>>(nullptr, 0, x, ldx, out, ldo, dtype, rows, cols, vec);
+  return check_launch("gelu_new_kernel");
+}
+extern "C" int tcavp_gelu_tanh_bwd(const void* dy, int lddy, const void* x, int ldx, void* dx, int lddx, int dtype, long long rows, int cols,
+                                   tcavp_stream_t stream) {
+  TCAVP_REQUIRE(rows >= 0 && cols > 0 && lddy >= cols && ldx >= cols && lddx >= cols, "tcavp_gelu_tanh_bwd: bad shape");
+  if (rows == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(dy && x && dx && DT_OK(dtype), "tcavp_gelu_tanh_bwd: bad pointer/dtype");
+  const int vec = gelu_vec_ok(dy, lddy, x, ldx, dx, lddx, dtype, cols);
+  const long long work = vec ? rows * (cols / 8) : rows * cols;
+  gelu_new_kernel<true><<<grid_cap((work + 255) / 256, 16), 256, 0, STREAM(stream)>>>(dy, lddy, x, ldx, dx, lddx, dtype, rows, cols, vec);
+  return check_launch("gelu_new_bwd_kernel");
 }
 
 extern "C" int tcavp_axpby(const void* a, int lda, int a_dtype, float alpha, const void* b, int ldb, int b_dtype, float beta, void* out,

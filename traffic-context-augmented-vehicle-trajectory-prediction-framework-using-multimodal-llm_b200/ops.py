@@ -611,6 +611,25 @@ def swiglu_bwd(dout, gu, dgu, *, rows, I):
     return dgu
 
 
+def gelu_tanh(x, out, *, rows, cols, ldx=None, ldo=None):
+    """out = gelu_new(x) (HF ACT2FN["gelu_new"], GPT-2 mlp.act) as a pass of its own (the fine-tune step keeps the pre-activation)."""
+    _need_cuda(x, out)
+    if x.dtype != out.dtype:
+        raise TypeError("gelu_tanh: dtype mismatch")
+    _call("tcavp_gelu_tanh", "gelu_new_kernel", _p(x), cols if ldx is None else ldx, _p(out), cols if ldo is None else ldo, dt(x), _ll(rows), cols)
+    return out
+
+
+def gelu_tanh_bwd(dy, x, dx, *, rows, cols, lddy=None, ldx=None, lddx=None):
+    """dx = dy * gelu_new'(x) on the stored pre-activation x."""
+    _need_cuda(dy, x, dx)
+    if not (dy.dtype == x.dtype == dx.dtype):
+        raise TypeError("gelu_tanh_bwd: dtype mismatch")
+    _call("tcavp_gelu_tanh_bwd", "gelu_new_bwd_kernel", _p(dy), cols if lddy is None else lddy, _p(x), cols if ldx is None else ldx, _p(dx),
+          cols if lddx is None else lddx, dt(x), _ll(rows), cols)
+    return dx
+
+
 def layernorm_bwd(dy, x, w, *, residual=None, eps=1e-5, dx=None, dw=None, db=None, rows=None, cols=None):
     _need_cuda(dy, x, w, residual, dx, dw, db)
     rows = x.numel() // x.shape[-1] if rows is None else rows

@@ -30,7 +30,7 @@ def _pad8(n):
 # site id = module << 20 | layer << 8 | kind.  The oracle (oracle/dropout.py) derives the same ids from the ORDER in which the
 # reference's forward calls F.dropout / scaled_dot_product_attention, so masks are bit-identical on both sides.
 MOD = dict(poly=1, qenc=2, qdec=3, llm=4, ltsf=5, dec=6)
-KIND = dict(sa_attn=0, drop1=1, ffn=2, drop2=3, ca_attn=4, drop3=5, post=6, cross_attn=7, lora_q=8, lora_k=9, lora_v=10)
+KIND = dict(sa_attn=0, drop1=1, ffn=2, drop2=3, ca_attn=4, drop3=5, post=6, cross_attn=7, lora_q=8, lora_k=9, lora_v=10, lora_c=11)
 
 
 def site_id(mod, layer, kind):
@@ -64,9 +64,6 @@ class TrainEngine(Engine):
     SPLIT_SMALL = False      # the fine-tune step keeps the fp32 layers in exact FFMA (their weights are re-packed every step)
 
     def __init__(self, model, compute_dtype="bf16"):
-        if model.mllm.llama_wrapper.config.get("arch") == "gpt2":
-            raise NotImplementedError("GPT-2-arch backbones are inference-only here: the hand-written backward (fine-tune step, stage-1 "
-                                      "objective) covers the Llama architecture")
         super().__init__(model, compute_dtype)
         self.model = model
         self.G = {}
@@ -93,7 +90,8 @@ class TrainEngine(Engine):
         as frozen even if requires_grad is set (full fine-tuning of the backbone is out of scope)."""
         self.params = self.model.trainable_named_parameters()
         wrap = self.model.mllm.llama_wrapper
-        self.llm_prefix = "mllm.llama_wrapper.llama_model." + ("base_model.model." if wrap.use_lora else "") + "model.layers."
+        self.llm_prefix = ("mllm.llama_wrapper.llama_model." + ("base_model.model." if wrap.use_lora else "") +
+                           ("transformer.h." if wrap.config.get("arch") == "gpt2" else "model.layers."))
 
     # ---- dropout plumbing -----------------------------------------------------------------------------
     def set_dropout_seed(self, base, step=0):
@@ -132,7 +130,10 @@ class TrainEngine(Engine):
         if d.use_post_mlp:
             pr[("dec", "post")] = float(d.post_mlp[2].p)
         wrap = m.mllm.llama_wrapper
-        if wrap.use_lora:
+        if wrap.use_lora and wrap.config.get("arch") == "gpt2":
+            # HF GPT2Config's own attn / resid / embd dropouts are taken as 0 (the shape dicts of config.py carry no such keys)
+            pr[("llm", "lora_c")] = float(wrap.causal_lm().transformer.h[0].attn.c_attn.lora_dropout_p)
+        elif wrap.use_lora:
             layer0 = wrap.causal_lm().model.layers[0].self_attn
             for t in wrap.llama_model.targets:
                 pr[("llm", "lora_" + t[0])] = float(getattr(layer0, t).lora_dropout_p)
@@ -170,6 +171,13 @@ class TrainEngine(Engine):
         self._pack_qformer(m.mllm)
         self._pack_ltsf(m.ltsf)
         self.lt["be_pos"] = self.lt["be"] + self.lt["pos"]
+        if self.llm.get("arch") == "gpt2":
+            if self.need_llm_bwd and not self._bwd_packed:
+                for ly in self.llm["layers"]:
+                    ly["wqkvT"] = ly["wqkv"].t().contiguous()           # [H + kx, 3H]: rows [0, H) -> d ln_1(x), rows [H, H + kx) -> d (x A^T)
+                self._bwd_packed = True
+            self._refresh_lora_gpt2()
+            return
         if self.need_llm_bwd and not self._bwd_packed:
             for ly in self.llm["layers"]:
                 ly["wdownT"] = ly["wdown"].t().contiguous()
@@ -220,6 +228,29 @@ class TrainEngine(Engine):
                     w[ti * r:(ti + 1) * r] = (ly["a_cat"][ti * r:(ti + 1) * r].float() * d.scale).to(self.act)
                     ly["a_cat_t"].append(w)
                     ly["a_catT_t"].append(w.t().contiguous())
+
+    def _refresh_lora_gpt2(self):
+        """c_attn's LoRA pair re-packed from the fp32 masters (they move every optimizer step): B alpha / r as the extra K columns of the
+        fused QKV weight, A as the skinny operand; with lora_dropout live, A also with 1 / (1 - p) folded in (the masked copy is x or 0)."""
+        L = self.llm
+        if not L["kx"]:
+            return
+        H, r = L["H"], L["r"]
+        d0 = self._lora_drops(0)
+        for ly, blk in zip(L["layers"], self.model.mllm.llama_wrapper.causal_lm().transformer.h):
+            ca = blk.attn.c_attn
+            ext = (ca.lora_B["default"].weight.detach().float().to(self.dev) * ca.scaling).to(self.act)          # [3H, r]
+            ly["wqkv"][:, H:H + r] = ext
+            if "wqkvT" in ly:
+                ly["wqkvT"][H:H + r, :] = ext.t()
+            A = ca.lora_A["default"].weight.detach().float().to(self.dev)
+            ly["a_cat"][:r] = A.to(self.act)
+            ly["a_catT"] = ly["a_cat"].t().contiguous()
+            ly.pop("a_cat_d", None)
+            if d0:
+                w = torch.zeros_like(ly["a_cat"])
+                w[:r] = (A * d0[0].scale).to(self.act)
+                ly["a_cat_d"], ly["a_catT_d"] = w, w.t().contiguous()
 
     def _lora_fused(self):
         """lora_dropout through the fused kernels (bf16 compute, rank 8 / 16, hidden size a multiple of 64); TCAVP_LORA_DROP_FUSED=0
@@ -526,8 +557,105 @@ class TrainEngine(Engine):
         Kx = m["H"] + m["kx"]
         return torch.zeros(M, Kx, dtype=self.act, device=self.dev) if m["kx"] != m["n_lora"] else self._new(M, Kx)
 
+    # ---- GPT-2-arch backbone (HF modeling_gpt2.py GPT2Model / GPT2Block, reached through scripts/train.py:445-453) ---------------
+    def _gpt2_fwd(self, fused, mask, B, L):
+        """Engine._gpt2_forward with every activation a gradient needs kept: per block (x_in, [ln_1(x) | LoRA side columns], qkv, attention
+        output, x_mid, ln_2(x_mid), c_fc pre-activation).  gelu_new runs as a pass of its own so the pre-activation survives."""
+        m = self.llm
+        H, nh, dh, I, kx = m["H"], m["nh"], m["dh"], m["I"], m["kx"]
+        M, Kx = B * L, H + kx
+        if L > m["wpe"].shape[0]:
+            raise ops._lib.TcavpError(f"sequence length {L} exceeds the backbone's n_positions {m['wpe'].shape[0]}")
+        pos = ops.cast(m["wpe"], self._new(M, H), rows=M, cols=H, in_row_mod=L)
+        x = ops.axpby(fused.view(M, H), self._new(M, H), rows=M, cols=H, b=pos)
+        sq = (L * 3 * H, 3 * H)
+        ctxs, xm = [], None
+        for li, ly in enumerate(m["layers"]):
+            h1 = ops.layernorm(x, ly["ln1"][0], ly["ln1"][1], self._new(M, H), eps=ly["ln1"][2])
+            if kx:
+                xs = torch.zeros(M, Kx, dtype=self.act, device=self.dev) if kx != m["n_lora"] else self._new(M, Kx)
+                ops.cast(h1, xs, rows=M, cols=H, ldi=H, ldo=Kx)
+                drops = self._lora_drops(li)
+                if drops:        # peft: lora_A(dropout(ln_1(x))) — masked copy (exact: x or 0), 1 / (1 - p) rides on the weight
+                    xm = self._new(M, H) if xm is None else xm
+                    ops.dropout(h1, xm, drops[0], rows=M, cols=H, scale=1.0)
+                    ops.gemm(xm, ly["a_cat_d"], xs[:, H:], M=M, N=m["n_lora"], K=H, ldo=Kx)
+                else:
+                    ops.gemm(h1, ly["a_cat"], xs[:, H:], M=M, N=m["n_lora"], K=H, ldo=Kx)
+                qkv = ops.gemm(xs, ly["wqkv"], self._new(M, 3 * H), M=M, N=3 * H, K=Kx, lda=Kx, bias=ly["bqkv"])
+            else:
+                xs = h1
+                qkv = ops.gemm(h1, ly["wqkv"], self._new(M, 3 * H), bias=ly["bqkv"])
+            attn = self._new(M, H)
+            ops.attention(qkv, qkv[:, H:], qkv[:, 2 * H:], attn, B=B, H=nh, Hkv=nh, Tq=L, Tk=L, dh=dh, q_strides=sq, k_strides=sq, v_strides=sq,
+                          o_strides=(L * H, H), scale=dh ** -0.5, causal=True, key_mask=mask)
+            x_mid = ops.gemm(attn, ly["proj"].w, self._new(M, H), bias=ly["proj"].b, residual=x)
+            h2 = ops.layernorm(x_mid, ly["ln2"][0], ly["ln2"][1], self._new(M, H), eps=ly["ln2"][2])
+            pre = ops.gemm(h2, ly["fc"].w, self._new(M, I), bias=ly["fc"].b)
+            mid = ops.gelu_tanh(pre, self._new(M, I), rows=M, cols=I)
+            x_out = ops.gemm(mid, ly["mproj"].w, self._new(M, H), bias=ly["mproj"].b, residual=x_mid)
+            ctxs.append((x, xs, qkv, attn, x_mid, pre))
+            x = x_out
+        fh = ops.layernorm(x, m["norm"][0], m["norm"][1], self._new(M, H), eps=m["norm"][2])
+        return fh, (ctxs, x, mask, None, B, L)
+
+    def _gpt2_bwd(self, dfh, ctx):
+        """Backward of _gpt2_fwd.  The base weights, biases and LayerNorms of the backbone are frozen (peft), so only dX flows through
+        them; c_attn's LoRA pair gets dB = (alpha / r) dqkv^T (dropout(h) A^T) and dA = (d(h A^T))^T dropout(h)."""
+        ctxs, x_last, mask, _, B, L = ctx
+        m = self.llm
+        H, nh, dh, I, kx, r = m["H"], m["nh"], m["dh"], m["I"], m["kx"], m["r"]
+        M, Kx = B * L, H + kx
+        sq = (L * 3 * H, 3 * H)
+        lnb = lambda dy, x, ln: ops.layernorm_bwd(dy, x, ln[0], eps=ln[2], dx=self._new(M, H))      # noqa: E731  frozen LayerNorm: dx only
+        dx = lnb(dfh, x_last, m["norm"])
+        xm = None
+        for i in reversed(range(len(ctxs))):
+            x_in, xs, qkv, attn, x_mid, pre = ctxs[i]
+            ly = m["layers"][i]
+            dmid = self._lin_bwd(dx, None, ly["mproj"], None, None, train=False)
+            dpre = ops.gelu_tanh_bwd(dmid, pre, dmid, rows=M, cols=I)
+            dh2 = self._lin_bwd(dpre, None, ly["fc"], None, None, train=False)
+            dx_mid = lnb(dh2, x_mid, ly["ln2"])
+            ops.axpby(dx_mid, dx_mid, rows=M, cols=H, b=dx)
+            dattn = self._lin_bwd(dx_mid, None, ly["proj"], None, None, train=False)
+            dqkv = self._new(M, 3 * H)
+            self._attn_bwd(qkv, qkv[:, H:], qkv[:, 2 * H:], dattn, B=B, H=nh, Hkv=nh, Tq=L, Tk=L, dh=dh, qs=sq, ks=sq, vs=sq, dos=(L * H, H),
+                           dq=dqkv, dqs=sq, dk_out=dqkv[:, H:], dv_out=dqkv[:, 2 * H:], ld_kv=3 * H, scale=dh ** -0.5, causal=True, key_mask=mask,
+                           o=attn)
+            dh1 = ops.gemm(dqkv, ly["wqkvT"][:H], self._new(M, H))
+            if kx:
+                du = ops.gemm(dqkv, ly["wqkvT"][H:], self._new(M, kx))               # gradient w.r.t. the LoRA side columns (dropout(h) A^T)
+                drops = self._lora_drops(i)
+                if drops:
+                    xm = self._new(M, H) if xm is None else xm
+                if self.tr_lora:
+                    dext = torch.zeros(3 * H, kx, dtype=torch.float32, device=self.dev)
+                    ops.skinny_dw(dqkv, xs[:, H:], dext, M=M, N=3 * H, J=kx, ldy=3 * H, ldz=Kx)
+                    dAp = torch.zeros(H, kx, dtype=torch.float32, device=self.dev)
+                    if drops:
+                        ops.dropout(xs, xm, drops[0], rows=M, cols=H, ldi=Kx, ldo=H, scale=1.0)
+                        ops.skinny_dw(xm, du, dAp, M=M, N=H, J=kx, ldy=H, ldz=kx)
+                        dAp *= drops[0].scale
+                    else:
+                        ops.skinny_dw(xs, du, dAp, M=M, N=H, J=kx, ldy=Kx, ldz=kx)
+                    ca = self.model.mllm.llama_wrapper.causal_lm().transformer.h[i].attn.c_attn
+                    pre_n = f"{self.llm_prefix}{i}.attn.c_attn."
+                    self.G[pre_n + "lora_B.default.weight"] = (dext[:, :r] * ca.scaling).contiguous()
+                    self.G[pre_n + "lora_A.default.weight"] = dAp[:, :r].t().contiguous()
+                if drops:        # dh1 += mask o (du . A / (1 - p))
+                    tmp = ops.gemm(du, ly["a_catT_d"], xm, M=M, N=H, K=kx)
+                    ops.dropout(tmp, dh1, drops[0], rows=M, cols=H, scale=1.0, accumulate=True)
+                else:
+                    ops.gemm(du, ly["a_catT"], dh1, M=M, N=H, K=kx, residual=dh1)
+            dx_in = lnb(dh1, x_in, ly["ln1"])
+            dx = ops.axpby(dx_in, dx_in, rows=M, cols=H, b=dx_mid)
+        return dx      # gradient w.r.t. the fused input embeddings (wpe is frozen: the position term adds nothing)
+
     def _llm_fwd(self, fused, mask, B, L):
         m = self.llm
+        if m.get("arch") == "gpt2":
+            return self._gpt2_fwd(fused, mask, B, L)
         if not m["fuse_rope"]:
             raise ops._lib.TcavpError("the fine-tune step needs head_dim % 32 == 0 (fused RoPE layout)")
         H, nh, nkv, dh, I, kx = m["H"], m["nh"], m["nkv"], m["dh"], m["I"], m["kx"]
@@ -579,6 +707,8 @@ class TrainEngine(Engine):
         return fh, (ctxs, xs, mask, table, B, L)
 
     def _llm_bwd(self, dfh, ctx):
+        if self.llm.get("arch") == "gpt2":
+            return self._gpt2_bwd(dfh, ctx)
         ctxs, xs_last, mask, table, B, L = ctx
         m = self.llm
         H, nh, nkv, dh, I, kx, r = m["H"], m["nh"], m["nkv"], m["dh"], m["I"], m["kx"], m["r"]
