@@ -408,6 +408,7 @@ TRAIN_WORKLOADS = {
     # name: (model preset, scenes per GPU per step, L_text)  — BASELINE.json configs[3]: LoRA fine-tune step, data parallel
     "cfg2": ("cfg1", 512, 128),
     "cfg3": ("cfg3", 128, 128),    # 103 GiB of the 180 GB at 128 scenes / GPU / step
+    "cfg2-gpt2": ("cfg1-gpt2", 512, 128),    # the cfg2 shape on the GPT-2 architecture (HF GPT2LMHeadModel, c_attn LoRA)
 }
 
 
@@ -505,7 +506,7 @@ def measure_train(ctx, workload, steps, warmup, scenes=0, dropout=None):
     pk = peaks()
     roof, _ = _roofline(prof, pk, ms / steps, 1, {"breakdown": "one eager step after the timed region (the timed steps replay a CUDA graph)"})
     probs = model.train_engine()._dropout_probs()
-    p_drop = {"lora": probs.get(("llm", "lora_q"), 0.0), "ltsf": probs.get(("ltsf", "ffn"), 0.0), "transformer_layers": probs.get(("qenc", "ffn"), 0.0),
+    p_drop = {"lora": probs.get(("llm", "lora_q"), probs.get(("llm", "lora_c"), 0.0)), "ltsf": probs.get(("ltsf", "ffn"), 0.0), "transformer_layers": probs.get(("qenc", "ffn"), 0.0),
               "applied": bool(ft.dropout_active), "masks": "counter-based (seed, step, site, element), regenerated in the backward pass"}
     out = {
         "metric": "LoRA fine-tune tokens/sec (forward + backward + grad all-reduce + AdamW)", "value": round(value, 1), "unit": "tokens/s",
@@ -629,6 +630,7 @@ def run_ours(args):
         extra = [("cfg2_gpt2", lambda: measure_infer(ctx, "cfg2-gpt2", k2, 3, e2e=True)[0])]      # the headline workload on the GPT-2 architecture
         if ctx.world == 1:
             extra.append(("stage1_cfg2", lambda: measure_stage1(ctx, k2, 3)))                    # CausalLM training step (single-GPU line)
+            extra.append(("train_cfg2_gpt2", lambda: measure_train(ctx, "cfg2-gpt2", k2, 3)))    # fine-tune step on the GPT-2 architecture
         for name, fn in [("cfg3", lambda: measure_infer(ctx, "cfg3", k2, 3, e2e=True)[0]),
                          ("cfg5", lambda: measure_infer(ctx, "cfg5", max(k2, 10), 3, e2e=True)[0]),
                          ("train_cfg2", lambda: measure_train(ctx, "cfg2", k2, 3)),

@@ -261,6 +261,11 @@ int tcavp_axpby(const void* a, int lda, int a_dtype, float alpha, const void* b,
 /* SwiGLU on interleaved (gate, up) columns (HF:190) and its backward; gu / dgu are [rows, 2I], out / dout [rows, I]. */
 int tcavp_swiglu(const void* gu, void* out, int dtype, long long rows, int I, tcavp_stream_t stream);
 int tcavp_swiglu_bwd(const void* dout, const void* gu, void* dgu, int dtype, long long rows, int I, tcavp_stream_t stream);
+/* LayerNorm backward for a FROZEN LayerNorm (no residual input, no dw / db): dx = rstd (g - mean(g) - xhat mean(g xhat)) [+ add],
+ * g = dy * w.  `add` (optional) is the gradient arriving on the residual branch, summed in the same pass.  Used by the fine-tune step
+ * of a GPT-2-arch backbone, whose ln_1 / ln_2 / ln_f are frozen under peft (HF modeling_gpt2.py GPT2Block.forward). */
+int tcavp_layernorm_bwd_dx(const void* dy, int lddy, const void* x, int ldx, const float* w, const void* add, int ldadd, void* dx, int lddx,
+                           int dtype, int rows, int cols, float eps, tcavp_stream_t stream);
 /* HF ACT2FN["gelu_new"] (GPT-2 mlp.act: 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))) on [rows, cols] as a pass of its own, and its
  * backward on the stored pre-activation x: dx = dy * d gelu_new(x) / dx.  The fine-tune step of a GPT-2-arch backbone (HF
  * modeling_gpt2.py GPT2MLP.forward, reached through reference scripts/train.py:445-453) keeps c_fc's output for the backward pass;

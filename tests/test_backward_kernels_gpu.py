@@ -89,6 +89,34 @@ def test_relu_bwd_axpby_swiglu(ops, dtype):
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("rows,cols,ld,with_add", [(300, 768, 768, True), (37, 128, 136, True), (65, 1024, 1024, False), (9, 2048, 2048, True),
+                                                   (5, 40, 40, True), (130, 256, 264, False)])
+def test_layernorm_bwd_dx_frozen(ops, dtype, rows, cols, ld, with_add):
+    """dx-only LayerNorm backward (frozen LayerNorm of a GPT-2-arch backbone) with the residual-branch gradient added in the same pass:
+    register path (bf16, <= 1024 columns), generic path, padded row strides — against autograd through F.layer_norm."""
+    td = _td(dtype)
+    x = _rand(rows, cols, seed=14).to(td).float().requires_grad_(True)
+    w = 1.0 + 0.1 * _rand(cols, seed=15)
+    b = 0.1 * _rand(cols, seed=16)
+    y = torch.nn.functional.layer_norm(x, (cols,), w, b, 1e-5)
+    dy = _rand(rows, cols, seed=17).to(td)
+    y.backward(dy.float())
+    add = _rand(rows, cols, seed=18).to(td) if with_add else None
+    want = x.grad + (add.float() if with_add else 0.0)
+
+    def pad(t):
+        o = torch.zeros(rows, ld, dtype=td, device=DEV)
+        o[:, :cols] = t.to(td).to(DEV)
+        return o
+    dx = torch.full((rows, ld), 3.0, dtype=td, device=DEV)
+    ops.layernorm_bwd_dx(pad(dy), pad(x.detach()), w.to(DEV), dx, rows=rows, cols=cols, eps=1e-5, add=pad(add) if with_add else None,
+                         lddy=ld, ldx=ld, ldadd=ld, lddx=ld)
+    tol = dict(rtol=1e-4, atol=2e-5) if dtype == "fp32" else dict(rtol=2e-2, atol=3e-2)
+    torch.testing.assert_close(dx[:, :cols].cpu().float(), want, **tol)
+    assert bool((dx[:, cols:] == 3.0).all())
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 @pytest.mark.parametrize("rows,cols,ld", [(129, 72, 72), (300, 3072, 3072), (33, 40, 48), (17, 37, 37)])
 def test_gelu_new_forward_and_backward(ops, dtype, rows, cols, ld):
     """HF ACT2FN["gelu_new"] as its own pass + backward on the stored pre-activation (GPT-2 fine-tune step), vector and scalar paths,

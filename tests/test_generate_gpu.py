@@ -21,21 +21,23 @@ def _oracle_logits(sd, cfg, lc, vision, ids_prefix, new_ids):
         img = restated.linear(img, sd[p + "q_proj.weight"], sd[p + "q_proj.bias"])
     img = img + sd[p + "vision_modality_embedding"]
     lp = restated.find_llm_prefix(sd)
-    E = sd[lp + "embed_tokens.weight"]
+    gpt2 = lc.get("arch") == "gpt2"
+    E = sd[lp + ("wte.weight" if gpt2 else "embed_tokens.weight")]
     parts = [img, E[ids_prefix] + sd[p + "text_modality_embedding"]]
     if new_ids is not None and new_ids.shape[1] > 0:
         parts.append(E[new_ids])
     fused = torch.cat(parts, dim=1)
     mask = torch.ones(fused.shape[:2], dtype=torch.long)
-    fh = restated.llama_stack(sd, lc, fused, mask, cfg.get("lora_alpha", 32) / cfg.get("lora_r", 8), lp)
-    head = sd[lp[: -len("model.")] + "lm_head.weight"]
+    fh = (restated.gpt2_stack if gpt2 else restated.llama_stack)(sd, lc, fused, mask, cfg.get("lora_alpha", 32) / cfg.get("lora_r", 8), lp)
+    head = sd[lp.rsplit(".", 2)[0] + ".lm_head.weight"]
     return fh[:, -1] @ head.t()
 
 
 @gpu
+@pytest.mark.parametrize("fixture", ["tiny_b6", "gpt2_tiny_b6"])
 @pytest.mark.parametrize("dtype,tol", [("fp32", 2e-4), ("bf16", 4e-2)])
-def test_next_token_logits_and_greedy_continuation_match_the_oracle(lib_built, dtype, tol):
-    fix = load_golden("tiny_b6")
+def test_next_token_logits_and_greedy_continuation_match_the_oracle(lib_built, dtype, tol, fixture):
+    fix = load_golden(fixture)
     m = build_filled_model(fix, dtype, "cuda")
     cfg, lc = fix["model_cfg"], fix["llama_cfg"]
     sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}

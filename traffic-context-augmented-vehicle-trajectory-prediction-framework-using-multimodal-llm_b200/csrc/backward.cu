@@ -578,6 +578,93 @@ __global__ void __launch_bounds__(256) dw_simt_kernel(const void* __restrict__ d
 //   P = softmax(scale * Q K^T + mask);  dP = dO V^T;  D_i = sum_j P_ij dP_ij;  dS = scale * P o (dP - D)
 //   dQ = dS K (owned rows, plain stores);  dK += dS^T Q;  dV += P^T dO  (fp32 atomics: q-blocks and GQA groups share keys)
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward for a FROZEN LayerNorm (GPT-2-arch backbone under peft: ln_1 / ln_2 / ln_f get no gradient): dx only, with the
+// gradient of the residual branch added in the same pass.   g = dy * w;  dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) + add
+// bf16 rows up to 1024 columns live in registers (one 16-byte load per 8 elements, x and dy read once); anything else takes the
+// generic warp-per-row loop.
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_bwd_dx_vec_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, const __nv_bfloat16* __restrict__ x,
+                                                                   int ldx, const float* __restrict__ w, const __nv_bfloat16* __restrict__ add,
+                                                                   int ldadd, __nv_bfloat16* __restrict__ dx, int lddx, int rows, int cols, float eps) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    const __nv_bfloat16* xr = x + (size_t)row * ldx;
+    const __nv_bfloat16* gr = dy + (size_t)row * lddy;
+    float xv[NV][8], gv[NV][8];
+    float s = 0.f, sg = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      if (c < cols) {
+        ld8_bf16(xr + c, xv[i]);
+        ld8_bf16(gr + c, gv[i]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          gv[i][e] *= __ldg(w + c + e);
+          s += xv[i][e];
+          sg += gv[i][e];
+        }
+      }
+    }
+    const float mean = warp_sum(s) / cols;
+    float q = 0.f, dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      if (c < cols) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          xv[i][e] -= mean;
+          q += xv[i][e] * xv[i][e];
+          dot += gv[i][e] * xv[i][e];
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / cols + eps);
+    const float s1 = warp_sum(sg) / cols;                    // mean(g)
+    const float s2 = warp_sum(dot) * rstd / cols;            // mean(g * xhat)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      if (c < cols) {
+        float o[8], ad[8];
+        if (add) ld8_bf16(add + (size_t)row * ldadd + c, ad);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = rstd * (gv[i][e] - s1 - xv[i][e] * rstd * s2) + (add ? ad[e] : 0.f);
+        st8_bf16(dx + (size_t)row * lddx + c, o);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) layernorm_bwd_dx_kernel(const void* __restrict__ dy, int lddy, const void* __restrict__ x, int ldx,
+                                                               const float* __restrict__ w, const void* __restrict__ add, int ldadd,
+                                                               void* __restrict__ dx, int lddx, int dtype, int rows, int cols, float eps) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    float s = 0.f;
+    for (int c = lane; c < cols; c += 32) s += load_as_f(x, (size_t)row * ldx + c, dtype);
+    const float mean = warp_sum(s) / cols;
+    float q = 0.f, sg = 0.f, dot = 0.f;
+    for (int c = lane; c < cols; c += 32) {
+      const float v = load_as_f(x, (size_t)row * ldx + c, dtype) - mean;
+      const float g = load_as_f(dy, (size_t)row * lddy + c, dtype) * __ldg(w + c);
+      q += v * v;
+      sg += g;
+      dot += g * v;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / cols + eps);
+    const float s1 = warp_sum(sg) / cols, s2 = warp_sum(dot) * rstd / cols;
+    for (int c = lane; c < cols; c += 32) {
+      const float xh = (load_as_f(x, (size_t)row * ldx + c, dtype) - mean) * rstd;
+      const float g = load_as_f(dy, (size_t)row * lddy + c, dtype) * __ldg(w + c);
+      store_from_f(dx, (size_t)row * lddx + c, dtype, rstd * (g - s1 - xh * s2) + (add ? load_as_f(add, (size_t)row * ldadd + c, dtype) : 0.f));
+    }
+  }
+}
+
 namespace ab {
 constexpr int QB = 16;
 constexpr int THREADS = 256;
@@ -885,6 +972,30 @@ extern "C" int tcavp_layernorm_bwd(const void* dy, int dy_dtype, const void* x, 
   layernorm_bwd_kernel<<<grid_cap((rows + 7) / 8, 4), 256, smem, STREAM(stream)>>>(dy, dy_dtype, x, residual, x_dtype, w, rows, cols, eps, dx,
                                                                                  dx_dtype, dw, db);
   return check_launch("layernorm_bwd_kernel");
+}
+
+extern "C" int tcavp_layernorm_bwd_dx(const void* dy, int lddy, const void* x, int ldx, const float* w, const void* add, int ldadd, void* dx,
+                                      int lddx, int dtype, int rows, int cols, float eps, tcavp_stream_t stream) {
+  TCAVP_REQUIRE(rows >= 0 && cols > 0 && lddy >= cols && ldx >= cols && lddx >= cols && (!add || ldadd >= cols), "tcavp_layernorm_bwd_dx: bad shape");
+  if (rows == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(dy && x && w && dx && DT_OK(dtype), "tcavp_layernorm_bwd_dx: bad pointer/dtype");
+  auto al = [](const void* p, int ld) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % 16 == 0 && ld % 8 == 0); };
+  if (dtype == TCAVP_BF16 && cols % 8 == 0 && cols <= 1024 && al(dy, lddy) && al(x, ldx) && al(add, ldadd) && al(dx, lddx)) {
+    const __nv_bfloat16* dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
+    const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
+    const __nv_bfloat16* ab = reinterpret_cast<const __nv_bfloat16*>(add);
+    __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(dx);
+    const int grid = grid_cap((rows + 7) / 8, 16);
+#define TCAVP_LB(NV) layernorm_bwd_dx_vec_kernel<NV><<<grid, 256, 0, STREAM(stream)>>>(dyb, lddy, xb, ldx, w, ab, ldadd, ob, lddx, rows, cols, eps)
+    if (cols <= 256) TCAVP_LB(1);
+    else if (cols <= 512) TCAVP_LB(2);
+    else if (cols <= 768) TCAVP_LB(3);
+    else TCAVP_LB(4);
+#undef TCAVP_LB
+    return check_launch("layernorm_bwd_dx_kernel");
+  }
+  layernorm_bwd_dx_kernel<<<grid_cap((rows + 7) / 8, 8), 256, 0, STREAM(stream)>>>(dy, lddy, x, ldx, w, add, ldadd, dx, lddx, dtype, rows, cols, eps);
+  return check_launch("layernorm_bwd_dx_kernel");
 }
 
 extern "C" int tcavp_rmsnorm_bwd(const void* dy, int lddy, const void* x, int ldx, const float* w, const void* add, int ldadd, void* dx,

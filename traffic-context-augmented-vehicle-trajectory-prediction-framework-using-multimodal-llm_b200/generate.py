@@ -95,8 +95,6 @@ def generate_ids(model, vision_embs, prompt_ids, max_new_tokens=128, temperature
 
 def generate_batch(model, vision_embs, prompt_ids, tokenizer, max_new_tokens=128, temperature=0.9, top_k=40, top_p=0.9, device="cuda"):
     """Drop-in for `LlamaMultiModal.generate_batch` (train.py:577-654): list of decoded strings, cut after the reference's end marker."""
-    if model.mllm.llama_wrapper.config.get("arch") == "gpt2":
-        raise NotImplementedError("generate_batch covers the Llama architecture (the GPT-2-arch backbone path is forward-only)")
     was_training = model.training
     model.eval()
     try:

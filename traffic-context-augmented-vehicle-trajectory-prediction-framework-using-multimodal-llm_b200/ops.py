@@ -639,6 +639,17 @@ def layernorm_bwd(dy, x, w, *, residual=None, eps=1e-5, dx=None, dw=None, db=Non
     return dx
 
 
+def layernorm_bwd_dx(dy, x, w, dx, *, rows, cols, eps=1e-5, add=None, lddy=None, ldx=None, ldadd=None, lddx=None):
+    """dx = LayerNorm backward w.r.t. its input (frozen LayerNorm: no dw / db) [+ add]."""
+    _need_cuda(dy, x, w, dx, add)
+    if not (dy.dtype == x.dtype == dx.dtype) or (add is not None and add.dtype != x.dtype):
+        raise TypeError("layernorm_bwd_dx: dtype mismatch")
+    _call("tcavp_layernorm_bwd_dx", "layernorm_bwd_dx_kernel", _p(dy), cols if lddy is None else lddy, _p(x), cols if ldx is None else ldx, _p(w),
+          _p(add), cols if ldadd is None else ldadd, _p(dx), cols if lddx is None else lddx, dt(x), rows, cols, c_float(eps),
+          nbytes=float(rows * cols * x.element_size() * (4 if add is not None else 3)))
+    return dx
+
+
 def rmsnorm_bwd(dy, x, dx, *, rows, cols, eps, w=None, add=None, lddy=None, ldx=None, ldadd=None, lddx=None):
     _need_cuda(dy, x, dx, w, add)
     _call("tcavp_rmsnorm_bwd", "rmsnorm_bwd_kernel", _p(dy), cols if lddy is None else lddy, _p(x), cols if ldx is None else ldx, _p(w),

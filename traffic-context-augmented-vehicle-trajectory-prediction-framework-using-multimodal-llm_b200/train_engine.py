@@ -607,7 +607,8 @@ class TrainEngine(Engine):
         H, nh, dh, I, kx, r = m["H"], m["nh"], m["dh"], m["I"], m["kx"], m["r"]
         M, Kx = B * L, H + kx
         sq = (L * 3 * H, 3 * H)
-        lnb = lambda dy, x, ln: ops.layernorm_bwd(dy, x, ln[0], eps=ln[2], dx=self._new(M, H))      # noqa: E731  frozen LayerNorm: dx only
+        # frozen LayerNorm: dx only, the residual-branch gradient added in the same pass
+        lnb = lambda dy, x, ln, add=None: ops.layernorm_bwd_dx(dy, x, ln[0], self._new(M, H), rows=M, cols=H, eps=ln[2], add=add)   # noqa: E731
         dx = lnb(dfh, x_last, m["norm"])
         xm = None
         for i in reversed(range(len(ctxs))):
@@ -616,8 +617,7 @@ class TrainEngine(Engine):
             dmid = self._lin_bwd(dx, None, ly["mproj"], None, None, train=False)
             dpre = ops.gelu_tanh_bwd(dmid, pre, dmid, rows=M, cols=I)
             dh2 = self._lin_bwd(dpre, None, ly["fc"], None, None, train=False)
-            dx_mid = lnb(dh2, x_mid, ly["ln2"])
-            ops.axpby(dx_mid, dx_mid, rows=M, cols=H, b=dx)
+            dx_mid = lnb(dh2, x_mid, ly["ln2"], dx)
             dattn = self._lin_bwd(dx_mid, None, ly["proj"], None, None, train=False)
             dqkv = self._new(M, 3 * H)
             self._attn_bwd(qkv, qkv[:, H:], qkv[:, 2 * H:], dattn, B=B, H=nh, Hkv=nh, Tq=L, Tk=L, dh=dh, qs=sq, ks=sq, vs=sq, dos=(L * H, H),
@@ -648,8 +648,7 @@ class TrainEngine(Engine):
                     ops.dropout(tmp, dh1, drops[0], rows=M, cols=H, scale=1.0, accumulate=True)
                 else:
                     ops.gemm(du, ly["a_catT"], dh1, M=M, N=H, K=kx, residual=dh1)
-            dx_in = lnb(dh1, x_in, ly["ln1"])
-            dx = ops.axpby(dx_in, dx_in, rows=M, cols=H, b=dx_mid)
+            dx = lnb(dh1, x_in, ly["ln1"], dx_mid)
         return dx      # gradient w.r.t. the fused input embeddings (wpe is frozen: the position term adds nothing)
 
     def _llm_fwd(self, fused, mask, B, L):
