@@ -135,6 +135,7 @@ DROP_FIXTURES = {
     "tiny_b5_grads_drop": ("tiny_b5_grads", 20261, 3),
     "cfg1_b3_grads_drop": ("cfg1_b3_grads", 77001, 11),
     "gpt2_tiny_b5_grads_drop": ("gpt2_tiny_b5_grads", 31337, 5),
+    "gpt2_l2_b3_grads_drop": ("gpt2_l2_b3_grads", 52007, 2),       # LoRA r 8, hidden 768: the fused lora-dropout kernels in bf16 mode
 }
 
 

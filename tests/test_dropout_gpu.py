@@ -150,7 +150,7 @@ def _drop_oracle(fix):
     return OD.DropOracle(fix["dropout"]["seed"], fix["dropout"]["step"], OD.default_probs(fix["model_cfg"]))
 
 
-@pytest.mark.parametrize("name", ["tiny_b5_grads_drop", "cfg1_b3_grads_drop", "gpt2_tiny_b5_grads_drop"])
+@pytest.mark.parametrize("name", ["tiny_b5_grads_drop", "cfg1_b3_grads_drop", "gpt2_tiny_b5_grads_drop", "gpt2_l2_b3_grads_drop"])
 def test_fp32_train_mode_gradients_match_reference(lib_built, name):
     """The whole fine-tune step in train() mode (p = 0.1 at every site of the reference) against the golden of the unmodified reference
     run with the same masks: loss, decoded, and the gradient of every trainable tensor."""
@@ -188,8 +188,10 @@ def test_fp32_train_mode_gradients_match_reference(lib_built, name):
     torch.testing.assert_close(l4.detach().cpu(), load_golden(name.replace("_drop", ""))["loss"], rtol=1e-4, atol=0)
 
 
-def test_bf16_train_mode_gradients_track_the_oracle(lib_built):
-    fix = load_golden("tiny_b5_grads_drop")
+@pytest.mark.parametrize("name", ["tiny_b5_grads_drop", "gpt2_l2_b3_grads_drop"])
+def test_bf16_train_mode_gradients_track_the_oracle(lib_built, name):
+    """bf16 train mode (gpt2_l2: LoRA r 8 on a 768-wide c_attn, so lora_dropout runs through the fused mask-regenerating kernels)."""
+    fix = load_golden(name)
     m = _model(fix, "bf16")
     m.set_dropout_seed(fix["dropout"]["seed"], fix["dropout"]["step"])
     loss, _ = _step(m, fix["inputs"])

@@ -247,7 +247,10 @@ class TrainEngine(Engine):
             ly["a_cat"][:r] = A.to(self.act)
             ly["a_catT"] = ly["a_cat"].t().contiguous()
             ly.pop("a_cat_d", None)
-            if d0:
+            ly.pop("a_cat_s", None)
+            if d0 and self._lora_fused():      # csrc/lora_drop.cu: the mask is regenerated on the operand fragments (no masked copy)
+                ly["a_cat_s"] = (A * d0[0].scale).to(self.act).contiguous()
+            elif d0:
                 w = torch.zeros_like(ly["a_cat"])
                 w[:r] = (A * d0[0].scale).to(self.act)
                 ly["a_cat_d"], ly["a_catT_d"] = w, w.t().contiguous()
@@ -576,7 +579,9 @@ class TrainEngine(Engine):
                 xs = torch.zeros(M, Kx, dtype=self.act, device=self.dev) if kx != m["n_lora"] else self._new(M, Kx)
                 ops.cast(h1, xs, rows=M, cols=H, ldi=H, ldo=Kx)
                 drops = self._lora_drops(li)
-                if drops:        # peft: lora_A(dropout(ln_1(x))) — masked copy (exact: x or 0), 1 / (1 - p) rides on the weight
+                if drops and "a_cat_s" in ly:
+                    ops.lora_a_drop(xs, ly["a_cat_s"], xs[:, H:], drops, M=M, H=H, r=m["r"], ldx=Kx, ldo=Kx)
+                elif drops:      # peft: lora_A(dropout(ln_1(x))) — masked copy (exact: x or 0), 1 / (1 - p) rides on the weight
                     xm = self._new(M, H) if xm is None else xm
                     ops.dropout(h1, xm, drops[0], rows=M, cols=H, scale=1.0)
                     ops.gemm(xm, ly["a_cat_d"], xs[:, H:], M=M, N=m["n_lora"], K=H, ldo=Kx)
@@ -627,13 +632,17 @@ class TrainEngine(Engine):
             if kx:
                 du = ops.gemm(dqkv, ly["wqkvT"][H:], self._new(M, kx))               # gradient w.r.t. the LoRA side columns (dropout(h) A^T)
                 drops = self._lora_drops(i)
-                if drops:
+                fused = bool(drops) and "a_cat_s" in ly
+                if drops and not fused:
                     xm = self._new(M, H) if xm is None else xm
                 if self.tr_lora:
                     dext = torch.zeros(3 * H, kx, dtype=torch.float32, device=self.dev)
                     ops.skinny_dw(dqkv, xs[:, H:], dext, M=M, N=3 * H, J=kx, ldy=3 * H, ldz=Kx)
                     dAp = torch.zeros(H, kx, dtype=torch.float32, device=self.dev)
-                    if drops:
+                    if fused:
+                        ops.lora_da_drop(xs, du, dAp, drops, M=M, H=H, r=r, ldx=Kx, lddt=kx)
+                        dAp *= drops[0].scale
+                    elif drops:
                         ops.dropout(xs, xm, drops[0], rows=M, cols=H, ldi=Kx, ldo=H, scale=1.0)
                         ops.skinny_dw(xm, du, dAp, M=M, N=H, J=kx, ldy=H, ldz=kx)
                         dAp *= drops[0].scale
@@ -643,7 +652,9 @@ class TrainEngine(Engine):
                     pre_n = f"{self.llm_prefix}{i}.attn.c_attn."
                     self.G[pre_n + "lora_B.default.weight"] = (dext[:, :r] * ca.scaling).contiguous()
                     self.G[pre_n + "lora_A.default.weight"] = dAp[:, :r].t().contiguous()
-                if drops:        # dh1 += mask o (du . A / (1 - p))
+                if fused:        # dh1 += mask o (du . A / (1 - p)), one pass
+                    ops.lora_dx_drop(du, ly["a_cat_s"], dh1, drops, M=M, H=H, r=r, lddt=kx, lddx=H)
+                elif drops:
                     tmp = ops.gemm(du, ly["a_catT_d"], xm, M=M, N=H, K=kx)
                     ops.dropout(tmp, dh1, drops[0], rows=M, cols=H, scale=1.0, accumulate=True)
                 else:
