@@ -357,17 +357,24 @@ def measure_infer(ctx, workload, steps, warmup, e2e=True, scenes=0, merge_lora=F
             return e2e_read((n - 1) & 1)
 
         e2e_run(2)
-        ctx.barrier()
-        t0 = time.perf_counter()
-        e2e_last = e2e_run(steps)
-        torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
-        if abs(e2e_last[0] / B - ade) > 1e-3 * max(ade, 1.0):
-            raise RuntimeError(f"end-to-end leg disagrees with the device-resident leg: ADE {e2e_last[0] / B} vs {ade}")
-        e2e_value = world * B * steps / ctx.max_over_ranks(e2e_s)
+        # host wall clock over K steps is exposed to a single scheduling hiccup of the host thread (one 40 ms stall = 10 % of a 10-step
+        # region): the leg is repeated three times, every repeat is K full steps, and the MEDIAN repeat is reported (all three listed)
+        e2e_repeats = []
+        for _ in range(3):
+            ctx.barrier()
+            t0 = time.perf_counter()
+            e2e_last = e2e_run(steps)
+            torch.cuda.synchronize()
+            e2e_s = time.perf_counter() - t0
+            if abs(e2e_last[0] / B - ade) > 1e-3 * max(ade, 1.0):
+                raise RuntimeError(f"end-to-end leg disagrees with the device-resident leg: ADE {e2e_last[0] / B} vs {ade}")
+            e2e_repeats.append(world * B * steps / ctx.max_over_ranks(e2e_s))
+        e2e_value = statistics.median(e2e_repeats)
         e2e_block = {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                      "api": "MultiModalTrajectoryModel.predict_with_metrics (pinned host tensors in, decoded + metrics out)",
-                     "pipeline": "2-deep: step i+1 is enqueued before the host reads step i (bulk H2D on a copy stream)"}
+                     "pipeline": "2-deep: step i+1 is enqueued before the host reads step i (bulk H2D on a copy stream)",
+                     "timing": f"host wall clock over {steps} steps, max over ranks; median of 3 repeats",
+                     "repeat_values": [round(v, 2) for v in e2e_repeats]}
 
     pk = peaks()
     Lseq = 16 + l_text
