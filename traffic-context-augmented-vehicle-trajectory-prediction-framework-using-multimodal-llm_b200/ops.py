@@ -262,7 +262,8 @@ def gemm(a, w, out, *, M=None, N=None, K=None, lda=None, ldw=None, ldo=None, bia
         if long_k and _ROUTE["wide_k"] and g.K >= _ROUTE["wide_k"]:
             kern = "gemm_tc_wide_kernel[N%d,K%d]" % (g.N, g.K)     # mirrors tcavp_gemm's dispatch (long contraction, >= 4 waves of tiles)
         elif g.N > 128 and g.M >= 2048:    # CTA-pair (cta_group::2) kernel for the large problems
-            kern = "gemm_tc_pair_kernel<256>[N%d,K%d]" % (g.N, g.K)
+            # small-M launches (the Q-Former's 16 query rows per scene) are reported apart from the token-stream launches of the same [N, K]
+            kern = "gemm_tc_pair_kernel<256>[%sN%d,K%d]" % ("M%d," % g.M if g.M < 32768 else "", g.N, g.K)
         else:
             kern = "gemm_tc_kernel<%d>[N%d,K%d]" % (32 if g.N <= 32 else 64 if g.N <= 64 else 128 if g.N <= 128 else 256, g.N, g.K)
     else:
