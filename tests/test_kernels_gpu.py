@@ -268,6 +268,33 @@ def test_layernorm_remap_rowvec(ops):
     assert (fused[:, Q:] == 0).all()
 
 
+@pytest.mark.parametrize("rows,cols,out_dtype,remap", [(65536 + 37, 768, "bf16", False), (70001, 512, "fp32", False), (65536, 1024, "bf16", False),
+                                                       (66000, 256, "bf16", True)])
+def test_layernorm_many_bf16_rows_through_the_bulk_copy_ring(ops, rows, cols, out_dtype, remap):
+    """>= 65536 bf16 rows take layernorm_pipe_kernel (rows staged through shared memory by cp.async.bulk, four rows in flight per warp):
+    row counts that leave the last ring slots of some warps empty, every column class, both output dtypes, row remap + row vector."""
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(rows, cols, generator=g) * 2 + 0.3 * torch.randn(rows, 1, generator=g)).bfloat16()
+    w, b = 1 + 0.1 * _rand(cols, seed=6), 0.1 * _rand(cols, seed=7)
+    od = torch.bfloat16 if out_dtype == "bf16" else torch.float32
+    want = R.layer_norm(x.float(), w, b)
+    tol = dict(rtol=2e-2, atol=2e-2) if out_dtype == "bf16" else dict(rtol=1e-4, atol=1e-4)
+    if remap:
+        gi, go = 16, 24                                   # rows of 16-row groups land in 24-row groups (the Q-Former -> fused-sequence scatter)
+        vec = _rand(cols, seed=8)
+        n_groups = rows // gi
+        rows = n_groups * gi
+        out = torch.zeros(n_groups * go, cols, dtype=od, device=DEV)
+        ops.layernorm(x[:rows].to(DEV), w.to(DEV), b.to(DEV), out, remap=(gi, go, 0), rowvec=vec.to(DEV), rows=rows, cols=cols)
+        got = out.view(n_groups, go, cols)
+        torch.testing.assert_close(got[:, :gi].float().cpu(), (want[:rows] + vec).view(n_groups, gi, cols), **tol)
+        assert bool((got[:, gi:] == 0).all())
+        return
+    out = torch.empty(rows, cols, dtype=od, device=DEV)
+    ops.layernorm(x.to(DEV), w.to(DEV), b.to(DEV), out)
+    torch.testing.assert_close(out.float().cpu(), want, **tol)
+
+
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 @pytest.mark.parametrize("nh,nkv,dh,theta", [(12, 12, 64, 10000.0), (4, 2, 32, 10000.0), (8, 2, 128, 500000.0)])
 def test_rope(ops, dtype, nh, nkv, dh, theta):
@@ -311,10 +338,10 @@ def test_embed_text_cast_rowvec(ops):
     torch.testing.assert_close(o2[:, :Q].cpu(), (x + tm).view(B, Q, H))
 
 
-def test_poly_embed_and_masked_mean(ops):
-    B, P, D = 4, 64, 64
+@pytest.mark.parametrize("B,P,D", [(4, 64, 64), (4, 48, 64), (4, 64, 6)])      # 16-byte path (D % 4 == 0, fp32 out) and the element-wise one
+def test_poly_embed_and_masked_mean(ops, B, P, D):
     poly = torch.rand(B, P, 2, generator=torch.Generator().manual_seed(1)) * 1000
-    lens = torch.tensor([0, 64, 1, 33], dtype=torch.int32)
+    lens = torch.tensor([0, P, 1, 33], dtype=torch.int32)
     w, b, pos = _rand(D, 2, seed=2, scale=0.01), _rand(D, seed=3), _rand(P, D, seed=4)
     out = torch.empty(B * P, D, device=DEV)
     km = torch.empty(B, P, dtype=torch.int32, device=DEV)

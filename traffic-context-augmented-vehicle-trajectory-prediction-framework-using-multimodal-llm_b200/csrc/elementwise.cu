@@ -182,6 +182,32 @@ __global__ void poly_embed_kernel(const float* __restrict__ poly, const int32_t*
   }
 }
 
+// fp32 output, D a multiple of 4: four features per thread — one 8-byte point load shared by the D / 4 threads of a point, 16-byte
+// weight / bias / position-table loads (L1-resident: 2D + D + P D floats), one 16-byte store.  The kernel is a pure 4 D-byte-per-point
+// write stream; the element-per-thread form above spent its time on 64-bit index arithmetic and 4-byte stores.
+__global__ void __launch_bounds__(256) poly_embed_vec_kernel(const float* __restrict__ poly, const int32_t* __restrict__ len, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, const float* __restrict__ pos, float* __restrict__ out,
+                                                             int32_t* __restrict__ key_mask, int B, int P, int D) {
+  const int dq = D >> 2;
+  const unsigned total = (unsigned)B * (unsigned)P * (unsigned)dq;      // the host checks B P D < 2^31
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned bp = i / (unsigned)dq;
+    const int d = (int)(i - bp * (unsigned)dq) << 2;
+    const int b = (int)(bp / (unsigned)P), p = (int)(bp - (unsigned)b * (unsigned)P);
+    const float2 pt = __ldg(reinterpret_cast<const float2*>(poly) + bp);
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + 2 * d)), w1 = __ldg(reinterpret_cast<const float4*>(w + 2 * d + 4));
+    const float4 bs = __ldg(reinterpret_cast<const float4*>(bias + d));
+    const float4 ps = __ldg(reinterpret_cast<const float4*>(pos + (size_t)p * D + d));
+    float4 o;      // same operation order as the scalar kernel: fma(wx, px, fma(wy, py, bias)) + pos
+    o.x = fmaf(w0.x, pt.x, fmaf(w0.y, pt.y, bs.x)) + ps.x;
+    o.y = fmaf(w0.z, pt.x, fmaf(w0.w, pt.y, bs.y)) + ps.y;
+    o.z = fmaf(w1.x, pt.x, fmaf(w1.y, pt.y, bs.z)) + ps.z;
+    o.w = fmaf(w1.z, pt.x, fmaf(w1.w, pt.y, bs.w)) + ps.w;
+    reinterpret_cast<float4*>(out)[i] = o;
+    if (d == 0 && key_mask) key_mask[bp] = p < __ldg(len + b);
+  }
+}
+
 __global__ void masked_mean_kernel(const void* __restrict__ x, int in_dtype, const int32_t* __restrict__ len, void* __restrict__ out,
                                    int out_dtype, int B, int P, int D) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -320,6 +346,13 @@ extern "C" int tcavp_poly_embed(const float* polygon, const int32_t* len, const 
   TCAVP_REQUIRE(B >= 0 && P > 0 && D > 0, "tcavp_poly_embed: bad shape");
   if (B == 0) return TCAVP_OK;
   TCAVP_REQUIRE(polygon && len && w && bias && pos && out && DT_OK(out_dtype), "tcavp_poly_embed: bad pointer/dtype");
+  auto al16 = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
+  if (out_dtype == TCAVP_F32 && D % 4 == 0 && (long long)B * P * D < (1ll << 31) && al16(w) && al16(bias) && al16(pos) && al16(out) &&
+      reinterpret_cast<uintptr_t>(polygon) % 8 == 0) {
+    poly_embed_vec_kernel<<<grid_for((long long)B * P * (D / 4), 256), 256, 0, STREAM(stream)>>>(polygon, len, w, bias, pos, reinterpret_cast<float*>(out),
+                                                                                              key_mask, B, P, D);
+    return check_launch("poly_embed_kernel");
+  }
   poly_embed_kernel<<<grid_for((long long)B * P * D, 256), 256, 0, STREAM(stream)>>>(polygon, len, w, bias, pos, out, out_dtype, key_mask, B, P, D);
   return check_launch("poly_embed_kernel");
 }

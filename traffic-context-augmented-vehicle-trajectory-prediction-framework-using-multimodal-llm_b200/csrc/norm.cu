@@ -179,6 +179,135 @@ __global__ void __launch_bounds__(256) layernorm_reg_kernel(const void* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over many bf16 rows (the 25 LayerNorm passes of a GPT-2-arch backbone at M = scenes x 144 rows): rows staged through shared
+// memory by the bulk-copy engine.  The register-resident kernel above keeps one row per warp in flight (1.5 KB at 768 columns, 32 warps
+// per SM at 56 registers = 48 KB per SM), which is latency-bound at ~2.9 TB/s; here every warp owns a ring of PIPE_STAGES row buffers
+// filled by cp.async.bulk (one elected lane, mbarrier complete_tx), so the bytes in flight per SM are the ring (8 warps x 4 rows x 1.5 KB
+// per block) and no longer cost registers.  Warps stride over the rows (persistent grid); statistics and the affine map are the same
+// fp32 arithmetic, in the same order, as layernorm_reg_kernel<32, NV>.
+// ------------------------------------------------------------------------------------------------
+namespace lnp {
+constexpr int PIPE_STAGES = 4, WARPS = 8;
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+}  // namespace lnp
+
+template <int NV>
+__global__ void __launch_bounds__(lnp::WARPS * 32) layernorm_pipe_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                                                                        const float* __restrict__ b, void* __restrict__ out, int rows, int cols,
+                                                                        float eps, int out_dtype, int gi, int go, int off,
+                                                                        const float* __restrict__ rowvec) {
+  using namespace lnp;
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t row_bytes = (uint32_t)cols * 2u;
+  const uint32_t ring = smem_u32(ln_smem) + (uint32_t)warp * PIPE_STAGES * row_bytes;
+  const uint32_t bars = smem_u32(ln_smem) + (uint32_t)WARPS * PIPE_STAGES * row_bytes + (uint32_t)warp * PIPE_STAGES * 8u;
+  const int wstride = gridDim.x * WARPS;
+  const int row0 = blockIdx.x * WARPS + warp;
+  if (lane == 0) {
+    for (int s = 0; s < PIPE_STAGES; ++s) mbar_init(bars + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  if (lane == 0) {      // prologue: the first PIPE_STAGES rows of this warp
+    for (int s = 0; s < PIPE_STAGES; ++s) {
+      const long long r = (long long)row0 + (long long)s * wstride;
+      if (r < rows) {
+        mbar_expect_tx(bars + 8 * s, row_bytes);
+        bulk_load(ring + s * row_bytes, x + (size_t)r * cols, row_bytes, bars + 8 * s);
+      }
+    }
+  }
+  int stage = 0;
+  uint32_t phase = 0;
+  for (long long row = row0; row < rows; row += wstride) {
+    mbar_wait(bars + 8 * stage, phase);
+    float v[NV][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      if (c < cols) {
+        uint4 u;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(ring + stage * row_bytes + c * 2));
+        const uint32_t q[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          v[i][2 * e] = __uint_as_float(q[e] << 16);
+          v[i][2 * e + 1] = __uint_as_float(q[e] & 0xffff0000u);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sum += v[i][e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[i][e] = 0.f;
+      }
+    }
+    // the row is in registers: hand the buffer back to the copy engine (every lane has read its part once the shuffle below has run;
+    // the refill is issued after the first reduction, which all lanes take part in)
+    sum = warp_sum(sum);
+    if (lane == 0) {
+      const long long nxt = row + (long long)PIPE_STAGES * wstride;
+      if (nxt < rows) {
+        mbar_expect_tx(bars + 8 * stage, row_bytes);
+        bulk_load(ring + stage * row_bytes, x + (size_t)nxt * cols, row_bytes, bars + 8 * stage);
+      }
+    }
+    const float mean = sum / cols;
+    float q2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if ((i * 32 + lane) * 8 < cols) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) q2 += (v[i][e] - mean) * (v[i][e] - mean);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q2) / cols + eps);
+    const size_t obase = (size_t)remap_row(gi, go, off, (int)row) * cols;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      if (c < cols) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + c)), w1 = __ldg(reinterpret_cast<const float4*>(w + c + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + c)), b1 = __ldg(reinterpret_cast<const float4*>(b + c + 4));
+        const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float o8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          o8[e] = (v[i][e] - mean) * rstd * ww[e] + bb[e];
+          if (rowvec) o8[e] += __ldg(rowvec + c + e);
+        }
+        store8(out, obase + c, out_dtype, o8);
+      }
+    }
+    if (++stage == PIPE_STAGES) { stage = 0; phase ^= 1; }
+  }
+}
+
 template <bool VEC>
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const void* __restrict__ x, const float* __restrict__ w,
                                                       void* __restrict__ out, int rows, int cols, int ldi, int ldo, float eps,
@@ -302,6 +431,30 @@ extern "C" int tcavp_layernorm(const void* x, const void* residual, const float*
   const int wpb = 8;
   const int grid = (rows + wpb - 1) / wpb;
   const bool wb_al = reinterpret_cast<uintptr_t>(w) % 16 == 0 && reinterpret_cast<uintptr_t>(b) % 16 == 0;
+  // many bf16 rows, no residual: rows staged through shared memory by the bulk-copy engine (see layernorm_pipe_kernel)
+  static int pipe_on = -1;
+  if (pipe_on < 0) {
+    const char* e = getenv("TCAVP_LN_PIPE");
+    pipe_on = e ? atoi(e) : 1;
+  }
+  if (pipe_on && vec && wb_al && !residual && in_dtype == TCAVP_BF16 && cols >= 256 && cols <= 1024 && rows >= 65536 &&
+      (!rowvec || reinterpret_cast<uintptr_t>(rowvec) % 4 == 0)) {
+    const size_t smem = (size_t)lnp::WARPS * lnp::PIPE_STAGES * ((size_t)cols * 2 + 8);
+    const int blocks_per_sm = (int)((200u << 10) / smem) > 4 ? 4 : (int)((200u << 10) / smem);
+    int grid_p = sm_count() * (blocks_per_sm < 1 ? 1 : blocks_per_sm);
+    if (grid_p > (rows + lnp::WARPS - 1) / lnp::WARPS) grid_p = (rows + lnp::WARPS - 1) / lnp::WARPS;
+#define TCAVP_LN_PIPE(NV)                                                                                                              \
+  do {                                                                                                                                 \
+    TCAVP_CUDA(cudaFuncSetAttribute(layernorm_pipe_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+    layernorm_pipe_kernel<NV><<<grid_p, lnp::WARPS * 32, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), w, b, out, rows, cols, eps, \
+                                                                         out_dtype, remap_gi, remap_go, remap_off, rowvec);            \
+  } while (0)
+    if (cols <= 512) TCAVP_LN_PIPE(2);
+    else if (cols <= 768) TCAVP_LN_PIPE(3);
+    else TCAVP_LN_PIPE(4);
+#undef TCAVP_LN_PIPE
+    return check_launch("layernorm_kernel");
+  }
   if (vec && wb_al && cols <= 1024) {
 #define TCAVP_LN_REG(G, NV)                                                                                                         \
   do {                                                                                                                              \
