@@ -164,6 +164,11 @@ int tcavp_attention(const tcavp_attn_args* args, tcavp_stream_t stream);
 int tcavp_layernorm(const void* x, const void* residual, const float* w, const float* b, void* out, int rows, int cols,
                     float eps, int in_dtype, int out_dtype, int remap_gi, int remap_go, int remap_off,
                     const float* rowvec, tcavp_stream_t stream);
+/* The same LayerNorm (no residual) with explicit row strides: out may be the leading columns of a wider operand — the GPT-2-arch path
+ * writes ln_1(x) straight into the K-extended [ln_1(x) | LoRA side columns] operand of the fused c_attn GEMM (HF modeling_gpt2.py
+ * GPT2Block.forward: ln_1 -> attn), which saves the copy into it.  bf16 rows of 256..1024 columns go through the bulk-copy ring. */
+int tcavp_layernorm_strided(const void* x, int ldx, const float* w, const float* b, void* out, int ldo, int rows, int cols, float eps,
+                            int in_dtype, int out_dtype, tcavp_stream_t stream);
 /* out[r,:] = w * (x[r,:] * rsqrt(mean(x^2) + eps))          (HF:53-70 LlamaRMSNorm).  ldi / ldo are the row strides of
  * x / out in elements (the residual stream lives in K-extended rows that also carry the LoRA side columns). */
 int tcavp_rmsnorm(const void* x, int ldi, const float* w, void* out, int rows, int cols, int ldo, float eps, int in_dtype,

@@ -268,6 +268,21 @@ def test_layernorm_remap_rowvec(ops):
     assert (fused[:, Q:] == 0).all()
 
 
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("rows,cols,ldo", [(1000, 768, 776), (37, 128, 136), (300, 512, 512), (9, 40, 44), (5000, 1024, 1040)])
+def test_layernorm_strided(ops, dtype, rows, cols, ldo):
+    """LayerNorm written into the leading columns of a wider operand (GPT-2 path: ln_1(x) -> [ln_1(x) | LoRA side columns]): the bulk-copy
+    kernel (bf16, 256..1024 columns) and the element-wise one; the columns past `cols` are left alone."""
+    td = torch.float32 if dtype == "fp32" else torch.bfloat16
+    x = (_rand(rows, cols, seed=21) * 1.5 + 0.2).to(td)
+    w, b = 1 + 0.1 * _rand(cols, seed=22), 0.1 * _rand(cols, seed=23)
+    out = torch.full((rows, ldo), 5.0, dtype=td, device=DEV)
+    ops.layernorm_strided(x.to(DEV), w.to(DEV), b.to(DEV), out, rows=rows, cols=cols, eps=1e-5, ldo=ldo)
+    tol = dict(rtol=1e-4, atol=1e-4) if dtype == "fp32" else dict(rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(out[:, :cols].float().cpu(), R.layer_norm(x.float(), w, b), **tol)
+    assert bool((out[:, cols:] == 5.0).all())
+
+
 @pytest.mark.parametrize("rows,cols,out_dtype,remap", [(65536 + 37, 768, "bf16", False), (70001, 512, "fp32", False), (65536, 1024, "bf16", False),
                                                        (66000, 256, "bf16", True)])
 def test_layernorm_many_bf16_rows_through_the_bulk_copy_ring(ops, rows, cols, out_dtype, remap):

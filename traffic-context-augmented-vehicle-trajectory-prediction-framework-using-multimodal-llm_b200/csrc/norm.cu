@@ -218,7 +218,7 @@ template <int NV>
 __global__ void __launch_bounds__(lnp::WARPS * 32) layernorm_pipe_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                                                                         const float* __restrict__ b, void* __restrict__ out, int rows, int cols,
                                                                         float eps, int out_dtype, int gi, int go, int off,
-                                                                        const float* __restrict__ rowvec) {
+                                                                        const float* __restrict__ rowvec, int ldo) {
   using namespace lnp;
   extern __shared__ __align__(128) uint8_t ln_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(lnp::WARPS * 32) layernorm_pipe_kernel(const _
       }
     }
     const float rstd = rsqrtf(warp_sum(q2) / cols + eps);
-    const size_t obase = (size_t)remap_row(gi, go, off, (int)row) * cols;
+    const size_t obase = (size_t)remap_row(gi, go, off, (int)row) * ldo;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 8;
@@ -306,6 +306,27 @@ __global__ void __launch_bounds__(lnp::WARPS * 32) layernorm_pipe_kernel(const _
     }
     if (++stage == PIPE_STAGES) { stage = 0; phase ^= 1; }
   }
+}
+
+// Row-strided LayerNorm for shapes outside the bulk-copy kernel (narrow / unaligned rows, fp32): warp per row, element-wise.
+__global__ void __launch_bounds__(256) layernorm_strided_kernel(const void* __restrict__ x, int ldx, const float* __restrict__ w,
+                                                                const float* __restrict__ b, void* __restrict__ out, int ldo, int rows, int cols,
+                                                                float eps, int in_dtype, int out_dtype) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const size_t base = (size_t)row * ldx, obase = (size_t)row * ldo;
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) s += load_as_f(x, base + c, in_dtype);
+  const float mean = warp_sum(s) / cols;
+  float q = 0.f;
+  for (int c = lane; c < cols; c += 32) {
+    const float d = load_as_f(x, base + c, in_dtype) - mean;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / cols + eps);
+  for (int c = lane; c < cols; c += 32)
+    store_from_f(out, obase + c, out_dtype, (load_as_f(x, base + c, in_dtype) - mean) * rstd * __ldg(w + c) + __ldg(b + c));
 }
 
 template <bool VEC>
@@ -447,7 +468,7 @@ extern "C" int tcavp_layernorm(const void* x, const void* residual, const float*
   do {                                                                                                                                 \
     TCAVP_CUDA(cudaFuncSetAttribute(layernorm_pipe_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
     layernorm_pipe_kernel<NV><<<grid_p, lnp::WARPS * 32, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), w, b, out, rows, cols, eps, \
-                                                                         out_dtype, remap_gi, remap_go, remap_off, rowvec);            \
+                                                                         out_dtype, remap_gi, remap_go, remap_off, rowvec, cols);      \
   } while (0)
     if (cols <= 512) TCAVP_LN_PIPE(2);
     else if (cols <= 768) TCAVP_LN_PIPE(3);
@@ -473,6 +494,38 @@ extern "C" int tcavp_layernorm(const void* x, const void* residual, const float*
     layernorm_kernel<true><<<grid, wpb * 32, 0, stream>>>(x, residual, w, b, out, rows, cols, eps, in_dtype, out_dtype, remap_gi, remap_go, remap_off, rowvec);
   else
     layernorm_kernel<false><<<grid, wpb * 32, 0, stream>>>(x, residual, w, b, out, rows, cols, eps, in_dtype, out_dtype, remap_gi, remap_go, remap_off, rowvec);
+  return check_launch("layernorm_kernel");
+}
+
+extern "C" int tcavp_layernorm_strided(const void* x, int ldx, const float* w, const float* b, void* out, int ldo, int rows, int cols, float eps,
+                                       int in_dtype, int out_dtype, tcavp_stream_t stream_) {
+  using namespace tcavp;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  TCAVP_REQUIRE(rows >= 0 && cols > 0 && ldx >= cols && ldo >= cols, "tcavp_layernorm_strided: bad shape rows=%d cols=%d ldx=%d ldo=%d", rows, cols, ldx, ldo);
+  if (rows == 0) return TCAVP_OK;
+  TCAVP_REQUIRE(x && w && b && out, "tcavp_layernorm_strided: null pointer");
+  TCAVP_REQUIRE((in_dtype | 1) == 1 && (out_dtype | 1) == 1, "tcavp_layernorm_strided: bad dtype");
+  const size_t osz = out_dtype == TCAVP_BF16 ? 2 : 4;
+  auto al = [](const void* p, size_t a) { return reinterpret_cast<uintptr_t>(p) % a == 0; };
+  if (in_dtype == TCAVP_BF16 && ldx == cols && cols % 8 == 0 && cols >= 256 && cols <= 1024 && al(x, 16) && al(w, 16) && al(b, 16) &&
+      al(out, 8 * osz) && ((size_t)ldo * osz) % (8 * osz) == 0) {
+    const size_t smem = (size_t)lnp::WARPS * lnp::PIPE_STAGES * ((size_t)cols * 2 + 8);
+    const int bps = (int)((200u << 10) / smem) > 4 ? 4 : (int)((200u << 10) / smem);
+    int grid_p = sm_count() * (bps < 1 ? 1 : bps);
+    if (grid_p > (rows + lnp::WARPS - 1) / lnp::WARPS) grid_p = (rows + lnp::WARPS - 1) / lnp::WARPS;
+#define TCAVP_LN_PIPE(NV)                                                                                                              \
+  do {                                                                                                                                 \
+    TCAVP_CUDA(cudaFuncSetAttribute(layernorm_pipe_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+    layernorm_pipe_kernel<NV><<<grid_p, lnp::WARPS * 32, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), w, b, out, rows, cols, eps, \
+                                                                         out_dtype, 0, 0, 0, nullptr, ldo);                            \
+  } while (0)
+    if (cols <= 512) TCAVP_LN_PIPE(2);
+    else if (cols <= 768) TCAVP_LN_PIPE(3);
+    else TCAVP_LN_PIPE(4);
+#undef TCAVP_LN_PIPE
+    return check_launch("layernorm_kernel");
+  }
+  layernorm_strided_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, ldx, w, b, out, ldo, rows, cols, eps, in_dtype, out_dtype);
   return check_launch("layernorm_kernel");
 }
 

@@ -165,12 +165,12 @@ class Engine:
         h = self._new(M, H)
         qkv, attn, mid = self._new(M, 3 * H), self._new(M, H), self._new(M, I)
         for ly in m["layers"]:
-            ops.layernorm(x, ly["ln1"][0], ly["ln1"][1], h, eps=ly["ln1"][2])
-            if kx:
-                ops.cast(h, xs, rows=M, cols=H, ldi=H, ldo=Kx)
+            if kx:      # ln_1(x) lands directly in the leading columns of the K-extended operand
+                ops.layernorm_strided(x, ly["ln1"][0], ly["ln1"][1], xs, rows=M, cols=H, eps=ly["ln1"][2], ldo=Kx)
                 ops.gemm(xs, ly["a_cat"], xs[:, H:], M=M, N=m["n_lora"], K=H, lda=Kx, ldo=Kx)
                 ops.gemm(xs, ly["wqkv"], qkv, M=M, N=3 * H, K=Kx, lda=Kx, bias=ly["bqkv"])
             else:
+                ops.layernorm(x, ly["ln1"][0], ly["ln1"][1], h, eps=ly["ln1"][2])
                 ops.gemm(h, ly["wqkv"], qkv, bias=ly["bqkv"])
             ops.attention(qkv, qkv[:, H:], qkv[:, 2 * H:], attn, B=B, H=nh, Hkv=nh, Tq=L, Tk=L, dh=dh, q_strides=(L * 3 * H, 3 * H),
                           k_strides=(L * 3 * H, 3 * H), v_strides=(L * 3 * H, 3 * H), o_strides=(L * H, H), scale=dh ** -0.5, causal=True,

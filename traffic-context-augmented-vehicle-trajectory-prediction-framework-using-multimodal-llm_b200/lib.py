@@ -25,7 +25,7 @@ EXPORTS = [
     "tcavp_transpose", "tcavp_period_sum", "tcavp_relu_bwd", "tcavp_axpby", "tcavp_swiglu", "tcavp_swiglu_bwd", "tcavp_layernorm_bwd",
     "tcavp_rmsnorm_bwd", "tcavp_rope_adjacent", "tcavp_copy_rows", "tcavp_masked_mean_bwd", "tcavp_nlinear_bwd", "tcavp_head_assemble",
     "tcavp_traj_loss_bwd", "tcavp_skinny_dw", "tcavp_dw", "tcavp_attention_bwd", "tcavp_attention_bwd_owned", "tcavp_adamw",
-    "tcavp_lora_a_drop", "tcavp_lora_dx_drop", "tcavp_lora_da_drop", "tcavp_ce_loss", "tcavp_gelu_tanh", "tcavp_gelu_tanh_bwd", "tcavp_layernorm_bwd_dx",
+    "tcavp_lora_a_drop", "tcavp_lora_dx_drop", "tcavp_lora_da_drop", "tcavp_ce_loss", "tcavp_gelu_tanh", "tcavp_gelu_tanh_bwd", "tcavp_layernorm_bwd_dx", "tcavp_layernorm_strided",
 ]
 
 

@@ -325,6 +325,15 @@ def layernorm(x, w, b, out, *, residual=None, eps=1e-5, remap=(0, 0, 0), rowvec=
     return out
 
 
+def layernorm_strided(x, w, b, out, *, rows, cols, eps=1e-5, ldx=None, ldo=None):
+    """LayerNorm (no residual) with row strides: `out` may be the leading columns of a wider buffer."""
+    _need_cuda(x, w, b, out)
+    with _Timed("layernorm_kernel", 0.0, float(rows * cols * (x.element_size() + out.element_size()))):
+        _lib.check(_lib.load().tcavp_layernorm_strided(_p(x), cols if ldx is None else ldx, _p(w), _p(b), _p(out), cols if ldo is None else ldo, rows, cols,
+                                                       c_float(eps), dt(x), dt(out), _stream()), "tcavp_layernorm_strided")
+    return out
+
+
 def rmsnorm(x, w, out, *, eps, rows=None, cols=None, ldi=None, ldo=None):
     _need_cuda(x, w, out)
     rows = x.numel() // x.shape[-1] if rows is None else rows

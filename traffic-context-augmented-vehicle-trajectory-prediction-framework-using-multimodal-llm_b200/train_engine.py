@@ -574,23 +574,22 @@ class TrainEngine(Engine):
         sq = (L * 3 * H, 3 * H)
         ctxs, xm = [], None
         for li, ly in enumerate(m["layers"]):
-            h1 = ops.layernorm(x, ly["ln1"][0], ly["ln1"][1], self._new(M, H), eps=ly["ln1"][2])
-            if kx:
+            if kx:      # ln_1(x) lands directly in the leading columns of the K-extended operand [ln_1(x) | LoRA side columns]
                 xs = torch.zeros(M, Kx, dtype=self.act, device=self.dev) if kx != m["n_lora"] else self._new(M, Kx)
-                ops.cast(h1, xs, rows=M, cols=H, ldi=H, ldo=Kx)
+                ops.layernorm_strided(x, ly["ln1"][0], ly["ln1"][1], xs, rows=M, cols=H, eps=ly["ln1"][2], ldo=Kx)
                 drops = self._lora_drops(li)
                 if drops and "a_cat_s" in ly:
                     ops.lora_a_drop(xs, ly["a_cat_s"], xs[:, H:], drops, M=M, H=H, r=m["r"], ldx=Kx, ldo=Kx)
                 elif drops:      # peft: lora_A(dropout(ln_1(x))) — masked copy (exact: x or 0), 1 / (1 - p) rides on the weight
                     xm = self._new(M, H) if xm is None else xm
-                    ops.dropout(h1, xm, drops[0], rows=M, cols=H, scale=1.0)
+                    ops.dropout(xs, xm, drops[0], rows=M, cols=H, ldi=Kx, ldo=H, scale=1.0)
                     ops.gemm(xm, ly["a_cat_d"], xs[:, H:], M=M, N=m["n_lora"], K=H, ldo=Kx)
                 else:
-                    ops.gemm(h1, ly["a_cat"], xs[:, H:], M=M, N=m["n_lora"], K=H, ldo=Kx)
+                    ops.gemm(xs, ly["a_cat"], xs[:, H:], M=M, N=m["n_lora"], K=H, lda=Kx, ldo=Kx)
                 qkv = ops.gemm(xs, ly["wqkv"], self._new(M, 3 * H), M=M, N=3 * H, K=Kx, lda=Kx, bias=ly["bqkv"])
             else:
-                xs = h1
-                qkv = ops.gemm(h1, ly["wqkv"], self._new(M, 3 * H), bias=ly["bqkv"])
+                xs = ops.layernorm(x, ly["ln1"][0], ly["ln1"][1], self._new(M, H), eps=ly["ln1"][2])
+                qkv = ops.gemm(xs, ly["wqkv"], self._new(M, 3 * H), bias=ly["bqkv"])
             attn = self._new(M, H)
             ops.attention(qkv, qkv[:, H:], qkv[:, 2 * H:], attn, B=B, H=nh, Hkv=nh, Tq=L, Tk=L, dh=dh, q_strides=sq, k_strides=sq, v_strides=sq,
                           o_strides=(L * H, H), scale=dh ** -0.5, causal=True, key_mask=mask)
