@@ -175,6 +175,32 @@ def test_rmsnorm_bwd(ops, dtype, unit_w):
     torch.testing.assert_close(dx.cpu().float(), x.grad + add.float(), **_tol(dtype))
 
 
+@pytest.mark.parametrize("kind", ["rms", "rms_unit_w", "ln"])
+@pytest.mark.parametrize("rows,cols,ldx,with_add", [(32768 + 19, 768, 784, True), (33000, 512, 512, False), (32768, 1024, 1024, True), (40001, 256, 264, True)])
+def test_norm_backward_over_many_bf16_rows_through_the_bulk_copy_ring(ops, kind, rows, cols, ldx, with_add):
+    """>= 32768 bf16 rows: RMSNorm backward and the dX-only LayerNorm backward run through norm_bwd_pipe_kernel (rows of x / dy / add
+    staged by cp.async.bulk, three row triples in flight per warp) — against autograd, with a padded x stride (the K-extended operand
+    of the Llama path), row counts that leave ring slots empty, with and without the residual-branch gradient."""
+    g = torch.Generator().manual_seed(31)
+    xb = torch.zeros(rows, ldx)
+    xb[:, :cols] = torch.randn(rows, cols, generator=g) * 1.5 + 0.25 * torch.randn(rows, 1, generator=g)
+    xb = xb.bfloat16()
+    x = xb[:, :cols].float().requires_grad_(True)
+    w = torch.ones(cols) if kind == "rms_unit_w" else 1.0 + 0.1 * _rand(cols, seed=32)
+    y = torch.nn.functional.layer_norm(x, (cols,), w, 0.1 * _rand(cols, seed=33), 1e-5) if kind == "ln" else R.rms_norm(x, w, 1e-6)
+    dy = torch.randn(rows, cols, generator=g).bfloat16()
+    y.backward(dy.float())
+    add = torch.randn(rows, cols, generator=g).bfloat16() if with_add else None
+    want = x.grad + (add.float() if with_add else 0.0)
+    dx = torch.empty(rows, cols, dtype=torch.bfloat16, device=DEV)
+    if kind == "ln":
+        ops.layernorm_bwd_dx(dy.to(DEV), xb.to(DEV), w.to(DEV), dx, rows=rows, cols=cols, eps=1e-5, add=add.to(DEV) if with_add else None, ldx=ldx)
+    else:
+        ops.rmsnorm_bwd(dy.to(DEV), xb.to(DEV), dx, rows=rows, cols=cols, eps=1e-6, w=None if kind == "rms_unit_w" else w.to(DEV),
+                        add=add.to(DEV) if with_add else None, ldx=ldx)
+    torch.testing.assert_close(dx.cpu().float(), want, rtol=2e-2, atol=3e-2)
+
+
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 def test_rope_adjacent_matches_fused_gemm_layout_and_inverts(ops, dtype):
     td = _td(dtype)

@@ -37,6 +37,15 @@ for rows, cols in ((147456, 768), (73728, 768), (147456, 512), (147456, 1024)):
     c = torch.empty_like(x)
     us = timed(lambda: ops.cast(x, c, rows=rows, cols=cols))
     print(f"   (copy of the same bytes: {us:7.1f} us  {rows * cols * 4 / us / 1e3:7.0f} GB/s)", flush=True)
+print("TCAVP_NORM_BWD_PIPE =", os.environ.get("TCAVP_NORM_BWD_PIPE", "1"))
+for rows, cols, ld in ((73728, 768, 784), (73728, 768, 768)):
+    x = torch.randn(rows, ld, device=dev).bfloat16()
+    dy, add, dx = (torch.randn(rows, cols, device=dev).bfloat16() for _ in range(3))
+    w = torch.ones(cols, device=dev)
+    us = timed(lambda: ops.rmsnorm_bwd(dy, x, dx, rows=rows, cols=cols, eps=1e-6, add=add, ldx=ld))
+    print(f"rmsnorm_bwd {rows} x {cols} (ldx {ld}) bf16, 4 streams: {us:7.1f} us  {rows * cols * 8 / us / 1e3:7.0f} GB/s", flush=True)
+    us = timed(lambda: ops.layernorm_bwd_dx(dy, x, w, dx, rows=rows, cols=cols, eps=1e-5, add=add, ldx=ld))
+    print(f"layernorm_bwd_dx {rows} x {cols} (ldx {ld}) bf16, 4 streams: {us:7.1f} us  {rows * cols * 8 / us / 1e3:7.0f} GB/s", flush=True)
 B, P, D = 4096, 48, 64
 poly = torch.rand(B, P, 2, device=dev) * 1000
 lens = torch.full((B,), 40, dtype=torch.int32, device=dev)

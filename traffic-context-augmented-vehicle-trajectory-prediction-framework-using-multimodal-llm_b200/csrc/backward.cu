@@ -665,6 +665,183 @@ __global__ void __launch_bounds__(256) layernorm_bwd_dx_kernel(const void* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// RMSNorm / frozen-LayerNorm backward over a long bf16 token stream, rows staged through shared memory by the bulk-copy engine (the
+// scheme of layernorm_pipe_kernel in norm.cu): every warp owns a three-deep ring of (x, dy[, add]) row triples filled by cp.async.bulk
+// + mbarrier complete_tx, so the bytes in flight per SM are the rings of 16 resident warps (~220 KB) instead of what the registers of
+// the *_vec kernels hold (~70 KB: they were latency-bound at 2.8 TB/s).  Same formulas as rmsnorm_bwd_vec_kernel /
+// layernorm_bwd_dx_vec_kernel.
+// ------------------------------------------------------------------------------------------------
+namespace nbp {
+constexpr int STAGES = 3, WARPS = 8;      // ~100 registers per thread: two blocks per SM, 2 x 8 x 3 row triples in flight
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void lds8_bf16(uint32_t addr, float (&v)[8]) {
+  uint32_t q[4];
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]) : "r"(addr));
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    v[2 * e] = __uint_as_float(q[e] << 16);
+    v[2 * e + 1] = __uint_as_float(q[e] & 0xffff0000u);
+  }
+}
+}  // namespace nbp
+
+template <int NV, bool LN>
+__global__ void __launch_bounds__(nbp::WARPS * 32) norm_bwd_pipe_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, const __nv_bfloat16* __restrict__ x,
+                                                                       int ldx, const float* __restrict__ w, const __nv_bfloat16* __restrict__ add,
+                                                                       int ldadd, __nv_bfloat16* __restrict__ dx, int lddx, int rows, int cols, float eps) {
+  using namespace nbp;
+  extern __shared__ __align__(128) uint8_t nb_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t row_bytes = (uint32_t)cols * 2u;
+  const uint32_t n_in = add ? 3u : 2u;
+  const uint32_t stage_bytes = 3u * row_bytes;
+  const uint32_t ring = smem_u32(nb_smem) + (uint32_t)warp * STAGES * stage_bytes;
+  const uint32_t bars = smem_u32(nb_smem) + (uint32_t)WARPS * STAGES * stage_bytes + (uint32_t)warp * STAGES * 8u;
+  const int wstride = gridDim.x * WARPS;
+  const int row0 = blockIdx.x * WARPS + warp;
+  auto issue = [&](long long r, int s) {      // lane 0 only
+    const uint32_t dst = ring + s * stage_bytes, bar = bars + 8 * s;
+    mbar_expect_tx(bar, n_in * row_bytes);
+    bulk_load(dst, x + (size_t)r * ldx, row_bytes, bar);
+    bulk_load(dst + row_bytes, dy + (size_t)r * lddy, row_bytes, bar);
+    if (add) bulk_load(dst + 2 * row_bytes, add + (size_t)r * ldadd, row_bytes, bar);
+  };
+  if (lane == 0) {
+    for (int s = 0; s < STAGES; ++s) mbar_init(bars + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      const long long r = (long long)row0 + (long long)s * wstride;
+      if (r < rows) issue(r, s);
+    }
+  }
+  __syncwarp();
+  int stage = 0;
+  uint32_t phase = 0;
+  for (long long row = row0; row < rows; row += wstride) {
+    mbar_wait(bars + 8 * stage, phase);
+    const uint32_t sx = ring + stage * stage_bytes, sg = sx + row_bytes, sa = sg + row_bytes;
+    float xv[NV][8], gv[NV][8];
+    float a0 = 0.f, a1 = 0.f;      // RMSNorm: sum x^2, sum g x;   LayerNorm: sum x, sum g
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      if (c < cols) {
+        lds8_bf16(sx + c * 2, xv[i]);
+        lds8_bf16(sg + c * 2, gv[i]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          if (w) gv[i][e] *= __ldg(w + c + e);
+          if (LN) {
+            a0 += xv[i][e];
+            a1 += gv[i][e];
+          } else {
+            a0 += xv[i][e] * xv[i][e];
+            a1 += gv[i][e] * xv[i][e];
+          }
+        }
+      }
+    }
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    float rstd, s1 = 0.f, s2;
+    if (LN) {
+      const float mean = a0 / cols;
+      float q = 0.f, dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if ((i * 32 + lane) * 8 < cols) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            xv[i][e] -= mean;
+            q += xv[i][e] * xv[i][e];
+            dot += gv[i][e] * xv[i][e];
+          }
+        }
+      }
+      rstd = rsqrtf(warp_sum(q) / cols + eps);
+      s1 = a1 / cols;
+      s2 = warp_sum(dot) * rstd / cols;
+    } else {
+      rstd = rsqrtf(a0 / cols + eps);
+      s2 = a1 * rstd / cols;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      if (c < cols) {
+        float o[8], ad[8];
+        if (add) lds8_bf16(sa + c * 2, ad);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = rstd * (gv[i][e] - s1 - xv[i][e] * rstd * s2) + (add ? ad[e] : 0.f);
+        st8_bf16(dx + (size_t)row * lddx + c, o);
+      }
+    }
+    __syncwarp();                 // every lane has read its part of the stage: hand it back to the copy engine
+    if (lane == 0) {
+      const long long nxt = row + (long long)STAGES * wstride;
+      if (nxt < rows) issue(nxt, stage);
+    }
+    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+  }
+}
+
+// host side: 1 = launched, 0 = not eligible
+template <bool LN>
+static int norm_bwd_pipe_launch(const void* dy, int lddy, const void* x, int ldx, const float* w, const void* add, int ldadd, void* dx, int lddx,
+                                int dtype, int rows, int cols, float eps, cudaStream_t stream) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("TCAVP_NORM_BWD_PIPE");
+    on = e ? atoi(e) : 1;
+  }
+  auto al = [](const void* p, int ld) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % 16 == 0 && ld % 8 == 0); };
+  if (!on || dtype != TCAVP_BF16 || cols % 8 || cols < 256 || cols > 1024 || rows < 32768 || !al(dy, lddy) || !al(x, ldx) || !al(add, ldadd) ||
+      !al(dx, lddx) || (LN && !w))
+    return 0;
+  const size_t smem = (size_t)nbp::WARPS * nbp::STAGES * ((size_t)cols * 6 + 8);
+  int bps = (int)((220u << 10) / (smem + 1024));
+  bps = bps > 2 ? 2 : (bps < 1 ? 1 : bps);
+  int grid = sm_count() * bps;
+  if (grid > (rows + nbp::WARPS - 1) / nbp::WARPS) grid = (rows + nbp::WARPS - 1) / nbp::WARPS;
+  const __nv_bfloat16* dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
+  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
+  const __nv_bfloat16* ab = reinterpret_cast<const __nv_bfloat16*>(add);
+  __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(dx);
+#define TCAVP_NBP(NV)                                                                                                            \
+  do {                                                                                                                           \
+    if (cudaFuncSetAttribute(norm_bwd_pipe_kernel<NV, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0; \
+    norm_bwd_pipe_kernel<NV, LN><<<grid, nbp::WARPS * 32, smem, stream>>>(dyb, lddy, xb, ldx, w, ab, ldadd, ob, lddx, rows, cols, eps);       \
+  } while (0)
+  if (cols <= 512) TCAVP_NBP(2);
+  else if (cols <= 768) TCAVP_NBP(3);
+  else TCAVP_NBP(4);
+#undef TCAVP_NBP
+  return 1;
+}
+
 namespace ab {
 constexpr int QB = 16;
 constexpr int THREADS = 256;
@@ -979,6 +1156,8 @@ extern "C" int tcavp_layernorm_bwd_dx(const void* dy, int lddy, const void* x, i
   TCAVP_REQUIRE(rows >= 0 && cols > 0 && lddy >= cols && ldx >= cols && lddx >= cols && (!add || ldadd >= cols), "tcavp_layernorm_bwd_dx: bad shape");
   if (rows == 0) return TCAVP_OK;
   TCAVP_REQUIRE(dy && x && w && dx && DT_OK(dtype), "tcavp_layernorm_bwd_dx: bad pointer/dtype");
+  if (norm_bwd_pipe_launch<true>(dy, lddy, x, ldx, w, add, ldadd, dx, lddx, dtype, rows, cols, eps, STREAM(stream)))
+    return check_launch("layernorm_bwd_dx_kernel");
   auto al = [](const void* p, int ld) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % 16 == 0 && ld % 8 == 0); };
   if (dtype == TCAVP_BF16 && cols % 8 == 0 && cols <= 1024 && al(dy, lddy) && al(x, ldx) && al(add, ldadd) && al(dx, lddx)) {
     const __nv_bfloat16* dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
@@ -1003,6 +1182,8 @@ extern "C" int tcavp_rmsnorm_bwd(const void* dy, int lddy, const void* x, int ld
   TCAVP_REQUIRE(rows >= 0 && cols > 0, "tcavp_rmsnorm_bwd: bad shape");
   if (rows == 0) return TCAVP_OK;
   TCAVP_REQUIRE(dy && x && dx && DT_OK(dtype), "tcavp_rmsnorm_bwd: bad pointer/dtype");
+  if (norm_bwd_pipe_launch<false>(dy, lddy, x, ldx, w, add, ldadd, dx, lddx, dtype, rows, cols, eps, STREAM(stream)))
+    return check_launch("rmsnorm_bwd_kernel");
   auto al = [](const void* p, int ld) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % 16 == 0 && ld % 8 == 0); };
   if (dtype == TCAVP_BF16 && cols % 8 == 0 && al(dy, lddy) && al(x, ldx) && al(add, ldadd) && al(dx, lddx)) {
     const __nv_bfloat16* dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
