@@ -738,6 +738,16 @@ __global__ void __launch_bounds__(nbp::WARPS * 32) norm_bwd_pipe_kernel(const __
     }
   }
   __syncwarp();
+  // LayerNorm: this lane's slice of the weight lives in registers for the whole kernel (per-row loads made the kernel L1TEX-bound)
+  float wr[LN ? NV : 1][8];
+  if (LN) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) wr[LN ? i : 0][e] = c < cols ? __ldg(w + c + e) : 0.f;
+    }
+  }
   int stage = 0;
   uint32_t phase = 0;
   for (long long row = row0; row < rows; row += wstride) {
@@ -753,7 +763,8 @@ __global__ void __launch_bounds__(nbp::WARPS * 32) norm_bwd_pipe_kernel(const __
         lds8_bf16(sg + c * 2, gv[i]);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          if (w) gv[i][e] *= __ldg(w + c + e);
+          if (LN) gv[i][e] *= wr[LN ? i : 0][e];
+          else if (w) gv[i][e] *= __ldg(w + c + e);
           if (LN) {
             a0 += xv[i][e];
             a1 += gv[i][e];

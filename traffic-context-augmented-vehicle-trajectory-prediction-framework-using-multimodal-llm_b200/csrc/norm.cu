@@ -183,12 +183,13 @@ __global__ void __launch_bounds__(256) layernorm_reg_kernel(const void* __restri
 // LayerNorm over many bf16 rows (the 25 LayerNorm passes of a GPT-2-arch backbone at M = scenes x 144 rows): rows staged through shared
 // memory by the bulk-copy engine.  The register-resident kernel above keeps one row per warp in flight (1.5 KB at 768 columns, 32 warps
 // per SM at 56 registers = 48 KB per SM), which is latency-bound at ~2.9 TB/s; here every warp owns a ring of PIPE_STAGES row buffers
-// filled by cp.async.bulk (one elected lane, mbarrier complete_tx), so the bytes in flight per SM are the ring (8 warps x 4 rows x 1.5 KB
-// per block) and no longer cost registers.  Warps stride over the rows (persistent grid); statistics and the affine map are the same
+// filled by cp.async.bulk (one elected lane, mbarrier complete_tx), so the bytes in flight per SM are the ring (8 warps x 8 rows x 1.5 KB
+// per block, two blocks per SM) and no longer cost registers.  Warps stride over the rows (persistent grid); statistics and the affine map are the same
 // fp32 arithmetic, in the same order, as layernorm_reg_kernel<32, NV>.
 // ------------------------------------------------------------------------------------------------
 namespace lnp {
-constexpr int PIPE_STAGES = 4, WARPS = 8;
+constexpr int MAX_STAGES = 8, WARPS = 8;
+__host__ __device__ inline int stages_for(int cols) { return cols <= 768 ? 8 : 6; }      // ~98 KB of ring per block: two blocks per SM
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -215,7 +216,7 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
 }  // namespace lnp
 
 template <int NV>
-__global__ void __launch_bounds__(lnp::WARPS * 32) layernorm_pipe_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(lnp::WARPS * 32, 2) layernorm_pipe_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                                                                         const float* __restrict__ b, void* __restrict__ out, int rows, int cols,
                                                                         float eps, int out_dtype, int gi, int go, int off,
                                                                         const float* __restrict__ rowvec, int ldo) {
@@ -223,6 +224,7 @@ __global__ void __launch_bounds__(lnp::WARPS * 32) layernorm_pipe_kernel(const _
   extern __shared__ __align__(128) uint8_t ln_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t row_bytes = (uint32_t)cols * 2u;
+  const int PIPE_STAGES = stages_for(cols);
   const uint32_t ring = smem_u32(ln_smem) + (uint32_t)warp * PIPE_STAGES * row_bytes;
   const uint32_t bars = smem_u32(ln_smem) + (uint32_t)WARPS * PIPE_STAGES * row_bytes + (uint32_t)warp * PIPE_STAGES * 8u;
   const int wstride = gridDim.x * WARPS;
@@ -239,6 +241,18 @@ __global__ void __launch_bounds__(lnp::WARPS * 32) layernorm_pipe_kernel(const _
         mbar_expect_tx(bars + 8 * s, row_bytes);
         bulk_load(ring + s * row_bytes, x + (size_t)r * cols, row_bytes, bars + 8 * s);
       }
+    }
+  }
+  // a lane handles the same columns of every row: its slice of the affine parameters lives in registers for the whole kernel (loaded
+  // per row they were 4x the row's own bytes through L1TEX: ncu showed l1tex 86 % busy against 45 % DRAM)
+  float wr[NV][8], br[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      wr[i][e] = c < cols ? __ldg(w + c + e) : 0.f;
+      br[i][e] = c < cols ? __ldg(b + c + e) : 0.f;
     }
   }
   int stage = 0;
@@ -291,14 +305,10 @@ __global__ void __launch_bounds__(lnp::WARPS * 32) layernorm_pipe_kernel(const _
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 8;
       if (c < cols) {
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + c)), w1 = __ldg(reinterpret_cast<const float4*>(w + c + 4));
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + c)), b1 = __ldg(reinterpret_cast<const float4*>(b + c + 4));
-        const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         float o8[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          o8[e] = (v[i][e] - mean) * rstd * ww[e] + bb[e];
+          o8[e] = (v[i][e] - mean) * rstd * wr[i][e] + br[i][e];
           if (rowvec) o8[e] += __ldg(rowvec + c + e);
         }
         store8(out, obase + c, out_dtype, o8);
@@ -460,8 +470,8 @@ extern "C" int tcavp_layernorm(const void* x, const void* residual, const float*
   }
   if (pipe_on && vec && wb_al && !residual && in_dtype == TCAVP_BF16 && cols >= 256 && cols <= 1024 && rows >= 65536 &&
       (!rowvec || reinterpret_cast<uintptr_t>(rowvec) % 4 == 0)) {
-    const size_t smem = (size_t)lnp::WARPS * lnp::PIPE_STAGES * ((size_t)cols * 2 + 8);
-    const int blocks_per_sm = (int)((200u << 10) / smem) > 4 ? 4 : (int)((200u << 10) / smem);
+    const size_t smem = (size_t)lnp::WARPS * lnp::stages_for(cols) * ((size_t)cols * 2 + 8);
+    const int blocks_per_sm = (int)((200u << 10) / smem) > 2 ? 2 : (int)((200u << 10) / smem);
     int grid_p = sm_count() * (blocks_per_sm < 1 ? 1 : blocks_per_sm);
     if (grid_p > (rows + lnp::WARPS - 1) / lnp::WARPS) grid_p = (rows + lnp::WARPS - 1) / lnp::WARPS;
 #define TCAVP_LN_PIPE(NV)                                                                                                              \
@@ -509,8 +519,8 @@ extern "C" int tcavp_layernorm_strided(const void* x, int ldx, const float* w, c
   auto al = [](const void* p, size_t a) { return reinterpret_cast<uintptr_t>(p) % a == 0; };
   if (in_dtype == TCAVP_BF16 && ldx == cols && cols % 8 == 0 && cols >= 256 && cols <= 1024 && al(x, 16) && al(w, 16) && al(b, 16) &&
       al(out, 8 * osz) && ((size_t)ldo * osz) % (8 * osz) == 0) {
-    const size_t smem = (size_t)lnp::WARPS * lnp::PIPE_STAGES * ((size_t)cols * 2 + 8);
-    const int bps = (int)((200u << 10) / smem) > 4 ? 4 : (int)((200u << 10) / smem);
+    const size_t smem = (size_t)lnp::WARPS * lnp::stages_for(cols) * ((size_t)cols * 2 + 8);
+    const int bps = (int)((200u << 10) / smem) > 2 ? 2 : (int)((200u << 10) / smem);
     int grid_p = sm_count() * (bps < 1 ? 1 : bps);
     if (grid_p > (rows + lnp::WARPS - 1) / lnp::WARPS) grid_p = (rows + lnp::WARPS - 1) / lnp::WARPS;
 #define TCAVP_LN_PIPE(NV)                                                                                                              \
