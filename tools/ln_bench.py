@@ -28,7 +28,7 @@ def timed(fn, n=50):
 
 
 print("TCAVP_LN_PIPE =", os.environ.get("TCAVP_LN_PIPE", "1"))
-for rows, cols in ((147456, 768), (73728, 768), (147456, 512), (147456, 1024)):
+for rows, cols in ((147456, 768), (73728, 768), (147456, 512), (147456, 1024), (16384, 768), (36864, 768)):
     x = torch.randn(rows, cols, device=dev).bfloat16()
     w, b = torch.ones(cols, device=dev), torch.zeros(cols, device=dev)
     out = torch.empty_like(x)

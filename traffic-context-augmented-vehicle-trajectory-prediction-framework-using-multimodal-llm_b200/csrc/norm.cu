@@ -463,12 +463,14 @@ extern "C" int tcavp_layernorm(const void* x, const void* residual, const float*
   const int grid = (rows + wpb - 1) / wpb;
   const bool wb_al = reinterpret_cast<uintptr_t>(w) % 16 == 0 && reinterpret_cast<uintptr_t>(b) % 16 == 0;
   // many bf16 rows, no residual: rows staged through shared memory by the bulk-copy engine (see layernorm_pipe_kernel)
-  static int pipe_on = -1;
+  static int pipe_on = -1, pipe_min_rows = 24576;      // 36 864 x 768: 31 us through the ring vs 39 us register-resident; 16 384 rows: equal
   if (pipe_on < 0) {
     const char* e = getenv("TCAVP_LN_PIPE");
     pipe_on = e ? atoi(e) : 1;
+    e = getenv("TCAVP_LN_PIPE_MIN_ROWS");
+    if (e) pipe_min_rows = atoi(e);
   }
-  if (pipe_on && vec && wb_al && !residual && in_dtype == TCAVP_BF16 && cols >= 256 && cols <= 1024 && rows >= 65536 &&
+  if (pipe_on && vec && wb_al && !residual && in_dtype == TCAVP_BF16 && cols >= 256 && cols <= 1024 && rows >= pipe_min_rows &&
       (!rowvec || reinterpret_cast<uintptr_t>(rowvec) % 4 == 0)) {
     const size_t smem = (size_t)lnp::WARPS * lnp::stages_for(cols) * ((size_t)cols * 2 + 8);
     const int blocks_per_sm = (int)((200u << 10) / smem) > 2 ? 2 : (int)((200u << 10) / smem);
