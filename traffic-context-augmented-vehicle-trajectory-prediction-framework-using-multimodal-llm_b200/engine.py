@@ -403,11 +403,15 @@ class Engine:
         else:   # zero decoder layers
             ops.add_rowvec(t, q["vis_mod"], fused, rows=B * Q, cols=Hq, remap=(Q, L_total, 0))
 
-    def llm_forward(self, fused, mask, B, L):
+    def llm_forward(self, fused, mask, B, L, kv_out=None):
         """HF:375-427 LlamaModel over inputs_embeds with LoRA on q/k/v (in place on `fused`); returns the
-        post-final-norm hidden states (= hidden_states[-1], reference scripts/train.py:553)."""
+        post-final-norm hidden states (= hidden_states[-1], reference scripts/train.py:553).
+        `kv_out` = (list, capacity): the prefill of a KV-cache decode — every layer's rotated keys and values are also stored in a
+        [B, capacity, 2 * n_kv * head_dim] cache appended to the list (generate.py; `llm_decode_step` continues from them)."""
         m = self.llm
         if m.get("arch") == "gpt2":
+            if kv_out is not None:
+                raise ops._lib.TcavpError("KV-cache decode covers the Llama architecture")
             return self._gpt2_forward(fused, mask, B, L)
         H, nh, nkv, dh, I, kx = m["H"], m["nh"], m["nkv"], m["dh"], m["I"], m["kx"]
         M = B * L
@@ -444,6 +448,10 @@ class Engine:
             ops.gemm(xs, ly["wqkv"], qkv, M=M, N=nqkv, K=Kx, lda=Kx, rope=rope, **norm1)
             if rope is None:
                 ops.rope_(qkv, rows=M, L=L, ld=nqkv, n_q_heads=nh, n_k_heads=nkv, dh=dh, table=table)
+            if kv_out is not None:
+                cache = torch.empty(B, kv_out[1], 2 * nkv * dh, dtype=self.act, device=self.dev)
+                cache[:, :L].copy_(qkv.view(B, L, nqkv)[:, :, nh * dh:])
+                kv_out[0].append(cache)
             ops.attention(qkv, qkv[:, nh * dh:], qkv[:, (nh + nkv) * dh:], attn, B=B, H=nh, Hkv=nkv, Tq=L, Tk=L, dh=dh,
                           q_strides=(L * nqkv, nqkv), k_strides=(L * nqkv, nqkv), v_strides=(L * nqkv, nqkv),
                           o_strides=(L * nh * dh, nh * dh), scale=dh ** -0.5, causal=True, key_mask=mask)
@@ -457,6 +465,48 @@ class Engine:
                 ops.gemm(xs, ly["wgu"], mid, M=M, K=H, lda=Kx, act=ops.ACT_SWIGLU, row_scale=rstd)
                 ops.gemm(mid, ly["wdown"], x, ldo=Kx, residual=x, ldr=Kx)
         return ops.rmsnorm(xs, m["norm"], self._new(M, H), eps=m["eps"], rows=M, cols=H, ldi=Kx)
+
+    def llm_decode_step(self, x_new, caches, t):
+        """One decode step of the KV-cache path (HF generate with past_key_values): `x_new` (B, H) = the embedding of
+        the token at position `t` of every sequence, `caches` = the per-layer [B, capacity, 2 n_kv dh] key / value caches filled up to
+        position t - 1 by `llm_forward(kv_out=...)` / earlier steps.  The new row's rotated key and value are appended, its query attends
+        over positions 0..t (one query, no mask needed), and the post-final-norm hidden state (B, H) is returned.  Same kernels as the
+        full forward: tcavp_gemm with the RMSNorm row factor / LoRA K-extension / RoPE / SwiGLU epilogues, tcavp_attention."""
+        m = self.llm
+        H, nh, nkv, dh, I, kx = m["H"], m["nh"], m["nkv"], m["dh"], m["I"], m["kx"]
+        B = x_new.shape[0]
+        cap = caches[0].shape[1]
+        if t >= cap:
+            raise ops._lib.TcavpError(f"llm_decode_step: position {t} is past the cache capacity {cap}")
+        lay = 1 if m["fuse_rope"] else 0
+        key = (cap, dh, lay)
+        if key not in self._rope:
+            self._rope[key] = ops.rope_table(cap, dh, m["theta"], self.dev, layout=lay)
+        full = self._rope[key]
+        table = (full[:, t:t + 1] if lay == 1 else full[t:t + 1]).contiguous()       # the one position this step needs (rope_L = 1)
+        Kx, nq, nk = H + kx, nh * dh, nkv * dh
+        nqkv = nq + 2 * nk
+        xs = torch.zeros(B, Kx, dtype=self.act, device=self.dev)
+        ops.cast(x_new.reshape(B, H), xs, rows=B, cols=H, ldi=H, ldo=Kx)
+        x = xs[:, :H]
+        rstd = torch.empty(B, dtype=torch.float32, device=self.dev)
+        qkv, attn, mid = self._new(B, nqkv), self._new(B, nq), self._new(B, I)
+        rope = (table, 1, dh, nq + nk) if m["fuse_rope"] else None
+        for ly, cache in zip(m["layers"], caches):
+            ops.row_rstd(xs, rstd, rows=B, cols=H, ldx=Kx, eps=m["eps"])
+            if kx:
+                ops.gemm(xs, ly["a_cat"], xs[:, H:], M=B, N=m["n_lora"], K=H, lda=Kx, ldo=Kx)
+            ops.gemm(xs, ly["wqkv"], qkv, M=B, N=nqkv, K=Kx, lda=Kx, rope=rope, row_scale=rstd)
+            if rope is None:
+                ops.rope_(qkv, rows=B, L=1, ld=nqkv, n_q_heads=nh, n_k_heads=nkv, dh=dh, table=table)
+            cache[:, t].copy_(qkv[:, nq:])
+            ops.attention(qkv, cache, cache[:, :, nk:], attn, B=B, H=nh, Hkv=nkv, Tq=1, Tk=t + 1, dh=dh, q_strides=(nqkv, nqkv),
+                          k_strides=(cap * 2 * nk, 2 * nk), v_strides=(cap * 2 * nk, 2 * nk), o_strides=(nq, nq), scale=dh ** -0.5)
+            ops.gemm(attn, ly["wo"], x, ldo=Kx, residual=x, ldr=Kx)
+            ops.row_rstd(xs, rstd, rows=B, cols=H, ldx=Kx, eps=m["eps"])
+            ops.gemm(xs, ly["wgu"], mid, M=B, K=H, lda=Kx, act=ops.ACT_SWIGLU, row_scale=rstd)
+            ops.gemm(mid, ly["wdown"], x, ldo=Kx, residual=x, ldr=Kx)
+        return ops.rmsnorm(xs, m["norm"], self._new(B, H), eps=m["eps"], rows=B, cols=H, ldi=Kx)
 
     def ltsf_encode(self, x, B):
         """reference scripts/train.py:837-840 -> enc (B*T_in, C)."""

@@ -8,8 +8,10 @@ no_repeat_ngram_size=3, repetition_penalty=1.2)`.  Here the same sampler runs ov
   * every step evaluates the decoder stack over the sequence so far (`Engine.llm_forward`: tcgen05 GEMMs, tcgen05 / flash attention)
     and the vocabulary logits of the LAST position with one M = B GEMM against lm_head;
   * logits processors in HF's order: repetition penalty -> no-repeat-ngram -> temperature -> top-k -> top-p -> multinomial draw.
-This is a once-per-epoch, batch-of-one diagnostic in the reference, so a step recomputes the prefix instead of keeping a KV cache
-(16 + prompt + 128 new tokens: a few hundred rows); the sampled tokens depend on torch's RNG, the logits do not.
+Llama-arch backbones decode with a KV cache: the prefix is evaluated once (`Engine.llm_forward(kv_out=...)` keeps every
+layer's rotated keys / values), then every new token is one `Engine.llm_decode_step` — a one-row pass through the same kernels whose
+query attends over the cached positions.  `kv_cache=False` (and GPT-2-arch backbones) recompute the sequence so far at every step, which
+is also what the cached path is tested against.  The sampled tokens depend on torch's RNG, the logits do not.
 
 Deviation from the reference, on purpose: the reference's patched embedding returns `fused_embeds[:, :len(ids)]` on the first call, i.e.
 it silently drops the last 16 prompt positions and hands HF an attention mask that is 16 longer than the input (train.py:604-611,
@@ -63,20 +65,28 @@ def process_logits(logits, seq, temperature, top_k, top_p, repetition_penalty, n
 
 @torch.no_grad()
 def generate_ids(model, vision_embs, prompt_ids, max_new_tokens=128, temperature=0.9, top_k=40, top_p=0.9, do_sample=True,
-                 repetition_penalty=1.2, no_repeat_ngram_size=3, eos_token_id=None, pad_token_id=None, generator=None):
+                 repetition_penalty=1.2, no_repeat_ngram_size=3, eos_token_id=None, pad_token_id=None, generator=None, kv_cache=True):
     """-> (B, prompt + new) token ids: the prompt followed by the generated tokens (rows that hit `eos_token_id` are padded)."""
     eng = model.engine()
     dev = eng.dev
     ids = prompt_ids.to(device=dev, dtype=torch.int64)
     B = ids.shape[0]
     prefix = eng.prefix_embeds(vision_embs, ids)                           # (B, Q + Lp, H)
+    P, H = prefix.shape[1], prefix.shape[2]
     seq = ids.clone()
     new_embeds = []
     done = torch.zeros(B, dtype=torch.bool, device=dev)
     pad = eos_token_id if pad_token_id is None else pad_token_id
-    for _ in range(int(max_new_tokens)):
-        embeds = prefix if not new_embeds else torch.cat([prefix] + new_embeds, dim=1)
-        logits = next_token_logits(eng, embeds)
+    use_cache = bool(kv_cache) and eng.llm.get("arch") != "gpt2" and int(max_new_tokens) > 0
+    caches, head, logits = [], eng.lm_head(), None
+    if use_cache:      # prefill: one pass over the prefix, keys / values of every layer kept
+        ones = torch.ones(B, P, dtype=torch.int32, device=dev)
+        fh = eng.llm_forward(prefix.clone(), ones, B, P, kv_out=(caches, P + int(max_new_tokens)))
+        logits = ops.gemm(fh.view(B, P, H)[:, P - 1].contiguous(), head, torch.empty(B, head.shape[0], dtype=torch.float32, device=dev))
+    for step in range(int(max_new_tokens)):
+        if not use_cache:
+            embeds = prefix if not new_embeds else torch.cat([prefix] + new_embeds, dim=1)
+            logits = next_token_logits(eng, embeds)
         logits = process_logits(logits, seq, temperature if do_sample else 1.0, top_k if do_sample else 0, top_p if do_sample else None,
                                 repetition_penalty, no_repeat_ngram_size)
         if do_sample:
@@ -87,9 +97,15 @@ def generate_ids(model, vision_embs, prompt_ids, max_new_tokens=128, temperature
             nxt = torch.where(done, torch.full_like(nxt, pad if pad is not None else 0), nxt)
             done = done | (nxt == eos_token_id)
         seq = torch.cat([seq, nxt[:, None]], dim=1)
-        new_embeds.append(eng.token_embeds(nxt[:, None]))                  # plain embedding rows (no modality vector): train.py:609-611
+        emb = eng.token_embeds(nxt[:, None])                               # plain embedding rows (no modality vector): train.py:609-611
         if eos_token_id is not None and bool(done.all()):
             break
+        if use_cache:
+            if step + 1 < int(max_new_tokens):
+                h = eng.llm_decode_step(emb.view(B, H), caches, P + step)
+                logits = ops.gemm(h, head, torch.empty(B, head.shape[0], dtype=torch.float32, device=dev))
+        else:
+            new_embeds.append(emb)
     return seq
 
 
