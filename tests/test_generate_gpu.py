@@ -51,8 +51,8 @@ def test_next_token_logits_and_greedy_continuation_match_the_oracle(lib_built, d
     scale = float(want.abs().max())
     torch.testing.assert_close(got, want, rtol=tol, atol=tol * scale)
     if dtype == "fp32":
-        # greedy continuation (no sampling, no penalties): the same tokens as the oracle's own loop, with the KV cache (Llama arch: prefill
-        # + one-row decode steps) and with the sequence recomputed at every step
+        # greedy continuation (no sampling, no penalties): the same tokens as the oracle's own loop, with the KV cache (prefill + one-row
+        # decode steps) and with the sequence recomputed at every step
         new = torch.zeros(2, 0, dtype=torch.long)
         for _ in range(5):
             nxt = _oracle_logits(sd, cfg, lc, vision, ids, new).argmax(-1)
@@ -61,21 +61,21 @@ def test_next_token_logits_and_greedy_continuation_match_the_oracle(lib_built, d
             seq = G.generate_ids(m, vision, ids, max_new_tokens=5, do_sample=False, repetition_penalty=1.0, no_repeat_ngram_size=0, kv_cache=kv)
             assert seq.shape == (2, 9 + 5) and torch.equal(seq[:, :9].cpu(), ids)
             assert torch.equal(seq[:, 9:].cpu(), new), kv
-    if fixture == "tiny_b6":
-        # the decode step itself: hidden state of position P + j from the cache == the same row of a full forward over the longer sequence
-        extra = eng.token_embeds(i["input_ids"][:2, 9:12].to(pre.device))
-        full = torch.cat([pre, extra], dim=1)
-        Lf, P, H = full.shape[1], pre.shape[1], pre.shape[2]
-        ones = torch.ones(2, Lf, dtype=torch.int32, device=pre.device)
-        want_h = eng.llm_forward(full.clone(), ones, 2, Lf).view(2, Lf, H).float().cpu()
-        caches = []
-        got0 = eng.llm_forward(pre.clone(), ones[:, :P].contiguous(), 2, P, kv_out=(caches, Lf)).view(2, P, H).float().cpu()
-        assert len(caches) == lc["num_hidden_layers"] and caches[0].shape[1] == Lf
-        ht = dict(rtol=tol, atol=tol * float(want_h.abs().max()))
-        torch.testing.assert_close(got0, want_h[:, :P], **ht)
-        for j in range(3):
-            h = eng.llm_decode_step(extra[:, j].contiguous(), caches, P + j).float().cpu()
-            torch.testing.assert_close(h, want_h[:, P + j], **ht)
+    # the decode step itself (Llama: RoPE at the new position; GPT-2: wpe[t]): hidden state of position P + j from the cache == the same
+    # row of a full forward over the longer sequence
+    extra = eng.token_embeds(i["input_ids"][:2, 9:12].to(pre.device))
+    full = torch.cat([pre, extra], dim=1)
+    Lf, P, H = full.shape[1], pre.shape[1], pre.shape[2]
+    ones = torch.ones(2, Lf, dtype=torch.int32, device=pre.device)
+    want_h = eng.llm_forward(full.clone(), ones, 2, Lf).view(2, Lf, H).float().cpu()
+    caches = []
+    got0 = eng.llm_forward(pre.clone(), ones[:, :P].contiguous(), 2, P, kv_out=(caches, Lf)).view(2, P, H).float().cpu()
+    assert len(caches) == lc["num_hidden_layers"] and caches[0].shape[1] == Lf
+    ht = dict(rtol=tol, atol=tol * float(want_h.abs().max()))
+    torch.testing.assert_close(got0, want_h[:, :P], **ht)
+    for j in range(3):
+        h = eng.llm_decode_step(extra[:, j].contiguous(), caches, P + j).float().cpu()
+        torch.testing.assert_close(h, want_h[:, P + j], **ht)
 
 
 @gpu

@@ -150,7 +150,7 @@ class Engine:
             self.llm["layers"].append(dict(wqkv=wqkv, bqkv=_f32(base_b, dev), a_cat=a_cat, ln1=self._ln(blk.ln_1), ln2=self._ln(blk.ln_2),
                                            proj=lin(blk.attn.c_proj), fc=lin(blk.mlp.c_fc), mproj=lin(blk.mlp.c_proj)))
 
-    def _gpt2_forward(self, fused, mask, B, L):
+    def _gpt2_forward(self, fused, mask, B, L, kv_out=None):
         """HF GPT2Model over inputs_embeds: + wpe[0 .. L), pre-norm blocks (LayerNorm -> fused c_attn (+ LoRA) -> causal attention with the
         key-padding mask -> c_proj + residual; LayerNorm -> c_fc + gelu_new -> c_proj + residual), ln_f.  Every projection is a
         tcavp_gemm with its bias / activation / residual in the epilogue; the attention is the tcgen05 kernel of the Llama path (no RoPE)."""
@@ -172,6 +172,10 @@ class Engine:
             else:
                 ops.layernorm(x, ly["ln1"][0], ly["ln1"][1], h, eps=ly["ln1"][2])
                 ops.gemm(h, ly["wqkv"], qkv, bias=ly["bqkv"])
+            if kv_out is not None:       # prefill of a KV-cache decode: keys / values of every layer kept ([B, capacity, 2H])
+                cache = torch.empty(B, kv_out[1], 2 * H, dtype=self.act, device=self.dev)
+                cache[:, :L].copy_(qkv.view(B, L, 3 * H)[:, :, H:])
+                kv_out[0].append(cache)
             ops.attention(qkv, qkv[:, H:], qkv[:, 2 * H:], attn, B=B, H=nh, Hkv=nh, Tq=L, Tk=L, dh=dh, q_strides=(L * 3 * H, 3 * H),
                           k_strides=(L * 3 * H, 3 * H), v_strides=(L * 3 * H, 3 * H), o_strides=(L * H, H), scale=dh ** -0.5, causal=True,
                           key_mask=mask)
@@ -180,6 +184,36 @@ class Engine:
             ops.gemm(h, ly["fc"].w, mid, bias=ly["fc"].b, act=ops.ACT_GELU_TANH)
             ops.gemm(mid, ly["mproj"].w, x, bias=ly["mproj"].b, residual=x)
         return ops.layernorm(x, m["norm"][0], m["norm"][1], self._new(M, H), eps=m["norm"][2])
+
+    def _gpt2_decode_step(self, x_new, caches, t):
+        """llm_decode_step for a GPT-2-arch backbone: + wpe[t], the block sequence of _gpt2_forward on one row per sequence, the new key /
+        value appended to the cache, one query over positions 0..t."""
+        m = self.llm
+        H, nh, dh, I, kx = m["H"], m["nh"], m["dh"], m["I"], m["kx"]
+        B, Kx = x_new.shape[0], H + kx
+        cap = caches[0].shape[1]
+        if t >= cap or t >= m["wpe"].shape[0]:
+            raise ops._lib.TcavpError(f"decode position {t} is past the cache capacity {cap} / n_positions {m['wpe'].shape[0]}")
+        pos = ops.cast(m["wpe"][t:t + 1], self._new(B, H), rows=B, cols=H, in_row_mod=1)
+        x = ops.axpby(x_new.reshape(B, H), self._new(B, H), rows=B, cols=H, b=pos)
+        xs = torch.zeros(B, Kx, dtype=self.act, device=self.dev)
+        h, qkv, attn, mid = self._new(B, H), self._new(B, 3 * H), self._new(B, H), self._new(B, I)
+        for ly, cache in zip(m["layers"], caches):
+            if kx:
+                ops.layernorm_strided(x, ly["ln1"][0], ly["ln1"][1], xs, rows=B, cols=H, eps=ly["ln1"][2], ldo=Kx)
+                ops.gemm(xs, ly["a_cat"], xs[:, H:], M=B, N=m["n_lora"], K=H, lda=Kx, ldo=Kx)
+                ops.gemm(xs, ly["wqkv"], qkv, M=B, N=3 * H, K=Kx, lda=Kx, bias=ly["bqkv"])
+            else:
+                ops.layernorm(x, ly["ln1"][0], ly["ln1"][1], h, eps=ly["ln1"][2])
+                ops.gemm(h, ly["wqkv"], qkv, bias=ly["bqkv"])
+            cache[:, t].copy_(qkv[:, H:])
+            ops.attention(qkv, cache, cache[:, :, H:], attn, B=B, H=nh, Hkv=nh, Tq=1, Tk=t + 1, dh=dh, q_strides=(3 * H, 3 * H),
+                          k_strides=(cap * 2 * H, 2 * H), v_strides=(cap * 2 * H, 2 * H), o_strides=(H, H), scale=dh ** -0.5)
+            ops.gemm(attn, ly["proj"].w, x, bias=ly["proj"].b, residual=x)
+            ops.layernorm(x, ly["ln2"][0], ly["ln2"][1], h, eps=ly["ln2"][2])
+            ops.gemm(h, ly["fc"].w, mid, bias=ly["fc"].b, act=ops.ACT_GELU_TANH)
+            ops.gemm(mid, ly["mproj"].w, x, bias=ly["mproj"].b, residual=x)
+        return ops.layernorm(x, m["norm"][0], m["norm"][1], self._new(B, H), eps=m["norm"][2])
 
     def _pack_llm(self, mllm):
         wrap = mllm.llama_wrapper
@@ -410,9 +444,7 @@ class Engine:
         [B, capacity, 2 * n_kv * head_dim] cache appended to the list (generate.py; `llm_decode_step` continues from them)."""
         m = self.llm
         if m.get("arch") == "gpt2":
-            if kv_out is not None:
-                raise ops._lib.TcavpError("KV-cache decode covers the Llama architecture")
-            return self._gpt2_forward(fused, mask, B, L)
+            return self._gpt2_forward(fused, mask, B, L, kv_out)
         H, nh, nkv, dh, I, kx = m["H"], m["nh"], m["nkv"], m["dh"], m["I"], m["kx"]
         M = B * L
         key = (L, dh, 1 if m["fuse_rope"] else 0)
@@ -473,6 +505,8 @@ class Engine:
         over positions 0..t (one query, no mask needed), and the post-final-norm hidden state (B, H) is returned.  Same kernels as the
         full forward: tcavp_gemm with the RMSNorm row factor / LoRA K-extension / RoPE / SwiGLU epilogues, tcavp_attention."""
         m = self.llm
+        if m.get("arch") == "gpt2":
+            return self._gpt2_decode_step(x_new, caches, t)
         H, nh, nkv, dh, I, kx = m["H"], m["nh"], m["nkv"], m["dh"], m["I"], m["kx"]
         B = x_new.shape[0]
         cap = caches[0].shape[1]

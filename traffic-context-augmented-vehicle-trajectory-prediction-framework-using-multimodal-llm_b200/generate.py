@@ -8,10 +8,10 @@ no_repeat_ngram_size=3, repetition_penalty=1.2)`.  Here the same sampler runs ov
   * every step evaluates the decoder stack over the sequence so far (`Engine.llm_forward`: tcgen05 GEMMs, tcgen05 / flash attention)
     and the vocabulary logits of the LAST position with one M = B GEMM against lm_head;
   * logits processors in HF's order: repetition penalty -> no-repeat-ngram -> temperature -> top-k -> top-p -> multinomial draw.
-Llama-arch backbones decode with a KV cache: the prefix is evaluated once (`Engine.llm_forward(kv_out=...)` keeps every
+Decoding uses a KV cache (Llama- and GPT-2-arch backbones): the prefix is evaluated once (`Engine.llm_forward(kv_out=...)` keeps every
 layer's rotated keys / values), then every new token is one `Engine.llm_decode_step` — a one-row pass through the same kernels whose
-query attends over the cached positions.  `kv_cache=False` (and GPT-2-arch backbones) recompute the sequence so far at every step, which
-is also what the cached path is tested against.  The sampled tokens depend on torch's RNG, the logits do not.
+query attends over the cached positions.  `kv_cache=False` recomputes the sequence so far at every step, which is also what the cached
+path is tested against.  The sampled tokens depend on torch's RNG, the logits do not.
 
 Deviation from the reference, on purpose: the reference's patched embedding returns `fused_embeds[:, :len(ids)]` on the first call, i.e.
 it silently drops the last 16 prompt positions and hands HF an attention mask that is 16 longer than the input (train.py:604-611,
@@ -77,7 +77,7 @@ def generate_ids(model, vision_embs, prompt_ids, max_new_tokens=128, temperature
     new_embeds = []
     done = torch.zeros(B, dtype=torch.bool, device=dev)
     pad = eos_token_id if pad_token_id is None else pad_token_id
-    use_cache = bool(kv_cache) and eng.llm.get("arch") != "gpt2" and int(max_new_tokens) > 0
+    use_cache = bool(kv_cache) and int(max_new_tokens) > 0
     caches, head, logits = [], eng.lm_head(), None
     if use_cache:      # prefill: one pass over the prefix, keys / values of every layer kept
         ones = torch.ones(B, P, dtype=torch.int32, device=dev)
