@@ -13,7 +13,7 @@ so = sys.argv[1] if len(sys.argv) > 1 else os.path.join(
 sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, check=True).stdout
 demangle = lambda n: subprocess.run(["cu++filt", n], capture_output=True, text=True).stdout.strip() or n   # noqa: E731
 PAT = OrderedDict([("UTC*MMA (tcgen05.mma)", r"\bUTC[A-Z]*MMA"), ("LDTM (tcgen05.ld)", r"\bLDTM"), ("STTM (tcgen05.st)", r"\bSTTM"),
-                   ("UTCBAR (tcgen05.commit)", r"\bUTCBAR"), ("UTMALDG (TMA load)", r"\bUTMALDG"), ("UTMASTG (TMA store)", r"\bUTMASTG"), ("SYNCS (mbarrier)", r"\bSYNCS"), ("HMMA (mma.sync)", r"\bHMMA"),
+                   ("UTCBAR (tcgen05.commit)", r"\bUTCBAR"), ("UTMALDG (TMA load)", r"\bUTMALDG"), ("UTMASTG (TMA store)", r"\bUTMASTG"), ("UBLKCP (cp.async.bulk)", r"\bUBLKCP"), ("SYNCS (mbarrier)", r"\bSYNCS"), ("HMMA (mma.sync)", r"\bHMMA"),
                    ("LDSM (ldmatrix)", r"\bLDSM"), ("LDGSTS (cp.async)", r"\bLDGSTS"), ("LDG/STG .256", r"\b(LDG|STG)[.A-Z0-9]*\.256"),
                    ("FFMA", r"\bFFMA")])
 rows, cur, cnt = [], None, Counter()
