@@ -149,6 +149,37 @@ def test_engine_packing_shapes():
     torch.testing.assert_close(e.lt["lane_fc"].w.view(To, C, -1)[3, 5], lf.view(C, To, -1)[5, 3])   # small path stays fp32
 
 
+def test_gpt2_train_engine_packing_and_lora_refresh():
+    """GPT-2-arch backbone under the fine-tune engine (host side only): c_attn packed as [W^T | (alpha / r) B] with the LoRA pair re-packed
+    from the fp32 masters on every sync, transposed copy for the dX GEMMs, trainable names in HF GPT2LMHeadModel + peft layout."""
+    from tcavp_b200.train_engine import DropPlan, TrainEngine
+    mc = dict(T.MODEL_PRESETS["tiny"], base_model_name="gpt2-tiny")
+    m = T.MultiModalTrajectoryModel(**mc, compute_dtype="fp32")
+    te = TrainEngine(m, "fp32")
+    te.drop = DropPlan(None, {})
+    c = T.resolve_llama("gpt2-tiny")
+    H, r = c["hidden_size"], 4
+    ca = m.mllm.llama_wrapper.causal_lm().transformer.h[1].attn.c_attn
+    with torch.no_grad():
+        ca.lora_B["default"].weight.normal_(0, 0.1)
+    te.sync_params()
+    ly = te.llm["layers"][1]
+    assert te.llm["kx"] == 8 and ly["wqkv"].shape == (3 * H, H + 8) and ly["wqkvT"].shape == (H + 8, 3 * H)
+    torch.testing.assert_close(ly["wqkv"][:, :H], ca.base_layer.weight.detach().t())                      # Conv1D [in, out] -> [N, K]
+    torch.testing.assert_close(ly["wqkv"][:, H:H + r], ca.lora_B["default"].weight.detach() * ca.scaling)
+    assert torch.count_nonzero(ly["wqkv"][:, H + r:]) == 0
+    torch.testing.assert_close(ly["wqkvT"], ly["wqkv"].t())
+    torch.testing.assert_close(ly["a_cat"][:r], ca.lora_A["default"].weight.detach())
+    torch.testing.assert_close(ly["a_catT"], ly["a_cat"].t())
+    with torch.no_grad():                                            # an optimizer step moves the masters: the next sync re-packs them
+        ca.lora_A["default"].weight.add_(1.0)
+    te.sync_params()
+    torch.testing.assert_close(te.llm["layers"][1]["a_cat"][:r], ca.lora_A["default"].weight.detach())
+    names = [n for n, _ in te.params if "lora_" in n]
+    assert len(names) == 2 * c["num_hidden_layers"] and all(n.startswith(te.llm_prefix) and ".attn.c_attn.lora_" in n for n in names)
+    assert te._dropout_probs()[("llm", "lora_c")] == pytest.approx(mc.get("lora_dropout", 0.1))
+
+
 def test_forward_without_cuda_fails_loudly():
     m = T.MultiModalTrajectoryModel(**T.MODEL_PRESETS["tiny"]).eval()
     s = T.make_scenes(2, 6, 12, vision_dim=32, l_text=8, vocab=97)
