@@ -23,7 +23,7 @@ import numpy as np
 import torch
 
 MOD = dict(poly=1, qenc=2, qdec=3, llm=4, ltsf=5, dec=6)
-KIND = dict(sa_attn=0, drop1=1, ffn=2, drop2=3, ca_attn=4, drop3=5, post=6, cross_attn=7, lora_q=8, lora_k=9, lora_v=10, lora_c=11)
+KIND = dict(sa_attn=0, drop1=1, ffn=2, drop2=3, ca_attn=4, drop3=5, post=6, cross_attn=7, lora_q=8, lora_k=9, lora_v=10, lora_c=11, embd=12, attn=13, resid1=14, resid2=15)
 _M32 = np.uint64(0xFFFFFFFF)
 
 
@@ -79,7 +79,7 @@ class DropOracle:
         return t if f is None else t * f
 
 
-def default_probs(model_cfg, transformer_p=0.1):
+def default_probs(model_cfg, transformer_p=0.1, llama_cfg=None):
     """Dropout probability of every site for a reference constructor-kwargs dict (train.py:848-872 defaults: 0.1 everywhere)."""
     lp, tp = float(model_cfg.get("lora_dropout", 0.1)), float(model_cfg.get("ltsf_dropout", 0.1))
     pr = {}
@@ -91,10 +91,13 @@ def default_probs(model_cfg, transformer_p=0.1):
     pr[("dec", "post")] = pr[("dec", "cross_attn")] = tp
     if model_cfg.get("use_lora", True):
         pr[("llm", "lora_q")] = pr[("llm", "lora_v")] = pr[("llm", "lora_c")] = lp      # lora_c: the c_attn target of a GPT-2-arch backbone
+    if llama_cfg is not None and llama_cfg.get("arch") == "gpt2":      # HF GPT2Config's own dropouts
+        pr[("llm", "embd")], pr[("llm", "attn")] = float(llama_cfg.get("embd_pdrop", 0.0)), float(llama_cfg.get("attn_pdrop", 0.0))
+        pr[("llm", "resid1")] = pr[("llm", "resid2")] = float(llama_cfg.get("resid_pdrop", 0.0))
     return pr
 
 
-def reference_call_sequence(model_cfg, n_llm_layers, lora_targets=("q_proj", "v_proj"), arch="llama"):
+def reference_call_sequence(model_cfg, n_llm_layers, lora_targets=("q_proj", "v_proj"), arch="llama", llama_cfg=None):
     """[(module, layer, kind, layout)] in the order the reference's forward reaches its dropout calls (train mode):
     lane_polygon_encoder -> mllm (Q-Former encoder, decoder, LoRA-Llama) -> ltsf (attention block, decoder) — train.py:926-939.
     layout: "flat" = the tensor's own row-major order is the canonical one; "tbe" = (T, B, E) tensors of the batch_first=False
@@ -109,11 +112,22 @@ def reference_call_sequence(model_cfg, n_llm_layers, lora_targets=("q_proj", "v_
     for l in range(model_cfg.get("q_dec_layers", 4)):        # torch TransformerDecoderLayer: _sa_block, _mha_block, _ff_block
         seq.extend([("qdec", l, "sa_attn", "flat"), ("qdec", l, "drop1", "flat"), ("qdec", l, "ca_attn", "flat"), ("qdec", l, "drop2", "flat"),
                     ("qdec", l, "ffn", "flat"), ("qdec", l, "drop3", "flat")])
-    if model_cfg.get("use_lora", True):
-        for l in range(n_llm_layers):                         # HF LlamaAttention.forward: q_proj, k_proj, v_proj in this order
-            if arch == "gpt2":                                # HF GPT2Attention.forward: one fused c_attn (peft's default target)
+    if arch == "gpt2":
+        # HF modeling_gpt2.py in train mode: GPT2Model.drop; per block c_attn (peft's lora_dropout on its input), attention-probability
+        # dropout, resid_dropout after attn.c_proj, GPT2MLP.dropout after mlp.c_proj.  Calls with p == 0 never reach the patched function.
+        g = llama_cfg or {}
+        lora = model_cfg.get("use_lora", True) and float(model_cfg.get("lora_dropout", 0.1)) > 0
+        if float(g.get("embd_pdrop", 0.0)) > 0:
+            seq.append(("llm", 0, "embd", "flat"))
+        for l in range(n_llm_layers):
+            if lora:
                 seq.append(("llm", l, "lora_c", "flat"))
-                continue
+            if float(g.get("attn_pdrop", 0.0)) > 0:
+                seq.append(("llm", l, "attn", "flat"))
+            if float(g.get("resid_pdrop", 0.0)) > 0:
+                seq.extend([("llm", l, "resid1", "flat"), ("llm", l, "resid2", "flat")])
+    elif model_cfg.get("use_lora", True):
+        for l in range(n_llm_layers):                         # HF LlamaAttention.forward: q_proj, k_proj, v_proj in this order
             for t in ("q_proj", "k_proj", "v_proj"):
                 if t in lora_targets:
                     seq.append(("llm", l, "lora_" + t[0], "flat"))

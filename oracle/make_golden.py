@@ -176,7 +176,7 @@ def make_grads(name="tiny_b5_grads"):
     def patched():
         if drop is None:
             return contextlib.nullcontext()
-        return OD.patch_reference_dropout(OD.DropOracle(drop[0], drop[1], {}), OD.reference_call_sequence(mc, n_llm, arch=lc.get("arch", "llama")))
+        return OD.patch_reference_dropout(OD.DropOracle(drop[0], drop[1], {}), OD.reference_call_sequence(mc, n_llm, arch=lc.get("arch", "llama"), llama_cfg=lc))
     if drop is not None:
         model.train()
     with torch.no_grad(), patched():
@@ -198,7 +198,7 @@ def make_grads(name="tiny_b5_grads"):
            "inputs": {k: s[k] for k in ("x", "y", "vision", "polygon", "poly_len", "norm_stat", "input_ids", "attention_mask")},
            "loss": loss.detach().float(), "loss_fp32_run": loss32.detach(), "decoded": decoded.detach().float(), "n_trainable": len(grads),
            "precision": "reference executed in float64 (see make_grads)",
-           "dropout": None if drop is None else {"seed": drop[0], "step": drop[1], "probs": {f"{k[0]}.{k[1]}": v for k, v in OD.default_probs(mc).items()},
+           "dropout": None if drop is None else {"seed": drop[0], "step": drop[1], "probs": {f"{k[0]}.{k[1]}": v for k, v in OD.default_probs(mc, llama_cfg=lc).items()},
                                                   "mode": "train(): counter-based masks of include/tcavp.h substituted for torch's RNG"},
            "grads": {k: restated.compress_grad(v) for k, v in grads.items()},
            "versions": {"torch": str(torch.__version__), "transformers": __import__("transformers").__version__}}

@@ -82,7 +82,8 @@ def load_reference(script: str = "scripts/train.py", llama_cfg: dict = None):
             return GPT2LMHeadModel(GPT2Config(vocab_size=c["vocab_size"], n_positions=c["n_positions"], n_embd=c["hidden_size"],
                                               n_layer=c["num_hidden_layers"], n_head=c["num_attention_heads"], n_inner=c["intermediate_size"],
                                               activation_function="gelu_new", layer_norm_epsilon=c.get("layer_norm_epsilon", 1e-5),
-                                              resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0))
+                                              resid_pdrop=c.get("resid_pdrop", 0.0), embd_pdrop=c.get("embd_pdrop", 0.0),
+                                              attn_pdrop=c.get("attn_pdrop", 0.0)))
         return LlamaForCausalLM(hf_llama_config(c))
 
     transformers.AutoModelForCausalLM.from_pretrained = classmethod(_from_pretrained)

@@ -269,7 +269,7 @@ def gpt2_stack(sd, cfg, embeds, attn_mask, lora_scaling, p=None):
     dh = H // nh
     eps = cfg.get("layer_norm_epsilon", 1e-5)
     allowed = torch.tril(torch.ones(L, L, dtype=torch.bool))[None] & attn_mask.bool()[:, None, :]
-    x = embeds + sd[p + "wpe.weight"][:L]
+    x = _D(embeds + sd[p + "wpe.weight"][:L], "llm", 0, "embd")                               # GPT2Model.drop (train mode only)
     for i in range(cfg["num_hidden_layers"]):
         bp = f"{p}h.{i}."
         h = layer_norm(x, sd[bp + "ln_1.weight"], sd[bp + "ln_1.bias"], eps)
@@ -277,11 +277,12 @@ def gpt2_stack(sd, cfg, embeds, attn_mask, lora_scaling, p=None):
         q, k, v = (t.view(B, L, nh, dh).transpose(1, 2) for t in (q, k, v))
         s = (q @ k.transpose(-1, -2)) * (dh ** -0.5)
         s = s.masked_fill(~allowed[:, None], float("-inf"))
-        a = (torch.softmax(s.float(), dim=-1).to(q.dtype) @ v).transpose(1, 2).reshape(B, L, H)
-        x = x + _conv1d(sd, bp + "attn.c_proj.", a, lora_scaling)
+        pr = _D(torch.softmax(s.float(), dim=-1).to(q.dtype), "llm", i, "attn")                # attn_dropout on the probabilities
+        a = (pr @ v).transpose(1, 2).reshape(B, L, H)
+        x = x + _D(_conv1d(sd, bp + "attn.c_proj.", a, lora_scaling), "llm", i, "resid1")      # resid_dropout
         h = layer_norm(x, sd[bp + "ln_2.weight"], sd[bp + "ln_2.bias"], eps)
         h = F.gelu(_conv1d(sd, bp + "mlp.c_fc.", h, lora_scaling), approximate="tanh")      # ACT2FN["gelu_new"]
-        x = x + _conv1d(sd, bp + "mlp.c_proj.", h, lora_scaling)
+        x = x + _D(_conv1d(sd, bp + "mlp.c_proj.", h, lora_scaling), "llm", i, "resid2")       # GPT2MLP.dropout
     return layer_norm(x, sd[p + "ln_f.weight"], sd[p + "ln_f.bias"], eps)
 
 

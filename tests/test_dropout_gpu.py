@@ -96,10 +96,12 @@ def test_fused_lora_dropout_kernels(lib_built, M, H, r, probs, ld_extra):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("B,H,Tq,Tk,dh,masked", [(3, 4, 33, 33, 16, True), (2, 2, 15, 15, 32, False), (2, 8, 16, 15, 96, False), (2, 2, 12, 40, 64, False),
-                                                 (2, 2, 25, 144, 384, False)])
-def test_attention_dropout_forward_and_backward(lib_built, dtype, B, H, Tq, Tk, dh, masked):
-    """Dropout on the attention probabilities (forward and backward kernels) against autograd through the same math with the oracle mask."""
+@pytest.mark.parametrize("B,H,Tq,Tk,dh,masked,causal", [(3, 4, 33, 33, 16, True, False), (2, 2, 15, 15, 32, False, False), (2, 8, 16, 15, 96, False, False),
+                                                        (2, 2, 12, 40, 64, False, False), (2, 2, 25, 144, 384, False, False),
+                                                        (3, 4, 40, 40, 32, True, True), (2, 12, 144, 144, 64, True, True)])
+def test_attention_dropout_forward_and_backward(lib_built, dtype, B, H, Tq, Tk, dh, masked, causal):
+    """Dropout on the attention probabilities (forward and backward kernels) against autograd through the same math with the oracle mask.
+    The causal cases are the GPT-2-arch backbone in train mode (HF attn_pdrop: causal + key-padding mask + dropout on the probabilities)."""
     from tcavp_b200 import ops
     g = torch.Generator().manual_seed(B * Tq + dh)
     E = H * dh
@@ -108,12 +110,16 @@ def test_attention_dropout_forward_and_backward(lib_built, dtype, B, H, Tq, Tk, 
     km = None
     if masked:
         km = (torch.arange(Tk)[None, :] < torch.tensor([Tk, 7, 20][:B])[:, None]).to(torch.int32)
+        if causal:      # right padding never masks a row completely under the causal mask
+            km = (torch.arange(Tk)[None, :] < torch.tensor([Tk, Tk - 9, Tk - 17][:B])[:, None]).to(torch.int32)
     site, p, scale = OD.site_id("poly", 1, "sa_attn"), 0.1, dh ** -0.5
     f = torch.from_numpy(OD.keep_mask(77, 2, site, p, B * H * Tq * Tk).astype(np.float32) / (1 - p)).view(B, H, Tq, Tk)
     qf, kf, vf = (t.float().clone().requires_grad_(True) for t in (q, k, v))
     s = (qf.view(B, Tq, H, dh).transpose(1, 2) @ kf.view(B, Tk, H, dh).transpose(1, 2).transpose(-1, -2)) * scale
     if km is not None:
         s = s.masked_fill(km[:, None, None, :] == 0, float("-inf"))
+    if causal:
+        s = s.masked_fill(~torch.ones(Tq, Tk, dtype=torch.bool).tril(), float("-inf"))
     o_ref = ((torch.softmax(s, -1) * f) @ vf.view(B, Tk, H, dh).transpose(1, 2)).transpose(1, 2).reshape(B, Tq, E)
     gq, gk, gv = torch.autograd.grad(o_ref, (qf, kf, vf), do.float())
     d = ops.Drop(_seed(77, 2), site, p)
@@ -122,32 +128,32 @@ def test_attention_dropout_forward_and_backward(lib_built, dtype, B, H, Tq, Tk, 
     out = torch.empty(B, Tq, E, dtype=dtype, device=DEV)
     st = lambda T_: (T_ * E, E)    # noqa: E731
     ops.attention(qd, kd, vd, out, B=B, H=H, Hkv=H, Tq=Tq, Tk=Tk, dh=dh, q_strides=st(Tq), k_strides=st(Tk), v_strides=st(Tk), o_strides=st(Tq),
-                  scale=scale, key_mask=kmd, drop=d)
+                  scale=scale, key_mask=kmd, drop=d, causal=causal)
     tol = dict(rtol=2e-4, atol=2e-4) if dtype == torch.float32 else dict(rtol=3e-2, atol=3e-2)
     torch.testing.assert_close(out.float().cpu(), o_ref.detach(), **tol)
     dq = torch.empty(B, Tq, E, dtype=dtype, device=DEV)
     dk, dv = torch.zeros(B, Tk, E, device=DEV), torch.zeros(B, Tk, E, device=DEV)
     ops.attention_bwd(qd, kd, vd, dod, dq, dk, dv, B=B, H=H, Hkv=H, Tq=Tq, Tk=Tk, dh=dh, q_strides=st(Tq), k_strides=st(Tk), v_strides=st(Tk),
                       do_strides=st(Tq), dq_strides=st(Tq), dk_strides=st(Tk), dv_strides=st(Tk), scale=scale, key_mask=kmd, o=out, o_strides=st(Tq),
-                      drop=d)
+                      drop=d, causal=causal)
     btol = dict(rtol=1e-3, atol=1e-3) if dtype == torch.float32 else dict(rtol=5e-2, atol=5e-2 * float(gq.abs().max()))
     torch.testing.assert_close(dq.float().cpu(), gq, **btol)
     torch.testing.assert_close(dk.cpu(), gk, **btol)
     torch.testing.assert_close(dv.cpu(), gv, **btol)
-    if ops.attention_bwd_owned_ok(qd, H=H, Hkv=H, Tq=Tq, Tk=Tk, dh=dh, o=out):
+    if ops.attention_bwd_owned_ok(qd, H=H, Hkv=H, Tq=Tq, Tk=Tk, dh=dh, o=out, causal=causal):
         # the "owned" form the fine-tune step uses (one CTA owns every key row: dk / dv stored directly in bf16)
         dq2 = torch.empty(B, Tq, E, dtype=dtype, device=DEV)
         dk2, dv2 = torch.empty(B, Tk, E, dtype=dtype, device=DEV), torch.empty(B, Tk, E, dtype=dtype, device=DEV)
         ops.attention_bwd_owned(qd, kd, vd, dod, dq2, dk2, dv2, B=B, H=H, Tq=Tq, Tk=Tk, dh=dh, q_strides=st(Tq), k_strides=st(Tk), v_strides=st(Tk),
                                 do_strides=st(Tq), dq_strides=st(Tq), dk_strides=st(Tk), dv_strides=st(Tk), scale=scale, key_mask=kmd, o=out,
-                                o_strides=st(Tq), drop=d)
+                                o_strides=st(Tq), drop=d, causal=causal)
         torch.testing.assert_close(dq2.float().cpu(), gq, **btol)
         torch.testing.assert_close(dk2.float().cpu(), gk, rtol=5e-2, atol=5e-2 * float(gk.abs().max()))
         torch.testing.assert_close(dv2.float().cpu(), gv, rtol=5e-2, atol=5e-2 * float(gv.abs().max()))
 
 
 def _drop_oracle(fix):
-    return OD.DropOracle(fix["dropout"]["seed"], fix["dropout"]["step"], OD.default_probs(fix["model_cfg"]))
+    return OD.DropOracle(fix["dropout"]["seed"], fix["dropout"]["step"], OD.default_probs(fix["model_cfg"], llama_cfg=fix["llama_cfg"]))
 
 
 @pytest.mark.parametrize("name", ["tiny_b5_grads_drop", "cfg1_b3_grads_drop", "gpt2_tiny_b5_grads_drop", "gpt2_l2_b3_grads_drop"])
@@ -188,7 +194,7 @@ def test_fp32_train_mode_gradients_match_reference(lib_built, name):
     torch.testing.assert_close(l4.detach().cpu(), load_golden(name.replace("_drop", ""))["loss"], rtol=1e-4, atol=0)
 
 
-@pytest.mark.parametrize("name", ["tiny_b5_grads_drop", "gpt2_l2_b3_grads_drop"])
+@pytest.mark.parametrize("name", ["tiny_b5_grads_drop", "gpt2_l2_b3_grads_drop", "gpt2_tiny_b5_grads_drop"])
 def test_bf16_train_mode_gradients_track_the_oracle(lib_built, name):
     """bf16 train mode (gpt2_l2: LoRA r 8 on a 768-wide c_attn, so lora_dropout runs through the fused mask-regenerating kernels)."""
     fix = load_golden(name)

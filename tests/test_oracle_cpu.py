@@ -95,7 +95,7 @@ def test_restated_train_mode_dropout_matches_reference(name):
     sd = m.state_dict()
     T.deterministic_fill_(sd, fix["weight_seed"])
     i = fix["inputs"]
-    orc = OD.DropOracle(fix["dropout"]["seed"], fix["dropout"]["step"], OD.default_probs(fix["model_cfg"]))
+    orc = OD.DropOracle(fix["dropout"]["seed"], fix["dropout"]["step"], OD.default_probs(fix["model_cfg"], llama_cfg=fix["llama_cfg"]))
     with restated.dropout(orc):
         loss, decoded, grads = restated.loss_and_grads(sd, fix["model_cfg"], fix["llama_cfg"], i["x"], i["vision"], i["polygon"], i["poly_len"],
                                                        i["input_ids"], i["attention_mask"], i["y"], i["norm_stat"])
@@ -103,7 +103,7 @@ def test_restated_train_mode_dropout_matches_reference(name):
     torch.testing.assert_close(loss, fix["loss"], rtol=1e-5, atol=0)
     torch.testing.assert_close(decoded, fix["decoded"], rtol=1e-4, atol=1e-5)
     lc = fix["llama_cfg"]
-    assert len(orc.used) == len(OD.reference_call_sequence(fix["model_cfg"], lc["num_hidden_layers"], arch=lc.get("arch", "llama")))
+    assert len(orc.used) == len(OD.reference_call_sequence(fix["model_cfg"], lc["num_hidden_layers"], arch=lc.get("arch", "llama"), llama_cfg=lc))
     for k, want in fix["grads"].items():
         ref_scale = float((want["full"] if "full" in want else want["head"]).abs().max()) + 1e-8
         _check_against_compressed(grads[k], want, rtol=2e-3, atol=2e-4 * ref_scale + 1e-6, key=k)

@@ -28,9 +28,9 @@ LLAMA_PRESETS = {
     # LoRA target for model_type "gpt2" is the fused c_attn projection): LayerNorm with bias, learned position embeddings, Conv1D
     # projections ([in, out] weights) with biases, gelu_new MLP, tied lm_head.  Values of the public gpt2 (small) config.json.
     "gpt2": dict(arch="gpt2", vocab_size=50257, hidden_size=768, intermediate_size=3072, num_hidden_layers=12, num_attention_heads=12,
-                 n_positions=1024, layer_norm_epsilon=1e-5, tie_word_embeddings=True),
+                 n_positions=1024, layer_norm_epsilon=1e-5, tie_word_embeddings=True, attn_pdrop=0.1, resid_pdrop=0.1, embd_pdrop=0.1),
     "gpt2-tiny": dict(arch="gpt2", vocab_size=97, hidden_size=128, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
-                      n_positions=64, layer_norm_epsilon=1e-5, tie_word_embeddings=True),
+                      n_positions=64, layer_norm_epsilon=1e-5, tie_word_embeddings=True, attn_pdrop=0.1, resid_pdrop=0.1, embd_pdrop=0.1),
     # tiny shape for golden fixtures that carry their full state_dict
     "llama-tiny": dict(vocab_size=97, hidden_size=128, intermediate_size=256, num_hidden_layers=2,
                        num_attention_heads=4, num_key_value_heads=2, head_dim=32, rms_norm_eps=1e-6,

@@ -669,8 +669,11 @@ class MultiModalTrajectoryModel(nn.Module):
                 m.p = float(p)
             elif isinstance(m, nn.MultiheadAttention):
                 m.dropout = float(p)
-            elif isinstance(m, LoraLinearW):
+            elif isinstance(m, (LoraLinearW, LoraConv1DW)):
                 m.lora_dropout_p = float(p)
+        cfg = self.mllm.llama_wrapper.config
+        if cfg.get("arch") == "gpt2":          # HF GPT2Config's own dropouts (embeddings, attention probabilities, the two c_proj outputs)
+            cfg["attn_pdrop"] = cfg["resid_pdrop"] = cfg["embd_pdrop"] = float(p)
         return self
 
     @torch.no_grad()

@@ -30,7 +30,7 @@ def _pad8(n):
 # site id = module << 20 | layer << 8 | kind.  The oracle (oracle/dropout.py) derives the same ids from the ORDER in which the
 # reference's forward calls F.dropout / scaled_dot_product_attention, so masks are bit-identical on both sides.
 MOD = dict(poly=1, qenc=2, qdec=3, llm=4, ltsf=5, dec=6)
-KIND = dict(sa_attn=0, drop1=1, ffn=2, drop2=3, ca_attn=4, drop3=5, post=6, cross_attn=7, lora_q=8, lora_k=9, lora_v=10, lora_c=11)
+KIND = dict(sa_attn=0, drop1=1, ffn=2, drop2=3, ca_attn=4, drop3=5, post=6, cross_attn=7, lora_q=8, lora_k=9, lora_v=10, lora_c=11, embd=12, attn=13, resid1=14, resid2=15)
 
 
 def site_id(mod, layer, kind):
@@ -130,9 +130,14 @@ class TrainEngine(Engine):
         if d.use_post_mlp:
             pr[("dec", "post")] = float(d.post_mlp[2].p)
         wrap = m.mllm.llama_wrapper
-        if wrap.use_lora and wrap.config.get("arch") == "gpt2":
-            # HF GPT2Config's own attn / resid / embd dropouts are taken as 0 (the shape dicts of config.py carry no such keys)
-            pr[("llm", "lora_c")] = float(wrap.causal_lm().transformer.h[0].attn.c_attn.lora_dropout_p)
+        if wrap.config.get("arch") == "gpt2":
+            # HF GPT2Config's own dropouts (modeling_gpt2.py: GPT2Model.drop on wte + wpe, attn_dropout on the probabilities, resid_dropout
+            # after attn.c_proj, GPT2MLP.dropout after mlp.c_proj); a shape dict without the keys means 0
+            c = wrap.config
+            pr[("llm", "embd")], pr[("llm", "attn")] = float(c.get("embd_pdrop", 0.0)), float(c.get("attn_pdrop", 0.0))
+            pr[("llm", "resid1")] = pr[("llm", "resid2")] = float(c.get("resid_pdrop", 0.0))
+            if wrap.use_lora:
+                pr[("llm", "lora_c")] = float(wrap.causal_lm().transformer.h[0].attn.c_attn.lora_dropout_p)
         elif wrap.use_lora:
             layer0 = wrap.causal_lm().model.layers[0].self_attn
             for t in wrap.llama_model.targets:
@@ -571,6 +576,8 @@ class TrainEngine(Engine):
             raise ops._lib.TcavpError(f"sequence length {L} exceeds the backbone's n_positions {m['wpe'].shape[0]}")
         pos = ops.cast(m["wpe"], self._new(M, H), rows=M, cols=H, in_row_mod=L)
         x = ops.axpby(fused.view(M, H), self._new(M, H), rows=M, cols=H, b=pos)
+        if self.drop("llm", 0, "embd") is not None:          # GPT2Model.drop(inputs_embeds + position_embeds)
+            self._drop_res(x, self.drop("llm", 0, "embd"), None)
         sq = (L * 3 * H, 3 * H)
         ctxs, xm = [], None
         for li, ly in enumerate(m["layers"]):
@@ -592,12 +599,12 @@ class TrainEngine(Engine):
                 qkv = ops.gemm(xs, ly["wqkv"], self._new(M, 3 * H), bias=ly["bqkv"])
             attn = self._new(M, H)
             ops.attention(qkv, qkv[:, H:], qkv[:, 2 * H:], attn, B=B, H=nh, Hkv=nh, Tq=L, Tk=L, dh=dh, q_strides=sq, k_strides=sq, v_strides=sq,
-                          o_strides=(L * H, H), scale=dh ** -0.5, causal=True, key_mask=mask)
-            x_mid = ops.gemm(attn, ly["proj"].w, self._new(M, H), bias=ly["proj"].b, residual=x)
+                          o_strides=(L * H, H), scale=dh ** -0.5, causal=True, key_mask=mask, drop=self.drop("llm", li, "attn"))
+            x_mid = self._sub_out(attn, ly["proj"], x, self.drop("llm", li, "resid1"))                  # x + resid_dropout(c_proj(a))
             h2 = ops.layernorm(x_mid, ly["ln2"][0], ly["ln2"][1], self._new(M, H), eps=ly["ln2"][2])
             pre = ops.gemm(h2, ly["fc"].w, self._new(M, I), bias=ly["fc"].b)
             mid = ops.gelu_tanh(pre, self._new(M, I), rows=M, cols=I)
-            x_out = ops.gemm(mid, ly["mproj"].w, self._new(M, H), bias=ly["mproj"].b, residual=x_mid)
+            x_out = self._sub_out(mid, ly["mproj"], x_mid, self.drop("llm", li, "resid2"))              # x + dropout(mlp.c_proj(.))
             ctxs.append((x, xs, qkv, attn, x_mid, pre))
             x = x_out
         fh = ops.layernorm(x, m["norm"][0], m["norm"][1], self._new(M, H), eps=m["norm"][2])
@@ -618,15 +625,15 @@ class TrainEngine(Engine):
         for i in reversed(range(len(ctxs))):
             x_in, xs, qkv, attn, x_mid, pre = ctxs[i]
             ly = m["layers"][i]
-            dmid = self._lin_bwd(dx, None, ly["mproj"], None, None, train=False)
+            dmid = self._lin_bwd(self._drop_grad(dx, self.drop("llm", i, "resid2")), None, ly["mproj"], None, None, train=False)
             dpre = ops.gelu_tanh_bwd(dmid, pre, dmid, rows=M, cols=I)
             dh2 = self._lin_bwd(dpre, None, ly["fc"], None, None, train=False)
             dx_mid = lnb(dh2, x_mid, ly["ln2"], dx)
-            dattn = self._lin_bwd(dx_mid, None, ly["proj"], None, None, train=False)
+            dattn = self._lin_bwd(self._drop_grad(dx_mid, self.drop("llm", i, "resid1")), None, ly["proj"], None, None, train=False)
             dqkv = self._new(M, 3 * H)
             self._attn_bwd(qkv, qkv[:, H:], qkv[:, 2 * H:], dattn, B=B, H=nh, Hkv=nh, Tq=L, Tk=L, dh=dh, qs=sq, ks=sq, vs=sq, dos=(L * H, H),
                            dq=dqkv, dqs=sq, dk_out=dqkv[:, H:], dv_out=dqkv[:, 2 * H:], ld_kv=3 * H, scale=dh ** -0.5, causal=True, key_mask=mask,
-                           o=attn)
+                           o=attn, drop=self.drop("llm", i, "attn"))
             dh1 = ops.gemm(dqkv, ly["wqkvT"][:H], self._new(M, H))
             if kx:
                 du = ops.gemm(dqkv, ly["wqkvT"][H:], self._new(M, kx))               # gradient w.r.t. the LoRA side columns (dropout(h) A^T)
@@ -659,6 +666,8 @@ class TrainEngine(Engine):
                 else:
                     ops.gemm(du, ly["a_catT"], dh1, M=M, N=H, K=kx, residual=dh1)
             dx = lnb(dh1, x_in, ly["ln1"], dx_mid)
+        if self.drop("llm", 0, "embd") is not None:
+            self._drop_res(dx, self.drop("llm", 0, "embd"), None)
         return dx      # gradient w.r.t. the fused input embeddings (wpe is frozen: the position term adds nothing)
 
     def _llm_fwd(self, fused, mask, B, L):
