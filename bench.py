@@ -513,7 +513,7 @@ def measure_train(ctx, workload, steps, warmup, scenes=0, dropout=None):
     pk = peaks()
     roof, _ = _roofline(prof, pk, ms / steps, 1, {"breakdown": "one eager step after the timed region (the timed steps replay a CUDA graph)"})
     probs = model.train_engine()._dropout_probs()
-    p_drop = {"lora": probs.get(("llm", "lora_q"), probs.get(("llm", "lora_c"), 0.0)), "ltsf": probs.get(("ltsf", "ffn"), 0.0), "transformer_layers": probs.get(("qenc", "ffn"), 0.0),
+    p_drop = {"lora": probs.get(("llm", "lora_q"), probs.get(("llm", "lora_c"), 0.0)), "gpt2_embd_attn_resid": probs.get(("llm", "attn")), "ltsf": probs.get(("ltsf", "ffn"), 0.0), "transformer_layers": probs.get(("qenc", "ffn"), 0.0),
               "applied": bool(ft.dropout_active), "masks": "counter-based (seed, step, site, element), regenerated in the backward pass"}
     out = {
         "metric": "LoRA fine-tune tokens/sec (forward + backward + grad all-reduce + AdamW)", "value": round(value, 1), "unit": "tokens/s",
